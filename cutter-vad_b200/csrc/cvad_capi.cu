@@ -1,0 +1,662 @@
+// cvad_capi.cu -- host side of the C ABI declared in include/cutter_vad_b200.h.
+//
+// Owns: the engine object (one GPU, one stream), weight repacking into the kernels'
+// streaming layout, the per-slot state arena in HBM, per-step scratch buffers and the
+// pinned staging used by the host-buffer entry point.  There is no CPU fallback: if no
+// sm_100 device is present every compute entry point fails with CVAD_E_NOGPU.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cutter_vad_b200.h"
+#include "cvad_v5.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct cvad_engine {
+    int device = 0;
+    int version = 0;
+    int max_streams = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+
+    // weights
+    float *w_fe = nullptr, *b_fe = nullptr, *w_rec = nullptr, *b_rec = nullptr, *w_dec = nullptr;
+    // per-slot state
+    float *h_state = nullptr, *c_state = nullptr;
+    int *sm_active = nullptr, *sm_scount = nullptr, *sm_ecount = nullptr;
+    long long *frames_done = nullptr;
+    double *start_p = nullptr, *end_p = nullptr;
+    int *n_start = nullptr, *n_end = nullptr;
+    unsigned char *denoise = nullptr;
+    // scratch (device)
+    DevBuf d_audio, d_slots, d_nframes, d_probs, d_flags, d_status, d_events, d_feat, d_dbg;
+    int *d_nevents = nullptr;
+    // pinned staging (host)
+    DevBuf h_in, h_out;
+};
+
+namespace {
+
+int fail(cvad_engine *e, int code, const std::string &msg) {
+    if (e) e->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU_TRY(e, call)                                                                        \
+    do {                                                                                       \
+        cudaError_t _st = (call);                                                              \
+        if (_st != cudaSuccess)                                                                \
+            return fail((e), CVAD_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_st)); \
+    } while (0)
+
+int grow(cvad_engine *e, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return CVAD_OK;
+    if (b.p) CU_TRY(e, cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t cap = bytes + bytes / 4 + 256;
+    CU_TRY(e, cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return CVAD_OK;
+}
+
+int grow_host(cvad_engine *e, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return CVAD_OK;
+    if (b.p) CU_TRY(e, cudaFreeHost(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t cap = bytes + bytes / 4 + 256;
+    CU_TRY(e, cudaMallocHost(&b.p, cap));
+    b.cap = cap;
+    return CVAD_OK;
+}
+
+bool is_host_pinned_or_device(const void *p, bool want_device) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (want_device) return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    return at.type == cudaMemoryTypeHost;
+}
+
+// ---- v5 weight repack (canonical blob order: see include/ and oracle/silero_ref.c)
+struct V5Packed {
+    std::vector<float> w_fe, b_fe, w_rec, b_rec, w_dec;
+};
+
+V5Packed pack_v5(const float *blob) {
+    const float *basis = blob;                       // [258][256]
+    const float *e0w = basis + 258 * 256;            // [128][129][3]
+    const float *e0b = e0w + 128 * 129 * 3;
+    const float *e1w = e0b + 128;                    // [64][128][3]
+    const float *e1b = e1w + 64 * 128 * 3;
+    const float *e2w = e1b + 64;                     // [64][64][3]
+    const float *e2b = e2w + 64 * 64 * 3;
+    const float *e3w = e2b + 64;                     // [128][64][3]
+    const float *e3b = e3w + 128 * 64 * 3;
+    const float *wih = e3b + 128;                    // [512][128]
+    const float *whh = wih + 512 * 128;
+    const float *bih = whh + 512 * 128;
+    const float *bhh = bih + 512;
+    const float *decw = bhh + 512;                   // [128]
+    const float *decb = decw + 128;
+
+    V5Packed P;
+    P.w_fe.assign(cvad::kFeStreamFloats, 0.f);
+    float *o = P.w_fe.data();
+    for (int k = 0; k < 256; ++k)
+        for (int n = 0; n < 256; ++n) {
+            int row;
+            if (n == 0) row = 0;
+            else if (n == 1) row = 128;
+            else row = (n & 1) ? 129 + (n >> 1) : (n >> 1);
+            o[k * 256 + n] = basis[row * 256 + k];
+        }
+    o += 65536;
+    for (int c = 0; c < 129; ++c)
+        for (int t = 0; t < 3; ++t)
+            for (int oc = 0; oc < 128; ++oc) o[(c * 3 + t) * 128 + oc] = e0w[(oc * 129 + c) * 3 + t];
+    o += 129 * 384;
+    for (int c = 0; c < 128; ++c)
+        for (int t = 0; t < 3; ++t)
+            for (int oc = 0; oc < 64; ++oc) o[(c * 3 + t) * 64 + oc] = e1w[(oc * 128 + c) * 3 + t];
+    o += 128 * 192;
+    for (int c = 0; c < 64; ++c)
+        for (int t = 0; t < 2; ++t)
+            for (int oc = 0; oc < 64; ++oc) o[(c * 2 + t) * 64 + oc] = e2w[(oc * 64 + c) * 3 + (t + 1)];
+    o += 64 * 128;
+    for (int c = 0; c < 64; ++c)
+        for (int oc = 0; oc < 128; ++oc) o[c * 128 + oc] = e3w[(oc * 64 + c) * 3 + 1];
+
+    P.b_fe.resize(cvad::kFeBiasFloats);
+    std::memcpy(P.b_fe.data(), e0b, 128 * 4);
+    std::memcpy(P.b_fe.data() + 128, e1b, 64 * 4);
+    std::memcpy(P.b_fe.data() + 192, e2b, 64 * 4);
+    std::memcpy(P.b_fe.data() + 256, e3b, 128 * 4);
+
+    P.w_rec.resize(cvad::kRecStreamFloats);
+    P.b_rec.resize(512);
+    for (int n = 0; n < 512; ++n) {
+        const int unit = n >> 2, gate = n & 3;
+        const int row = gate * 128 + unit;
+        for (int k = 0; k < 128; ++k) {
+            P.w_rec[k * 512 + n] = wih[row * 128 + k];
+            P.w_rec[(128 + k) * 512 + n] = whh[row * 128 + k];
+        }
+        P.b_rec[n] = bih[row] + bhh[row];
+    }
+    P.w_dec.resize(129);
+    std::memcpy(P.w_dec.data(), decw, 128 * 4);
+    P.w_dec[128] = decb[0];
+    return P;
+}
+
+template <typename T>
+int upload(cvad_engine *e, T **dst, const std::vector<T> &src) {
+    CU_TRY(e, cudaMalloc(reinterpret_cast<void **>(dst), src.size() * sizeof(T)));
+    CU_TRY(e, cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return CVAD_OK;
+}
+
+template <typename T>
+int alloc_fill(cvad_engine *e, T **dst, size_t n, T value) {
+    std::vector<T> tmp(n, value);
+    return upload(e, dst, tmp);
+}
+
+size_t elem_size(int pcm) { return pcm == CVAD_PCM_F32 ? 4 : 2; }
+
+int validate_args(cvad_engine *e, const cvad_step_args *a) {
+    if (!e) return CVAD_E_INVALID;
+    if (!a) return fail(e, CVAD_E_INVALID, "step args are NULL");
+    if (a->n_streams < 0 || a->n_streams > e->max_streams)
+        return fail(e, CVAD_E_CAPACITY, "n_streams outside [0, max_streams]");
+    if (a->n_streams > 0 && !a->audio) return fail(e, CVAD_E_INVALID, "Audio data is empty");
+    if (a->pcm_format < 0 || a->pcm_format > 2) return fail(e, CVAD_E_INVALID, "unknown pcm_format");
+    if (a->max_frames < 0) return fail(e, CVAD_E_INVALID, "max_frames < 0");
+    if (a->frame_len < 1 || a->frame_len > 2048) return fail(e, CVAD_E_INVALID, "frame_len outside [1, 2048]");
+    if (a->hop < 1) return fail(e, CVAD_E_INVALID, "hop < 1");
+    if (a->src_rate != 0 && a->src_rate != 16000)
+        return fail(e, CVAD_E_INVALID, "src_rate: only 16000 is implemented in this build");
+    if (a->max_events < 0) return fail(e, CVAD_E_INVALID, "max_events < 0");
+    return CVAD_OK;
+}
+
+// Enqueue the two kernels.  Every pointer in `a` is a DEVICE pointer here.
+int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status, int commit, float *d_dbg) {
+    if (a->n_streams == 0 || a->max_frames == 0) return CVAD_OK;
+    const int n_stiles = (a->n_streams + cvad::kTile - 1) / cvad::kTile;
+    const size_t feat_bytes = (size_t)a->max_frames * n_stiles * 128 * cvad::kTile * sizeof(float);
+    int rc = grow(e, e->d_feat, feat_bytes);
+    if (rc) return rc;
+
+    cvad::V5Step p{};
+    p.audio = a->audio;
+    p.pcm = a->pcm_format;
+    p.stride = a->stream_stride;
+    p.frame_len = a->frame_len;
+    p.hop = a->hop;
+    const size_t es = elem_size(a->pcm_format);
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(a->audio);
+    p.vec_ok = (addr % (4 * es) == 0) && (a->stream_stride % 4 == 0) && (a->hop % 4 == 0);
+    p.n_streams = a->n_streams;
+    p.n_stiles = n_stiles;
+    p.max_frames = a->max_frames;
+    p.max_streams = e->max_streams;
+    p.slots = a->slots;
+    p.n_frames = a->n_frames;
+    p.denoise = e->denoise;
+    p.status = d_status;
+    p.feat = static_cast<float *>(e->d_feat.p);
+    p.w_fe = e->w_fe; p.b_fe = e->b_fe; p.w_rec = e->w_rec; p.b_rec = e->b_rec; p.w_dec = e->w_dec;
+    p.h_state = e->h_state; p.c_state = e->c_state;
+    p.sm_active = e->sm_active; p.sm_scount = e->sm_scount; p.sm_ecount = e->sm_ecount;
+    p.frames_done = e->frames_done;
+    p.start_p = e->start_p; p.end_p = e->end_p; p.n_start = e->n_start; p.n_end = e->n_end;
+    p.probs = a->probs_out;
+    p.flags = a->flags_out;
+    p.events = a->events_out;
+    p.max_events = a->max_events;
+    p.n_events = a->n_events_out;
+    p.commit = commit;
+    p.dbg = d_dbg;
+
+    const int n_tiles = a->max_frames * n_stiles;
+    const int grid_fe = std::min(n_tiles, e->num_sms);
+    cvad::v5_frontend_kernel<<<grid_fe, cvad::kThreads, cvad::kFeSmemBytes, e->stream>>>(p);
+    CU_TRY(e, cudaGetLastError());
+    e->launches++;
+    if (!d_dbg) {
+        cvad::v5_recurrent_kernel<<<n_stiles, cvad::kThreads, cvad::kRecSmemBytes, e->stream>>>(p);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+    }
+    return CVAD_OK;
+}
+
+}  // namespace
+
+namespace {
+template <typename T>
+__global__ void fill_slots_kernel(T *dst, const int *slots, int n, int all_n, T value, int ld, int rows) {
+    // dst is [rows][ld]; set column slot (or every column when slots == nullptr) to value
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int count = slots ? n : all_n;
+    if (idx >= count * rows) return;
+    const int r = idx / count, k = idx - r * count;
+    const int slot = slots ? slots[k] : k;
+    dst[(size_t)r * ld + slot] = value;
+}
+
+template <typename T>
+int fill_slots(cvad_engine *e, T *dst, const int *d_slots, int n, T value, int rows) {
+    const int count = d_slots ? n : e->max_streams;
+    if (count == 0) return CVAD_OK;
+    const int total = count * rows;
+    fill_slots_kernel<T><<<(total + 255) / 256, 256, 0, e->stream>>>(dst, d_slots, n, e->max_streams, value,
+                                                                    e->max_streams, rows);
+    CU_TRY(e, cudaGetLastError());
+    return CVAD_OK;
+}
+
+int stage_slots(cvad_engine *e, int n, const int32_t *slots, const int **d_slots) {
+    *d_slots = nullptr;
+    if (!slots) return CVAD_OK;
+    for (int i = 0; i < n; ++i)
+        if (slots[i] < 0 || slots[i] >= e->max_streams) return fail(e, CVAD_E_CAPACITY, "slot id out of range");
+    int rc = grow(e, e->d_slots, (size_t)std::max(n, 1) * sizeof(int));
+    if (rc) return rc;
+    CU_TRY(e, cudaMemcpyAsync(e->d_slots.p, slots, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));  // `slots` is pageable caller memory
+    *d_slots = static_cast<const int *>(e->d_slots.p);
+    return CVAD_OK;
+}
+}  // namespace
+
+namespace {
+// Host-buffer step; `dbg_out` != nullptr turns it into the debug dump (front end only, no commit).
+int step_host(cvad_engine *e, const cvad_step_args *a, float *dbg_out, size_t dbg_floats) {
+    int rc = validate_args(e, a);
+    if (rc) return rc;
+    CU_TRY(e, cudaSetDevice(e->device));
+    const int n = a->n_streams, T = a->max_frames;
+    if (a->n_events_out) *a->n_events_out = 0;
+    if (n == 0 || T == 0) return CVAD_OK;
+    if (a->slots) {
+        for (int i = 0; i < n; ++i)
+            if (a->slots[i] < 0 || a->slots[i] >= e->max_streams)
+                return fail(e, CVAD_E_CAPACITY, "slot id out of range");
+    }
+    if (a->n_frames) {
+        for (int i = 0; i < n; ++i)
+            if (a->n_frames[i] < 0 || a->n_frames[i] > T)
+                return fail(e, CVAD_E_INVALID, "n_frames[i] outside [0, max_frames]");
+    }
+    const size_t es = elem_size(a->pcm_format);
+    const size_t row = (size_t)(T - 1) * a->hop + a->frame_len;
+    if (n > 1 && (a->stream_stride < 0 || (size_t)a->stream_stride < row))
+        return fail(e, CVAD_E_INVALID, "stream_stride shorter than (max_frames-1)*hop + frame_len");
+    const size_t audio_elems = (size_t)(n - 1) * a->stream_stride + row;
+    const size_t audio_bytes = audio_elems * es;
+
+    // ---- device scratch
+    if ((rc = grow(e, e->d_audio, audio_bytes + 16)) || (rc = grow(e, e->d_slots, (size_t)n * 4)) ||
+        (rc = grow(e, e->d_nframes, (size_t)n * 4)) || (rc = grow(e, e->d_probs, (size_t)n * T * 4)) ||
+        (rc = grow(e, e->d_flags, (size_t)n * T)) || (rc = grow(e, e->d_status, (size_t)n * 4)) ||
+        (rc = grow(e, e->d_events, (size_t)std::max(a->max_events, 1) * sizeof(cvad_event))))
+        return rc;
+
+    // ---- host -> device (pinned memory goes straight; pageable memory is staged)
+    const size_t small_in = (size_t)n * 8;
+    if ((rc = grow_host(e, e->h_in, audio_bytes + small_in + 64))) return rc;
+    unsigned char *hin = static_cast<unsigned char *>(e->h_in.p);
+    int *h_slots = reinterpret_cast<int *>(hin);
+    int *h_nfr = h_slots + n;
+    if (a->slots) std::memcpy(h_slots, a->slots, (size_t)n * 4);
+    if (a->n_frames) std::memcpy(h_nfr, a->n_frames, (size_t)n * 4);
+    const void *src_audio = a->audio;
+    if (!is_host_pinned_or_device(a->audio, false)) {
+        unsigned char *stage = hin + ((small_in + 63) / 64) * 64;
+        std::memcpy(stage, a->audio, audio_bytes);
+        src_audio = stage;
+    }
+    CU_TRY(e, cudaMemcpyAsync(e->d_audio.p, src_audio, audio_bytes, cudaMemcpyHostToDevice, e->stream));
+    if (a->slots) CU_TRY(e, cudaMemcpyAsync(e->d_slots.p, h_slots, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    if (a->n_frames) CU_TRY(e, cudaMemcpyAsync(e->d_nframes.p, h_nfr, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(e, cudaMemsetAsync(e->d_status.p, 0, (size_t)n * 4, e->stream));
+    CU_TRY(e, cudaMemsetAsync(e->d_nevents, 0, sizeof(int), e->stream));
+
+    cvad_step_args d = *a;
+    d.audio = e->d_audio.p;
+    d.slots = a->slots ? static_cast<const int32_t *>(e->d_slots.p) : nullptr;
+    d.n_frames = a->n_frames ? static_cast<const int32_t *>(e->d_nframes.p) : nullptr;
+    d.probs_out = static_cast<float *>(e->d_probs.p);
+    d.flags_out = static_cast<uint8_t *>(e->d_flags.p);
+    d.status_out = nullptr;
+    d.events_out = static_cast<cvad_event *>(e->d_events.p);
+    d.n_events_out = e->d_nevents;
+
+    float *d_dbg = nullptr;
+    if (dbg_out) {
+        if (dbg_floats < (size_t)cvad::kDbgFloats) return fail(e, CVAD_E_CAPACITY, "dbg_out too small");
+        if ((rc = grow(e, e->d_dbg, (size_t)cvad::kDbgFloats * 4))) return rc;
+        d_dbg = static_cast<float *>(e->d_dbg.p);
+        CU_TRY(e, cudaMemsetAsync(d_dbg, 0, (size_t)cvad::kDbgFloats * 4, e->stream));
+    }
+    rc = launch_step(e, &d, static_cast<unsigned int *>(e->d_status.p), dbg_out ? 0 : 1, d_dbg);
+    if (rc) return rc;
+
+    if (dbg_out) {
+        CU_TRY(e, cudaMemcpyAsync(dbg_out, d_dbg, (size_t)cvad::kDbgFloats * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(e, cudaStreamSynchronize(e->stream));
+        return cvad::kDbgFloats;
+    }
+
+    // ---- device -> host
+    const size_t probs_b = (size_t)n * T * 4, flags_b = (size_t)n * T, status_b = (size_t)n * 4;
+    const size_t ev_b = (size_t)a->max_events * sizeof(cvad_event);
+    const size_t out_total = probs_b + flags_b + status_b + 64 + ev_b + 256;
+    if ((rc = grow_host(e, e->h_out, out_total))) return rc;
+    unsigned char *ho = static_cast<unsigned char *>(e->h_out.p);
+    float *h_probs = reinterpret_cast<float *>(ho);
+    unsigned int *h_status = reinterpret_cast<unsigned int *>(ho + probs_b);
+    int *h_nev = reinterpret_cast<int *>(ho + probs_b + status_b);
+    cvad_event *h_ev = reinterpret_cast<cvad_event *>(ho + probs_b + status_b + 64);
+    unsigned char *h_flags = ho + probs_b + status_b + 64 + ((ev_b + 63) / 64) * 64;
+    // flags of frames never run (ragged n_frames) must read as 0
+    if (a->probs_out) CU_TRY(e, cudaMemcpyAsync(h_probs, e->d_probs.p, probs_b, cudaMemcpyDeviceToHost, e->stream));
+    if (a->flags_out) CU_TRY(e, cudaMemcpyAsync(h_flags, e->d_flags.p, flags_b, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaMemcpyAsync(h_status, e->d_status.p, status_b, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaMemcpyAsync(h_nev, e->d_nevents, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    int nev = *h_nev;
+    if (a->n_events_out) *a->n_events_out = nev;
+    if (a->events_out && a->max_events > 0 && nev > 0) {
+        const int take = std::min(nev, a->max_events);
+        CU_TRY(e, cudaMemcpy(h_ev, e->d_events.p, (size_t)take * sizeof(cvad_event), cudaMemcpyDeviceToHost));
+        std::sort(h_ev, h_ev + take, [](const cvad_event &x, const cvad_event &y) {
+            if (x.stream != y.stream) return x.stream < y.stream;
+            if (x.frame != y.frame) return x.frame < y.frame;
+            return x.kind < y.kind;
+        });
+        std::memcpy(a->events_out, h_ev, (size_t)take * sizeof(cvad_event));
+    }
+    if (a->probs_out || a->flags_out) {
+        for (int i = 0; i < n; ++i) {
+            const int nf = (h_status[i] != 0u) ? 0 : (a->n_frames ? a->n_frames[i] : T);
+            if (a->probs_out) {
+                std::memcpy(a->probs_out + (size_t)i * T, h_probs + (size_t)i * T, (size_t)nf * 4);
+                for (int j = nf; j < T; ++j) a->probs_out[(size_t)i * T + j] = 0.f;
+            }
+            if (a->flags_out) {
+                std::memcpy(a->flags_out + (size_t)i * T, h_flags + (size_t)i * T, (size_t)nf);
+                for (int j = nf; j < T; ++j) a->flags_out[(size_t)i * T + j] = 0;
+            }
+        }
+    }
+    if (a->status_out)
+        for (int i = 0; i < n; ++i) a->status_out[i] = (uint8_t)(h_status[i] & 0xffu);
+    return CVAD_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int cvad_abi_version(void) { return CVAD_ABI_VERSION; }
+
+int cvad_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp pr{};
+        if (cudaGetDeviceProperties(&pr, d) == cudaSuccess && pr.major == 10) ++ok;
+    }
+    return ok;
+}
+
+const char *cvad_last_error(const cvad_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int cvad_create(const float *weights, size_t n_weight_floats, int model_version, int max_streams, int device,
+                cvad_engine **out) {
+    if (!out) return fail(nullptr, CVAD_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!weights) return fail(nullptr, CVAD_E_INVALID, "weights is NULL");
+    if (max_streams < 1) return fail(nullptr, CVAD_E_INVALID, "max_streams < 1");
+    if (model_version != CVAD_MODEL_V5)
+        return fail(nullptr, CVAD_E_INVALID, "model_version: only CVAD_MODEL_V5 is implemented in this build");
+    if (n_weight_floats != CVAD_V5_WEIGHT_FLOATS)
+        return fail(nullptr, CVAD_E_WEIGHTS, "v5 weight blob must hold 309633 floats");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, CVAD_E_NOGPU, "no CUDA device visible (this engine has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, CVAD_E_INVALID, "device index out of range");
+    cudaDeviceProp pr{};
+    if (cudaGetDeviceProperties(&pr, device) != cudaSuccess || pr.major != 10)
+        return fail(nullptr, CVAD_E_NOGPU, "device is not sm_100 (kernels are built for sm_100a only)");
+
+    cvad_engine *e = new cvad_engine();
+    e->device = device;
+    e->version = model_version;
+    e->max_streams = max_streams;
+    e->num_sms = pr.multiProcessorCount;
+    auto bail = [&](int rc) {
+        g_create_error = e->err;
+        cvad_destroy(e);
+        return rc;
+    };
+#define CR_TRY(call)                                                              \
+    do {                                                                          \
+        cudaError_t _st = (call);                                                 \
+        if (_st != cudaSuccess) {                                                 \
+            e->err = std::string(#call) + ": " + cudaGetErrorString(_st);         \
+            return bail(CVAD_E_CUDA);                                             \
+        }                                                                         \
+    } while (0)
+    CR_TRY(cudaSetDevice(device));
+    CR_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+    CR_TRY(cudaFuncSetAttribute(cvad::v5_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::kFeSmemBytes));
+    CR_TRY(cudaFuncSetAttribute(cvad::v5_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::kRecSmemBytes));
+    {
+        V5Packed P = pack_v5(weights);
+        int rc;
+        if ((rc = upload(e, &e->w_fe, P.w_fe)) || (rc = upload(e, &e->b_fe, P.b_fe)) ||
+            (rc = upload(e, &e->w_rec, P.w_rec)) || (rc = upload(e, &e->b_rec, P.b_rec)) ||
+            (rc = upload(e, &e->w_dec, P.w_dec)))
+            return bail(rc);
+    }
+    {
+        const size_t ms = (size_t)max_streams;
+        int rc;
+        if ((rc = alloc_fill<float>(e, &e->h_state, 128 * ms, 0.f)) ||
+            (rc = alloc_fill<float>(e, &e->c_state, 128 * ms, 0.f)) ||
+            (rc = alloc_fill<int>(e, &e->sm_active, ms, 0)) || (rc = alloc_fill<int>(e, &e->sm_scount, ms, 0)) ||
+            (rc = alloc_fill<int>(e, &e->sm_ecount, ms, 0)) ||
+            (rc = alloc_fill<long long>(e, &e->frames_done, ms, 0)) ||
+            (rc = alloc_fill<double>(e, &e->start_p, ms, 0.7)) || (rc = alloc_fill<double>(e, &e->end_p, ms, 0.7)) ||
+            (rc = alloc_fill<int>(e, &e->n_start, ms, 10)) || (rc = alloc_fill<int>(e, &e->n_end, ms, 50)) ||
+            (rc = alloc_fill<unsigned char>(e, &e->denoise, ms, 1)))
+            return bail(rc);
+    }
+    CR_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_nevents), sizeof(int)));
+#undef CR_TRY
+    *out = e;
+    return CVAD_OK;
+}
+
+int cvad_destroy(cvad_engine *e) {
+    if (!e) return CVAD_OK;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    void *ptrs[] = {e->w_fe, e->b_fe, e->w_rec, e->b_rec, e->w_dec, e->h_state, e->c_state, e->sm_active,
+                    e->sm_scount, e->sm_ecount, e->frames_done, e->start_p, e->end_p, e->n_start, e->n_end,
+                    e->denoise, e->d_nevents, e->d_audio.p, e->d_slots.p, e->d_nframes.p, e->d_probs.p,
+                    e->d_flags.p, e->d_status.p, e->d_events.p, e->d_feat.p, e->d_dbg.p};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (e->h_in.p) cudaFreeHost(e->h_in.p);
+    if (e->h_out.p) cudaFreeHost(e->h_out.p);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return CVAD_OK;
+}
+
+int cvad_set_stream(cvad_engine *e, void *cuda_stream) {
+    if (!e) return CVAD_E_INVALID;
+    CU_TRY(e, cudaSetDevice(e->device));
+    if (e->stream) CU_TRY(e, cudaStreamSynchronize(e->stream));
+    if (cuda_stream == nullptr) {
+        if (!e->own_stream) {
+            CU_TRY(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+            e->own_stream = true;
+        }
+        return CVAD_OK;
+    }
+    if (e->own_stream && e->stream) CU_TRY(e, cudaStreamDestroy(e->stream));
+    e->own_stream = false;
+    e->stream = static_cast<cudaStream_t>(cuda_stream);
+    return CVAD_OK;
+}
+
+int cvad_reset(cvad_engine *e, int n, const int32_t *slots) {
+    if (!e) return CVAD_E_INVALID;
+    if (slots && n < 0) return fail(e, CVAD_E_INVALID, "n < 0");
+    CU_TRY(e, cudaSetDevice(e->device));
+    const int *ds = nullptr;
+    int rc = stage_slots(e, n, slots, &ds);
+    if (rc) return rc;
+    if ((rc = fill_slots<float>(e, e->h_state, ds, n, 0.f, 128)) ||
+        (rc = fill_slots<float>(e, e->c_state, ds, n, 0.f, 128)) ||
+        (rc = fill_slots<int>(e, e->sm_active, ds, n, 0, 1)) || (rc = fill_slots<int>(e, e->sm_scount, ds, n, 0, 1)) ||
+        (rc = fill_slots<int>(e, e->sm_ecount, ds, n, 0, 1)) ||
+        (rc = fill_slots<long long>(e, e->frames_done, ds, n, 0ll, 1)))
+        return rc;
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    return CVAD_OK;
+}
+
+int cvad_configure(cvad_engine *e, int n, const int32_t *slots, double vad_start_probability,
+                   double vad_end_probability, int voice_start_frame_count, int voice_end_frame_count,
+                   int enable_denoising) {
+    if (!e) return CVAD_E_INVALID;
+    if (slots && n < 0) return fail(e, CVAD_E_INVALID, "n < 0");
+    if (voice_start_frame_count < 1 || voice_end_frame_count < 1)
+        return fail(e, CVAD_E_INVALID, "frame counts must be >= 1");
+    if (!(vad_start_probability >= 0.0 && vad_start_probability <= 1.0) ||
+        !(vad_end_probability >= 0.0 && vad_end_probability <= 1.0))
+        return fail(e, CVAD_E_INVALID, "probabilities must be within [0, 1]");
+    CU_TRY(e, cudaSetDevice(e->device));
+    const int *ds = nullptr;
+    int rc = stage_slots(e, n, slots, &ds);
+    if (rc) return rc;
+    if ((rc = fill_slots<double>(e, e->start_p, ds, n, vad_start_probability, 1)) ||
+        (rc = fill_slots<double>(e, e->end_p, ds, n, vad_end_probability, 1)) ||
+        (rc = fill_slots<int>(e, e->n_start, ds, n, voice_start_frame_count, 1)) ||
+        (rc = fill_slots<int>(e, e->n_end, ds, n, voice_end_frame_count, 1)) ||
+        (rc = fill_slots<unsigned char>(e, e->denoise, ds, n, (unsigned char)(enable_denoising ? 1 : 0), 1)))
+        return rc;
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    return CVAD_OK;
+}
+
+int cvad_get_state(cvad_engine *e, int slot, float *h, float *c, int32_t *sm, int64_t *frames_done) {
+    if (!e) return CVAD_E_INVALID;
+    if (slot < 0 || slot >= e->max_streams) return fail(e, CVAD_E_CAPACITY, "slot id out of range");
+    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    const size_t pitch = (size_t)e->max_streams * sizeof(float);
+    if (h) CU_TRY(e, cudaMemcpy2D(h, sizeof(float), e->h_state + slot, pitch, sizeof(float), 128, cudaMemcpyDeviceToHost));
+    if (c) CU_TRY(e, cudaMemcpy2D(c, sizeof(float), e->c_state + slot, pitch, sizeof(float), 128, cudaMemcpyDeviceToHost));
+    if (sm) {
+        CU_TRY(e, cudaMemcpy(&sm[0], e->sm_active + slot, sizeof(int), cudaMemcpyDeviceToHost));
+        CU_TRY(e, cudaMemcpy(&sm[1], e->sm_scount + slot, sizeof(int), cudaMemcpyDeviceToHost));
+        CU_TRY(e, cudaMemcpy(&sm[2], e->sm_ecount + slot, sizeof(int), cudaMemcpyDeviceToHost));
+        sm[3] = 0;
+    }
+    if (frames_done) {
+        long long v = 0;
+        CU_TRY(e, cudaMemcpy(&v, e->frames_done + slot, sizeof(long long), cudaMemcpyDeviceToHost));
+        *frames_done = v;
+    }
+    return CVAD_OK;
+}
+
+int cvad_set_state(cvad_engine *e, int slot, const float *h, const float *c, const int32_t *sm) {
+    if (!e) return CVAD_E_INVALID;
+    if (slot < 0 || slot >= e->max_streams) return fail(e, CVAD_E_CAPACITY, "slot id out of range");
+    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    const size_t pitch = (size_t)e->max_streams * sizeof(float);
+    if (h) CU_TRY(e, cudaMemcpy2D(e->h_state + slot, pitch, h, sizeof(float), sizeof(float), 128, cudaMemcpyHostToDevice));
+    if (c) CU_TRY(e, cudaMemcpy2D(e->c_state + slot, pitch, c, sizeof(float), sizeof(float), 128, cudaMemcpyHostToDevice));
+    if (sm) {
+        CU_TRY(e, cudaMemcpy(e->sm_active + slot, &sm[0], sizeof(int), cudaMemcpyHostToDevice));
+        CU_TRY(e, cudaMemcpy(e->sm_scount + slot, &sm[1], sizeof(int), cudaMemcpyHostToDevice));
+        CU_TRY(e, cudaMemcpy(e->sm_ecount + slot, &sm[2], sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return CVAD_OK;
+}
+
+int cvad_sync(cvad_engine *e) {
+    if (!e) return CVAD_E_INVALID;
+    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    return CVAD_OK;
+}
+
+int64_t cvad_launch_count(const cvad_engine *e) { return e ? e->launches : 0; }
+
+void *cvad_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void cvad_free_pinned(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int cvad_step_device(cvad_engine *e, const cvad_step_args *a) {
+    int rc = validate_args(e, a);
+    if (rc) return rc;
+    CU_TRY(e, cudaSetDevice(e->device));
+    if (a->n_streams == 0 || a->max_frames == 0) return CVAD_OK;
+    unsigned int *d_status = nullptr;
+    if (a->status_out) {
+        // status is one byte per stream at the ABI; the kernels use a 32-bit word per stream
+        return fail(e, CVAD_E_INVALID, "cvad_step_device: status_out must be NULL (use cvad_step for status)");
+    }
+    rc = grow(e, e->d_status, (size_t)a->n_streams * sizeof(unsigned int));
+    if (rc) return rc;
+    d_status = static_cast<unsigned int *>(e->d_status.p);
+    CU_TRY(e, cudaMemsetAsync(d_status, 0, (size_t)a->n_streams * sizeof(unsigned int), e->stream));
+    if (a->n_events_out) CU_TRY(e, cudaMemsetAsync(a->n_events_out, 0, sizeof(int), e->stream));
+    return launch_step(e, a, d_status, 1, nullptr);
+}
+
+int cvad_step(cvad_engine *e, const cvad_step_args *a) { return step_host(e, a, nullptr, 0); }
+
+int cvad_debug_dump(cvad_engine *e, const cvad_step_args *a, float *dbg_out, size_t dbg_floats) {
+    if (!dbg_out) return fail(e, CVAD_E_INVALID, "dbg_out is NULL");
+    return step_host(e, a, dbg_out, dbg_floats);
+}
+
+}  // extern "C"

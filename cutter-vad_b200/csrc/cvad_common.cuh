@@ -1,0 +1,86 @@
+// cvad_common.cuh -- shared device helpers: mbarrier + bulk-copy (TMA 1-D) weight ring.
+//
+// The weights of every layer are pre-packed on the host into the exact order the
+// kernels consume them ("weight stream"): a sequence of <=16 KB chunks.  One thread
+// per CTA pushes chunks into a shared-memory ring with cp.async.bulk (SASS: UBLKCP)
+// completing on an mbarrier; all threads wait on the barrier, consume the chunk with
+// LDS.128, and a __syncthreads() hands the slot back to the producer.  The stream is
+// periodic (one period per tile / per frame), so prefetch runs across layer and tile
+// boundaries and the ring is drained before the CTA exits.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cvad {
+
+constexpr int kTile = 32;            // streams (items) per CTA tile
+constexpr int kThreads = 256;        // threads per CTA
+constexpr int kRingStages = 4;       // weight ring depth
+constexpr int kRingSlotFloats = 4096;// 16 KB per ring slot
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// 1-D bulk async copy global -> shared, completion counted in bytes on `bar`.
+// bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+
+// acc[i][j] += a[i] * w[j] for an 8x4 register tile
+__device__ __forceinline__ void fma8x4(float (&acc)[8][4], const float4 &a0, const float4 &a1, const float4 &w) {
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float b[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Periodic weight stream -> shared-memory ring.
+struct WeightRing {
+    float *buf;          // kRingStages * kRingSlotFloats
+    uint64_t *bars;      // kRingStages "full" barriers
+    const float *gsrc;   // packed weight stream in HBM/L2
+    uint32_t g;          // chunks consumed so far by this CTA (uniform across threads)
+};
+
+}  // namespace cvad

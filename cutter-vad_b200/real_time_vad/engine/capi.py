@@ -1,0 +1,96 @@
+"""ctypes binding of the C ABI in include/cutter_vad_b200.h (libcvad_b200.so).
+
+The library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a).  There
+is NO fallback: a missing library raises at import of this module's `lib()`, and
+`cvad_create` fails with CVAD_E_NOGPU when no sm_100 device is visible.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+PKG_ROOT = Path(__file__).resolve().parents[2]          # .../cutter-vad_b200
+LIB_PATH = PKG_ROOT / "libcvad_b200.so"
+
+OK, E_INVALID, E_CUDA, E_NOGPU, E_WEIGHTS, E_CAPACITY = 0, -1, -2, -3, -4, -5
+MODEL_V5, MODEL_V4 = 5, 4
+PCM_F32, PCM_S16_32767, PCM_S16_32768 = 0, 1, 2
+FLAG_STARTED, FLAG_ENDED, FLAG_CONTINUING = 1, 2, 4
+STATUS_NONFINITE = 1
+
+EXPORTS = (
+    "cvad_abi_version", "cvad_device_count", "cvad_last_error", "cvad_create", "cvad_destroy",
+    "cvad_set_stream", "cvad_reset", "cvad_configure", "cvad_get_state", "cvad_set_state",
+    "cvad_step", "cvad_step_device", "cvad_sync", "cvad_launch_count", "cvad_debug_dump",
+    "cvad_alloc_pinned", "cvad_free_pinned",
+)
+
+
+class Event(C.Structure):
+    _fields_ = [("stream", C.c_int32), ("slot", C.c_int32), ("frame", C.c_int32), ("kind", C.c_int32),
+                ("stream_frame", C.c_int64)]
+
+
+class StepArgs(C.Structure):
+    _fields_ = [
+        ("n_streams", C.c_int32),
+        ("slots", C.c_void_p),
+        ("audio", C.c_void_p),
+        ("pcm_format", C.c_int32),
+        ("stream_stride", C.c_int64),
+        ("n_frames", C.c_void_p),
+        ("max_frames", C.c_int32),
+        ("frame_len", C.c_int32),
+        ("hop", C.c_int32),
+        ("src_rate", C.c_int32),
+        ("probs_out", C.c_void_p),
+        ("flags_out", C.c_void_p),
+        ("status_out", C.c_void_p),
+        ("events_out", C.c_void_p),
+        ("max_events", C.c_int32),
+        ("n_events_out", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+class EngineLibraryMissing(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load libcvad_b200.so (once).  Raises EngineLibraryMissing if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("CVAD_B200_LIB", LIB_PATH))
+    if not path.exists():
+        raise EngineLibraryMissing(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). This engine has no CPU or PyTorch fallback.")
+    L = C.CDLL(str(path))
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    L.cvad_abi_version.restype = i32
+    L.cvad_device_count.restype = i32
+    L.cvad_last_error.restype = C.c_char_p
+    L.cvad_last_error.argtypes = [vp]
+    L.cvad_create.argtypes = [vp, C.c_size_t, i32, i32, i32, C.POINTER(vp)]
+    L.cvad_destroy.argtypes = [vp]
+    L.cvad_set_stream.argtypes = [vp, vp]
+    L.cvad_reset.argtypes = [vp, i32, vp]
+    L.cvad_configure.argtypes = [vp, i32, vp, dbl, dbl, i32, i32, i32]
+    L.cvad_get_state.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.cvad_set_state.argtypes = [vp, i32, vp, vp, vp]
+    L.cvad_step.argtypes = [vp, C.POINTER(StepArgs)]
+    L.cvad_step_device.argtypes = [vp, C.POINTER(StepArgs)]
+    L.cvad_sync.argtypes = [vp]
+    L.cvad_launch_count.restype = i64
+    L.cvad_launch_count.argtypes = [vp]
+    L.cvad_debug_dump.argtypes = [vp, C.POINTER(StepArgs), vp, C.c_size_t]
+    L.cvad_alloc_pinned.restype = vp
+    L.cvad_alloc_pinned.argtypes = [C.c_size_t]
+    L.cvad_free_pinned.argtypes = [vp]
+    _lib = L
+    return L

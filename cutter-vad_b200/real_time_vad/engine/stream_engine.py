@@ -1,0 +1,199 @@
+"""StreamEngine: numpy-facing handle on one GPU's VAD engine (thin layer over the C ABI).
+
+One engine owns `max_streams` slots.  Each slot carries the per-stream state the
+reference keeps on a `VADProcessor` / `SileroVADModel` pair
+(/root/reference/src/real_time_vad/core/silero_model.py:264-267 LSTM state,
+:596-628 state-machine fields), resident in HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import capi
+from .onnx_weights import canonical_blob_v5
+
+MODELS_DIR = Path(__file__).resolve().parents[1] / "models"
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[cvad {code}] {message}")
+        self.code = code
+        self.message = message
+
+
+@dataclass
+class StepResult:
+    probs: np.ndarray            # [n_streams, max_frames] float32
+    flags: np.ndarray            # [n_streams, max_frames] uint8 (FLAG_* bits)
+    status: np.ndarray           # [n_streams] uint8 (STATUS_* bits)
+    events: List[Tuple[int, int, int, int, int]]  # (stream, slot, frame, kind, stream_frame), stream-then-frame order
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class StreamEngine:
+    def __init__(self, model_version: str = "v5", max_streams: int = 1, device: int = 0,
+                 model_path: Optional[Path] = None):
+        self._L = capi.lib()
+        self._h = C.c_void_p()
+        if model_version != "v5":
+            raise EngineError(capi.E_INVALID, f"model version {model_version!r} not available in this build")
+        path = Path(model_path) if model_path else MODELS_DIR / "silero_vad_v5.onnx"
+        self.weights = canonical_blob_v5(path)
+        rc = self._L.cvad_create(_ptr(self.weights), self.weights.size, capi.MODEL_V5, int(max_streams),
+                                 int(device), C.byref(self._h))
+        if rc != capi.OK:
+            raise EngineError(rc, (self._L.cvad_last_error(None) or b"").decode())
+        self.max_streams = int(max_streams)
+        self.device = int(device)
+        self.model_version = model_version
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int) -> None:
+        if rc < 0:
+            raise EngineError(rc, (self._L.cvad_last_error(self._h) or b"").decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.cvad_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self._check(self._L.cvad_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def sync(self) -> None:
+        self._check(self._L.cvad_sync(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._L.cvad_launch_count(self._h))
+
+    # ------------------------------------------------------------------ per-slot control
+    @staticmethod
+    def _slots(slots: Optional[Sequence[int]]):
+        if slots is None:
+            return 0, None
+        arr = np.ascontiguousarray(slots, dtype=np.int32)
+        return int(arr.size), arr
+
+    def reset(self, slots: Optional[Sequence[int]] = None) -> None:
+        n, arr = self._slots(slots)
+        self._check(self._L.cvad_reset(self._h, n, _ptr(arr)))
+
+    def configure(self, slots: Optional[Sequence[int]] = None, *, vad_start_probability: float = 0.7,
+                  vad_end_probability: float = 0.7, voice_start_frame_count: int = 10,
+                  voice_end_frame_count: int = 50, enable_denoising: bool = True) -> None:
+        n, arr = self._slots(slots)
+        self._check(self._L.cvad_configure(self._h, n, _ptr(arr), float(vad_start_probability),
+                                           float(vad_end_probability), int(voice_start_frame_count),
+                                           int(voice_end_frame_count), int(bool(enable_denoising))))
+
+    def get_state(self, slot: int):
+        h = np.zeros(128, np.float32)
+        c = np.zeros(128, np.float32)
+        sm = np.zeros(4, np.int32)
+        fd = C.c_int64(0)
+        self._check(self._L.cvad_get_state(self._h, int(slot), _ptr(h), _ptr(c), _ptr(sm), C.byref(fd)))
+        return h, c, sm, int(fd.value)
+
+    def set_state(self, slot: int, h: Optional[np.ndarray] = None, c: Optional[np.ndarray] = None,
+                  sm: Optional[np.ndarray] = None) -> None:
+        h = None if h is None else np.ascontiguousarray(h, np.float32)
+        c = None if c is None else np.ascontiguousarray(c, np.float32)
+        sm = None if sm is None else np.ascontiguousarray(sm, np.int32)
+        self._check(self._L.cvad_set_state(self._h, int(slot), _ptr(h), _ptr(c), _ptr(sm)))
+
+    # ------------------------------------------------------------------ the hot call
+    def _args(self, audio: np.ndarray, slots, n_frames, max_frames, frame_len, hop, pcm_format):
+        if audio.ndim != 2:
+            raise EngineError(capi.E_INVALID, "audio must be [n_streams, samples]")
+        if pcm_format == capi.PCM_F32:
+            audio = np.ascontiguousarray(audio, dtype=np.float32)
+        else:
+            audio = np.ascontiguousarray(audio, dtype=np.int16)
+        n = audio.shape[0]
+        keep = [audio]
+        a = capi.StepArgs()
+        a.n_streams = n
+        if slots is not None:
+            s = np.ascontiguousarray(slots, dtype=np.int32)
+            if s.size != n:
+                raise EngineError(capi.E_INVALID, "len(slots) != n_streams")
+            keep.append(s)
+            a.slots = s.ctypes.data
+        if n_frames is not None:
+            nf = np.ascontiguousarray(n_frames, dtype=np.int32)
+            if nf.size != n:
+                raise EngineError(capi.E_INVALID, "len(n_frames) != n_streams")
+            keep.append(nf)
+            a.n_frames = nf.ctypes.data
+        a.audio = audio.ctypes.data
+        a.pcm_format = pcm_format
+        a.stream_stride = audio.shape[1]
+        a.max_frames = int(max_frames)
+        a.frame_len = int(frame_len)
+        a.hop = int(hop)
+        a.src_rate = 16000
+        return a, keep
+
+    def step(self, audio: np.ndarray, *, slots: Optional[Sequence[int]] = None,
+             n_frames: Optional[Sequence[int]] = None, max_frames: Optional[int] = None,
+             frame_len: int = 512, hop: int = 512, pcm_format: int = capi.PCM_F32,
+             max_events: int = 0) -> StepResult:
+        """Advance every listed stream by its n_frames frames (host buffers in and out)."""
+        audio = np.asarray(audio)
+        if max_frames is None:
+            max_frames = 0 if audio.shape[1] < frame_len else (audio.shape[1] - frame_len) // hop + 1
+        a, keep = self._args(audio, slots, n_frames, max_frames, frame_len, hop, pcm_format)
+        n = a.n_streams
+        probs = np.zeros((n, max_frames), np.float32)
+        flags = np.zeros((n, max_frames), np.uint8)
+        status = np.zeros(n, np.uint8)
+        if max_events <= 0:
+            max_events = max(16, 2 * n * max(max_frames, 1))
+        ev = (capi.Event * max_events)()
+        nev = C.c_int32(0)
+        a.probs_out = probs.ctypes.data
+        a.flags_out = flags.ctypes.data
+        a.status_out = status.ctypes.data
+        a.events_out = C.addressof(ev)
+        a.max_events = max_events
+        a.n_events_out = C.addressof(nev)
+        self._check(self._L.cvad_step(self._h, C.byref(a)))
+        k = min(int(nev.value), max_events)
+        events = [(ev[i].stream, ev[i].slot, ev[i].frame, ev[i].kind, ev[i].stream_frame) for i in range(k)]
+        return StepResult(probs, flags, status, events)
+
+    def debug_dump(self, audio: np.ndarray, *, frame_len: int = 512, hop: int = 512,
+                   pcm_format: int = capi.PCM_F32):
+        """Front-end intermediates of the first tile, frame 0 (test hook; engine state untouched)."""
+        a, keep = self._args(np.asarray(audio), None, None, 1, frame_len, hop, pcm_format)
+        n_dbg = 129 * 96 + 128 * 96 + 64 * 64 + 64 * 32 + 128 * 32
+        out = np.zeros(n_dbg, np.float32)
+        rc = self._L.cvad_debug_dump(self._h, C.byref(a), _ptr(out), out.size)
+        self._check(rc)
+        o = 0
+        res = {}
+        for name, shape in (("mag", (129, 3, 32)), ("e0", (128, 3, 32)), ("e1", (64, 2, 32)),
+                            ("e2", (64, 32)), ("feat", (128, 32))):
+            size = int(np.prod(shape))
+            res[name] = out[o:o + size].reshape(shape)
+            o += size
+        return res

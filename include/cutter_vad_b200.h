@@ -1,0 +1,174 @@
+/*
+ * cutter_vad_b200.h -- C ABI of the B200-native Silero-VAD stream engine.
+ *
+ * This is the drop-in boundary for the reference's hot path: every entry point
+ * below replaces a piece of Picurit/cutter-vad's per-frame Python/onnxruntime
+ * pipeline (paths relative to the reference root):
+ *
+ *   cvad_create          <- ort.InferenceSession(model_path, ...)         src/real_time_vad/core/silero_model.py:321-325
+ *                           + SileroVADModel._reset_states                silero_model.py:384-401
+ *   cvad_step            <- the hot loop of VADWrapper._process_audio_frames
+ *                           src/real_time_vad/core/vad_wrapper.py:627-644, i.e. per frame:
+ *                             AudioUtils.split_into_frames                src/real_time_vad/utils/audio.py:164-190
+ *                             AudioUtils.validate_audio_data              audio.py:211-231
+ *                             AudioUtils.denoise_audio                    audio.py:104-121
+ *                             SileroVADModel._prepare_audio_input         silero_model.py:449-474
+ *                             session.run (v5 / v4 16 kHz graph)          silero_model.py:433
+ *                             _extract_probability / _update_states       silero_model.py:501-537
+ *                             VADProcessor._process_voice_state           silero_model.py:790-923
+ *                           and, where the north star adds it,
+ *                             AudioUtils.resample_audio                   audio.py:19-55
+ *   cvad_configure       <- VADConfig thresholds                          src/real_time_vad/core/config.py:54-94
+ *                           as applied by VADWrapper.set_thresholds       vad_wrapper.py:367-419
+ *   cvad_reset           <- VADProcessor.reset / SileroVADModel.reset     silero_model.py:951-968, :539-546
+ *   cvad_get_state/set   <- SileroVADModel.model_state (numpy h/c)        silero_model.py:264-267, :526-537
+ *   cvad_last_error      <- the VADError family's messages                src/real_time_vad/core/exceptions.py
+ *
+ * Plain pointers and sizes only; no torch / numpy types.  All functions return 0
+ * on success and a negative CVAD_E_* code on failure (cvad_last_error gives text).
+ * One engine = one GPU = one CUDA stream; call it from one thread at a time.
+ * Streams ("slots") are independent: h/c state, the three state-machine words and
+ * the per-slot thresholds live in HBM for the engine's lifetime.
+ */
+#ifndef CUTTER_VAD_B200_H
+#define CUTTER_VAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVAD_ABI_VERSION 1
+
+/* error codes */
+#define CVAD_OK 0
+#define CVAD_E_INVALID (-1)   /* bad argument */
+#define CVAD_E_CUDA (-2)      /* CUDA runtime failure */
+#define CVAD_E_NOGPU (-3)     /* no usable sm_100 device: there is no CPU fallback */
+#define CVAD_E_WEIGHTS (-4)   /* weight blob has the wrong size for the model version */
+#define CVAD_E_CAPACITY (-5)  /* slot id or buffer size out of range */
+
+/* model versions (SileroModelVersion, config.py:23-26) */
+#define CVAD_MODEL_V5 5
+#define CVAD_MODEL_V4 4
+
+/* audio sample formats accepted by cvad_step */
+#define CVAD_PCM_F32 0        /* float32 in [-1, 1] */
+#define CVAD_PCM_S16_32767 1  /* int16, divided by 32767.0f  (websocket server, vad_websocket_server.py:341) */
+#define CVAD_PCM_S16_32768 2  /* int16, divided by 32768.0f  (AudioUtils.pcm_to_float32, audio.py:308) */
+
+/* per-frame flag bits written to flags_out (ProcessingResult, silero_model.py:99-113) */
+#define CVAD_FLAG_STARTED 1u
+#define CVAD_FLAG_ENDED 2u
+#define CVAD_FLAG_CONTINUING 4u
+
+/* per-stream status bits written to status_out */
+#define CVAD_STATUS_NONFINITE 1u /* NaN/Inf in the stream's audio: no frame of it was processed (audio.py:227-228) */
+
+/* number of float32 values in the canonical weight blob, per model version */
+#define CVAD_V5_WEIGHT_FLOATS 309633
+#define CVAD_V4_WEIGHT_FLOATS 155908
+
+typedef struct cvad_engine cvad_engine;
+
+/* One voice start / end, in stream-then-frame order. */
+typedef struct cvad_event {
+    int32_t stream;      /* index into this step's slot list */
+    int32_t slot;        /* engine slot id */
+    int32_t frame;       /* frame index inside this step (0-based) */
+    int32_t kind;        /* CVAD_FLAG_STARTED or CVAD_FLAG_ENDED */
+    int64_t stream_frame;/* frame index since the slot's last reset */
+} cvad_event;
+
+/* Arguments of one batched step: every listed slot advances by n_frames[i] frames. */
+typedef struct cvad_step_args {
+    int32_t n_streams;        /* number of slots stepped in this call (>= 0) */
+    const int32_t *slots;     /* [n_streams] distinct slot ids; NULL = 0..n_streams-1 */
+    const void *audio;        /* sample (i, k) at audio[i*stream_stride + k] (elements) */
+    int32_t pcm_format;       /* CVAD_PCM_* */
+    int64_t stream_stride;    /* elements between consecutive streams' first samples */
+    const int32_t *n_frames;  /* [n_streams] frames per stream (0..max_frames); NULL = max_frames each */
+    int32_t max_frames;       /* row length of probs_out / flags_out */
+    int32_t frame_len;        /* samples per frame before zero-padding/truncation to 512 (1..2048) */
+    int32_t hop;              /* samples between frame starts (>= 1) */
+    int32_t src_rate;         /* 16000 (no resampling); 8000/24000/48000 reserved for the fused resampler */
+    float *probs_out;         /* [n_streams][max_frames] speech probabilities (may be NULL) */
+    uint8_t *flags_out;       /* [n_streams][max_frames] CVAD_FLAG_* (may be NULL) */
+    uint8_t *status_out;      /* [n_streams] CVAD_STATUS_* (may be NULL) */
+    cvad_event *events_out;   /* [max_events] (may be NULL) */
+    int32_t max_events;
+    int32_t *n_events_out;    /* total events produced, even if > max_events (may be NULL) */
+} cvad_step_args;
+
+/* Library / device probes. */
+int cvad_abi_version(void);
+int cvad_device_count(void);              /* number of sm_100 devices visible; 0 = none */
+const char *cvad_last_error(const cvad_engine *e); /* e may be NULL: last create() failure */
+
+/*
+ * Build an engine on `device`.  `weights` is the canonical float32 blob for the
+ * model version (order documented in DESIGN.md and oracle/silero_ref.c); it is
+ * repacked into the kernels' streaming layout and copied to HBM once.
+ */
+int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
+                int max_streams, int device, cvad_engine **out);
+int cvad_destroy(cvad_engine *e);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*); NULL = engine's own. */
+int cvad_set_stream(cvad_engine *e, void *cuda_stream);
+
+/* Zero h/c, clear the state machine and the frame counter.  slots==NULL: all slots. */
+int cvad_reset(cvad_engine *e, int n, const int32_t *slots);
+
+/*
+ * Per-slot thresholds and options (VADConfig, config.py:54-100).  Probabilities are
+ * compared in double exactly as the reference's Python does (silero_model.py:832,:898).
+ * slots==NULL: all slots.  Does NOT reset state (VADWrapper.set_thresholds resets
+ * explicitly, vad_wrapper.py:411-413; the host mirror calls cvad_reset).
+ */
+int cvad_configure(cvad_engine *e, int n, const int32_t *slots, double vad_start_probability,
+                   double vad_end_probability, int voice_start_frame_count,
+                   int voice_end_frame_count, int enable_denoising);
+
+/* LSTM state of one slot: h[128], c[128] for v5; h[2*64], c[2*64] for v4.
+   sm[4] = {is_voice_active, voice_start_frame_count, voice_end_frame_count, reserved}. */
+int cvad_get_state(cvad_engine *e, int slot, float *h, float *c, int32_t *sm, int64_t *frames_done);
+int cvad_set_state(cvad_engine *e, int slot, const float *h, const float *c, const int32_t *sm);
+
+/*
+ * One batched step with HOST buffers: pinned staging + H2D, kernels, D2H, sync.
+ * This is what the reference-facing Python mirror calls.
+ */
+int cvad_step(cvad_engine *e, const cvad_step_args *a);
+
+/*
+ * Same step with every pointer in `a` (audio, slots, n_frames, outputs) already in
+ * DEVICE memory; enqueues on the engine's stream and returns without synchronising.
+ * events_out/n_events_out (device) are filled by the kernel in arbitrary order.
+ */
+int cvad_step_device(cvad_engine *e, const cvad_step_args *a);
+
+/* Block until everything enqueued on the engine's stream has finished. */
+int cvad_sync(cvad_engine *e);
+
+/* Page-locked host memory for callers that want cvad_step to DMA straight from their
+   buffer (pageable buffers are staged through the engine's own pinned area). */
+void *cvad_alloc_pinned(size_t bytes);
+void cvad_free_pinned(void *p);
+
+/* Number of kernel launches issued by this engine since creation (for bench accounting). */
+int64_t cvad_launch_count(const cvad_engine *e);
+
+/*
+ * Test hook: run the front end + one recurrent step for the first tile (<= 32 streams,
+ * frame 0) of `a` WITHOUT touching engine state and copy the intermediate activations
+ * to `dbg_out` (host).  Layout in DESIGN.md ("debug dump").  Returns floats written.
+ */
+int cvad_debug_dump(cvad_engine *e, const cvad_step_args *a, float *dbg_out, size_t dbg_floats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUTTER_VAD_B200_H */
