@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 Silero-VAD stream engine.
+
+Metric (BASELINE.json): audio-seconds per wall-second over N concurrent 16 kHz streams
+(Silero v5), plus p99 latency of one batched frame step.  Workload = configs[1]:
+4,096 concurrent 16 kHz streams per GPU, every step advances every stream by
+`--frames-per-step` 512-sample frames (hop 512).  Weak scaling: streams per GPU fixed.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]              our arm
+  python bench.py --impl reference [...]                            CPU arm (oracle port, all host threads)
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "cutter-vad_b200"))
+
+FLOP_FRAME = 1_127_936          # v5/16k nominal FLOP per 512-sample frame
+FLOP_FRONTEND = 865_536         # STFT + encoder.0-3 share (432,768 MAC)
+FLOP_RECURRENT = 262_400        # LSTM + decoder share (131,200 MAC)
+SMS, FP32_LANES = 148, 128
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def synth_audio(n_streams: int, n_samples: int, seed: int) -> np.ndarray:
+    """Vectorised version of the tests' signal recipe: per-stream noise floor plus gated
+    harmonic 'voice' bursts (reference examples/probability_demo.py:60-67), float32."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n_samples, dtype=np.float32) / 16000.0
+    sigma = np.array([0.005, 0.02, 0.1], np.float32)[np.arange(n_streams) % 3][:, None]
+    level = np.array([0.3, 0.7], np.float32)[(np.arange(n_streams) // 3) % 2][:, None]
+    f0 = rng.uniform(110, 220, size=(n_streams, 1)).astype(np.float32)
+    out = rng.standard_normal((n_streams, n_samples), dtype=np.float32) * sigma
+    ph = 2 * np.pi * f0 * t[None, :]
+    voice = level * (0.4 * np.sin(ph) + 0.3 * np.sin(2 * ph) + 0.2 * np.sin(4 * ph))
+    period = rng.uniform(1.0, 4.0, size=(n_streams, 1)).astype(np.float32)
+    phase = rng.uniform(0, 1, size=(n_streams, 1)).astype(np.float32)
+    gate = (((t[None, :] / period) + phase) % 1.0) < 0.5
+    out += np.where(gate, voice, 0.0).astype(np.float32)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+
+def cpu_port(native=True):
+    sys.path.insert(0, str(ROOT / "oracle"))
+    from vad_oracle import RefLib, RefV5, v5_blob
+    lib = RefLib(native=native)
+    blob = v5_blob(str(ROOT / "cutter-vad_b200" / "real_time_vad" / "models" / "silero_vad_v5.onnx"))
+    return lib, RefV5(blob, lib)
+
+
+def cpu_baseline_sample(n_streams: int, target_s: float = 12.0):
+    """Oracle port (plain C + OpenMP, every host thread) on a bounded sample of the workload."""
+    lib, ref = cpu_port()
+    cores = lib.max_threads()
+    n = min(n_streams, 1024)
+    audio = synth_audio(n, 512 * 8, seed=99)
+    t0 = time.perf_counter()
+    ref.run(audio, 8, nthreads=cores)
+    dt = time.perf_counter() - t0
+    rate = n * 8 / dt
+    frames = int(max(8, min(4000, rate * target_s / n)))
+    audio = synth_audio(n, 512 * frames, seed=100)
+    t0 = time.perf_counter()
+    ref.run(audio, frames, nthreads=cores)
+    dt = time.perf_counter() - t0
+    fps = n * frames / dt
+    return {"value": fps * 0.032, "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "frames_per_s": fps,
+            "sample": f"{n} streams x {frames} frames (hop 512) of the same synthetic recipe, {dt:.1f} s, "
+                      f"oracle/silero_ref.c -O3 -march=native + OpenMP; CPU restatement, not onnxruntime"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lib, ref = cpu_port()
+    cores = lib.max_threads()
+    n, F = args.streams, args.frames_per_step
+    pool = [synth_audio(n, 512 * F, seed=1000 + i) for i in range(4)]
+    h = np.zeros((n, 128), np.float32)
+    c = np.zeros((n, 128), np.float32)
+    for i in range(args.warmup):
+        ref.run(pool[i % 4], F, h=h, c=c, nthreads=cores)
+    lat = []
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        t1 = time.perf_counter()
+        ref.run(pool[i % 4], F, h=h, c=c, nthreads=cores)
+        lat.append(time.perf_counter() - t1)
+    dt = time.perf_counter() - t0
+    value = n * F * args.steps * 0.032 / dt
+    line = {
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, pool_mb=None),
+        "p99_step_ms": 1e3 * float(np.percentile(lat, 99)),
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                         "sample": f"every step = full workload ({n} streams x {F} frames); oracle/silero_ref.c "
+                                   f"(plain C, OpenMP, {cores} threads); CPU restatement of the reference's "
+                                   "onnxruntime path, onnxruntime itself is absent from this image"},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, pool_mb):
+    return {"workload": f"Silero v5, {args.streams} concurrent 16 kHz streams per GPU batched per frame step "
+                        f"(BASELINE.json configs[1])",
+            "streams_per_gpu": args.streams, "frames_per_step": args.frames_per_step, "hop": 512,
+            "frame_len": 512, "denoise": True, "state_machine": True,
+            "l2": (f"inputs cycle through a pool of distinct step buffers totalling {pool_mb} MB (> 126 MB L2)"
+                   if pool_mb else "n/a (CPU arm)")}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from real_time_vad.engine import capi
+    from real_time_vad.engine.stream_engine import StreamEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n, F = args.streams, args.frames_per_step
+    step_samples = 512 * F
+    step_bytes = n * step_samples * 4
+    pool_n = max(2, int(np.ceil(300e6 / step_bytes)))  # > 2x L2 worth of distinct inputs
+    pool_n = min(pool_n, 64)
+    peaks, peaks_src = load_peaks()
+
+    eng = StreamEngine("v5", max_streams=n, device=local)
+    eng.configure(enable_denoising=True)
+    stream = torch.cuda.Stream(device=local)
+    eng.set_stream(stream.cuda_stream)
+
+    # ---- synthetic inputs: pinned host pool (e2e) and device pool (kernel-only)
+    host_pool = []
+    for i in range(pool_n):
+        t = torch.empty((n, step_samples), dtype=torch.float32).pin_memory()
+        t.numpy()[:] = synth_audio(n, step_samples, seed=rank * 7919 + i)
+        host_pool.append(t)
+    dev_pool = [t.to(f"cuda:{local}", non_blocking=False) for t in host_pool]
+    d_probs = torch.zeros((n, F), dtype=torch.float32, device=f"cuda:{local}")
+    d_flags = torch.zeros((n, F), dtype=torch.uint8, device=f"cuda:{local}")
+    d_events = torch.zeros((max(16, 2 * n * F) * 24,), dtype=torch.uint8, device=f"cuda:{local}")
+    d_nev = torch.zeros((1,), dtype=torch.int32, device=f"cuda:{local}")
+
+    def dev_args(buf):
+        a = capi.StepArgs()
+        a.n_streams = n
+        a.audio = buf.data_ptr()
+        a.pcm_format = capi.PCM_F32
+        a.stream_stride = step_samples
+        a.max_frames = F
+        a.frame_len = 512
+        a.hop = 512
+        a.src_rate = 16000
+        a.probs_out = d_probs.data_ptr()
+        a.flags_out = d_flags.data_ptr()
+        a.events_out = d_events.data_ptr()
+        a.max_events = max(16, 2 * n * F)
+        a.n_events_out = d_nev.data_ptr()
+        return a
+
+    dargs = [dev_args(b) for b in dev_pool]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ================= kernel-only (`value`): inputs resident in HBM, CUDA events on the engine's stream
+    eng.reset()
+    for i in range(args.warmup):
+        eng.step_device(dargs[i % pool_n])
+    eng.sync()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    eng.set_timing(True)
+    launches0 = eng.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for i in range(args.steps):
+            eng.step_device(dargs[(args.warmup + i) % pool_n])
+        e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    fe_ms, rec_ms, n_timed = eng.read_timing()
+    eng.set_timing(False)
+    launches = eng.launch_count() - launches0
+
+    # per-step latency distribution (device side), one step at a time
+    lat = []
+    for i in range(min(args.steps, 200)):
+        a0 = torch.cuda.Event(enable_timing=True)
+        a1 = torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        eng.step_device(dargs[i % pool_n])
+        a1.record(stream)
+        a1.synchronize()
+        lat.append(a0.elapsed_time(a1))
+    clocks = sampler.stop()
+
+    # ================= end to end (`e2e`): public host-buffer call, H2D + D2H inside the timed region
+    eng.reset()
+    host_np = [t.numpy() for t in host_pool]
+    for i in range(args.warmup):
+        eng.step(host_np[i % pool_n])
+    barrier()
+    e2e_lat = []
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        t1 = time.perf_counter()
+        r = eng.step(host_np[(args.warmup + i) % pool_n])
+        e2e_lat.append(time.perf_counter() - t1)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_events = len(r.events)
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(times[0]), float(times[1])
+
+    audio_s_per_step = n * F * 0.032
+    total_audio = audio_s_per_step * args.steps * world
+    value = total_audio / (dev_ms_max * 1e-3)
+    e2e_value = total_audio / (e2e_ms_max * 1e-3)
+    frames_per_step = n * F
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    peak_fp32 = SMS * FP32_LANES * 2 * sm_max * 1e6 / 1e12
+    fe_avg_s = fe_ms / max(n_timed, 1) * 1e-3
+    rec_avg_s = rec_ms / max(n_timed, 1) * 1e-3
+    fe_tflops = frames_per_step * FLOP_FRONTEND / fe_avg_s / 1e12 if fe_avg_s > 0 else 0.0
+    step_tflops = frames_per_step * FLOP_FRAME / (dev_ms / args.steps * 1e-3) / 1e12
+
+    if rank == 0:
+        cpu = cpu_baseline_sample(n)
+        line = {
+            "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, pool_mb=round(pool_n * step_bytes / 1e6)),
+            "p99_step_ms": float(np.percentile(lat, 99)), "p50_step_ms": float(np.percentile(lat, 50)),
+            "frames_per_s": value / 0.032,
+            "roofline": {
+                "bound": "fp32_ffma", "kernel": "v5_frontend_kernel", "achieved": fe_tflops, "peak": peak_fp32,
+                "unit": "TFLOP/s", "frac": fe_tflops / peak_fp32, "traffic": None,
+                "peak_source": f"148 SMs x 128 FP32 lanes x 2 x sm_max_mhz {sm_max:.0f} ({peaks_src} "
+                               "MEASURED_PEAKS.json clock); the path is FP32-FFMA bound, not HBM or tensor bound",
+                "algorithmic_flop_per_frame": FLOP_FRONTEND, "frames_per_launch": frames_per_step,
+                "avg_launch_ms": fe_avg_s * 1e3,
+                "recurrent_kernel": {"avg_launch_ms": rec_avg_s * 1e3,
+                                     "achieved": frames_per_step * FLOP_RECURRENT / rec_avg_s / 1e12 if rec_avg_s else 0,
+                                     "algorithmic_flop_per_frame": FLOP_RECURRENT},
+                "whole_step": {"achieved": step_tflops, "frac": step_tflops / peak_fp32,
+                               "algorithmic_flop_per_frame": FLOP_FRAME},
+                "hbm": {"algorithmic_bytes_per_frame": 2048 + 2 * 1024 + 4 + 1,
+                        "achieved_gbs": frames_per_step * (2048 + 2048 + 5) / (dev_ms / args.steps * 1e-3) / 1e9,
+                        "peak_gbs": peaks.get("hbm_gbs")},
+            },
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": step_bytes,
+                    "d2h_bytes_per_step": n * F * 5 + n * 4 + 4, "ms_per_step": e2e_ms_max / args.steps,
+                    "p99_step_ms": 1e3 * float(np.percentile(e2e_lat, 99)),
+                    "api": "StreamEngine.step -> cvad_step (pinned host buffers)", "events_last_step": e2e_events},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
+    ap.add_argument("--frames-per-step", type=int, default=1, help="512-sample frames per stream per step")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

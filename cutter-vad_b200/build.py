@@ -1,0 +1,30 @@
+"""Build recipe for libcvad_b200.so (nvcc, sm_100a only, in-tree)."""
+from __future__ import annotations
+
+import os
+import subprocess
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+SRC = HERE / "csrc" / "cvad_capi.cu"
+OUT = HERE / "libcvad_b200.so"
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def sources():
+    return sorted((HERE / "csrc").glob("*.cu")) + sorted((HERE / "csrc").glob("*.cuh")) + \
+        [HERE.parent / "include" / "cutter_vad_b200.h"]
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and OUT.exists() and all(OUT.stat().st_mtime >= s.stat().st_mtime for s in sources()):
+        return OUT
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(OUT), str(SRC)]
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -49,6 +49,10 @@ struct cvad_engine {
     int *d_nevents = nullptr;
     // pinned staging (host)
     DevBuf h_in, h_out;
+    // optional per-kernel timing (bench): event triples (before FE, between, after REC)
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
 };
 
 namespace {
@@ -236,14 +240,28 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
 
     const int n_tiles = a->max_frames * n_stiles;
     const int grid_fe = std::min(n_tiles, e->num_sms);
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    const bool timed = e->timing && !d_dbg;
+    if (timed) {
+        while (e->ev_pool.size() < e->ev_used + 3) {
+            cudaEvent_t x;
+            CU_TRY(e, cudaEventCreate(&x));
+            e->ev_pool.push_back(x);
+        }
+        for (int i = 0; i < 3; ++i) ev[i] = e->ev_pool[e->ev_used + i];
+        e->ev_used += 3;
+        CU_TRY(e, cudaEventRecord(ev[0], e->stream));
+    }
     cvad::v5_frontend_kernel<<<grid_fe, cvad::kThreads, cvad::kFeSmemBytes, e->stream>>>(p);
     CU_TRY(e, cudaGetLastError());
     e->launches++;
+    if (timed) CU_TRY(e, cudaEventRecord(ev[1], e->stream));
     if (!d_dbg) {
         cvad::v5_recurrent_kernel<<<n_stiles, cvad::kThreads, cvad::kRecSmemBytes, e->stream>>>(p);
         CU_TRY(e, cudaGetLastError());
         e->launches++;
     }
+    if (timed) CU_TRY(e, cudaEventRecord(ev[2], e->stream));
     return CVAD_OK;
 }
 
@@ -514,6 +532,7 @@ int cvad_destroy(cvad_engine *e) {
         if (p) cudaFree(p);
     if (e->h_in.p) cudaFreeHost(e->h_in.p);
     if (e->h_out.p) cudaFreeHost(e->h_out.p);
+    for (cudaEvent_t x : e->ev_pool) cudaEventDestroy(x);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return CVAD_OK;
@@ -623,6 +642,32 @@ int cvad_sync(cvad_engine *e) {
 }
 
 int64_t cvad_launch_count(const cvad_engine *e) { return e ? e->launches : 0; }
+
+int cvad_set_timing(cvad_engine *e, int enabled) {
+    if (!e) return CVAD_E_INVALID;
+    e->timing = enabled != 0;
+    e->ev_used = 0;
+    return CVAD_OK;
+}
+
+int cvad_read_timing(cvad_engine *e, double *frontend_ms, double *recurrent_ms, int *n_steps) {
+    if (!e) return CVAD_E_INVALID;
+    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    double fe = 0.0, rec = 0.0;
+    const size_t n = e->ev_used / 3;
+    for (size_t i = 0; i < n; ++i) {
+        float a = 0.f, b = 0.f;
+        CU_TRY(e, cudaEventElapsedTime(&a, e->ev_pool[3 * i], e->ev_pool[3 * i + 1]));
+        CU_TRY(e, cudaEventElapsedTime(&b, e->ev_pool[3 * i + 1], e->ev_pool[3 * i + 2]));
+        fe += a; rec += b;
+    }
+    if (frontend_ms) *frontend_ms = fe;
+    if (recurrent_ms) *recurrent_ms = rec;
+    if (n_steps) *n_steps = (int)n;
+    e->ev_used = 0;
+    return CVAD_OK;
+}
 
 void *cvad_alloc_pinned(size_t bytes) {
     void *p = nullptr;

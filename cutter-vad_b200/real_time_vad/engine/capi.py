@@ -23,7 +23,7 @@ EXPORTS = (
     "cvad_abi_version", "cvad_device_count", "cvad_last_error", "cvad_create", "cvad_destroy",
     "cvad_set_stream", "cvad_reset", "cvad_configure", "cvad_get_state", "cvad_set_state",
     "cvad_step", "cvad_step_device", "cvad_sync", "cvad_launch_count", "cvad_debug_dump",
-    "cvad_alloc_pinned", "cvad_free_pinned",
+    "cvad_alloc_pinned", "cvad_free_pinned", "cvad_set_timing", "cvad_read_timing",
 )
 
 
@@ -92,5 +92,7 @@ def lib() -> C.CDLL:
     L.cvad_alloc_pinned.restype = vp
     L.cvad_alloc_pinned.argtypes = [C.c_size_t]
     L.cvad_free_pinned.argtypes = [vp]
+    L.cvad_set_timing.argtypes = [vp, i32]
+    L.cvad_read_timing.argtypes = [vp, vp, vp, vp]
     _lib = L
     return L

@@ -85,6 +85,19 @@ class StreamEngine:
     def launch_count(self) -> int:
         return int(self._L.cvad_launch_count(self._h))
 
+    def set_timing(self, enabled: bool) -> None:
+        self._check(self._L.cvad_set_timing(self._h, int(enabled)))
+
+    def read_timing(self):
+        """-> (frontend_ms_total, recurrent_ms_total, n_steps) since the last read."""
+        fe, rec, n = C.c_double(0), C.c_double(0), C.c_int(0)
+        self._check(self._L.cvad_read_timing(self._h, C.byref(fe), C.byref(rec), C.byref(n)))
+        return fe.value, rec.value, n.value
+
+    def step_device(self, args: "capi.StepArgs") -> None:
+        """Enqueue one step whose buffers are all device pointers (no sync)."""
+        self._check(self._L.cvad_step_device(self._h, C.byref(args)))
+
     # ------------------------------------------------------------------ per-slot control
     @staticmethod
     def _slots(slots: Optional[Sequence[int]]):

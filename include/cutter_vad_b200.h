@@ -162,6 +162,15 @@ void cvad_free_pinned(void *p);
 int64_t cvad_launch_count(const cvad_engine *e);
 
 /*
+ * Per-kernel device timing for bench.py: while enabled, every step records CUDA
+ * events on the engine's stream around the front-end and the recurrent kernel.
+ * cvad_read_timing synchronises, returns the summed durations (ms) and the number of
+ * steps they cover, and clears the record.
+ */
+int cvad_set_timing(cvad_engine *e, int enabled);
+int cvad_read_timing(cvad_engine *e, double *frontend_ms, double *recurrent_ms, int *n_steps);
+
+/*
  * Test hook: run the front end + one recurrent step for the first tile (<= 32 streams,
  * frame 0) of `a` WITHOUT touching engine state and copy the intermediate activations
  * to `dbg_out` (host).  Layout in DESIGN.md ("debug dump").  Returns floats written.
