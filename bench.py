@@ -325,7 +325,7 @@ def run_ours(args):
     step_tflops = frames_per_step * FLOP_FRAME / (dev_ms / args.steps * 1e-3) / 1e12
 
     if rank == 0:
-        cpu = cpu_baseline_sample(n)
+        cpu = None if args.skip_cpu else cpu_baseline_sample(n)
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
@@ -371,6 +371,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
     ap.add_argument("--frames-per-step", type=int, default=1, help="512-sample frames per stream per step")
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -63,14 +63,50 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
-// acc[i][j] += a[i] * w[j] for an 8x4 register tile
-__device__ __forceinline__ void fma8x4(float (&acc)[8][4], const float4 &a0, const float4 &a1, const float4 &w) {
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float b[4] = {w.x, w.y, w.z, w.w};
+// Register tiles use the sm_100 packed FP32 FMA (PTX fma.rn.f32x2, SASS FFMA2): one
+// instruction = two IEEE fp32 FMAs on a 64-bit register pair.  A 3-register scalar FFMA
+// issues at most every other cycle per scheduler on Blackwell; FFMA2 restores the full
+// 128 FMA/clk/SM.  Accumulators are paired along the ITEM axis (pairs come straight out
+// of the LDS.128 of the activations); the weight is duplicated into both halves.
+//   acc[ip][j] = (item 2ip, item 2ip+1) x output j
+struct Dup4 {
+    float2 d[4];
+};
+__device__ __forceinline__ Dup4 dup4(const float4 &w) {
+    Dup4 r;
+    r.d[0] = make_float2(w.x, w.x);
+    r.d[1] = make_float2(w.y, w.y);
+    r.d[2] = make_float2(w.z, w.z);
+    r.d[3] = make_float2(w.w, w.w);
+    return r;
+}
+
+// acc (8 items x 4 outputs) += a (8 items) (x) w (4 outputs)
+__device__ __forceinline__ void fma8x4(float2 (&acc)[4][4], const float4 &a0, const float4 &a1, const Dup4 &w) {
+    const float2 a[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
+                         make_float2(a1.z, a1.w)};
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int ip = 0; ip < 4; ++ip)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[ip][j] = __ffma2_rn(a[ip], w.d[j], acc[ip][j]);
+}
+
+__device__ __forceinline__ void zero_tile(float2 (&acc)[4][4]) {
+#pragma unroll
+    for (int ip = 0; ip < 4; ++ip)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[ip][j] = make_float2(0.f, 0.f);
+}
+
+// view the paired accumulators as v[item][output] (pure register renaming)
+__device__ __forceinline__ void unpack_tile(const float2 (&acc)[4][4], float (&v)[8][4]) {
+#pragma unroll
+    for (int ip = 0; ip < 4; ++ip)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[2 * ip][j] = acc[ip][j].x;
+            v[2 * ip + 1][j] = acc[ip][j].y;
+        }
 }
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }

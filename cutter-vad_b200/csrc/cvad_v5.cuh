@@ -237,24 +237,20 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
             const float *xT = bufA;
             float *magT = bufB;
             const int tn = tid >> 2;  // 0..63 -> columns 4tn..4tn+3 = bins 2tn, 2tn+1
-            float acc[3][8][4];
+            float2 acc2[3][4][4];
 #pragma unroll
-            for (int t = 0; t < 3; ++t)
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
+            for (int t = 0; t < 3; ++t) zero_tile(acc2[t]);
 
             for (int ci = 0; ci < 16; ++ci) {
                 const float *w = ring_wait(ring);
 #pragma unroll 4
                 for (int kk = 0; kk < 16; ++kk) {
                     const int k = ci * 16 + kk;
-                    const float4 wv = ld4(w + kk * 256 + 4 * tn);
+                    const Dup4 wv = dup4(ld4(w + kk * 256 + 4 * tn));
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
                         const float *xr = xT + (128 * t + k) * kTile + 8 * tm;
-                        fma8x4(acc[t], ld4(xr), ld4(xr + 4), wv);
+                        fma8x4(acc2[t], ld4(xr), ld4(xr + 4), wv);
                     }
                 }
                 __syncthreads();
@@ -264,10 +260,12 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
             // magnitude = sqrt(re^2 + im^2) with separately rounded squares (ONNX Pow, Pow, Add, Sqrt)
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
+                float acc[1][8][4];
+                unpack_tile(acc2[t], acc[0]);
                 float m0[8], m1[8], m2[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float x = acc[t][i][0], y = acc[t][i][1], z = acc[t][i][2], w = acc[t][i][3];
+                    const float x = acc[0][i][0], y = acc[0][i][1], z = acc[0][i][2], w = acc[0][i][3];
                     if (tn == 0) {
                         m0[i] = sqrtf(__fmul_rn(x, x));                                 // bin 0   (im == 0)
                         m2[i] = sqrtf(__fmul_rn(y, y));                                 // bin 128 (im == 0)
@@ -299,13 +297,9 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
             float *e0T = bufA;
             const int tn = (tid >> 2) & 31;  // outputs 4tn..4tn+3
             const int grp = tid >> 7;        // 0..1
-            float acc[3][8][4];
+            float2 acc2[3][4][4];
 #pragma unroll
-            for (int t = 0; t < 3; ++t)
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
+            for (int t = 0; t < 3; ++t) zero_tile(acc2[t]);
 
             for (int ci = 0; ci < 13; ++ci) {
                 const float *w = ring_wait(ring);
@@ -314,20 +308,23 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
                 for (int cc = 0; cc < cnt; ++cc) {
                     const int c = cbase + cc;
                     const float *wl = w + ((5 * grp + cc) * 3) * 128 + 4 * tn;
-                    const float4 w0 = ld4(wl), w1 = ld4(wl + 128), w2 = ld4(wl + 256);
+                    const Dup4 w0 = dup4(ld4(wl)), w1 = dup4(ld4(wl + 128)), w2 = dup4(ld4(wl + 256));
                     const float *ar = magT + (c * 3) * kTile + 8 * tm;
                     const float4 a00 = ld4(ar), a01 = ld4(ar + 4);
                     const float4 a10 = ld4(ar + kTile), a11 = ld4(ar + kTile + 4);
                     const float4 a20 = ld4(ar + 2 * kTile), a21 = ld4(ar + 2 * kTile + 4);
                     // out t: taps k with input time t+k-1 in [0,3)
-                    fma8x4(acc[0], a00, a01, w1); fma8x4(acc[0], a10, a11, w2);
-                    fma8x4(acc[1], a00, a01, w0); fma8x4(acc[1], a10, a11, w1); fma8x4(acc[1], a20, a21, w2);
-                    fma8x4(acc[2], a10, a11, w0); fma8x4(acc[2], a20, a21, w1);
+                    fma8x4(acc2[0], a00, a01, w1); fma8x4(acc2[0], a10, a11, w2);
+                    fma8x4(acc2[1], a00, a01, w0); fma8x4(acc2[1], a10, a11, w1); fma8x4(acc2[1], a20, a21, w2);
+                    fma8x4(acc2[2], a10, a11, w0); fma8x4(acc2[2], a20, a21, w1);
                 }
                 __syncthreads();
                 if (tid == 0) fe_ring_issue(ring, ring.g + kRingStages);
                 ++ring.g;
             }
+            float acc[3][8][4];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) unpack_tile(acc2[t], acc[t]);
             // reduce the two K halves through the output buffer, add bias, ReLU
             if (grp == 1) {
 #pragma unroll
@@ -367,13 +364,9 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
             float *e1T = bufB;
             const int tn = (tid >> 2) & 15;  // outputs 4tn..4tn+3 of 64
             const int grp = tid >> 6;        // 0..3
-            float acc[2][8][4];
-#pragma unroll
-            for (int t = 0; t < 2; ++t)
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
+            float2 acc2[2][4][4];
+            zero_tile(acc2[0]);
+            zero_tile(acc2[1]);
 
             for (int ci = 0; ci < 8; ++ci) {
                 const float *w = ring_wait(ring);
@@ -381,19 +374,22 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
                 for (int cc = 0; cc < 4; ++cc) {
                     const int c = ci * 16 + 4 * grp + cc;
                     const float *wl = w + ((4 * grp + cc) * 3) * 64 + 4 * tn;
-                    const float4 w0 = ld4(wl), w1 = ld4(wl + 64), w2 = ld4(wl + 128);
+                    const Dup4 w0 = dup4(ld4(wl)), w1 = dup4(ld4(wl + 64)), w2 = dup4(ld4(wl + 128));
                     const float *ar = e0T + (c * 3) * kTile + 8 * tm;
                     const float4 a00 = ld4(ar), a01 = ld4(ar + 4);
                     const float4 a10 = ld4(ar + kTile), a11 = ld4(ar + kTile + 4);
                     const float4 a20 = ld4(ar + 2 * kTile), a21 = ld4(ar + 2 * kTile + 4);
                     // out t' reads input time 2t'+k-1: t'=0 -> (k1,t0),(k2,t1); t'=1 -> (k0,t1),(k1,t2)
-                    fma8x4(acc[0], a00, a01, w1); fma8x4(acc[0], a10, a11, w2);
-                    fma8x4(acc[1], a10, a11, w0); fma8x4(acc[1], a20, a21, w1);
+                    fma8x4(acc2[0], a00, a01, w1); fma8x4(acc2[0], a10, a11, w2);
+                    fma8x4(acc2[1], a10, a11, w0); fma8x4(acc2[1], a20, a21, w1);
                 }
                 __syncthreads();
                 if (tid == 0) fe_ring_issue(ring, ring.g + kRingStages);
                 ++ring.g;
             }
+            float acc[2][8][4];
+            unpack_tile(acc2[0], acc[0]);
+            unpack_tile(acc2[1], acc[1]);
             for (int r = 1; r < 4; ++r) {
                 if (grp == r) {
 #pragma unroll
@@ -438,26 +434,25 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
             float *e2T = bufA;
             const int tn = (tid >> 2) & 15;
             const int grp = tid >> 6;
-            float acc[8][4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            float2 acc2[4][4];
+            zero_tile(acc2);
             for (int ci = 0; ci < 2; ++ci) {
                 const float *w = ring_wait(ring);
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
                     const int c = ci * 32 + 8 * grp + cc;
                     const float *wl = w + ((8 * grp + cc) * 2) * 64 + 4 * tn;
-                    const float4 w1 = ld4(wl), w2 = ld4(wl + 64);
+                    const Dup4 w1 = dup4(ld4(wl)), w2 = dup4(ld4(wl + 64));
                     const float *ar = e1T + (c * 2) * kTile + 8 * tm;
-                    fma8x4(acc, ld4(ar), ld4(ar + 4), w1);
-                    fma8x4(acc, ld4(ar + kTile), ld4(ar + kTile + 4), w2);
+                    fma8x4(acc2, ld4(ar), ld4(ar + 4), w1);
+                    fma8x4(acc2, ld4(ar + kTile), ld4(ar + kTile + 4), w2);
                 }
                 __syncthreads();
                 if (tid == 0) fe_ring_issue(ring, ring.g + kRingStages);
                 ++ring.g;
             }
+            float acc[8][4];
+            unpack_tile(acc2, acc);
             for (int r = 1; r < 4; ++r) {
                 if (grp == r) {
 #pragma unroll
@@ -495,24 +490,23 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
             float *scratch = bufB;
             const int tn = (tid >> 2) & 31;
             const int grp = tid >> 7;
-            float acc[8][4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            float2 acc2[4][4];
+            zero_tile(acc2);
             for (int ci = 0; ci < 2; ++ci) {
                 const float *w = ring_wait(ring);
 #pragma unroll
                 for (int cc = 0; cc < 16; ++cc) {
                     const int c = ci * 32 + 16 * grp + cc;
-                    const float4 wv = ld4(w + (16 * grp + cc) * 128 + 4 * tn);
+                    const Dup4 wv = dup4(ld4(w + (16 * grp + cc) * 128 + 4 * tn));
                     const float *ar = e2T + c * kTile + 8 * tm;
-                    fma8x4(acc, ld4(ar), ld4(ar + 4), wv);
+                    fma8x4(acc2, ld4(ar), ld4(ar + 4), wv);
                 }
                 __syncthreads();
                 if (tid == 0) fe_ring_issue(ring, ring.g + kRingStages);
                 ++ring.g;
             }
+            float acc[8][4];
+            unpack_tile(acc2, acc);
             if (grp == 1) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -654,11 +648,9 @@ __global__ void __launch_bounds__(kThreads, 1) v5_recurrent_kernel(const V5Step 
         const float *xb = xbuf + (j & 1) * 4096;
         mbar_wait(&xbars[j & 1], (uint32_t)(j >> 1) & 1u);
 
-        float acc[8][8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+        float2 acc2[2][4][4];  // [column half][item pair][column]
+        zero_tile(acc2[0]);
+        zero_tile(acc2[1]);
 
         for (int ci = 0; ci < kRecChunks; ++ci) {
             const float *w = ring_wait(ring);
@@ -667,13 +659,9 @@ __global__ void __launch_bounds__(kThreads, 1) v5_recurrent_kernel(const V5Step 
             for (int kk = 0; kk < 8; ++kk) {
                 const float *ar = abase + kk * kTile + 8 * tm;
                 const float4 a0 = ld4(ar), a1 = ld4(ar + 4);
-                const float4 w0 = ld4(w + kk * 512 + 8 * tn), w1 = ld4(w + kk * 512 + 8 * tn + 4);
-                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                const float b[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(a[i], b[c], acc[i][c]);
+                const Dup4 w0 = dup4(ld4(w + kk * 512 + 8 * tn)), w1 = dup4(ld4(w + kk * 512 + 8 * tn + 4));
+                fma8x4(acc2[0], a0, a1, w0);
+                fma8x4(acc2[1], a0, a1, w1);
             }
             __syncthreads();
             if (tid == 0) rec_ring_issue(ring, ring.g + kRingStages);
@@ -686,6 +674,16 @@ __global__ void __launch_bounds__(kThreads, 1) v5_recurrent_kernel(const V5Step 
                      &xbars[j & 1]);
         }
         // LSTM cell (PyTorch LSTMCell == ONNX LSTM with both biases added)
+        float acc[8][8];
+        {
+            float v0[8][4], v1[8][4];
+            unpack_tile(acc2[0], v0);
+            unpack_tile(acc2[1], v1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { acc[i][c] = v0[i][c]; acc[i][4 + c] = v1[i][c]; }
+        }
         const float bi[8] = {bia0.x, bia0.y, bia0.z, bia0.w, bia1.x, bia1.y, bia1.z, bia1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
