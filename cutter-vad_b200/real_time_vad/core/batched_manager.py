@@ -1,0 +1,299 @@
+"""BatchedVADManager: thousands of independent audio streams stepped per GPU launch.
+
+New entry point named by the north star (SURVEY.md section 8b "New entry"); the
+reference has no equivalent -- it builds one `VADWrapper` + one onnxruntime session per
+stream (websocket_service/server/vad_websocket_server.py:248-290) and runs one model
+call per frame on the event loop (:369).  Here a stream is a *slot* of resident state
+in HBM (LSTM h/c, the state-machine words, thresholds); `step()` advances every stream
+that has at least one complete frame buffered, in ONE `cvad_step`:
+
+    mgr = BatchedVADManager(max_streams=10_000)
+    sid = mgr.open_stream(VADConfig(...), on_voice_start=..., on_voice_end=..., on_voice_continue=...)
+    mgr.push(sid, samples)            # float32 in [-1,1] or int16 PCM, any length
+    out = mgr.step()                  # events in stream-then-frame order, callbacks fired
+
+Per stream the results equal what a `VADWrapper` fed the same frames would produce:
+same probabilities (FP32, 1e-4), same start/end frame indices, same callback payloads
+(`voice_end` WAV of the gated frames buffered since the first above-threshold frame,
+`voice_continue` float32 bytes of the gated frame; silero_model.py:839-869, :891-895, :932-949).
+Framing is configurable: `frame_len` samples per frame, `hop` between frames
+(hop == frame_len for the websocket service's one-frame-per-message mode, frame_len/2 for
+the wrapper's overlapped mode); leftovers shorter than a frame are carried to the next step.
+"""
+from __future__ import annotations
+
+import threading
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, NamedTuple, Optional, Sequence
+
+import numpy as np
+
+from ..engine import capi
+from ..engine.stream_engine import StreamEngine
+from ..utils.wav_writer import WAVWriter
+from .config import SileroModelVersion, VADConfig
+from .exceptions import AudioProcessingError, CallbackError, ConfigurationError, VADError
+
+
+class StreamEvent(NamedTuple):
+    stream_id: int        # slot id returned by open_stream
+    kind: str             # "start" | "end"
+    frame_index: int      # frame index since the stream was opened / last reset
+    step_frame: int       # frame index inside the step that produced it
+
+
+@dataclass
+class StepOutput:
+    events: List[StreamEvent]
+    probabilities: Dict[int, np.ndarray]   # stream id -> probabilities of the frames run in this step
+    frames: int                            # total frames run in this step
+
+
+@dataclass
+class _Stream:
+    config: VADConfig
+    writer: WAVWriter
+    pending: np.ndarray
+    on_start: Optional[Callable[[], None]] = None
+    on_end: Optional[Callable[[bytes], None]] = None
+    on_continue: Optional[Callable[[bytes], None]] = None
+    active: bool = False
+    pre_roll: List[np.ndarray] = field(default_factory=list)
+    segment: List[np.ndarray] = field(default_factory=list)
+
+    @property
+    def wants_audio(self) -> bool:
+        return self.on_end is not None or self.on_continue is not None
+
+
+class BatchedVADManager:
+    def __init__(self, max_streams: int = 4096, model_version: SileroModelVersion = SileroModelVersion.V5,
+                 device: Optional[int] = None, frame_len: int = 512, hop: Optional[int] = None,
+                 pcm_format: int = capi.PCM_F32) -> None:
+        if not (1 <= frame_len <= 2048):
+            raise ConfigurationError("frame_len", str(frame_len))
+        self.frame_len = int(frame_len)
+        self.hop = int(hop) if hop is not None else int(frame_len)
+        if self.hop < 1:
+            raise ConfigurationError("hop", str(hop))
+        self.pcm_format = pcm_format
+        self._dtype = np.float32 if pcm_format == capi.PCM_F32 else np.int16
+        from ..engine.pool import default_device
+        try:
+            self._engine = StreamEngine(model_version.value, max_streams=max_streams,
+                                        device=default_device() if device is None else device)
+        except Exception as exc:
+            raise VADError(f"Failed to initialize VAD processor: {exc}")
+        self.max_streams = max_streams
+        self._free = list(range(max_streams - 1, -1, -1))
+        self._streams: Dict[int, _Stream] = {}
+        self._lock = threading.Lock()
+
+    # ------------------------------------------------------------------ stream lifecycle
+    @property
+    def engine(self) -> StreamEngine:
+        return self._engine
+
+    def open_stream(self, config: Optional[VADConfig] = None, on_voice_start: Optional[Callable[[], None]] = None,
+                    on_voice_end: Optional[Callable[[bytes], None]] = None,
+                    on_voice_continue: Optional[Callable[[bytes], None]] = None) -> int:
+        cfg = config if config is not None else VADConfig()
+        if int(cfg.sample_rate) != 16000:
+            raise ConfigurationError("sample_rate", str(cfg.sample_rate),
+                                     "BatchedVADManager streams are 16 kHz; resample before push()")
+        with self._lock:
+            if not self._free:
+                raise VADError(f"all {self.max_streams} stream slots are in use")
+            sid = self._free.pop()
+            self._engine.reset([sid])
+            self._apply_config(sid, cfg)
+            self._streams[sid] = _Stream(
+                config=cfg, writer=WAVWriter(cfg.output_wav_sample_rate, cfg.output_wav_bit_depth, 1),
+                pending=np.zeros(0, self._dtype), on_start=on_voice_start, on_end=on_voice_end,
+                on_continue=on_voice_continue)
+            return sid
+
+    def _apply_config(self, sid: int, cfg: VADConfig) -> None:
+        self._engine.configure([sid], vad_start_probability=cfg.vad_start_probability,
+                               vad_end_probability=cfg.vad_end_probability,
+                               voice_start_frame_count=cfg.voice_start_frame_count,
+                               voice_end_frame_count=cfg.voice_end_frame_count,
+                               enable_denoising=cfg.enable_denoising)
+
+    def close_stream(self, stream_id: int) -> None:
+        with self._lock:
+            if self._streams.pop(stream_id, None) is not None:
+                self._engine.reset([stream_id])
+                self._free.append(stream_id)
+
+    def reset_stream(self, stream_id: int) -> None:
+        """VADProcessor.reset (silero_model.py:951-968) for one stream; buffered samples are dropped."""
+        with self._lock:
+            st = self._stream(stream_id)
+            self._engine.reset([stream_id])
+            st.pending = np.zeros(0, self._dtype)
+            st.active = False
+            st.pre_roll.clear()
+            st.segment.clear()
+
+    def update_config(self, stream_id: int, config: VADConfig) -> None:
+        with self._lock:
+            st = self._stream(stream_id)
+            st.config = config
+            st.writer = WAVWriter(config.output_wav_sample_rate, config.output_wav_bit_depth, 1)
+            self._apply_config(stream_id, config)
+        self.reset_stream(stream_id)
+
+    def _stream(self, stream_id: int) -> _Stream:
+        try:
+            return self._streams[stream_id]
+        except KeyError:
+            raise VADError(f"stream {stream_id} is not open")
+
+    def is_voice_active(self, stream_id: int) -> bool:
+        return self._stream(stream_id).active
+
+    @property
+    def open_streams(self) -> List[int]:
+        return sorted(self._streams)
+
+    # ------------------------------------------------------------------ data path
+    def push(self, stream_id: int, samples) -> None:
+        """Append audio to a stream's buffer (no GPU work).  NaN/Inf is rejected here, before any
+        state changes, as `AudioUtils.validate_audio_data` does (audio.py:227-228)."""
+        st = self._stream(stream_id)
+        x = np.asarray(samples)
+        if x.size == 0:
+            raise AudioProcessingError("Audio data is empty")
+        if x.ndim == 2:
+            x = x.mean(axis=1)
+        if self._dtype == np.float32:
+            x = x.astype(np.float32, copy=False)
+            if not np.isfinite(x).all():
+                raise AudioProcessingError("Audio data contains infinite or NaN values")
+        else:
+            x = x.astype(np.int16, copy=False)
+        st.pending = x.copy() if st.pending.size == 0 else np.concatenate([st.pending, x])
+
+    def _gate(self, st: _Stream, frame: np.ndarray) -> np.ndarray:
+        f = frame.astype(np.float32)
+        if self.pcm_format == capi.PCM_S16_32767:
+            f = f / np.float32(32767.0)
+        elif self.pcm_format == capi.PCM_S16_32768:
+            f = f / np.float32(32768.0)
+        if st.config.enable_denoising:
+            f = np.where(np.abs(f) > 0.01, f, 0.0).astype(np.float32)
+        return f
+
+    def step(self) -> StepOutput:
+        """Run every complete buffered frame of every open stream in one GPU step."""
+        with self._lock:
+            ids: List[int] = []
+            counts: List[int] = []
+            for sid, st in self._streams.items():
+                n = st.pending.size
+                if n >= self.frame_len:
+                    ids.append(sid)
+                    counts.append((n - self.frame_len) // self.hop + 1)
+            if not ids:
+                return StepOutput([], {}, 0)
+            tmax = max(counts)
+            row = (tmax - 1) * self.hop + self.frame_len
+            row += (-row) % 4
+            block = np.zeros((len(ids), row), self._dtype)
+            for k, sid in enumerate(ids):
+                p = self._streams[sid].pending
+                use = (counts[k] - 1) * self.hop + self.frame_len
+                block[k, :use] = p[:use]
+            r = self._engine.step(block, slots=ids, n_frames=counts, max_frames=tmax, frame_len=self.frame_len,
+                                  hop=self.hop, pcm_format=self.pcm_format)
+            events: List[StreamEvent] = []
+            probs: Dict[int, np.ndarray] = {}
+            for k, sid in enumerate(ids):
+                st = self._streams[sid]
+                if r.status[k]:
+                    st.pending = np.zeros(0, self._dtype)
+                    raise AudioProcessingError("Audio data contains infinite or NaN values")
+                probs[sid] = r.probs[k, :counts[k]].copy()
+            for (k, slot, j, kind, stream_frame) in r.events:
+                events.append(StreamEvent(slot, "start" if kind == capi.FLAG_STARTED else "end", stream_frame, j))
+            self._deliver(ids, counts, r.probs, r.flags)
+            for k, sid in enumerate(ids):
+                st = self._streams[sid]
+                st.pending = st.pending[counts[k] * self.hop:].copy()
+            return StepOutput(events, probs, int(sum(counts)))
+
+    def _deliver(self, ids: Sequence[int], counts: Sequence[int], probs: np.ndarray, flags: np.ndarray) -> None:
+        """Host side of the callbacks: segment assembly from the device's per-frame flags."""
+        for k, sid in enumerate(ids):
+            st = self._streams[sid]
+            fl_row = flags[k]
+            if not st.wants_audio and st.on_start is None:
+                last = counts[k] - 1
+                ended = np.flatnonzero(fl_row[:counts[k]] & 2)
+                started = np.flatnonzero(fl_row[:counts[k]] & 1)
+                if ended.size or started.size:
+                    st.active = (started.max() if started.size else -1) > (ended.max() if ended.size else -1)
+                else:
+                    st.active = bool(fl_row[last] & 4) if last >= 0 else st.active
+                continue
+            start_p = st.config.vad_start_probability
+            for j in range(counts[k]):
+                fl = int(fl_row[j])
+                frame = None
+                if st.wants_audio:
+                    if st.active or float(probs[k, j]) >= start_p:
+                        frame = self._gate(st, st.pending[j * self.hop: j * self.hop + self.frame_len])
+                if not st.active:
+                    if float(probs[k, j]) >= start_p:
+                        if frame is not None:
+                            st.pre_roll.append(frame)
+                        if fl & 1:
+                            st.segment = st.pre_roll
+                            st.pre_roll = []
+                            st.active = True
+                            self._call(st.on_start, "voice_start")
+                    else:
+                        st.pre_roll = []
+                else:
+                    if frame is not None:
+                        st.segment.append(frame)
+                    wav = None
+                    if fl & 2:
+                        if st.on_end is not None and st.segment:
+                            wav = st.writer.write_wav_data(np.concatenate(st.segment))
+                        st.segment = []
+                        st.active = False
+                    if wav:
+                        self._call(st.on_end, "voice_end", wav)
+                    if frame is not None:
+                        self._call(st.on_continue, "voice_continue", frame.tobytes())
+
+    @staticmethod
+    def _call(cb: Optional[Callable], name: str, *args) -> None:
+        if cb is None:
+            return
+        try:
+            cb(*args)
+        except Exception as exc:
+            raise CallbackError(name, exc)
+
+    # ------------------------------------------------------------------ lock-step block API
+    def step_block(self, audio: np.ndarray, stream_ids: Optional[Sequence[int]] = None):
+        """Lock-step fast path: `audio[k]` holds whole frames for stream `stream_ids[k]` (no buffering,
+        no callbacks).  -> engine StepResult (probs, flags, status, events)."""
+        ids = list(self.open_streams) if stream_ids is None else list(stream_ids)
+        with self._lock:
+            return self._engine.step(audio, slots=ids, frame_len=self.frame_len, hop=self.hop,
+                                     pcm_format=self.pcm_format)
+
+    def close(self) -> None:
+        with self._lock:
+            self._streams.clear()
+            self._engine.close()
+
+    def __enter__(self) -> "BatchedVADManager":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()

@@ -53,7 +53,8 @@ class _Scope:
 
 
 def _sigmoid(x):
-    return 1.0 / (1.0 + np.exp(-x))
+    with np.errstate(over="ignore"):
+        return 1.0 / (1.0 + np.exp(-x))
 
 
 class OnnxInterpreter:

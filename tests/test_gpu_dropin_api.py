@@ -1,0 +1,193 @@
+"""GPU: the reference-facing API on the CUDA engine vs golden vectors produced by the
+reference's unmodified Python (tests/golden/sample_voice.npz, oracle/make_golden.py).
+
+Bars: probabilities within 1e-4 absolute, events at identical frame indices, callback
+payloads (WAV bytes) identical."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, synth_streams
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _spy_wrapper(cfg):
+    from real_time_vad import VADWrapper
+    w = VADWrapper(cfg)
+    log = {"events": [], "wavs": [], "cont": 0}
+    w.set_callbacks(
+        voice_start_callback=lambda: log["events"].append((w._state.total_frames_processed, 1)),
+        voice_end_callback=lambda b: (log["events"].append((w._state.total_frames_processed, 2)), log["wavs"].append(b)),
+        voice_continue_callback=lambda b: log.__setitem__("cont", log["cont"] + 1))
+    return w, log
+
+
+@pytest.mark.parametrize("mode", ["A", "B", "C"])
+def test_vadwrapper_matches_reference_python_on_sample_voice(mode):
+    from real_time_vad import SampleRate, VADConfig
+    g = np.load(GOLDEN / "sample_voice.npz")
+    if mode == "A":
+        cfg = VADConfig(sample_rate=SampleRate.SAMPLERATE_16, buffer_size=480, vad_start_probability=0.4,
+                        vad_end_probability=0.3, voice_start_frame_count=6, voice_end_frame_count=12)
+        q = g["q16k"]
+        chunks = [q[i * 480:(i + 1) * 480].astype(np.float32) / 32767.0 for i in range(len(q) // 480)]
+    elif mode == "B":
+        cfg, chunks = VADConfig(), [g["y16k"]]
+    else:
+        cfg = VADConfig()
+        y = g["y16k"]
+        chunks = [y[i * 512:(i + 1) * 512] for i in range(len(y) // 512)]
+    w, log = _spy_wrapper(cfg)
+    assert w.processor.supports_batched() is True
+    probs = []
+    for c in chunks:
+        before = len(w.processor.voice_probabilities)
+        w.process_audio_data(c)
+        if mode != "B":
+            probs.append(w.processor.voice_probabilities[-1])
+    want_p = g[f"{mode}_probs"]
+    assert w.get_statistics()["total_frames_processed"] == len(want_p)
+    if mode == "B":
+        probs = list(w.processor.voice_probabilities)                  # deque(maxlen=100): the last 100
+        assert np.abs(np.array(probs) - want_p[-100:]).max() <= TOL
+    else:
+        assert np.abs(np.array(probs) - want_p).max() <= TOL
+    assert log["events"] == [tuple(e) for e in g[f"{mode}_events"].tolist()]
+    assert [len(b) for b in log["wavs"]] == g[f"{mode}_wav_len"].tolist()
+    assert [hashlib.sha256(b).hexdigest() for b in log["wavs"]] == g[f"{mode}_wav_sha"].tolist()
+    assert log["cont"] > 0
+    if mode == "A":
+        assert [k for _, k in log["events"]] == [1, 2] * 4               # the reference's 4-segment known answer
+    w.cleanup()
+
+
+def test_compat_session_run_equals_fast_path_and_oracle(ref_v5):
+    """`ort.InferenceSession.run` (state in / state out, like onnxruntime) vs the batched step."""
+    from real_time_vad.core.config import SileroModelVersion
+    from real_time_vad.core.silero_model import SileroVADModel
+    from conftest import V5_ONNX
+    g = np.load(GOLDEN / "v5_frames.npz")
+    m = SileroVADModel(str(V5_ONNX), SileroModelVersion.V5)
+    assert m.get_model_info()["has_cuda"] is True
+    for name in ("zeros", "sine440", "noise"):
+        m.reset()
+        got = [m.predict(g[f"in_{name}"], 16000) for _ in range(6)]
+        assert np.abs(np.array(got) - g[f"p_{name}"]).max() <= TOL
+        assert np.abs(m.model_state.state - g[f"state_{name}"]).max() <= 1e-3
+    assert m.prediction_count == 18
+    with pytest.raises(Exception, match="Model prediction failed"):
+        m.predict(g["in_noise"], 8000)                                   # only the 16 kHz branch exists
+
+
+def test_process_frame_and_batched_paths_interleave_consistently():
+    from real_time_vad import VADConfig, VADWrapper
+    x = synth_streams(1, 512 * 60, seed=31)[0]
+    cfg = VADConfig(vad_start_probability=0.5, vad_end_probability=0.35, voice_start_frame_count=3,
+                    voice_end_frame_count=4)
+    a, b = VADWrapper(cfg), VADWrapper(cfg)
+    ev_a, ev_b = [], []
+    a.set_callbacks(voice_start_callback=lambda: ev_a.append(("S", a._state.total_frames_processed)),
+                    voice_end_callback=lambda w_: ev_a.append(("E", a._state.total_frames_processed, len(w_))))
+    b.set_callbacks(voice_start_callback=lambda: ev_b.append(("S", b._state.total_frames_processed)),
+                    voice_end_callback=lambda w_: ev_b.append(("E", b._state.total_frames_processed, len(w_))))
+    a.process_audio_data(x)                                              # one batched call, hop 256
+    # b: alternate between the per-frame compat path and small batched calls over the same frames
+    pos, frames_done, k = 0, 0, 0
+    n_total = (len(x) - 512) // 256 + 1
+    while frames_done < n_total:
+        if k % 2 == 0:
+            r = b.processor.process_frame(x[pos:pos + 512].copy())
+            b._handle_callbacks(r)
+            b._state.total_frames_processed += 1
+            pos += 256
+            frames_done += 1
+        else:
+            take = min(5, n_total - frames_done)
+            b.process_audio_data(x[pos:pos + 512 + (take - 1) * 256])
+            pos += take * 256
+            frames_done += take
+        k += 1
+    assert ev_a == ev_b and len(ev_a) >= 2
+    pa, pb = np.array(a.processor.voice_probabilities), np.array(b.processor.voice_probabilities)
+    assert np.abs(pa - pb).max() <= 2e-6
+
+
+def test_batched_manager_equals_per_stream_wrappers(ref_v5, ref_lib):
+    from real_time_vad import BatchedVADManager, VADConfig
+    from vad_oracle import sm_run_c
+    n, T = 37, 90
+    audio = synth_streams(n, 512 * T, seed=41)
+    cfgs = [VADConfig(vad_start_probability=(0.4, 0.6)[s % 2], vad_end_probability=0.3,
+                      voice_start_frame_count=(3, 5)[s % 2], voice_end_frame_count=(4, 9)[(s // 2) % 2],
+                      enable_denoising=bool(s % 3)) for s in range(n)]
+    mgr = BatchedVADManager(max_streams=64, frame_len=512, hop=512)
+    logs = {}
+    ids = []
+    for s in range(n):
+        logs[s] = []
+        ids.append(mgr.open_stream(
+            cfgs[s], on_voice_start=(lambda s=s: logs[s].append(("S",))),
+            on_voice_end=(lambda b, s=s: logs[s].append(("E", len(b)))) if s % 2 == 0 else None))
+    rng = np.random.default_rng(5)
+    all_events, probs = [], {s: [] for s in range(n)}
+    pos = np.zeros(n, int)
+    while (pos < 512 * T).any():
+        for s in range(n):                                               # ragged, jittered arrival
+            if pos[s] < 512 * T:
+                k = int(rng.integers(100, 1500))
+                mgr.push(ids[s], audio[s, pos[s]:pos[s] + k])
+                pos[s] += k
+        out = mgr.step()
+        all_events += out.events
+        for sid, p in out.probabilities.items():
+            probs[ids.index(sid)].append(p)
+    n_ev = 0
+    for s in range(n):
+        got = np.concatenate(probs[s])
+        assert len(got) == T
+        want, _, _ = ref_v5.run(audio[s:s + 1], T, denoise=cfgs[s].enable_denoising)
+        assert np.abs(got - want[0]).max() <= TOL
+        c = cfgs[s]
+        fl, _ = sm_run_c(ref_lib, want[0], c.vad_start_probability, c.vad_end_probability, 0.8, 0.95,
+                         c.voice_start_frame_count, c.voice_end_frame_count)
+        want_ev = [(int(j), "start") for j in np.flatnonzero(fl & 1)] + [(int(j), "end") for j in np.flatnonzero(fl & 2)]
+        got_ev = [(e.frame_index, e.kind) for e in all_events if e.stream_id == ids[s]]
+        assert sorted(got_ev) == sorted(want_ev), s
+        n_ev += len(got_ev)
+        assert [e[0] for e in logs[s]].count("S") == sum(k == "start" for _, k in got_ev)
+        if s % 2 == 0:
+            assert [e[0] for e in logs[s]].count("E") == sum(k == "end" for _, k in got_ev)
+    assert n_ev > 20
+    # WAV payload of the first ended segment of an even stream == what a VADWrapper would deliver
+    from real_time_vad import VADWrapper
+    s = next(s for s in range(0, n, 2) if any(e[0] == "E" for e in logs[s]))
+    c = cfgs[s].model_copy(update={"buffer_size": 512})
+    w = VADWrapper(c)
+    w._DEFAULT_FRAME_OVERLAP_RATIO = 1.0                                   # hop == frame, like the manager
+    wavs = []
+    w.set_callbacks(voice_end_callback=lambda b: wavs.append(len(b)))
+    w.process_audio_data(audio[s])
+    assert wavs == [e[1] for e in logs[s] if e[0] == "E"]
+    mgr.close_stream(ids[0])
+    assert ids[0] not in mgr.open_streams
+    mgr.close()
+
+
+def test_manager_rejects_nonfinite_push_and_bad_config():
+    from real_time_vad import BatchedVADManager, SampleRate, VADConfig
+    from real_time_vad.core.exceptions import AudioProcessingError, ConfigurationError
+    mgr = BatchedVADManager(max_streams=8)
+    sid = mgr.open_stream()
+    with pytest.raises(AudioProcessingError, match="infinite or NaN"):
+        mgr.push(sid, np.array([0.1, np.inf], np.float32))
+    with pytest.raises(AudioProcessingError, match="empty"):
+        mgr.push(sid, np.zeros(0, np.float32))
+    with pytest.raises(ConfigurationError):
+        mgr.open_stream(VADConfig(sample_rate=SampleRate.SAMPLERATE_8))
+    mgr.push(sid, np.zeros(100, np.float32))
+    assert mgr.step().frames == 0                                         # less than one frame buffered
+    mgr.close()

@@ -1,0 +1,117 @@
+"""CPU: pin the oracle before trusting it.
+
+Golden vectors in tests/golden/ were produced by the reference's UNMODIFIED Python
+(/root/reference/src) running on the op-by-op ONNX interpreter (oracle/make_golden.py).
+They pin (a) the plain-C restatement used as the GPU checker and CPU baseline,
+(b) the state machine, against the expectations of the reference's own tests
+(tests/test_silero_model.py:542-614, :870-954), (c) framing (tests/test_audio_utils.py:138-168)
+and (d) the end-to-end known answer SampleVoiceMono.wav -> 4 segments
+(websocket_service/README.md:290).  Model arithmetic remains UNPINNED against real
+onnxruntime (absent from the image); see DESIGN.md.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, V5_ONNX
+
+from vad_oracle import StateMachine, events_from_flags, sm_run_c, split_into_frames
+
+
+def test_c_restatement_matches_reference_python_on_fixed_frames(ref_v5):
+    g = np.load(GOLDEN / "v5_frames.npz")
+    for name in ("zeros", "sine440", "noise"):
+        x = g[f"in_{name}"]
+        h = np.zeros(128, np.float32)
+        c = np.zeros(128, np.float32)
+        got = [ref_v5.frame(x, h, c)[0] for _ in range(6)]
+        assert np.abs(np.array(got) - g[f"p_{name}"]).max() <= 5e-6, name
+        st = g[f"state_{name}"]
+        assert np.abs(h - st[0, 0]).max() <= 2e-5 and np.abs(c - st[1, 0]).max() <= 1e-4
+
+
+def test_survey_probe_values_for_zero_frames():
+    """SURVEY.md section 8c lists these (hand restatement + interpreter agreed to all digits)."""
+    g = np.load(GOLDEN / "v5_frames.npz")
+    want = [0.0442627, 0.0336124, 0.0221236, 0.0163143, 0.0121521, 0.0092669]
+    assert np.abs(g["p_zeros"] - np.array(want)).max() < 2e-7
+
+
+def test_onnx_interpreter_fp32_vs_fp64_bound():
+    from onnx_interp import OnnxInterpreter
+    g = np.load(GOLDEN / "v5_frames.npz")
+    worst = 0.0
+    for dt in (np.float32, np.float64):
+        it = OnnxInterpreter(str(V5_ONNX), dt)
+        st = np.zeros((2, 1, 128), np.float32)
+        ps = []
+        for _ in range(6):
+            out, st = it.run({"input": g["in_noise"][None], "state": st.astype(np.float32),
+                              "sr": np.array([16000], np.int64)})
+            ps.append(float(out[0, 0]))
+        if dt is np.float32:
+            assert np.abs(np.array(ps) - g["p_noise"]).max() < 1e-7   # the golden IS this path
+            p32 = np.array(ps)
+        else:
+            worst = np.abs(np.array(ps) - p32).max()
+    assert worst < 1e-5
+
+
+@pytest.mark.parametrize("mode,frame_len,hop", [("A", 480, 480), ("B", 512, 256), ("C", 512, 512)])
+def test_sample_voice_known_answer_and_probabilities(ref_v5, ref_lib, mode, frame_len, hop):
+    g = np.load(GOLDEN / "sample_voice.npz")
+    if mode == "A":
+        x = g["q16k"].astype(np.float32) / np.float32(32767.0)
+        cfg = (0.4, 0.3, 0.8, 0.95, 6, 12)
+    else:
+        x = g["y16k"]
+        cfg = (0.7, 0.7, 0.8, 0.95, 10, 50)
+    want_p = g[f"{mode}_probs"]
+    T = len(want_p)
+    assert T == (len(x) - frame_len) // hop + 1 if mode != "A" else T == len(x) // 480
+    probs, _, _ = ref_v5.run(x[None, :], T, hop=hop, frame_len=frame_len, denoise=True)
+    assert np.abs(probs[0] - want_p).max() <= 2e-5
+    flags, _ = sm_run_c(ref_lib, probs[0], *cfg)
+    ev = [(i, 1 if k == "S" else 2) for i, k in events_from_flags(flags)]
+    assert ev == [tuple(e) for e in g[f"{mode}_events"].tolist()]
+    if mode == "A":
+        assert [k for _, k in ev] == [1, 2] * 4          # exactly 4 voice segments
+
+
+def test_state_machine_matches_reference_python_bit_exact(ref_lib):
+    g = np.load(GOLDEN / "state_machine.npz")
+    tags = sorted({k.rsplit("_", 1)[0] for k in g.files})
+    assert len(tags) >= 18
+    for tag in tags:
+        probs, want, cfg = g[f"{tag}_probs"], g[f"{tag}_flags"], g[f"{tag}_cfg"]
+        sp, ep, sr, er, ns, ne = cfg[0], cfg[1], cfg[2], cfg[3], int(cfg[4]), int(cfg[5])
+        got_c, _ = sm_run_c(ref_lib, probs, sp, ep, sr, er, ns, ne)
+        assert np.array_equal(got_c, want), tag
+        sm = StateMachine(sp, ep, sr, er, ns, ne)
+        got_py = np.array([sm.step(float(p)) for p in probs], np.uint8)
+        assert np.array_equal(got_py, want), tag
+
+
+def test_state_machine_reference_test_expectations(ref_lib):
+    """tests/test_silero_model.py:870-922: 5x0.1, 5x0.8 -> START on the 3rd voiced frame (index 7);
+    10x0.7 continuing; END on the 5th 0.2 (index 24)."""
+    probs = np.array([0.1] * 5 + [0.8] * 5 + [0.7] * 10 + [0.2] * 5, np.float32)
+    flags, _ = sm_run_c(ref_lib, probs, 0.7, 0.3, 0.8, 0.95, 3, 5)
+    assert events_from_flags(flags) == [(7, "S"), (24, "E")]
+    assert all(flags[i] & 4 for i in range(8, 25)) and not any(flags[i] & 4 for i in range(0, 8))
+    # caps of the two deques (silero_model.py:620-628): N_s > 20 never starts, N_e > 100 never ends
+    g = np.load(GOLDEN / "state_machine.npz")
+    assert not (g["cap20_flags"] & 1).any()
+    assert (g["cap100_flags"] & 1).any() and not (g["cap100_flags"] & 2).any()
+    assert (g["edge20_flags"] & 1).any() and (g["edge20_flags"] & 2).any()
+
+
+def test_framing_counts_like_the_reference():
+    """audio.py:183: n = (len - frame)//hop + 1; 256..511 -> 0 frames, 512..767 -> 1, 768 -> 2,
+    1..255 raises (negative dimension) -- SURVEY.md section 7 'Overlapped framing'."""
+    for n, want in ((256, 0), (511, 0), (512, 1), (767, 1), (768, 2), (960000, 3749)):
+        assert split_into_frames(np.zeros(n, np.float32), 512, 256).shape == (want, 512)
+    with pytest.raises(ValueError):
+        split_into_frames(np.zeros(255, np.float32), 512, 256)
+    x = np.arange(10, dtype=np.float32)
+    f = split_into_frames(x, 4, 2)
+    assert f.tolist() == [[0, 1, 2, 3], [2, 3, 4, 5], [4, 5, 6, 7], [6, 7, 8, 9]]
