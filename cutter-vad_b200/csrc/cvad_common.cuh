@@ -14,7 +14,9 @@
 namespace cvad {
 
 constexpr int kTile = 32;            // streams (items) per CTA tile
-constexpr int kThreads = 256;        // threads per CTA
+constexpr int kThreads = 512;        // threads per CTA (16 warps: 4 per scheduler)
+constexpr int kIG = 4;               // items per thread (one LDS.128 of the k-major activations)
+constexpr int kTM = kTile / kIG;     // 8 item groups per tile
 constexpr int kRingStages = 4;       // weight ring depth
 constexpr int kRingSlotFloats = 4096;// 16 KB per ring slot
 
@@ -81,32 +83,44 @@ __device__ __forceinline__ Dup4 dup4(const float4 &w) {
     return r;
 }
 
-// acc (8 items x 4 outputs) += a (8 items) (x) w (4 outputs)
-__device__ __forceinline__ void fma8x4(float2 (&acc)[4][4], const float4 &a0, const float4 &a1, const Dup4 &w) {
-    const float2 a[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
-                         make_float2(a1.z, a1.w)};
+// acc (4 items x 4 outputs) += a (4 items) (x) w (4 outputs): 8 FFMA2
+__device__ __forceinline__ void fma4x4(float2 (&acc)[2][4], const float4 &a, const Dup4 &w) {
+    const float2 a0 = make_float2(a.x, a.y), a1 = make_float2(a.z, a.w);
 #pragma unroll
-    for (int ip = 0; ip < 4; ++ip)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[ip][j] = __ffma2_rn(a[ip], w.d[j], acc[ip][j]);
+    for (int j = 0; j < 4; ++j) {
+        acc[0][j] = __ffma2_rn(a0, w.d[j], acc[0][j]);
+        acc[1][j] = __ffma2_rn(a1, w.d[j], acc[1][j]);
+    }
 }
 
-__device__ __forceinline__ void zero_tile(float2 (&acc)[4][4]) {
+__device__ __forceinline__ void zero_tile(float2 (&acc)[2][4]) {
 #pragma unroll
-    for (int ip = 0; ip < 4; ++ip)
+    for (int ip = 0; ip < 2; ++ip)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[ip][j] = make_float2(0.f, 0.f);
 }
 
 // view the paired accumulators as v[item][output] (pure register renaming)
-__device__ __forceinline__ void unpack_tile(const float2 (&acc)[4][4], float (&v)[8][4]) {
+__device__ __forceinline__ void unpack_tile(const float2 (&acc)[2][4], float (&v)[4][4]) {
 #pragma unroll
-    for (int ip = 0; ip < 4; ++ip)
+    for (int ip = 0; ip < 2; ++ip)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             v[2 * ip][j] = acc[ip][j].x;
             v[2 * ip + 1][j] = acc[ip][j].y;
         }
+}
+
+// column j of a 4x4 tile as a float4 over the 4 items
+__device__ __forceinline__ float4 col4(const float (&v)[4][4], int j) {
+    return make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
+}
+__device__ __forceinline__ float4 add4(const float4 &a, const float4 &b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 bias_relu4(const float4 &a, const float4 &b, float bias) {
+    return make_float4(fmaxf(a.x + b.x + bias, 0.f), fmaxf(a.y + b.y + bias, 0.f), fmaxf(a.z + b.z + bias, 0.f),
+                       fmaxf(a.w + b.w + bias, 0.f));
 }
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -10,12 +10,13 @@
 //
 // The front end has no dependence between frames, so it is batched over
 // (stream, frame) items; only the recurrent kernel walks frames in order.
-// One CTA owns a tile of 32 items; activations live in shared memory k-major
-// ([channel][time][item]) so that a thread's 8 items are one LDS.128 pair, and
-// each thread owns an 8-item x 4-output register tile for ALL time columns of
-// the layer, which lets the k=3 convolutions skip their zero-pad taps statically.
-// Arithmetic is FP32 FFMA with ascending-k accumulation (SURVEY.md section 0 fact 5:
-// plain TF32/BF16 operands miss the 1e-4 bar).
+// One CTA (512 threads) owns a tile of 32 items; activations live in shared memory
+// k-major ([channel][time][item]) so that a thread's 4 items are one LDS.128, and each
+// thread owns a 4-item x 4-output register tile for ALL time columns of the layer,
+// which lets the k=3 convolutions skip their zero-pad taps statically.  Small layers
+// split K over 2 or 4 thread groups and reduce through the output buffer.
+// Arithmetic is FP32 (packed FFMA2) with ascending-k accumulation (SURVEY.md section 0
+// fact 5: plain TF32/BF16 operands miss the 1e-4 bar).
 #pragma once
 #include "cvad_common.cuh"
 
@@ -132,6 +133,12 @@ __device__ __forceinline__ void block_copy_to_global(float *dst, const float *sr
 // =====================================================================================
 // Front end: frame loader -> STFT -> magnitude -> encoder.0..3 -> feat
 // =====================================================================================
+__device__ __forceinline__ void fe_release(WeightRing &ring, int tid) {
+    __syncthreads();
+    if (tid == 0) fe_ring_issue(ring, ring.g + kRingStages);
+    ++ring.g;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *ring_buf = reinterpret_cast<float *>(smem_raw);
@@ -144,7 +151,8 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int tm = tid & 3;  // 8-item group within the tile
+    const int tm = tid & 7;   // item group: items 4tm..4tm+3
+    const int tq = tid >> 3;  // 0..63
 
     WeightRing ring{ring_buf, bars, p.w_fe, 0u};
     if (tid == 0) {
@@ -189,8 +197,8 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
             const long long base = (long long)i * p.stride + (long long)frame * p.hop;
             bool bad = false;
 #pragma unroll 4
-            for (int it = 0; it < 16; ++it) {
-                const int q = it * 8 + warp;  // float4 index 0..127
+            for (int it = 0; it < 8; ++it) {
+                const int q = it * 16 + warp;  // float4 index 0..127
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
                 if (valid) {
                     const int k0 = 4 * q;
@@ -236,56 +244,43 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
         {
             const float *xT = bufA;
             float *magT = bufB;
-            const int tn = tid >> 2;  // 0..63 -> columns 4tn..4tn+3 = bins 2tn, 2tn+1
-            float2 acc2[3][4][4];
+            const int tn = tq;  // columns 4tn..4tn+3 = bins 2tn, 2tn+1
+            float2 acc2[3][2][4];
 #pragma unroll
             for (int t = 0; t < 3; ++t) zero_tile(acc2[t]);
 
             for (int ci = 0; ci < 16; ++ci) {
                 const float *w = ring_wait(ring);
-#pragma unroll 4
+                const float *xk = xT + (ci * 16) * kTile + 4 * tm;
+#pragma unroll 8
                 for (int kk = 0; kk < 16; ++kk) {
-                    const int k = ci * 16 + kk;
                     const Dup4 wv = dup4(ld4(w + kk * 256 + 4 * tn));
 #pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        const float *xr = xT + (128 * t + k) * kTile + 8 * tm;
-                        fma8x4(acc2[t], ld4(xr), ld4(xr + 4), wv);
-                    }
+                    for (int t = 0; t < 3; ++t) fma4x4(acc2[t], ld4(xk + (128 * t + kk) * kTile), wv);
                 }
-                __syncthreads();
-                if (tid == 0) fe_ring_issue(ring, ring.g + kRingStages);
-                ++ring.g;
+                fe_release(ring, tid);
             }
             // magnitude = sqrt(re^2 + im^2) with separately rounded squares (ONNX Pow, Pow, Add, Sqrt)
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
-                float acc[1][8][4];
-                unpack_tile(acc2[t], acc[0]);
-                float m0[8], m1[8], m2[8];
+                float v[4][4];
+                unpack_tile(acc2[t], v);
+                float m0[4], m1[4], m2[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float x = acc[0][i][0], y = acc[0][i][1], z = acc[0][i][2], w = acc[0][i][3];
+                for (int i = 0; i < 4; ++i) {
+                    const float x = v[i][0], y = v[i][1], z = v[i][2], w = v[i][3];
                     if (tn == 0) {
-                        m0[i] = sqrtf(__fmul_rn(x, x));                                 // bin 0   (im == 0)
-                        m2[i] = sqrtf(__fmul_rn(y, y));                                 // bin 128 (im == 0)
+                        m0[i] = sqrtf(__fmul_rn(x, x));                              // bin 0   (im == 0)
+                        m2[i] = sqrtf(__fmul_rn(y, y));                              // bin 128 (im == 0)
                     } else {
-                        m0[i] = sqrtf(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));     // bin 2tn
+                        m0[i] = sqrtf(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));  // bin 2tn
                         m2[i] = 0.f;
                     }
-                    m1[i] = sqrtf(__fadd_rn(__fmul_rn(z, z), __fmul_rn(w, w)));         // bin 2tn+1
+                    m1[i] = sqrtf(__fadd_rn(__fmul_rn(z, z), __fmul_rn(w, w)));      // bin 2tn+1
                 }
-                float *d0 = magT + ((2 * tn) * 3 + t) * kTile + 8 * tm;
-                float *d1 = magT + ((2 * tn + 1) * 3 + t) * kTile + 8 * tm;
-                st4(d0, make_float4(m0[0], m0[1], m0[2], m0[3]));
-                st4(d0 + 4, make_float4(m0[4], m0[5], m0[6], m0[7]));
-                st4(d1, make_float4(m1[0], m1[1], m1[2], m1[3]));
-                st4(d1 + 4, make_float4(m1[4], m1[5], m1[6], m1[7]));
-                if (tn == 0) {
-                    float *d2 = magT + (128 * 3 + t) * kTile + 8 * tm;
-                    st4(d2, make_float4(m2[0], m2[1], m2[2], m2[3]));
-                    st4(d2 + 4, make_float4(m2[4], m2[5], m2[6], m2[7]));
-                }
+                st4(magT + ((2 * tn) * 3 + t) * kTile + 4 * tm, make_float4(m0[0], m0[1], m0[2], m0[3]));
+                st4(magT + ((2 * tn + 1) * 3 + t) * kTile + 4 * tm, make_float4(m1[0], m1[1], m1[2], m1[3]));
+                if (tn == 0) st4(magT + (128 * 3 + t) * kTile + 4 * tm, make_float4(m2[0], m2[1], m2[2], m2[3]));
             }
         }
         __syncthreads();
@@ -295,9 +290,9 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
         {
             const float *magT = bufB;
             float *e0T = bufA;
-            const int tn = (tid >> 2) & 31;  // outputs 4tn..4tn+3
-            const int grp = tid >> 7;        // 0..1
-            float2 acc2[3][4][4];
+            const int tn = tq & 31;   // outputs 4tn..4tn+3
+            const int grp = tq >> 5;  // 0..1
+            float2 acc2[3][2][4];
 #pragma unroll
             for (int t = 0; t < 3; ++t) zero_tile(acc2[t]);
 
@@ -306,35 +301,26 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
                 const int cbase = ci * 10 + 5 * grp;
                 const int cnt = min(5, 129 - cbase);
                 for (int cc = 0; cc < cnt; ++cc) {
-                    const int c = cbase + cc;
                     const float *wl = w + ((5 * grp + cc) * 3) * 128 + 4 * tn;
                     const Dup4 w0 = dup4(ld4(wl)), w1 = dup4(ld4(wl + 128)), w2 = dup4(ld4(wl + 256));
-                    const float *ar = magT + (c * 3) * kTile + 8 * tm;
-                    const float4 a00 = ld4(ar), a01 = ld4(ar + 4);
-                    const float4 a10 = ld4(ar + kTile), a11 = ld4(ar + kTile + 4);
-                    const float4 a20 = ld4(ar + 2 * kTile), a21 = ld4(ar + 2 * kTile + 4);
+                    const float *ar = magT + ((cbase + cc) * 3) * kTile + 4 * tm;
+                    const float4 a0 = ld4(ar), a1 = ld4(ar + kTile), a2 = ld4(ar + 2 * kTile);
                     // out t: taps k with input time t+k-1 in [0,3)
-                    fma8x4(acc2[0], a00, a01, w1); fma8x4(acc2[0], a10, a11, w2);
-                    fma8x4(acc2[1], a00, a01, w0); fma8x4(acc2[1], a10, a11, w1); fma8x4(acc2[1], a20, a21, w2);
-                    fma8x4(acc2[2], a10, a11, w0); fma8x4(acc2[2], a20, a21, w1);
+                    fma4x4(acc2[0], a0, w1); fma4x4(acc2[0], a1, w2);
+                    fma4x4(acc2[1], a0, w0); fma4x4(acc2[1], a1, w1); fma4x4(acc2[1], a2, w2);
+                    fma4x4(acc2[2], a1, w0); fma4x4(acc2[2], a2, w1);
                 }
-                __syncthreads();
-                if (tid == 0) fe_ring_issue(ring, ring.g + kRingStages);
-                ++ring.g;
+                fe_release(ring, tid);
             }
-            float acc[3][8][4];
-#pragma unroll
-            for (int t = 0; t < 3; ++t) unpack_tile(acc2[t], acc[t]);
             // reduce the two K halves through the output buffer, add bias, ReLU
+            float v[3][4][4];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) unpack_tile(acc2[t], v[t]);
             if (grp == 1) {
 #pragma unroll
                 for (int t = 0; t < 3; ++t)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float *d = e0T + ((4 * tn + j) * 3 + t) * kTile + 8 * tm;
-                        st4(d, make_float4(acc[t][0][j], acc[t][1][j], acc[t][2][j], acc[t][3][j]));
-                        st4(d + 4, make_float4(acc[t][4][j], acc[t][5][j], acc[t][6][j], acc[t][7][j]));
-                    }
+                    for (int j = 0; j < 4; ++j) st4(e0T + ((4 * tn + j) * 3 + t) * kTile + 4 * tm, col4(v[t], j));
             }
             __syncthreads();
             if (grp == 0) {
@@ -343,14 +329,8 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
                     const float b = __ldg(p.b_fe + 4 * tn + j);
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
-                        float *d = e0T + ((4 * tn + j) * 3 + t) * kTile + 8 * tm;
-                        const float4 p0 = ld4(d), p1 = ld4(d + 4);
-                        float4 r0, r1;
-                        r0.x = fmaxf(acc[t][0][j] + p0.x + b, 0.f); r0.y = fmaxf(acc[t][1][j] + p0.y + b, 0.f);
-                        r0.z = fmaxf(acc[t][2][j] + p0.z + b, 0.f); r0.w = fmaxf(acc[t][3][j] + p0.w + b, 0.f);
-                        r1.x = fmaxf(acc[t][4][j] + p1.x + b, 0.f); r1.y = fmaxf(acc[t][5][j] + p1.y + b, 0.f);
-                        r1.z = fmaxf(acc[t][6][j] + p1.z + b, 0.f); r1.w = fmaxf(acc[t][7][j] + p1.w + b, 0.f);
-                        st4(d, r0); st4(d + 4, r1);
+                        float *d = e0T + ((4 * tn + j) * 3 + t) * kTile + 4 * tm;
+                        st4(d, bias_relu4(col4(v[t], j), ld4(d), b));
                     }
                 }
             }
@@ -362,12 +342,11 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
         {
             const float *e0T = bufA;
             float *e1T = bufB;
-            const int tn = (tid >> 2) & 15;  // outputs 4tn..4tn+3 of 64
-            const int grp = tid >> 6;        // 0..3
-            float2 acc2[2][4][4];
+            const int tn = tq & 15;   // outputs 4tn..4tn+3 of 64
+            const int grp = tq >> 4;  // 0..3
+            float2 acc2[2][2][4];
             zero_tile(acc2[0]);
             zero_tile(acc2[1]);
-
             for (int ci = 0; ci < 8; ++ci) {
                 const float *w = ring_wait(ring);
 #pragma unroll
@@ -375,34 +354,25 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
                     const int c = ci * 16 + 4 * grp + cc;
                     const float *wl = w + ((4 * grp + cc) * 3) * 64 + 4 * tn;
                     const Dup4 w0 = dup4(ld4(wl)), w1 = dup4(ld4(wl + 64)), w2 = dup4(ld4(wl + 128));
-                    const float *ar = e0T + (c * 3) * kTile + 8 * tm;
-                    const float4 a00 = ld4(ar), a01 = ld4(ar + 4);
-                    const float4 a10 = ld4(ar + kTile), a11 = ld4(ar + kTile + 4);
-                    const float4 a20 = ld4(ar + 2 * kTile), a21 = ld4(ar + 2 * kTile + 4);
+                    const float *ar = e0T + (c * 3) * kTile + 4 * tm;
+                    const float4 a0 = ld4(ar), a1 = ld4(ar + kTile), a2 = ld4(ar + 2 * kTile);
                     // out t' reads input time 2t'+k-1: t'=0 -> (k1,t0),(k2,t1); t'=1 -> (k0,t1),(k1,t2)
-                    fma8x4(acc2[0], a00, a01, w1); fma8x4(acc2[0], a10, a11, w2);
-                    fma8x4(acc2[1], a10, a11, w0); fma8x4(acc2[1], a20, a21, w1);
+                    fma4x4(acc2[0], a0, w1); fma4x4(acc2[0], a1, w2);
+                    fma4x4(acc2[1], a1, w0); fma4x4(acc2[1], a2, w1);
                 }
-                __syncthreads();
-                if (tid == 0) fe_ring_issue(ring, ring.g + kRingStages);
-                ++ring.g;
+                fe_release(ring, tid);
             }
-            float acc[2][8][4];
-            unpack_tile(acc2[0], acc[0]);
-            unpack_tile(acc2[1], acc[1]);
+            float v[2][4][4];
+            unpack_tile(acc2[0], v[0]);
+            unpack_tile(acc2[1], v[1]);
             for (int r = 1; r < 4; ++r) {
                 if (grp == r) {
 #pragma unroll
                     for (int t = 0; t < 2; ++t)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            float *d = e1T + ((4 * tn + j) * 2 + t) * kTile + 8 * tm;
-                            float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-                            if (r > 1) { p0 = ld4(d); p1 = ld4(d + 4); }
-                            st4(d, make_float4(acc[t][0][j] + p0.x, acc[t][1][j] + p0.y, acc[t][2][j] + p0.z,
-                                               acc[t][3][j] + p0.w));
-                            st4(d + 4, make_float4(acc[t][4][j] + p1.x, acc[t][5][j] + p1.y, acc[t][6][j] + p1.z,
-                                                   acc[t][7][j] + p1.w));
+                            float *d = e1T + ((4 * tn + j) * 2 + t) * kTile + 4 * tm;
+                            st4(d, r > 1 ? add4(col4(v[t], j), ld4(d)) : col4(v[t], j));
                         }
                 }
                 __syncthreads();
@@ -413,14 +383,8 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
                     const float b = __ldg(p.b_fe + 128 + 4 * tn + j);
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
-                        float *d = e1T + ((4 * tn + j) * 2 + t) * kTile + 8 * tm;
-                        const float4 p0 = ld4(d), p1 = ld4(d + 4);
-                        float4 r0, r1;
-                        r0.x = fmaxf(acc[t][0][j] + p0.x + b, 0.f); r0.y = fmaxf(acc[t][1][j] + p0.y + b, 0.f);
-                        r0.z = fmaxf(acc[t][2][j] + p0.z + b, 0.f); r0.w = fmaxf(acc[t][3][j] + p0.w + b, 0.f);
-                        r1.x = fmaxf(acc[t][4][j] + p1.x + b, 0.f); r1.y = fmaxf(acc[t][5][j] + p1.y + b, 0.f);
-                        r1.z = fmaxf(acc[t][6][j] + p1.z + b, 0.f); r1.w = fmaxf(acc[t][7][j] + p1.w + b, 0.f);
-                        st4(d, r0); st4(d + 4, r1);
+                        float *d = e1T + ((4 * tn + j) * 2 + t) * kTile + 4 * tm;
+                        st4(d, bias_relu4(col4(v[t], j), ld4(d), b));
                     }
                 }
             }
@@ -432,9 +396,9 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
         {
             const float *e1T = bufB;
             float *e2T = bufA;
-            const int tn = (tid >> 2) & 15;
-            const int grp = tid >> 6;
-            float2 acc2[4][4];
+            const int tn = tq & 15;
+            const int grp = tq >> 4;
+            float2 acc2[2][4];
             zero_tile(acc2);
             for (int ci = 0; ci < 2; ++ci) {
                 const float *w = ring_wait(ring);
@@ -443,25 +407,20 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
                     const int c = ci * 32 + 8 * grp + cc;
                     const float *wl = w + ((8 * grp + cc) * 2) * 64 + 4 * tn;
                     const Dup4 w1 = dup4(ld4(wl)), w2 = dup4(ld4(wl + 64));
-                    const float *ar = e1T + (c * 2) * kTile + 8 * tm;
-                    fma8x4(acc2, ld4(ar), ld4(ar + 4), w1);
-                    fma8x4(acc2, ld4(ar + kTile), ld4(ar + kTile + 4), w2);
+                    const float *ar = e1T + (c * 2) * kTile + 4 * tm;
+                    fma4x4(acc2, ld4(ar), w1);
+                    fma4x4(acc2, ld4(ar + kTile), w2);
                 }
-                __syncthreads();
-                if (tid == 0) fe_ring_issue(ring, ring.g + kRingStages);
-                ++ring.g;
+                fe_release(ring, tid);
             }
-            float acc[8][4];
-            unpack_tile(acc2, acc);
+            float v[4][4];
+            unpack_tile(acc2, v);
             for (int r = 1; r < 4; ++r) {
                 if (grp == r) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float *d = e2T + (4 * tn + j) * kTile + 8 * tm;
-                        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-                        if (r > 1) { p0 = ld4(d); p1 = ld4(d + 4); }
-                        st4(d, make_float4(acc[0][j] + p0.x, acc[1][j] + p0.y, acc[2][j] + p0.z, acc[3][j] + p0.w));
-                        st4(d + 4, make_float4(acc[4][j] + p1.x, acc[5][j] + p1.y, acc[6][j] + p1.z, acc[7][j] + p1.w));
+                        float *d = e2T + (4 * tn + j) * kTile + 4 * tm;
+                        st4(d, r > 1 ? add4(col4(v, j), ld4(d)) : col4(v, j));
                     }
                 }
                 __syncthreads();
@@ -470,14 +429,8 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float b = __ldg(p.b_fe + 192 + 4 * tn + j);
-                    float *d = e2T + (4 * tn + j) * kTile + 8 * tm;
-                    const float4 p0 = ld4(d), p1 = ld4(d + 4);
-                    float4 r0, r1;
-                    r0.x = fmaxf(acc[0][j] + p0.x + b, 0.f); r0.y = fmaxf(acc[1][j] + p0.y + b, 0.f);
-                    r0.z = fmaxf(acc[2][j] + p0.z + b, 0.f); r0.w = fmaxf(acc[3][j] + p0.w + b, 0.f);
-                    r1.x = fmaxf(acc[4][j] + p1.x + b, 0.f); r1.y = fmaxf(acc[5][j] + p1.y + b, 0.f);
-                    r1.z = fmaxf(acc[6][j] + p1.z + b, 0.f); r1.w = fmaxf(acc[7][j] + p1.w + b, 0.f);
-                    st4(d, r0); st4(d + 4, r1);
+                    float *d = e2T + (4 * tn + j) * kTile + 4 * tm;
+                    st4(d, bias_relu4(col4(v, j), ld4(d), b));
                 }
             }
         }
@@ -488,9 +441,9 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
         {
             const float *e2T = bufA;
             float *scratch = bufB;
-            const int tn = (tid >> 2) & 31;
-            const int grp = tid >> 7;
-            float2 acc2[4][4];
+            const int tn = tq & 31;
+            const int grp = tq >> 5;
+            float2 acc2[2][4];
             zero_tile(acc2);
             for (int ci = 0; ci < 2; ++ci) {
                 const float *w = ring_wait(ring);
@@ -498,22 +451,15 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
                 for (int cc = 0; cc < 16; ++cc) {
                     const int c = ci * 32 + 16 * grp + cc;
                     const Dup4 wv = dup4(ld4(w + (16 * grp + cc) * 128 + 4 * tn));
-                    const float *ar = e2T + c * kTile + 8 * tm;
-                    fma8x4(acc2, ld4(ar), ld4(ar + 4), wv);
+                    fma4x4(acc2, ld4(e2T + c * kTile + 4 * tm), wv);
                 }
-                __syncthreads();
-                if (tid == 0) fe_ring_issue(ring, ring.g + kRingStages);
-                ++ring.g;
+                fe_release(ring, tid);
             }
-            float acc[8][4];
-            unpack_tile(acc2, acc);
+            float v[4][4];
+            unpack_tile(acc2, v);
             if (grp == 1) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float *d = scratch + (4 * tn + j) * kTile + 8 * tm;
-                    st4(d, make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]));
-                    st4(d + 4, make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]));
-                }
+                for (int j = 0; j < 4; ++j) st4(scratch + (4 * tn + j) * kTile + 4 * tm, col4(v, j));
             }
             __syncthreads();
             if (grp == 0) {
@@ -521,19 +467,10 @@ __global__ void __launch_bounds__(kThreads, 1) v5_frontend_kernel(const V5Step p
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float b = __ldg(p.b_fe + 256 + 4 * tn + j);
-                    const float *d = scratch + (4 * tn + j) * kTile + 8 * tm;
-                    const float4 p0 = ld4(d), p1 = ld4(d + 4);
-                    float4 r0, r1;
-                    r0.x = fmaxf(acc[0][j] + p0.x + b, 0.f); r0.y = fmaxf(acc[1][j] + p0.y + b, 0.f);
-                    r0.z = fmaxf(acc[2][j] + p0.z + b, 0.f); r0.w = fmaxf(acc[3][j] + p0.w + b, 0.f);
-                    r1.x = fmaxf(acc[4][j] + p1.x + b, 0.f); r1.y = fmaxf(acc[5][j] + p1.y + b, 0.f);
-                    r1.z = fmaxf(acc[6][j] + p1.z + b, 0.f); r1.w = fmaxf(acc[7][j] + p1.w + b, 0.f);
-                    float *g = fout + (4 * tn + j) * kTile + 8 * tm;
-                    st4(g, r0); st4(g + 4, r1);
-                    if (p.dbg && tile == 0) {
-                        float *dg = p.dbg + kDbgMag + kDbgE0 + kDbgE1 + kDbgE2 + (4 * tn + j) * kTile + 8 * tm;
-                        st4(dg, r0); st4(dg + 4, r1);
-                    }
+                    const float4 r = bias_relu4(col4(v, j), ld4(scratch + (4 * tn + j) * kTile + 4 * tm), b);
+                    st4(fout + (4 * tn + j) * kTile + 4 * tm, r);
+                    if (p.dbg && tile == 0)
+                        st4(p.dbg + kDbgMag + kDbgE0 + kDbgE1 + kDbgE2 + (4 * tn + j) * kTile + 4 * tm, r);
                 }
             }
         }
@@ -569,8 +506,8 @@ __global__ void __launch_bounds__(kThreads, 1) v5_recurrent_kernel(const V5Step 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int tm = tid & 3;
-    const int tn = tid >> 2;  // 0..63: hidden units 2tn, 2tn+1 (packed columns 8tn..8tn+7)
+    const int tm = tid & 7;   // items 4tm..4tm+3
+    const int tn = tid >> 3;  // 0..63: hidden units 2tn, 2tn+1 (packed columns 8tn..8tn+7)
     const int st = blockIdx.x;
     const int ms = p.max_streams;
 
@@ -619,10 +556,10 @@ __global__ void __launch_bounds__(kThreads, 1) v5_recurrent_kernel(const V5Step 
         const int slot = s_slot[s];
         hbuf[idx] = slot >= 0 ? p.h_state[(size_t)u * ms + slot] : 0.f;
     }
-    float creg[8][2];
+    float creg[4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int slot = s_slot[8 * tm + i];
+    for (int i = 0; i < 4; ++i) {
+        const int slot = s_slot[4 * tm + i];
 #pragma unroll
         for (int u = 0; u < 2; ++u) creg[i][u] = slot >= 0 ? p.c_state[(size_t)(2 * tn + u) * ms + slot] : 0.f;
     }
@@ -648,20 +585,19 @@ __global__ void __launch_bounds__(kThreads, 1) v5_recurrent_kernel(const V5Step 
         const float *xb = xbuf + (j & 1) * 4096;
         mbar_wait(&xbars[j & 1], (uint32_t)(j >> 1) & 1u);
 
-        float2 acc2[2][4][4];  // [column half][item pair][column]
+        float2 acc2[2][2][4];  // [column half][item pair][column]
         zero_tile(acc2[0]);
         zero_tile(acc2[1]);
 
         for (int ci = 0; ci < kRecChunks; ++ci) {
             const float *w = ring_wait(ring);
-            const float *abase = (ci < 16) ? (xb + ci * 8 * kTile) : (hbuf + (ci - 16) * 8 * kTile);
+            const float *abase = ((ci < 16) ? (xb + ci * 8 * kTile) : (hbuf + (ci - 16) * 8 * kTile)) + 4 * tm;
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
-                const float *ar = abase + kk * kTile + 8 * tm;
-                const float4 a0 = ld4(ar), a1 = ld4(ar + 4);
+                const float4 a = ld4(abase + kk * kTile);
                 const Dup4 w0 = dup4(ld4(w + kk * 512 + 8 * tn)), w1 = dup4(ld4(w + kk * 512 + 8 * tn + 4));
-                fma8x4(acc2[0], a0, a1, w0);
-                fma8x4(acc2[1], a0, a1, w1);
+                fma4x4(acc2[0], a, w0);
+                fma4x4(acc2[1], a, w1);
             }
             __syncthreads();
             if (tid == 0) rec_ring_issue(ring, ring.g + kRingStages);
@@ -674,27 +610,21 @@ __global__ void __launch_bounds__(kThreads, 1) v5_recurrent_kernel(const V5Step 
                      &xbars[j & 1]);
         }
         // LSTM cell (PyTorch LSTMCell == ONNX LSTM with both biases added)
-        float acc[8][8];
-        {
-            float v0[8][4], v1[8][4];
-            unpack_tile(acc2[0], v0);
-            unpack_tile(acc2[1], v1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { acc[i][c] = v0[i][c]; acc[i][4 + c] = v1[i][c]; }
-        }
+        float g0[4][4], g1[4][4];
+        unpack_tile(acc2[0], g0);
+        unpack_tile(acc2[1], g1);
         const float bi[8] = {bia0.x, bia0.y, bia0.z, bia0.w, bia1.x, bia1.y, bia1.z, bia1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = 8 * tm + i;
+        for (int i = 0; i < 4; ++i) {
+            const int row = 4 * tm + i;
             const bool live = j < s_nfr[row];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const float ig = sigmoid_f(acc[i][4 * u + 0] + bi[4 * u + 0]);
-                const float fg = sigmoid_f(acc[i][4 * u + 1] + bi[4 * u + 1]);
-                const float gg = tanhf(acc[i][4 * u + 2] + bi[4 * u + 2]);
-                const float og = sigmoid_f(acc[i][4 * u + 3] + bi[4 * u + 3]);
+                const float (&g)[4][4] = u == 0 ? g0 : g1;
+                const float ig = sigmoid_f(g[i][0] + bi[4 * u + 0]);
+                const float fg = sigmoid_f(g[i][1] + bi[4 * u + 1]);
+                const float gg = tanhf(g[i][2] + bi[4 * u + 2]);
+                const float og = sigmoid_f(g[i][3] + bi[4 * u + 3]);
                 const float cn = __fadd_rn(__fmul_rn(fg, creg[i][u]), __fmul_rn(ig, gg));
                 const float hn = og * tanhf(cn);
                 if (live) {
@@ -760,9 +690,9 @@ __global__ void __launch_bounds__(kThreads, 1) v5_recurrent_kernel(const V5Step 
             if (slot >= 0 && s_nfr[s] > 0) p.h_state[(size_t)u * ms + slot] = hbuf[idx];
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int slot = s_slot[8 * tm + i];
-            if (slot >= 0 && s_nfr[8 * tm + i] > 0) {
+        for (int i = 0; i < 4; ++i) {
+            const int slot = s_slot[4 * tm + i];
+            if (slot >= 0 && s_nfr[4 * tm + i] > 0) {
 #pragma unroll
                 for (int u = 0; u < 2; ++u) p.c_state[(size_t)(2 * tn + u) * ms + slot] = creg[i][u];
             }
