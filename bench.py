@@ -43,6 +43,26 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def ncu_traffic_bytes(kernel: str):
+    """DRAM read+write bytes per launch of `kernel` from the newest committed ncu --set full summary
+    (profiles/*.json, written by tools/ncu_summary.py from the same bench command); None if absent."""
+    best = None
+    for f in sorted((ROOT / "profiles").glob("*.json")):
+        try:
+            d = json.loads(f.read_text())
+            for k in d.get("full_capture", []):
+                if kernel in k.get("kernel", ""):
+                    tot = 0.0
+                    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                        val, _, unit = k.get(key, "0 byte").partition(" ")
+                        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit.strip(), 1)
+                        tot += float(val) * mult
+                    best = {"bytes": tot, "source": f"profiles/{f.name}"}
+        except Exception:
+            continue
+    return best
+
+
 def synth_audio(n_streams: int, n_samples: int, seed: int) -> np.ndarray:
     """Vectorised version of the tests' signal recipe: per-stream noise floor plus gated
     harmonic 'voice' bursts (reference examples/probability_demo.py:60-67), float32."""
@@ -289,7 +309,6 @@ def run_ours(args):
         a1.record(stream)
         a1.synchronize()
         lat.append(a0.elapsed_time(a1))
-    clocks = sampler.stop()
 
     # ================= end to end (`e2e`): public host-buffer call, H2D + D2H inside the timed region
     eng.reset()
@@ -306,6 +325,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_events = len(r.events)
+    clocks = sampler.stop()
 
     times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
@@ -325,6 +345,7 @@ def run_ours(args):
     step_tflops = frames_per_step * FLOP_FRAME / (dev_ms / args.steps * 1e-3) / 1e12
 
     if rank == 0:
+        traffic = ncu_traffic_bytes("v5_frontend_kernel") if (n == 4096 and F == 1) else None
         cpu = None if args.skip_cpu else cpu_baseline_sample(n)
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
@@ -335,7 +356,9 @@ def run_ours(args):
             "frames_per_s": value / 0.032,
             "roofline": {
                 "bound": "fp32_ffma", "kernel": "v5_frontend_kernel", "achieved": fe_tflops, "peak": peak_fp32,
-                "unit": "TFLOP/s", "frac": fe_tflops / peak_fp32, "traffic": None,
+                "unit": "TFLOP/s", "frac": fe_tflops / peak_fp32,
+                "traffic": (traffic or {}).get("bytes"), "traffic_source": (traffic or {}).get("source"),
+                "algorithmic_bytes_per_launch": frames_per_step * 2048 + 156032 * 4 + frames_per_step * 512,
                 "peak_source": f"148 SMs x 128 FP32 lanes x 2 x sm_max_mhz {sm_max:.0f} ({peaks_src} "
                                "MEASURED_PEAKS.json clock); the path is FP32-FFMA bound, not HBM or tensor bound",
                 "algorithmic_flop_per_frame": FLOP_FRONTEND, "frames_per_launch": frames_per_step,
@@ -366,8 +389,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
     ap.add_argument("--frames-per-step", type=int, default=1, help="512-sample frames per stream per step")
