@@ -44,11 +44,20 @@ struct cvad_engine {
     double *start_p = nullptr, *end_p = nullptr;
     int *n_start = nullptr, *n_end = nullptr;
     unsigned char *denoise = nullptr;
-    // scratch (device)
-    DevBuf d_audio, d_slots, d_nframes, d_probs, d_flags, d_status, d_events, d_feat, d_dbg;
-    int *d_nevents = nullptr;
-    // pinned staging (host)
-    DevBuf h_in, h_out;
+    // scratch shared by every step (kernels of consecutive steps are serialised by `last_done`)
+    DevBuf d_status_dev, d_feat, d_dbg, d_cfg_slots;
+    cudaEvent_t last_done = nullptr;   // recorded after the kernels of the most recent step
+    // host-buffer steps run on two lanes so that step i+1's H2D overlaps step i's kernels
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        DevBuf d_audio, d_slots, d_nframes, d_probs, d_flags, d_status, d_events;
+        int *d_nevents = nullptr;
+        DevBuf h_in, h_out;             // pinned staging
+        bool busy = false;
+        cvad_step_args args{};          // caller's (host) argument block of the step in flight
+        std::vector<int32_t> nfr_copy;  // n_frames as submitted (caller may reuse its array)
+    } lanes[2];
+    int next_lane = 0;
     // optional per-kernel timing (bench): event triples (before FE, between, after REC)
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -200,8 +209,11 @@ int validate_args(cvad_engine *e, const cvad_step_args *a) {
 }
 
 // Enqueue the two kernels.  Every pointer in `a` is a DEVICE pointer here.
-int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status, int commit, float *d_dbg) {
+int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status, int commit, float *d_dbg,
+                cudaStream_t stream) {
     if (a->n_streams == 0 || a->max_frames == 0) return CVAD_OK;
+    // state and `feat` are shared: kernels of consecutive steps never overlap, whatever stream they use
+    CU_TRY(e, cudaStreamWaitEvent(stream, e->last_done, 0));
     const int n_stiles = (a->n_streams + cvad::kTile - 1) / cvad::kTile;
     const size_t feat_bytes = (size_t)a->max_frames * n_stiles * 128 * cvad::kTile * sizeof(float);
     int rc = grow(e, e->d_feat, feat_bytes);
@@ -250,18 +262,19 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         }
         for (int i = 0; i < 3; ++i) ev[i] = e->ev_pool[e->ev_used + i];
         e->ev_used += 3;
-        CU_TRY(e, cudaEventRecord(ev[0], e->stream));
+        CU_TRY(e, cudaEventRecord(ev[0], stream));
     }
-    cvad::v5_frontend_kernel<<<grid_fe, cvad::kThreads, cvad::kFeSmemBytes, e->stream>>>(p);
+    cvad::v5_frontend_kernel<<<grid_fe, cvad::kThreads, cvad::kFeSmemBytes, stream>>>(p);
     CU_TRY(e, cudaGetLastError());
     e->launches++;
-    if (timed) CU_TRY(e, cudaEventRecord(ev[1], e->stream));
+    if (timed) CU_TRY(e, cudaEventRecord(ev[1], stream));
     if (!d_dbg) {
-        cvad::v5_recurrent_kernel<<<n_stiles, cvad::kThreads, cvad::kRecSmemBytes, e->stream>>>(p);
+        cvad::v5_recurrent_kernel<<<n_stiles, cvad::kThreads, cvad::kRecSmemBytes, stream>>>(p);
         CU_TRY(e, cudaGetLastError());
         e->launches++;
     }
-    if (timed) CU_TRY(e, cudaEventRecord(ev[2], e->stream));
+    if (timed) CU_TRY(e, cudaEventRecord(ev[2], stream));
+    CU_TRY(e, cudaEventRecord(e->last_done, stream));
     return CVAD_OK;
 }
 
@@ -295,116 +308,151 @@ int stage_slots(cvad_engine *e, int n, const int32_t *slots, const int **d_slots
     if (!slots) return CVAD_OK;
     for (int i = 0; i < n; ++i)
         if (slots[i] < 0 || slots[i] >= e->max_streams) return fail(e, CVAD_E_CAPACITY, "slot id out of range");
-    int rc = grow(e, e->d_slots, (size_t)std::max(n, 1) * sizeof(int));
+    int rc = grow(e, e->d_cfg_slots, (size_t)std::max(n, 1) * sizeof(int));
     if (rc) return rc;
-    CU_TRY(e, cudaMemcpyAsync(e->d_slots.p, slots, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(e, cudaMemcpyAsync(e->d_cfg_slots.p, slots, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     CU_TRY(e, cudaStreamSynchronize(e->stream));  // `slots` is pageable caller memory
-    *d_slots = static_cast<const int *>(e->d_slots.p);
+    *d_slots = static_cast<const int *>(e->d_cfg_slots.p);
     return CVAD_OK;
 }
 }  // namespace
 
 namespace {
-// Host-buffer step; `dbg_out` != nullptr turns it into the debug dump (front end only, no commit).
-int step_host(cvad_engine *e, const cvad_step_args *a, float *dbg_out, size_t dbg_floats) {
+
+int quiesce(cvad_engine *e) {
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    for (auto &ln : e->lanes) CU_TRY(e, cudaStreamSynchronize(ln.stream));
+    return CVAD_OK;
+}
+
+// Enqueue one host-buffer step on `ln` (H2D, kernels, D2H) without waiting for it.
+// `dbg_out` != nullptr turns it into the debug dump (front end only, no commit).
+int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, float *dbg_out, size_t dbg_floats) {
     int rc = validate_args(e, a);
     if (rc) return rc;
     CU_TRY(e, cudaSetDevice(e->device));
     const int n = a->n_streams, T = a->max_frames;
-    if (a->n_events_out) *a->n_events_out = 0;
+    ln.args = *a;
+    ln.nfr_copy.clear();
+    ln.busy = true;
     if (n == 0 || T == 0) return CVAD_OK;
     if (a->slots) {
         for (int i = 0; i < n; ++i)
-            if (a->slots[i] < 0 || a->slots[i] >= e->max_streams)
+            if (a->slots[i] < 0 || a->slots[i] >= e->max_streams) {
+                ln.busy = false;
                 return fail(e, CVAD_E_CAPACITY, "slot id out of range");
+            }
     }
     if (a->n_frames) {
         for (int i = 0; i < n; ++i)
-            if (a->n_frames[i] < 0 || a->n_frames[i] > T)
+            if (a->n_frames[i] < 0 || a->n_frames[i] > T) {
+                ln.busy = false;
                 return fail(e, CVAD_E_INVALID, "n_frames[i] outside [0, max_frames]");
+            }
+        ln.nfr_copy.assign(a->n_frames, a->n_frames + n);
     }
     const size_t es = elem_size(a->pcm_format);
     const size_t row = (size_t)(T - 1) * a->hop + a->frame_len;
-    if (n > 1 && (a->stream_stride < 0 || (size_t)a->stream_stride < row))
+    if (n > 1 && (a->stream_stride < 0 || (size_t)a->stream_stride < row)) {
+        ln.busy = false;
         return fail(e, CVAD_E_INVALID, "stream_stride shorter than (max_frames-1)*hop + frame_len");
+    }
     const size_t audio_elems = (size_t)(n - 1) * a->stream_stride + row;
     const size_t audio_bytes = audio_elems * es;
+    auto bail = [&](int code) { ln.busy = false; return code; };
 
-    // ---- device scratch
-    if ((rc = grow(e, e->d_audio, audio_bytes + 16)) || (rc = grow(e, e->d_slots, (size_t)n * 4)) ||
-        (rc = grow(e, e->d_nframes, (size_t)n * 4)) || (rc = grow(e, e->d_probs, (size_t)n * T * 4)) ||
-        (rc = grow(e, e->d_flags, (size_t)n * T)) || (rc = grow(e, e->d_status, (size_t)n * 4)) ||
-        (rc = grow(e, e->d_events, (size_t)std::max(a->max_events, 1) * sizeof(cvad_event))))
-        return rc;
+    // ---- device scratch of this lane
+    if ((rc = grow(e, ln.d_audio, audio_bytes + 16)) || (rc = grow(e, ln.d_slots, (size_t)n * 4)) ||
+        (rc = grow(e, ln.d_nframes, (size_t)n * 4)) || (rc = grow(e, ln.d_probs, (size_t)n * T * 4)) ||
+        (rc = grow(e, ln.d_flags, (size_t)n * T)) || (rc = grow(e, ln.d_status, (size_t)n * 4)) ||
+        (rc = grow(e, ln.d_events, (size_t)std::max(a->max_events, 1) * sizeof(cvad_event))))
+        return bail(rc);
 
-    // ---- host -> device (pinned memory goes straight; pageable memory is staged)
+    // ---- host -> device (pinned caller memory goes straight; pageable memory is staged)
     const size_t small_in = (size_t)n * 8;
-    if ((rc = grow_host(e, e->h_in, audio_bytes + small_in + 64))) return rc;
-    unsigned char *hin = static_cast<unsigned char *>(e->h_in.p);
+    const bool direct = is_host_pinned_or_device(a->audio, false);
+    if ((rc = grow_host(e, ln.h_in, (direct ? 0 : audio_bytes) + small_in + 128))) return bail(rc);
+    unsigned char *hin = static_cast<unsigned char *>(ln.h_in.p);
     int *h_slots = reinterpret_cast<int *>(hin);
     int *h_nfr = h_slots + n;
     if (a->slots) std::memcpy(h_slots, a->slots, (size_t)n * 4);
     if (a->n_frames) std::memcpy(h_nfr, a->n_frames, (size_t)n * 4);
     const void *src_audio = a->audio;
-    if (!is_host_pinned_or_device(a->audio, false)) {
+    if (!direct) {
         unsigned char *stage = hin + ((small_in + 63) / 64) * 64;
         std::memcpy(stage, a->audio, audio_bytes);
         src_audio = stage;
     }
-    CU_TRY(e, cudaMemcpyAsync(e->d_audio.p, src_audio, audio_bytes, cudaMemcpyHostToDevice, e->stream));
-    if (a->slots) CU_TRY(e, cudaMemcpyAsync(e->d_slots.p, h_slots, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
-    if (a->n_frames) CU_TRY(e, cudaMemcpyAsync(e->d_nframes.p, h_nfr, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
-    CU_TRY(e, cudaMemsetAsync(e->d_status.p, 0, (size_t)n * 4, e->stream));
-    CU_TRY(e, cudaMemsetAsync(e->d_nevents, 0, sizeof(int), e->stream));
+    cudaStream_t st = ln.stream;
+    CU_TRY(e, cudaMemcpyAsync(ln.d_audio.p, src_audio, audio_bytes, cudaMemcpyHostToDevice, st));
+    if (a->slots) CU_TRY(e, cudaMemcpyAsync(ln.d_slots.p, h_slots, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (a->n_frames) CU_TRY(e, cudaMemcpyAsync(ln.d_nframes.p, h_nfr, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(e, cudaMemsetAsync(ln.d_status.p, 0, (size_t)n * 4, st));
+    CU_TRY(e, cudaMemsetAsync(ln.d_nevents, 0, sizeof(int), st));
 
     cvad_step_args d = *a;
-    d.audio = e->d_audio.p;
-    d.slots = a->slots ? static_cast<const int32_t *>(e->d_slots.p) : nullptr;
-    d.n_frames = a->n_frames ? static_cast<const int32_t *>(e->d_nframes.p) : nullptr;
-    d.probs_out = static_cast<float *>(e->d_probs.p);
-    d.flags_out = static_cast<uint8_t *>(e->d_flags.p);
+    d.audio = ln.d_audio.p;
+    d.slots = a->slots ? static_cast<const int32_t *>(ln.d_slots.p) : nullptr;
+    d.n_frames = a->n_frames ? static_cast<const int32_t *>(ln.d_nframes.p) : nullptr;
+    d.probs_out = static_cast<float *>(ln.d_probs.p);
+    d.flags_out = static_cast<uint8_t *>(ln.d_flags.p);
     d.status_out = nullptr;
-    d.events_out = static_cast<cvad_event *>(e->d_events.p);
-    d.n_events_out = e->d_nevents;
+    d.events_out = static_cast<cvad_event *>(ln.d_events.p);
+    d.n_events_out = ln.d_nevents;
 
     float *d_dbg = nullptr;
     if (dbg_out) {
-        if (dbg_floats < (size_t)cvad::kDbgFloats) return fail(e, CVAD_E_CAPACITY, "dbg_out too small");
-        if ((rc = grow(e, e->d_dbg, (size_t)cvad::kDbgFloats * 4))) return rc;
+        if (dbg_floats < (size_t)cvad::kDbgFloats) return bail(fail(e, CVAD_E_CAPACITY, "dbg_out too small"));
+        if ((rc = grow(e, e->d_dbg, (size_t)cvad::kDbgFloats * 4))) return bail(rc);
         d_dbg = static_cast<float *>(e->d_dbg.p);
-        CU_TRY(e, cudaMemsetAsync(d_dbg, 0, (size_t)cvad::kDbgFloats * 4, e->stream));
+        CU_TRY(e, cudaMemsetAsync(d_dbg, 0, (size_t)cvad::kDbgFloats * 4, st));
     }
-    rc = launch_step(e, &d, static_cast<unsigned int *>(e->d_status.p), dbg_out ? 0 : 1, d_dbg);
-    if (rc) return rc;
-
+    rc = launch_step(e, &d, static_cast<unsigned int *>(ln.d_status.p), dbg_out ? 0 : 1, d_dbg, st);
+    if (rc) return bail(rc);
     if (dbg_out) {
-        CU_TRY(e, cudaMemcpyAsync(dbg_out, d_dbg, (size_t)cvad::kDbgFloats * 4, cudaMemcpyDeviceToHost, e->stream));
-        CU_TRY(e, cudaStreamSynchronize(e->stream));
-        return cvad::kDbgFloats;
+        CU_TRY(e, cudaMemcpyAsync(dbg_out, d_dbg, (size_t)cvad::kDbgFloats * 4, cudaMemcpyDeviceToHost, st));
+        return CVAD_OK;
     }
 
-    // ---- device -> host
+    // ---- device -> host into this lane's pinned block (unpacked by step_collect)
     const size_t probs_b = (size_t)n * T * 4, flags_b = (size_t)n * T, status_b = (size_t)n * 4;
     const size_t ev_b = (size_t)a->max_events * sizeof(cvad_event);
     const size_t out_total = probs_b + flags_b + status_b + 64 + ev_b + 256;
-    if ((rc = grow_host(e, e->h_out, out_total))) return rc;
-    unsigned char *ho = static_cast<unsigned char *>(e->h_out.p);
+    if ((rc = grow_host(e, ln.h_out, out_total))) return bail(rc);
+    unsigned char *ho = static_cast<unsigned char *>(ln.h_out.p);
+    if (a->probs_out) CU_TRY(e, cudaMemcpyAsync(ho, ln.d_probs.p, probs_b, cudaMemcpyDeviceToHost, st));
+    CU_TRY(e, cudaMemcpyAsync(ho + probs_b, ln.d_status.p, status_b, cudaMemcpyDeviceToHost, st));
+    CU_TRY(e, cudaMemcpyAsync(ho + probs_b + status_b, ln.d_nevents, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (a->flags_out)
+        CU_TRY(e, cudaMemcpyAsync(ho + probs_b + status_b + 64 + ((ev_b + 63) / 64) * 64, ln.d_flags.p, flags_b,
+                                  cudaMemcpyDeviceToHost, st));
+    return CVAD_OK;
+}
+
+// Wait for the step in flight on `ln` and unpack its results into the caller's buffers.
+int step_collect(cvad_engine *e, cvad_engine::Lane &ln, bool is_dbg) {
+    if (!ln.busy) return fail(e, CVAD_E_INVALID, "no step in flight on this ticket");
+    ln.busy = false;
+    CU_TRY(e, cudaSetDevice(e->device));
+    const cvad_step_args *a = &ln.args;
+    const int n = a->n_streams, T = a->max_frames;
+    if (a->n_events_out) *a->n_events_out = 0;
+    if (n == 0 || T == 0) return CVAD_OK;
+    CU_TRY(e, cudaStreamSynchronize(ln.stream));
+    if (is_dbg) return cvad::kDbgFloats;
+    const size_t probs_b = (size_t)n * T * 4, status_b = (size_t)n * 4;
+    const size_t ev_b = (size_t)a->max_events * sizeof(cvad_event);
+    unsigned char *ho = static_cast<unsigned char *>(ln.h_out.p);
     float *h_probs = reinterpret_cast<float *>(ho);
     unsigned int *h_status = reinterpret_cast<unsigned int *>(ho + probs_b);
     int *h_nev = reinterpret_cast<int *>(ho + probs_b + status_b);
     cvad_event *h_ev = reinterpret_cast<cvad_event *>(ho + probs_b + status_b + 64);
     unsigned char *h_flags = ho + probs_b + status_b + 64 + ((ev_b + 63) / 64) * 64;
-    // flags of frames never run (ragged n_frames) must read as 0
-    if (a->probs_out) CU_TRY(e, cudaMemcpyAsync(h_probs, e->d_probs.p, probs_b, cudaMemcpyDeviceToHost, e->stream));
-    if (a->flags_out) CU_TRY(e, cudaMemcpyAsync(h_flags, e->d_flags.p, flags_b, cudaMemcpyDeviceToHost, e->stream));
-    CU_TRY(e, cudaMemcpyAsync(h_status, e->d_status.p, status_b, cudaMemcpyDeviceToHost, e->stream));
-    CU_TRY(e, cudaMemcpyAsync(h_nev, e->d_nevents, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    CU_TRY(e, cudaStreamSynchronize(e->stream));
-    int nev = *h_nev;
+    const int nev = *h_nev;
     if (a->n_events_out) *a->n_events_out = nev;
     if (a->events_out && a->max_events > 0 && nev > 0) {
         const int take = std::min(nev, a->max_events);
-        CU_TRY(e, cudaMemcpy(h_ev, e->d_events.p, (size_t)take * sizeof(cvad_event), cudaMemcpyDeviceToHost));
+        CU_TRY(e, cudaMemcpy(h_ev, ln.d_events.p, (size_t)take * sizeof(cvad_event), cudaMemcpyDeviceToHost));
         std::sort(h_ev, h_ev + take, [](const cvad_event &x, const cvad_event &y) {
             if (x.stream != y.stream) return x.stream < y.stream;
             if (x.frame != y.frame) return x.frame < y.frame;
@@ -412,9 +460,16 @@ int step_host(cvad_engine *e, const cvad_step_args *a, float *dbg_out, size_t db
         });
         std::memcpy(a->events_out, h_ev, (size_t)take * sizeof(cvad_event));
     }
-    if (a->probs_out || a->flags_out) {
+    const bool ragged = !ln.nfr_copy.empty();
+    bool any_bad = false;
+    for (int i = 0; i < n && !any_bad; ++i) any_bad = h_status[i] != 0u;
+    if (!ragged && !any_bad) {
+        if (a->probs_out) std::memcpy(a->probs_out, h_probs, probs_b);
+        if (a->flags_out) std::memcpy(a->flags_out, h_flags, (size_t)n * T);
+    } else {
+        // frames that never ran (ragged n_frames, rejected streams) read as 0
         for (int i = 0; i < n; ++i) {
-            const int nf = (h_status[i] != 0u) ? 0 : (a->n_frames ? a->n_frames[i] : T);
+            const int nf = (h_status[i] != 0u) ? 0 : (ragged ? ln.nfr_copy[i] : T);
             if (a->probs_out) {
                 std::memcpy(a->probs_out + (size_t)i * T, h_probs + (size_t)i * T, (size_t)nf * 4);
                 for (int j = nf; j < T; ++j) a->probs_out[(size_t)i * T + j] = 0.f;
@@ -514,7 +569,11 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
             (rc = alloc_fill<unsigned char>(e, &e->denoise, ms, 1)))
             return bail(rc);
     }
-    CR_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_nevents), sizeof(int)));
+    CR_TRY(cudaEventCreateWithFlags(&e->last_done, cudaEventDisableTiming));
+    for (auto &ln : e->lanes) {
+        CR_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        CR_TRY(cudaMalloc(reinterpret_cast<void **>(&ln.d_nevents), sizeof(int)));
+    }
 #undef CR_TRY
     *out = e;
     return CVAD_OK;
@@ -524,14 +583,24 @@ int cvad_destroy(cvad_engine *e) {
     if (!e) return CVAD_OK;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto &ln : e->lanes)
+        if (ln.stream) cudaStreamSynchronize(ln.stream);
     void *ptrs[] = {e->w_fe, e->b_fe, e->w_rec, e->b_rec, e->w_dec, e->h_state, e->c_state, e->sm_active,
                     e->sm_scount, e->sm_ecount, e->frames_done, e->start_p, e->end_p, e->n_start, e->n_end,
-                    e->denoise, e->d_nevents, e->d_audio.p, e->d_slots.p, e->d_nframes.p, e->d_probs.p,
-                    e->d_flags.p, e->d_status.p, e->d_events.p, e->d_feat.p, e->d_dbg.p};
+                    e->denoise, e->d_status_dev.p, e->d_feat.p, e->d_dbg.p, e->d_cfg_slots.p};
     for (void *p : ptrs)
         if (p) cudaFree(p);
-    if (e->h_in.p) cudaFreeHost(e->h_in.p);
-    if (e->h_out.p) cudaFreeHost(e->h_out.p);
+    for (auto &ln : e->lanes) {
+        if (ln.stream) cudaStreamSynchronize(ln.stream);
+        void *lp[] = {ln.d_audio.p, ln.d_slots.p, ln.d_nframes.p, ln.d_probs.p, ln.d_flags.p, ln.d_status.p,
+                      ln.d_events.p, ln.d_nevents};
+        for (void *p : lp)
+            if (p) cudaFree(p);
+        if (ln.h_in.p) cudaFreeHost(ln.h_in.p);
+        if (ln.h_out.p) cudaFreeHost(ln.h_out.p);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+    }
+    if (e->last_done) cudaEventDestroy(e->last_done);
     for (cudaEvent_t x : e->ev_pool) cudaEventDestroy(x);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -560,8 +629,9 @@ int cvad_reset(cvad_engine *e, int n, const int32_t *slots) {
     if (slots && n < 0) return fail(e, CVAD_E_INVALID, "n < 0");
     CU_TRY(e, cudaSetDevice(e->device));
     const int *ds = nullptr;
-    int rc = stage_slots(e, n, slots, &ds);
+    int rc = quiesce(e);
     if (rc) return rc;
+    if ((rc = stage_slots(e, n, slots, &ds))) return rc;
     if ((rc = fill_slots<float>(e, e->h_state, ds, n, 0.f, 128)) ||
         (rc = fill_slots<float>(e, e->c_state, ds, n, 0.f, 128)) ||
         (rc = fill_slots<int>(e, e->sm_active, ds, n, 0, 1)) || (rc = fill_slots<int>(e, e->sm_scount, ds, n, 0, 1)) ||
@@ -584,8 +654,9 @@ int cvad_configure(cvad_engine *e, int n, const int32_t *slots, double vad_start
         return fail(e, CVAD_E_INVALID, "probabilities must be within [0, 1]");
     CU_TRY(e, cudaSetDevice(e->device));
     const int *ds = nullptr;
-    int rc = stage_slots(e, n, slots, &ds);
+    int rc = quiesce(e);
     if (rc) return rc;
+    if ((rc = stage_slots(e, n, slots, &ds))) return rc;
     if ((rc = fill_slots<double>(e, e->start_p, ds, n, vad_start_probability, 1)) ||
         (rc = fill_slots<double>(e, e->end_p, ds, n, vad_end_probability, 1)) ||
         (rc = fill_slots<int>(e, e->n_start, ds, n, voice_start_frame_count, 1)) ||
@@ -600,7 +671,7 @@ int cvad_get_state(cvad_engine *e, int slot, float *h, float *c, int32_t *sm, in
     if (!e) return CVAD_E_INVALID;
     if (slot < 0 || slot >= e->max_streams) return fail(e, CVAD_E_CAPACITY, "slot id out of range");
     CU_TRY(e, cudaSetDevice(e->device));
-    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    { int rcq = quiesce(e); if (rcq) return rcq; }
     const size_t pitch = (size_t)e->max_streams * sizeof(float);
     if (h) CU_TRY(e, cudaMemcpy2D(h, sizeof(float), e->h_state + slot, pitch, sizeof(float), 128, cudaMemcpyDeviceToHost));
     if (c) CU_TRY(e, cudaMemcpy2D(c, sizeof(float), e->c_state + slot, pitch, sizeof(float), 128, cudaMemcpyDeviceToHost));
@@ -622,7 +693,7 @@ int cvad_set_state(cvad_engine *e, int slot, const float *h, const float *c, con
     if (!e) return CVAD_E_INVALID;
     if (slot < 0 || slot >= e->max_streams) return fail(e, CVAD_E_CAPACITY, "slot id out of range");
     CU_TRY(e, cudaSetDevice(e->device));
-    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    { int rcq = quiesce(e); if (rcq) return rcq; }
     const size_t pitch = (size_t)e->max_streams * sizeof(float);
     if (h) CU_TRY(e, cudaMemcpy2D(e->h_state + slot, pitch, h, sizeof(float), sizeof(float), 128, cudaMemcpyHostToDevice));
     if (c) CU_TRY(e, cudaMemcpy2D(e->c_state + slot, pitch, c, sizeof(float), sizeof(float), 128, cudaMemcpyHostToDevice));
@@ -637,8 +708,7 @@ int cvad_set_state(cvad_engine *e, int slot, const float *h, const float *c, con
 int cvad_sync(cvad_engine *e) {
     if (!e) return CVAD_E_INVALID;
     CU_TRY(e, cudaSetDevice(e->device));
-    CU_TRY(e, cudaStreamSynchronize(e->stream));
-    return CVAD_OK;
+    return quiesce(e);
 }
 
 int64_t cvad_launch_count(const cvad_engine *e) { return e ? e->launches : 0; }
@@ -689,19 +759,49 @@ int cvad_step_device(cvad_engine *e, const cvad_step_args *a) {
         // status is one byte per stream at the ABI; the kernels use a 32-bit word per stream
         return fail(e, CVAD_E_INVALID, "cvad_step_device: status_out must be NULL (use cvad_step for status)");
     }
-    rc = grow(e, e->d_status, (size_t)a->n_streams * sizeof(unsigned int));
+    rc = grow(e, e->d_status_dev, (size_t)a->n_streams * sizeof(unsigned int));
     if (rc) return rc;
-    d_status = static_cast<unsigned int *>(e->d_status.p);
+    d_status = static_cast<unsigned int *>(e->d_status_dev.p);
     CU_TRY(e, cudaMemsetAsync(d_status, 0, (size_t)a->n_streams * sizeof(unsigned int), e->stream));
     if (a->n_events_out) CU_TRY(e, cudaMemsetAsync(a->n_events_out, 0, sizeof(int), e->stream));
-    return launch_step(e, a, d_status, 1, nullptr);
+    return launch_step(e, a, d_status, 1, nullptr, e->stream);
 }
 
-int cvad_step(cvad_engine *e, const cvad_step_args *a) { return step_host(e, a, nullptr, 0); }
+int cvad_step_submit(cvad_engine *e, const cvad_step_args *a, int *ticket) {
+    if (!e) return CVAD_E_INVALID;
+    if (!ticket) return fail(e, CVAD_E_INVALID, "ticket is NULL");
+    const int lane = e->next_lane;
+    if (e->lanes[lane].busy) return fail(e, CVAD_E_CAPACITY, "two steps are already in flight: collect one first");
+    int rc = step_submit(e, e->lanes[lane], a, nullptr, 0);
+    if (rc) return rc;
+    *ticket = lane;
+    e->next_lane = lane ^ 1;
+    return CVAD_OK;
+}
+
+int cvad_step_collect(cvad_engine *e, int ticket) {
+    if (!e) return CVAD_E_INVALID;
+    if (ticket < 0 || ticket > 1) return fail(e, CVAD_E_INVALID, "bad ticket");
+    return step_collect(e, e->lanes[ticket], false);
+}
+
+int cvad_step(cvad_engine *e, const cvad_step_args *a) {
+    int ticket = 0;
+    int rc = cvad_step_submit(e, a, &ticket);
+    if (rc) return rc;
+    return cvad_step_collect(e, ticket);
+}
 
 int cvad_debug_dump(cvad_engine *e, const cvad_step_args *a, float *dbg_out, size_t dbg_floats) {
+    if (!e) return CVAD_E_INVALID;
     if (!dbg_out) return fail(e, CVAD_E_INVALID, "dbg_out is NULL");
-    return step_host(e, a, dbg_out, dbg_floats);
+    int rc = quiesce(e);
+    if (rc) return rc;
+    cvad_engine::Lane &ln = e->lanes[0];
+    if (ln.busy || e->lanes[1].busy) return fail(e, CVAD_E_INVALID, "steps in flight");
+    rc = step_submit(e, ln, a, dbg_out, dbg_floats);
+    if (rc) return rc;
+    return step_collect(e, ln, true);
 }
 
 }  // extern "C"

@@ -35,6 +35,29 @@ class StepResult:
     events: List[Tuple[int, int, int, int, int]]  # (stream, slot, frame, kind, stream_frame), stream-then-frame order
 
 
+class PendingStep:
+    """A step in flight (see StreamEngine.submit)."""
+
+    def __init__(self, engine, ticket, args, keep, probs, flags, status, ev, nev):
+        self._engine, self._ticket, self._args, self._keep = engine, ticket, args, keep
+        self._probs, self._flags, self._status, self._ev, self._nev = probs, flags, status, ev, nev
+        self._result: Optional[StepResult] = None
+
+    def collect(self) -> StepResult:
+        if self._result is None:
+            eng = self._engine
+            eng._check(eng._L.cvad_step_collect(eng._h, self._ticket))
+            k = min(int(self._nev[0]), self._args.max_events)
+            events = []
+            if k:
+                rec = self._ev[:3 * k].view(np.int32).reshape(k, 6)
+                sf = self._ev[:3 * k].reshape(k, 3)[:, 2]
+                events = [(int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(f)) for r, f in zip(rec, sf)]
+            self._result = StepResult(self._probs, self._flags, self._status, events)
+            self._keep = None
+        return self._result
+
+
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -166,33 +189,38 @@ class StreamEngine:
         a.src_rate = 16000
         return a, keep
 
-    def step(self, audio: np.ndarray, *, slots: Optional[Sequence[int]] = None,
-             n_frames: Optional[Sequence[int]] = None, max_frames: Optional[int] = None,
-             frame_len: int = 512, hop: int = 512, pcm_format: int = capi.PCM_F32,
-             max_events: int = 0) -> StepResult:
-        """Advance every listed stream by its n_frames frames (host buffers in and out)."""
+    def submit(self, audio: np.ndarray, *, slots: Optional[Sequence[int]] = None,
+               n_frames: Optional[Sequence[int]] = None, max_frames: Optional[int] = None,
+               frame_len: int = 512, hop: int = 512, pcm_format: int = capi.PCM_F32,
+               max_events: int = 0) -> "PendingStep":
+        """Enqueue one step (H2D, kernels, D2H) and return at once; `.collect()` waits for it.
+        Up to two steps may be in flight: the second one's copy overlaps the first one's kernels.
+        `audio` must stay untouched until collect (pinned arrays are DMA'd in place)."""
         audio = np.asarray(audio)
         if max_frames is None:
             max_frames = 0 if audio.shape[1] < frame_len else (audio.shape[1] - frame_len) // hop + 1
         a, keep = self._args(audio, slots, n_frames, max_frames, frame_len, hop, pcm_format)
         n = a.n_streams
-        probs = np.zeros((n, max_frames), np.float32)
-        flags = np.zeros((n, max_frames), np.uint8)
+        probs = np.empty((n, max_frames), np.float32)
+        flags = np.empty((n, max_frames), np.uint8)
         status = np.zeros(n, np.uint8)
         if max_events <= 0:
             max_events = max(16, 2 * n * max(max_frames, 1))
-        ev = (capi.Event * max_events)()
-        nev = C.c_int32(0)
+        ev = np.empty(max_events * 3, np.int64)           # 24-byte cvad_event records
+        nev = np.zeros(1, np.int32)
         a.probs_out = probs.ctypes.data
         a.flags_out = flags.ctypes.data
         a.status_out = status.ctypes.data
-        a.events_out = C.addressof(ev)
+        a.events_out = ev.ctypes.data
         a.max_events = max_events
-        a.n_events_out = C.addressof(nev)
-        self._check(self._L.cvad_step(self._h, C.byref(a)))
-        k = min(int(nev.value), max_events)
-        events = [(ev[i].stream, ev[i].slot, ev[i].frame, ev[i].kind, ev[i].stream_frame) for i in range(k)]
-        return StepResult(probs, flags, status, events)
+        a.n_events_out = nev.ctypes.data
+        ticket = C.c_int(0)
+        self._check(self._L.cvad_step_submit(self._h, C.byref(a), C.byref(ticket)))
+        return PendingStep(self, ticket.value, a, keep, probs, flags, status, ev, nev)
+
+    def step(self, audio: np.ndarray, **kw) -> StepResult:
+        """Advance every listed stream by its n_frames frames (host buffers in and out)."""
+        return self.submit(audio, **kw).collect()
 
     def debug_dump(self, audio: np.ndarray, *, frame_len: int = 512, hop: int = 512,
                    pcm_format: int = capi.PCM_F32):

@@ -241,3 +241,38 @@ def test_sample_voice_known_answer_four_segments(engine_factory, ref_v5):
     xf = (q[:T * 480].astype(np.float32) / np.float32(32767.0))[None]
     want, _, _ = ref_v5.run(xf, T, hop=480, frame_len=480, denoise=True)
     assert np.abs(r.probs - want).max() <= TOL
+
+
+def test_pipelined_submit_collect_equals_blocking_steps(engine_factory, ref_v5):
+    """Two steps in flight (cvad_step_submit/collect) must give what blocking cvad_step gives,
+    in submission order, with state carried from step to step."""
+    from real_time_vad.engine.stream_engine import EngineError
+    eng = engine_factory(128)
+    eng.reset()
+    eng.configure(enable_denoising=True, vad_start_probability=0.5, vad_end_probability=0.35,
+                  voice_start_frame_count=3, voice_end_frame_count=4)
+    n, steps, F = 70, 14, 3
+    audio = synth_streams(n, 512 * F * steps, seed=29)
+    want, _, _ = ref_v5.run(audio, F * steps, denoise=True)
+    chunks = [np.ascontiguousarray(audio[:, k * 512 * F:(k + 1) * 512 * F]) for k in range(steps)]
+    got, flags = [], []
+    pending = eng.submit(chunks[0])
+    for k in range(1, steps):
+        nxt = eng.submit(chunks[k])
+        if k == 1:
+            with pytest.raises(EngineError):
+                eng.submit(chunks[k])                      # a third step in flight is refused
+        r = pending.collect()
+        got.append(r.probs.copy())
+        flags.append(r.flags.copy())
+        pending = nxt
+    r = pending.collect()
+    got.append(r.probs)
+    flags.append(r.flags)
+    got = np.concatenate(got, axis=1)
+    assert np.abs(got - want).max() <= TOL
+    # same run with blocking calls: bit-identical
+    eng.reset()
+    again = np.concatenate([eng.step(c).probs for c in chunks], axis=1)
+    assert np.array_equal(got, again)
+    assert eng.get_state(0)[3] == F * steps
