@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "../../include/cutter_vad_b200.h"
-#include "cvad_v5.cuh"
+#include "cvad_v4.cuh"
 
 namespace {
 
@@ -177,6 +177,93 @@ V5Packed pack_v5(const float *blob) {
     return P;
 }
 
+// ---- v4 weight repack (canonical blob order: oracle/silero_ref.c "Silero VAD v4")
+V5Packed pack_v4(const float *blob) {
+    const float *p = blob;
+    auto take = [&](size_t n) { const float *r = p; p += n; return r; };
+    const float *basis = take(258 * 256), *nfilt = take(7);
+    const float *f_dw = take(258 * 5), *f_dwb = take(258), *f_pw = take(16 * 258), *f_pwb = take(16),
+                *f_pj = take(16 * 258), *f_pjb = take(16);
+    const float *c1 = take(256), *c1b = take(16);
+    const float *e3_dw = take(80), *e3_dwb = take(16), *e3_pw = take(512), *e3_pwb = take(32), *e3_pj = take(512),
+                *e3_pjb = take(32);
+    const float *c2 = take(1024), *c2b = take(32);
+    const float *e7_dw = take(160), *e7_dwb = take(32), *e7_pw = take(1024), *e7_pwb = take(32);
+    const float *c3 = take(1024), *c3b = take(32);
+    const float *e11_dw = take(160), *e11_dwb = take(32), *e11_pw = take(2048), *e11_pwb = take(64),
+                *e11_pj = take(2048), *e11_pjb = take(64);
+    const float *c4 = take(4096), *c4b = take(64);
+    const float *l1w = take(16384), *l1r = take(16384), *l1b = take(512);
+    const float *l2w = take(16384), *l2r = take(16384), *l2b = take(512);
+    const float *decw = take(64), *decb = take(1);
+
+    V5Packed P;
+    P.w_fe.assign(cvad::kV4FeStreamFloats, 0.f);
+    float *o = P.w_fe.data();
+    for (int k = 0; k < 256; ++k)
+        for (int n = 0; n < 256; ++n) {
+            int row;
+            if (n == 0) row = 0;
+            else if (n == 1) row = 128;
+            else row = (n & 1) ? 129 + (n >> 1) : (n >> 1);
+            o[k * 256 + n] = basis[row * 256 + k];
+        }
+    o = P.w_fe.data() + cvad::kV4OffFirst;
+    for (int c = 0; c < 258; ++c) {
+        float *r = o + c * 40;
+        for (int d = 0; d < 5; ++d) r[d] = f_dw[c * 5 + d];
+        r[5] = f_dwb[c];
+        for (int oc = 0; oc < 16; ++oc) { r[8 + oc] = f_pw[oc * 258 + c]; r[24 + oc] = f_pj[oc * 258 + c]; }
+    }
+    auto put_T = [](float *dst, const float *w, int cout, int cin) {  // w[co][ci] -> dst[ci][co]
+        for (int co = 0; co < cout; ++co)
+            for (int ci = 0; ci < cin; ++ci) dst[ci * cout + co] = w[co * cin + ci];
+    };
+    auto put_dw = [](float *dst, const float *w, int c) {             // w[c][5] -> dst[5][c]
+        for (int ch = 0; ch < c; ++ch)
+            for (int d = 0; d < 5; ++d) dst[d * c + ch] = w[ch * 5 + d];
+    };
+    o = P.w_fe.data() + cvad::kV4OffS0;
+    put_T(o, c1, 16, 16); std::memcpy(o + 256, c1b, 64);
+    put_dw(o + 272, e3_dw, 16); std::memcpy(o + 352, e3_dwb, 64);
+    put_T(o + 368, e3_pw, 32, 16); std::memcpy(o + 880, e3_pwb, 128);
+    put_T(o + 912, e3_pj, 32, 16); std::memcpy(o + 1424, e3_pjb, 128);
+    put_T(o + 1456, c2, 32, 32); std::memcpy(o + 2480, c2b, 128);
+    o = P.w_fe.data() + cvad::kV4OffS1;
+    put_dw(o, e7_dw, 32); std::memcpy(o + 160, e7_dwb, 128);
+    put_T(o + 192, e7_pw, 32, 32); std::memcpy(o + 1216, e7_pwb, 128);
+    put_T(o + 1248, c3, 32, 32); std::memcpy(o + 2272, c3b, 128);
+    o = P.w_fe.data() + cvad::kV4OffS2;
+    put_dw(o, e11_dw, 32); std::memcpy(o + 160, e11_dwb, 128);
+    put_T(o + 192, e11_pw, 64, 32); std::memcpy(o + 2240, e11_pwb, 256);
+    o = P.w_fe.data() + cvad::kV4OffS3;
+    put_T(o, e11_pj, 64, 32); std::memcpy(o + 2048, e11_pjb, 256); std::memcpy(o + 2112, c4b, 256);
+    o = P.w_fe.data() + cvad::kV4OffS4;
+    put_T(o, c4, 64, 64);
+    o = P.w_fe.data() + cvad::kV4OffMisc;
+    for (int oc = 0; oc < 16; ++oc) o[oc] = f_pwb[oc] + f_pjb[oc];
+    for (int d = 0; d < 7; ++d) o[16 + d] = nfilt[d];
+    P.b_fe.assign(4, 0.f);  // unused for v4
+
+    P.w_rec.assign(cvad::kV4RecStreamFloats, 0.f);
+    P.b_rec.assign(512, 0.f);
+    const float *W[2] = {l1w, l2w}, *R[2] = {l1r, l2r}, *B[2] = {l1b, l2b};
+    for (int l = 0; l < 2; ++l)
+        for (int n = 0; n < 256; ++n) {
+            const int unit = n >> 2, gate = n & 3;
+            const int row = gate * 64 + unit;  // ONNX order i,o,f,c
+            for (int k = 0; k < 64; ++k) {
+                P.w_rec[(size_t)l * 32768 + k * 256 + n] = W[l][row * 64 + k];
+                P.w_rec[(size_t)l * 32768 + (64 + k) * 256 + n] = R[l][row * 64 + k];
+            }
+            P.b_rec[l * 256 + n] = B[l][row] + B[l][256 + row];
+        }
+    P.w_dec.resize(65);
+    std::memcpy(P.w_dec.data(), decw, 64 * 4);
+    P.w_dec[64] = decb[0];
+    return P;
+}
+
 template <typename T>
 int upload(cvad_engine *e, T **dst, const std::vector<T> &src) {
     CU_TRY(e, cudaMalloc(reinterpret_cast<void **>(dst), src.size() * sizeof(T)));
@@ -250,7 +337,8 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
     p.commit = commit;
     p.dbg = d_dbg;
 
-    const int n_tiles = a->max_frames * n_stiles;
+    const bool v4 = e->version == CVAD_MODEL_V4;
+    const int n_tiles = a->max_frames * n_stiles * (v4 ? 2 : 1);
     const int grid_fe = std::min(n_tiles, e->num_sms);
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     const bool timed = e->timing && !d_dbg;
@@ -264,12 +352,14 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         e->ev_used += 3;
         CU_TRY(e, cudaEventRecord(ev[0], stream));
     }
-    cvad::v5_frontend_kernel<<<grid_fe, cvad::kThreads, cvad::kFeSmemBytes, stream>>>(p);
+    if (v4) cvad::v4_frontend_kernel<<<grid_fe, cvad::kThreads, cvad::kV4FeSmemBytes, stream>>>(p);
+    else cvad::v5_frontend_kernel<<<grid_fe, cvad::kThreads, cvad::kFeSmemBytes, stream>>>(p);
     CU_TRY(e, cudaGetLastError());
     e->launches++;
     if (timed) CU_TRY(e, cudaEventRecord(ev[1], stream));
     if (!d_dbg) {
-        cvad::v5_recurrent_kernel<<<n_stiles, cvad::kThreads, cvad::kRecSmemBytes, stream>>>(p);
+        if (v4) cvad::v4_recurrent_kernel<<<n_stiles, cvad::kThreads, cvad::kV4RecSmemBytes, stream>>>(p);
+        else cvad::v5_recurrent_kernel<<<n_stiles, cvad::kThreads, cvad::kRecSmemBytes, stream>>>(p);
         CU_TRY(e, cudaGetLastError());
         e->launches++;
     }
@@ -402,15 +492,17 @@ int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, 
 
     float *d_dbg = nullptr;
     if (dbg_out) {
-        if (dbg_floats < (size_t)cvad::kDbgFloats) return bail(fail(e, CVAD_E_CAPACITY, "dbg_out too small"));
-        if ((rc = grow(e, e->d_dbg, (size_t)cvad::kDbgFloats * 4))) return bail(rc);
+        const size_t nd = e->version == CVAD_MODEL_V4 ? (size_t)cvad::kV4DbgFloats : (size_t)cvad::kDbgFloats;
+        if (dbg_floats < nd) return bail(fail(e, CVAD_E_CAPACITY, "dbg_out too small"));
+        if ((rc = grow(e, e->d_dbg, nd * 4))) return bail(rc);
         d_dbg = static_cast<float *>(e->d_dbg.p);
-        CU_TRY(e, cudaMemsetAsync(d_dbg, 0, (size_t)cvad::kDbgFloats * 4, st));
+        CU_TRY(e, cudaMemsetAsync(d_dbg, 0, nd * 4, st));
     }
     rc = launch_step(e, &d, static_cast<unsigned int *>(ln.d_status.p), dbg_out ? 0 : 1, d_dbg, st);
     if (rc) return bail(rc);
     if (dbg_out) {
-        CU_TRY(e, cudaMemcpyAsync(dbg_out, d_dbg, (size_t)cvad::kDbgFloats * 4, cudaMemcpyDeviceToHost, st));
+        const size_t nd = e->version == CVAD_MODEL_V4 ? (size_t)cvad::kV4DbgFloats : (size_t)cvad::kDbgFloats;
+        CU_TRY(e, cudaMemcpyAsync(dbg_out, d_dbg, nd * 4, cudaMemcpyDeviceToHost, st));
         return CVAD_OK;
     }
 
@@ -439,7 +531,7 @@ int step_collect(cvad_engine *e, cvad_engine::Lane &ln, bool is_dbg) {
     if (a->n_events_out) *a->n_events_out = 0;
     if (n == 0 || T == 0) return CVAD_OK;
     CU_TRY(e, cudaStreamSynchronize(ln.stream));
-    if (is_dbg) return cvad::kDbgFloats;
+    if (is_dbg) return e->version == CVAD_MODEL_V4 ? cvad::kV4DbgFloats : cvad::kDbgFloats;
     const size_t probs_b = (size_t)n * T * 4, status_b = (size_t)n * 4;
     const size_t ev_b = (size_t)a->max_events * sizeof(cvad_event);
     unsigned char *ho = static_cast<unsigned char *>(ln.h_out.p);
@@ -509,10 +601,12 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
     *out = nullptr;
     if (!weights) return fail(nullptr, CVAD_E_INVALID, "weights is NULL");
     if (max_streams < 1) return fail(nullptr, CVAD_E_INVALID, "max_streams < 1");
-    if (model_version != CVAD_MODEL_V5)
-        return fail(nullptr, CVAD_E_INVALID, "model_version: only CVAD_MODEL_V5 is implemented in this build");
-    if (n_weight_floats != CVAD_V5_WEIGHT_FLOATS)
+    if (model_version != CVAD_MODEL_V5 && model_version != CVAD_MODEL_V4)
+        return fail(nullptr, CVAD_E_INVALID, "model_version must be CVAD_MODEL_V5 or CVAD_MODEL_V4");
+    if (model_version == CVAD_MODEL_V5 && n_weight_floats != CVAD_V5_WEIGHT_FLOATS)
         return fail(nullptr, CVAD_E_WEIGHTS, "v5 weight blob must hold 309633 floats");
+    if (model_version == CVAD_MODEL_V4 && n_weight_floats != CVAD_V4_WEIGHT_FLOATS)
+        return fail(nullptr, CVAD_E_WEIGHTS, "v4 weight blob must hold 155908 floats");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -548,8 +642,12 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
                                 (int)cvad::kFeSmemBytes));
     CR_TRY(cudaFuncSetAttribute(cvad::v5_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::kRecSmemBytes));
+    CR_TRY(cudaFuncSetAttribute(cvad::v4_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::kV4FeSmemBytes));
+    CR_TRY(cudaFuncSetAttribute(cvad::v4_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::kV4RecSmemBytes));
     {
-        V5Packed P = pack_v5(weights);
+        V5Packed P = model_version == CVAD_MODEL_V5 ? pack_v5(weights) : pack_v4(weights);
         int rc;
         if ((rc = upload(e, &e->w_fe, P.w_fe)) || (rc = upload(e, &e->b_fe, P.b_fe)) ||
             (rc = upload(e, &e->w_rec, P.w_rec)) || (rc = upload(e, &e->b_rec, P.b_rec)) ||

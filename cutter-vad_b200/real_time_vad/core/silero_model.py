@@ -399,7 +399,8 @@ class VADProcessor(BaseModel):
         """True when the model is the real engine-backed one (not a test double) on the 16 kHz v5 path."""
         m = self.model
         return (isinstance(m, SileroVADModel) and isinstance(m.session, ort.InferenceSession)
-                and m.session.version == "v5" and int(self.config.sample_rate) == 16000)
+                and m.session.version == self.config.model_version.value
+                and int(self.config.sample_rate) == 16000)
 
     def process_audio_batched(self, audio: np.ndarray, frame_size: int, hop_size: int) -> Iterator[ProcessingResult]:
         """All frames `audio[j*hop : j*hop+frame_size]` through one `cvad_step` on this stream's model
@@ -424,7 +425,10 @@ class VADProcessor(BaseModel):
                           voice_end_frame_count=cfg.voice_end_frame_count, enable_denoising=cfg.enable_denoising)
             sm_in = np.array([int(self.is_voice_active), self.voice_start_frame_count,
                               self.voice_end_frame_count, 0], np.int32)
-            eng.set_state(slot, ms.state[0, 0], ms.state[1, 0], sm_in)
+            if ms.state is not None:
+                eng.set_state(slot, ms.state[0, 0], ms.state[1, 0], sm_in)
+            else:
+                eng.set_state(slot, ms.hidden_state.reshape(128), ms.cell_state.reshape(128), sm_in)
             try:
                 r = eng.step(audio[None, :], slots=[slot], n_frames=[n_frames], max_frames=n_frames,
                              frame_len=frame_size, hop=hop_size)
@@ -434,7 +438,11 @@ class VADProcessor(BaseModel):
             finally:
                 eng.configure([slot], enable_denoising=False)  # the compat session.run must not gate
         d = self.__dict__  # bypass pydantic's per-assignment validation on the per-frame bookkeeping
-        ms.__dict__["state"] = np.stack([h[None, :], c[None, :]], axis=0).astype(np.float32)
+        if ms.state is not None:
+            ms.__dict__["state"] = np.stack([h[None, :], c[None, :]], axis=0).astype(np.float32)
+        else:
+            ms.__dict__["hidden_state"] = h.reshape(2, 1, 64).astype(np.float32)
+            ms.__dict__["cell_state"] = c.reshape(2, 1, 64).astype(np.float32)
         self.model.__dict__["prediction_count"] = self.model.prediction_count + n_frames
         probs = r.probs[0]
         flags = r.flags[0]

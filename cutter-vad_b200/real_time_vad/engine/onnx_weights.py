@@ -165,3 +165,44 @@ def canonical_blob_v5(path: Union[str, Path]) -> np.ndarray:
     blob = np.concatenate(parts)
     assert blob.size == V5_WEIGHT_FLOATS
     return blob
+
+
+# canonical order of the v4 / 16 kHz branch.  Conv weights are top-level initializers
+# (`model.*` plus the anonymous 1110..1120); the two LSTM layers are anonymous initializers
+# inside the nested If subgraphs of the 16 kHz branch (W/R/B = 343/345/347 and 415/417/419).
+_V4_LAYOUT = (
+    ("model.feature_extractor.forward_basis_buffer", 258 * 256), ("model.adaptive_normalization.filter_", 7),
+    ("model.first_layer.0.dw_conv.0.weight", 258 * 5), ("model.first_layer.0.dw_conv.0.bias", 258),
+    ("model.first_layer.0.pw_conv.0.weight", 16 * 258), ("model.first_layer.0.pw_conv.0.bias", 16),
+    ("model.first_layer.0.proj.weight", 16 * 258), ("model.first_layer.0.proj.bias", 16),
+    ("1110", 256), ("1111", 16),
+    ("model.encoder.3.0.dw_conv.0.weight", 80), ("model.encoder.3.0.dw_conv.0.bias", 16),
+    ("model.encoder.3.0.pw_conv.0.weight", 512), ("model.encoder.3.0.pw_conv.0.bias", 32),
+    ("model.encoder.3.0.proj.weight", 512), ("model.encoder.3.0.proj.bias", 32),
+    ("1113", 1024), ("1114", 32),
+    ("model.encoder.7.0.dw_conv.0.weight", 160), ("model.encoder.7.0.dw_conv.0.bias", 32),
+    ("model.encoder.7.0.pw_conv.0.weight", 1024), ("model.encoder.7.0.pw_conv.0.bias", 32),
+    ("1116", 1024), ("1117", 32),
+    ("model.encoder.11.0.dw_conv.0.weight", 160), ("model.encoder.11.0.dw_conv.0.bias", 32),
+    ("model.encoder.11.0.pw_conv.0.weight", 2048), ("model.encoder.11.0.pw_conv.0.bias", 64),
+    ("model.encoder.11.0.proj.weight", 2048), ("model.encoder.11.0.proj.bias", 64),
+    ("1119", 4096), ("1120", 64),
+    ("343", 16384), ("345", 16384), ("347", 512), ("415", 16384), ("417", 16384), ("419", 512),
+    ("model.decoder.decoder.1.weight", 64), ("model.decoder.decoder.1.bias", 1),
+)
+V4_WEIGHT_FLOATS = 155908
+
+
+def canonical_blob_v4(path: Union[str, Path]) -> np.ndarray:
+    tensors = read_float_tensors(path)
+    parts = []
+    for name, size in _V4_LAYOUT:
+        if name not in tensors:
+            raise KeyError(f"{path}: tensor {name!r} not found (is this silero_vad.onnx, the v4 model?)")
+        t = np.ascontiguousarray(tensors[name], dtype=np.float32).reshape(-1)
+        if t.size != size:
+            raise ValueError(f"{path}: tensor {name} has {t.size} values, expected {size}")
+        parts.append(t)
+    blob = np.concatenate(parts)
+    assert blob.size == V4_WEIGHT_FLOATS
+    return blob

@@ -124,22 +124,29 @@ class InferenceSession:
         if sr != 16000:
             raise ValueError(f"sr={sr}: only the 16 kHz branch is implemented "
                              "(the reference's v5 graph cannot run 512-sample frames at other rates either)")
-        if self.version != "v5":
-            raise NotImplementedError("v4 is not available in this build")
-        state = np.asarray(input_feed["state"], dtype=np.float32)
-        if state.shape != (2, 1, 128):
-            raise ValueError(f"state must have shape (2, 1, 128), got {state.shape}")
+        if self.version == "v5":
+            state = np.asarray(input_feed["state"], dtype=np.float32)
+            if state.shape != (2, 1, 128):
+                raise ValueError(f"state must have shape (2, 1, 128), got {state.shape}")
+            h_in, c_in = state[0, 0], state[1, 0]
+        else:
+            h_in = np.asarray(input_feed["h"], dtype=np.float32)
+            c_in = np.asarray(input_feed["c"], dtype=np.float32)
+            if h_in.shape != (2, 1, 64) or c_in.shape != (2, 1, 64):
+                raise ValueError(f"h and c must have shape (2, 1, 64), got {h_in.shape} / {c_in.shape}")
+            h_in, c_in = h_in.reshape(128), c_in.reshape(128)      # engine rows: layer-major [2][64]
         eng = self._pooled.engine
         with self._pooled.lock:
-            eng.set_state(self._slot, state[0, 0], state[1, 0], np.zeros(4, np.int32))
+            eng.set_state(self._slot, h_in, c_in, np.zeros(4, np.int32))
             frame_len = min(x.shape[1], 512)
             r = eng.step(x, slots=[self._slot], max_frames=1, frame_len=frame_len, hop=max(frame_len, 1))
             if r.status[0]:
                 raise ValueError("Audio data contains infinite or NaN values")
             h, c, _, _ = eng.get_state(self._slot)
         out = r.probs.reshape(1, 1).astype(np.float32)
-        state_n = np.stack([h[None, :], c[None, :]], axis=0).astype(np.float32)
-        return [out, state_n]
+        if self.version == "v5":
+            return [out, np.stack([h[None, :], c[None, :]], axis=0).astype(np.float32)]
+        return [out, h.reshape(2, 1, 64).astype(np.float32), c.reshape(2, 1, 64).astype(np.float32)]
 
 
 def _is_packaged(path: Path) -> bool:

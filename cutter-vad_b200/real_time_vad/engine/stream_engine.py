@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import capi
-from .onnx_weights import canonical_blob_v5
+from .onnx_weights import canonical_blob_v4, canonical_blob_v5
 
 MODELS_DIR = Path(__file__).resolve().parents[1] / "models"
 
@@ -67,11 +67,15 @@ class StreamEngine:
                  model_path: Optional[Path] = None):
         self._L = capi.lib()
         self._h = C.c_void_p()
-        if model_version != "v5":
-            raise EngineError(capi.E_INVALID, f"model version {model_version!r} not available in this build")
-        path = Path(model_path) if model_path else MODELS_DIR / "silero_vad_v5.onnx"
-        self.weights = canonical_blob_v5(path)
-        rc = self._L.cvad_create(_ptr(self.weights), self.weights.size, capi.MODEL_V5, int(max_streams),
+        if model_version == "v5":
+            path = Path(model_path) if model_path else MODELS_DIR / "silero_vad_v5.onnx"
+            self.weights, code = canonical_blob_v5(path), capi.MODEL_V5
+        elif model_version == "v4":
+            path = Path(model_path) if model_path else MODELS_DIR / "silero_vad.onnx"
+            self.weights, code = canonical_blob_v4(path), capi.MODEL_V4
+        else:
+            raise EngineError(capi.E_INVALID, f"unknown model version {model_version!r}")
+        rc = self._L.cvad_create(_ptr(self.weights), self.weights.size, code, int(max_streams),
                                  int(device), C.byref(self._h))
         if rc != capi.OK:
             raise EngineError(rc, (self._L.cvad_last_error(None) or b"").decode())
@@ -226,14 +230,19 @@ class StreamEngine:
                    pcm_format: int = capi.PCM_F32):
         """Front-end intermediates of the first tile, frame 0 (test hook; engine state untouched)."""
         a, keep = self._args(np.asarray(audio), None, None, 1, frame_len, hop, pcm_format)
-        n_dbg = 129 * 96 + 128 * 96 + 64 * 64 + 64 * 32 + 128 * 32
+        if self.model_version == "v5":
+            layout = (("mag", (129, 3, 32)), ("e0", (128, 3, 32)), ("e1", (64, 2, 32)), ("e2", (64, 32)),
+                      ("feat", (128, 32)))
+        else:
+            layout = (("mag", (129, 8, 16)), ("norm", (129, 8, 16)), ("r3", (16, 8, 16)), ("r15", (32, 4, 16)),
+                      ("r27", (32, 2, 16)), ("r39", (64, 16)), ("feat", (64, 16)))
+        n_dbg = sum(int(np.prod(sh)) for _, sh in layout)
         out = np.zeros(n_dbg, np.float32)
         rc = self._L.cvad_debug_dump(self._h, C.byref(a), _ptr(out), out.size)
         self._check(rc)
         o = 0
         res = {}
-        for name, shape in (("mag", (129, 3, 32)), ("e0", (128, 3, 32)), ("e1", (64, 2, 32)),
-                            ("e2", (64, 32)), ("feat", (128, 32))):
+        for name, shape in layout:
             size = int(np.prod(shape))
             res[name] = out[o:o + size].reshape(shape)
             o += size

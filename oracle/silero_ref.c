@@ -201,6 +201,220 @@ void sref_v5_run(const sref_v5 *m, const float *audio, long stride, int n_stream
     }
 }
 
+
+/* ========================================================================
+ * Silero VAD v4, 16 kHz branch (silero_vad.onnx, If(sr==16000) then-branch),
+ * SURVEY.md section 8a table "S4".  Canonical blob (155,908 floats):
+ *   basis[258][256] norm_filter[7]
+ *   first: dw_w[258][5] dw_b[258] pw_w[16][258] pw_b[16] proj_w[16][258] proj_b[16]
+ *   c1_w[16][16] c1_b[16]                                   (initializers 1110,1111; stride 2)
+ *   enc3: dw_w[16][5] dw_b[16] pw_w[32][16] pw_b[32] proj_w[32][16] proj_b[32]
+ *   c2_w[32][32] c2_b[32]                                   (1113,1114; stride 2)
+ *   enc7: dw_w[32][5] dw_b[32] pw_w[32][32] pw_b[32]        (identity residual)
+ *   c3_w[32][32] c3_b[32]                                   (1116,1117; stride 2)
+ *   enc11: dw_w[32][5] dw_b[32] pw_w[64][32] pw_b[64] proj_w[64][32] proj_b[64]
+ *   c4_w[64][64] c4_b[64]                                   (1119,1120)
+ *   lstm1: W[256][64] R[256][64] B[512]   lstm2: W[256][64] R[256][64] B[512]   (ONNX gate order i,o,f,c)
+ *   dec_w[64] dec_b[1]
+ */
+#define V4_BLOB_FLOATS 155908
+
+typedef struct {
+    const float *basis, *nfilt;
+    const float *f_dw, *f_dwb, *f_pw, *f_pwb, *f_pj, *f_pjb;
+    const float *c1, *c1b;
+    const float *e3_dw, *e3_dwb, *e3_pw, *e3_pwb, *e3_pj, *e3_pjb;
+    const float *c2, *c2b;
+    const float *e7_dw, *e7_dwb, *e7_pw, *e7_pwb;
+    const float *c3, *c3b;
+    const float *e11_dw, *e11_dwb, *e11_pw, *e11_pwb, *e11_pj, *e11_pjb;
+    const float *c4, *c4b;
+    const float *l1w, *l1r, *l1b, *l2w, *l2r, *l2b;
+    const float *decw, *decb;
+    float *basis_t; /* [256 k][258 f] */
+    float *blob;
+} sref_v4;
+
+sref_v4 *sref_v4_create(const float *blob_in) {
+    sref_v4 *m = (sref_v4 *)calloc(1, sizeof(sref_v4));
+    m->blob = (float *)malloc(sizeof(float) * V4_BLOB_FLOATS);
+    memcpy(m->blob, blob_in, sizeof(float) * V4_BLOB_FLOATS);
+    const float *p = m->blob;
+#define TAKE(field, n) m->field = p; p += (n)
+    TAKE(basis, 258 * 256); TAKE(nfilt, 7);
+    TAKE(f_dw, 258 * 5); TAKE(f_dwb, 258); TAKE(f_pw, 16 * 258); TAKE(f_pwb, 16); TAKE(f_pj, 16 * 258); TAKE(f_pjb, 16);
+    TAKE(c1, 256); TAKE(c1b, 16);
+    TAKE(e3_dw, 80); TAKE(e3_dwb, 16); TAKE(e3_pw, 512); TAKE(e3_pwb, 32); TAKE(e3_pj, 512); TAKE(e3_pjb, 32);
+    TAKE(c2, 1024); TAKE(c2b, 32);
+    TAKE(e7_dw, 160); TAKE(e7_dwb, 32); TAKE(e7_pw, 1024); TAKE(e7_pwb, 32);
+    TAKE(c3, 1024); TAKE(c3b, 32);
+    TAKE(e11_dw, 160); TAKE(e11_dwb, 32); TAKE(e11_pw, 2048); TAKE(e11_pwb, 64); TAKE(e11_pj, 2048); TAKE(e11_pjb, 64);
+    TAKE(c4, 4096); TAKE(c4b, 64);
+    TAKE(l1w, 16384); TAKE(l1r, 16384); TAKE(l1b, 512); TAKE(l2w, 16384); TAKE(l2r, 16384); TAKE(l2b, 512);
+    TAKE(decw, 64); TAKE(decb, 1);
+#undef TAKE
+    m->basis_t = transpose_conv(m->basis, 258, 256, 1);
+    return m;
+}
+
+void sref_v4_free(sref_v4 *m) {
+    if (!m) return;
+    free(m->basis_t); free(m->blob); free(m);
+}
+
+/* depthwise conv k5 pad 2 + bias + relu over [C][T] */
+static void dw5_relu(const float *in, int C, int T, const float *w, const float *b, float *out) {
+    for (int c = 0; c < C; ++c)
+        for (int t = 0; t < T; ++t) {
+            float a = 0.0f;
+            for (int d = 0; d < 5; ++d) {
+                int ti = t + d - 2;
+                if (ti >= 0 && ti < T) a += w[c * 5 + d] * in[c * T + ti];
+            }
+            a += b[c];
+            out[c * T + t] = a > 0.0f ? a : 0.0f;
+        }
+}
+
+/* 1x1 conv with stride over [Cin][T] -> [Cout][Tout], no activation */
+static void pw(const float *in, int Cin, int T, const float *w, const float *b, int Cout, int stride, int Tout,
+               float *out) {
+    for (int o = 0; o < Cout; ++o)
+        for (int t = 0; t < Tout; ++t) {
+            float a = 0.0f;
+            for (int c = 0; c < Cin; ++c) a += w[o * Cin + c] * in[c * T + t * stride];
+            out[o * Tout + t] = a + b[o];
+        }
+}
+
+static void relu_n(float *x, int n) { for (int i = 0; i < n; ++i) x[i] = x[i] > 0.0f ? x[i] : 0.0f; }
+
+static void lstm_iofc(const float *W, const float *R, const float *B, const float *x, float *h, float *c) {
+    float g[256];
+    for (int n = 0; n < 256; ++n) {
+        float a = 0.0f;
+        for (int k = 0; k < 64; ++k) a += W[n * 64 + k] * x[k];
+        float r = 0.0f;
+        for (int k = 0; k < 64; ++k) r += R[n * 64 + k] * h[k];
+        g[n] = a + r + B[n] + B[256 + n];
+    }
+    for (int j = 0; j < 64; ++j) {
+        float ig = sigmoidf_(g[j]), og = sigmoidf_(g[64 + j]), fg = sigmoidf_(g[128 + j]), cg = tanhf(g[192 + j]);
+        float cn = fg * c[j] + ig * cg;
+        c[j] = cn;
+        h[j] = og * tanhf(cn);
+    }
+}
+
+/* dbg (optional): mag[129][8] norm[129][8] r3[16][8] r7[16][4] r15[32][4] r19[32][2] r27[32][2] r31[32] r39[64] r43[64] */
+#define V4_DBG_FLOATS (1032 + 1032 + 128 + 64 + 128 + 64 + 64 + 32 + 64 + 64)
+
+/* h, c: [2][64] (layer-major), as the reference keeps them (silero_model.py:397-401). */
+void sref_v4_frame(const sref_v4 *m, const float *x, float *h, float *c, float *prob, float *dbg) {
+    float xp[704];
+    for (int i = 0; i < 96; ++i) xp[i] = x[96 - i];            /* reflect, no edge repeat */
+    for (int i = 0; i < 512; ++i) xp[96 + i] = x[i];
+    for (int i = 0; i < 96; ++i) xp[608 + i] = x[510 - i];
+    float mag[129 * 8], sp[129 * 8], x1[258 * 8];
+    for (int t = 0; t < 8; ++t) {
+        float s[258];
+        for (int f = 0; f < 258; ++f) s[f] = 0.0f;
+        for (int k = 0; k < 256; ++k) {
+            float v = xp[64 * t + k];
+            const float *w = m->basis_t + (size_t)k * 258;
+            for (int f = 0; f < 258; ++f) s[f] += w[f] * v;
+        }
+        for (int f = 0; f < 129; ++f) {
+            float mg = sqrtf(s[f] * s[f] + s[129 + f] * s[129 + f]);
+            mag[f * 8 + t] = mg;
+            sp[f * 8 + t] = logf(1.0f + mg * 1048576.0f);
+        }
+    }
+    /* adaptive normalisation: mean over bins, reflect-pad 3, 7-tap filter, mean over time */
+    float mean[8], mp[14];
+    for (int t = 0; t < 8; ++t) {
+        float a = 0.0f;
+        for (int f = 0; f < 129; ++f) a += sp[f * 8 + t];
+        mean[t] = a / 129.0f;
+    }
+    for (int i = 0; i < 3; ++i) mp[i] = mean[3 - i];
+    for (int i = 0; i < 8; ++i) mp[3 + i] = mean[i];
+    for (int i = 0; i < 3; ++i) mp[11 + i] = mean[6 - i];
+    float mm = 0.0f;
+    for (int t = 0; t < 8; ++t) {
+        float a = 0.0f;
+        for (int d = 0; d < 7; ++d) a += m->nfilt[d] * mp[t + d];
+        mm += a;
+    }
+    mm /= 8.0f;
+    for (int i = 0; i < 1032; ++i) { x1[i] = mag[i]; x1[1032 + i] = sp[i] - mm; }
+
+    float d1[258 * 8], a16[16 * 8], b16[16 * 8], r7[16 * 4];
+    dw5_relu(x1, 258, 8, m->f_dw, m->f_dwb, d1);
+    pw(d1, 258, 8, m->f_pw, m->f_pwb, 16, 1, 8, a16);
+    pw(x1, 258, 8, m->f_pj, m->f_pjb, 16, 1, 8, b16);
+    for (int i = 0; i < 128; ++i) a16[i] += b16[i];
+    relu_n(a16, 128);                                           /* r3 */
+    pw(a16, 16, 8, m->c1, m->c1b, 16, 2, 4, r7); relu_n(r7, 64);
+    float d3[16 * 4], a32[32 * 4], b32[32 * 4], r19[32 * 2];
+    dw5_relu(r7, 16, 4, m->e3_dw, m->e3_dwb, d3);
+    pw(d3, 16, 4, m->e3_pw, m->e3_pwb, 32, 1, 4, a32);
+    pw(r7, 16, 4, m->e3_pj, m->e3_pjb, 32, 1, 4, b32);
+    for (int i = 0; i < 128; ++i) a32[i] += b32[i];
+    relu_n(a32, 128);                                           /* r15 */
+    pw(a32, 32, 4, m->c2, m->c2b, 32, 2, 2, r19); relu_n(r19, 64);
+    float d7[32 * 2], r27[32 * 2], r31[32];
+    dw5_relu(r19, 32, 2, m->e7_dw, m->e7_dwb, d7);
+    pw(d7, 32, 2, m->e7_pw, m->e7_pwb, 32, 1, 2, r27);
+    for (int i = 0; i < 64; ++i) r27[i] += r19[i];
+    relu_n(r27, 64);
+    pw(r27, 32, 2, m->c3, m->c3b, 32, 2, 1, r31); relu_n(r31, 32);
+    float d11[32], r39[64], q39[64], r43[64];
+    dw5_relu(r31, 32, 1, m->e11_dw, m->e11_dwb, d11);
+    pw(d11, 32, 1, m->e11_pw, m->e11_pwb, 64, 1, 1, r39);
+    pw(r31, 32, 1, m->e11_pj, m->e11_pjb, 64, 1, 1, q39);
+    for (int i = 0; i < 64; ++i) r39[i] += q39[i];
+    relu_n(r39, 64);
+    pw(r39, 64, 1, m->c4, m->c4b, 64, 1, 1, r43); relu_n(r43, 64);
+
+    lstm_iofc(m->l1w, m->l1r, m->l1b, r43, h, c);
+    lstm_iofc(m->l2w, m->l2r, m->l2b, h, h + 64, c + 64);
+    float acc = 0.0f;
+    for (int j = 0; j < 64; ++j) acc += m->decw[j] * (h[64 + j] > 0.0f ? h[64 + j] : 0.0f);
+    *prob = sigmoidf_(acc + m->decb[0]);
+    if (dbg) {
+        float *d = dbg;
+        memcpy(d, mag, 4 * 1032); d += 1032;
+        memcpy(d, x1 + 1032, 4 * 1032); d += 1032;
+        memcpy(d, a16, 4 * 128); d += 128;
+        memcpy(d, r7, 4 * 64); d += 64;
+        memcpy(d, a32, 4 * 128); d += 128;
+        memcpy(d, r19, 4 * 64); d += 64;
+        memcpy(d, r27, 4 * 64); d += 64;
+        memcpy(d, r31, 4 * 32); d += 32;
+        memcpy(d, r39, 4 * 64); d += 64;
+        memcpy(d, r43, 4 * 64);
+    }
+}
+
+/* h,c: [n_streams][2][64] */
+void sref_v4_run(const sref_v4 *m, const float *audio, long stride, int n_streams, int n_frames, int hop,
+                 int frame_len, int denoise, float *h, float *c, float *probs, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+    for (int s = 0; s < n_streams; ++s) {
+        float x[512];
+        for (int j = 0; j < n_frames; ++j) {
+            load_frame(audio + (size_t)s * stride + (size_t)j * hop, frame_len, denoise, x);
+            sref_v4_frame(m, x, h + (size_t)s * 128, c + (size_t)s * 128, probs + (size_t)s * n_frames + j, 0);
+        }
+    }
+}
+int sref_v4_blob_floats(void) { return V4_BLOB_FLOATS; }
+int sref_v4_dbg_floats(void) { return V4_DBG_FLOATS; }
+
 /* ------------------------------------------------------------------------
  * Start / end state machine, silero_model.py:790-923 restated with the deques
  * kept literally (recent_start_frames maxlen 20 :620-623, recent_end_frames

@@ -80,6 +80,55 @@ def v5_blob(onnx_path: str) -> np.ndarray:
     return blob
 
 
+V4_ORDER = [
+    ("model.feature_extractor.forward_basis_buffer", 258 * 256), ("model.adaptive_normalization.filter_", 7),
+    ("model.first_layer.0.dw_conv.0.weight", 258 * 5), ("model.first_layer.0.dw_conv.0.bias", 258),
+    ("model.first_layer.0.pw_conv.0.weight", 16 * 258), ("model.first_layer.0.pw_conv.0.bias", 16),
+    ("model.first_layer.0.proj.weight", 16 * 258), ("model.first_layer.0.proj.bias", 16),
+    ("1110", 256), ("1111", 16),
+    ("model.encoder.3.0.dw_conv.0.weight", 80), ("model.encoder.3.0.dw_conv.0.bias", 16),
+    ("model.encoder.3.0.pw_conv.0.weight", 512), ("model.encoder.3.0.pw_conv.0.bias", 32),
+    ("model.encoder.3.0.proj.weight", 512), ("model.encoder.3.0.proj.bias", 32),
+    ("1113", 1024), ("1114", 32),
+    ("model.encoder.7.0.dw_conv.0.weight", 160), ("model.encoder.7.0.dw_conv.0.bias", 32),
+    ("model.encoder.7.0.pw_conv.0.weight", 1024), ("model.encoder.7.0.pw_conv.0.bias", 32),
+    ("1116", 1024), ("1117", 32),
+    ("model.encoder.11.0.dw_conv.0.weight", 160), ("model.encoder.11.0.dw_conv.0.bias", 32),
+    ("model.encoder.11.0.pw_conv.0.weight", 2048), ("model.encoder.11.0.pw_conv.0.bias", 64),
+    ("model.encoder.11.0.proj.weight", 2048), ("model.encoder.11.0.proj.bias", 64),
+    ("1119", 4096), ("1120", 64),
+    ("343", 16384), ("345", 16384), ("347", 512), ("415", 16384), ("417", 16384), ("419", 512),
+    ("model.decoder.decoder.1.weight", 64), ("model.decoder.decoder.1.bias", 1),
+]
+
+
+def _all_float_tensors(g: Graph, out: Dict[str, np.ndarray]) -> None:
+    for k, v in g.initializers.items():
+        if v.dtype == np.float32:
+            out.setdefault(k, v)
+    for n in g.nodes:
+        for a in n.attrs.values():
+            if isinstance(a, Graph):
+                _all_float_tensors(a, out)
+
+
+def v4_blob(onnx_path: str) -> np.ndarray:
+    """v4 keeps conv weights as top-level initializers (`model.*`, anonymous 1110..1120) and the
+    LSTM weights as anonymous initializers inside the nested If subgraphs of the 16 kHz branch
+    (343,345,347 / 415,417,419) -- SURVEY.md section 2 row 10 and section 8a S4 row 13."""
+    m = load_model(onnx_path)
+    named: Dict[str, np.ndarray] = {}
+    _all_float_tensors(m.graph, named)
+    parts = []
+    for name, size in V4_ORDER:
+        a = named[name]
+        assert a.size == size, (name, a.shape, size)
+        parts.append(np.ascontiguousarray(a, dtype=np.float32).reshape(-1))
+    blob = np.concatenate(parts)
+    assert blob.size == 155908
+    return blob
+
+
 # ----------------------------------------------------------------------------
 # C restatement: build + bind
 # ----------------------------------------------------------------------------
@@ -121,6 +170,12 @@ class RefLib:
                                   ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                   ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_ubyte)]
         L.sref_max_threads.restype = ctypes.c_int
+        L.sref_v4_create.restype = ctypes.c_void_p
+        L.sref_v4_create.argtypes = [_f32p]
+        L.sref_v4_free.argtypes = [ctypes.c_void_p]
+        L.sref_v4_frame.argtypes = [ctypes.c_void_p, _f32p, _f32p, _f32p, _f32p, _f32p]
+        L.sref_v4_run.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _f32p, _f32p, ctypes.c_int]
         self.L = L
 
     def max_threads(self) -> int:
@@ -162,6 +217,43 @@ class RefV5:
         c = np.zeros((n, 128), np.float32) if c is None else c
         probs = np.zeros((n, n_frames), np.float32)
         self.lib.L.sref_v5_run(self.handle, _fp(audio), audio.shape[1], n, n_frames, hop, frame_len,
+                               int(denoise), _fp(h), _fp(c), _fp(probs), nthreads)
+        return probs, h, c
+
+
+class RefV4:
+    """Batched v4/16 kHz model: plain-C restatement.  State per stream: h[2][64], c[2][64]."""
+
+    DBG = 1032 + 1032 + 128 + 64 + 128 + 64 + 64 + 32 + 64 + 64
+
+    def __init__(self, blob: np.ndarray, lib: Optional[RefLib] = None):
+        self.lib = lib or RefLib()
+        self.blob = np.ascontiguousarray(blob, dtype=np.float32)
+        self.handle = ctypes.c_void_p(self.lib.L.sref_v4_create(_fp(self.blob)))
+
+    def __del__(self):
+        try:
+            self.lib.L.sref_v4_free(self.handle)
+        except Exception:
+            pass
+
+    def frame(self, x512: np.ndarray, h: np.ndarray, c: np.ndarray, want_dbg: bool = False):
+        x = np.ascontiguousarray(x512, dtype=np.float32)
+        assert x.shape == (512,) and h.shape == (2, 64) and c.shape == (2, 64)
+        p = np.zeros(1, np.float32)
+        dbg = np.zeros(self.DBG, np.float32) if want_dbg else None
+        self.lib.L.sref_v4_frame(self.handle, _fp(x), _fp(h), _fp(c), _fp(p), _fp(dbg) if want_dbg else None)
+        return float(p[0]), dbg
+
+    def run(self, audio: np.ndarray, n_frames: int, hop: int = 512, frame_len: int = 512, denoise: bool = True,
+            h: Optional[np.ndarray] = None, c: Optional[np.ndarray] = None, nthreads: int = 0):
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        n = audio.shape[0]
+        assert audio.shape[1] >= (n_frames - 1) * hop + frame_len
+        h = np.zeros((n, 2, 64), np.float32) if h is None else h
+        c = np.zeros((n, 2, 64), np.float32) if c is None else c
+        probs = np.zeros((n, n_frames), np.float32)
+        self.lib.L.sref_v4_run(self.handle, _fp(audio), audio.shape[1], n, n_frames, hop, frame_len,
                                int(denoise), _fp(h), _fp(c), _fp(probs), nthreads)
         return probs, h, c
 

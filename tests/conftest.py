@@ -77,3 +77,9 @@ def engine_factory():
     yield make
     for e in made:
         e.close()
+
+
+@pytest.fixture(scope="session")
+def ref_v4(ref_lib):
+    from vad_oracle import RefV4, v4_blob
+    return RefV4(v4_blob(str(V4_ONNX)), ref_lib)
