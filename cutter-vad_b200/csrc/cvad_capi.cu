@@ -12,6 +12,9 @@
 #include <vector>
 
 #include "../../include/cutter_vad_b200.h"
+#include <cmath>
+
+#include "cvad_resample.cuh"
 #include "cvad_v4.cuh"
 
 namespace {
@@ -47,6 +50,8 @@ struct cvad_engine {
     // scratch shared by every step (kernels of consecutive steps are serialised by `last_done`)
     DevBuf d_status_dev, d_feat, d_dbg, d_cfg_slots;
     cudaEvent_t last_done = nullptr;   // recorded after the kernels of the most recent step
+    float *rs_rt[3] = {nullptr, nullptr, nullptr};  // R^T for 8 / 24 / 48 kHz, built on first use
+    DevBuf d_res;                      // resampled 16 kHz audio of the step being launched
     // host-buffer steps run on two lanes so that step i+1's H2D overlaps step i's kernels
     struct Lane {
         cudaStream_t stream = nullptr;
@@ -279,6 +284,9 @@ int alloc_fill(cvad_engine *e, T **dst, size_t n, T value) {
 
 size_t elem_size(int pcm) { return pcm == CVAD_PCM_F32 ? 4 : 2; }
 
+int rate_index(int src_rate) { return src_rate == 8000 ? 0 : src_rate == 24000 ? 1 : src_rate == 48000 ? 2 : -1; }
+int rate_n_in(int src_rate) { return (int)((long long)src_rate * 512 / 16000); }
+
 int validate_args(cvad_engine *e, const cvad_step_args *a) {
     if (!e) return CVAD_E_INVALID;
     if (!a) return fail(e, CVAD_E_INVALID, "step args are NULL");
@@ -289,10 +297,40 @@ int validate_args(cvad_engine *e, const cvad_step_args *a) {
     if (a->max_frames < 0) return fail(e, CVAD_E_INVALID, "max_frames < 0");
     if (a->frame_len < 1 || a->frame_len > 2048) return fail(e, CVAD_E_INVALID, "frame_len outside [1, 2048]");
     if (a->hop < 1) return fail(e, CVAD_E_INVALID, "hop < 1");
-    if (a->src_rate != 0 && a->src_rate != 16000)
-        return fail(e, CVAD_E_INVALID, "src_rate: only 16000 is implemented in this build");
+    if (a->src_rate != 0 && a->src_rate != 16000) {
+        if (rate_index(a->src_rate) < 0) return fail(e, CVAD_E_INVALID, "src_rate must be 8000, 16000, 24000 or 48000");
+        const int n_in = rate_n_in(a->src_rate);
+        if (a->frame_len != n_in || a->hop != n_in)
+            return fail(e, CVAD_E_INVALID,
+                        "resampled streams: frame_len and hop must equal 512*src_rate/16000 source samples");
+    }
     if (a->max_events < 0) return fail(e, CVAD_E_INVALID, "max_events < 0");
     return CVAD_OK;
+}
+
+// R^T[m][n] of scipy.signal.resample(x[N_in] -> 512), float64 closed form rounded to float32
+// (formula and the two Nyquist rules: cvad_resample.cuh header).
+void build_resample_rt(int n_in, std::vector<float> &rt) {
+    const int num = 512;
+    const double PI = 3.14159265358979323846;
+    const int K = std::min(num, n_in) / 2;
+    rt.assign((size_t)n_in * num, 0.f);
+    for (int m = 0; m < n_in; ++m)
+        for (int n = 0; n < num; ++n) {
+            // theta/2 = pi (n/num - m/n_in), reduced with exact integer arithmetic
+            const long long L = (long long)num * n_in;
+            long long r = ((long long)n * n_in - (long long)m * num) % L;
+            if (r < 0) r += L;
+            const double half = PI * (double)r / (double)L;  // in [0, pi)
+            double dk;
+            if (r == 0) dk = 2.0 * K - 1.0;
+            else dk = std::sin((2.0 * K - 1.0) * half) / std::sin(half);
+            double nyq;
+            if (n_in > num) nyq = 2.0 * std::cos(PI * (double)(((long long)num * m) % (2LL * n_in)) / (double)n_in) *
+                                  ((n & 1) ? -1.0 : 1.0);
+            else nyq = std::cos(2.0 * K * half);
+            rt[(size_t)m * num + n] = (float)((dk + nyq) / (double)n_in);
+        }
 }
 
 // Enqueue the two kernels.  Every pointer in `a` is a DEVICE pointer here.
@@ -312,9 +350,35 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
     p.stride = a->stream_stride;
     p.frame_len = a->frame_len;
     p.hop = a->hop;
-    const size_t es = elem_size(a->pcm_format);
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(a->audio);
-    p.vec_ok = (addr % (4 * es) == 0) && (a->stream_stride % 4 == 0) && (a->hop % 4 == 0);
+    const bool resampled = a->src_rate != 0 && a->src_rate != 16000;
+    if (resampled) {
+        // stage 0: source-rate chunks -> 16 kHz float frames in HBM; the model kernels then see native input
+        const int ri = rate_index(a->src_rate), n_in = rate_n_in(a->src_rate);
+        if (!e->rs_rt[ri]) {
+            std::vector<float> rt;
+            build_resample_rt(n_in, rt);
+            CU_TRY(e, cudaMalloc(reinterpret_cast<void **>(&e->rs_rt[ri]), rt.size() * sizeof(float)));
+            CU_TRY(e, cudaMemcpyAsync(e->rs_rt[ri], rt.data(), rt.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+            CU_TRY(e, cudaStreamSynchronize(stream));
+        }
+        if ((rc = grow(e, e->d_res, (size_t)a->n_streams * a->max_frames * 512 * sizeof(float)))) return rc;
+        cvad::ResampleStep r{};
+        r.audio = a->audio; r.pcm = a->pcm_format; r.stride = a->stream_stride; r.n_in = n_in;
+        r.n_streams = a->n_streams; r.n_stiles = n_stiles; r.max_frames = a->max_frames; r.n_frames = a->n_frames;
+        r.rt = e->rs_rt[ri]; r.out = static_cast<float *>(e->d_res.p);
+        const int grid_rs = std::min(a->max_frames * n_stiles, e->num_sms);
+        cvad::resample_kernel<<<grid_rs, cvad::kThreads, cvad::kRsSmemBytes, stream>>>(r);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+        p.audio = e->d_res.p;
+        p.pcm = CVAD_PCM_F32;
+        p.stride = (long long)a->max_frames * 512;
+        p.frame_len = 512;
+        p.hop = 512;
+    }
+    const size_t es = elem_size(p.pcm);
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p.audio);
+    p.vec_ok = (addr % (4 * es) == 0) && (p.stride % 4 == 0) && (p.hop % 4 == 0);
     p.n_streams = a->n_streams;
     p.n_stiles = n_stiles;
     p.max_frames = a->max_frames;
@@ -642,6 +706,8 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
                                 (int)cvad::kFeSmemBytes));
     CR_TRY(cudaFuncSetAttribute(cvad::v5_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::kRecSmemBytes));
+    CR_TRY(cudaFuncSetAttribute(cvad::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::kRsSmemBytes));
     CR_TRY(cudaFuncSetAttribute(cvad::v4_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::kV4FeSmemBytes));
     CR_TRY(cudaFuncSetAttribute(cvad::v4_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -685,7 +751,8 @@ int cvad_destroy(cvad_engine *e) {
         if (ln.stream) cudaStreamSynchronize(ln.stream);
     void *ptrs[] = {e->w_fe, e->b_fe, e->w_rec, e->b_rec, e->w_dec, e->h_state, e->c_state, e->sm_active,
                     e->sm_scount, e->sm_ecount, e->frames_done, e->start_p, e->end_p, e->n_start, e->n_end,
-                    e->denoise, e->d_status_dev.p, e->d_feat.p, e->d_dbg.p, e->d_cfg_slots.p};
+                    e->denoise, e->d_status_dev.p, e->d_feat.p, e->d_dbg.p, e->d_cfg_slots.p, e->d_res.p,
+                    e->rs_rt[0], e->rs_rt[1], e->rs_rt[2]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &ln : e->lanes) {
@@ -863,6 +930,16 @@ int cvad_step_device(cvad_engine *e, const cvad_step_args *a) {
     CU_TRY(e, cudaMemsetAsync(d_status, 0, (size_t)a->n_streams * sizeof(unsigned int), e->stream));
     if (a->n_events_out) CU_TRY(e, cudaMemsetAsync(a->n_events_out, 0, sizeof(int), e->stream));
     return launch_step(e, a, d_status, 1, nullptr, e->stream);
+}
+
+int cvad_resample_matrix(int src_rate, float *rt_out, size_t n_floats) {
+    if (rate_index(src_rate) < 0 || !rt_out) return CVAD_E_INVALID;
+    const int n_in = rate_n_in(src_rate);
+    if (n_floats < (size_t)n_in * 512) return CVAD_E_CAPACITY;
+    std::vector<float> rt;
+    build_resample_rt(n_in, rt);
+    std::memcpy(rt_out, rt.data(), rt.size() * sizeof(float));
+    return n_in;
 }
 
 int cvad_step_submit(cvad_engine *e, const cvad_step_args *a, int *ticket) {

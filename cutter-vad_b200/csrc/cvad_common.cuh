@@ -133,4 +133,10 @@ struct WeightRing {
     uint32_t g;          // chunks consumed so far by this CTA (uniform across threads)
 };
 
+__device__ __forceinline__ const float *ring_wait(const WeightRing &r) {
+    const uint32_t slot = r.g % kRingStages;
+    mbar_wait(&r.bars[slot], (r.g / kRingStages) & 1u);
+    return r.buf + slot * kRingSlotFloats;
+}
+
 }  // namespace cvad

@@ -60,12 +60,6 @@ __device__ __forceinline__ void rec_ring_issue(const WeightRing &r, uint32_t g) 
     bulk_g2s(r.buf + slot * kRingSlotFloats, r.gsrc + ci * kRingSlotFloats, kRingSlotFloats * 4u, &r.bars[slot]);
 }
 
-__device__ __forceinline__ const float *ring_wait(const WeightRing &r) {
-    const uint32_t slot = r.g % kRingStages;
-    mbar_wait(&r.bars[slot], (r.g / kRingStages) & 1u);
-    return r.buf + slot * kRingSlotFloats;
-}
-
 // ---------------------------------------------------------------- step parameters
 struct V5Step {
     const void *audio;            // device

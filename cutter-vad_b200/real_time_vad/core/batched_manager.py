@@ -69,7 +69,15 @@ class _Stream:
 class BatchedVADManager:
     def __init__(self, max_streams: int = 4096, model_version: SileroModelVersion = SileroModelVersion.V5,
                  device: Optional[int] = None, frame_len: int = 512, hop: Optional[int] = None,
-                 pcm_format: int = capi.PCM_F32) -> None:
+                 pcm_format: int = capi.PCM_F32, source_rate: int = 16000) -> None:
+        """`source_rate` 8000 / 24000 / 48000: streams deliver audio at that rate and every chunk of
+        512*rate/16000 samples is resampled to one 16 kHz model frame on the GPU (frame_len and hop
+        are then fixed to that chunk size)."""
+        if source_rate not in (8000, 16000, 24000, 48000):
+            raise ConfigurationError("source_rate", str(source_rate))
+        self.source_rate = int(source_rate)
+        if source_rate != 16000:
+            frame_len = hop = source_rate * 512 // 16000
         if not (1 <= frame_len <= 2048):
             raise ConfigurationError("frame_len", str(frame_len))
         self.frame_len = int(frame_len)
@@ -98,9 +106,9 @@ class BatchedVADManager:
                     on_voice_end: Optional[Callable[[bytes], None]] = None,
                     on_voice_continue: Optional[Callable[[bytes], None]] = None) -> int:
         cfg = config if config is not None else VADConfig()
-        if int(cfg.sample_rate) != 16000:
+        if int(cfg.sample_rate) != self.source_rate:
             raise ConfigurationError("sample_rate", str(cfg.sample_rate),
-                                     "BatchedVADManager streams are 16 kHz; resample before push()")
+                                     f"this manager takes {self.source_rate} Hz streams")
         with self._lock:
             if not self._free:
                 raise VADError(f"all {self.max_streams} stream slots are in use")
@@ -181,6 +189,11 @@ class BatchedVADManager:
             f = f / np.float32(32767.0)
         elif self.pcm_format == capi.PCM_S16_32768:
             f = f / np.float32(32768.0)
+        if self.source_rate != 16000:
+            # callback payloads are 16 kHz audio: same operator as the GPU resampler, host side,
+            # only for the frames that actually reach a payload
+            from ..utils.audio import AudioUtils
+            f = AudioUtils.resample_audio(f, self.source_rate, 16000)
         if st.config.enable_denoising:
             f = np.where(np.abs(f) > 0.01, f, 0.0).astype(np.float32)
         return f
@@ -206,7 +219,7 @@ class BatchedVADManager:
                 use = (counts[k] - 1) * self.hop + self.frame_len
                 block[k, :use] = p[:use]
             r = self._engine.step(block, slots=ids, n_frames=counts, max_frames=tmax, frame_len=self.frame_len,
-                                  hop=self.hop, pcm_format=self.pcm_format)
+                                  hop=self.hop, pcm_format=self.pcm_format, src_rate=self.source_rate)
             events: List[StreamEvent] = []
             probs: Dict[int, np.ndarray] = {}
             for k, sid in enumerate(ids):
@@ -285,7 +298,7 @@ class BatchedVADManager:
         ids = list(self.open_streams) if stream_ids is None else list(stream_ids)
         with self._lock:
             return self._engine.step(audio, slots=ids, frame_len=self.frame_len, hop=self.hop,
-                                     pcm_format=self.pcm_format)
+                                     pcm_format=self.pcm_format, src_rate=self.source_rate)
 
     def close(self) -> None:
         with self._lock:

@@ -106,6 +106,16 @@ class StreamEngine:
     def set_stream(self, cuda_stream: int) -> None:
         self._check(self._L.cvad_set_stream(self._h, C.c_void_p(cuda_stream)))
 
+    @staticmethod
+    def resample_matrix(src_rate: int) -> np.ndarray:
+        """R^T [n_in][512] of the engine's resampler (== scipy.signal.resample's operator)."""
+        n_in = src_rate * 512 // 16000
+        rt = np.zeros((n_in, 512), np.float32)
+        rc = capi.lib().cvad_resample_matrix(int(src_rate), rt.ctypes.data, rt.size)
+        if rc != n_in:
+            raise EngineError(rc, f"no resampler for {src_rate} Hz")
+        return rt
+
     def sync(self) -> None:
         self._check(self._L.cvad_sync(self._h))
 
@@ -161,7 +171,7 @@ class StreamEngine:
         self._check(self._L.cvad_set_state(self._h, int(slot), _ptr(h), _ptr(c), _ptr(sm)))
 
     # ------------------------------------------------------------------ the hot call
-    def _args(self, audio: np.ndarray, slots, n_frames, max_frames, frame_len, hop, pcm_format):
+    def _args(self, audio: np.ndarray, slots, n_frames, max_frames, frame_len, hop, pcm_format, src_rate=16000):
         if audio.ndim != 2:
             raise EngineError(capi.E_INVALID, "audio must be [n_streams, samples]")
         if pcm_format == capi.PCM_F32:
@@ -190,20 +200,23 @@ class StreamEngine:
         a.max_frames = int(max_frames)
         a.frame_len = int(frame_len)
         a.hop = int(hop)
-        a.src_rate = 16000
+        a.src_rate = int(src_rate)
         return a, keep
 
     def submit(self, audio: np.ndarray, *, slots: Optional[Sequence[int]] = None,
                n_frames: Optional[Sequence[int]] = None, max_frames: Optional[int] = None,
                frame_len: int = 512, hop: int = 512, pcm_format: int = capi.PCM_F32,
-               max_events: int = 0) -> "PendingStep":
+               max_events: int = 0, src_rate: int = 16000) -> "PendingStep":
         """Enqueue one step (H2D, kernels, D2H) and return at once; `.collect()` waits for it.
         Up to two steps may be in flight: the second one's copy overlaps the first one's kernels.
         `audio` must stay untouched until collect (pinned arrays are DMA'd in place)."""
         audio = np.asarray(audio)
+        if src_rate not in (0, 16000):
+            # source-rate input: every chunk of 512*src_rate/16000 samples becomes one model frame
+            frame_len = hop = src_rate * 512 // 16000
         if max_frames is None:
             max_frames = 0 if audio.shape[1] < frame_len else (audio.shape[1] - frame_len) // hop + 1
-        a, keep = self._args(audio, slots, n_frames, max_frames, frame_len, hop, pcm_format)
+        a, keep = self._args(audio, slots, n_frames, max_frames, frame_len, hop, pcm_format, src_rate)
         n = a.n_streams
         probs = np.empty((n, max_frames), np.float32)
         flags = np.empty((n, max_frames), np.uint8)

@@ -93,7 +93,9 @@ typedef struct cvad_step_args {
     int32_t max_frames;       /* row length of probs_out / flags_out */
     int32_t frame_len;        /* samples per frame before zero-padding/truncation to 512 (1..2048) */
     int32_t hop;              /* samples between frame starts (>= 1) */
-    int32_t src_rate;         /* 16000 (no resampling); 8000/24000/48000 reserved for the fused resampler */
+    int32_t src_rate;         /* 16000 or 0: native.  8000/24000/48000: every chunk of 512*src_rate/16000 source
+                                 samples (= frame_len = hop) is resampled to one 512-sample frame on the GPU with
+                                 scipy.signal.resample's operator (AudioUtils.resample_audio, audio.py:19-55) */
     float *probs_out;         /* [n_streams][max_frames] speech probabilities (may be NULL) */
     uint8_t *flags_out;       /* [n_streams][max_frames] CVAD_FLAG_* (may be NULL) */
     uint8_t *status_out;      /* [n_streams] CVAD_STATUS_* (may be NULL) */
@@ -162,6 +164,10 @@ int cvad_step_device(cvad_engine *e, const cvad_step_args *a);
 
 /* Block until everything enqueued on the engine's stream has finished. */
 int cvad_sync(cvad_engine *e);
+
+/* The resampler's operator for tests and non-GPU hosts: R^T[m][n] (n_in x 512 floats, row-major)
+   such that y[n] = sum_m R^T[m][n] x[m] equals scipy.signal.resample(x, 512).  Returns n_in. */
+int cvad_resample_matrix(int src_rate, float *rt_out, size_t n_floats);
 
 /* Page-locked host memory for callers that want cvad_step to DMA straight from their
    buffer (pageable buffers are staged through the engine's own pinned area). */

@@ -87,3 +87,18 @@ def test_missing_library_is_an_error_not_a_fallback(tmp_path, monkeypatch):
     monkeypatch.setattr(capi, "_lib", None)
     monkeypatch.delenv("CVAD_B200_LIB")
     capi.lib()
+
+
+@pytest.mark.parametrize("rate,n_in", [(8000, 256), (24000, 768), (48000, 1536)])
+def test_resample_operator_equals_scipy(rate, n_in):
+    """The closed-form R^T the engine uploads == scipy.signal.resample applied to the identity
+    (incl. both Nyquist rules), i.e. AudioUtils.resample_audio on one chunk (audio.py:19-55)."""
+    from scipy import signal
+    from real_time_vad.engine.stream_engine import StreamEngine
+    rt = StreamEngine.resample_matrix(rate)
+    assert rt.shape == (n_in, 512)
+    R = signal.resample(np.eye(n_in), 512, axis=0)
+    assert np.abs(rt.T - R).max() < 6e-8
+    x = np.random.default_rng(rate).standard_normal(n_in).astype(np.float32)
+    y = signal.resample(x, 512).astype(np.float32)
+    assert np.abs(x.astype(np.float64) @ rt.astype(np.float64) - y).max() < 2e-6

@@ -1,0 +1,115 @@
+"""GPU: fused 8/24/48 kHz -> 16 kHz resampling.
+
+Oracle: AudioUtils.resample_audio (= scipy.signal.resample, FFT method) applied to each
+chunk of 512*sr/16000 source samples, then the 16 kHz model -- the definition SURVEY.md
+section 0 fact 4 / section 7 gives, since the reference itself never resamples on its path."""
+import numpy as np
+import pytest
+
+from conftest import synth_streams
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _source_audio(n, T, rate, seed):
+    """Band-limited source-rate signal: the 16 kHz recipe upsampled by scipy, plus a little wideband noise."""
+    from scipy import signal
+    n_in = rate * 512 // 16000
+    base = synth_streams(n, 512 * T, seed=seed)
+    up = signal.resample(base, n_in * T, axis=1).astype(np.float32)
+    up += (0.003 * np.random.default_rng(seed).standard_normal(up.shape)).astype(np.float32)
+    return up, n_in
+
+
+def _oracle_16k(x, n_in):
+    from vad_oracle import resample
+    n, L = x.shape
+    T = L // n_in
+    y = np.zeros((n, 512 * T), np.float32)
+    rate = n_in * 16000 // 512
+    for s in range(n):
+        for j in range(T):
+            y[s, j * 512:(j + 1) * 512] = resample(x[s, j * n_in:(j + 1) * n_in], rate, 16000)
+    return y
+
+
+@pytest.mark.parametrize("rate", [8000, 24000, 48000])
+def test_resampled_streams_match_scipy_then_model(engine_factory, ref_v5, rate):
+    eng = engine_factory(128)
+    eng.reset()
+    eng.configure(enable_denoising=False)
+    n, T = 37, 12
+    x, n_in = _source_audio(n, T, rate, seed=rate // 1000)
+    y = _oracle_16k(x, n_in)
+    want, _, _ = ref_v5.run(y, T, denoise=False)
+    r1 = eng.step(x[:, :n_in * 5], src_rate=rate)            # two calls: state carries across resampled steps
+    r2 = eng.step(x[:, n_in * 5:], src_rate=rate)
+    got = np.concatenate([r1.probs, r2.probs], axis=1)
+    assert got.shape == (n, T)
+    assert np.abs(got - want).max() <= TOL
+
+
+def test_resampled_int16_with_noise_gate(engine_factory, ref_v5):
+    """48 kHz int16 PCM, gate on.  The gate (|x| > 0.01) is discontinuous, so a resampled sample
+    within 1e-6 of the threshold may fall on the other side than scipy's FP32 FFT puts it; such a
+    flip moves one sample by 0.01.  Assert the 1e-4 bar on (nearly) all frames and a loose bound on all."""
+    from real_time_vad.engine import capi
+    eng = engine_factory(128)
+    eng.reset()
+    eng.configure(enable_denoising=True)
+    n, T = 33, 10
+    x, n_in = _source_audio(n, T, 48000, seed=5)
+    q = np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16)
+    xf = q.astype(np.float32) / np.float32(32767.0)
+    want, _, _ = ref_v5.run(_oracle_16k(xf, n_in), T, denoise=True)
+    r = eng.step(q, src_rate=48000, pcm_format=capi.PCM_S16_32767)
+    err = np.abs(r.probs - want)
+    assert (err <= TOL).mean() >= 0.99
+    assert err.max() <= 5e-3
+
+
+def test_resampled_v4_model_8k(engine_factory, ref_v4):
+    """BASELINE config 3: v4 model, 8 kHz streams resampled to 16 kHz in-kernel."""
+    eng = engine_factory(128, model_version="v4")
+    eng.reset()
+    eng.configure(enable_denoising=False)
+    n, T = 40, 9
+    x, n_in = _source_audio(n, T, 8000, seed=8)
+    assert n_in == 256
+    want, _, _ = ref_v4.run(_oracle_16k(x, n_in), T, denoise=False)
+    r = eng.step(x, src_rate=8000)
+    assert np.abs(r.probs - want).max() <= TOL
+
+
+def test_resampler_argument_checks(engine_factory):
+    from real_time_vad.engine.stream_engine import EngineError
+    eng = engine_factory(128)
+    with pytest.raises(EngineError):
+        eng.step(np.zeros((2, 4096), np.float32), src_rate=44100)
+    with pytest.raises(EngineError):                            # frame_len/hop must be the chunk size
+        a, keep = eng._args(np.zeros((2, 1536), np.float32), None, None, 1, 512, 512, 0, 48000)
+        eng._check(eng._L.cvad_step(eng.handle, __import__("ctypes").byref(a)))
+
+
+def test_batched_manager_with_24k_streams(ref_v5):
+    from real_time_vad import BatchedVADManager, SampleRate, VADConfig
+    n, T = 9, 14
+    x, n_in = _source_audio(n, T, 24000, seed=24)
+    cfg = VADConfig(sample_rate=SampleRate.SAMPLERATE_24, enable_denoising=False, vad_start_probability=0.5,
+                    vad_end_probability=0.35, voice_start_frame_count=2, voice_end_frame_count=3)
+    mgr = BatchedVADManager(max_streams=16, source_rate=24000)
+    assert mgr.frame_len == 768
+    ids = [mgr.open_stream(cfg) for _ in range(n)]
+    probs = {i: [] for i in ids}
+    for lo in range(0, x.shape[1], 1000):                        # arbitrary push sizes
+        for k, sid in enumerate(ids):
+            mgr.push(sid, x[k, lo:lo + 1000])
+        out = mgr.step()
+        for sid, p in out.probabilities.items():
+            probs[sid].append(p)
+    want, _, _ = ref_v5.run(_oracle_16k(x, n_in), T, denoise=False)
+    for k, sid in enumerate(ids):
+        got = np.concatenate(probs[sid])
+        assert len(got) == T and np.abs(got - want[k]).max() <= TOL
+    mgr.close()
