@@ -203,8 +203,12 @@ def run_reference_arm(args):
 
 
 def workload_config(args, pool_mb):
-    return {"workload": f"Silero v5, {args.streams} concurrent 16 kHz streams per GPU batched per frame step "
-                        f"(BASELINE.json configs[1])",
+    model = getattr(args, "model", "v5")
+    rate = getattr(args, "src_rate", 16000)
+    return {"workload": f"Silero {model}, {args.streams} concurrent {rate // 1000} kHz streams per GPU batched per "
+                        f"frame step" + (" (BASELINE.json configs[1])" if (model, rate) == ("v5", 16000) else
+                                         ", resampled to 16 kHz on the GPU" if rate != 16000 else ""),
+            "model": model, "src_rate": rate,
             "streams_per_gpu": args.streams, "frames_per_step": args.frames_per_step, "hop": 512,
             "frame_len": 512, "denoise": True, "state_machine": True,
             "l2": (f"inputs cycle through a pool of distinct step buffers totalling {pool_mb} MB (> 126 MB L2)"
@@ -229,13 +233,20 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n, F = args.streams, args.frames_per_step
-    step_samples = 512 * F
+    n_in = args.src_rate * 512 // 16000          # source samples per model frame
+    step_samples = n_in * F
     step_bytes = n * step_samples * 4
     pool_n = max(2, int(np.ceil(300e6 / step_bytes)))  # > 2x L2 worth of distinct inputs
     pool_n = min(pool_n, 64)
     peaks, peaks_src = load_peaks()
 
-    eng = StreamEngine("v5", max_streams=n, device=local)
+    eng = StreamEngine(args.model, max_streams=n, device=local)
+    flop_frame = FLOP_FRAME if args.model == "v5" else 1_379_280
+    flop_fe = FLOP_FRONTEND if args.model == "v5" else 1_379_280 - 2 * 65_600
+    flop_rec = FLOP_RECURRENT if args.model == "v5" else 2 * 65_600
+    if args.src_rate != 16000:
+        flop_fe += 2 * 512 * n_in                  # the resampling GEMM runs ahead of the front end
+        flop_frame += 2 * 512 * n_in
     eng.configure(enable_denoising=True)
     stream = torch.cuda.Stream(device=local)
     eng.set_stream(stream.cuda_stream)
@@ -259,9 +270,9 @@ def run_ours(args):
         a.pcm_format = capi.PCM_F32
         a.stream_stride = step_samples
         a.max_frames = F
-        a.frame_len = 512
-        a.hop = 512
-        a.src_rate = 16000
+        a.frame_len = n_in
+        a.hop = n_in
+        a.src_rate = args.src_rate
         a.probs_out = d_probs.data_ptr()
         a.flags_out = d_flags.data_ptr()
         a.events_out = d_events.data_ptr()
@@ -314,14 +325,14 @@ def run_ours(args):
     eng.reset()
     host_np = [t.numpy() for t in host_pool]
     for i in range(args.warmup):
-        eng.step(host_np[i % pool_n])
+        eng.step(host_np[i % pool_n], src_rate=args.src_rate)
     barrier()
     # (a) blocking calls: one step at a time -> per-call latency distribution
     e2e_lat = []
     t0 = time.perf_counter()
     for i in range(min(args.steps, 300)):
         t1 = time.perf_counter()
-        r = eng.step(host_np[(args.warmup + i) % pool_n])
+        r = eng.step(host_np[(args.warmup + i) % pool_n], src_rate=args.src_rate)
         e2e_lat.append(time.perf_counter() - t1)
     torch.cuda.synchronize()
     e2e_blocking_s = (time.perf_counter() - t0) / min(args.steps, 300)
@@ -330,9 +341,9 @@ def run_ours(args):
     eng.reset()
     barrier()
     t0 = time.perf_counter()
-    pending = eng.submit(host_np[args.warmup % pool_n])
+    pending = eng.submit(host_np[args.warmup % pool_n], src_rate=args.src_rate)
     for i in range(1, args.steps):
-        nxt = eng.submit(host_np[(args.warmup + i) % pool_n])
+        nxt = eng.submit(host_np[(args.warmup + i) % pool_n], src_rate=args.src_rate)
         r = pending.collect()
         pending = nxt
     r = pending.collect()
@@ -355,11 +366,12 @@ def run_ours(args):
     peak_fp32 = SMS * FP32_LANES * 2 * sm_max * 1e6 / 1e12
     fe_avg_s = fe_ms / max(n_timed, 1) * 1e-3
     rec_avg_s = rec_ms / max(n_timed, 1) * 1e-3
-    fe_tflops = frames_per_step * FLOP_FRONTEND / fe_avg_s / 1e12 if fe_avg_s > 0 else 0.0
-    step_tflops = frames_per_step * FLOP_FRAME / (dev_ms / args.steps * 1e-3) / 1e12
+    fe_tflops = frames_per_step * flop_fe / fe_avg_s / 1e12 if fe_avg_s > 0 else 0.0
+    step_tflops = frames_per_step * flop_frame / (dev_ms / args.steps * 1e-3) / 1e12
 
     if rank == 0:
-        traffic = ncu_traffic_bytes("v5_frontend_kernel") if (n == 4096 and F == 1) else None
+        traffic = (ncu_traffic_bytes("v5_frontend_kernel")
+                   if (n == 4096 and F == 1 and args.model == "v5" and args.src_rate == 16000) else None)
         cpu = None if args.skip_cpu else cpu_baseline_sample(n)
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
@@ -369,19 +381,20 @@ def run_ours(args):
             "p99_step_ms": float(np.percentile(lat, 99)), "p50_step_ms": float(np.percentile(lat, 50)),
             "frames_per_s": value / 0.032,
             "roofline": {
-                "bound": "fp32_ffma", "kernel": "v5_frontend_kernel", "achieved": fe_tflops, "peak": peak_fp32,
+                "bound": "fp32_ffma", "kernel": f"{args.model}_frontend_kernel" +
+                ("+resample_kernel" if args.src_rate != 16000 else ""), "achieved": fe_tflops, "peak": peak_fp32,
                 "unit": "TFLOP/s", "frac": fe_tflops / peak_fp32,
                 "traffic": (traffic or {}).get("bytes"), "traffic_source": (traffic or {}).get("source"),
                 "algorithmic_bytes_per_launch": frames_per_step * 2048 + 156032 * 4 + frames_per_step * 512,
                 "peak_source": f"148 SMs x 128 FP32 lanes x 2 x sm_max_mhz {sm_max:.0f} ({peaks_src} "
                                "MEASURED_PEAKS.json clock); the path is FP32-FFMA bound, not HBM or tensor bound",
-                "algorithmic_flop_per_frame": FLOP_FRONTEND, "frames_per_launch": frames_per_step,
+                "algorithmic_flop_per_frame": flop_fe, "frames_per_launch": frames_per_step,
                 "avg_launch_ms": fe_avg_s * 1e3,
                 "recurrent_kernel": {"avg_launch_ms": rec_avg_s * 1e3,
-                                     "achieved": frames_per_step * FLOP_RECURRENT / rec_avg_s / 1e12 if rec_avg_s else 0,
-                                     "algorithmic_flop_per_frame": FLOP_RECURRENT},
+                                     "achieved": frames_per_step * flop_rec / rec_avg_s / 1e12 if rec_avg_s else 0,
+                                     "algorithmic_flop_per_frame": flop_rec},
                 "whole_step": {"achieved": step_tflops, "frac": step_tflops / peak_fp32,
-                               "algorithmic_flop_per_frame": FLOP_FRAME},
+                               "algorithmic_flop_per_frame": flop_frame},
                 "hbm": {"algorithmic_bytes_per_frame": 2048 + 2 * 1024 + 4 + 1,
                         "achieved_gbs": frames_per_step * (2048 + 2048 + 5) / (dev_ms / args.steps * 1e-3) / 1e9,
                         "peak_gbs": peaks.get("hbm_gbs")},
@@ -413,6 +426,9 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
     ap.add_argument("--frames-per-step", type=int, default=1, help="512-sample frames per stream per step")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--model", choices=["v5", "v4"], default="v5", help="v5 = headline (configs[1]); v4 = configs[2]")
+    ap.add_argument("--src-rate", type=int, default=16000, choices=[8000, 16000, 24000, 48000],
+                    help="source rate of the synthetic streams; != 16000 adds the GPU resampler (configs[2..3])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -339,6 +339,18 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
     if (a->n_streams == 0 || a->max_frames == 0) return CVAD_OK;
     // state and `feat` are shared: kernels of consecutive steps never overlap, whatever stream they use
     CU_TRY(e, cudaStreamWaitEvent(stream, e->last_done, 0));
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    const bool timed = e->timing && !d_dbg;
+    if (timed) {
+        while (e->ev_pool.size() < e->ev_used + 3) {
+            cudaEvent_t x;
+            CU_TRY(e, cudaEventCreate(&x));
+            e->ev_pool.push_back(x);
+        }
+        for (int i = 0; i < 3; ++i) ev[i] = e->ev_pool[e->ev_used + i];
+        e->ev_used += 3;
+        CU_TRY(e, cudaEventRecord(ev[0], stream));
+    }
     const int n_stiles = (a->n_streams + cvad::kTile - 1) / cvad::kTile;
     const size_t feat_bytes = (size_t)a->max_frames * n_stiles * 128 * cvad::kTile * sizeof(float);
     int rc = grow(e, e->d_feat, feat_bytes);
@@ -404,18 +416,6 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
     const bool v4 = e->version == CVAD_MODEL_V4;
     const int n_tiles = a->max_frames * n_stiles * (v4 ? 2 : 1);
     const int grid_fe = std::min(n_tiles, e->num_sms);
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    const bool timed = e->timing && !d_dbg;
-    if (timed) {
-        while (e->ev_pool.size() < e->ev_used + 3) {
-            cudaEvent_t x;
-            CU_TRY(e, cudaEventCreate(&x));
-            e->ev_pool.push_back(x);
-        }
-        for (int i = 0; i < 3; ++i) ev[i] = e->ev_pool[e->ev_used + i];
-        e->ev_used += 3;
-        CU_TRY(e, cudaEventRecord(ev[0], stream));
-    }
     if (v4) cvad::v4_frontend_kernel<<<grid_fe, cvad::kThreads, cvad::kV4FeSmemBytes, stream>>>(p);
     else cvad::v5_frontend_kernel<<<grid_fe, cvad::kThreads, cvad::kFeSmemBytes, stream>>>(p);
     CU_TRY(e, cudaGetLastError());

@@ -115,3 +115,27 @@ def test_framing_counts_like_the_reference():
     x = np.arange(10, dtype=np.float32)
     f = split_into_frames(x, 4, 2)
     assert f.tolist() == [[0, 1, 2, 3], [2, 3, 4, 5], [4, 5, 6, 7], [6, 7, 8, 9]]
+
+
+def test_v4_is_ill_conditioned_on_band_limited_input(ref_v4, ref_v5):
+    """Why the 8 kHz -> v4 parity bound is looser than 1e-4 (tests/test_gpu_resample.py): v4 feeds
+    log(1 + 2^20 |STFT|) into the network, so the empty 4-8 kHz band of up-sampled audio turns
+    rounding noise into signal.  Two CPU resamplers that agree to < 3e-7 on the audio -- scipy's FP32
+    FFT and the exact operator rounded once -- move v4's probability by > 1e-4, but v5's by ~1e-6."""
+    from scipy import signal
+    from conftest import synth_streams
+    n, T, n_in = 24, 9, 256
+    up = signal.resample(synth_streams(n, 512 * T, seed=8), n_in * T, axis=1).astype(np.float32)
+    R = signal.resample(np.eye(n_in), 512, axis=0)                       # [512][256], float64
+    ya = np.zeros((n, 512 * T), np.float32)
+    yb = np.zeros_like(ya)
+    for s in range(n):
+        for j in range(T):
+            ch = up[s, j * n_in:(j + 1) * n_in]
+            ya[s, j * 512:(j + 1) * 512] = signal.resample(ch, 512).astype(np.float32)
+            yb[s, j * 512:(j + 1) * 512] = (R @ ch.astype(np.float64)).astype(np.float32)
+    assert np.abs(ya - yb).max() < 1e-6
+    d4 = np.abs(ref_v4.run(ya, T, denoise=False)[0] - ref_v4.run(yb, T, denoise=False)[0])
+    d5 = np.abs(ref_v5.run(ya, T, denoise=False)[0] - ref_v5.run(yb, T, denoise=False)[0])
+    assert d5.max() < 2e-5
+    assert d4.max() > 1e-4 and d4.max() > 20 * d5.max()
