@@ -147,7 +147,7 @@ def cpu_port(native=True):
 def cpu_baseline_sample(n_streams: int, target_s: float = 12.0):
     """Oracle port (plain C + OpenMP, every host thread) on a bounded sample of the workload."""
     lib, ref = cpu_port()
-    cores = lib.max_threads()
+    cores = host_threads()
     n = min(n_streams, 1024)
     audio = synth_audio(n, 512 * 8, seed=99)
     t0 = time.perf_counter()
@@ -171,7 +171,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     lib, ref = cpu_port()
-    cores = lib.max_threads()
+    cores = host_threads()
     n, F = args.streams, args.frames_per_step
     pool = [synth_audio(n, 512 * F, seed=1000 + i) for i in range(4)]
     h = np.zeros((n, 128), np.float32)
@@ -199,7 +199,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, pool_mb):
@@ -411,10 +411,36 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line there.
+    Send fd 1 to stderr for the duration of the run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def host_threads() -> int:
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm ignores it)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def main():
@@ -431,6 +457,7 @@ def main():
                     help="source rate of the synthetic streams; != 16000 adds the GPU resampler (configs[2..3])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    _protect_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
