@@ -42,18 +42,28 @@ class StreamEvent(NamedTuple):
     step_frame: int       # frame index inside the step that produced it
 
 
-@dataclass
 class StepOutput:
-    events: List[StreamEvent]
-    probabilities: Dict[int, np.ndarray]   # stream id -> probabilities of the frames run in this step
-    frames: int                            # total frames run in this step
+    """Result of one `step()`.  Arrays are per stepped stream (row k <-> stream_ids[k])."""
+
+    def __init__(self, events: List[StreamEvent], stream_ids: np.ndarray, counts: np.ndarray,
+                 probs: np.ndarray, flags: np.ndarray):
+        self.events = events                 # stream-then-frame order
+        self.stream_ids = stream_ids         # [n] slot ids that ran at least one frame
+        self.counts = counts                 # [n] frames run per stream
+        self.probs = probs                   # [n, max(counts)] float32 (columns >= counts[k] are 0)
+        self.flags = flags                   # [n, max(counts)] uint8, FLAG_* bits
+        self.frames = int(counts.sum()) if counts.size else 0
+
+    @property
+    def probabilities(self) -> Dict[int, np.ndarray]:
+        """stream id -> probabilities of the frames run in this step (built on demand)."""
+        return {int(s): self.probs[k, :int(c)].copy() for k, (s, c) in enumerate(zip(self.stream_ids, self.counts))}
 
 
 @dataclass
 class _Stream:
     config: VADConfig
     writer: WAVWriter
-    pending: np.ndarray
     on_start: Optional[Callable[[], None]] = None
     on_end: Optional[Callable[[bytes], None]] = None
     on_continue: Optional[Callable[[bytes], None]] = None
@@ -96,6 +106,14 @@ class BatchedVADManager:
         self._free = list(range(max_streams - 1, -1, -1))
         self._streams: Dict[int, _Stream] = {}
         self._lock = threading.Lock()
+        # pending audio lives in one arena [slot][sample] with a fill count per slot, so that a step
+        # gathers / compacts all streams with a handful of numpy calls instead of a Python loop
+        self._cap = self.frame_len + 8 * max(self.hop, self.frame_len)
+        self._buf = np.zeros((max_streams, self._cap), self._dtype)
+        self._fill = np.zeros(max_streams, np.int64)
+        self._open = np.zeros(max_streams, bool)
+        self._has_cb = np.zeros(max_streams, bool)
+        self._active = np.zeros(max_streams, bool)
 
     # ------------------------------------------------------------------ stream lifecycle
     @property
@@ -117,8 +135,11 @@ class BatchedVADManager:
             self._apply_config(sid, cfg)
             self._streams[sid] = _Stream(
                 config=cfg, writer=WAVWriter(cfg.output_wav_sample_rate, cfg.output_wav_bit_depth, 1),
-                pending=np.zeros(0, self._dtype), on_start=on_voice_start, on_end=on_voice_end,
-                on_continue=on_voice_continue)
+                on_start=on_voice_start, on_end=on_voice_end, on_continue=on_voice_continue)
+            self._fill[sid] = 0
+            self._active[sid] = False
+            self._open[sid] = True
+            self._has_cb[sid] = any(cb is not None for cb in (on_voice_start, on_voice_end, on_voice_continue))
             return sid
 
     def _apply_config(self, sid: int, cfg: VADConfig) -> None:
@@ -132,6 +153,8 @@ class BatchedVADManager:
         with self._lock:
             if self._streams.pop(stream_id, None) is not None:
                 self._engine.reset([stream_id])
+                self._open[stream_id] = False
+                self._fill[stream_id] = 0
                 self._free.append(stream_id)
 
     def reset_stream(self, stream_id: int) -> None:
@@ -139,7 +162,8 @@ class BatchedVADManager:
         with self._lock:
             st = self._stream(stream_id)
             self._engine.reset([stream_id])
-            st.pending = np.zeros(0, self._dtype)
+            self._fill[stream_id] = 0
+            self._active[stream_id] = False
             st.active = False
             st.pre_roll.clear()
             st.segment.clear()
@@ -159,29 +183,64 @@ class BatchedVADManager:
             raise VADError(f"stream {stream_id} is not open")
 
     def is_voice_active(self, stream_id: int) -> bool:
-        return self._stream(stream_id).active
+        self._stream(stream_id)
+        return bool(self._active[stream_id])
 
     @property
     def open_streams(self) -> List[int]:
         return sorted(self._streams)
 
     # ------------------------------------------------------------------ data path
-    def push(self, stream_id: int, samples) -> None:
-        """Append audio to a stream's buffer (no GPU work).  NaN/Inf is rejected here, before any
-        state changes, as `AudioUtils.validate_audio_data` does (audio.py:227-228)."""
-        st = self._stream(stream_id)
+    def _check_samples(self, samples) -> np.ndarray:
         x = np.asarray(samples)
         if x.size == 0:
             raise AudioProcessingError("Audio data is empty")
-        if x.ndim == 2:
-            x = x.mean(axis=1)
         if self._dtype == np.float32:
             x = x.astype(np.float32, copy=False)
             if not np.isfinite(x).all():
                 raise AudioProcessingError("Audio data contains infinite or NaN values")
         else:
             x = x.astype(np.int16, copy=False)
-        st.pending = x.copy() if st.pending.size == 0 else np.concatenate([st.pending, x])
+        return x
+
+    def _ensure_cap(self, need: int) -> None:
+        if need <= self._cap:
+            return
+        cap = max(need, 2 * self._cap)
+        buf = np.zeros((self.max_streams, cap), self._dtype)
+        buf[:, :self._cap] = self._buf
+        self._buf, self._cap = buf, cap
+
+    def push(self, stream_id: int, samples) -> None:
+        """Append audio to a stream's buffer (no GPU work).  NaN/Inf is rejected here, before any
+        state changes, as `AudioUtils.validate_audio_data` does (audio.py:227-228)."""
+        self._stream(stream_id)
+        x = self._check_samples(samples)
+        if x.ndim == 2:
+            x = x.mean(axis=1).astype(self._dtype)
+        f = int(self._fill[stream_id])
+        self._ensure_cap(f + x.size)
+        self._buf[stream_id, f:f + x.size] = x
+        self._fill[stream_id] = f + x.size
+
+    def push_many(self, stream_ids: Sequence[int], block: np.ndarray) -> None:
+        """Lock-step producers: `block[k]` is appended to stream `stream_ids[k]` (all rows the same length)."""
+        ids = np.asarray(stream_ids, np.int64)
+        x = self._check_samples(block)
+        if x.ndim != 2 or x.shape[0] != ids.size:
+            raise AudioProcessingError("push_many expects block[len(stream_ids), samples]")
+        if not self._open[ids].all():
+            raise VADError("push_many: a stream is not open")
+        m = x.shape[1]
+        fills = self._fill[ids]
+        self._ensure_cap(int(fills.max()) + m)
+        f0 = int(fills[0])
+        if (fills == f0).all():
+            self._buf[ids, f0:f0 + m] = x
+        else:
+            cols = fills[:, None] + np.arange(m)[None, :]
+            self._buf[ids[:, None], cols] = x
+        self._fill[ids] = fills + m
 
     def _gate(self, st: _Stream, frame: np.ndarray) -> np.ndarray:
         f = frame.astype(np.float32)
@@ -201,62 +260,61 @@ class BatchedVADManager:
     def step(self) -> StepOutput:
         """Run every complete buffered frame of every open stream in one GPU step."""
         with self._lock:
-            ids: List[int] = []
-            counts: List[int] = []
-            for sid, st in self._streams.items():
-                n = st.pending.size
-                if n >= self.frame_len:
-                    ids.append(sid)
-                    counts.append((n - self.frame_len) // self.hop + 1)
-            if not ids:
-                return StepOutput([], {}, 0)
-            tmax = max(counts)
+            fill = self._fill
+            counts_all = np.where(self._open & (fill >= self.frame_len), (fill - self.frame_len) // self.hop + 1, 0)
+            ids = np.flatnonzero(counts_all)
+            if ids.size == 0:
+                z = np.zeros(0, np.int64)
+                return StepOutput([], z, z, np.zeros((0, 0), np.float32), np.zeros((0, 0), np.uint8))
+            counts = counts_all[ids]
+            tmax = int(counts.max())
             row = (tmax - 1) * self.hop + self.frame_len
             row += (-row) % 4
-            block = np.zeros((len(ids), row), self._dtype)
-            for k, sid in enumerate(ids):
-                p = self._streams[sid].pending
-                use = (counts[k] - 1) * self.hop + self.frame_len
-                block[k, :use] = p[:use]
-            r = self._engine.step(block, slots=ids, n_frames=counts, max_frames=tmax, frame_len=self.frame_len,
-                                  hop=self.hop, pcm_format=self.pcm_format, src_rate=self.source_rate)
-            events: List[StreamEvent] = []
-            probs: Dict[int, np.ndarray] = {}
-            for k, sid in enumerate(ids):
-                st = self._streams[sid]
-                if r.status[k]:
-                    st.pending = np.zeros(0, self._dtype)
-                    raise AudioProcessingError("Audio data contains infinite or NaN values")
-                probs[sid] = r.probs[k, :counts[k]].copy()
-            for (k, slot, j, kind, stream_frame) in r.events:
-                events.append(StreamEvent(slot, "start" if kind == capi.FLAG_STARTED else "end", stream_frame, j))
-            self._deliver(ids, counts, r.probs, r.flags)
-            for k, sid in enumerate(ids):
-                st = self._streams[sid]
-                st.pending = st.pending[counts[k] * self.hop:].copy()
-            return StepOutput(events, probs, int(sum(counts)))
+            self._ensure_cap(row)
+            block = self._buf[ids, :row]                      # one gather: [n, row], contiguous
+            r = self._engine.step(block, slots=ids.astype(np.int32), n_frames=counts.astype(np.int32),
+                                  max_frames=tmax, frame_len=self.frame_len, hop=self.hop,
+                                  pcm_format=self.pcm_format, src_rate=self.source_rate)
+            if r.status.any():
+                self._fill[ids[r.status != 0]] = 0
+                raise AudioProcessingError("Audio data contains infinite or NaN values")
+            events = [StreamEvent(slot, "start" if kind == capi.FLAG_STARTED else "end", stream_frame, j)
+                      for (k, slot, j, kind, stream_frame) in r.events]
+            self._deliver(ids, counts, block, r.probs, r.flags)
+            # compact: drop the consumed hop-multiples, keep the tail (vectorised per distinct amount)
+            used = counts * self.hop
+            rem = fill[ids] - used
+            keep = rem > 0
+            if keep.any():
+                for u in np.unique(used[keep]):
+                    sel = ids[keep & (used == u)]
+                    w = int((fill[sel] - u).max())
+                    self._buf[sel, :w] = self._buf[sel, int(u):int(u) + w]
+            self._fill[ids] = rem
+            return StepOutput(events, ids, counts, r.probs, r.flags)
 
-    def _deliver(self, ids: Sequence[int], counts: Sequence[int], probs: np.ndarray, flags: np.ndarray) -> None:
-        """Host side of the callbacks: segment assembly from the device's per-frame flags."""
-        for k, sid in enumerate(ids):
+    def _deliver(self, ids: np.ndarray, counts: np.ndarray, block: np.ndarray, probs: np.ndarray,
+                 flags: np.ndarray) -> None:
+        """Host side of the callbacks: segment assembly from the device's per-frame flags.  Streams
+        without callbacks only get their `active` mirror refreshed, and only when something happened."""
+        # every stream: voice-active mirror from the flags of its last frame (ended -> off, started or
+        # continuing -> on), one vectorised pass
+        last = flags[np.arange(ids.size), counts - 1]
+        self._active[ids] = ((last & 2) == 0) & ((last & 5) != 0)
+        # streams with callbacks: replay their frames on the host to assemble payloads
+        for k in np.flatnonzero(self._has_cb[ids]):
+            sid = int(ids[k])
             st = self._streams[sid]
             fl_row = flags[k]
-            if not st.wants_audio and st.on_start is None:
-                last = counts[k] - 1
-                ended = np.flatnonzero(fl_row[:counts[k]] & 2)
-                started = np.flatnonzero(fl_row[:counts[k]] & 1)
-                if ended.size or started.size:
-                    st.active = (started.max() if started.size else -1) > (ended.max() if ended.size else -1)
-                else:
-                    st.active = bool(fl_row[last] & 4) if last >= 0 else st.active
-                continue
+            n_k = int(counts[k])
             start_p = st.config.vad_start_probability
-            for j in range(counts[k]):
+            pending = block[k]
+            for j in range(n_k):
                 fl = int(fl_row[j])
                 frame = None
                 if st.wants_audio:
                     if st.active or float(probs[k, j]) >= start_p:
-                        frame = self._gate(st, st.pending[j * self.hop: j * self.hop + self.frame_len])
+                        frame = self._gate(st, pending[j * self.hop: j * self.hop + self.frame_len])
                 if not st.active:
                     if float(probs[k, j]) >= start_p:
                         if frame is not None:
@@ -303,6 +361,7 @@ class BatchedVADManager:
     def close(self) -> None:
         with self._lock:
             self._streams.clear()
+            self._open[:] = False
             self._engine.close()
 
     def __enter__(self) -> "BatchedVADManager":

@@ -191,3 +191,36 @@ def test_manager_rejects_nonfinite_push_and_bad_config():
     mgr.push(sid, np.zeros(100, np.float32))
     assert mgr.step().frames == 0                                         # less than one frame buffered
     mgr.close()
+
+
+def test_manager_push_many_lockstep_matches_single_pushes(ref_v5):
+    """Vectorised producer path (push_many) == per-stream push, incl. compaction of leftovers."""
+    from real_time_vad import BatchedVADManager, VADConfig
+    n, T = 70, 25
+    audio = synth_streams(n, 512 * T + 100, seed=51)
+    cfg = VADConfig(enable_denoising=True, vad_start_probability=0.5, vad_end_probability=0.35,
+                    voice_start_frame_count=2, voice_end_frame_count=3)
+    a = BatchedVADManager(max_streams=128, frame_len=512, hop=256)
+    b = BatchedVADManager(max_streams=128, frame_len=512, hop=256)
+    ia = [a.open_stream(cfg) for _ in range(n)]
+    ib = [b.open_stream(cfg) for _ in range(n)]
+    pa, pb, ea, eb = [], [], [], []
+    for lo in range(0, audio.shape[1], 700):
+        chunk = audio[:, lo:lo + 700]
+        a.push_many(ia, chunk)
+        for k, sid in enumerate(ib):
+            b.push(sid, chunk[k])
+        oa, ob = a.step(), b.step()
+        pa.append(oa.probs[:, :int(oa.counts.max())] if oa.counts.size else np.zeros((n, 0), np.float32))
+        pb.append(ob.probs[:, :int(ob.counts.max())] if ob.counts.size else np.zeros((n, 0), np.float32))
+        ea += [(e.stream_id, e.kind, e.frame_index) for e in oa.events]
+        eb += [(e.stream_id, e.kind, e.frame_index) for e in ob.events]
+    pa, pb = np.concatenate(pa, axis=1), np.concatenate(pb, axis=1)
+    assert np.array_equal(pa, pb) and ea == eb and len(ea) > 10
+    Tn = (audio.shape[1] - 512) // 256 + 1
+    assert pa.shape == (n, Tn)
+    want, _, _ = ref_v5.run(audio, Tn, hop=256, denoise=True)
+    assert np.abs(pa - want).max() <= TOL
+    assert a.is_voice_active(ia[0]) == bool((a.engine.get_state(ia[0])[2][0]))
+    a.close()
+    b.close()
