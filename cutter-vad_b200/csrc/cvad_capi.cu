@@ -15,6 +15,7 @@
 #include <cmath>
 
 #include "cvad_resample.cuh"
+#include "cvad_tc.cuh"
 #include "cvad_v4.cuh"
 
 namespace {
@@ -930,6 +931,29 @@ int cvad_step_device(cvad_engine *e, const cvad_step_args *a) {
     CU_TRY(e, cudaMemsetAsync(d_status, 0, (size_t)a->n_streams * sizeof(unsigned int), e->stream));
     if (a->n_events_out) CU_TRY(e, cudaMemsetAsync(a->n_events_out, 0, sizeof(int), e->stream));
     return launch_step(e, a, d_status, 1, nullptr, e->stream);
+}
+
+// Hardware probe of the tcgen05 path (test hook): D[128][32] = A[128][256] * B[32][256]^T, operands are
+// raw bf16 bit patterns on the host, D is float32.  Returns 0, or a negative CVAD_E_* code.
+int cvad_tc_probe(int device, const uint16_t *a_bf16, const uint16_t *b_bf16, float *d_out) {
+    using namespace cvad::tc;
+    if (!a_bf16 || !b_bf16 || !d_out) return CVAD_E_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, CVAD_E_NOGPU, "cudaSetDevice failed");
+    __nv_bfloat16 *dA = nullptr, *dB = nullptr;
+    float *dD = nullptr;
+    CU_TRY(nullptr, cudaMalloc(reinterpret_cast<void **>(&dA), kProbeM * kProbeK * 2));
+    CU_TRY(nullptr, cudaMalloc(reinterpret_cast<void **>(&dB), kProbeN * kProbeK * 2));
+    CU_TRY(nullptr, cudaMalloc(reinterpret_cast<void **>(&dD), kProbeM * kProbeN * 4));
+    CU_TRY(nullptr, cudaMemcpy(dA, a_bf16, kProbeM * kProbeK * 2, cudaMemcpyHostToDevice));
+    CU_TRY(nullptr, cudaMemcpy(dB, b_bf16, kProbeN * kProbeK * 2, cudaMemcpyHostToDevice));
+    CU_TRY(nullptr, cudaMemset(dD, 0xFF, kProbeM * kProbeN * 4));
+    CU_TRY(nullptr, cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kProbeSmem));
+    tc_probe_kernel<<<1, 128, kProbeSmem>>>(dA, dB, dD);
+    CU_TRY(nullptr, cudaGetLastError());
+    CU_TRY(nullptr, cudaDeviceSynchronize());
+    CU_TRY(nullptr, cudaMemcpy(d_out, dD, kProbeM * kProbeN * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    return CVAD_OK;
 }
 
 int cvad_resample_matrix(int src_rate, float *rt_out, size_t n_floats) {

@@ -23,7 +23,7 @@ EXPORTS = (
     "cvad_abi_version", "cvad_device_count", "cvad_last_error", "cvad_create", "cvad_destroy",
     "cvad_set_stream", "cvad_reset", "cvad_configure", "cvad_get_state", "cvad_set_state",
     "cvad_step", "cvad_step_submit", "cvad_step_collect", "cvad_step_device", "cvad_sync", "cvad_launch_count", "cvad_debug_dump",
-    "cvad_alloc_pinned", "cvad_free_pinned", "cvad_set_timing", "cvad_read_timing", "cvad_resample_matrix",
+    "cvad_alloc_pinned", "cvad_free_pinned", "cvad_set_timing", "cvad_read_timing", "cvad_resample_matrix", "cvad_tc_probe",
 )
 
 
@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
     L.cvad_set_state.argtypes = [vp, i32, vp, vp, vp]
     L.cvad_step.argtypes = [vp, C.POINTER(StepArgs)]
     L.cvad_step_device.argtypes = [vp, C.POINTER(StepArgs)]
+    L.cvad_tc_probe.argtypes = [i32, vp, vp, vp]
     L.cvad_resample_matrix.argtypes = [i32, vp, C.c_size_t]
     L.cvad_step_submit.argtypes = [vp, C.POINTER(StepArgs), C.POINTER(C.c_int)]
     L.cvad_step_collect.argtypes = [vp, i32]

@@ -169,6 +169,10 @@ int cvad_sync(cvad_engine *e);
    such that y[n] = sum_m R^T[m][n] x[m] equals scipy.signal.resample(x, 512).  Returns n_in. */
 int cvad_resample_matrix(int src_rate, float *rt_out, size_t n_floats);
 
+/* Test hook: one 128x32x256 BF16 tensor-core GEMM (tcgen05, TMEM accumulator) on `device`;
+   a_bf16[128][256], b_bf16[32][256] are raw bf16 bit patterns, d_out[128][32] = A * B^T in float32. */
+int cvad_tc_probe(int device, const uint16_t *a_bf16, const uint16_t *b_bf16, float *d_out);
+
 /* Page-locked host memory for callers that want cvad_step to DMA straight from their
    buffer (pageable buffers are staged through the engine's own pinned area). */
 void *cvad_alloc_pinned(size_t bytes);
