@@ -6,6 +6,7 @@
 // sm_100 device is present every compute entry point fails with CVAD_E_NOGPU.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -17,6 +18,7 @@
 #include "cvad_resample.cuh"
 #include "cvad_tc.cuh"
 #include "cvad_v4.cuh"
+#include "cvad_v5tc.cuh"
 
 namespace {
 
@@ -41,6 +43,12 @@ struct cvad_engine {
 
     // weights
     float *w_fe = nullptr, *b_fe = nullptr, *w_rec = nullptr, *b_rec = nullptr, *w_dec = nullptr;
+    // tensor-core path (v5 only): BF16x3 tile streams + the FP32 side tables
+    int math = CVAD_MATH_FP32;
+    unsigned char *w_fe_tc = nullptr, *w_rec_tc = nullptr;
+    float *nyq_w = nullptr, *b_rec_tc = nullptr;
+    DevBuf d_feat_tc;
+    long long *d_prof = nullptr;       // 128 clock64 marks of CTA 0 (cvad_set_profile)
     // per-slot state
     float *h_state = nullptr, *c_state = nullptr;
     int *sm_active = nullptr, *sm_scount = nullptr, *sm_ecount = nullptr;
@@ -180,6 +188,94 @@ V5Packed pack_v5(const float *blob) {
     P.w_dec.resize(129);
     std::memcpy(P.w_dec.data(), decw, 128 * 4);
     P.w_dec[128] = decb[0];
+    return P;
+}
+
+
+// ---- v5 tensor-core repack: every GEMM weight as three BF16 parts (w = w0 + w1 + w2 to 24 bits), cut into
+// (rows x 64 K) tiles in the SWIZZLE_128B K-major operand layout, in the order cvad_v5tc.cuh consumes them.
+struct V5TcPacked {
+    std::vector<unsigned char> w_fe, w_rec;
+    std::vector<float> nyq_w, b_rec;
+};
+
+uint16_t bf16_rn_bits(float x) {
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    const uint32_t r = ((u >> 16) & 1u) + 0x7FFFu;
+    return (uint16_t)((u + r) >> 16);
+}
+float bf16_val(uint16_t b) {
+    const uint32_t u = (uint32_t)b << 16;
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+// append the three part tiles of W(row, k), rows x [k0, k0 + 64)
+template <typename F>
+void emit_tiles(std::vector<unsigned char> &out, int rows, int k0, F W) {
+    const size_t tile = (size_t)rows * 128;
+    const size_t at = out.size();
+    out.resize(at + 3 * tile, 0);
+    for (int r = 0; r < rows; ++r)
+        for (int kk = 0; kk < 64; ++kk) {
+            float x = W(r, k0 + kk);
+            const size_t off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((((kk >> 3) ^ r) & 7) << 4) + (size_t)(kk & 7) * 2;
+            for (int part = 0; part < 3; ++part) {
+                const uint16_t b = bf16_rn_bits(x);
+                std::memcpy(&out[at + part * tile + off], &b, 2);
+                x -= bf16_val(b);
+            }
+        }
+}
+
+V5TcPacked pack_v5_tc(const float *blob) {
+    const float *basis = blob;                       // [258][256]
+    const float *e0w = basis + 258 * 256;            // [128][129][3]
+    const float *e0b = e0w + 128 * 129 * 3;
+    const float *e1w = e0b + 128;                    // [64][128][3]
+    const float *e1b = e1w + 64 * 128 * 3;
+    const float *e2w = e1b + 64;                     // [64][64][3]
+    const float *e2b = e2w + 64 * 64 * 3;
+    const float *e3w = e2b + 64;                     // [128][64][3]
+    const float *e3b = e3w + 128 * 64 * 3;
+    const float *wih = e3b + 128;                    // [512][128]
+    const float *whh = wih + 512 * 128;
+    const float *bih = whh + 512 * 128;
+    const float *bhh = bih + 512;
+
+    V5TcPacked P;
+    P.w_fe.reserve(cvad::tc5::kFeStreamBytes);
+    for (int blk = 0; blk < 2; ++blk)
+        for (int kb = 0; kb < 4; ++kb)
+            emit_tiles(P.w_fe, 128, kb * 64, [&](int m, int k) {
+                const int row = blk == 0 ? m : (m == 0 ? 128 : 129 + m);
+                return basis[row * 256 + k];
+            });
+    static const int taps0[3] = {1, 0, 2}, taps1[3] = {1, 2, 0};
+    for (int kb = 0; kb < 2; ++kb)
+        for (int ti = 0; ti < 3; ++ti)
+            emit_tiles(P.w_fe, 128, kb * 64, [&](int o, int c) { return e0w[(o * 129 + c) * 3 + taps0[ti]]; });
+    for (int kb = 0; kb < 2; ++kb)
+        for (int ti = 0; ti < 3; ++ti)
+            emit_tiles(P.w_fe, 64, kb * 64, [&](int o, int c) { return e1w[(o * 128 + c) * 3 + taps1[ti]]; });
+    for (int tap = 1; tap <= 2; ++tap)
+        emit_tiles(P.w_fe, 64, 0, [&](int o, int c) { return e2w[(o * 64 + c) * 3 + tap]; });
+    emit_tiles(P.w_fe, 128, 0, [&](int o, int c) { return e3w[(o * 64 + c) * 3 + 1]; });
+
+    for (int g = 0; g < 4; ++g)
+        for (int kb = 0; kb < 4; ++kb)
+            emit_tiles(P.w_rec, 128, kb * 64, [&](int u, int k) {
+                const int row = g * 128 + u;
+                return k < 128 ? wih[row * 128 + k] : whh[row * 128 + (k - 128)];
+            });
+
+    P.nyq_w.assign(128 * 4, 0.f);
+    for (int o = 0; o < 128; ++o)
+        for (int t = 0; t < 3; ++t) P.nyq_w[o * 4 + t] = e0w[(o * 129 + 128) * 3 + t];
+    P.b_rec.resize(512);
+    for (int n = 0; n < 512; ++n) P.b_rec[n] = bih[n] + bhh[n];
     return P;
 }
 
@@ -413,6 +509,27 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
     p.n_events = a->n_events_out;
     p.commit = commit;
     p.dbg = d_dbg;
+
+    if (e->version == CVAD_MODEL_V5 && e->math == CVAD_MATH_TC) {
+        if ((rc = grow(e, e->d_feat_tc, (size_t)a->max_frames * n_stiles * cvad::tc5::kFeatTileBytes))) return rc;
+        p.w_fe_tc = e->w_fe_tc; p.w_rec_tc = e->w_rec_tc; p.nyq_w = e->nyq_w; p.b_rec_tc = e->b_rec_tc;
+        p.feat_tc = static_cast<unsigned char *>(e->d_feat_tc.p);
+        p.prof = e->d_prof;
+        const int grid = std::min(a->max_frames * n_stiles, e->num_sms);
+        if (d_dbg) cvad::tc5::v5tc_frontend_kernel<true><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFeSmemTC, stream>>>(p);
+        else cvad::tc5::v5tc_frontend_kernel<false><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFeSmemTC, stream>>>(p);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+        if (timed) CU_TRY(e, cudaEventRecord(ev[1], stream));
+        if (!d_dbg) {
+            cvad::tc5::v5tc_recurrent_kernel<<<n_stiles, cvad::tc5::kThreadsTC, cvad::tc5::kRecSmemTC, stream>>>(p);
+            CU_TRY(e, cudaGetLastError());
+            e->launches++;
+        }
+        if (timed) CU_TRY(e, cudaEventRecord(ev[2], stream));
+        CU_TRY(e, cudaEventRecord(e->last_done, stream));
+        return CVAD_OK;
+    }
 
     const bool v4 = e->version == CVAD_MODEL_V4;
     const int n_tiles = a->max_frames * n_stiles * (v4 ? 2 : 1);
@@ -713,6 +830,25 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
                                 (int)cvad::kV4FeSmemBytes));
     CR_TRY(cudaFuncSetAttribute(cvad::v4_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::kV4RecSmemBytes));
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::tc5::kFeSmemTC));
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::tc5::kFeSmemTC));
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::tc5::kRecSmemTC));
+    if (model_version == CVAD_MODEL_V5) {
+        V5TcPacked T = pack_v5_tc(weights);
+        if (T.w_fe.size() != cvad::tc5::kFeStreamBytes || T.w_rec.size() != cvad::tc5::kRecStreamBytes) {
+            e->err = "internal: tensor-core weight stream has the wrong size";
+            return bail(CVAD_E_WEIGHTS);
+        }
+        int rc;
+        if ((rc = upload(e, &e->w_fe_tc, T.w_fe)) || (rc = upload(e, &e->w_rec_tc, T.w_rec)) ||
+            (rc = upload(e, &e->nyq_w, T.nyq_w)) || (rc = upload(e, &e->b_rec_tc, T.b_rec)))
+            return bail(rc);
+        const char *m = std::getenv("CVAD_MATH");
+        if (m && std::strcmp(m, "tc") == 0) e->math = CVAD_MATH_TC;
+    }
     {
         V5Packed P = model_version == CVAD_MODEL_V5 ? pack_v5(weights) : pack_v4(weights);
         int rc;
@@ -753,7 +889,8 @@ int cvad_destroy(cvad_engine *e) {
     void *ptrs[] = {e->w_fe, e->b_fe, e->w_rec, e->b_rec, e->w_dec, e->h_state, e->c_state, e->sm_active,
                     e->sm_scount, e->sm_ecount, e->frames_done, e->start_p, e->end_p, e->n_start, e->n_end,
                     e->denoise, e->d_status_dev.p, e->d_feat.p, e->d_dbg.p, e->d_cfg_slots.p, e->d_res.p,
-                    e->rs_rt[0], e->rs_rt[1], e->rs_rt[2]};
+                    e->rs_rt[0], e->rs_rt[1], e->rs_rt[2], e->w_fe_tc, e->w_rec_tc, e->nyq_w, e->b_rec_tc,
+                    e->d_feat_tc.p, e->d_prof};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &ln : e->lanes) {
@@ -770,6 +907,37 @@ int cvad_destroy(cvad_engine *e) {
     for (cudaEvent_t x : e->ev_pool) cudaEventDestroy(x);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
+    return CVAD_OK;
+}
+
+int cvad_set_math(cvad_engine *e, int math) {
+    if (!e) return CVAD_E_INVALID;
+    if (math != CVAD_MATH_FP32 && math != CVAD_MATH_TC) return fail(e, CVAD_E_INVALID, "math must be CVAD_MATH_FP32 or CVAD_MATH_TC");
+    if (math == CVAD_MATH_TC && e->version != CVAD_MODEL_V5)
+        return fail(e, CVAD_E_INVALID, "the tensor-core path exists for the v5 model only");
+    e->math = math;
+    return CVAD_OK;
+}
+
+int cvad_get_math(const cvad_engine *e) { return e ? e->math : CVAD_E_INVALID; }
+
+int cvad_set_profile(cvad_engine *e, int enabled) {
+    if (!e) return CVAD_E_INVALID;
+    if (enabled && !e->d_prof) {
+        CU_TRY(e, cudaMalloc(reinterpret_cast<void **>(&e->d_prof), 128 * sizeof(long long)));
+        CU_TRY(e, cudaMemset(e->d_prof, 0, 128 * sizeof(long long)));
+    } else if (!enabled && e->d_prof) {
+        CU_TRY(e, cudaDeviceSynchronize());
+        cudaFree(e->d_prof);
+        e->d_prof = nullptr;
+    }
+    return CVAD_OK;
+}
+
+int cvad_read_profile(cvad_engine *e, long long *out128) {
+    if (!e || !out128 || !e->d_prof) return CVAD_E_INVALID;
+    CU_TRY(e, cudaDeviceSynchronize());
+    CU_TRY(e, cudaMemcpy(out128, e->d_prof, 128 * sizeof(long long), cudaMemcpyDeviceToHost));
     return CVAD_OK;
 }
 
@@ -953,6 +1121,23 @@ int cvad_tc_probe(int device, const uint16_t *a_bf16, const uint16_t *b_bf16, fl
     CU_TRY(nullptr, cudaDeviceSynchronize());
     CU_TRY(nullptr, cudaMemcpy(d_out, dD, kProbeM * kProbeN * 4, cudaMemcpyDeviceToHost));
     cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    return CVAD_OK;
+}
+
+
+int cvad_tc_rate(int device, int M, int N, int reps, int a_tiles, int n_acc, int grid, long long *out2) {
+    using namespace cvad::tc;
+    if (!out2 || a_tiles < 1 || a_tiles > 10 || (M != 64 && M != 128) || N < 8 || N > 256 || grid < 1 || n_acc < 1 || n_acc * N > 512) return CVAD_E_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, CVAD_E_NOGPU, "cudaSetDevice failed");
+    long long *d = nullptr;
+    const size_t smem = (size_t)a_tiles * 16384 + 32768 + 1024 + 64;
+    CU_TRY(nullptr, cudaMalloc(reinterpret_cast<void **>(&d), 16));
+    CU_TRY(nullptr, cudaFuncSetAttribute(tc_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_rate_kernel<<<grid, 128, smem>>>(M, N, reps, a_tiles, n_acc, d);
+    CU_TRY(nullptr, cudaGetLastError());
+    CU_TRY(nullptr, cudaDeviceSynchronize());
+    CU_TRY(nullptr, cudaMemcpy(out2, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
     return CVAD_OK;
 }
 

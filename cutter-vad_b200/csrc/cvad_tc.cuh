@@ -52,6 +52,12 @@ __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fenc
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ bool elect_one() {      // true on exactly one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -91,7 +97,7 @@ constexpr size_t kProbeSmem = (size_t)(kProbeM + kProbeN) * kProbeK * 2 + 1024 +
 __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const __nv_bfloat16 *A, const __nv_bfloat16 *B, float *D) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte alignment is required by SWIZZLE_128B
-    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     unsigned char *sA = base;                                   // 128 x 256 bf16 = 64 KB
     unsigned char *sB = sA + kProbeM * kProbeK * 2;             // 32 x 256 bf16 = 16 KB
     uint64_t *bar = reinterpret_cast<uint64_t *>(sB + kProbeN * kProbeK * 2);
@@ -147,6 +153,64 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const __nv_bfloat16 *A
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
+
+// ---- issue-rate probe (tools/tc_mma_rate.py): how many cycles does one M x N x 16 BF16 MMA cost when both
+// operands come from shared memory?  One thread issues `reps` groups of 4 MMAs (one 64-element K block),
+// commits, and the CTA waits; cycles are taken with clock64 by the issuing thread.  out[0] = cycles,
+// out[1] = number of MMAs.  a_tiles distinct A tiles are cycled so the A operand address changes like a
+// weight stream's does.
+__global__ void __launch_bounds__(128, 1) tc_rate_kernel(int M, int N, int reps, int a_tiles, int n_acc, long long *out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
+    unsigned char *sA = base;                                   // a_tiles x (128 x 64 bf16 = 16 KB)
+    unsigned char *sB = sA + (size_t)a_tiles * 16384;           // 256 x 64 bf16 = 32 KB
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sB + 32768);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (a_tiles * 16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t *>(sA)[i] = 0x3C003C00u;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    long long t0 = 0, t1 = 0;
+    if (tmem != 0) __trap();      // sole CTA on the SM, whole TMEM allocated: base is column 0 / lane 0
+    if (warp == 0) {              // warp-uniform issue loop, one elected lane issues (keeps operands in uniform registers)
+        const uint32_t idesc = idesc_bf16_f32(M, N);
+        const uint64_t a_base = smem_desc_sw128(smem_u32(sA)), b_base = smem_desc_sw128(smem_u32(sB));
+        int at = 0, acc = 0;
+        t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            const uint64_t ad = a_base + (uint64_t)(at * (16384 >> 4));
+            const uint32_t d = acc * N;
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) mma_bf16(d, ad + ks * 2, b_base + ks * 2, idesc, 1u);
+            }
+            if (++at == a_tiles) at = 0;
+            if (++acc == n_acc) acc = 0;
+        }
+        if (elect_one()) mma_commit(bar);
+        __syncwarp();
+    }
+    mbar_wait(bar, 0);
+    if (tid == 0) {
+        t1 = clock64();
+        if (blockIdx.x == 0) {
+            out[0] = t1 - t0;
+            out[1] = (long long)reps * 4;
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace tc

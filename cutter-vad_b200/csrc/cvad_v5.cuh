@@ -103,6 +103,13 @@ struct V5Step {
     int *n_events;                // device counter or null
     int commit;                   // 0: do not write state back (debug)
     float *dbg;                   // front-end debug dump for tile 0, or null
+    // tensor-core path (cvad_v5tc.cuh): BF16x3 weight tile streams, Nyquist-channel weights, gate biases, hand-off
+    const unsigned char *w_fe_tc;
+    const unsigned char *w_rec_tc;
+    const float *nyq_w;           // [128][4]: encoder.0 weight of input channel 128, taps 0..2
+    const float *b_rec_tc;        // [4][128] gate-major (i,f,g,o), b_ih + b_hh
+    unsigned char *feat_tc;       // [max_frames * n_stiles][tc5::kFeatTileBytes]
+    long long *prof;              // optional clock64 marks of CTA 0 (cvad_set_profile), or null
 };
 
 struct EventRec {

@@ -1,0 +1,908 @@
+// cvad_v5tc.cuh -- Silero VAD v5 (16 kHz branch) on the 5th-gen tensor cores (tcgen05 + TMEM),
+// FP32-accurate through a three-way BF16 operand split.
+//
+// Same pipeline and same hand-off as cvad_v5.cuh (the reference's per-frame session.run,
+// /root/reference/src/real_time_vad/core/silero_model.py:433; graph = SURVEY.md 8a "S5"), but every
+// GEMM-shaped stage runs as tcgen05.mma.kind::f16 with FP32 accumulation in TMEM:
+//
+//   x = x0 + x1 + x2,  w = w0 + w1 + w2   (x0 = bf16(x), x1 = bf16(x - x0), x2 = bf16(x - x0 - x1): 24 bits)
+//   w.x ~= w0.x0  +  (w0.x1 + w1.x0)  +  (w0.x2 + w1.x1 + w2.x0)          dropped terms <= 2^-24 relative
+//
+// A single BF16 pass misses the 1e-4 parity bar by two orders of magnitude and the usual 3-pass split
+// (16 bits) leaves 5e-5; the 6-product form is indistinguishable from an FP32 GEMM (tools/tc_probe_accuracy.py,
+// measured on B200: 3.2e-7 vs 4.1e-7 relative for cuBLAS-style FP32).
+//
+// GEMM orientation: A = WEIGHTS (M = 128 or 64 output channels, K-major, streamed from L2 through a
+// shared-memory ring by cp.async.bulk, already in the SWIZZLE_128B operand layout), B = ACTIVATIONS
+// (N = items x time columns, K-major), D[channel][item] in TMEM.  With the weights as the M side a tile can
+// be as small as 32 items, which is what a 4,096-stream frame step needs to fill 128 SMs.  An MMA whose
+// operands both come from shared memory costs max(N/2, (M+N)/4, ~41) cycles on B200 (tools/tc_mma_rate.py),
+// so time columns are batched into N (N = 96 for the STFT and encoder.0) and the recurrent kernel
+// concatenates the three activation parts along N.
+//
+// Warp roles (576 threads): warps 0-15 = loader + epilogue (TMEM -> registers -> activation -> next B operand;
+// warp w reads TMEM lanes 32 (w % 4).. and column group w / 4), warp 16 = weight producer (one lane),
+// warp 17 = MMA issuer (one elected lane).  Layers of one tile are
+// strictly sequential, so ONE activation region is reused in place from layer to layer.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "cvad_tc.cuh"
+#include "cvad_v5.cuh"
+
+namespace cvad {
+namespace tc5 {
+
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kProducerWarp = 16;
+constexpr int kMmaWarp = 17;
+constexpr int kThreadsTC = 576;
+constexpr uint32_t kSlotBytes = 16384;       // one 128-row x 64-K BF16 weight tile
+constexpr uint32_t kColMain = 0;             // TMEM column of the w0.x0 accumulator
+constexpr uint32_t kColCorr = 256;           // TMEM column of the five correction products
+
+// ---------------------------------------------------------------- front-end weight stream
+// Period = 69 tiles, in consumption order (each tile: rows x 64 K-elements, SW128 K-major, BF16 part p):
+//   stft : blk 0..1 (0: re bins 0..127; 1: row 0 = re bin 128, rows 1..127 = im bins 1..127) x kb 0..3 x p 0..2   24 x 16 KB
+//   enc0 : kb 0..1 x tap {1,0,2} x p   (channel 128, the Nyquist bin, is applied in the epilogue in FP32)           18 x 16 KB
+//   enc1 : kb 0..1 x tap {1,2,0} x p   (64 rows)                                                                    18 x  8 KB
+//   enc2 : tap {1,2} x p               (64 rows; tap 0 only ever meets the zero pad)                                 6 x  8 KB
+//   enc3 : centre tap x p                                                                                            3 x 16 KB
+constexpr int kFeSlotsPerTile = 69;
+constexpr size_t kFeStreamBytes = 42 * 16384 + 24 * 8192 + 3 * 16384;
+__host__ __device__ __forceinline__ void fe_slot(int s, uint32_t &off, uint32_t &bytes) {
+    if (s < 42) { off = (uint32_t)s * 16384u; bytes = 16384u; }
+    else if (s < 66) { off = 42u * 16384u + (uint32_t)(s - 42) * 8192u; bytes = 8192u; }
+    else { off = 42u * 16384u + 24u * 8192u + (uint32_t)(s - 66) * 16384u; bytes = 16384u; }
+}
+// Recurrent weight stream: gate blk 0..3 (i,f,g,o) x kb 0..3 (K = [x 128 | h 128]) x p 0..2, 16 KB each.
+constexpr int kRecSlotsPerFrame = 48;
+constexpr size_t kRecStreamBytes = (size_t)kRecSlotsPerFrame * 16384;
+
+// ---------------------------------------------------------------- shared memory plans
+// front end: ACT (96 KB) | ring | nyq[96] f32 | barriers | tmem slot | tile meta
+constexpr int kFeRing = 7;
+constexpr uint32_t kActBytes = 98304;
+constexpr uint32_t kAudPart = 32768;         // AUD: part stride; K block stride 16384; row = seg*32 + item (128 rows)
+constexpr uint32_t kMagPart = 24576;         // MAG/E0: 96 rows x 128 K; K block stride 12288
+constexpr uint32_t kMagKb = 12288;
+constexpr uint32_t kE1Part = 8192;           // E1: 64 rows x 64 K
+constexpr uint32_t kE2Part = 4096;           // E2: 32 rows x 64 K
+constexpr size_t kFeSmemTC = 1024 + kActBytes + (size_t)kFeRing * kSlotBytes + 96 * 4 + (2 * kFeRing + 2) * 8 + 16 +
+                             2 * kTile * 4 + 64;
+// feature hand-off (front end -> recurrent), per (frame, stream tile): the x half of the recurrent B operand,
+// byte for byte: [kb 0..1][row = part*32 + item (96 rows)][128 B], SW128
+constexpr uint32_t kFeatTileBytes = 2 * 12288;
+// recurrent: X[2] (2 x 24 KB) | H (24 KB) | ring | sbuf f32 [128][33] | dec partials [4][32] | barriers | meta
+constexpr int kRecRing = 7;
+constexpr uint32_t kXhKb = 12288;
+constexpr size_t kRecSmemTC = 1024 + 3 * (size_t)kFeatTileBytes + (size_t)kRecRing * kSlotBytes + 128 * 33 * 4 + 4 * 32 * 4 +
+                              (2 * kRecRing + 4) * 8 + 16 + kTile * (2 * 8 + 2 * 4) + 64;
+
+// ---------------------------------------------------------------- small device helpers
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// x -> three BF16 parts (bit patterns)
+__device__ __forceinline__ void split3(float x, unsigned short &p0, unsigned short &p1, unsigned short &p2) {
+    const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(b0);
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(b1);
+    const __nv_bfloat16 b2 = __float2bfloat16_rn(r2);
+    p0 = __bfloat16_as_ushort(b0);
+    p1 = __bfloat16_as_ushort(b1);
+    p2 = __bfloat16_as_ushort(b2);
+}
+// two values at once: word j holds part j of a (low half) and of b (high half); one F2FP per part
+__device__ __forceinline__ void split3x2(float a, float b, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w0) : "f"(b), "f"(a));
+    const float ra = a - __uint_as_float(w0 << 16), rb = b - __uint_as_float(w0 & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(rb), "f"(ra));
+    const float sa = ra - __uint_as_float(w1 << 16), sb = rb - __uint_as_float(w1 & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w2) : "f"(sb), "f"(sa));
+}
+// store the parts of values a (row) and b (row + 1) at column k of a B operand with R rows (part stride ps);
+// rows row and row + 1 lie in the same 8-row swizzle atom (row even)
+__device__ __forceinline__ void store_parts2(unsigned char *base, uint32_t ps, uint32_t row, uint32_t k, uint32_t R, float a, float b) {
+    uint32_t w0, w1, w2;
+    split3x2(a, b, w0, w1, w2);
+    unsigned char *da = base + tc::sw128_offset(row, k, R);
+    unsigned char *db = base + tc::sw128_offset(row + 1, k, R);
+    *reinterpret_cast<unsigned short *>(da) = (unsigned short)w0;
+    *reinterpret_cast<unsigned short *>(da + ps) = (unsigned short)w1;
+    *reinterpret_cast<unsigned short *>(da + 2 * ps) = (unsigned short)w2;
+    *reinterpret_cast<unsigned short *>(db) = (unsigned short)(w0 >> 16);
+    *reinterpret_cast<unsigned short *>(db + ps) = (unsigned short)(w1 >> 16);
+    *reinterpret_cast<unsigned short *>(db + 2 * ps) = (unsigned short)(w2 >> 16);
+}
+// store the three parts of v at element (row, k) of a B operand with R rows (part stride ps)
+__device__ __forceinline__ void store_parts(unsigned char *base, uint32_t ps, uint32_t row, uint32_t k, uint32_t R, float v) {
+    unsigned short p0, p1, p2;
+    split3(v, p0, p1, p2);
+    unsigned char *d = base + tc::sw128_offset(row, k, R);
+    *reinterpret_cast<unsigned short *>(d) = p0;
+    *reinterpret_cast<unsigned short *>(d + ps) = p1;
+    *reinterpret_cast<unsigned short *>(d + 2 * ps) = p2;
+}
+
+// warp-uniform: does tile (frame, stream tile) hold at least one live (stream, frame) item?
+__device__ __forceinline__ bool tile_live(const V5Step &p, int frame, int st, int lane, int *slot_out, int *valid_out) {
+    const int i = st * kTile + lane;
+    int valid = 0, slot = -1;
+    if (i < p.n_streams) {
+        slot = p.slots ? p.slots[i] : i;
+        const int nf = p.n_frames ? p.n_frames[i] : p.max_frames;
+        valid = frame < nf;
+    }
+    if (slot_out) *slot_out = slot;
+    if (valid_out) *valid_out = valid;
+    return __any_sync(0xffffffffu, valid);
+}
+
+// MMAs of one weight tile (part wp of the A operand) for one 64-element K block: four K steps against the
+// activation parts that pair with wp.  b0 = address of activation part 0 for this K block, parts are ps apart.
+// w0.x0 accumulates in d_main, everything else in d_corr.
+__device__ __forceinline__ void issue_split(int wp, uint32_t a_addr, uint32_t b0, uint32_t ps, uint32_t d_main,
+                                            uint32_t d_corr, uint32_t idesc, bool first) {
+    const uint64_t ad = tc::smem_desc_sw128(a_addr);
+    const uint64_t bd0 = tc::smem_desc_sw128(b0), bd1 = tc::smem_desc_sw128(b0 + ps), bd2 = tc::smem_desc_sw128(b0 + 2 * ps);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t fresh = (first && ks == 0) ? 0u : 1u;
+        if (wp == 0) {
+            tc::mma_bf16(d_corr, ad + ks * 2, bd2 + ks * 2, idesc, fresh);
+            tc::mma_bf16(d_corr, ad + ks * 2, bd1 + ks * 2, idesc, 1u);
+            tc::mma_bf16(d_main, ad + ks * 2, bd0 + ks * 2, idesc, fresh);
+        } else if (wp == 1) {
+            tc::mma_bf16(d_corr, ad + ks * 2, bd1 + ks * 2, idesc, 1u);
+            tc::mma_bf16(d_corr, ad + ks * 2, bd0 + ks * 2, idesc, 1u);
+        } else {
+            tc::mma_bf16(d_corr, ad + ks * 2, bd0 + ks * 2, idesc, 1u);
+        }
+    }
+}
+
+#define CVAD_PROF(k) do { if (p.prof && blockIdx.x == 0 && first_tile) p.prof[(k)] = clock64(); } while (0)
+
+struct Ring {
+    uint32_t buf;        // shared address of slot 0
+    uint64_t *full;      // [n]
+    uint64_t *empty;     // [n]
+};
+
+// =====================================================================================
+// Front end: frame loader -> STFT -> magnitude -> encoder.0..3 -> feat (BF16x3 operand for the recurrent kernel)
+// =====================================================================================
+template <bool DBG>
+__global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5Step p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
+    unsigned char *act = base;
+    unsigned char *ring_buf = act + kActBytes;
+    float *nyq = reinterpret_cast<float *>(ring_buf + kFeRing * kSlotBytes);   // [96] |X[128]| per (t, item)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(nyq + 96);
+    uint64_t *full = bars, *empty = bars + kFeRing, *act_ready = bars + 2 * kFeRing, *acc_ready = act_ready + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 1);
+    int *s_slot = reinterpret_cast<int *>(tmem_slot + 4);
+    int *s_valid = s_slot + kTile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int i = 0; i < kFeRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(act_ready, 1);
+        mbar_init(acc_ready, 1);
+        mbar_fence_init();
+    }
+    if (warp == kProducerWarp) tc::tmem_alloc(tmem_slot, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    if (*tmem_slot != 0u) __trap();   // sole CTA on the SM and all 512 columns: TMEM base is lane 0 / column 0
+
+    const int n_tiles = p.max_frames * p.n_stiles;
+    const uint32_t act_s = smem_u32(act), ring_s = smem_u32(ring_buf);
+
+    if (warp == kProducerWarp) {
+        // ------------------------------------------------------------ weight producer
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
+            if (!tile_live(p, frame, st, lane, nullptr, nullptr)) continue;
+            if (lane == 0) {
+                for (int s = 0; s < kFeSlotsPerTile; ++s, ++g) {
+                    const uint32_t slot = g % kFeRing;
+                    mbar_wait(&empty[slot], ((g / kFeRing) & 1u) ^ 1u);
+                    uint32_t off, bytes;
+                    fe_slot(s, off, bytes);
+                    mbar_arrive_expect_tx(&full[slot], bytes);
+                    bulk_g2s(ring_buf + slot * kSlotBytes, p.w_fe_tc + off, bytes, &full[slot]);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == kMmaWarp) {
+        // ------------------------------------------------------------ MMA issuer
+        uint32_t g = 0, act_phase = 0;
+        const uint32_t i128_96 = tc::idesc_bf16_f32(128, 96), i128_64 = tc::idesc_bf16_f32(128, 64),
+                       i128_32 = tc::idesc_bf16_f32(128, 32), i64_64 = tc::idesc_bf16_f32(64, 64),
+                       i64_32 = tc::idesc_bf16_f32(64, 32);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
+            if (!tile_live(p, frame, st, lane, nullptr, nullptr)) continue;
+            const bool first_tile = tile == (int)blockIdx.x && lane == 0;
+#define CVAD_TC_SLOT(BODY)                                                   \
+    {                                                                        \
+        const uint32_t slot = g % kFeRing;                                   \
+        mbar_wait(&full[slot], (g / kFeRing) & 1u);                          \
+        tc::fence_after_sync();                                              \
+        const uint32_t a_addr = ring_s + slot * kSlotBytes;                  \
+        if (tc::elect_one()) {                                               \
+            BODY;                                                            \
+            tc::mma_commit(&empty[slot]);                                    \
+        }                                                                    \
+        __syncwarp();                                                        \
+        ++g;                                                                 \
+    }
+            // ---- STFT: D[blk][bin][(t, item)] = sum_k W[bin][k] x[128 t + k]; K block kb uses segment rows t + kb/2
+            mbar_wait(act_ready, act_phase); act_phase ^= 1u;
+            CVAD_PROF(32);
+            tc::fence_after_sync();
+            for (int blk = 0; blk < 2; ++blk)
+                for (int kb = 0; kb < 4; ++kb)
+                    for (int wp = 0; wp < 3; ++wp)
+                        CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + (kb & 1) * 16384u + (kb >> 1) * 4096u, kAudPart,
+                                                 kColMain + blk * 96, kColCorr + blk * 96, i128_96, kb == 0 && wp == 0))
+            if (tc::elect_one()) tc::mma_commit(acc_ready);
+            CVAD_PROF(33);
+            __syncwarp();
+            // ---- encoder.0 (k3 s1 p1): tap 1: out t <- in t (N 96); tap 0: out 1,2 <- in 0,1; tap 2: out 0,1 <- in 1,2
+            mbar_wait(act_ready, act_phase); act_phase ^= 1u;
+            CVAD_PROF(34);
+            tc::fence_after_sync();
+            for (int kb = 0; kb < 2; ++kb) {
+                for (int wp = 0; wp < 3; ++wp)
+                    CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + kb * kMagKb, kMagPart, kColMain, kColCorr, i128_96,
+                                             kb == 0 && wp == 0))
+                for (int wp = 0; wp < 3; ++wp)
+                    CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + kb * kMagKb, kMagPart, kColMain + 32, kColCorr + 32,
+                                             i128_64, false))
+                for (int wp = 0; wp < 3; ++wp)
+                    CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + kb * kMagKb + 32 * 128, kMagPart, kColMain, kColCorr,
+                                             i128_64, false))
+            }
+            if (tc::elect_one()) tc::mma_commit(acc_ready);
+            CVAD_PROF(35);
+            __syncwarp();
+            // ---- encoder.1 (k3 s2 p1, 64 out): E0 row blocks are stored in time order {0, 2, 1}
+            //      tap 1: out 0,1 <- in 0,2 (rows 0..63); tap 2: out 0 <- in 1 (rows 64..95); tap 0: out 1 <- in 1
+            mbar_wait(act_ready, act_phase); act_phase ^= 1u;
+            CVAD_PROF(36);
+            tc::fence_after_sync();
+            for (int kb = 0; kb < 2; ++kb) {
+                for (int wp = 0; wp < 3; ++wp)
+                    CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + kb * kMagKb, kMagPart, kColMain, kColCorr, i64_64,
+                                             kb == 0 && wp == 0))
+                for (int wp = 0; wp < 3; ++wp)
+                    CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + kb * kMagKb + 64 * 128, kMagPart, kColMain, kColCorr,
+                                             i64_32, false))
+                for (int wp = 0; wp < 3; ++wp)
+                    CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + kb * kMagKb + 64 * 128, kMagPart, kColMain + 32,
+                                             kColCorr + 32, i64_32, false))
+            }
+            if (tc::elect_one()) tc::mma_commit(acc_ready);
+            CVAD_PROF(37);
+            __syncwarp();
+            // ---- encoder.2 (k3 s2 p1, 64 out, T 2 -> 1): tap 1 <- in 0 (rows 0..31), tap 2 <- in 1 (rows 32..63)
+            mbar_wait(act_ready, act_phase); act_phase ^= 1u;
+            CVAD_PROF(38);
+            tc::fence_after_sync();
+            for (int wp = 0; wp < 3; ++wp)
+                CVAD_TC_SLOT(issue_split(wp, a_addr, act_s, kE1Part, kColMain, kColCorr, i64_32, wp == 0))
+            for (int wp = 0; wp < 3; ++wp)
+                CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + 32 * 128, kE1Part, kColMain, kColCorr, i64_32, false))
+            if (tc::elect_one()) tc::mma_commit(acc_ready);
+            CVAD_PROF(39);
+            __syncwarp();
+            // ---- encoder.3 (centre tap, 128 out)
+            mbar_wait(act_ready, act_phase); act_phase ^= 1u;
+            CVAD_PROF(40);
+            tc::fence_after_sync();
+            for (int wp = 0; wp < 3; ++wp)
+                CVAD_TC_SLOT(issue_split(wp, a_addr, act_s, kE2Part, kColMain, kColCorr, i128_32, wp == 0))
+            if (tc::elect_one()) tc::mma_commit(acc_ready);
+            CVAD_PROF(41);
+            __syncwarp();
+#undef CVAD_TC_SLOT
+        }
+    } else {
+        // ------------------------------------------------------------ loader + epilogue warps
+        const int q = warp & 3, cg = warp >> 2;          // TMEM lane quadrant, column group 0..3
+        const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+        uint32_t acc_phase = 0;
+        const int flen = p.frame_len < 512 ? p.frame_len : 512;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
+            int my_slot, my_valid;
+            if (!tile_live(p, frame, st, lane, &my_slot, &my_valid)) continue;
+            if (warp == 0) { s_slot[lane] = my_slot; s_valid[lane] = my_valid; }
+            epi_bar();
+            const bool dbg = DBG && tile == 0;
+            const bool first_tile = tile == (int)blockIdx.x && tid == 0;
+            CVAD_PROF(0);
+
+            // ---- frame loader (audio.py:164-190 split, :104-121 gate, silero_model.py:449-474 pad/truncate):
+            //      8 samples per work unit -> 3 x 16-byte BF16 chunks of the AUD operand, row = segment*32 + item.
+            //      All global loads of the thread's 4 units are issued before the first use.
+            {
+                const bool fast = p.vec_ok && flen == 512;
+                float v[4][8];
+                bool ok[4];
+#pragma unroll
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const int unit = u4 * kEpiThreads + tid;
+                    const int s = unit >> 6, c8 = unit & 63;
+                    ok[u4] = s_valid[s] != 0;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[u4][e] = 0.f;
+                    if (ok[u4]) {
+                        const long long b0 = (long long)(st * kTile + s) * p.stride + (long long)frame * p.hop + 8 * c8;
+                        if (fast && p.pcm == 0) {
+                            const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.audio) + b0);
+                            const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
+                            v[u4][0] = t0.x; v[u4][1] = t0.y; v[u4][2] = t0.z; v[u4][3] = t0.w;
+                            v[u4][4] = t1.x; v[u4][5] = t1.y; v[u4][6] = t1.z; v[u4][7] = t1.w;
+                        } else if (fast) {
+                            const short4 *src = reinterpret_cast<const short4 *>(reinterpret_cast<const short *>(p.audio) + b0);
+                            const short4 t0 = __ldg(src), t1 = __ldg(src + 1);
+                            v[u4][0] = (float)t0.x; v[u4][1] = (float)t0.y; v[u4][2] = (float)t0.z; v[u4][3] = (float)t0.w;
+                            v[u4][4] = (float)t1.x; v[u4][5] = (float)t1.y; v[u4][6] = (float)t1.z; v[u4][7] = (float)t1.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (8 * c8 + e < flen)
+                                    v[u4][e] = p.pcm == 0 ? __ldg(reinterpret_cast<const float *>(p.audio) + b0 + e)
+                                                          : (float)__ldg(reinterpret_cast<const short *>(p.audio) + b0 + e);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const int unit = u4 * kEpiThreads + tid;
+                    const int s = unit >> 6, c8 = unit & 63;
+                    if (ok[u4]) {
+                        const bool dn = p.denoise[s_slot[s]] != 0;
+                        bool bad = false;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float x = v[u4][e];
+                            if (p.pcm == 1) x = __fdiv_rn(x, 32767.0f);
+                            else if (p.pcm == 2) x = x * (1.0f / 32768.0f);
+                            if (!isfinite(x)) bad = true;
+                            if (dn && !(fabsf(x) > 0.01f)) x = 0.0f;
+                            v[u4][e] = x;
+                        }
+                        if (bad && p.status) atomicOr(&p.status[st * kTile + s], 1u);
+                    }
+                    uint32_t w[3][4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split3x2(v[u4][2 * e], v[u4][2 * e + 1], w[0][e], w[1][e], w[2][e]);
+                    const uint32_t seg = (uint32_t)c8 >> 4, kk = ((uint32_t)c8 & 15u) * 8u;   // k inside the 128-sample segment
+                    const uint32_t off = tc::sw128_offset(seg * 32u + (uint32_t)s, kk, 128u);
+#pragma unroll
+                    for (int part = 0; part < 3; ++part)
+                        *reinterpret_cast<uint4 *>(act + part * kAudPart + off) = make_uint4(w[part][0], w[part][1], w[part][2], w[part][3]);
+                }
+            }
+            tc::fence_async_smem();
+            epi_bar();
+            if (tid == 0) mbar_arrive(act_ready);
+            CVAD_PROF(1);
+
+            // ---- STFT epilogue: magnitude = sqrt(re^2 + im^2), squares rounded separately (ONNX Pow, Pow, Add, Sqrt)
+            mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
+            CVAD_PROF(2);
+            tc::fence_after_sync();
+            {
+                const int b = 32 * q + lane;   // bin; TMEM lane b of block 1 holds im[b] (b >= 1) or re[128] (b == 0)
+#pragma unroll 1
+                for (int ch = 0; ch < 3; ++ch) {
+                    const int c0 = cg * 24 + ch * 8;
+                    float mr[8], mi[8], cr[8], ci[8];
+                    tmem_ld8(lane_addr + kColMain + c0, mr);
+                    tmem_ld8(lane_addr + kColMain + 96 + c0, mi);
+                    tmem_ld8(lane_addr + kColCorr + c0, cr);
+                    tmem_ld8(lane_addr + kColCorr + 96 + c0, ci);
+                    tmem_wait_ld();
+                    float mag[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float re = mr[e] + cr[e];
+                        float im = mi[e] + ci[e];
+                        if (b == 0) {
+                            const float m128 = sqrtf(__fmul_rn(im, im));
+                            nyq[c0 + e] = m128;
+                            if (dbg) p.dbg[(128 * 3 + ((c0 + e) >> 5)) * 32 + ((c0 + e) & 31)] = m128;
+                            im = 0.f;
+                        }
+                        mag[e] = sqrtf(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+                        if (dbg) p.dbg[(b * 3 + ((c0 + e) >> 5)) * 32 + ((c0 + e) & 31)] = mag[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) store_parts2(act, kMagPart, (uint32_t)(c0 + e), (uint32_t)b, 96u, mag[e], mag[e + 1]);
+                }
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            epi_bar();
+            if (tid == 0) mbar_arrive(act_ready);
+            CVAD_PROF(3);
+
+            // ---- encoder.0 epilogue: + bias + Nyquist channel (FP32) -> ReLU -> E0 (row blocks in time order 0,2,1)
+            mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
+            CVAD_PROF(4);
+            tc::fence_after_sync();
+            {
+                const int o = 32 * q + lane;
+                const float bias = __ldg(p.b_fe + o);
+                const float wn0 = __ldg(p.nyq_w + 4 * o), wn1 = __ldg(p.nyq_w + 4 * o + 1), wn2 = __ldg(p.nyq_w + 4 * o + 2);
+#pragma unroll 1
+                for (int ch = 0; ch < 3; ++ch) {
+                    const int c0 = cg * 24 + ch * 8;
+                    const int t = c0 >> 5, i0 = c0 & 31;
+                    const uint32_t rb = t == 0 ? 0u : (t == 1 ? 64u : 32u);
+                    float m[8], cr[8], v[8];
+                    tmem_ld8(lane_addr + kColMain + c0, m);
+                    tmem_ld8(lane_addr + kColCorr + c0, cr);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int i = i0 + e;
+                        float a = m[e] + cr[e];
+                        if (t > 0) a = fmaf(wn0, nyq[(t - 1) * 32 + i], a);
+                        a = fmaf(wn1, nyq[t * 32 + i], a);
+                        if (t < 2) a = fmaf(wn2, nyq[(t + 1) * 32 + i], a);
+                        v[e] = fmaxf(a + bias, 0.f);
+                        if (dbg) p.dbg[kDbgMag + (o * 3 + t) * 32 + i] = v[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) store_parts2(act, kMagPart, rb + (uint32_t)(i0 + e), (uint32_t)o, 96u, v[e], v[e + 1]);
+                }
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            epi_bar();
+            if (tid == 0) mbar_arrive(act_ready);
+            CVAD_PROF(5);
+
+            // ---- encoder.1 epilogue (M = 64: channel 16q + lane lives in TMEM lane 32q + lane, lanes >= 16 idle)
+            mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
+            CVAD_PROF(6);
+            tc::fence_after_sync();
+            {
+                const int o = 16 * q + (lane & 15);
+                const float bias = __ldg(p.b_fe + 128 + o);
+#pragma unroll 1
+                for (int ch = 0; ch < 2; ++ch) {
+                    const int c0 = cg * 16 + ch * 8;
+                    float m[8], cr[8], v[8];
+                    tmem_ld8(lane_addr + kColMain + c0, m);
+                    tmem_ld8(lane_addr + kColCorr + c0, cr);
+                    tmem_wait_ld();
+                    if (lane < 16) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            v[e] = fmaxf(m[e] + cr[e] + bias, 0.f);
+                            if (dbg) p.dbg[kDbgMag + kDbgE0 + (o * 2 + ((c0 + e) >> 5)) * 32 + ((c0 + e) & 31)] = v[e];
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2) store_parts2(act, kE1Part, (uint32_t)(c0 + e), (uint32_t)o, 64u, v[e], v[e + 1]);
+                    }
+                }
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            epi_bar();
+            if (tid == 0) mbar_arrive(act_ready);
+            CVAD_PROF(7);
+
+            // ---- encoder.2 epilogue (M = 64, 32 columns)
+            mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
+            CVAD_PROF(8);
+            tc::fence_after_sync();
+            {
+                const int o = 16 * q + (lane & 15);
+                const float bias = __ldg(p.b_fe + 192 + o);
+                const int c0 = cg * 8;
+                float m[8], cr[8], v[8];
+                tmem_ld8(lane_addr + kColMain + c0, m);
+                tmem_ld8(lane_addr + kColCorr + c0, cr);
+                tmem_wait_ld();
+                if (lane < 16) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        v[e] = fmaxf(m[e] + cr[e] + bias, 0.f);
+                        if (dbg) p.dbg[kDbgMag + kDbgE0 + kDbgE1 + o * 32 + c0 + e] = v[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) store_parts2(act, kE2Part, (uint32_t)(c0 + e), (uint32_t)o, 32u, v[e], v[e + 1]);
+                }
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            epi_bar();
+            if (tid == 0) mbar_arrive(act_ready);
+            CVAD_PROF(9);
+
+            // ---- encoder.3 epilogue -> feat tile in HBM, already in the recurrent kernel's B-operand bytes
+            mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
+            CVAD_PROF(10);
+            tc::fence_after_sync();
+            {
+                const int o = 32 * q + lane;
+                const float bias = __ldg(p.b_fe + 256 + o);
+                const int c0 = cg * 8;
+                float m[8], cr[8], v[8];
+                tmem_ld8(lane_addr + kColMain + c0, m);
+                tmem_ld8(lane_addr + kColCorr + c0, cr);
+                tmem_wait_ld();
+                unsigned char *fout = p.feat_tc + (size_t)tile * kFeatTileBytes;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    v[e] = fmaxf(m[e] + cr[e] + bias, 0.f);
+                    if (dbg) p.dbg[kDbgMag + kDbgE0 + kDbgE1 + kDbgE2 + o * 32 + c0 + e] = v[e];
+                }
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) store_parts2(fout, 32 * 128, (uint32_t)(c0 + e), (uint32_t)o, 96u, v[e], v[e + 1]);
+            }
+            tc::fence_before_sync();   // TMEM reads of this tile are ordered before the next tile's act_ready arrive
+            epi_bar();
+            CVAD_PROF(11);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == kProducerWarp) tc::tmem_dealloc(0u, 512);
+}
+
+// =====================================================================================
+// Recurrent part: LSTMCell(128) gates on the tensor cores, cell + decoder + state machine on the CUDA cores
+// =====================================================================================
+// B operand XH: rows = part*32 + item (96 rows), K = [x 128 | h 128] = 4 K blocks.  One weight tile of part wp
+// multiplies the first (3 - wp) activation parts in ONE MMA (N = 96 / 64 / 32) whose output lands at TMEM column
+// 32*wp of the gate block, so that columns [0,32) collect w0.x0, [32,64) w0.x1 + w1.x0 and [64,96) the three
+// smallest products.
+__global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5Step p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
+    unsigned char *xbuf = base;                               // [2][kFeatTileBytes]
+    unsigned char *hbuf = xbuf + 2 * kFeatTileBytes;          // [kFeatTileBytes]: K blocks 2,3
+    unsigned char *ring_buf = hbuf + kFeatTileBytes;
+    float *sbuf = reinterpret_cast<float *>(ring_buf + kRecRing * kSlotBytes);   // [128][33]
+    float *dpart = sbuf + 128 * 33;                                              // [4][32]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dpart + 128);
+    uint64_t *full = bars, *empty = bars + kRecRing, *xfull = bars + 2 * kRecRing, *h_ready = xfull + 2,
+             *acc_ready = h_ready + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 1);
+    double *s_startp = reinterpret_cast<double *>(tmem_slot + 4);
+    double *s_endp = s_startp + kTile;
+    int *s_slot = reinterpret_cast<int *>(s_endp + kTile);
+    int *s_nfr = s_slot + kTile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int st = blockIdx.x;
+    const int ms = p.max_streams;
+
+    if (tid < kTile) {
+        const int i = st * kTile + tid;
+        int slot = -1, nf = 0;
+        if (i < p.n_streams) {
+            slot = p.slots ? p.slots[i] : i;
+            nf = p.n_frames ? p.n_frames[i] : p.max_frames;
+            if (p.status && p.status[i] != 0u) nf = 0;  // NaN/Inf: the reference raises before any frame runs
+            s_startp[tid] = p.start_p[slot];
+            s_endp[tid] = p.end_p[slot];
+        }
+        s_slot[tid] = slot;
+        s_nfr[tid] = nf;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kRecRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(&xfull[0], 1);
+        mbar_init(&xfull[1], 1);
+        mbar_init(h_ready, 1);
+        mbar_init(acc_ready, 1);
+        mbar_fence_init();
+    }
+    if (warp == kProducerWarp) tc::tmem_alloc(tmem_slot, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    if (*tmem_slot != 0u) __trap();
+    int tmax = 0;
+    {
+        int v = s_nfr[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        tmax = v;
+    }
+    const uint32_t ring_s = smem_u32(ring_buf), x_s = smem_u32(xbuf), h_s = smem_u32(hbuf);
+
+    if (tmax > 0) {
+        if (warp == kProducerWarp) {
+            if (lane == 0) {
+                uint32_t g = 0;
+                for (int j = 0; j < tmax; ++j)
+                    for (int s = 0; s < kRecSlotsPerFrame; ++s, ++g) {
+                        const uint32_t slot = g % kRecRing;
+                        mbar_wait(&empty[slot], ((g / kRecRing) & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(&full[slot], kSlotBytes);
+                        bulk_g2s(ring_buf + slot * kSlotBytes, p.w_rec_tc + (size_t)s * kSlotBytes, kSlotBytes, &full[slot]);
+                    }
+            }
+            __syncwarp();
+        } else if (warp == kMmaWarp) {
+            uint32_t g = 0;
+            const uint32_t idesc[3] = {tc::idesc_bf16_f32(128, 96), tc::idesc_bf16_f32(128, 64), tc::idesc_bf16_f32(128, 32)};
+            for (int j = 0; j < tmax; ++j) {
+                const bool first_tile = lane == 0 && j < 8;
+                mbar_wait(&xfull[j & 1], (uint32_t)(j >> 1) & 1u);
+                CVAD_PROF(96 + 3 * j);
+                mbar_wait(h_ready, (uint32_t)j & 1u);
+                tc::fence_after_sync();
+                CVAD_PROF(97 + 3 * j);
+                for (int blk = 0; blk < 4; ++blk)
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint32_t b_addr = kb < 2 ? x_s + (j & 1) * kFeatTileBytes + kb * kXhKb : h_s + (kb - 2) * kXhKb;
+                        for (int wp = 0; wp < 3; ++wp, ++g) {
+                            const uint32_t slot = g % kRecRing;
+                            mbar_wait(&full[slot], (g / kRecRing) & 1u);
+                            tc::fence_after_sync();
+                            if (tc::elect_one()) {
+                                const uint64_t ad = tc::smem_desc_sw128(ring_s + slot * kSlotBytes);
+                                const uint64_t bd = tc::smem_desc_sw128(b_addr);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    tc::mma_bf16(blk * 96 + wp * 32, ad + ks * 2, bd + ks * 2, idesc[wp],
+                                                 (kb == 0 && wp == 0 && ks == 0) ? 0u : 1u);
+                                tc::mma_commit(&empty[slot]);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                if (tc::elect_one()) tc::mma_commit(acc_ready);
+                __syncwarp();
+                CVAD_PROF(98 + 3 * j);
+            }
+        } else {
+            // -------------------------------------------------------- state + epilogue warps
+            const int q = warp & 3, cg = warp >> 2;
+            const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+            const int u = 32 * q + lane;          // hidden unit owned by this thread (TMEM lane)
+            const int i0 = 8 * cg;                // its 8 streams
+            bool first_tile = tid == 0;
+            CVAD_PROF(64);
+            if (tid == 0)
+                for (int j = 0; j < 2 && j < tmax; ++j) {
+                    mbar_arrive_expect_tx(&xfull[j], kFeatTileBytes);
+                    bulk_g2s(xbuf + j * kFeatTileBytes, p.feat_tc + ((size_t)j * p.n_stiles + st) * kFeatTileBytes,
+                             kFeatTileBytes, &xfull[j]);
+                }
+            // resident state: h -> BF16x3 rows of the B operand, c -> registers (coalesced through sbuf;
+            // both global reads are in flight before the first barrier)
+            float hreg[8], creg[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int idx = e * kEpiThreads + tid;
+                const int slot = s_slot[idx & 31];
+                hreg[e] = slot >= 0 ? __ldg(p.h_state + (size_t)(idx >> 5) * ms + slot) : 0.f;
+                creg[e] = slot >= 0 ? __ldg(p.c_state + (size_t)(idx >> 5) * ms + slot) : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int idx = e * kEpiThreads + tid;
+                sbuf[(idx >> 5) * 33 + (idx & 31)] = hreg[e];
+            }
+            epi_bar();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hreg[e] = sbuf[u * 33 + i0 + e];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) store_parts2(hbuf, 32 * 128, (uint32_t)(i0 + e), (uint32_t)u, 96u, hreg[e], hreg[e + 1]);
+            epi_bar();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int idx = e * kEpiThreads + tid;
+                sbuf[(idx >> 5) * 33 + (idx & 31)] = creg[e];
+            }
+            epi_bar();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) creg[e] = sbuf[u * 33 + i0 + e];
+            tc::fence_async_smem();
+            epi_bar();
+            if (tid == 0) mbar_arrive(h_ready);
+            CVAD_PROF(65);
+
+            // state machine words (warp 0, one lane per stream)
+            int sm_active = 0, sm_sc = 0, sm_ec = 0, sm_ns = 1, sm_ne = 1;
+            long long sm_f0 = 0;
+            if (warp == 0 && s_slot[lane] >= 0) {
+                const int slot = s_slot[lane];
+                sm_active = p.sm_active[slot];
+                sm_sc = p.sm_scount[slot];
+                sm_ec = p.sm_ecount[slot];
+                sm_ns = p.n_start[slot];
+                sm_ne = p.n_end[slot];
+                sm_f0 = p.frames_done[slot];
+            }
+            const float b_i = __ldg(p.b_rec_tc + u), b_f = __ldg(p.b_rec_tc + 128 + u), b_g = __ldg(p.b_rec_tc + 256 + u),
+                        b_o = __ldg(p.b_rec_tc + 384 + u);
+            const float wd = __ldg(p.w_dec + u), dec_b = __ldg(p.w_dec + 128);
+            int nfr[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) nfr[e] = s_nfr[i0 + e];
+
+            for (int j = 0; j < tmax; ++j) {
+                first_tile = tid == 0 && j < 8;
+                mbar_wait(acc_ready, (uint32_t)j & 1u);
+                tc::fence_after_sync();
+                CVAD_PROF(66 + 3 * j);
+                // frame j's MMAs are complete: its x buffer is free for frame j + 2
+                if (tid == 0 && j + 2 < tmax) {
+                    mbar_arrive_expect_tx(&xfull[j & 1], kFeatTileBytes);
+                    bulk_g2s(xbuf + (j & 1) * kFeatTileBytes, p.feat_tc + ((size_t)(j + 2) * p.n_stiles + st) * kFeatTileBytes,
+                             kFeatTileBytes, &xfull[j & 1]);
+                }
+                float gate[4][8];
+#pragma unroll
+                for (int blk = 0; blk < 4; ++blk) {
+                    float g0[8], g1[8], g2[8];
+                    tmem_ld8(lane_addr + blk * 96 + i0, g0);
+                    tmem_ld8(lane_addr + blk * 96 + 32 + i0, g1);
+                    tmem_ld8(lane_addr + blk * 96 + 64 + i0, g2);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) gate[blk][e] = g0[e] + (g1[e] + g2[e]);
+                }
+                float dv[8], hn[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float ig = sigmoid_f(gate[0][e] + b_i);
+                    const float fg = sigmoid_f(gate[1][e] + b_f);
+                    const float gg = tanhf(gate[2][e] + b_g);
+                    const float og = sigmoid_f(gate[3][e] + b_o);
+                    const float cn = __fadd_rn(__fmul_rn(fg, creg[e]), __fmul_rn(ig, gg));
+                    const float hv = og * tanhf(cn);
+                    const bool live = j < nfr[e];
+                    creg[e] = live ? cn : creg[e];
+                    hreg[e] = live ? hv : hreg[e];
+                    hn[e] = hreg[e];                  // a finished stream keeps its last h in the operand
+                    dv[e] = wd * fmaxf(hv, 0.f);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) store_parts2(hbuf, 32 * 128, (uint32_t)(i0 + e), (uint32_t)u, 96u, hn[e], hn[e + 1]);
+                // decoder dot over the 128 units: 8 values x 32 lanes -> every lane ends with item (lane & 7)
+#pragma unroll
+                for (int w = 4; w >= 1; w >>= 1) {
+                    const bool upper = (lane & w) != 0;
+#pragma unroll
+                    for (int e = 0; e < w; ++e) {
+                        const float send = upper ? dv[e] : dv[e + w];
+                        const float keep = upper ? dv[e + w] : dv[e];
+                        dv[e] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+                    }
+                }
+                dv[0] += __shfl_xor_sync(0xffffffffu, dv[0], 8);
+                dv[0] += __shfl_xor_sync(0xffffffffu, dv[0], 16);
+                if (lane < 8) dpart[q * 32 + i0 + lane] = dv[0];
+                tc::fence_async_smem();
+                tc::fence_before_sync();
+                epi_bar();
+                if (tid == 0) mbar_arrive(h_ready);
+                CVAD_PROF(67 + 3 * j);
+                // sigmoid(w . relu(h') + b), then the start/end state machine (silero_model.py:790-923)
+                if (warp == 0 && j < s_nfr[lane]) {
+                    const float a = (dpart[lane] + dpart[32 + lane]) + (dpart[64 + lane] + dpart[96 + lane]);
+                    const float prob = sigmoid_f(a + dec_b);
+                    const double pd = (double)prob;
+                    unsigned int fl = 0u;
+                    if (!sm_active) {
+                        if (pd >= s_startp[lane]) {
+                            ++sm_sc;
+                            if (sm_sc >= sm_ns && sm_ns <= 20) {  // deque(maxlen=20), silero_model.py:620-623
+                                sm_active = 1; sm_sc = 0; sm_ec = 0; fl |= 1u;
+                            }
+                        } else {
+                            sm_sc = 0;
+                        }
+                    } else {
+                        fl |= 4u;
+                        if (pd < s_endp[lane]) {
+                            ++sm_ec;
+                            if (sm_ec >= sm_ne && sm_ne <= 100) {  // deque(maxlen=100), :625-628
+                                sm_active = 0; sm_ec = 0; fl |= 2u;
+                            }
+                        } else {
+                            sm_ec = 0;
+                        }
+                    }
+                    const int i = st * kTile + lane;
+                    if (p.probs) p.probs[(size_t)i * p.max_frames + j] = prob;
+                    if (p.flags) p.flags[(size_t)i * p.max_frames + j] = (unsigned char)fl;
+                    if ((fl & 3u) && p.n_events) {
+                        EventRec *ev = reinterpret_cast<EventRec *>(p.events);
+                        for (unsigned int kind = 1u; kind <= 2u; kind <<= 1) {
+                            if (fl & kind) {
+                                const int at = atomicAdd(p.n_events, 1);
+                                if (ev && at < p.max_events) {
+                                    ev[at].stream = i; ev[at].slot = s_slot[lane]; ev[at].frame = j;
+                                    ev[at].kind = (int)kind; ev[at].stream_frame = sm_f0 + j;
+                                }
+                            }
+                        }
+                    }
+                }
+                epi_bar();   // dpart is rewritten by the next frame
+                CVAD_PROF(68 + 3 * j);
+            }
+
+            // ---- write the resident state back (coalesced through sbuf)
+            if (p.commit) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sbuf[u * 33 + i0 + e] = hreg[e];
+                epi_bar();
+                for (int idx = tid; idx < 4096; idx += kEpiThreads) {
+                    const int s = idx & 31, uu = idx >> 5;
+                    const int slot = s_slot[s];
+                    if (slot >= 0 && s_nfr[s] > 0) p.h_state[(size_t)uu * ms + slot] = sbuf[uu * 33 + s];
+                }
+                epi_bar();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sbuf[u * 33 + i0 + e] = creg[e];
+                epi_bar();
+                for (int idx = tid; idx < 4096; idx += kEpiThreads) {
+                    const int s = idx & 31, uu = idx >> 5;
+                    const int slot = s_slot[s];
+                    if (slot >= 0 && s_nfr[s] > 0) p.c_state[(size_t)uu * ms + slot] = sbuf[uu * 33 + s];
+                }
+                if (warp == 0 && s_slot[lane] >= 0 && s_nfr[lane] > 0) {
+                    const int slot = s_slot[lane];
+                    p.sm_active[slot] = sm_active;
+                    p.sm_scount[slot] = sm_sc;
+                    p.sm_ecount[slot] = sm_ec;
+                    p.frames_done[slot] = sm_f0 + s_nfr[lane];
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == kProducerWarp) tc::tmem_dealloc(0u, 512);
+}
+
+}  // namespace tc5
+}  // namespace cvad

@@ -18,12 +18,14 @@ MODEL_V5, MODEL_V4 = 5, 4
 PCM_F32, PCM_S16_32767, PCM_S16_32768 = 0, 1, 2
 FLAG_STARTED, FLAG_ENDED, FLAG_CONTINUING = 1, 2, 4
 STATUS_NONFINITE = 1
+MATH_FP32, MATH_TC = 0, 1
 
 EXPORTS = (
     "cvad_abi_version", "cvad_device_count", "cvad_last_error", "cvad_create", "cvad_destroy",
     "cvad_set_stream", "cvad_reset", "cvad_configure", "cvad_get_state", "cvad_set_state",
     "cvad_step", "cvad_step_submit", "cvad_step_collect", "cvad_step_device", "cvad_sync", "cvad_launch_count", "cvad_debug_dump",
-    "cvad_alloc_pinned", "cvad_free_pinned", "cvad_set_timing", "cvad_read_timing", "cvad_resample_matrix", "cvad_tc_probe",
+    "cvad_alloc_pinned", "cvad_free_pinned", "cvad_set_timing", "cvad_read_timing", "cvad_resample_matrix", "cvad_tc_probe", "cvad_tc_rate",
+    "cvad_set_math", "cvad_get_math", "cvad_set_profile", "cvad_read_profile",
 )
 
 
@@ -79,6 +81,10 @@ def lib() -> C.CDLL:
     L.cvad_create.argtypes = [vp, C.c_size_t, i32, i32, i32, C.POINTER(vp)]
     L.cvad_destroy.argtypes = [vp]
     L.cvad_set_stream.argtypes = [vp, vp]
+    L.cvad_set_math.argtypes = [vp, i32]
+    L.cvad_get_math.argtypes = [vp]
+    L.cvad_set_profile.argtypes = [vp, i32]
+    L.cvad_read_profile.argtypes = [vp, vp]
     L.cvad_reset.argtypes = [vp, i32, vp]
     L.cvad_configure.argtypes = [vp, i32, vp, dbl, dbl, i32, i32, i32]
     L.cvad_get_state.argtypes = [vp, i32, vp, vp, vp, vp]
@@ -86,6 +92,7 @@ def lib() -> C.CDLL:
     L.cvad_step.argtypes = [vp, C.POINTER(StepArgs)]
     L.cvad_step_device.argtypes = [vp, C.POINTER(StepArgs)]
     L.cvad_tc_probe.argtypes = [i32, vp, vp, vp]
+    L.cvad_tc_rate.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp]
     L.cvad_resample_matrix.argtypes = [i32, vp, C.c_size_t]
     L.cvad_step_submit.argtypes = [vp, C.POINTER(StepArgs), C.POINTER(C.c_int)]
     L.cvad_step_collect.argtypes = [vp, i32]

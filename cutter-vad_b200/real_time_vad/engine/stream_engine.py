@@ -64,7 +64,7 @@ def _ptr(a: Optional[np.ndarray]):
 
 class StreamEngine:
     def __init__(self, model_version: str = "v5", max_streams: int = 1, device: int = 0,
-                 model_path: Optional[Path] = None):
+                 model_path: Optional[Path] = None, math: Optional[str] = None):
         self._L = capi.lib()
         self._h = C.c_void_p()
         if model_version == "v5":
@@ -82,8 +82,21 @@ class StreamEngine:
         self.max_streams = int(max_streams)
         self.device = int(device)
         self.model_version = model_version
+        if math is not None:
+            self.set_math(math)
 
     # ------------------------------------------------------------------ plumbing
+    def set_math(self, math: str) -> None:
+        """'fp32' = packed FP32 FMA kernels; 'tc' = tcgen05 tensor cores with the 3-way BF16 split (v5 only)."""
+        code = {"fp32": capi.MATH_FP32, "tc": capi.MATH_TC}.get(math)
+        if code is None:
+            raise EngineError(capi.E_INVALID, f"unknown math mode {math!r}")
+        self._check(self._L.cvad_set_math(self._h, code))
+
+    @property
+    def math(self) -> str:
+        return "tc" if self._L.cvad_get_math(self._h) == capi.MATH_TC else "fp32"
+
     def _check(self, rc: int) -> None:
         if rc < 0:
             raise EngineError(rc, (self._L.cvad_last_error(self._h) or b"").decode())

@@ -54,6 +54,12 @@ extern "C" {
 #define CVAD_MODEL_V5 5
 #define CVAD_MODEL_V4 4
 
+/* arithmetic of the v5 GEMM stages (cvad_set_math).  Both hold the 1e-4 parity bar with two orders of margin:
+   FP32  = packed FP32 FMA on the CUDA cores;
+   TC    = tcgen05 tensor cores, BF16 operands split three ways (6 products, FP32 accumulation in TMEM). */
+#define CVAD_MATH_FP32 0
+#define CVAD_MATH_TC 1
+
 /* audio sample formats accepted by cvad_step */
 #define CVAD_PCM_F32 0        /* float32 in [-1, 1] */
 #define CVAD_PCM_S16_32767 1  /* int16, divided by 32767.0f  (websocket server, vad_websocket_server.py:341) */
@@ -118,6 +124,16 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
                 int max_streams, int device, cvad_engine **out);
 int cvad_destroy(cvad_engine *e);
 
+/* Select the arithmetic of the model kernels (CVAD_MATH_*); v4 engines only accept CVAD_MATH_FP32.
+   The initial mode is CVAD_MATH_FP32 unless the environment variable CVAD_MATH is "tc". */
+int cvad_set_math(cvad_engine *e, int math);
+int cvad_get_math(const cvad_engine *e);
+
+/* Development aid for the tensor-core kernels: when enabled, CTA 0 of each kernel records SM-clock marks at its
+   phase boundaries (layout in csrc/cvad_v5tc.cuh, CVAD_PROF); cvad_read_profile copies the 128 marks out. */
+int cvad_set_profile(cvad_engine *e, int enabled);
+int cvad_read_profile(cvad_engine *e, long long *out128);
+
 /* Use an existing CUDA stream (cudaStream_t passed as void*); NULL = engine's own. */
 int cvad_set_stream(cvad_engine *e, void *cuda_stream);
 
@@ -172,6 +188,10 @@ int cvad_resample_matrix(int src_rate, float *rt_out, size_t n_floats);
 /* Test hook: one 128x32x256 BF16 tensor-core GEMM (tcgen05, TMEM accumulator) on `device`;
    a_bf16[128][256], b_bf16[32][256] are raw bf16 bit patterns, d_out[128][32] = A * B^T in float32. */
 int cvad_tc_probe(int device, const uint16_t *a_bf16, const uint16_t *b_bf16, float *d_out);
+
+/* Measurement hook: issue reps x 4 BF16 MMAs of shape M x N x 16 (both operands in shared memory) on
+   `grid` CTAs, cycling over n_acc TMEM accumulators; out2[0] = SM cycles from first issue to completion on CTA 0, out2[1] = MMAs issued. */
+int cvad_tc_rate(int device, int M, int N, int reps, int a_tiles, int n_acc, int grid, long long *out2);
 
 /* Page-locked host memory for callers that want cvad_step to DMA straight from their
    buffer (pageable buffers are staged through the engine's own pinned area). */
