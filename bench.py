@@ -189,7 +189,8 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 operands, f32 accumulate (FP32-equivalent)" if math == "tc" else "f32", "data": "synthetic",
         "config": workload_config(args, pool_mb=None),
         "p99_step_ms": 1e3 * float(np.percentile(lat, 99)),
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
@@ -210,7 +211,7 @@ def workload_config(args, pool_mb):
                                          ", resampled to 16 kHz on the GPU" if rate != 16000 else ""),
             "model": model, "src_rate": rate,
             "streams_per_gpu": args.streams, "frames_per_step": args.frames_per_step, "hop": 512,
-            "frame_len": 512, "denoise": True, "state_machine": True,
+            "frame_len": 512, "denoise": True, "state_machine": True, "math": getattr(args, "math", "fp32") if model == "v5" else "fp32",
             "l2": (f"inputs cycle through a pool of distinct step buffers totalling {pool_mb} MB (> 126 MB L2)"
                    if pool_mb else "n/a (CPU arm)")}
 
@@ -241,6 +242,8 @@ def run_ours(args):
     peaks, peaks_src = load_peaks()
 
     eng = StreamEngine(args.model, max_streams=n, device=local)
+    math = args.math if args.model == "v5" else "fp32"
+    eng.set_math(math)
     flop_frame = FLOP_FRAME if args.model == "v5" else 1_379_280
     flop_fe = FLOP_FRONTEND if args.model == "v5" else 1_379_280 - 2 * 65_600
     flop_rec = FLOP_RECURRENT if args.model == "v5" else 2 * 65_600
@@ -295,7 +298,6 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    eng.set_timing(True)
     launches0 = eng.launch_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -306,9 +308,16 @@ def run_ours(args):
         e1.record(stream)
     barrier()
     dev_ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    # per-kernel durations for the roofline: the same K steps again with an event between the two kernels
+    # (kept out of the pass above: the events would sit between the kernels and serialise their overlap)
+    eng.set_timing(True)
+    with torch.cuda.stream(stream):
+        for i in range(args.steps):
+            eng.step_device(dargs[(args.warmup + i) % pool_n])
+    barrier()
     fe_ms, rec_ms, n_timed = eng.read_timing()
     eng.set_timing(False)
-    launches = eng.launch_count() - launches0
 
     # per-step latency distribution (device side), one step at a time
     lat = []
@@ -370,35 +379,53 @@ def run_ours(args):
     step_tflops = frames_per_step * flop_frame / (dev_ms / args.steps * 1e-3) / 1e12
 
     if rank == 0:
-        traffic = (ncu_traffic_bytes("v5_frontend_kernel")
+        tc = math == "tc"
+        fe_kernel = ("v5tc_frontend_kernel" if tc else f"{args.model}_frontend_kernel") + \
+            ("+resample_kernel" if args.src_rate != 16000 else "")
+        traffic = (ncu_traffic_bytes("v5tc_frontend_kernel" if tc else "v5_frontend_kernel")
                    if (n == 4096 and F == 1 and args.model == "v5" and args.src_rate == 16000) else None)
+        peak_bf16 = float(peaks.get("bf16_tflops", 1645.0))
+        rec_tflops = frames_per_step * flop_rec / rec_avg_s / 1e12 if rec_avg_s else 0.0
+        fe_weight_bytes = 933_888 if tc else 156032 * 4
+        roofline = {
+            # tc: every algorithmic MAC is executed as 6 BF16 tensor-core products (3-way operand split), so the
+            # executed rate is 6x `achieved`; the path is bound by shared-memory operand bandwidth, not by the
+            # tensor pipe
+            "bound": "tensor" if tc else "fp32_ffma", "kernel": fe_kernel,
+            "achieved": fe_tflops, "peak": peak_bf16 if tc else peak_fp32, "unit": "TFLOP/s",
+            "frac": fe_tflops / (peak_bf16 if tc else peak_fp32),
+            "traffic": (traffic or {}).get("bytes"), "traffic_source": (traffic or {}).get("source"),
+            "algorithmic_bytes_per_launch": frames_per_step * 2048 + fe_weight_bytes + frames_per_step * (768 if tc else 512),
+            "peak_source": (f"{peaks_src} MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)" if tc else
+                            f"148 SMs x 128 FP32 lanes x 2 x sm_max_mhz {sm_max:.0f} ({peaks_src} "
+                            "MEASURED_PEAKS.json clock); the path is FP32-FFMA bound, not HBM or tensor bound"),
+            "algorithmic_flop_per_frame": flop_fe, "frames_per_launch": frames_per_step,
+            "avg_launch_ms": fe_avg_s * 1e3,
+            "kernel_timing": "second pass over the same K steps with a CUDA event between the two kernels",
+            "recurrent_kernel": {"kernel": "v5tc_recurrent_kernel" if tc else f"{args.model}_recurrent_kernel",
+                                 "avg_launch_ms": rec_avg_s * 1e3, "achieved": rec_tflops,
+                                 "algorithmic_flop_per_frame": flop_rec},
+            "whole_step": {"achieved": step_tflops, "frac": step_tflops / (peak_bf16 if tc else peak_fp32),
+                           "algorithmic_flop_per_frame": flop_frame},
+            "vs_fp32_ffma_peak": {"peak": peak_fp32, "kernel_frac": fe_tflops / peak_fp32,
+                                  "whole_step_frac": step_tflops / peak_fp32},
+            "hbm": {"algorithmic_bytes_per_frame": 2048 + 2 * 1024 + 4 + 1,
+                    "achieved_gbs": frames_per_step * (2048 + 2048 + 5) / (dev_ms / args.steps * 1e-3) / 1e9,
+                    "peak_gbs": peaks.get("hbm_gbs")},
+        }
+        if tc:
+            roofline["executed_bf16_tflops"] = 6 * fe_tflops
+            roofline["executed_frac"] = 6 * fe_tflops / peak_bf16
         cpu = None if args.skip_cpu else cpu_baseline_sample(n)
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 operands, f32 accumulate (FP32-equivalent)" if math == "tc" else "f32",
             "data": "synthetic", "config": workload_config(args, pool_mb=round(pool_n * step_bytes / 1e6)),
             "p99_step_ms": float(np.percentile(lat, 99)), "p50_step_ms": float(np.percentile(lat, 50)),
             "frames_per_s": value / 0.032,
-            "roofline": {
-                "bound": "fp32_ffma", "kernel": f"{args.model}_frontend_kernel" +
-                ("+resample_kernel" if args.src_rate != 16000 else ""), "achieved": fe_tflops, "peak": peak_fp32,
-                "unit": "TFLOP/s", "frac": fe_tflops / peak_fp32,
-                "traffic": (traffic or {}).get("bytes"), "traffic_source": (traffic or {}).get("source"),
-                "algorithmic_bytes_per_launch": frames_per_step * 2048 + 156032 * 4 + frames_per_step * 512,
-                "peak_source": f"148 SMs x 128 FP32 lanes x 2 x sm_max_mhz {sm_max:.0f} ({peaks_src} "
-                               "MEASURED_PEAKS.json clock); the path is FP32-FFMA bound, not HBM or tensor bound",
-                "algorithmic_flop_per_frame": flop_fe, "frames_per_launch": frames_per_step,
-                "avg_launch_ms": fe_avg_s * 1e3,
-                "recurrent_kernel": {"avg_launch_ms": rec_avg_s * 1e3,
-                                     "achieved": frames_per_step * flop_rec / rec_avg_s / 1e12 if rec_avg_s else 0,
-                                     "algorithmic_flop_per_frame": flop_rec},
-                "whole_step": {"achieved": step_tflops, "frac": step_tflops / peak_fp32,
-                               "algorithmic_flop_per_frame": flop_frame},
-                "hbm": {"algorithmic_bytes_per_frame": 2048 + 2 * 1024 + 4 + 1,
-                        "achieved_gbs": frames_per_step * (2048 + 2048 + 5) / (dev_ms / args.steps * 1e-3) / 1e9,
-                        "peak_gbs": peaks.get("hbm_gbs")},
-            },
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": step_bytes,
                     "d2h_bytes_per_step": n * F * 5 + n * 4 + 4, "ms_per_step": e2e_ms_max / args.steps,
@@ -452,6 +479,8 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
     ap.add_argument("--frames-per-step", type=int, default=1, help="512-sample frames per stream per step")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--math", choices=["tc", "fp32"], default="tc",
+                    help="v5 GEMM arithmetic: tc = tcgen05 tensor cores with the 3-way BF16 split, fp32 = packed FP32 FMA")
     ap.add_argument("--model", choices=["v5", "v4"], default="v5", help="v5 = headline (configs[1]); v4 = configs[2]")
     ap.add_argument("--src-rate", type=int, default=16000, choices=[8000, 16000, 24000, 48000],
                     help="source rate of the synthetic streams; != 16000 adds the GPU resampler (configs[2..3])")

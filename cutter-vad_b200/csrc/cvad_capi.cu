@@ -522,7 +522,19 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         e->launches++;
         if (timed) CU_TRY(e, cudaEventRecord(ev[1], stream));
         if (!d_dbg) {
-            cvad::tc5::v5tc_recurrent_kernel<<<n_stiles, cvad::tc5::kThreadsTC, cvad::tc5::kRecSmemTC, stream>>>(p);
+            // programmatic dependent launch: the recurrent grid is scheduled while the front end still runs and
+            // overlaps its prologue with it (not when per-kernel timing events sit between the two launches)
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)n_stiles);
+            cfg.blockDim = dim3((unsigned)cvad::tc5::kThreadsTC);
+            cfg.dynamicSmemBytes = cvad::tc5::kRecSmemTC;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = timed ? 0 : 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CU_TRY(e, cudaLaunchKernelEx(&cfg, cvad::tc5::v5tc_recurrent_kernel, p));
             CU_TRY(e, cudaGetLastError());
             e->launches++;
         }
@@ -847,7 +859,7 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
             (rc = upload(e, &e->nyq_w, T.nyq_w)) || (rc = upload(e, &e->b_rec_tc, T.b_rec)))
             return bail(rc);
         const char *m = std::getenv("CVAD_MATH");
-        if (m && std::strcmp(m, "tc") == 0) e->math = CVAD_MATH_TC;
+        e->math = (m && std::strcmp(m, "fp32") == 0) ? CVAD_MATH_FP32 : CVAD_MATH_TC;
     }
     {
         V5Packed P = model_version == CVAD_MODEL_V5 ? pack_v5(weights) : pack_v4(weights);

@@ -187,6 +187,12 @@ __device__ __forceinline__ void issue_split(int wp, uint32_t a_addr, uint32_t b0
     }
 }
 
+__device__ __forceinline__ long long gtime_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define CVAD_PROF_NS(k) do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(k)] = gtime_ns(); } while (0)
 #define CVAD_PROF(k) do { if (p.prof && blockIdx.x == 0 && first_tile) p.prof[(k)] = clock64(); } while (0)
 
 struct Ring {
@@ -212,6 +218,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     int *s_valid = s_slot + kTile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    CVAD_PROF_NS(120);
 
     if (tid == 0) {
         for (int i = 0; i < kFeRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -224,6 +231,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     __syncthreads();
     tc::fence_after_sync();
     if (*tmem_slot != 0u) __trap();   // sole CTA on the SM and all 512 columns: TMEM base is lane 0 / column 0
+    CVAD_PROF_NS(121);
+    // programmatic dependent launch: the recurrent kernel may be scheduled now; it runs its own prologue (state
+    // load, weight prefetch) and blocks in griddepcontrol.wait until this grid has completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int n_tiles = p.max_frames * p.n_stiles;
     const uint32_t act_s = smem_u32(act), ring_s = smem_u32(ring_buf);
@@ -588,6 +599,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     tc::fence_before_sync();
     __syncthreads();
     if (warp == kProducerWarp) tc::tmem_dealloc(0u, 512);
+    CVAD_PROF_NS(122);
 }
 
 // =====================================================================================
@@ -617,14 +629,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int st = blockIdx.x;
     const int ms = p.max_streams;
+    CVAD_PROF_NS(123);
 
     if (tid < kTile) {
         const int i = st * kTile + tid;
         int slot = -1, nf = 0;
         if (i < p.n_streams) {
             slot = p.slots ? p.slots[i] : i;
-            nf = p.n_frames ? p.n_frames[i] : p.max_frames;
-            if (p.status && p.status[i] != 0u) nf = 0;  // NaN/Inf: the reference raises before any frame runs
+            nf = p.n_frames ? p.n_frames[i] : p.max_frames;   // loop bound; the NaN/Inf status is applied after the grid dependency
             s_startp[tid] = p.start_p[slot];
             s_endp[tid] = p.end_p[slot];
         }
@@ -644,6 +656,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
     __syncthreads();
     tc::fence_after_sync();
     if (*tmem_slot != 0u) __trap();
+    CVAD_PROF_NS(124);
     int tmax = 0;
     {
         int v = s_nfr[lane];
@@ -707,12 +720,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
             const int i0 = 8 * cg;                // its 8 streams
             bool first_tile = tid == 0;
             CVAD_PROF(64);
-            if (tid == 0)
-                for (int j = 0; j < 2 && j < tmax; ++j) {
-                    mbar_arrive_expect_tx(&xfull[j], kFeatTileBytes);
-                    bulk_g2s(xbuf + j * kFeatTileBytes, p.feat_tc + ((size_t)j * p.n_stiles + st) * kFeatTileBytes,
-                             kFeatTileBytes, &xfull[j]);
-                }
             // resident state: h -> BF16x3 rows of the B operand, c -> registers (coalesced through sbuf;
             // both global reads are in flight before the first barrier)
             float hreg[8], creg[8];
@@ -746,6 +753,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
             epi_bar();
             if (tid == 0) mbar_arrive(h_ready);
             CVAD_PROF(65);
+            // ---- everything above only touched state owned by this kernel; the front end's outputs (status, feat)
+            //      are read after the grid dependency resolves
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            if (warp == 0) {
+                const int i = st * kTile + lane;
+                if (i < p.n_streams && p.status && p.status[i] != 0u) s_nfr[lane] = 0;  // NaN/Inf: the reference raises before any frame runs
+            }
+            epi_bar();
+            if (tid == 0)
+                for (int j = 0; j < 2 && j < tmax; ++j) {
+                    mbar_arrive_expect_tx(&xfull[j], kFeatTileBytes);
+                    bulk_g2s(xbuf + j * kFeatTileBytes, p.feat_tc + ((size_t)j * p.n_stiles + st) * kFeatTileBytes,
+                             kFeatTileBytes, &xfull[j]);
+                }
 
             // state machine words (warp 0, one lane per stream)
             int sm_active = 0, sm_sc = 0, sm_ec = 0, sm_ns = 1, sm_ne = 1;
@@ -902,6 +923,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
     tc::fence_before_sync();
     __syncthreads();
     if (warp == kProducerWarp) tc::tmem_dealloc(0u, 512);
+    CVAD_PROF_NS(125);
 }
 
 }  // namespace tc5

@@ -125,7 +125,7 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
 int cvad_destroy(cvad_engine *e);
 
 /* Select the arithmetic of the model kernels (CVAD_MATH_*); v4 engines only accept CVAD_MATH_FP32.
-   The initial mode is CVAD_MATH_FP32 unless the environment variable CVAD_MATH is "tc". */
+   A v5 engine starts in CVAD_MATH_TC unless the environment variable CVAD_MATH is "fp32"; v4 engines are FP32. */
 int cvad_set_math(cvad_engine *e, int math);
 int cvad_get_math(const cvad_engine *e);
 

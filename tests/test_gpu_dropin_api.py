@@ -12,6 +12,19 @@ from conftest import GOLDEN, synth_streams
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["tc", "fp32"])
+def math_mode(request, monkeypatch):
+    """Every test runs on both arithmetic paths of the v5 engine: tcgen05 tensor cores (BF16 3-way split) and
+    packed FP32 FMA.  cvad_create reads CVAD_MATH; engines are created inside the tests."""
+    monkeypatch.setenv("CVAD_MATH", request.param)
+    from real_time_vad.engine import pool
+    for (version, _dev, _path), engines in pool._ENGINES.items():   # engines the process-wide pool already holds
+        if version == "v5":
+            for pe in engines:
+                pe.engine.set_math(request.param)
+    return request.param
+
 TOL = 1e-4
 
 

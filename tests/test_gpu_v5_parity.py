@@ -10,6 +10,14 @@ from conftest import GOLDEN, synth_streams
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["tc", "fp32"])
+def math_mode(request, monkeypatch):
+    """Every test runs on both arithmetic paths of the v5 engine: tcgen05 tensor cores (BF16 3-way split) and
+    packed FP32 FMA.  cvad_create reads CVAD_MATH; engines are created inside the tests."""
+    monkeypatch.setenv("CVAD_MATH", request.param)
+    return request.param
+
 TOL = 1e-4
 
 

@@ -33,3 +33,5 @@ print("recurrent epilogue: start 0, state loaded", out[65] - r0)
 for j in range(min(T, 8)):
     print(f"  frame {j}: acc_ready {out[66 + 3 * j] - r0}, h written {out[67 + 3 * j] - r0}, frame done {out[68 + 3 * j] - r0}"
           f" | mma: x ready {out[96 + 3 * j] - r0}, h ready {out[97 + 3 * j] - r0}, issued {out[98 + 3 * j] - r0}")
+g = out[120:126] - out[120]
+print("globaltimer ns: FE entry 0, FE prologue done", g[1], "FE exit", g[2], "| REC entry", g[3], "REC prologue done", g[4], "REC exit", g[5])
