@@ -345,20 +345,54 @@ def run_ours(args):
         e2e_lat.append(time.perf_counter() - t1)
     torch.cuda.synchronize()
     e2e_blocking_s = (time.perf_counter() - t0) / min(args.steps, 300)
-    # (b) pipelined calls (submit step i+1 before collecting step i): the throughput figure.
+    # (b) pipelined calls (submit steps i+1, i+2 before collecting step i): the throughput figure.
     #     Every step's H2D of its inputs and D2H of its results is inside the timed region.
     eng.reset()
     barrier()
+    from collections import deque
+    depth = 3                                      # steps in flight (the engine allows 4)
+    inflight = deque()
     t0 = time.perf_counter()
-    pending = eng.submit(host_np[args.warmup % pool_n], src_rate=args.src_rate)
-    for i in range(1, args.steps):
-        nxt = eng.submit(host_np[(args.warmup + i) % pool_n], src_rate=args.src_rate)
-        r = pending.collect()
-        pending = nxt
-    r = pending.collect()
+    for i in range(args.steps):
+        inflight.append(eng.submit(host_np[(args.warmup + i) % pool_n], src_rate=args.src_rate))
+        if len(inflight) == depth:
+            r = inflight.popleft().collect()
+    while inflight:
+        r = inflight.popleft().collect()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_events = len(r.events)
+    # (c) the same pipelined loop with 16-bit PCM in the host buffers (the websocket service's wire format,
+    #     vad_websocket_server.py:341; converted with /32767.0f in the frame loader): half the PCIe bytes
+    e2e_s16_s = None
+    if args.src_rate == 16000:
+        s16_pool = []
+        for i in range(min(pool_n, 8)):
+            t = torch.empty((n, step_samples), dtype=torch.int16).pin_memory()
+            t.numpy()[:] = np.clip(np.rint(host_np[i] * 32767.0), -32768, 32767).astype(np.int16)
+            s16_pool.append(t.numpy())
+        eng.reset()
+        for i in range(args.warmup):
+            eng.step(s16_pool[i % len(s16_pool)], pcm_format=capi.PCM_S16_32767)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            inflight.append(eng.submit(s16_pool[i % len(s16_pool)], pcm_format=capi.PCM_S16_32767))
+            if len(inflight) == depth:
+                inflight.popleft().collect()
+        while inflight:
+            inflight.popleft().collect()
+        torch.cuda.synchronize()
+        e2e_s16_s = time.perf_counter() - t0
+    # raw pinned host -> device copy rate of one step's input, for context (e2e is transfer-bound)
+    h0 = torch.cuda.Event(enable_timing=True)
+    h1 = torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for i in range(10):
+        dev_pool[i % pool_n].copy_(host_pool[i % pool_n], non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 10 * step_bytes / (h0.elapsed_time(h1) * 1e-3) / 1e9
     clocks = sampler.stop()
 
     times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
@@ -432,7 +466,11 @@ def run_ours(args):
                     "p99_step_ms": 1e3 * float(np.percentile(e2e_lat, 99)),
                     "blocking_ms_per_step": 1e3 * e2e_blocking_s,
                     "blocking_value": audio_s_per_step / e2e_blocking_s,
-                    "api": "StreamEngine.submit/collect -> cvad_step_submit/cvad_step_collect, two steps in flight, "
+                    "pinned_h2d_gbs": h2d_gbs, "transfer_bound_value": audio_s_per_step * world / (step_bytes / (h2d_gbs * 1e9)),
+                    "s16": (None if e2e_s16_s is None else
+                            {"value": audio_s_per_step * args.steps * world / e2e_s16_s, "h2d_bytes_per_step": step_bytes // 2,
+                             "pcm": "int16 / 32767.0f in the frame loader (CVAD_PCM_S16_32767)"}),
+                    "api": "StreamEngine.submit/collect -> cvad_step_submit/cvad_step_collect, three steps in flight, "
                            "float32 PCM in pinned host buffers; p99_step_ms and blocking_* are the one-call-at-a-time "
                            "StreamEngine.step figures", "events_last_step": e2e_events},
             "gpu_launches": int(launches),

@@ -31,6 +31,8 @@ struct DevBuf {
 
 }  // namespace
 
+constexpr int kLanes = 4;   // host-buffer steps in flight (cvad_step_submit)
+
 struct cvad_engine {
     int device = 0;
     int version = 0;
@@ -61,7 +63,7 @@ struct cvad_engine {
     cudaEvent_t last_done = nullptr;   // recorded after the kernels of the most recent step
     float *rs_rt[3] = {nullptr, nullptr, nullptr};  // R^T for 8 / 24 / 48 kHz, built on first use
     DevBuf d_res;                      // resampled 16 kHz audio of the step being launched
-    // host-buffer steps run on two lanes so that step i+1's H2D overlaps step i's kernels
+    // host-buffer steps run on kLanes lanes so that later steps' H2D copies overlap earlier steps' kernels and D2H
     struct Lane {
         cudaStream_t stream = nullptr;
         DevBuf d_audio, d_slots, d_nframes, d_probs, d_flags, d_status, d_events;
@@ -70,7 +72,7 @@ struct cvad_engine {
         bool busy = false;
         cvad_step_args args{};          // caller's (host) argument block of the step in flight
         std::vector<int32_t> nfr_copy;  // n_frames as submitted (caller may reuse its array)
-    } lanes[2];
+    } lanes[kLanes];
     int next_lane = 0;
     // optional per-kernel timing (bench): event triples (before FE, between, after REC)
     bool timing = false;
@@ -1167,17 +1169,17 @@ int cvad_step_submit(cvad_engine *e, const cvad_step_args *a, int *ticket) {
     if (!e) return CVAD_E_INVALID;
     if (!ticket) return fail(e, CVAD_E_INVALID, "ticket is NULL");
     const int lane = e->next_lane;
-    if (e->lanes[lane].busy) return fail(e, CVAD_E_CAPACITY, "two steps are already in flight: collect one first");
+    if (e->lanes[lane].busy) return fail(e, CVAD_E_CAPACITY, "four steps are already in flight: collect one first");
     int rc = step_submit(e, e->lanes[lane], a, nullptr, 0);
     if (rc) return rc;
     *ticket = lane;
-    e->next_lane = lane ^ 1;
+    e->next_lane = (lane + 1) % kLanes;
     return CVAD_OK;
 }
 
 int cvad_step_collect(cvad_engine *e, int ticket) {
     if (!e) return CVAD_E_INVALID;
-    if (ticket < 0 || ticket > 1) return fail(e, CVAD_E_INVALID, "bad ticket");
+    if (ticket < 0 || ticket >= kLanes) return fail(e, CVAD_E_INVALID, "bad ticket");
     return step_collect(e, e->lanes[ticket], false);
 }
 
@@ -1194,7 +1196,8 @@ int cvad_debug_dump(cvad_engine *e, const cvad_step_args *a, float *dbg_out, siz
     int rc = quiesce(e);
     if (rc) return rc;
     cvad_engine::Lane &ln = e->lanes[0];
-    if (ln.busy || e->lanes[1].busy) return fail(e, CVAD_E_INVALID, "steps in flight");
+    for (auto &l : e->lanes)
+        if (l.busy) return fail(e, CVAD_E_INVALID, "steps in flight");
     rc = step_submit(e, ln, a, dbg_out, dbg_floats);
     if (rc) return rc;
     return step_collect(e, ln, true);

@@ -221,7 +221,7 @@ class StreamEngine:
                frame_len: int = 512, hop: int = 512, pcm_format: int = capi.PCM_F32,
                max_events: int = 0, src_rate: int = 16000) -> "PendingStep":
         """Enqueue one step (H2D, kernels, D2H) and return at once; `.collect()` waits for it.
-        Up to two steps may be in flight: the second one's copy overlaps the first one's kernels.
+        Up to four steps may be in flight: later copies overlap earlier steps' kernels and result copies.
         `audio` must stay untouched until collect (pinned arrays are DMA'd in place)."""
         audio = np.asarray(audio)
         if src_rate not in (0, 16000):

@@ -164,9 +164,9 @@ int cvad_step(cvad_engine *e, const cvad_step_args *a);
 /*
  * Pipelined form of cvad_step: submit enqueues H2D, kernels and D2H and returns; collect
  * waits and fills the output buffers named in `a` (which, like `a->audio` when it is
- * pinned memory, must stay valid and untouched until then).  Up to two steps may be in
- * flight; they execute in submission order, and the second step's host-to-device copy
- * overlaps the first step's kernels.  cvad_step == submit + collect.
+ * pinned memory, must stay valid and untouched until then).  Up to four steps may be in
+ * flight; they execute in submission order, and later steps' host-to-device copies
+ * overlap earlier steps' kernels and result copies.  cvad_step == submit + collect.
  */
 int cvad_step_submit(cvad_engine *e, const cvad_step_args *a, int *ticket);
 int cvad_step_collect(cvad_engine *e, int ticket);

@@ -252,7 +252,7 @@ def test_sample_voice_known_answer_four_segments(engine_factory, ref_v5):
 
 
 def test_pipelined_submit_collect_equals_blocking_steps(engine_factory, ref_v5):
-    """Two steps in flight (cvad_step_submit/collect) must give what blocking cvad_step gives,
+    """Up to four steps in flight (cvad_step_submit/collect) must give what blocking cvad_step gives,
     in submission order, with state carried from step to step."""
     from real_time_vad.engine.stream_engine import EngineError
     eng = engine_factory(128)
@@ -264,19 +264,24 @@ def test_pipelined_submit_collect_equals_blocking_steps(engine_factory, ref_v5):
     want, _, _ = ref_v5.run(audio, F * steps, denoise=True)
     chunks = [np.ascontiguousarray(audio[:, k * 512 * F:(k + 1) * 512 * F]) for k in range(steps)]
     got, flags = [], []
-    pending = eng.submit(chunks[0])
-    for k in range(1, steps):
-        nxt = eng.submit(chunks[k])
-        if k == 1:
-            with pytest.raises(EngineError):
-                eng.submit(chunks[k])                      # a third step in flight is refused
-        r = pending.collect()
+    from collections import deque
+    inflight = deque()
+    refused = False
+    for k in range(steps):
+        inflight.append(eng.submit(chunks[k]))
+        if len(inflight) == 4:
+            if not refused:
+                with pytest.raises(EngineError):
+                    eng.submit(chunks[k])                  # a fifth step in flight is refused
+                refused = True
+            r = inflight.popleft().collect()
+            got.append(r.probs.copy())
+            flags.append(r.flags.copy())
+    while inflight:
+        r = inflight.popleft().collect()
         got.append(r.probs.copy())
         flags.append(r.flags.copy())
-        pending = nxt
-    r = pending.collect()
-    got.append(r.probs)
-    flags.append(r.flags)
+    assert refused
     got = np.concatenate(got, axis=1)
     assert np.abs(got - want).max() <= TOL
     # same run with blocking calls: bit-identical
