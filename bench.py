@@ -208,6 +208,8 @@ def workload_config(args, pool_mb):
     rate = getattr(args, "src_rate", 16000)
     return {"workload": f"Silero {model}, {args.streams} concurrent {rate // 1000} kHz streams per GPU batched per "
                         f"frame step" + (" (BASELINE.json configs[1])" if (model, rate) == ("v5", 16000) else
+                                         ", mixed 24/48 kHz by stream parity, resampled to 16 kHz on the GPU in one step "
+                                         "(BASELINE.json configs[3] per-GPU share)" if getattr(args, "mixed_rates", False) else
                                          ", resampled to 16 kHz on the GPU" if rate != 16000 else ""),
             "model": model, "src_rate": rate,
             "streams_per_gpu": args.streams, "frames_per_step": args.frames_per_step, "hop": 512,
@@ -235,6 +237,11 @@ def run_ours(args):
 
     n, F = args.streams, args.frames_per_step
     n_in = args.src_rate * 512 // 16000          # source samples per model frame
+    mixed = bool(getattr(args, "mixed_rates", False))
+    if mixed:                                      # BASELINE.json configs[3]: 24 / 48 kHz by stream parity, one step
+        args.src_rate = 48000
+        n_in = 1536                                # row length; 24 kHz streams use the first half of their row
+        rates_np = np.where(np.arange(n) & 1, 48000, 24000).astype(np.int32)
     step_samples = n_in * F
     step_bytes = n * step_samples * 4
     pool_n = max(2, int(np.ceil(300e6 / step_bytes)))  # > 2x L2 worth of distinct inputs
@@ -248,8 +255,9 @@ def run_ours(args):
     flop_fe = FLOP_FRONTEND if args.model == "v5" else 1_379_280 - 2 * 65_600
     flop_rec = FLOP_RECURRENT if args.model == "v5" else 2 * 65_600
     if args.src_rate != 16000:
-        flop_fe += 2 * 512 * n_in                  # the resampling GEMM runs ahead of the front end
-        flop_frame += 2 * 512 * n_in
+        rs_flop = 2 * 512 * (n_in if not mixed else (768 + 1536) // 2)
+        flop_fe += rs_flop                         # the resampling GEMM runs ahead of the front end
+        flop_frame += rs_flop
     eng.configure(enable_denoising=True)
     stream = torch.cuda.Stream(device=local)
     eng.set_stream(stream.cuda_stream)
@@ -266,6 +274,9 @@ def run_ours(args):
     d_events = torch.zeros((max(16, 2 * n * F) * 24,), dtype=torch.uint8, device=f"cuda:{local}")
     d_nev = torch.zeros((1,), dtype=torch.int32, device=f"cuda:{local}")
 
+    d_rates = torch.from_numpy(rates_np).to(f"cuda:{local}") if mixed else None
+    rate_kw = {"src_rates": rates_np, "max_frames": F} if mixed else {"src_rate": args.src_rate}
+
     def dev_args(buf):
         a = capi.StepArgs()
         a.n_streams = n
@@ -276,6 +287,8 @@ def run_ours(args):
         a.frame_len = n_in
         a.hop = n_in
         a.src_rate = args.src_rate
+        if mixed:
+            a.src_rates = d_rates.data_ptr()
         a.probs_out = d_probs.data_ptr()
         a.flags_out = d_flags.data_ptr()
         a.events_out = d_events.data_ptr()
@@ -334,14 +347,14 @@ def run_ours(args):
     eng.reset()
     host_np = [t.numpy() for t in host_pool]
     for i in range(args.warmup):
-        eng.step(host_np[i % pool_n], src_rate=args.src_rate)
+        eng.step(host_np[i % pool_n], **rate_kw)
     barrier()
     # (a) blocking calls: one step at a time -> per-call latency distribution
     e2e_lat = []
     t0 = time.perf_counter()
     for i in range(min(args.steps, 300)):
         t1 = time.perf_counter()
-        r = eng.step(host_np[(args.warmup + i) % pool_n], src_rate=args.src_rate)
+        r = eng.step(host_np[(args.warmup + i) % pool_n], **rate_kw)
         e2e_lat.append(time.perf_counter() - t1)
     torch.cuda.synchronize()
     e2e_blocking_s = (time.perf_counter() - t0) / min(args.steps, 300)
@@ -354,7 +367,7 @@ def run_ours(args):
     inflight = deque()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        inflight.append(eng.submit(host_np[(args.warmup + i) % pool_n], src_rate=args.src_rate))
+        inflight.append(eng.submit(host_np[(args.warmup + i) % pool_n], **rate_kw))
         if len(inflight) == depth:
             r = inflight.popleft().collect()
     while inflight:
@@ -517,6 +530,8 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
     ap.add_argument("--frames-per-step", type=int, default=1, help="512-sample frames per stream per step")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--mixed-rates", action="store_true",
+                    help="BASELINE.json configs[3] per-GPU share: 24 / 48 kHz streams by parity, resampled in one step")
     ap.add_argument("--math", choices=["tc", "fp32"], default="tc",
                     help="v5 GEMM arithmetic: tc = tcgen05 tensor cores with the 3-way BF16 split, fp32 = packed FP32 FMA")
     ap.add_argument("--model", choices=["v5", "v4"], default="v5", help="v5 = headline (configs[1]); v4 = configs[2]")

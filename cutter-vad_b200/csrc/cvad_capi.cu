@@ -63,10 +63,11 @@ struct cvad_engine {
     cudaEvent_t last_done = nullptr;   // recorded after the kernels of the most recent step
     float *rs_rt[3] = {nullptr, nullptr, nullptr};  // R^T for 8 / 24 / 48 kHz, built on first use
     DevBuf d_res;                      // resampled 16 kHz audio of the step being launched
+    DevBuf d_rate_lists;               // mixed-rate steps: [4][n] stream lists + 4 counters
     // host-buffer steps run on kLanes lanes so that later steps' H2D copies overlap earlier steps' kernels and D2H
     struct Lane {
         cudaStream_t stream = nullptr;
-        DevBuf d_audio, d_slots, d_nframes, d_probs, d_flags, d_status, d_events;
+        DevBuf d_audio, d_slots, d_nframes, d_probs, d_flags, d_status, d_events, d_rates;
         int *d_nevents = nullptr;
         DevBuf h_in, h_out;             // pinned staging
         bool busy = false;
@@ -394,6 +395,8 @@ int validate_args(cvad_engine *e, const cvad_step_args *a) {
     if (a->n_streams > 0 && !a->audio) return fail(e, CVAD_E_INVALID, "Audio data is empty");
     if (a->pcm_format < 0 || a->pcm_format > 2) return fail(e, CVAD_E_INVALID, "unknown pcm_format");
     if (a->max_frames < 0) return fail(e, CVAD_E_INVALID, "max_frames < 0");
+    if (a->max_events < 0) return fail(e, CVAD_E_INVALID, "max_events < 0");
+    if (a->src_rates) return CVAD_OK;   // per-stream rates: frame_len / hop / src_rate are not used
     if (a->frame_len < 1 || a->frame_len > 2048) return fail(e, CVAD_E_INVALID, "frame_len outside [1, 2048]");
     if (a->hop < 1) return fail(e, CVAD_E_INVALID, "hop < 1");
     if (a->src_rate != 0 && a->src_rate != 16000) {
@@ -433,8 +436,21 @@ void build_resample_rt(int n_in, std::vector<float> &rt) {
 }
 
 // Enqueue the two kernels.  Every pointer in `a` is a DEVICE pointer here.
+int ensure_rt(cvad_engine *e, int src_rate, cudaStream_t stream) {
+    const int ri = rate_index(src_rate), n_in = rate_n_in(src_rate);
+    if (e->rs_rt[ri]) return CVAD_OK;
+    std::vector<float> rt;
+    build_resample_rt(n_in, rt);
+    CU_TRY(e, cudaMalloc(reinterpret_cast<void **>(&e->rs_rt[ri]), rt.size() * sizeof(float)));
+    CU_TRY(e, cudaMemcpyAsync(e->rs_rt[ri], rt.data(), rt.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CU_TRY(e, cudaStreamSynchronize(stream));
+    return CVAD_OK;
+}
+
+// `rates_mask`: which of the rate slots {8000, 24000, 48000, 16000} may occur in a->src_rates (bit r); callers
+// that cannot look at the array (device-pointer steps) pass 0xF
 int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status, int commit, float *d_dbg,
-                cudaStream_t stream) {
+                cudaStream_t stream, unsigned rates_mask = 0xFu) {
     if (a->n_streams == 0 || a->max_frames == 0) return CVAD_OK;
     // state and `feat` are shared: kernels of consecutive steps never overlap, whatever stream they use
     CU_TRY(e, cudaStreamWaitEvent(stream, e->last_done, 0));
@@ -461,26 +477,55 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
     p.stride = a->stream_stride;
     p.frame_len = a->frame_len;
     p.hop = a->hop;
-    const bool resampled = a->src_rate != 0 && a->src_rate != 16000;
+    const bool mixed = a->src_rates != nullptr;
+    const bool resampled = mixed || (a->src_rate != 0 && a->src_rate != 16000);
     if (resampled) {
         // stage 0: source-rate chunks -> 16 kHz float frames in HBM; the model kernels then see native input
-        const int ri = rate_index(a->src_rate), n_in = rate_n_in(a->src_rate);
-        if (!e->rs_rt[ri]) {
-            std::vector<float> rt;
-            build_resample_rt(n_in, rt);
-            CU_TRY(e, cudaMalloc(reinterpret_cast<void **>(&e->rs_rt[ri]), rt.size() * sizeof(float)));
-            CU_TRY(e, cudaMemcpyAsync(e->rs_rt[ri], rt.data(), rt.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
-            CU_TRY(e, cudaStreamSynchronize(stream));
-        }
         if ((rc = grow(e, e->d_res, (size_t)a->n_streams * a->max_frames * 512 * sizeof(float)))) return rc;
         cvad::ResampleStep r{};
-        r.audio = a->audio; r.pcm = a->pcm_format; r.stride = a->stream_stride; r.n_in = n_in;
+        r.audio = a->audio; r.pcm = a->pcm_format; r.stride = a->stream_stride;
         r.n_streams = a->n_streams; r.n_stiles = n_stiles; r.max_frames = a->max_frames; r.n_frames = a->n_frames;
-        r.rt = e->rs_rt[ri]; r.out = static_cast<float *>(e->d_res.p);
+        r.out = static_cast<float *>(e->d_res.p);
         const int grid_rs = std::min(a->max_frames * n_stiles, e->num_sms);
-        cvad::resample_kernel<<<grid_rs, cvad::kThreads, cvad::kRsSmemBytes, stream>>>(r);
-        CU_TRY(e, cudaGetLastError());
-        e->launches++;
+        if (!mixed) {
+            if ((rc = ensure_rt(e, a->src_rate, stream))) return rc;
+            r.n_in = rate_n_in(a->src_rate);
+            r.rt = e->rs_rt[rate_index(a->src_rate)];
+            cvad::resample_kernel<<<grid_rs, cvad::kThreads, cvad::kRsSmemBytes, stream>>>(r);
+            CU_TRY(e, cudaGetLastError());
+            e->launches++;
+        } else {
+            // one launch per source rate over that rate's stream list (built on the device: no host round trip)
+            const size_t n = (size_t)a->n_streams;
+            if ((rc = grow(e, e->d_rate_lists, (4 * n + 4) * sizeof(int)))) return rc;
+            int *lists = static_cast<int *>(e->d_rate_lists.p);
+            int *counts = lists + 4 * n;
+            CU_TRY(e, cudaMemsetAsync(counts, 0, 4 * sizeof(int), stream));
+            cvad::rate_lists_kernel<<<(a->n_streams + 255) / 256, 256, 0, stream>>>(a->src_rates, a->n_streams, lists, counts,
+                                                                                  d_status);
+            CU_TRY(e, cudaGetLastError());
+            e->launches++;
+            static const int kRates[3] = {8000, 24000, 48000};
+            for (int ri = 0; ri < 3; ++ri) {
+                if (!(rates_mask & (1u << ri))) continue;
+                if ((rc = ensure_rt(e, kRates[ri], stream))) return rc;
+                r.n_in = rate_n_in(kRates[ri]);
+                r.rt = e->rs_rt[ri];
+                r.list = lists + (size_t)ri * n;
+                r.count = counts + ri;
+                cvad::resample_kernel<<<grid_rs, cvad::kThreads, cvad::kRsSmemBytes, stream>>>(r);
+                CU_TRY(e, cudaGetLastError());
+                e->launches++;
+            }
+            if (rates_mask & 8u) {
+                r.n_in = 512;
+                r.list = lists + 3 * n;
+                r.count = counts + 3;
+                cvad::passthrough_kernel<<<std::min(4 * e->num_sms, (a->n_streams * a->max_frames * 2) + 1), 256, 0, stream>>>(r);
+                CU_TRY(e, cudaGetLastError());
+                e->launches++;
+            }
+        }
         p.audio = e->d_res.p;
         p.pcm = CVAD_PCM_F32;
         p.stride = (long long)a->max_frames * 512;
@@ -638,12 +683,27 @@ int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, 
         ln.nfr_copy.assign(a->n_frames, a->n_frames + n);
     }
     const size_t es = elem_size(a->pcm_format);
-    const size_t row = (size_t)(T - 1) * a->hop + a->frame_len;
+    size_t row = (size_t)(T - 1) * a->hop + a->frame_len;
+    size_t last_row = row;
+    unsigned rates_mask = 0;
+    if (a->src_rates) {
+        row = 0;
+        for (int i = 0; i < n; ++i) {
+            const int r = cvad::rate_slot(a->src_rates[i]);
+            if (r < 0) {
+                ln.busy = false;
+                return fail(e, CVAD_E_INVALID, "src_rates[i] must be 8000, 16000, 24000 or 48000");
+            }
+            rates_mask |= 1u << r;
+            last_row = (size_t)T * (size_t)rate_n_in(a->src_rates[i]);
+            row = std::max(row, last_row);
+        }
+    }
     if (n > 1 && (a->stream_stride < 0 || (size_t)a->stream_stride < row)) {
         ln.busy = false;
-        return fail(e, CVAD_E_INVALID, "stream_stride shorter than (max_frames-1)*hop + frame_len");
+        return fail(e, CVAD_E_INVALID, "stream_stride shorter than one stream's samples in this step");
     }
-    const size_t audio_elems = (size_t)(n - 1) * a->stream_stride + row;
+    const size_t audio_elems = (size_t)(n - 1) * a->stream_stride + last_row;
     const size_t audio_bytes = audio_elems * es;
     auto bail = [&](int code) { ln.busy = false; return code; };
 
@@ -651,11 +711,12 @@ int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, 
     if ((rc = grow(e, ln.d_audio, audio_bytes + 16)) || (rc = grow(e, ln.d_slots, (size_t)n * 4)) ||
         (rc = grow(e, ln.d_nframes, (size_t)n * 4)) || (rc = grow(e, ln.d_probs, (size_t)n * T * 4)) ||
         (rc = grow(e, ln.d_flags, (size_t)n * T)) || (rc = grow(e, ln.d_status, (size_t)n * 4)) ||
-        (rc = grow(e, ln.d_events, (size_t)std::max(a->max_events, 1) * sizeof(cvad_event))))
+        (rc = grow(e, ln.d_events, (size_t)std::max(a->max_events, 1) * sizeof(cvad_event))) ||
+        (a->src_rates && (rc = grow(e, ln.d_rates, (size_t)n * 4))))
         return bail(rc);
 
     // ---- host -> device (pinned caller memory goes straight; pageable memory is staged)
-    const size_t small_in = (size_t)n * 8;
+    const size_t small_in = (size_t)n * 12;
     const bool direct = is_host_pinned_or_device(a->audio, false);
     if ((rc = grow_host(e, ln.h_in, (direct ? 0 : audio_bytes) + small_in + 128))) return bail(rc);
     unsigned char *hin = static_cast<unsigned char *>(ln.h_in.p);
@@ -663,6 +724,8 @@ int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, 
     int *h_nfr = h_slots + n;
     if (a->slots) std::memcpy(h_slots, a->slots, (size_t)n * 4);
     if (a->n_frames) std::memcpy(h_nfr, a->n_frames, (size_t)n * 4);
+    int *h_rates = h_nfr + n;
+    if (a->src_rates) std::memcpy(h_rates, a->src_rates, (size_t)n * 4);
     const void *src_audio = a->audio;
     if (!direct) {
         unsigned char *stage = hin + ((small_in + 63) / 64) * 64;
@@ -673,6 +736,7 @@ int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, 
     CU_TRY(e, cudaMemcpyAsync(ln.d_audio.p, src_audio, audio_bytes, cudaMemcpyHostToDevice, st));
     if (a->slots) CU_TRY(e, cudaMemcpyAsync(ln.d_slots.p, h_slots, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     if (a->n_frames) CU_TRY(e, cudaMemcpyAsync(ln.d_nframes.p, h_nfr, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (a->src_rates) CU_TRY(e, cudaMemcpyAsync(ln.d_rates.p, h_rates, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CU_TRY(e, cudaMemsetAsync(ln.d_status.p, 0, (size_t)n * 4, st));
     CU_TRY(e, cudaMemsetAsync(ln.d_nevents, 0, sizeof(int), st));
 
@@ -680,6 +744,7 @@ int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, 
     d.audio = ln.d_audio.p;
     d.slots = a->slots ? static_cast<const int32_t *>(ln.d_slots.p) : nullptr;
     d.n_frames = a->n_frames ? static_cast<const int32_t *>(ln.d_nframes.p) : nullptr;
+    d.src_rates = a->src_rates ? static_cast<const int32_t *>(ln.d_rates.p) : nullptr;
     d.probs_out = static_cast<float *>(ln.d_probs.p);
     d.flags_out = static_cast<uint8_t *>(ln.d_flags.p);
     d.status_out = nullptr;
@@ -694,7 +759,8 @@ int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, 
         d_dbg = static_cast<float *>(e->d_dbg.p);
         CU_TRY(e, cudaMemsetAsync(d_dbg, 0, nd * 4, st));
     }
-    rc = launch_step(e, &d, static_cast<unsigned int *>(ln.d_status.p), dbg_out ? 0 : 1, d_dbg, st);
+    rc = launch_step(e, &d, static_cast<unsigned int *>(ln.d_status.p), dbg_out ? 0 : 1, d_dbg, st,
+                     a->src_rates ? rates_mask : 0xFu);
     if (rc) return bail(rc);
     if (dbg_out) {
         const size_t nd = e->version == CVAD_MODEL_V4 ? (size_t)cvad::kV4DbgFloats : (size_t)cvad::kDbgFloats;
@@ -904,13 +970,13 @@ int cvad_destroy(cvad_engine *e) {
                     e->sm_scount, e->sm_ecount, e->frames_done, e->start_p, e->end_p, e->n_start, e->n_end,
                     e->denoise, e->d_status_dev.p, e->d_feat.p, e->d_dbg.p, e->d_cfg_slots.p, e->d_res.p,
                     e->rs_rt[0], e->rs_rt[1], e->rs_rt[2], e->w_fe_tc, e->w_rec_tc, e->nyq_w, e->b_rec_tc,
-                    e->d_feat_tc.p, e->d_prof};
+                    e->d_feat_tc.p, e->d_prof, e->d_rate_lists.p};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &ln : e->lanes) {
         if (ln.stream) cudaStreamSynchronize(ln.stream);
         void *lp[] = {ln.d_audio.p, ln.d_slots.p, ln.d_nframes.p, ln.d_probs.p, ln.d_flags.p, ln.d_status.p,
-                      ln.d_events.p, ln.d_nevents};
+                      ln.d_events.p, ln.d_nevents, ln.d_rates.p};
         for (void *p : lp)
             if (p) cudaFree(p);
         if (ln.h_in.p) cudaFreeHost(ln.h_in.p);

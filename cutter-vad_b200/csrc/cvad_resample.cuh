@@ -33,10 +33,14 @@ struct ResampleStep {
     const int *n_frames; // or null
     const float *rt;     // R^T [n_in][512]
     float *out;          // [n_streams][max_frames * 512]
+    // mixed-rate steps: this launch handles the streams listed in `list` (their number is read from the
+    // device word `count`); null = all n_streams in order
+    const int *list;
+    const int *count;
 };
 
 constexpr int kRsPiece = 128;  // source samples staged per piece
-constexpr size_t kRsSmemBytes = (size_t)(kRingStages * kRingSlotFloats + 2 * kRsPiece * kTile) * 4 + 64 + 256;
+constexpr size_t kRsSmemBytes = (size_t)(kRingStages * kRingSlotFloats + 2 * kRsPiece * kTile) * 4 + 64 + 512;
 
 __device__ __forceinline__ void rs_ring_issue(const WeightRing &r, uint32_t g, uint32_t period) {
     const uint32_t slot = g % kRingStages;
@@ -69,22 +73,29 @@ __global__ void __launch_bounds__(kThreads, 1) resample_kernel(const ResampleSte
     if (tid == 0)
         for (uint32_t i = 0; i < kRingStages; ++i) rs_ring_issue(ring, i, period);
 
-    const int n_tiles = p.max_frames * p.n_stiles;
+    const int n_items = p.count ? *p.count : p.n_streams;
+    const int n_stiles = p.count ? (n_items + kTile - 1) / kTile : p.n_stiles;
+    const int n_tiles = p.max_frames * n_stiles;
+    int *s_gi = s_valid + kTile;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int frame = tile / p.n_stiles;
-        const int st = tile - frame * p.n_stiles;
+        const int frame = tile / n_stiles;
+        const int st = tile - frame * n_stiles;
         if (tid < kTile) {
-            const int i = st * kTile + tid;
-            int valid = 0;
-            if (i < p.n_streams) valid = frame < (p.n_frames ? p.n_frames[i] : p.max_frames);
+            const int j = st * kTile + tid;
+            int valid = 0, i = -1;
+            if (j < n_items) {
+                i = p.list ? p.list[j] : j;
+                valid = frame < (p.n_frames ? p.n_frames[i] : p.max_frames);
+            }
             s_valid[tid] = valid;
+            s_gi[tid] = i;
         }
         const int any_valid = __syncthreads_or(tid < kTile ? s_valid[tid] : 0);
         if (!any_valid) continue;
 
         // piece loader: lane = item, each thread two float4 of the 128-sample piece
         const int s = lane;
-        const int gi = st * kTile + s;
+        const int gi = s_gi[s];
         const bool valid = s_valid[s] != 0;
         const long long base = (long long)gi * p.stride + (long long)frame * p.n_in;
         auto load_piece = [&](int piece, float (&v)[2][4]) {
@@ -151,8 +162,8 @@ __global__ void __launch_bounds__(kThreads, 1) resample_kernel(const ResampleSte
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int item = 4 * tm + i;
-            const int gidx = st * kTile + item;
-            if (gidx < p.n_streams && s_valid[item]) {
+            const int gidx = s_gi[item];
+            if (gidx >= 0 && s_valid[item]) {
                 float *dst = p.out + (size_t)gidx * p.max_frames * 512 + (size_t)frame * 512 + 8 * tn;
                 st4(dst, make_float4(v0[i][0], v0[i][1], v0[i][2], v0[i][3]));
                 st4(dst + 4, make_float4(v1[i][0], v1[i][1], v1[i][2], v1[i][3]));
@@ -163,6 +174,45 @@ __global__ void __launch_bounds__(kThreads, 1) resample_kernel(const ResampleSte
     for (int i = 0; i < kRingStages; ++i) {
         ring_wait(ring);
         ++ring.g;
+    }
+}
+
+// ---- mixed-rate steps: per-rate stream lists, and the pass-through of streams that are already at 16 kHz
+__device__ __host__ __forceinline__ int rate_slot(int rate) {
+    return rate == 8000 ? 0 : rate == 24000 ? 1 : rate == 48000 ? 2 : rate == 16000 ? 3 : -1;
+}
+
+// lists[r][0 .. counts[r]) = indices of the streams whose source rate has slot r (order is irrelevant:
+// streams are independent); a stream with an unknown rate gets status bit 2
+__global__ void rate_lists_kernel(const int *src_rates, int n, int *lists, int *counts, unsigned int *status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = rate_slot(src_rates[i]);
+    if (r < 0) {
+        if (status) atomicOr(&status[i], 2u);
+        return;
+    }
+    lists[(size_t)r * n + atomicAdd(&counts[r], 1)] = i;
+}
+
+// 16 kHz streams of a mixed-rate step: PCM -> float32 frames in the resampler's output layout
+__global__ void passthrough_kernel(const ResampleStep p) {
+    const int n_items = *p.count;
+    const long long per = (long long)p.max_frames * 512;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n_items * per;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / per);
+        const long long k = idx - j * per;
+        const int i = p.list[j];
+        if ((int)(k >> 9) >= (p.n_frames ? p.n_frames[i] : p.max_frames)) continue;
+        const long long off = (long long)i * p.stride + k;
+        float x;
+        if (p.pcm == 0) x = __ldg(reinterpret_cast<const float *>(p.audio) + off);
+        else {
+            x = (float)__ldg(reinterpret_cast<const short *>(p.audio) + off);
+            x = p.pcm == 1 ? __fdiv_rn(x, 32767.0f) : x * (1.0f / 32768.0f);
+        }
+        p.out[(size_t)i * per + k] = x;
     }
 }
 

@@ -52,6 +52,7 @@ class StepArgs(C.Structure):
         ("events_out", C.c_void_p),
         ("max_events", C.c_int32),
         ("n_events_out", C.c_void_p),
+        ("src_rates", C.c_void_p),
     ]
 
 

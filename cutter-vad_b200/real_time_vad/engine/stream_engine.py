@@ -184,7 +184,8 @@ class StreamEngine:
         self._check(self._L.cvad_set_state(self._h, int(slot), _ptr(h), _ptr(c), _ptr(sm)))
 
     # ------------------------------------------------------------------ the hot call
-    def _args(self, audio: np.ndarray, slots, n_frames, max_frames, frame_len, hop, pcm_format, src_rate=16000):
+    def _args(self, audio: np.ndarray, slots, n_frames, max_frames, frame_len, hop, pcm_format, src_rate=16000,
+              src_rates=None):
         if audio.ndim != 2:
             raise EngineError(capi.E_INVALID, "audio must be [n_streams, samples]")
         if pcm_format == capi.PCM_F32:
@@ -214,22 +215,34 @@ class StreamEngine:
         a.frame_len = int(frame_len)
         a.hop = int(hop)
         a.src_rate = int(src_rate)
+        if src_rates is not None:
+            sr = np.ascontiguousarray(src_rates, dtype=np.int32)
+            if sr.size != n:
+                raise EngineError(capi.E_INVALID, "len(src_rates) != n_streams")
+            keep.append(sr)
+            a.src_rates = sr.ctypes.data
         return a, keep
 
     def submit(self, audio: np.ndarray, *, slots: Optional[Sequence[int]] = None,
                n_frames: Optional[Sequence[int]] = None, max_frames: Optional[int] = None,
                frame_len: int = 512, hop: int = 512, pcm_format: int = capi.PCM_F32,
-               max_events: int = 0, src_rate: int = 16000) -> "PendingStep":
+               max_events: int = 0, src_rate: int = 16000,
+               src_rates: Optional[Sequence[int]] = None) -> "PendingStep":
         """Enqueue one step (H2D, kernels, D2H) and return at once; `.collect()` waits for it.
         Up to four steps may be in flight: later copies overlap earlier steps' kernels and result copies.
         `audio` must stay untouched until collect (pinned arrays are DMA'd in place)."""
         audio = np.asarray(audio)
-        if src_rate not in (0, 16000):
+        if src_rates is not None:
+            # per-stream source rates in ONE step: stream i holds max_frames chunks of 512*rate_i/16000 samples
+            if max_frames is None:
+                raise EngineError(capi.E_INVALID, "max_frames is required with src_rates")
+            frame_len = hop = 512
+        elif src_rate not in (0, 16000):
             # source-rate input: every chunk of 512*src_rate/16000 samples becomes one model frame
             frame_len = hop = src_rate * 512 // 16000
         if max_frames is None:
             max_frames = 0 if audio.shape[1] < frame_len else (audio.shape[1] - frame_len) // hop + 1
-        a, keep = self._args(audio, slots, n_frames, max_frames, frame_len, hop, pcm_format, src_rate)
+        a, keep = self._args(audio, slots, n_frames, max_frames, frame_len, hop, pcm_format, src_rate, src_rates)
         n = a.n_streams
         probs = np.empty((n, max_frames), np.float32)
         flags = np.empty((n, max_frames), np.uint8)

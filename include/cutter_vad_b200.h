@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define CVAD_ABI_VERSION 1
+#define CVAD_ABI_VERSION 2
 
 /* error codes */
 #define CVAD_OK 0
@@ -108,6 +108,10 @@ typedef struct cvad_step_args {
     cvad_event *events_out;   /* [max_events] (may be NULL) */
     int32_t max_events;
     int32_t *n_events_out;    /* total events produced, even if > max_events (may be NULL) */
+    const int32_t *src_rates; /* ABI 2. [n_streams] per-stream source rate (8000 / 16000 / 24000 / 48000), or NULL.
+                                 When given, src_rate, frame_len and hop are ignored: stream i delivers max_frames
+                                 chunks of 512*src_rates[i]/16000 samples back to back from audio[i*stream_stride],
+                                 each resampled (or, at 16000, passed through) to one 512-sample model frame. */
 } cvad_step_args;
 
 /* Library / device probes. */

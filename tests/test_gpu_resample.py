@@ -129,3 +129,47 @@ def test_batched_manager_with_24k_streams(ref_v5):
         got = np.concatenate(probs[sid])
         assert len(got) == T and np.abs(got - want[k]).max() <= TOL
     mgr.close()
+
+
+def test_mixed_source_rates_in_one_step_equal_per_rate_steps(engine_factory):
+    """BASELINE.json configs[3]: streams at different source rates advance in ONE cvad_step (src_rates[]).
+    Streams are independent, so the result must be bit-identical to stepping each rate group on its own."""
+    rates = np.array([48000, 24000, 16000, 8000, 24000, 48000, 48000, 16000, 8000, 24000] * 7, np.int32)[:67]
+    n, T = rates.size, 5
+    rng = np.random.default_rng(41)
+    n_in = rates * 512 // 16000
+    stride = int(T * n_in.max())
+    audio = np.zeros((n, stride), np.float32)
+    t = np.arange(stride)
+    for i in range(n):
+        L = T * n_in[i]
+        audio[i, :L] = (0.2 * np.sin(2 * np.pi * (180 + 7 * i) * t[:L] / rates[i]) * (1 + 0.5 * np.sin(2 * np.pi * 3 * t[:L] / rates[i]))
+                        + 0.02 * rng.standard_normal(L)).astype(np.float32)
+    nfr = np.full(n, T, np.int32)
+    nfr[3] = 2
+    nfr[10] = 0
+    eng = engine_factory(128)
+    eng.reset()
+    eng.configure(enable_denoising=True)
+    mixed = eng.step(audio, src_rates=rates, max_frames=T, n_frames=nfr)
+    assert mixed.status.sum() == 0
+    # reference: one engine step per rate group, same slots
+    eng.reset()
+    want = np.zeros((n, T), np.float32)
+    for r in (8000, 16000, 24000, 48000):
+        idx = np.nonzero(rates == r)[0]
+        L = T * (r * 512 // 16000)
+        res = eng.step(np.ascontiguousarray(audio[idx, :L]), slots=idx, src_rate=r, n_frames=nfr[idx], max_frames=T)
+        want[idx] = res.probs
+    assert np.array_equal(mixed.probs, want)
+    assert mixed.probs[10].sum() == 0 and np.all(mixed.probs[3, 2:] == 0)
+    # a second mixed step carries the per-slot state on
+    again = eng.step(audio, src_rates=rates, max_frames=T, n_frames=nfr)
+    assert again.probs.shape == (n, T)
+
+
+def test_mixed_source_rates_reject_unknown_rate(engine_factory):
+    from real_time_vad.engine.stream_engine import EngineError
+    eng = engine_factory(8)
+    with pytest.raises(EngineError):
+        eng.step(np.zeros((2, 1536), np.float32), src_rates=[48000, 44100], max_frames=1)
