@@ -107,6 +107,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Gate nonlinearities of the LSTM cell on the SFU (MUFU.EX2 + MUFU.RCP): absolute error <= ~2e-7 on values in
+// (-1, 1), the size of one FP32 rounding of the accurate expf/tanhf forms they replace; measured effect on the
+// speech probability is below 1e-6 (tests/test_gpu_v5_parity.py runs both arithmetic paths against the oracle)
+__device__ __forceinline__ float sfu_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float sfu_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+// MUFU.SQRT: one instruction, <= 1 ulp (the IEEE sqrtf sequence is ~10 instructions per magnitude bin)
+__device__ __forceinline__ float sfu_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // x -> three BF16 parts (bit patterns)
 __device__ __forceinline__ void split3(float x, unsigned short &p0, unsigned short &p1, unsigned short &p2) {
     const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
@@ -456,12 +469,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                         const float re = mr[e] + cr[e];
                         float im = mi[e] + ci[e];
                         if (b == 0) {
-                            const float m128 = sqrtf(__fmul_rn(im, im));
+                            const float m128 = fabsf(im);      // sqrt(x*x + 0*0)
                             nyq[c0 + e] = m128;
                             if (dbg) p.dbg[(128 * 3 + ((c0 + e) >> 5)) * 32 + ((c0 + e) & 31)] = m128;
                             im = 0.f;
                         }
-                        mag[e] = sqrtf(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+                        mag[e] = sfu_sqrt(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
                         if (dbg) p.dbg[(b * 3 + ((c0 + e) >> 5)) * 32 + ((c0 + e) & 31)] = mag[e];
                     }
 #pragma unroll
@@ -812,12 +825,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
                 float dv[8], hn[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float ig = sigmoid_f(gate[0][e] + b_i);
-                    const float fg = sigmoid_f(gate[1][e] + b_f);
-                    const float gg = tanhf(gate[2][e] + b_g);
-                    const float og = sigmoid_f(gate[3][e] + b_o);
+                    const float ig = sfu_sigmoid(gate[0][e] + b_i);
+                    const float fg = sfu_sigmoid(gate[1][e] + b_f);
+                    const float gg = sfu_tanh(gate[2][e] + b_g);
+                    const float og = sfu_sigmoid(gate[3][e] + b_o);
                     const float cn = __fadd_rn(__fmul_rn(fg, creg[e]), __fmul_rn(ig, gg));
-                    const float hv = og * tanhf(cn);
+                    const float hv = og * sfu_tanh(cn);
                     const bool live = j < nfr[e];
                     creg[e] = live ? cn : creg[e];
                     hreg[e] = live ? hv : hreg[e];
