@@ -47,6 +47,7 @@ struct cvad_engine {
     float *w_fe = nullptr, *b_fe = nullptr, *w_rec = nullptr, *b_rec = nullptr, *w_dec = nullptr;
     // tensor-core path (v5 only): BF16x3 tile streams + the FP32 side tables
     int math = CVAD_MATH_FP32;
+    bool fuse_single_frame = true;     // CVAD_FUSE=0 keeps the two-kernel form for one-frame steps (measurement)
     unsigned char *w_fe_tc = nullptr, *w_rec_tc = nullptr;
     float *nyq_w = nullptr, *b_rec_tc = nullptr;
     DevBuf d_feat_tc;
@@ -563,8 +564,20 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         p.feat_tc = static_cast<unsigned char *>(e->d_feat_tc.p);
         p.prof = e->d_prof;
         const int grid = std::min(a->max_frames * n_stiles, e->num_sms);
-        if (d_dbg) cvad::tc5::v5tc_frontend_kernel<true><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFeSmemTC, stream>>>(p);
-        else cvad::tc5::v5tc_frontend_kernel<false><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFeSmemTC, stream>>>(p);
+        if (a->max_frames == 1 && !d_dbg && e->fuse_single_frame) {
+            // one frame per stream: front end + LSTM step + state machine in ONE kernel (no hand-off, no second launch)
+            cvad::tc5::v5tc_frontend_kernel<false, true><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFusedSmemTC, stream>>>(p);
+            CU_TRY(e, cudaGetLastError());
+            e->launches++;
+            if (timed) {   // the whole step is the "front-end" interval, the "recurrent" interval is empty
+                CU_TRY(e, cudaEventRecord(ev[1], stream));
+                CU_TRY(e, cudaEventRecord(ev[2], stream));
+            }
+            CU_TRY(e, cudaEventRecord(e->last_done, stream));
+            return CVAD_OK;
+        }
+        if (d_dbg) cvad::tc5::v5tc_frontend_kernel<true, false><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFeSmemTC, stream>>>(p);
+        else cvad::tc5::v5tc_frontend_kernel<false, false><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFeSmemTC, stream>>>(p);
         CU_TRY(e, cudaGetLastError());
         e->launches++;
         if (timed) CU_TRY(e, cudaEventRecord(ev[1], stream));
@@ -910,10 +923,12 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
                                 (int)cvad::kV4FeSmemBytes));
     CR_TRY(cudaFuncSetAttribute(cvad::v4_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::kV4RecSmemBytes));
-    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kFeSmemTC));
-    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kFeSmemTC));
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::tc5::kFusedSmemTC));
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kRecSmemTC));
     if (model_version == CVAD_MODEL_V5) {
@@ -928,6 +943,8 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
             return bail(rc);
         const char *m = std::getenv("CVAD_MATH");
         e->math = (m && std::strcmp(m, "fp32") == 0) ? CVAD_MATH_FP32 : CVAD_MATH_TC;
+        const char *fz = std::getenv("CVAD_FUSE");
+        e->fuse_single_frame = !(fz && std::strcmp(fz, "0") == 0);
     }
     {
         V5Packed P = model_version == CVAD_MODEL_V5 ? pack_v5(weights) : pack_v4(weights);

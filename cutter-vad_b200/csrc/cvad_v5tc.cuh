@@ -40,7 +40,7 @@ constexpr int kMmaWarp = 17;
 constexpr int kThreadsTC = 576;
 constexpr uint32_t kSlotBytes = 16384;       // one 128-row x 64-K BF16 weight tile
 constexpr uint32_t kColMain = 0;             // TMEM column of the w0.x0 accumulator
-constexpr uint32_t kColCorr = 256;           // TMEM column of the five correction products
+constexpr uint32_t kColCorr = 192;           // TMEM column of the five correction products (columns 384.. hold the fused kernel's gates)
 
 // ---------------------------------------------------------------- front-end weight stream
 // Period = 69 tiles, in consumption order (each tile: rows x 64 K-elements, SW128 K-major, BF16 part p):
@@ -71,6 +71,14 @@ constexpr uint32_t kE1Part = 8192;           // E1: 64 rows x 64 K
 constexpr uint32_t kE2Part = 4096;           // E2: 32 rows x 64 K
 constexpr size_t kFeSmemTC = 1024 + kActBytes + (size_t)kFeRing * kSlotBytes + 96 * 4 + (2 * kFeRing + 2) * 8 + 16 +
                              2 * kTile * 4 + 64;
+// fused single-frame kernel (max_frames == 1): the front end plus the LSTM step of the same 32 streams in one CTA.
+// ACT | H operand (24 KB) | ring (6 slots) | nyq | decoder partials | barriers | meta.  Weight stream per tile:
+// 24 W_hh tiles (issued while the loader runs), the 69 front-end tiles, 24 W_ih tiles.
+constexpr int kFusedRing = 6;
+constexpr int kFusedSlotsPerTile = 24 + kFeSlotsPerTile + 24;
+constexpr uint32_t kColGate = 384;           // TMEM columns 384 + 32 g: gate g (i,f,g,o), one accumulator per gate
+constexpr size_t kFusedSmemTC = 1024 + kActBytes + 24576 + (size_t)kFusedRing * kSlotBytes + 96 * 4 + 128 * 4 +
+                                (2 * kFusedRing + 3) * 8 + 16 + 2 * kTile * 4 + kTile * 16 + 64;
 // feature hand-off (front end -> recurrent), per (frame, stream tile): the x half of the recurrent B operand,
 // byte for byte: [kb 0..1][row = part*32 + item (96 rows)][128 B], SW128
 constexpr uint32_t kFeatTileBytes = 2 * 12288;
@@ -208,6 +216,26 @@ __device__ __forceinline__ long long gtime_ns() {
 #define CVAD_PROF_NS(k) do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(k)] = gtime_ns(); } while (0)
 #define CVAD_PROF(k) do { if (p.prof && blockIdx.x == 0 && first_tile) p.prof[(k)] = clock64(); } while (0)
 
+// LSTM gate products of one weight tile (part wp) in the fused kernel: all six products of a MAC go to ONE
+// accumulator (TMEM has no room for column groups next to the front end's); b0 = activation part 0, parts 4096 B apart
+__device__ __forceinline__ void issue_gate(int wp, uint32_t a_addr, uint32_t b0, uint32_t d, uint32_t idesc, bool first) {
+    const uint64_t ad = tc::smem_desc_sw128(a_addr);
+    const uint64_t bd0 = tc::smem_desc_sw128(b0), bd1 = tc::smem_desc_sw128(b0 + 4096u), bd2 = tc::smem_desc_sw128(b0 + 8192u);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        if (wp == 0) {
+            tc::mma_bf16(d, ad + ks * 2, bd2 + ks * 2, idesc, (first && ks == 0) ? 0u : 1u);
+            tc::mma_bf16(d, ad + ks * 2, bd1 + ks * 2, idesc, 1u);
+            tc::mma_bf16(d, ad + ks * 2, bd0 + ks * 2, idesc, 1u);
+        } else if (wp == 1) {
+            tc::mma_bf16(d, ad + ks * 2, bd1 + ks * 2, idesc, 1u);
+            tc::mma_bf16(d, ad + ks * 2, bd0 + ks * 2, idesc, 1u);
+        } else {
+            tc::mma_bf16(d, ad + ks * 2, bd0 + ks * 2, idesc, 1u);
+        }
+    }
+}
+
 struct Ring {
     uint32_t buf;        // shared address of slot 0
     uint64_t *full;      // [n]
@@ -217,26 +245,34 @@ struct Ring {
 // =====================================================================================
 // Front end: frame loader -> STFT -> magnitude -> encoder.0..3 -> feat (BF16x3 operand for the recurrent kernel)
 // =====================================================================================
-template <bool DBG>
+// FUSED (max_frames == 1): the same CTA also runs the LSTM step, decoder and state machine of its 32 streams
+// (the W_hh.h products are issued while the frame loader runs, the W_ih.x products after encoder.3).
+template <bool DBG, bool FUSED>
 __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5Step p) {
+    constexpr int RING = FUSED ? kFusedRing : kFeRing;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     unsigned char *act = base;
-    unsigned char *ring_buf = act + kActBytes;
-    float *nyq = reinterpret_cast<float *>(ring_buf + kFeRing * kSlotBytes);   // [96] |X[128]| per (t, item)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(nyq + 96);
-    uint64_t *full = bars, *empty = bars + kFeRing, *act_ready = bars + 2 * kFeRing, *acc_ready = act_ready + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 1);
+    unsigned char *hbuf = act + kActBytes;                                   // FUSED: [2 K blocks][96 rows][128 B]
+    unsigned char *ring_buf = hbuf + (FUSED ? 24576 : 0);
+    float *nyq = reinterpret_cast<float *>(ring_buf + RING * kSlotBytes);    // [96] |X[128]| per (t, item)
+    float *dpart = nyq + 96;                                                 // FUSED: [4][32] decoder partial sums
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dpart + (FUSED ? 128 : 0));
+    uint64_t *full = bars, *empty = bars + RING, *act_ready = bars + 2 * RING, *acc_ready = act_ready + 1,
+             *h_ready = acc_ready + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_ready + 1);
     int *s_slot = reinterpret_cast<int *>(tmem_slot + 4);
     int *s_valid = s_slot + kTile;
+    double *s_thr = reinterpret_cast<double *>(s_valid + kTile);             // FUSED: start_p[32], end_p[32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     CVAD_PROF_NS(120);
 
     if (tid == 0) {
-        for (int i = 0; i < kFeRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(act_ready, 1);
         mbar_init(acc_ready, 1);
+        mbar_init(h_ready, 1);
         mbar_fence_init();
     }
     if (warp == kProducerWarp) tc::tmem_alloc(tmem_slot, 512);
@@ -250,7 +286,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int n_tiles = p.max_frames * p.n_stiles;
-    const uint32_t act_s = smem_u32(act), ring_s = smem_u32(ring_buf);
+    const uint32_t act_s = smem_u32(act), ring_s = smem_u32(ring_buf), h_s = smem_u32(hbuf);
 
     if (warp == kProducerWarp) {
         // ------------------------------------------------------------ weight producer
@@ -259,20 +295,30 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
             if (!tile_live(p, frame, st, lane, nullptr, nullptr)) continue;
             if (lane == 0) {
-                for (int s = 0; s < kFeSlotsPerTile; ++s, ++g) {
-                    const uint32_t slot = g % kFeRing;
-                    mbar_wait(&empty[slot], ((g / kFeRing) & 1u) ^ 1u);
+                for (int s = 0; s < (FUSED ? kFusedSlotsPerTile : kFeSlotsPerTile); ++s, ++g) {
+                    const uint32_t slot = g % RING;
+                    mbar_wait(&empty[slot], ((g / RING) & 1u) ^ 1u);
                     uint32_t off, bytes;
-                    fe_slot(s, off, bytes);
+                    const unsigned char *src;
+                    if (FUSED && (s < 24 || s >= 24 + kFeSlotsPerTile)) {
+                        // LSTM tiles of the recurrent stream (gate, K block, part): W_hh = K blocks 2,3 first, W_ih = 0,1 last
+                        const int r = s < 24 ? s : s - 24 - kFeSlotsPerTile;
+                        const int gate = r / 6, kb = (r / 3) % 2 + (s < 24 ? 2 : 0), part = r % 3;
+                        src = p.w_rec_tc + (size_t)((gate * 4 + kb) * 3 + part) * kSlotBytes;
+                        bytes = kSlotBytes;
+                    } else {
+                        fe_slot(FUSED ? s - 24 : s, off, bytes);
+                        src = p.w_fe_tc + off;
+                    }
                     mbar_arrive_expect_tx(&full[slot], bytes);
-                    bulk_g2s(ring_buf + slot * kSlotBytes, p.w_fe_tc + off, bytes, &full[slot]);
+                    bulk_g2s(ring_buf + slot * kSlotBytes, src, bytes, &full[slot]);
                 }
             }
             __syncwarp();
         }
     } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------ MMA issuer
-        uint32_t g = 0, act_phase = 0;
+        uint32_t g = 0, act_phase = 0, h_phase = 0;
         const uint32_t i128_96 = tc::idesc_bf16_f32(128, 96), i128_64 = tc::idesc_bf16_f32(128, 64),
                        i128_32 = tc::idesc_bf16_f32(128, 32), i64_64 = tc::idesc_bf16_f32(64, 64),
                        i64_32 = tc::idesc_bf16_f32(64, 32);
@@ -282,8 +328,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             const bool first_tile = tile == (int)blockIdx.x && lane == 0;
 #define CVAD_TC_SLOT(BODY)                                                   \
     {                                                                        \
-        const uint32_t slot = g % kFeRing;                                   \
-        mbar_wait(&full[slot], (g / kFeRing) & 1u);                          \
+        const uint32_t slot = g % RING;                                      \
+        mbar_wait(&full[slot], (g / RING) & 1u);                             \
         tc::fence_after_sync();                                              \
         const uint32_t a_addr = ring_s + slot * kSlotBytes;                  \
         if (tc::elect_one()) {                                               \
@@ -293,6 +339,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
         __syncwarp();                                                        \
         ++g;                                                                 \
     }
+            if (FUSED) {
+                // ---- W_hh . h of the LSTM gates: needs only the resident state, runs under the frame loader
+                mbar_wait(h_ready, h_phase); h_phase ^= 1u;
+                tc::fence_after_sync();
+                for (int gate = 0; gate < 4; ++gate)
+                    for (int kb = 0; kb < 2; ++kb)
+                        for (int wp = 0; wp < 3; ++wp)
+                            CVAD_TC_SLOT(issue_gate(wp, a_addr, h_s + kb * kXhKb, kColGate + 32 * gate, i128_32,
+                                                    kb == 0 && wp == 0))
+                CVAD_PROF(42);
+            }
             // ---- STFT: D[blk][bin][(t, item)] = sum_k W[bin][k] x[128 t + k]; K block kb uses segment rows t + kb/2
             mbar_wait(act_ready, act_phase); act_phase ^= 1u;
             CVAD_PROF(32);
@@ -362,6 +419,19 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             if (tc::elect_one()) tc::mma_commit(acc_ready);
             CVAD_PROF(41);
             __syncwarp();
+            if (FUSED) {
+                // ---- W_ih . x: x = encoder.3 output, written into ACT as a 96-row operand by the epilogue
+                mbar_wait(act_ready, act_phase); act_phase ^= 1u;
+                tc::fence_after_sync();
+                CVAD_PROF(43);
+                for (int gate = 0; gate < 4; ++gate)
+                    for (int kb = 0; kb < 2; ++kb)
+                        for (int wp = 0; wp < 3; ++wp)
+                            CVAD_TC_SLOT(issue_gate(wp, a_addr, act_s + kb * kXhKb, kColGate + 32 * gate, i128_32, false))
+                if (tc::elect_one()) tc::mma_commit(acc_ready);
+                CVAD_PROF(44);
+                __syncwarp();
+            }
 #undef CVAD_TC_SLOT
         }
     } else {
@@ -374,11 +444,54 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
             int my_slot, my_valid;
             if (!tile_live(p, frame, st, lane, &my_slot, &my_valid)) continue;
-            if (warp == 0) { s_slot[lane] = my_slot; s_valid[lane] = my_valid; }
+            if (warp == 0) {
+                s_slot[lane] = my_slot;
+                s_valid[lane] = my_valid;
+                if (FUSED && my_slot >= 0) { s_thr[lane] = p.start_p[my_slot]; s_thr[kTile + lane] = p.end_p[my_slot]; }
+            }
             epi_bar();
             const bool dbg = DBG && tile == 0;
             const bool first_tile = tile == (int)blockIdx.x && tid == 0;
             CVAD_PROF(0);
+            // FUSED: resident state of the tile's streams: h -> BF16x3 rows of the H operand, c -> registers
+            // (global reads coalesced over streams, transposed through the still-unused ACT region)
+            float creg[8];
+            const int u_own = 32 * q + lane, i_own = 8 * cg;   // this thread's hidden unit (TMEM lane) and 8 streams
+            if (FUSED) {
+                float *sbuf = reinterpret_cast<float *>(act);   // [128][33]
+                float hreg[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int idx = e * kEpiThreads + tid;
+                    const int slot = s_valid[idx & 31] ? s_slot[idx & 31] : -1;
+                    hreg[e] = slot >= 0 ? __ldg(p.h_state + (size_t)(idx >> 5) * p.max_streams + slot) : 0.f;
+                    creg[e] = slot >= 0 ? __ldg(p.c_state + (size_t)(idx >> 5) * p.max_streams + slot) : 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int idx = e * kEpiThreads + tid;
+                    sbuf[(idx >> 5) * 33 + (idx & 31)] = hreg[e];
+                }
+                epi_bar();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) hreg[e] = sbuf[u_own * 33 + i_own + e];
+#pragma unroll
+                for (int e = 0; e < 8; e += 2)
+                    store_parts2(hbuf, 32 * 128, (uint32_t)(i_own + e), (uint32_t)u_own, 96u, hreg[e], hreg[e + 1]);
+                epi_bar();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int idx = e * kEpiThreads + tid;
+                    sbuf[(idx >> 5) * 33 + (idx & 31)] = creg[e];
+                }
+                epi_bar();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) creg[e] = sbuf[u_own * 33 + i_own + e];
+                tc::fence_async_smem();
+                epi_bar();                                     // also: sbuf reads done before the loader rewrites ACT
+                if (tid == 0) mbar_arrive(h_ready);
+                CVAD_PROF(12);
+            }
 
             // ---- frame loader (audio.py:164-190 split, :104-121 gate, silero_model.py:449-474 pad/truncate):
             //      8 samples per work unit -> 3 x 16-byte BF16 chunks of the AUD operand, row = segment*32 + item.
@@ -595,7 +708,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 tmem_ld8(lane_addr + kColMain + c0, m);
                 tmem_ld8(lane_addr + kColCorr + c0, cr);
                 tmem_wait_ld();
-                unsigned char *fout = p.feat_tc + (size_t)tile * kFeatTileBytes;
+                unsigned char *fout = FUSED ? act : p.feat_tc + (size_t)tile * kFeatTileBytes;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     v[e] = fmaxf(m[e] + cr[e] + bias, 0.f);
@@ -604,9 +717,137 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) store_parts2(fout, 32 * 128, (uint32_t)(c0 + e), (uint32_t)o, 96u, v[e], v[e + 1]);
             }
+            if (FUSED) tc::fence_async_smem();
             tc::fence_before_sync();   // TMEM reads of this tile are ordered before the next tile's act_ready arrive
             epi_bar();
             CVAD_PROF(11);
+            if (FUSED) {
+                if (tid == 0) mbar_arrive(act_ready);          // x operand is in ACT: the W_ih products may start
+                // ---- LSTM cell, decoder, state machine (same arithmetic as v5tc_recurrent_kernel, one frame)
+                const int u = u_own, i0 = i_own;
+                const float b_i = __ldg(p.b_rec_tc + u), b_f = __ldg(p.b_rec_tc + 128 + u),
+                            b_g = __ldg(p.b_rec_tc + 256 + u), b_o = __ldg(p.b_rec_tc + 384 + u);
+                const float wd = __ldg(p.w_dec + u), dec_b = __ldg(p.w_dec + 128);
+                // NaN/Inf streams were flagged by this CTA's own loader (atomicOr at L2): the reference raises
+                // before any frame runs, so such a stream keeps its state and reports nothing
+                if (warp == 0) {
+                    const int i = st * kTile + lane;
+                    if (s_valid[lane] && p.status && __ldcg(p.status + i) != 0u) s_valid[lane] = 0;
+                }
+                epi_bar();
+                mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
+                tc::fence_after_sync();
+                CVAD_PROF(13);
+                float gate[4][8];
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) tmem_ld8(lane_addr + kColGate + 32 * gi + i0, gate[gi]);
+                tmem_wait_ld();
+                float dv[8], hn[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float ig = sfu_sigmoid(gate[0][e] + b_i);
+                    const float fg = sfu_sigmoid(gate[1][e] + b_f);
+                    const float gg = sfu_tanh(gate[2][e] + b_g);
+                    const float og = sfu_sigmoid(gate[3][e] + b_o);
+                    const float cn = __fadd_rn(__fmul_rn(fg, creg[e]), __fmul_rn(ig, gg));
+                    hn[e] = og * sfu_tanh(cn);
+                    creg[e] = cn;
+                    dv[e] = wd * fmaxf(hn[e], 0.f);
+                }
+#pragma unroll
+                for (int w = 4; w >= 1; w >>= 1) {
+                    const bool upper = (lane & w) != 0;
+#pragma unroll
+                    for (int e = 0; e < w; ++e) {
+                        const float send = upper ? dv[e] : dv[e + w];
+                        const float keep = upper ? dv[e + w] : dv[e];
+                        dv[e] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+                    }
+                }
+                dv[0] += __shfl_xor_sync(0xffffffffu, dv[0], 8);
+                dv[0] += __shfl_xor_sync(0xffffffffu, dv[0], 16);
+                if (lane < 8) dpart[q * 32 + i0 + lane] = dv[0];
+                // new state back to HBM, coalesced over streams through ACT (dead: every MMA of the tile is complete)
+                float *sbuf = reinterpret_cast<float *>(act);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sbuf[u * 33 + i0 + e] = hn[e];
+                tc::fence_before_sync();
+                epi_bar();
+                if (p.commit) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int idx = e * kEpiThreads + tid;
+                        const int s = idx & 31;
+                        if (s_valid[s]) p.h_state[(size_t)(idx >> 5) * p.max_streams + s_slot[s]] = sbuf[(idx >> 5) * 33 + s];
+                    }
+                }
+                epi_bar();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sbuf[u * 33 + i0 + e] = creg[e];
+                epi_bar();
+                if (p.commit) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int idx = e * kEpiThreads + tid;
+                        const int s = idx & 31;
+                        if (s_valid[s]) p.c_state[(size_t)(idx >> 5) * p.max_streams + s_slot[s]] = sbuf[(idx >> 5) * 33 + s];
+                    }
+                }
+                // sigmoid(w . relu(h') + b), then the start/end state machine (silero_model.py:790-923)
+                if (warp == 0 && s_valid[lane]) {
+                    const int slot = s_slot[lane];
+                    int sm_active = p.sm_active[slot], sm_sc = p.sm_scount[slot], sm_ec = p.sm_ecount[slot];
+                    const int sm_ns = p.n_start[slot], sm_ne = p.n_end[slot];
+                    const long long sm_f0 = p.frames_done[slot];
+                    const float a = (dpart[lane] + dpart[32 + lane]) + (dpart[64 + lane] + dpart[96 + lane]);
+                    const float prob = sigmoid_f(a + dec_b);
+                    const double pd = (double)prob;
+                    unsigned int fl = 0u;
+                    if (!sm_active) {
+                        if (pd >= s_thr[lane]) {
+                            ++sm_sc;
+                            if (sm_sc >= sm_ns && sm_ns <= 20) {  // deque(maxlen=20), silero_model.py:620-623
+                                sm_active = 1; sm_sc = 0; sm_ec = 0; fl |= 1u;
+                            }
+                        } else {
+                            sm_sc = 0;
+                        }
+                    } else {
+                        fl |= 4u;
+                        if (pd < s_thr[kTile + lane]) {
+                            ++sm_ec;
+                            if (sm_ec >= sm_ne && sm_ne <= 100) {  // deque(maxlen=100), :625-628
+                                sm_active = 0; sm_ec = 0; fl |= 2u;
+                            }
+                        } else {
+                            sm_ec = 0;
+                        }
+                    }
+                    const int i = st * kTile + lane;
+                    if (p.probs) p.probs[(size_t)i * p.max_frames] = prob;
+                    if (p.flags) p.flags[(size_t)i * p.max_frames] = (unsigned char)fl;
+                    if ((fl & 3u) && p.n_events) {
+                        EventRec *ev = reinterpret_cast<EventRec *>(p.events);
+                        for (unsigned int kind = 1u; kind <= 2u; kind <<= 1) {
+                            if (fl & kind) {
+                                const int at = atomicAdd(p.n_events, 1);
+                                if (ev && at < p.max_events) {
+                                    ev[at].stream = i; ev[at].slot = slot; ev[at].frame = 0;
+                                    ev[at].kind = (int)kind; ev[at].stream_frame = sm_f0;
+                                }
+                            }
+                        }
+                    }
+                    if (p.commit) {
+                        p.sm_active[slot] = sm_active;
+                        p.sm_scount[slot] = sm_sc;
+                        p.sm_ecount[slot] = sm_ec;
+                        p.frames_done[slot] = sm_f0 + 1;
+                    }
+                }
+                epi_bar();   // ACT, dpart and s_valid are rewritten by the next tile
+                CVAD_PROF(14);
+            }
         }
     }
     tc::fence_before_sync();

@@ -28,6 +28,8 @@ print("front end, epilogue thread 0 (cycles since tile start, delta):")
 for i, nm in enumerate(names):
     print(f"  {nm:12s} {fe[i]:8d} {fe[i] - (fe[i - 1] if i else 0):8d}")
 print("front end, MMA warp: (act_ready seen, layer issued) x 5:", mm.tolist())
+if out[12]:
+    print("fused: state loaded", out[12] - out[0], "| hh issued", out[42] - out[0], "| x ready", out[43] - out[0], "ih issued", out[44] - out[0], "| gates ready", out[13] - out[0], "cell done", out[14] - out[0])
 r0 = out[64]
 print("recurrent epilogue: start 0, state loaded", out[65] - r0)
 for j in range(min(T, 8)):
