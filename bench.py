@@ -425,15 +425,20 @@ def run_ours(args):
     fe_tflops = frames_per_step * flop_fe / fe_avg_s / 1e12 if fe_avg_s > 0 else 0.0
     step_tflops = frames_per_step * flop_frame / (dev_ms / args.steps * 1e-3) / 1e12
 
+    fused = math == "tc" and F == 1 and os.environ.get("CVAD_FUSE", "1") != "0"
+    if fused:
+        # one kernel does the whole step (front end + LSTM step + state machine): its FLOPs are the frame's
+        flop_fe = flop_frame
+        fe_tflops = frames_per_step * flop_fe / fe_avg_s / 1e12 if fe_avg_s > 0 else 0.0
     if rank == 0:
         tc = math == "tc"
-        fe_kernel = ("v5tc_frontend_kernel" if tc else f"{args.model}_frontend_kernel") + \
-            ("+resample_kernel" if args.src_rate != 16000 else "")
+        fe_kernel = (("v5tc_frontend_kernel<FUSED>" if fused else "v5tc_frontend_kernel") if tc
+                     else f"{args.model}_frontend_kernel") + ("+resample_kernel" if args.src_rate != 16000 else "")
         traffic = (ncu_traffic_bytes("v5tc_frontend_kernel" if tc else "v5_frontend_kernel")
                    if (n == 4096 and F == 1 and args.model == "v5" and args.src_rate == 16000) else None)
         peak_bf16 = float(peaks.get("bf16_tflops", 1645.0))
         rec_tflops = frames_per_step * flop_rec / rec_avg_s / 1e12 if rec_avg_s else 0.0
-        fe_weight_bytes = 933_888 if tc else 156032 * 4
+        fe_weight_bytes = (933_888 + (786_432 if fused else 0)) if tc else 156032 * 4
         roofline = {
             # tc: every algorithmic MAC is executed as 6 BF16 tensor-core products (3-way operand split), so the
             # executed rate is 6x `achieved`; the path is bound by shared-memory operand bandwidth, not by the
@@ -442,16 +447,19 @@ def run_ours(args):
             "achieved": fe_tflops, "peak": peak_bf16 if tc else peak_fp32, "unit": "TFLOP/s",
             "frac": fe_tflops / (peak_bf16 if tc else peak_fp32),
             "traffic": (traffic or {}).get("bytes"), "traffic_source": (traffic or {}).get("source"),
-            "algorithmic_bytes_per_launch": frames_per_step * 2048 + fe_weight_bytes + frames_per_step * (768 if tc else 512),
+            "algorithmic_bytes_per_launch": frames_per_step * 2048 + fe_weight_bytes +
+            frames_per_step * ((2 * 1024 + 5) if fused else 768 if tc else 512),
             "peak_source": (f"{peaks_src} MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)" if tc else
                             f"148 SMs x 128 FP32 lanes x 2 x sm_max_mhz {sm_max:.0f} ({peaks_src} "
                             "MEASURED_PEAKS.json clock); the path is FP32-FFMA bound, not HBM or tensor bound"),
             "algorithmic_flop_per_frame": flop_fe, "frames_per_launch": frames_per_step,
             "avg_launch_ms": fe_avg_s * 1e3,
             "kernel_timing": "second pass over the same K steps with a CUDA event between the two kernels",
-            "recurrent_kernel": {"kernel": "v5tc_recurrent_kernel" if tc else f"{args.model}_recurrent_kernel",
-                                 "avg_launch_ms": rec_avg_s * 1e3, "achieved": rec_tflops,
-                                 "algorithmic_flop_per_frame": flop_rec},
+            "recurrent_kernel": ({"kernel": "(fused into the kernel above for one-frame steps)", "avg_launch_ms": 0.0,
+                                  "achieved": 0.0, "algorithmic_flop_per_frame": 0} if fused else
+                                 {"kernel": "v5tc_recurrent_kernel" if tc else f"{args.model}_recurrent_kernel",
+                                  "avg_launch_ms": rec_avg_s * 1e3, "achieved": rec_tflops,
+                                  "algorithmic_flop_per_frame": flop_rec}),
             "whole_step": {"achieved": step_tflops, "frac": step_tflops / (peak_bf16 if tc else peak_fp32),
                            "algorithmic_flop_per_frame": flop_frame},
             "vs_fp32_ffma_peak": {"peak": peak_fp32, "kernel_frac": fe_tflops / peak_fp32,

@@ -79,10 +79,15 @@ class _Stream:
 class BatchedVADManager:
     def __init__(self, max_streams: int = 4096, model_version: SileroModelVersion = SileroModelVersion.V5,
                  device: Optional[int] = None, frame_len: int = 512, hop: Optional[int] = None,
-                 pcm_format: int = capi.PCM_F32, source_rate: int = 16000) -> None:
+                 pcm_format: int = capi.PCM_F32, source_rate: Optional[int] = 16000) -> None:
         """`source_rate` 8000 / 24000 / 48000: streams deliver audio at that rate and every chunk of
         512*rate/16000 samples is resampled to one 16 kHz model frame on the GPU (frame_len and hop
-        are then fixed to that chunk size)."""
+        are then fixed to that chunk size).  `source_rate=None`: every stream has its own rate
+        (`VADConfig.sample_rate` at open_stream, any of 8000 / 16000 / 24000 / 48000) and all of them
+        advance in ONE engine step (cvad_step_args.src_rates), the way a websocket server meets them."""
+        self.mixed = source_rate is None
+        if self.mixed:
+            source_rate, frame_len, hop = 48000, 1536, 1536        # arena sizing; per-stream values in _n_in
         if source_rate not in (8000, 16000, 24000, 48000):
             raise ConfigurationError("source_rate", str(source_rate))
         self.source_rate = int(source_rate)
@@ -114,6 +119,8 @@ class BatchedVADManager:
         self._open = np.zeros(max_streams, bool)
         self._has_cb = np.zeros(max_streams, bool)
         self._active = np.zeros(max_streams, bool)
+        self._n_in = np.full(max_streams, self.frame_len, np.int64)   # source samples per model frame, per stream
+        self._rate = np.full(max_streams, self.source_rate, np.int32)
 
     # ------------------------------------------------------------------ stream lifecycle
     @property
@@ -124,7 +131,10 @@ class BatchedVADManager:
                     on_voice_end: Optional[Callable[[bytes], None]] = None,
                     on_voice_continue: Optional[Callable[[bytes], None]] = None) -> int:
         cfg = config if config is not None else VADConfig()
-        if int(cfg.sample_rate) != self.source_rate:
+        if self.mixed:
+            if int(cfg.sample_rate) not in (8000, 16000, 24000, 48000):
+                raise ConfigurationError("sample_rate", str(cfg.sample_rate), "8000, 16000, 24000 or 48000")
+        elif int(cfg.sample_rate) != self.source_rate:
             raise ConfigurationError("sample_rate", str(cfg.sample_rate),
                                      f"this manager takes {self.source_rate} Hz streams")
         with self._lock:
@@ -138,6 +148,9 @@ class BatchedVADManager:
                 on_start=on_voice_start, on_end=on_voice_end, on_continue=on_voice_continue)
             self._fill[sid] = 0
             self._active[sid] = False
+            if self.mixed:
+                self._rate[sid] = int(cfg.sample_rate)
+                self._n_in[sid] = int(cfg.sample_rate) * 512 // 16000
             self._open[sid] = True
             self._has_cb[sid] = any(cb is not None for cb in (on_voice_start, on_voice_end, on_voice_continue))
             return sid
@@ -248,11 +261,12 @@ class BatchedVADManager:
             f = f / np.float32(32767.0)
         elif self.pcm_format == capi.PCM_S16_32768:
             f = f / np.float32(32768.0)
-        if self.source_rate != 16000:
+        rate = int(st.config.sample_rate) if self.mixed else self.source_rate
+        if rate != 16000:
             # callback payloads are 16 kHz audio: same operator as the GPU resampler, host side,
             # only for the frames that actually reach a payload
             from ..utils.audio import AudioUtils
-            f = AudioUtils.resample_audio(f, self.source_rate, 16000)
+            f = AudioUtils.resample_audio(f, rate, 16000)
         if st.config.enable_denoising:
             f = np.where(np.abs(f) > 0.01, f, 0.0).astype(np.float32)
         return f
@@ -261,6 +275,8 @@ class BatchedVADManager:
         """Run every complete buffered frame of every open stream in one GPU step."""
         with self._lock:
             fill = self._fill
+            if self.mixed:
+                return self._step_mixed()
             counts_all = np.where(self._open & (fill >= self.frame_len), (fill - self.frame_len) // self.hop + 1, 0)
             ids = np.flatnonzero(counts_all)
             if ids.size == 0:
@@ -293,6 +309,39 @@ class BatchedVADManager:
             self._fill[ids] = rem
             return StepOutput(events, ids, counts, r.probs, r.flags)
 
+    def _step_mixed(self) -> StepOutput:
+        """step() for per-stream source rates: stream i consumes whole chunks of n_in[i] samples (hop = chunk)."""
+        fill, n_in = self._fill, self._n_in
+        counts_all = np.where(self._open, fill // n_in, 0)
+        ids = np.flatnonzero(counts_all)
+        if ids.size == 0:
+            z = np.zeros(0, np.int64)
+            return StepOutput([], z, z, np.zeros((0, 0), np.float32), np.zeros((0, 0), np.uint8))
+        counts = counts_all[ids]
+        tmax = int(counts.max())
+        row = tmax * int(n_in[ids].max())
+        row += (-row) % 4
+        self._ensure_cap(row)
+        block = self._buf[ids, :row]
+        r = self._engine.step(block, slots=ids.astype(np.int32), n_frames=counts.astype(np.int32), max_frames=tmax,
+                              pcm_format=self.pcm_format, src_rates=self._rate[ids])
+        if r.status.any():
+            self._fill[ids[r.status != 0]] = 0
+            raise AudioProcessingError("Audio data contains infinite or NaN values")
+        events = [StreamEvent(slot, "start" if kind == capi.FLAG_STARTED else "end", stream_frame, j)
+                  for (k, slot, j, kind, stream_frame) in r.events]
+        self._deliver(ids, counts, block, r.probs, r.flags)
+        used = counts * n_in[ids]
+        rem = fill[ids] - used
+        keep = rem > 0
+        if keep.any():
+            for u in np.unique(used[keep]):
+                sel = ids[keep & (used == u)]
+                w = int((fill[sel] - u).max())
+                self._buf[sel, :w] = self._buf[sel, int(u):int(u) + w]
+        self._fill[ids] = rem
+        return StepOutput(events, ids, counts, r.probs, r.flags)
+
     def _deliver(self, ids: np.ndarray, counts: np.ndarray, block: np.ndarray, probs: np.ndarray,
                  flags: np.ndarray) -> None:
         """Host side of the callbacks: segment assembly from the device's per-frame flags.  Streams
@@ -314,7 +363,11 @@ class BatchedVADManager:
                 frame = None
                 if st.wants_audio:
                     if st.active or float(probs[k, j]) >= start_p:
-                        frame = self._gate(st, pending[j * self.hop: j * self.hop + self.frame_len])
+                        if self.mixed:
+                            ni = int(self._n_in[sid])
+                            frame = self._gate(st, pending[j * ni:(j + 1) * ni])
+                        else:
+                            frame = self._gate(st, pending[j * self.hop: j * self.hop + self.frame_len])
                 if not st.active:
                     if float(probs[k, j]) >= start_p:
                         if frame is not None:
@@ -354,6 +407,8 @@ class BatchedVADManager:
         """Lock-step fast path: `audio[k]` holds whole frames for stream `stream_ids[k]` (no buffering,
         no callbacks).  -> engine StepResult (probs, flags, status, events)."""
         ids = list(self.open_streams) if stream_ids is None else list(stream_ids)
+        if self.mixed:
+            raise ConfigurationError("source_rate", "None", "step_block needs one source rate for all streams")
         with self._lock:
             return self._engine.step(audio, slots=ids, frame_len=self.frame_len, hop=self.hop,
                                      pcm_format=self.pcm_format, src_rate=self.source_rate)

@@ -237,3 +237,55 @@ def test_manager_push_many_lockstep_matches_single_pushes(ref_v5):
     assert a.is_voice_active(ia[0]) == bool((a.engine.get_state(ia[0])[2][0]))
     a.close()
     b.close()
+
+
+def test_manager_mixed_source_rates_one_step_equals_per_rate_managers():
+    """BatchedVADManager(source_rate=None): every stream has its own VADConfig.sample_rate and all of them advance
+    in one engine step; probabilities, events and voice-end payloads equal those of one manager per rate."""
+    from real_time_vad import BatchedVADManager, SampleRate, VADConfig
+    from scipy import signal
+    rates = {8000: SampleRate.SAMPLERATE_8, 16000: SampleRate.SAMPLERATE_16, 24000: SampleRate.SAMPLERATE_24,
+             48000: SampleRate.SAMPLERATE_48}
+    T = 40
+    base = synth_streams(8, 512 * T, seed=77)
+    plan = [48000, 16000, 24000, 8000, 48000, 24000, 16000, 8000]
+
+    def cfg(rate):
+        return VADConfig(sample_rate=rates[rate], enable_denoising=True, vad_start_probability=0.5,
+                         vad_end_probability=0.35, voice_start_frame_count=2, voice_end_frame_count=3)
+
+    audio = [signal.resample(base[k], plan[k] * 512 // 16000 * T).astype(np.float32) for k in range(8)]
+    mixed = BatchedVADManager(max_streams=16, source_rate=None)
+    ends_m = {k: [] for k in range(8)}
+    ids_m = [mixed.open_stream(cfg(plan[k]), on_voice_end=ends_m[k].append) for k in range(8)]
+    solo = {r: BatchedVADManager(max_streams=16, source_rate=r) for r in set(plan)}
+    ends_s = {k: [] for k in range(8)}
+    ids_s = [solo[plan[k]].open_stream(cfg(plan[k]), on_voice_end=ends_s[k].append) for k in range(8)]
+    probs_m = {k: [] for k in range(8)}
+    probs_s = {k: [] for k in range(8)}
+    ev_m, ev_s = [], []
+    for step in range(5):                                   # ragged arrival: 8 chunks per push
+        for k in range(8):
+            n_in = plan[k] * 512 // 16000
+            piece = audio[k][step * 8 * n_in:(step + 1) * 8 * n_in]
+            mixed.push(ids_m[k], piece)
+            solo[plan[k]].push(ids_s[k], piece)
+        out = mixed.step()
+        for sid, p in out.probabilities.items():
+            probs_m[ids_m.index(sid)].append(p)
+        ev_m += [(ids_m.index(e.stream_id), e.kind, e.frame_index) for e in out.events]
+        for r, mgr in solo.items():
+            o = mgr.step()
+            for sid, p in o.probabilities.items():
+                k = [kk for kk in range(8) if plan[kk] == r and ids_s[kk] == sid][0]
+                probs_s[k].append(p)
+            ev_s += [([kk for kk in range(8) if plan[kk] == r and ids_s[kk] == e.stream_id][0], e.kind, e.frame_index)
+                     for e in o.events]
+    for k in range(8):
+        assert np.array_equal(np.concatenate(probs_m[k]), np.concatenate(probs_s[k])), k
+        assert len(np.concatenate(probs_m[k])) == T
+        assert ends_m[k] == ends_s[k]
+    assert sorted(ev_m) == sorted(ev_s) and len(ev_m) > 0
+    mixed.close()
+    for mgr in solo.values():
+        mgr.close()
