@@ -47,6 +47,7 @@ struct cvad_engine {
     float *w_fe = nullptr, *b_fe = nullptr, *w_rec = nullptr, *b_rec = nullptr, *w_dec = nullptr;
     // tensor-core path (v5 only): BF16x3 tile streams + the FP32 side tables
     int math = CVAD_MATH_FP32;
+    bool v4_t2 = false;                // CVAD_MODEL_V4_8K: two LSTM time steps per frame
     bool fuse_single_frame = true;     // CVAD_FUSE=0 keeps the two-kernel form for one-frame steps (measurement)
     unsigned char *w_fe_tc = nullptr, *w_rec_tc = nullptr;
     float *nyq_w = nullptr, *b_rec_tc = nullptr;
@@ -468,7 +469,7 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         CU_TRY(e, cudaEventRecord(ev[0], stream));
     }
     const int n_stiles = (a->n_streams + cvad::kTile - 1) / cvad::kTile;
-    const size_t feat_bytes = (size_t)a->max_frames * n_stiles * 128 * cvad::kTile * sizeof(float);
+    const size_t feat_bytes = (size_t)a->max_frames * n_stiles * 128 * cvad::kTile * sizeof(float);   // v4: 64 x (1 or 2 time steps)
     int rc = grow(e, e->d_feat, feat_bytes);
     if (rc) return rc;
 
@@ -557,6 +558,7 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
     p.n_events = a->n_events_out;
     p.commit = commit;
     p.dbg = d_dbg;
+    p.v4_t2 = e->v4_t2 ? 1 : 0;
 
     if (e->version == CVAD_MODEL_V5 && e->math == CVAD_MATH_TC) {
         if ((rc = grow(e, e->d_feat_tc, (size_t)a->max_frames * n_stiles * cvad::tc5::kFeatTileBytes))) return rc;
@@ -876,8 +878,10 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
     *out = nullptr;
     if (!weights) return fail(nullptr, CVAD_E_INVALID, "weights is NULL");
     if (max_streams < 1) return fail(nullptr, CVAD_E_INVALID, "max_streams < 1");
+    const bool v4_8k = model_version == CVAD_MODEL_V4_8K;
+    if (v4_8k) model_version = CVAD_MODEL_V4;   // same kernels and blob layout, T = 2 at the LSTM
     if (model_version != CVAD_MODEL_V5 && model_version != CVAD_MODEL_V4)
-        return fail(nullptr, CVAD_E_INVALID, "model_version must be CVAD_MODEL_V5 or CVAD_MODEL_V4");
+        return fail(nullptr, CVAD_E_INVALID, "model_version must be CVAD_MODEL_V5, CVAD_MODEL_V4 or CVAD_MODEL_V4_8K");
     if (model_version == CVAD_MODEL_V5 && n_weight_floats != CVAD_V5_WEIGHT_FLOATS)
         return fail(nullptr, CVAD_E_WEIGHTS, "v5 weight blob must hold 309633 floats");
     if (model_version == CVAD_MODEL_V4 && n_weight_floats != CVAD_V4_WEIGHT_FLOATS)
@@ -895,6 +899,7 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
     cvad_engine *e = new cvad_engine();
     e->device = device;
     e->version = model_version;
+    e->v4_t2 = v4_8k;
     e->max_streams = max_streams;
     e->num_sms = pr.multiProcessorCount;
     auto bail = [&](int rc) {

@@ -111,7 +111,7 @@ __device__ __forceinline__ void v4_dw_relu(const float *in, const float *w, cons
 template <int CIN, int COUT, int TIN, int TOUT, int STRIDE>
 __device__ __forceinline__ void v4_pw(const float *in1, const float *w1T, const float *b1, const float *in2,
                                       const float *w2T, const float *b2, const float *res, float *out,
-                                      float *gout, int gstride, int tid) {
+                                      float *gout, int gstride, int tid, int gtstride = 0) {
     for (int wi = tid; wi < COUT * TOUT * 4; wi += kThreads) {
         const int tm = wi & 3, t = (wi >> 2) % TOUT, co = wi / (4 * TOUT);
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -134,7 +134,7 @@ __device__ __forceinline__ void v4_pw(const float *in1, const float *w1T, const 
         }
         a = relu4(a);
         if (out) st4(out + (co * TOUT + t) * kV4Tile + 4 * tm, a);
-        if (gout) st4(gout + co * gstride + 4 * tm, a);
+        if (gout) st4(gout + t * gtstride + co * gstride + 4 * tm, a);
     }
 }
 
@@ -403,7 +403,10 @@ __global__ void __launch_bounds__(kThreads, 1) v4_frontend_kernel(const V5Step p
 
         // ---- the small layers; activations now live in bufX / bufM (spectrogram is dead)
         float *r7 = bufX, *d3 = bufX + 1024, *r15 = bufX + 2048, *r19 = bufX + 4096, *d7 = bufX + 5120;
-        float *r27 = bufX + 6144, *r31 = bufX + 7168, *d11 = bufX + 7680, *r39 = bufX + 8192;
+        // 8 kHz sub-model: the third 1x1 convolution has stride 1, so T = 2 survives to the LSTM
+        const bool t2 = p.v4_t2 != 0;
+        float *r27 = bufX + 6144, *r31 = bufX + 7168, *d11 = t2 ? bufX + 8192 : bufX + 7680,
+              *r39 = t2 ? bufX + 9216 : bufX + 8192;
         {
             const float *w = ring_wait(ring);  // S0
             const float *c1T = w, *c1b = w + 256, *e3dw = w + 272, *e3dwb = w + 352, *e3pwT = w + 368,
@@ -425,7 +428,8 @@ __global__ void __launch_bounds__(kThreads, 1) v4_frontend_kernel(const V5Step p
             __syncthreads();
             v4_pw<32, 32, 2, 2, 1>(d7, e7pwT, e7pwb, nullptr, nullptr, nullptr, r19, r27, nullptr, 0, tid);
             __syncthreads();
-            v4_pw<32, 32, 2, 1, 2>(r27, c3T, c3b, nullptr, nullptr, nullptr, nullptr, r31, nullptr, 0, tid);
+            if (t2) v4_pw<32, 32, 2, 2, 1>(r27, c3T, c3b, nullptr, nullptr, nullptr, nullptr, r31, nullptr, 0, tid);
+            else v4_pw<32, 32, 2, 1, 2>(r27, c3T, c3b, nullptr, nullptr, nullptr, nullptr, r31, nullptr, 0, tid);
             v4_fe_release(ring, tid);
         }
         if (p.dbg && tile == 0) {
@@ -435,14 +439,16 @@ __global__ void __launch_bounds__(kThreads, 1) v4_frontend_kernel(const V5Step p
         {
             const float *w2 = ring_wait(ring);  // S2 (kept while S3 is consumed)
             const float *e11dw = w2, *e11dwb = w2 + 160, *e11pwT = w2 + 192, *e11pwb = w2 + 2240;
-            v4_dw_relu<32, 1>(r31, e11dw, e11dwb, d11, tid);
+            if (t2) v4_dw_relu<32, 2>(r31, e11dw, e11dwb, d11, tid);
+            else v4_dw_relu<32, 1>(r31, e11dw, e11dwb, d11, tid);
             __syncthreads();
             // S3 sits in the next ring slot
             const uint32_t slot3 = (ring.g + 1) % kRingStages;
             mbar_wait(&ring.bars[slot3], ((ring.g + 1) / kRingStages) & 1u);
             const float *w3 = ring.buf + slot3 * kRingSlotFloats;
             const float *e11pjT = w3, *e11pjb = w3 + 2048;
-            v4_pw<32, 64, 1, 1, 1>(d11, e11pwT, e11pwb, r31, e11pjT, e11pjb, nullptr, r39, nullptr, 0, tid);
+            if (t2) v4_pw<32, 64, 2, 2, 1>(d11, e11pwT, e11pwb, r31, e11pjT, e11pjb, nullptr, r39, nullptr, 0, tid);
+            else v4_pw<32, 64, 1, 1, 1>(d11, e11pwT, e11pwb, r31, e11pjT, e11pjb, nullptr, r39, nullptr, 0, tid);
             v4_fe_release(ring, tid);  // S2
             v4_fe_release(ring, tid);  // S3
         }
@@ -451,13 +457,15 @@ __global__ void __launch_bounds__(kThreads, 1) v4_frontend_kernel(const V5Step p
         {
             const float *w = ring_wait(ring);  // S4: c4T[64][64]; its bias travels in S3's global copy
             const float *c4b = p.w_fe + kV4OffS3 + 2112;
-            // feat is tile-transposed for the recurrent kernel: [frame][rtile][64][32]
-            float *gout = p.feat + ((size_t)frame * p.n_stiles + (ft >> 1)) * (64 * kTile) + (ft & 1) * kV4Tile;
+            // feat is tile-transposed for the recurrent kernel: [frame (x 2 time steps at 8 kHz)][rtile][64][32]
+            float *gout = p.feat + ((size_t)frame * (t2 ? 2 : 1) * p.n_stiles + (ft >> 1)) * (64 * kTile) + (ft & 1) * kV4Tile;
             float *dbgf = (p.dbg && tile == 0)
                               ? p.dbg + kV4DbgMag + kV4DbgNorm + kV4DbgR3 + kV4DbgR15 + kV4DbgR27 + kV4DbgR39
                               : nullptr;
-            v4_pw<64, 64, 1, 1, 1>(r39, w, c4b, nullptr, nullptr, nullptr, nullptr, dbgf ? bufM : nullptr, gout,
-                                   kTile, tid);
+            if (t2) v4_pw<64, 64, 2, 2, 1>(r39, w, c4b, nullptr, nullptr, nullptr, nullptr, nullptr, gout, kTile, tid,
+                                           p.n_stiles * 64 * kTile);
+            else v4_pw<64, 64, 1, 1, 1>(r39, w, c4b, nullptr, nullptr, nullptr, nullptr, dbgf ? bufM : nullptr, gout,
+                                        kTile, tid);
             v4_fe_release(ring, tid);
             if (dbgf) block_copy_to_global(dbgf, bufM, kV4DbgFeat);
         }
@@ -527,9 +535,13 @@ __global__ void __launch_bounds__(kThreads, 1) v4_recurrent_kernel(const V5Step 
         mbar_fence_init();
     }
     __syncthreads();
+    // 8 kHz sub-model: every frame is two LSTM time steps ("virtual frames" jj = 2 j + t); the decoder output of
+    // the frame is the mean of the two sigmoids (ONNX ReduceMean over T)
+    const int T2 = p.v4_t2 ? 2 : 1;
+    const int vmax = tmax * T2;
     if (tid == 0) {
         for (uint32_t i = 0; i < kRingStages; ++i) v4_rec_ring_issue(ring, i);
-        for (int j = 0; j < 2 && j < tmax; ++j) {
+        for (int j = 0; j < 2 && j < vmax; ++j) {
             mbar_arrive_expect_tx(&xbars[j], 2048 * 4u);
             bulk_g2s(xbuf + j * 2048, p.feat + ((size_t)j * p.n_stiles + st) * 2048, 2048 * 4u, &xbars[j]);
         }
@@ -558,9 +570,11 @@ __global__ void __launch_bounds__(kThreads, 1) v4_recurrent_kernel(const V5Step 
     const float dec_b = __ldg(p.w_dec + 64);
     __syncthreads();
 
-    for (int j = 0; j < tmax; ++j) {
-        const float *xb = xbuf + (j & 1) * 2048;
-        mbar_wait(&xbars[j & 1], (uint32_t)(j >> 1) & 1u);
+    float psum = 0.f;
+    for (int jj = 0; jj < vmax; ++jj) {
+        const int j = jj / T2;
+        const float *xb = xbuf + (jj & 1) * 2048;
+        mbar_wait(&xbars[jj & 1], (uint32_t)(jj >> 1) & 1u);
 #pragma unroll
         for (int layer = 0; layer < 2; ++layer) {
             float2 acc2[2][4];
@@ -577,10 +591,10 @@ __global__ void __launch_bounds__(kThreads, 1) v4_recurrent_kernel(const V5Step 
                 if (tid == 0) v4_rec_ring_issue(ring, ring.g + kRingStages);
                 ++ring.g;
             }
-            if (layer == 1 && tid == 0 && j + 2 < tmax) {
-                mbar_arrive_expect_tx(&xbars[j & 1], 2048 * 4u);
-                bulk_g2s(xbuf + (j & 1) * 2048, p.feat + ((size_t)(j + 2) * p.n_stiles + st) * 2048, 2048 * 4u,
-                         &xbars[j & 1]);
+            if (layer == 1 && tid == 0 && jj + 2 < vmax) {
+                mbar_arrive_expect_tx(&xbars[jj & 1], 2048 * 4u);
+                bulk_g2s(xbuf + (jj & 1) * 2048, p.feat + ((size_t)(jj + 2) * p.n_stiles + st) * 2048, 2048 * 4u,
+                         &xbars[jj & 1]);
             }
             float g[4][4];
             unpack_tile(acc2, g);
@@ -606,7 +620,11 @@ __global__ void __launch_bounds__(kThreads, 1) v4_recurrent_kernel(const V5Step 
             float a = 0.f;
 #pragma unroll 8
             for (int u = 0; u < 64; ++u) a = fmaf(__ldg(p.w_dec + u), fmaxf(hbuf[2048 + u * kTile + lane], 0.f), a);
-            const float prob = sigmoid_f(a + dec_b);
+            float prob = sigmoid_f(a + dec_b);
+            if (T2 == 2) {
+                if ((jj & 1) == 0) { psum = prob; continue; }   // first time step: wait for the second
+                prob = (psum + prob) * 0.5f;
+            }
             const double pd = (double)prob;
             unsigned int fl = 0u;
             if (!sm_active) {

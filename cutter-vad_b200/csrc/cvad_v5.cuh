@@ -110,6 +110,7 @@ struct V5Step {
     const float *b_rec_tc;        // [4][128] gate-major (i,f,g,o), b_ih + b_hh
     unsigned char *feat_tc;       // [max_frames * n_stiles][tc5::kFeatTileBytes]
     long long *prof;              // optional clock64 marks of CTA 0 (cvad_set_profile), or null
+    int v4_t2;                    // v4 8 kHz sub-model: two time steps reach the LSTM per frame
 };
 
 struct EventRec {

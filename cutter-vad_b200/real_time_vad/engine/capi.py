@@ -14,7 +14,7 @@ PKG_ROOT = Path(__file__).resolve().parents[2]          # .../cutter-vad_b200
 LIB_PATH = PKG_ROOT / "libcvad_b200.so"
 
 OK, E_INVALID, E_CUDA, E_NOGPU, E_WEIGHTS, E_CAPACITY = 0, -1, -2, -3, -4, -5
-MODEL_V5, MODEL_V4 = 5, 4
+MODEL_V5, MODEL_V4, MODEL_V4_8K = 5, 4, 48
 PCM_F32, PCM_S16_32767, PCM_S16_32768 = 0, 1, 2
 FLAG_STARTED, FLAG_ENDED, FLAG_CONTINUING = 1, 2, 4
 STATUS_NONFINITE = 1

@@ -193,10 +193,21 @@ _V4_LAYOUT = (
 V4_WEIGHT_FLOATS = 155908
 
 
-def canonical_blob_v4(path: Union[str, Path]) -> np.ndarray:
+# the 8 kHz sub-model (`model_8k.*`, the graph's else-branch: any sr != 16000): same tensor shapes, its own
+# anonymous 1x1 convolutions (1122..1132) and LSTM initializers (833/835/837, 905/907/909)
+_V4_8K_RENAME = {"1110": "1122", "1111": "1123", "1113": "1125", "1114": "1126", "1116": "1128", "1117": "1129",
+                 "1119": "1131", "1120": "1132", "343": "833", "345": "835", "347": "837", "415": "905", "417": "907",
+                 "419": "909"}
+
+
+def canonical_blob_v4(path: Union[str, Path], branch: str = "16k") -> np.ndarray:
+    if branch not in ("16k", "8k"):
+        raise ValueError(f"unknown v4 branch {branch!r}")
     tensors = read_float_tensors(path)
     parts = []
     for name, size in _V4_LAYOUT:
+        if branch == "8k":
+            name = _V4_8K_RENAME.get(name, name.replace("model.", "model_8k.", 1))
         if name not in tensors:
             raise KeyError(f"{path}: tensor {name!r} not found (is this silero_vad.onnx, the v4 model?)")
         t = np.ascontiguousarray(tensors[name], dtype=np.float32).reshape(-1)

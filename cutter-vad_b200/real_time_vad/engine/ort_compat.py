@@ -73,6 +73,7 @@ class InferenceSession:
         else:
             raise ValueError(f"{path}: not a Silero VAD v4/v5 model")
         self._path = path
+        self._pooled8, self._slot8 = None, -1          # v4 only: slot on the 8 kHz sub-model's engine, leased on first use
         self._pooled, self._slot = pool.lease_slot(self.version, model_path=None if _is_packaged(path) else path)
         with self._pooled.lock:
             self._pooled.engine.configure([self._slot], enable_denoising=False)
@@ -106,8 +107,11 @@ class InferenceSession:
         if getattr(self, "_pooled", None) is not None:
             try:
                 self._pooled.release(self._slot)
+                if getattr(self, "_pooled8", None) is not None:
+                    self._pooled8.release(self._slot8)
             finally:
                 self._pooled = None
+                self._pooled8 = None
 
     def __del__(self):
         try:
@@ -121,9 +125,20 @@ class InferenceSession:
         if x.ndim != 2 or x.shape[0] != 1:
             raise ValueError("compat session.run handles one stream per call; use BatchedVADManager for batches")
         sr = int(np.asarray(input_feed["sr"]).reshape(-1)[0])
+        pooled, slot = self._pooled, self._slot
         if sr != 16000:
-            raise ValueError(f"sr={sr}: only the 16 kHz branch is implemented "
-                             "(the reference's v5 graph cannot run 512-sample frames at other rates either)")
+            # both graphs are `If(sr == 16000) 16 kHz model else 8 kHz model`.  v4's 8 kHz sub-model takes the same
+            # 512-sample frames and runs on its own engine; v5's cannot run a 512-sample frame (the LSTM input
+            # becomes 5-D) and fails in onnxruntime as it does here
+            if self.version != "v4":
+                raise ValueError(f"sr={sr}: the v5 graph's 8 kHz branch cannot run 512-sample frames "
+                                 "(invalid LSTM input in the reference as well)")
+            if self._pooled8 is None:
+                self._pooled8, self._slot8 = pool.lease_slot(
+                    "v4_8k", model_path=None if _is_packaged(self._path) else self._path)
+                with self._pooled8.lock:
+                    self._pooled8.engine.configure([self._slot8], enable_denoising=False)
+            pooled, slot = self._pooled8, self._slot8
         if self.version == "v5":
             state = np.asarray(input_feed["state"], dtype=np.float32)
             if state.shape != (2, 1, 128):
@@ -135,14 +150,14 @@ class InferenceSession:
             if h_in.shape != (2, 1, 64) or c_in.shape != (2, 1, 64):
                 raise ValueError(f"h and c must have shape (2, 1, 64), got {h_in.shape} / {c_in.shape}")
             h_in, c_in = h_in.reshape(128), c_in.reshape(128)      # engine rows: layer-major [2][64]
-        eng = self._pooled.engine
-        with self._pooled.lock:
-            eng.set_state(self._slot, h_in, c_in, np.zeros(4, np.int32))
+        eng = pooled.engine
+        with pooled.lock:
+            eng.set_state(slot, h_in, c_in, np.zeros(4, np.int32))
             frame_len = min(x.shape[1], 512)
-            r = eng.step(x, slots=[self._slot], max_frames=1, frame_len=frame_len, hop=max(frame_len, 1))
+            r = eng.step(x, slots=[slot], max_frames=1, frame_len=frame_len, hop=max(frame_len, 1))
             if r.status[0]:
                 raise ValueError("Audio data contains infinite or NaN values")
-            h, c, _, _ = eng.get_state(self._slot)
+            h, c, _, _ = eng.get_state(slot)
         out = r.probs.reshape(1, 1).astype(np.float32)
         if self.version == "v5":
             return [out, np.stack([h[None, :], c[None, :]], axis=0).astype(np.float32)]

@@ -73,6 +73,10 @@ class StreamEngine:
         elif model_version == "v4":
             path = Path(model_path) if model_path else MODELS_DIR / "silero_vad.onnx"
             self.weights, code = canonical_blob_v4(path), capi.MODEL_V4
+        elif model_version == "v4_8k":
+            # v4's 8 kHz sub-model: what the reference's session runs for v4 when sr != 16000
+            path = Path(model_path) if model_path else MODELS_DIR / "silero_vad.onnx"
+            self.weights, code = canonical_blob_v4(path, branch="8k"), capi.MODEL_V4_8K
         else:
             raise EngineError(capi.E_INVALID, f"unknown model version {model_version!r}")
         rc = self._L.cvad_create(_ptr(self.weights), self.weights.size, code, int(max_streams),

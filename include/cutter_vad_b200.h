@@ -53,6 +53,9 @@ extern "C" {
 /* model versions (SileroModelVersion, config.py:23-26) */
 #define CVAD_MODEL_V5 5
 #define CVAD_MODEL_V4 4
+#define CVAD_MODEL_V4_8K 48    /* v4's 8 kHz sub-model (`model_8k.*`): what the reference runs for v4 with sample_rate 8000
+                                (silero_model.py:433 feeds sr; the graph's else-branch): 512-sample frames of 8 kHz audio,
+                                two LSTM time steps per frame, the two sigmoid outputs averaged */
 
 /* arithmetic of the v5 GEMM stages (cvad_set_math).  Both hold the 1e-4 parity bar with two orders of margin:
    FP32  = packed FP32 FMA on the CUDA cores;

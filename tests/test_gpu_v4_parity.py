@@ -107,3 +107,65 @@ def test_v4_wrapper_and_compat_session(ref_v4):
     assert np.abs(pa - pb).max() <= 2e-6
     want, _, _ = ref_v4.run(x[None], T, hop=256, denoise=True)
     assert np.abs(pa - want[0, -len(pa):]).max() <= TOL
+
+
+def _interp_v4(audio, sr, dtype=np.float32):
+    """Frames of 512 samples through the reference's silero_vad.onnx, op by op (oracle/onnx_interp.py)."""
+    from conftest import V4_ONNX
+    from onnx_interp import OnnxInterpreter
+    it = OnnxInterpreter(str(V4_ONNX), dtype=dtype)
+    n, L = audio.shape
+    T = L // 512
+    probs = np.zeros((n, T), np.float32)
+    hs, cs = [], []
+    for s in range(n):
+        h = np.zeros((2, 1, 64), np.float32)
+        c = np.zeros((2, 1, 64), np.float32)
+        for j in range(T):
+            out, h, c = it.run({"input": audio[s:s + 1, j * 512:(j + 1) * 512], "h": h, "c": c,
+                                "sr": np.array(sr, np.int64)})
+            probs[s, j] = out.reshape(-1)[0]
+        hs.append(np.asarray(h).reshape(128))
+        cs.append(np.asarray(c).reshape(128))
+    return probs, np.stack(hs), np.stack(cs)
+
+
+def test_v4_8k_submodel_matches_onnx_graph(engine_factory):
+    """v4's 8 kHz sub-model (the graph's else-branch, what the reference runs for v4 with
+    sample_rate 8000): two LSTM time steps per 512-sample frame, the two sigmoid outputs averaged."""
+    n, T = 6, 9
+    audio = synth_streams(n, 512 * T, seed=61)           # interpreted as 8 kHz samples; a noise floor keeps v4 well conditioned
+    want, h_ref, c_ref = _interp_v4(audio, 8000)
+    want16, _, _ = _interp_v4(audio[:2], 16000)
+    assert np.abs(want[:2] - want16).max() > 1e-3          # it really is a different model
+    eng = engine_factory(32, model_version="v4_8k")
+    eng.configure(enable_denoising=False)
+    got = np.concatenate([eng.step(audio[:, :512 * 4]).probs, eng.step(audio[:, 512 * 4:]).probs], axis=1)
+    assert got.shape == (n, T)
+    assert np.abs(got - want).max() <= TOL
+    h, c, _, fd = eng.get_state(n - 1)
+    assert fd == T
+    assert np.abs(h - h_ref[n - 1]).max() <= 1e-4 and np.abs(c - c_ref[n - 1]).max() <= 1e-3
+
+
+def test_v4_8k_through_the_reference_facing_session():
+    """The `ort` seam: a v4 InferenceSession fed sr = 8000 runs the 8 kHz sub-model (state in, state out), as
+    onnxruntime does for the reference (silero_model.py:433, :476-499); a v5 session refuses, as the graph does."""
+    from conftest import V4_ONNX, V5_ONNX
+    from real_time_vad.engine import ort_compat as ort
+    audio = synth_streams(1, 512 * 5, seed=63)
+    want, _, _ = _interp_v4(audio, 8000)
+    sess = ort.InferenceSession(str(V4_ONNX))
+    h = np.zeros((2, 1, 64), np.float32)
+    c = np.zeros((2, 1, 64), np.float32)
+    got = []
+    for j in range(5):
+        out, h, c = sess.run(None, {"input": audio[:, j * 512:(j + 1) * 512], "h": h, "c": c,
+                                    "sr": np.array([8000], np.int64)})
+        got.append(float(out[0, 0]))
+    assert np.abs(np.array(got) - want[0]).max() <= TOL
+    sess.close()
+    s5 = ort.InferenceSession(str(V5_ONNX))
+    with pytest.raises(ValueError):
+        s5.run(None, {"input": audio[:, :512], "state": np.zeros((2, 1, 128), np.float32), "sr": np.array([8000], np.int64)})
+    s5.close()
