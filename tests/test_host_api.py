@@ -252,3 +252,16 @@ def test_async_wrapper_dispatches_coroutine_callbacks():
     asyncio.run(main())
     assert seen[0] == "start" and seen[1][0] == "end"
     aw.cleanup()
+
+
+def test_v4_weight_blobs_of_both_branches():
+    """canonical_blob_v4 lays out the 16 kHz branch or the 8 kHz sub-model (`model_8k.*`) in the same order."""
+    from conftest import V4_ONNX
+    from real_time_vad.engine.onnx_weights import V4_WEIGHT_FLOATS, canonical_blob_v4
+    b16 = canonical_blob_v4(V4_ONNX)
+    b8 = canonical_blob_v4(V4_ONNX, branch="8k")
+    assert b16.size == b8.size == V4_WEIGHT_FLOATS
+    assert np.isfinite(b8).all() and not np.array_equal(b16, b8)
+    assert b8[-1] != b16[-1]                                # decoder bias differs between the two sub-models
+    with pytest.raises(ValueError):
+        canonical_blob_v4(V4_ONNX, branch="44k")
