@@ -213,7 +213,7 @@ def workload_config(args, pool_mb):
                                          ", resampled to 16 kHz on the GPU" if rate != 16000 else ""),
             "model": model, "src_rate": rate,
             "streams_per_gpu": args.streams, "frames_per_step": args.frames_per_step, "hop": 512,
-            "frame_len": 512, "denoise": True, "state_machine": True, "math": getattr(args, "math", "fp32") if model == "v5" else "fp32",
+            "frame_len": 512, "denoise": True, "state_machine": True, "math": getattr(args, "math", "fp32"),
             "l2": (f"inputs cycle through a pool of distinct step buffers totalling {pool_mb} MB (> 126 MB L2)"
                    if pool_mb else "n/a (CPU arm)")}
 
@@ -249,7 +249,7 @@ def run_ours(args):
     peaks, peaks_src = load_peaks()
 
     eng = StreamEngine(args.model, max_streams=n, device=local)
-    math = args.math if args.model == "v5" else "fp32"
+    math = args.math
     eng.set_math(math)
     flop_frame = FLOP_FRAME if args.model == "v5" else 1_379_280
     flop_fe = FLOP_FRONTEND if args.model == "v5" else 1_379_280 - 2 * 65_600
@@ -425,14 +425,15 @@ def run_ours(args):
     fe_tflops = frames_per_step * flop_fe / fe_avg_s / 1e12 if fe_avg_s > 0 else 0.0
     step_tflops = frames_per_step * flop_frame / (dev_ms / args.steps * 1e-3) / 1e12
 
-    fused = math == "tc" and F == 1 and os.environ.get("CVAD_FUSE", "1") != "0"
+    fused = math == "tc" and args.model == "v5" and F == 1 and os.environ.get("CVAD_FUSE", "1") != "0"
     if fused:
         # one kernel does the whole step (front end + LSTM step + state machine): its FLOPs are the frame's
         flop_fe = flop_frame
         fe_tflops = frames_per_step * flop_fe / fe_avg_s / 1e12 if fe_avg_s > 0 else 0.0
     if rank == 0:
         tc = math == "tc"
-        fe_kernel = (("v5tc_frontend_kernel<FUSED>" if fused else "v5tc_frontend_kernel") if tc
+        fe_kernel = (("v4tc_stft_kernel+v4_frontend_kernel" if args.model == "v4" else
+                      "v5tc_frontend_kernel<FUSED>" if fused else "v5tc_frontend_kernel") if tc
                      else f"{args.model}_frontend_kernel") + ("+resample_kernel" if args.src_rate != 16000 else "")
         traffic = (ncu_traffic_bytes("v5tc_frontend_kernel" if tc else "v5_frontend_kernel")
                    if (n == 4096 and F == 1 and args.model == "v5" and args.src_rate == 16000) else None)

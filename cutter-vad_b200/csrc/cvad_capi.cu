@@ -18,6 +18,7 @@
 #include "cvad_resample.cuh"
 #include "cvad_tc.cuh"
 #include "cvad_v4.cuh"
+#include "cvad_v4tc.cuh"
 #include "cvad_v5tc.cuh"
 
 namespace {
@@ -52,6 +53,7 @@ struct cvad_engine {
     unsigned char *w_fe_tc = nullptr, *w_rec_tc = nullptr;
     float *nyq_w = nullptr, *b_rec_tc = nullptr;
     DevBuf d_feat_tc;
+    DevBuf d_v4_mag;                   // v4 tensor-core path: |STFT| tiles between the two front-end kernels
     long long *d_prof = nullptr;       // 128 clock64 marks of CTA 0 (cvad_set_profile)
     // per-slot state
     float *h_state = nullptr, *c_state = nullptr;
@@ -282,6 +284,20 @@ V5TcPacked pack_v5_tc(const float *blob) {
     P.b_rec.resize(512);
     for (int n = 0; n < 512; ++n) P.b_rec[n] = bih[n] + bhh[n];
     return P;
+}
+
+// v4 tensor-core STFT: the basis as 24 BF16x3 tiles (same row packing as v5's STFT block of pack_v5_tc)
+std::vector<unsigned char> pack_v4_stft_tc(const float *blob) {
+    const float *basis = blob;   // [258][256]
+    std::vector<unsigned char> out;
+    out.reserve(cvad::tc5::kV4StftStreamBytes);
+    for (int blk = 0; blk < 2; ++blk)
+        for (int kb = 0; kb < 4; ++kb)
+            emit_tiles(out, 128, kb * 64, [&](int m, int k) {
+                const int row = blk == 0 ? m : (m == 0 ? 128 : 129 + m);
+                return basis[row * 256 + k];
+            });
+    return out;
 }
 
 // ---- v4 weight repack (canonical blob order: oracle/silero_ref.c "Silero VAD v4")
@@ -608,6 +624,15 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
     const bool v4 = e->version == CVAD_MODEL_V4;
     const int n_tiles = a->max_frames * n_stiles * (v4 ? 2 : 1);
     const int grid_fe = std::min(n_tiles, e->num_sms);
+    if (v4 && e->math == CVAD_MATH_TC) {
+        // the STFT (77 % of v4's MACs) on the tensor cores; |STFT| tiles go through HBM to the FP32 front end
+        if ((rc = grow(e, e->d_v4_mag, (size_t)n_tiles * cvad::tc5::kV4MagTile * sizeof(float)))) return rc;
+        p.w_fe_tc = e->w_fe_tc;
+        p.v4_mag = static_cast<float *>(e->d_v4_mag.p);
+        cvad::tc5::v4tc_stft_kernel<<<grid_fe, cvad::tc5::kThreadsTC, cvad::tc5::kV4tcSmem, stream>>>(p);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+    }
     if (v4) cvad::v4_frontend_kernel<<<grid_fe, cvad::kThreads, cvad::kV4FeSmemBytes, stream>>>(p);
     else cvad::v5_frontend_kernel<<<grid_fe, cvad::kThreads, cvad::kFeSmemBytes, stream>>>(p);
     CU_TRY(e, cudaGetLastError());
@@ -951,6 +976,17 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
         const char *fz = std::getenv("CVAD_FUSE");
         e->fuse_single_frame = !(fz && std::strcmp(fz, "0") == 0);
     }
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v4tc_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::tc5::kV4tcSmem));
+    if (model_version == CVAD_MODEL_V4) {
+        std::vector<unsigned char> T = pack_v4_stft_tc(weights);
+        int rc;
+        if ((rc = upload(e, &e->w_fe_tc, T))) return bail(rc);
+        // v4 feeds log(1 + 2^20 |STFT|) into the network, which amplifies the tensor cores' (truncating) FP32
+        // accumulation on weak bins: FP32 FMA stays the default for v4, the tensor-core STFT is opt-in
+        const char *m = std::getenv("CVAD_MATH");
+        e->math = (m && std::strcmp(m, "tc") == 0) ? CVAD_MATH_TC : CVAD_MATH_FP32;
+    }
     {
         V5Packed P = model_version == CVAD_MODEL_V5 ? pack_v5(weights) : pack_v4(weights);
         int rc;
@@ -992,7 +1028,7 @@ int cvad_destroy(cvad_engine *e) {
                     e->sm_scount, e->sm_ecount, e->frames_done, e->start_p, e->end_p, e->n_start, e->n_end,
                     e->denoise, e->d_status_dev.p, e->d_feat.p, e->d_dbg.p, e->d_cfg_slots.p, e->d_res.p,
                     e->rs_rt[0], e->rs_rt[1], e->rs_rt[2], e->w_fe_tc, e->w_rec_tc, e->nyq_w, e->b_rec_tc,
-                    e->d_feat_tc.p, e->d_prof, e->d_rate_lists.p};
+                    e->d_feat_tc.p, e->d_prof, e->d_rate_lists.p, e->d_v4_mag.p};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &ln : e->lanes) {
@@ -1015,8 +1051,6 @@ int cvad_destroy(cvad_engine *e) {
 int cvad_set_math(cvad_engine *e, int math) {
     if (!e) return CVAD_E_INVALID;
     if (math != CVAD_MATH_FP32 && math != CVAD_MATH_TC) return fail(e, CVAD_E_INVALID, "math must be CVAD_MATH_FP32 or CVAD_MATH_TC");
-    if (math == CVAD_MATH_TC && e->version != CVAD_MODEL_V5)
-        return fail(e, CVAD_E_INVALID, "the tensor-core path exists for the v5 model only");
     e->math = math;
     return CVAD_OK;
 }

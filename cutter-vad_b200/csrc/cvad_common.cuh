@@ -131,6 +131,8 @@ struct WeightRing {
     uint64_t *bars;      // kRingStages "full" barriers
     const float *gsrc;   // packed weight stream in HBM/L2
     uint32_t g;          // chunks consumed so far by this CTA (uniform across threads)
+    uint32_t first = 0;  // v4 front end fed with a ready-made spectrogram: the stream starts at chunk `first` ...
+    uint32_t period = 0; // ... and repeats every `period` chunks (0 = the kernel's full period)
 };
 
 __device__ __forceinline__ const float *ring_wait(const WeightRing &r) {

@@ -49,7 +49,7 @@ __device__ __forceinline__ void v4_fe_chunk(int ci, uint32_t &off, uint32_t &n) 
 
 __device__ __forceinline__ void v4_fe_ring_issue(const WeightRing &r, uint32_t g) {
     uint32_t off, n;
-    v4_fe_chunk(static_cast<int>(g % kV4FeChunks), off, n);
+    v4_fe_chunk(static_cast<int>(r.period ? r.first + g % r.period : g % kV4FeChunks), off, n);
     const uint32_t slot = g % kRingStages;
     mbar_arrive_expect_tx(&r.bars[slot], n * 4u);
     bulk_g2s(r.buf + slot * kRingSlotFloats, r.gsrc + off, n * 4u, &r.bars[slot]);
@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) v4_frontend_kernel(const V5Step p
     const int warp = tid >> 5;
 
     WeightRing ring{ring_buf, bars, p.w_fe, 0u};
+    if (p.v4_mag) { ring.first = 16u; ring.period = 8u; }   // the STFT ran on the tensor cores: skip its 16 chunks
     if (tid == 0) {
         for (int i = 0; i < kRingStages; ++i) mbar_init(&bars[i], 1);
         mbar_fence_init();
@@ -185,6 +186,11 @@ __global__ void __launch_bounds__(kThreads, 1) v4_frontend_kernel(const V5Step p
         const int any_valid = __syncthreads_or(tid < kV4Tile ? s_valid[tid] : 0);
         if (!any_valid) continue;
 
+        if (p.v4_mag) {
+            // |STFT| of this tile was produced by v4tc_stft_kernel (same [bin][t][item] layout as bufM)
+            const float4 *src = reinterpret_cast<const float4 *>(p.v4_mag + (size_t)tile * kV4BufM);
+            for (int idx = tid; idx < kV4BufM / 4; idx += kThreads) st4(bufM + 4 * idx, __ldg(src + idx));
+        } else {
         // ---- frame loader into the middle of the reflect-padded buffer: xT[96 + k][item]
         {
             float *xT = bufX;
@@ -288,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) v4_frontend_kernel(const V5Step p
                 if (tn == 0) st4(bufM + (128 * 8 + tt) * kV4Tile + 4 * tm, make_float4(m2[0], m2[1], m2[2], m2[3]));
             }
         }
+        }   // !p.v4_mag
         __syncthreads();  // mag complete; xT dead
         // ---- spect = log(1 + 2^20 mag)  (ONNX Mul, Add, Log)
         for (int idx = tid; idx < kV4BufM / 4; idx += kThreads) {

@@ -1,0 +1,199 @@
+// cvad_v4tc.cuh -- the STFT of Silero VAD v4 on the tcgen05 tensor cores.
+//
+// 77 % of v4's 689,640 MAC per frame are the STFT (8 columns x 258 rows x 256 taps, SURVEY.md 8a "S4"); the rest
+// of the front end is depthwise / 1x1 layers of 16..64 channels that stay on the CUDA cores (cvad_v4.cuh).  This
+// kernel computes |STFT| of one tile of 16 (stream, frame) items with the same machinery as cvad_v5tc.cuh
+// (three-way BF16 split, six products per MAC, FP32 accumulators in TMEM, weight tiles streamed by cp.async.bulk)
+// and writes the magnitude tile [129][8][16] to HBM, where v4_frontend_kernel picks it up (V5Step::v4_mag).
+//
+// The hop (64 samples) equals one 64-element K block, so the sliding windows need no im2col copy: the
+// reflect-padded frame (704 samples) is stored as 11 segments of 64 samples, B operand rows = segment*16 + item,
+// and weight K block kb multiplies rows of segments kb .. kb+7: ONE MMA of N = 8 columns x 16 items = 128.
+#pragma once
+#include "cvad_v5tc.cuh"
+
+namespace cvad {
+namespace tc5 {
+
+constexpr int kV4tcRing = 8;
+constexpr uint32_t kV4tcPart = 11 * 16 * 128;          // one part of the padded-audio operand: 176 rows x 128 B
+constexpr size_t kV4StftStreamBytes = 24 * 16384;      // blk 0..1 x kb 0..3 x part 0..2 (same row packing as v5's STFT)
+constexpr size_t kV4tcSmem = 1024 + 3 * (size_t)kV4tcPart + (size_t)kV4tcRing * kSlotBytes + (2 * kV4tcRing + 2) * 8 + 16 +
+                             2 * 16 * 4 + 64;
+constexpr int kV4MagTile = 129 * 8 * 16;               // floats per tile
+
+__global__ void __launch_bounds__(kThreadsTC, 1) v4tc_stft_kernel(const V5Step p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *aud = base;
+    unsigned char *ring_buf = aud + 3 * kV4tcPart;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring_buf + kV4tcRing * kSlotBytes);
+    uint64_t *full = bars, *empty = bars + kV4tcRing, *act_ready = bars + 2 * kV4tcRing, *acc_ready = act_ready + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 1);
+    int *s_slot = reinterpret_cast<int *>(tmem_slot + 4);
+    int *s_valid = s_slot + 16;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < kV4tcRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(act_ready, 1);
+        mbar_init(acc_ready, 1);
+        mbar_fence_init();
+    }
+    if (warp == kProducerWarp) tc::tmem_alloc(tmem_slot, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    if (*tmem_slot != 0u) __trap();
+
+    const int n_ft = 2 * p.n_stiles;                   // 16-item tiles per frame (same indexing as v4_frontend_kernel)
+    const int n_tiles = p.max_frames * n_ft;
+    const uint32_t aud_s = smem_u32(aud), ring_s = smem_u32(ring_buf);
+
+    // warp-uniform liveness of tile (frame, ft): lanes 0..15 look at the tile's 16 streams
+    auto tile_live16 = [&](int frame, int ft, int *slot_out, int *valid_out) {
+        const int i = ft * 16 + (lane & 15);
+        int valid = 0, slot = -1;
+        if (i < p.n_streams) {
+            slot = p.slots ? p.slots[i] : i;
+            valid = frame < (p.n_frames ? p.n_frames[i] : p.max_frames);
+        }
+        if (slot_out) *slot_out = slot;
+        if (valid_out) *valid_out = valid;
+        return __any_sync(0xffffffffu, valid) != 0;
+    };
+
+    if (warp == kProducerWarp) {
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int frame = tile / n_ft, ft = tile - frame * n_ft;
+            if (!tile_live16(frame, ft, nullptr, nullptr)) continue;
+            if (lane == 0) {
+                for (int s = 0; s < 24; ++s, ++g) {
+                    const uint32_t slot = g % kV4tcRing;
+                    mbar_wait(&empty[slot], ((g / kV4tcRing) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&full[slot], kSlotBytes);
+                    bulk_g2s(ring_buf + slot * kSlotBytes, p.w_fe_tc + (size_t)s * kSlotBytes, kSlotBytes, &full[slot]);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == kMmaWarp) {
+        uint32_t g = 0, act_phase = 0;
+        const uint32_t idesc = tc::idesc_bf16_f32(128, 128);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int frame = tile / n_ft, ft = tile - frame * n_ft;
+            if (!tile_live16(frame, ft, nullptr, nullptr)) continue;
+            mbar_wait(act_ready, act_phase); act_phase ^= 1u;
+            tc::fence_after_sync();
+            for (int blk = 0; blk < 2; ++blk)
+                for (int kb = 0; kb < 4; ++kb)
+                    for (int wp = 0; wp < 3; ++wp, ++g) {
+                        const uint32_t slot = g % kV4tcRing;
+                        mbar_wait(&full[slot], (g / kV4tcRing) & 1u);
+                        tc::fence_after_sync();
+                        if (tc::elect_one()) {
+                            // column t of the STFT = samples 64 t .. 64 t + 255 = segments t .. t+3: K block kb <-> segment t + kb
+                            issue_split(wp, ring_s + slot * kSlotBytes, aud_s + kb * 2048u, kV4tcPart, blk * 128u,
+                                        256u + blk * 128u, idesc, kb == 0 && wp == 0);
+                            tc::mma_commit(&empty[slot]);
+                        }
+                        __syncwarp();
+                    }
+            if (tc::elect_one()) tc::mma_commit(acc_ready);
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3, cg = warp >> 2;
+        const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+        uint32_t acc_phase = 0;
+        const int flen = p.frame_len < 512 ? p.frame_len : 512;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int frame = tile / n_ft, ft = tile - frame * n_ft;
+            int my_slot, my_valid;
+            if (!tile_live16(frame, ft, &my_slot, &my_valid)) continue;
+            if (warp == 0 && lane < 16) { s_slot[lane] = my_slot; s_valid[lane] = my_valid; }
+            epi_bar();
+            // ---- loader: frame (zero-padded / truncated to 512) -> gate -> reflect-pad 96|96 -> 3 BF16 parts.
+            //      Work unit = 8 consecutive samples of the PADDED frame of one item (88 units per item).
+            for (int unit = tid; unit < 16 * 88; unit += kEpiThreads) {
+                const int s = unit / 88, c8 = unit - s * 88;
+                const int i = ft * 16 + s;
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                if (s_valid[s]) {
+                    const bool dn = p.denoise[s_slot[s]] != 0;
+                    const long long b0 = (long long)i * p.stride + (long long)frame * p.hop;
+                    bool bad = false;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int P = 8 * c8 + e;                                  // padded position 0..703
+                        const int k = P < 96 ? 96 - P : (P < 608 ? P - 96 : 1118 - P);   // reflect, no edge repeat
+                        float x = 0.f;
+                        if (k < flen) {
+                            x = p.pcm == 0 ? __ldg(reinterpret_cast<const float *>(p.audio) + b0 + k)
+                                           : (float)__ldg(reinterpret_cast<const short *>(p.audio) + b0 + k);
+                            if (p.pcm == 1) x = __fdiv_rn(x, 32767.0f);
+                            else if (p.pcm == 2) x = x * (1.0f / 32768.0f);
+                            if (!isfinite(x)) bad = true;
+                            if (dn && !(fabsf(x) > 0.01f)) x = 0.0f;
+                        }
+                        v[e] = x;
+                    }
+                    if (bad && p.status) atomicOr(&p.status[i], 1u);
+                }
+                uint32_t w[3][4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split3x2(v[2 * e], v[2 * e + 1], w[0][e], w[1][e], w[2][e]);
+                const uint32_t seg = (uint32_t)c8 >> 3, kk = ((uint32_t)c8 & 7u) * 8u;
+                const uint32_t off = tc::sw128_offset(seg * 16u + (uint32_t)s, kk, 176u);
+#pragma unroll
+                for (int part = 0; part < 3; ++part)
+                    *reinterpret_cast<uint4 *>(aud + part * kV4tcPart + off) = make_uint4(w[part][0], w[part][1], w[part][2], w[part][3]);
+            }
+            tc::fence_async_smem();
+            epi_bar();
+            if (tid == 0) mbar_arrive(act_ready);
+
+            // ---- magnitude (ONNX Slice, Pow, Pow, Add, Sqrt) -> HBM tile [bin][t][item]
+            mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
+            tc::fence_after_sync();
+            {
+                const int b = 32 * q + lane;
+                float *mout = p.v4_mag + (size_t)tile * kV4MagTile;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int c0 = cg * 32 + ch * 8;           // column = t*16 + item
+                    float mr[8], mi[8], cr[8], ci[8], mag[8];
+                    tmem_ld8(lane_addr + c0, mr);
+                    tmem_ld8(lane_addr + 128 + c0, mi);
+                    tmem_ld8(lane_addr + 256 + c0, cr);
+                    tmem_ld8(lane_addr + 384 + c0, ci);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float re = mr[e] + cr[e];
+                        float im = mi[e] + ci[e];
+                        if (b == 0) {
+                            mout[128 * 128 + c0 + e] = sqrtf(__fmul_rn(im, im));   // bin 128 rides in row 0 of the im block
+                            im = 0.f;
+                        }
+                        mag[e] = sqrtf(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+                    }
+                    float4 *dst = reinterpret_cast<float4 *>(mout + b * 128 + c0);
+                    dst[0] = make_float4(mag[0], mag[1], mag[2], mag[3]);
+                    dst[1] = make_float4(mag[4], mag[5], mag[6], mag[7]);
+                }
+            }
+            tc::fence_before_sync();
+            epi_bar();
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == kProducerWarp) tc::tmem_dealloc(0u, 512);
+}
+
+}  // namespace tc5
+}  // namespace cvad

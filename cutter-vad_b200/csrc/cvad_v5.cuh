@@ -111,6 +111,7 @@ struct V5Step {
     unsigned char *feat_tc;       // [max_frames * n_stiles][tc5::kFeatTileBytes]
     long long *prof;              // optional clock64 marks of CTA 0 (cvad_set_profile), or null
     int v4_t2;                    // v4 8 kHz sub-model: two time steps reach the LSTM per frame
+    float *v4_mag;                // v4 tensor-core path: |STFT| tiles [tile][129][8][16] written by v4tc_stft_kernel, or null
 };
 
 struct EventRec {

@@ -131,8 +131,10 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
                 int max_streams, int device, cvad_engine **out);
 int cvad_destroy(cvad_engine *e);
 
-/* Select the arithmetic of the model kernels (CVAD_MATH_*); v4 engines only accept CVAD_MATH_FP32.
-   A v5 engine starts in CVAD_MATH_TC unless the environment variable CVAD_MATH is "fp32"; v4 engines are FP32. */
+/* Select the arithmetic of the model kernels (CVAD_MATH_*).  For v5 every GEMM stage moves to the tensor cores;
+   for v4 the STFT (77 % of its MACs) does, the small layers and the two LSTM(64) stay FP32.
+   A v5 engine starts in CVAD_MATH_TC unless the environment variable CVAD_MATH is "fp32"; a v4 engine starts in
+   CVAD_MATH_FP32 unless CVAD_MATH is "tc" (v4's log(1 + 2^20 |STFT|) amplifies accumulation-order differences). */
 int cvad_set_math(cvad_engine *e, int math);
 int cvad_get_math(const cvad_engine *e);
 

@@ -13,6 +13,18 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
+@pytest.fixture(autouse=True, params=["tc", "fp32"])
+def math_mode(request, monkeypatch):
+    """Both builds of the v4 front end: STFT on the tcgen05 tensor cores (BF16 3-way split) or on the FP32 pipes."""
+    monkeypatch.setenv("CVAD_MATH", request.param)
+    from real_time_vad.engine import pool
+    for (version, _dev, _path), engines in pool._ENGINES.items():
+        if version.startswith("v4"):
+            for pe in engines:
+                pe.engine.set_math(request.param)
+    return request.param
+
+
 def test_v4_frontend_layers_match_oracle(engine_factory, ref_v4):
     eng = engine_factory(64, model_version="v4")
     eng.configure(enable_denoising=False)
@@ -30,10 +42,19 @@ def test_v4_frontend_layers_match_oracle(engine_factory, ref_v4):
             if name in want:
                 want[name].append(d[o:o + n].reshape(shape))
             o += n
+    mag_ref = np.stack(want["mag"], axis=-1)
     for name in ("mag", "norm", "r3", "r15", "r27", "r39", "feat"):
         w = np.stack(want[name], axis=-1)
         g = got[name]
         scale = max(1.0, float(np.abs(w).max()))
+        if name == "norm":
+            # norm = log(1 + 2^20 |STFT|) - mean: a weak bin turns an absolute spectrogram difference d into up to
+            # 2^20 d.  The FP32 build accumulates in the oracle's own order and lands on it (|d| <= 2e-6 here); the
+            # tensor cores accumulate 16 partial dot products with truncation (|d| <= 1.5e-5 = 6e-7 of full scale),
+            # so the bound carries the derivative of the log at d = 2e-6 for the bin's own magnitude
+            allowed = 5e-5 * scale + 2.0 ** 20 * 2e-6 / (1.0 + 2.0 ** 20 * mag_ref)
+            assert np.all(np.abs(g - w) <= allowed), f"norm: max abs err {np.abs(g - w).max()}"
+            continue
         err = float(np.abs(g - w).max())
         assert err <= 5e-5 * scale, f"{name}: max abs err {err} (scale {scale})"
 
