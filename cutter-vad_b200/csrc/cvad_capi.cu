@@ -66,6 +66,7 @@ struct cvad_engine {
     DevBuf d_status_dev, d_feat, d_dbg, d_cfg_slots;
     cudaEvent_t last_done = nullptr;   // recorded after the kernels of the most recent step
     float *rs_rt[3] = {nullptr, nullptr, nullptr};  // R^T for 8 / 24 / 48 kHz, built on first use
+    unsigned char *rs_tc[3] = {nullptr, nullptr, nullptr};  // the same operators as BF16x3 tiles for resample_tc_kernel
     DevBuf d_res;                      // resampled 16 kHz audio of the step being launched
     DevBuf d_rate_lists;               // mixed-rate steps: [4][n] stream lists + 4 counters
     // host-buffer steps run on kLanes lanes so that later steps' H2D copies overlap earlier steps' kernels and D2H
@@ -465,6 +466,23 @@ int ensure_rt(cvad_engine *e, int src_rate, cudaStream_t stream) {
     return CVAD_OK;
 }
 
+// R as BF16x3 tiles for resample_tc_kernel: K block kb-major, then output block (128 samples), then part
+int ensure_rt_tc(cvad_engine *e, int src_rate, cudaStream_t stream) {
+    const int ri = rate_index(src_rate), n_in = rate_n_in(src_rate);
+    if (e->rs_tc[ri]) return CVAD_OK;
+    std::vector<float> rt;
+    build_resample_rt(n_in, rt);            // R^T [n_in][512]
+    std::vector<unsigned char> tiles;
+    tiles.reserve((size_t)512 * n_in * 6);
+    for (int kb = 0; kb < n_in / 64; ++kb)
+        for (int blk = 0; blk < 4; ++blk)
+            emit_tiles(tiles, 128, kb * 64, [&](int r, int m) { return rt[(size_t)m * 512 + blk * 128 + r]; });
+    CU_TRY(e, cudaMalloc(reinterpret_cast<void **>(&e->rs_tc[ri]), tiles.size()));
+    CU_TRY(e, cudaMemcpyAsync(e->rs_tc[ri], tiles.data(), tiles.size(), cudaMemcpyHostToDevice, stream));
+    CU_TRY(e, cudaStreamSynchronize(stream));
+    return CVAD_OK;
+}
+
 // `rates_mask`: which of the rate slots {8000, 24000, 48000, 16000} may occur in a->src_rates (bit r); callers
 // that cannot look at the array (device-pointer steps) pass 0xF
 int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status, int commit, float *d_dbg,
@@ -505,11 +523,20 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         r.n_streams = a->n_streams; r.n_stiles = n_stiles; r.max_frames = a->max_frames; r.n_frames = a->n_frames;
         r.out = static_cast<float *>(e->d_res.p);
         const int grid_rs = std::min(a->max_frames * n_stiles, e->num_sms);
+        const bool rs_tc = e->math == CVAD_MATH_TC;
+        const int grid_rs_tc = std::min(a->max_frames * ((a->n_streams + cvad::tc5::kRsTcTile - 1) / cvad::tc5::kRsTcTile),
+                                        e->num_sms);
         if (!mixed) {
-            if ((rc = ensure_rt(e, a->src_rate, stream))) return rc;
             r.n_in = rate_n_in(a->src_rate);
-            r.rt = e->rs_rt[rate_index(a->src_rate)];
-            cvad::resample_kernel<<<grid_rs, cvad::kThreads, cvad::kRsSmemBytes, stream>>>(r);
+            if (rs_tc) {
+                if ((rc = ensure_rt_tc(e, a->src_rate, stream))) return rc;
+                cvad::tc5::resample_tc_kernel<<<grid_rs_tc, cvad::tc5::kThreadsTC, cvad::tc5::kRsTcSmem, stream>>>(
+                    r, e->rs_tc[rate_index(a->src_rate)]);
+            } else {
+                if ((rc = ensure_rt(e, a->src_rate, stream))) return rc;
+                r.rt = e->rs_rt[rate_index(a->src_rate)];
+                cvad::resample_kernel<<<grid_rs, cvad::kThreads, cvad::kRsSmemBytes, stream>>>(r);
+            }
             CU_TRY(e, cudaGetLastError());
             e->launches++;
         } else {
@@ -526,12 +553,18 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
             static const int kRates[3] = {8000, 24000, 48000};
             for (int ri = 0; ri < 3; ++ri) {
                 if (!(rates_mask & (1u << ri))) continue;
-                if ((rc = ensure_rt(e, kRates[ri], stream))) return rc;
                 r.n_in = rate_n_in(kRates[ri]);
-                r.rt = e->rs_rt[ri];
                 r.list = lists + (size_t)ri * n;
                 r.count = counts + ri;
-                cvad::resample_kernel<<<grid_rs, cvad::kThreads, cvad::kRsSmemBytes, stream>>>(r);
+                if (rs_tc) {
+                    if ((rc = ensure_rt_tc(e, kRates[ri], stream))) return rc;
+                    cvad::tc5::resample_tc_kernel<<<grid_rs_tc, cvad::tc5::kThreadsTC, cvad::tc5::kRsTcSmem, stream>>>(
+                        r, e->rs_tc[ri]);
+                } else {
+                    if ((rc = ensure_rt(e, kRates[ri], stream))) return rc;
+                    r.rt = e->rs_rt[ri];
+                    cvad::resample_kernel<<<grid_rs, cvad::kThreads, cvad::kRsSmemBytes, stream>>>(r);
+                }
                 CU_TRY(e, cudaGetLastError());
                 e->launches++;
             }
@@ -978,6 +1011,8 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
     }
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::v4tc_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kV4tcSmem));
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::resample_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::tc5::kRsTcSmem));
     if (model_version == CVAD_MODEL_V4) {
         std::vector<unsigned char> T = pack_v4_stft_tc(weights);
         int rc;
@@ -1028,7 +1063,7 @@ int cvad_destroy(cvad_engine *e) {
                     e->sm_scount, e->sm_ecount, e->frames_done, e->start_p, e->end_p, e->n_start, e->n_end,
                     e->denoise, e->d_status_dev.p, e->d_feat.p, e->d_dbg.p, e->d_cfg_slots.p, e->d_res.p,
                     e->rs_rt[0], e->rs_rt[1], e->rs_rt[2], e->w_fe_tc, e->w_rec_tc, e->nyq_w, e->b_rec_tc,
-                    e->d_feat_tc.p, e->d_prof, e->d_rate_lists.p, e->d_v4_mag.p};
+                    e->d_feat_tc.p, e->d_prof, e->d_rate_lists.p, e->d_v4_mag.p, e->rs_tc[0], e->rs_tc[1], e->rs_tc[2]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &ln : e->lanes) {

@@ -10,6 +10,7 @@
 // reflect-padded frame (704 samples) is stored as 11 segments of 64 samples, B operand rows = segment*16 + item,
 // and weight K block kb multiplies rows of segments kb .. kb+7: ONE MMA of N = 8 columns x 16 items = 128.
 #pragma once
+#include "cvad_resample.cuh"
 #include "cvad_v5tc.cuh"
 
 namespace cvad {
@@ -184,6 +185,188 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v4tc_stft_kernel(const V5Step p
                     float4 *dst = reinterpret_cast<float4 *>(mout + b * 128 + c0);
                     dst[0] = make_float4(mag[0], mag[1], mag[2], mag[3]);
                     dst[1] = make_float4(mag[4], mag[5], mag[6], mag[7]);
+                }
+            }
+            tc::fence_before_sync();
+            epi_bar();
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == kProducerWarp) tc::tmem_dealloc(0u, 512);
+}
+
+// =====================================================================================
+// Resampler on the tensor cores: y[512] = R x[n_in] per frame-sized chunk (cvad_resample.cuh has the operator and
+// the FP32 build).  A = R (4 blocks of 128 output samples x 64-sample K blocks, BF16x3 tiles streamed in the
+// order kb-major / block / part), B = the chunk's K block for a tile of 64 streams (double-buffered: the loader
+// converts K block kb+1 while the MMAs of kb run), D = 4 x 64 columns (+ the correction accumulators) in TMEM.
+// Output: float32 16 kHz frames in HBM, exactly where resample_kernel puts them.
+// =====================================================================================
+constexpr int kRsTcTile = 64;
+constexpr int kRsTcRing = 8;
+constexpr uint32_t kRsTcBPart = kRsTcTile * 128;                 // one part of one B buffer: 64 rows x 128 B
+constexpr size_t kRsTcSmem = 1024 + 2 * 3 * (size_t)kRsTcBPart + (size_t)kRsTcRing * kSlotBytes + (2 * kRsTcRing + 5) * 8 +
+                             16 + 2 * kRsTcTile * 4 + 64;
+
+__global__ void __launch_bounds__(kThreadsTC, 1) resample_tc_kernel(const ResampleStep p, const unsigned char *r_tiles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *bbuf = base;                                   // [2][3 parts][64 rows][128 B]
+    unsigned char *ring_buf = bbuf + 2 * 3 * kRsTcBPart;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring_buf + kRsTcRing * kSlotBytes);
+    uint64_t *full = bars, *empty = bars + kRsTcRing, *b_full = bars + 2 * kRsTcRing, *b_empty = b_full + 2,
+             *acc_ready = b_empty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 1);
+    int *s_gi = reinterpret_cast<int *>(tmem_slot + 4);           // [64] stream index of each tile row, or -1
+    int *s_valid = s_gi + kRsTcTile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < kRsTcRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(acc_ready, 1);
+        mbar_fence_init();
+    }
+    if (warp == kProducerWarp) tc::tmem_alloc(tmem_slot, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    if (*tmem_slot != 0u) __trap();
+
+    const int n_items = p.count ? *p.count : p.n_streams;
+    const int n_st = (n_items + kRsTcTile - 1) / kRsTcTile;
+    const int n_tiles = p.max_frames * n_st;
+    const int n_kb = p.n_in / 64;
+    const uint32_t b_s = smem_u32(bbuf), ring_s = smem_u32(ring_buf);
+
+    // warp-uniform: does tile (frame, st) hold a live (stream, frame) item?  (every warp evaluates all 64 rows)
+    auto tile_live64 = [&](int frame, int st, int *gi2, int *valid2) {
+        bool any = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = st * kRsTcTile + h * 32 + lane;
+            int valid = 0, gi = -1;
+            if (j < n_items) {
+                gi = p.list ? p.list[j] : j;
+                valid = frame < (p.n_frames ? p.n_frames[gi] : p.max_frames);
+            }
+            if (gi2) { gi2[h] = gi; valid2[h] = valid; }
+            any = any || __any_sync(0xffffffffu, valid);
+        }
+        return any;
+    };
+
+    if (warp == kProducerWarp) {
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int frame = tile / n_st, st = tile - frame * n_st;
+            if (!tile_live64(frame, st, nullptr, nullptr)) continue;
+            if (lane == 0) {
+                for (int s = 0; s < 12 * n_kb; ++s, ++g) {
+                    const uint32_t slot = g % kRsTcRing;
+                    mbar_wait(&empty[slot], ((g / kRsTcRing) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&full[slot], kSlotBytes);
+                    bulk_g2s(ring_buf + slot * kSlotBytes, r_tiles + (size_t)s * kSlotBytes, kSlotBytes, &full[slot]);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == kMmaWarp) {
+        uint32_t g = 0, nb = 0;                                   // weight slots and B buffers consumed so far
+        const uint32_t idesc = tc::idesc_bf16_f32(128, kRsTcTile);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int frame = tile / n_st, st = tile - frame * n_st;
+            if (!tile_live64(frame, st, nullptr, nullptr)) continue;
+            for (int kb = 0; kb < n_kb; ++kb, ++nb) {
+                const uint32_t bb = nb & 1u;
+                mbar_wait(&b_full[bb], (nb >> 1) & 1u);
+                tc::fence_after_sync();
+                for (int blk = 0; blk < 4; ++blk)
+                    for (int wp = 0; wp < 3; ++wp, ++g) {
+                        const uint32_t slot = g % kRsTcRing;
+                        mbar_wait(&full[slot], (g / kRsTcRing) & 1u);
+                        tc::fence_after_sync();
+                        if (tc::elect_one()) {
+                            issue_split(wp, ring_s + slot * kSlotBytes, b_s + bb * 3 * kRsTcBPart, kRsTcBPart, blk * 64u,
+                                        256u + blk * 64u, idesc, kb == 0 && wp == 0);
+                            tc::mma_commit(&empty[slot]);
+                        }
+                        __syncwarp();
+                    }
+                if (tc::elect_one()) tc::mma_commit(&b_empty[bb]);    // this K block's operand may be overwritten
+                __syncwarp();
+            }
+            if (tc::elect_one()) tc::mma_commit(acc_ready);
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3, cg = warp >> 2;
+        const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+        uint32_t acc_phase = 0, nb = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int frame = tile / n_st, st = tile - frame * n_st;
+            int gi2[2], valid2[2];
+            if (!tile_live64(frame, st, gi2, valid2)) continue;
+            if (warp == 0) {
+                s_gi[lane] = gi2[0]; s_gi[32 + lane] = gi2[1];
+                s_valid[lane] = valid2[0]; s_valid[32 + lane] = valid2[1];
+            }
+            epi_bar();
+            // one work unit per thread and K block: 8 source samples of one stream
+            const int s = tid >> 3, c8 = tid & 7;
+            const bool valid = s_valid[s] != 0;
+            const long long b0 = valid ? (long long)s_gi[s] * p.stride + (long long)frame * p.n_in + 8 * c8 : 0;
+            const uint32_t off = tc::sw128_offset((uint32_t)s, (uint32_t)c8 * 8u, (uint32_t)kRsTcTile);
+            for (int kb = 0; kb < n_kb; ++kb, ++nb) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                if (valid) {
+                    const long long o = b0 + 64LL * kb;
+                    if (p.pcm == 0) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = __ldg(reinterpret_cast<const float *>(p.audio) + o + e);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float x = (float)__ldg(reinterpret_cast<const short *>(p.audio) + o + e);
+                            v[e] = p.pcm == 1 ? __fdiv_rn(x, 32767.0f) : x * (1.0f / 32768.0f);
+                        }
+                    }
+                }
+                uint32_t w[3][4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split3x2(v[2 * e], v[2 * e + 1], w[0][e], w[1][e], w[2][e]);
+                const uint32_t bb = nb & 1u;
+                mbar_wait(&b_empty[bb], ((nb >> 1) & 1u) ^ 1u);   // the MMAs that read this buffer two K blocks ago are done
+                unsigned char *dst = bbuf + bb * 3 * kRsTcBPart + off;
+#pragma unroll
+                for (int part = 0; part < 3; ++part)
+                    *reinterpret_cast<uint4 *>(dst + part * kRsTcBPart) = make_uint4(w[part][0], w[part][1], w[part][2], w[part][3]);
+                tc::fence_async_smem();
+                epi_bar();
+                if (tid == 0) mbar_arrive(&b_full[bb]);
+            }
+            // ---- epilogue: D[sample][stream] -> out[stream][frame*512 + sample]
+            mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
+            tc::fence_after_sync();
+#pragma unroll 1
+            for (int blk = 0; blk < 4; ++blk) {
+                const int sample = blk * 128 + 32 * q + lane;
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    const int c0 = cg * 16 + ch * 8;
+                    float m[8], cr[8];
+                    tmem_ld8(lane_addr + blk * 64 + c0, m);
+                    tmem_ld8(lane_addr + 256 + blk * 64 + c0, cr);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = c0 + e;
+                        if (s_valid[c])
+                            p.out[(size_t)s_gi[c] * p.max_frames * 512 + (size_t)frame * 512 + sample] = m[e] + cr[e];
+                    }
                 }
             }
             tc::fence_before_sync();

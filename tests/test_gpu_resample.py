@@ -12,6 +12,13 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
+@pytest.fixture(autouse=True, params=["tc", "fp32"])
+def math_mode(request, monkeypatch):
+    """Both builds: resampler + model GEMMs on the tcgen05 tensor cores (BF16 3-way split), or FP32 FMA."""
+    monkeypatch.setenv("CVAD_MATH", request.param)
+    return request.param
+
+
 def _source_audio(n, T, rate, seed):
     """Band-limited source-rate signal: the 16 kHz recipe upsampled by scipy, plus a little wideband noise."""
     from scipy import signal
