@@ -300,14 +300,25 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     mbar_wait(&empty[slot], ((g / RING) & 1u) ^ 1u);
                     uint32_t off, bytes;
                     const unsigned char *src;
-                    if (FUSED && (s < 24 || s >= 24 + kFeSlotsPerTile)) {
-                        // LSTM tiles of the recurrent stream (gate, K block, part): W_hh = K blocks 2,3 first, W_ih = 0,1 last
-                        const int r = s < 24 ? s : s - 24 - kFeSlotsPerTile;
-                        const int gate = r / 6, kb = (r / 3) % 2 + (s < 24 ? 2 : 0), part = r % 3;
+                    // FUSED order: hh gate 0 | STFT (24) | hh gate 1 | enc0 (18) | hh gate 2 | enc1 (18) | hh gate 3 |
+                    //              enc2 + enc3 (9) | W_ih of the four gates (24).  hh gate g = 6 tiles (K blocks 2,3 x part)
+                    int fe_idx = s, gate = -1, kb = 0, part = 0;
+                    if (FUSED) {
+                        if (s < 6) { gate = 0; kb = 2 + s / 3; part = s % 3; }
+                        else if (s < 30) fe_idx = s - 6;
+                        else if (s < 36) { gate = 1; kb = 2 + (s - 30) / 3; part = (s - 30) % 3; }
+                        else if (s < 54) fe_idx = s - 36 + 24;
+                        else if (s < 60) { gate = 2; kb = 2 + (s - 54) / 3; part = (s - 54) % 3; }
+                        else if (s < 78) fe_idx = s - 60 + 42;
+                        else if (s < 84) { gate = 3; kb = 2 + (s - 78) / 3; part = (s - 78) % 3; }
+                        else if (s < 93) fe_idx = s - 84 + 60;
+                        else { const int r = s - 93; gate = r / 6; kb = (r / 3) % 2; part = r % 3; }
+                    }
+                    if (gate >= 0) {
                         src = p.w_rec_tc + (size_t)((gate * 4 + kb) * 3 + part) * kSlotBytes;
                         bytes = kSlotBytes;
                     } else {
-                        fe_slot(FUSED ? s - 24 : s, off, bytes);
+                        fe_slot(fe_idx, off, bytes);
                         src = p.w_fe_tc + off;
                     }
                     mbar_arrive_expect_tx(&full[slot], bytes);
@@ -339,17 +350,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
         __syncwarp();                                                        \
         ++g;                                                                 \
     }
+            // FUSED: W_hh . h of gate G needs only the resident state; the four gates are issued where the tensor pipe
+            // would otherwise idle: under the frame loader and under the epilogues of the STFT, encoder.0 and encoder.1
+#define CVAD_TC_HH(G)                                                                                              \
+    if (FUSED) {                                                                                                   \
+        for (int kb = 0; kb < 2; ++kb)                                                                             \
+            for (int wp = 0; wp < 3; ++wp)                                                                         \
+                CVAD_TC_SLOT(issue_gate(wp, a_addr, h_s + kb * kXhKb, kColGate + 32 * (G), i128_32, kb == 0 && wp == 0)) \
+    }
             if (FUSED) {
-                // ---- W_hh . h of the LSTM gates: needs only the resident state, runs under the frame loader
                 mbar_wait(h_ready, h_phase); h_phase ^= 1u;
                 tc::fence_after_sync();
-                for (int gate = 0; gate < 4; ++gate)
-                    for (int kb = 0; kb < 2; ++kb)
-                        for (int wp = 0; wp < 3; ++wp)
-                            CVAD_TC_SLOT(issue_gate(wp, a_addr, h_s + kb * kXhKb, kColGate + 32 * gate, i128_32,
-                                                    kb == 0 && wp == 0))
-                CVAD_PROF(42);
             }
+            CVAD_TC_HH(0)
+            CVAD_PROF(42);
             // ---- STFT: D[blk][bin][(t, item)] = sum_k W[bin][k] x[128 t + k]; K block kb uses segment rows t + kb/2
             mbar_wait(act_ready, act_phase); act_phase ^= 1u;
             CVAD_PROF(32);
@@ -360,6 +374,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                         CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + (kb & 1) * 16384u + (kb >> 1) * 4096u, kAudPart,
                                                  kColMain + blk * 96, kColCorr + blk * 96, i128_96, kb == 0 && wp == 0))
             if (tc::elect_one()) tc::mma_commit(acc_ready);
+            CVAD_TC_HH(1)
             CVAD_PROF(33);
             __syncwarp();
             // ---- encoder.0 (k3 s1 p1): tap 1: out t <- in t (N 96); tap 0: out 1,2 <- in 0,1; tap 2: out 0,1 <- in 1,2
@@ -378,6 +393,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                                              i128_64, false))
             }
             if (tc::elect_one()) tc::mma_commit(acc_ready);
+            CVAD_TC_HH(2)
             CVAD_PROF(35);
             __syncwarp();
             // ---- encoder.1 (k3 s2 p1, 64 out): E0 row blocks are stored in time order {0, 2, 1}
@@ -397,6 +413,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                                              kColCorr + 32, i64_32, false))
             }
             if (tc::elect_one()) tc::mma_commit(acc_ready);
+            CVAD_TC_HH(3)
             CVAD_PROF(37);
             __syncwarp();
             // ---- encoder.2 (k3 s2 p1, 64 out, T 2 -> 1): tap 1 <- in 0 (rows 0..31), tap 2 <- in 1 (rows 32..63)
@@ -432,6 +449,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 CVAD_PROF(44);
                 __syncwarp();
             }
+#undef CVAD_TC_HH
 #undef CVAD_TC_SLOT
         }
     } else {
