@@ -190,7 +190,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 operands, f32 accumulate (FP32-equivalent)" if math == "tc" else "f32", "data": "synthetic",
+            "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, pool_mb=None),
         "p99_step_ms": 1e3 * float(np.percentile(lat, 99)),
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
