@@ -289,3 +289,32 @@ def test_pipelined_submit_collect_equals_blocking_steps(engine_factory, ref_v5):
     again = np.concatenate([eng.step(c).probs for c in chunks], axis=1)
     assert np.array_equal(got, again)
     assert eng.get_state(0)[3] == F * steps
+
+
+@pytest.mark.parametrize("case", ["zeros", "tiny", "denormal", "loud_x30", "int16_scale", "huge_1e8", "square", "dc", "impulses"])
+def test_extreme_inputs_stay_finite_and_on_the_oracle(engine_factory, ref_v5, case):
+    """The reference accepts any finite float32 audio (audio.py:211-231 only rejects NaN/Inf): un-normalised
+    int16-scale floats, silence, denormals, clipping square waves.  Both arithmetic paths must stay finite and on
+    the oracle there too (the BF16 operand parts keep FP32's exponent range), one call and one frame per step."""
+    T = 20
+    rng = np.random.default_rng(3)
+    base = synth_streams(4, 512 * T, seed=9)
+    t = np.arange(512 * T)
+    x = {"zeros": np.zeros((4, 512 * T), np.float32),
+         "tiny": (1e-6 * rng.standard_normal((4, 512 * T))).astype(np.float32),
+         "denormal": np.full((4, 512 * T), 1e-40, np.float32),
+         "loud_x30": (30 * base).astype(np.float32),
+         "int16_scale": (32768 * base).astype(np.float32),
+         "huge_1e8": (1e8 * base).astype(np.float32),
+         "square": np.sign(np.sin(2 * np.pi * 200 * t / 16000))[None, :].repeat(4, 0).astype(np.float32),
+         "dc": np.full((4, 512 * T), 0.5, np.float32),
+         "impulses": (rng.random((4, 512 * T)) > 0.999).astype(np.float32)}[case]
+    eng = engine_factory(8)
+    eng.reset()
+    eng.configure(enable_denoising=False)
+    want, _, _ = ref_v5.run(x, T, denoise=False)
+    one = eng.step(x).probs
+    eng.reset()
+    steps = np.stack([eng.step(x[:, j * 512:(j + 1) * 512]).probs[:, 0] for j in range(T)], axis=1)
+    assert np.isfinite(one).all() and np.isfinite(steps).all()
+    assert np.abs(one - want).max() <= TOL and np.abs(steps - want).max() <= TOL
