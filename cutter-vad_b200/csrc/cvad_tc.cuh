@@ -213,5 +213,37 @@ __global__ void __launch_bounds__(128, 1) tc_rate_kernel(int M, int N, int reps,
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// ---- bulk-copy stream probe (tools/tc_stream_rate.py): how fast can ONE SM pull 16 KB tiles from L2 into a
+// shared-memory ring with cp.async.bulk when nothing consumes them?  out[0] = cycles, out[1] = tiles.
+__global__ void __launch_bounds__(64, 1) bulk_rate_kernel(const unsigned char *src, size_t src_bytes, int tiles, int depth,
+                                                          int tile_bytes, long long *out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)depth * tile_bytes);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < depth; ++i) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t src_mask = (uint32_t)(src_bytes / tile_bytes) - 1u;   // power of two
+        const long long t0 = clock64();
+        int slot = 0;
+        uint32_t round = 0;
+        for (int g = 0; g < tiles + depth; ++g) {
+            if (g >= depth) mbar_wait(&bars[slot], (round - 1u) & 1u);       // previous fill of this slot landed
+            if (g < tiles) {
+                mbar_arrive_expect_tx(&bars[slot], tile_bytes);
+                bulk_g2s(base + (uint32_t)slot * (uint32_t)tile_bytes, src + (size_t)(((uint32_t)g & src_mask) * (uint32_t)tile_bytes),
+                         tile_bytes, &bars[slot]);
+            }
+            if (++slot == depth) { slot = 0; ++round; }
+        }
+        const long long t1 = clock64();
+        if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = tiles; }
+    }
+}
+
 }  // namespace tc
 }  // namespace cvad

@@ -24,7 +24,7 @@ EXPORTS = (
     "cvad_abi_version", "cvad_device_count", "cvad_last_error", "cvad_create", "cvad_destroy",
     "cvad_set_stream", "cvad_reset", "cvad_configure", "cvad_get_state", "cvad_set_state",
     "cvad_step", "cvad_step_submit", "cvad_step_collect", "cvad_step_device", "cvad_sync", "cvad_launch_count", "cvad_debug_dump",
-    "cvad_alloc_pinned", "cvad_free_pinned", "cvad_set_timing", "cvad_read_timing", "cvad_resample_matrix", "cvad_tc_probe", "cvad_tc_rate",
+    "cvad_alloc_pinned", "cvad_free_pinned", "cvad_set_timing", "cvad_read_timing", "cvad_resample_matrix", "cvad_tc_probe", "cvad_tc_rate", "cvad_bulk_rate",
     "cvad_set_math", "cvad_get_math", "cvad_set_profile", "cvad_read_profile",
 )
 
@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
     L.cvad_step_device.argtypes = [vp, C.POINTER(StepArgs)]
     L.cvad_tc_probe.argtypes = [i32, vp, vp, vp]
     L.cvad_tc_rate.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp]
+    L.cvad_bulk_rate.argtypes = [i32, i32, i32, i32, i32, C.c_size_t, vp]
     L.cvad_resample_matrix.argtypes = [i32, vp, C.c_size_t]
     L.cvad_step_submit.argtypes = [vp, C.POINTER(StepArgs), C.POINTER(C.c_int)]
     L.cvad_step_collect.argtypes = [vp, i32]
