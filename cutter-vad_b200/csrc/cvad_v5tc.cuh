@@ -471,6 +471,41 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             const bool dbg = DBG && tile == 0;
             const bool first_tile = tile == (int)blockIdx.x && tid == 0;
             CVAD_PROF(0);
+            // ---- frame loader (audio.py:164-190 split, :104-121 gate, silero_model.py:449-474 pad/truncate):
+            //      8 samples per work unit -> 3 x 16-byte BF16 chunks of the AUD operand, row = segment*32 + item.
+            //      All global loads of the thread's 4 units are issued before the first use -- and, in the fused
+            //      kernel, before the resident state is fetched, so that both HBM latencies overlap.
+                const bool fast = p.vec_ok && flen == 512;
+                float v[4][8];
+                bool ok[4];
+#pragma unroll
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const int unit = u4 * kEpiThreads + tid;
+                    const int s = unit >> 6, c8 = unit & 63;
+                    ok[u4] = s_valid[s] != 0;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[u4][e] = 0.f;
+                    if (ok[u4]) {
+                        const long long b0 = (long long)(st * kTile + s) * p.stride + (long long)frame * p.hop + 8 * c8;
+                        if (fast && p.pcm == 0) {
+                            const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.audio) + b0);
+                            const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
+                            v[u4][0] = t0.x; v[u4][1] = t0.y; v[u4][2] = t0.z; v[u4][3] = t0.w;
+                            v[u4][4] = t1.x; v[u4][5] = t1.y; v[u4][6] = t1.z; v[u4][7] = t1.w;
+                        } else if (fast) {
+                            const short4 *src = reinterpret_cast<const short4 *>(reinterpret_cast<const short *>(p.audio) + b0);
+                            const short4 t0 = __ldg(src), t1 = __ldg(src + 1);
+                            v[u4][0] = (float)t0.x; v[u4][1] = (float)t0.y; v[u4][2] = (float)t0.z; v[u4][3] = (float)t0.w;
+                            v[u4][4] = (float)t1.x; v[u4][5] = (float)t1.y; v[u4][6] = (float)t1.z; v[u4][7] = (float)t1.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (8 * c8 + e < flen)
+                                    v[u4][e] = p.pcm == 0 ? __ldg(reinterpret_cast<const float *>(p.audio) + b0 + e)
+                                                          : (float)__ldg(reinterpret_cast<const short *>(p.audio) + b0 + e);
+                        }
+                    }
+                }
             // FUSED: resident state of the tile's streams: h -> BF16x3 rows of the H operand, c -> registers
             // (global reads coalesced over streams, transposed through the still-unused ACT region)
             float creg[8];
@@ -511,41 +546,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 CVAD_PROF(12);
             }
 
-            // ---- frame loader (audio.py:164-190 split, :104-121 gate, silero_model.py:449-474 pad/truncate):
-            //      8 samples per work unit -> 3 x 16-byte BF16 chunks of the AUD operand, row = segment*32 + item.
-            //      All global loads of the thread's 4 units are issued before the first use.
+            // ---- frame loader, second half: convert, gate, split, store
             {
-                const bool fast = p.vec_ok && flen == 512;
-                float v[4][8];
-                bool ok[4];
-#pragma unroll
-                for (int u4 = 0; u4 < 4; ++u4) {
-                    const int unit = u4 * kEpiThreads + tid;
-                    const int s = unit >> 6, c8 = unit & 63;
-                    ok[u4] = s_valid[s] != 0;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[u4][e] = 0.f;
-                    if (ok[u4]) {
-                        const long long b0 = (long long)(st * kTile + s) * p.stride + (long long)frame * p.hop + 8 * c8;
-                        if (fast && p.pcm == 0) {
-                            const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.audio) + b0);
-                            const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
-                            v[u4][0] = t0.x; v[u4][1] = t0.y; v[u4][2] = t0.z; v[u4][3] = t0.w;
-                            v[u4][4] = t1.x; v[u4][5] = t1.y; v[u4][6] = t1.z; v[u4][7] = t1.w;
-                        } else if (fast) {
-                            const short4 *src = reinterpret_cast<const short4 *>(reinterpret_cast<const short *>(p.audio) + b0);
-                            const short4 t0 = __ldg(src), t1 = __ldg(src + 1);
-                            v[u4][0] = (float)t0.x; v[u4][1] = (float)t0.y; v[u4][2] = (float)t0.z; v[u4][3] = (float)t0.w;
-                            v[u4][4] = (float)t1.x; v[u4][5] = (float)t1.y; v[u4][6] = (float)t1.z; v[u4][7] = (float)t1.w;
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                if (8 * c8 + e < flen)
-                                    v[u4][e] = p.pcm == 0 ? __ldg(reinterpret_cast<const float *>(p.audio) + b0 + e)
-                                                          : (float)__ldg(reinterpret_cast<const short *>(p.audio) + b0 + e);
-                        }
-                    }
-                }
 #pragma unroll
                 for (int u4 = 0; u4 < 4; ++u4) {
                     const int unit = u4 * kEpiThreads + tid;
