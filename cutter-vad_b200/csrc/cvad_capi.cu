@@ -1385,3 +1385,5 @@ int cvad_debug_dump(cvad_engine *e, const cvad_step_args *a, float *dbg_out, siz
 }
 
 }  // extern "C"
+
+#include "cvad_feeder.cuh"

@@ -1,0 +1,566 @@
+// cvad_feeder.cuh -- host half of the service mode: per-slot pending-audio arena in pinned memory,
+// native gather / compaction around one cvad_step, and voice-segment assembly from the device's flags.
+//
+// What it replaces in the reference (one VADWrapper + one onnxruntime session per websocket client):
+//   ClientState.process_audio_frame        websocket_service/server/vad_websocket_server.py:326-369   -> cvad_feeder_push
+//   VADWrapper._process_audio_frames       src/real_time_vad/core/vad_wrapper.py:610-647               -> cvad_feeder_step
+//   VADProcessor voice_buffer / current_voice_data / _finalize_voice_segment
+//                                          src/real_time_vad/core/silero_model.py:839-869,:925-949     -> deliver()
+// Included by cvad_capi.cu (one translation unit); plain C++17, no device code.
+#pragma once
+
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+struct cvad_feeder {
+    cvad_engine *eng = nullptr;        // may be NULL: gather / deliver test hooks only
+    int max_streams = 0;
+    int pcm_format = CVAD_PCM_F32;
+    int frame_len = 512, hop = 512;
+    int src_rate = 16000;              // 0 = per-slot rates (mixed)
+    int max_step_frames = 8;           // frames one stream may run per step (a stream further behind catches up over steps)
+    size_t es = 4;                     // bytes per sample
+    size_t cap = 0;                    // arena row length (samples)
+    unsigned char *arena = nullptr;    // pinned [max_streams][cap]
+    std::mutex mu;                     // guards arena + fill + slot table (push vs step)
+    std::string err;
+
+    struct Slot {
+        bool open = false;
+        int rate = 16000;
+        int n_in = 512;                // source samples per model frame (mixed mode)
+        int payload = 0;               // CVAD_PAYLOAD_*
+        bool denoise = true;
+        double start_p = 0.7;
+        bool active = false;           // host mirror of is_voice_active
+        int64_t skip = 0;              // hop > frame_len: samples between frames that had not arrived when their frame ran
+        std::vector<float> pre_roll, segment;
+    };
+    std::vector<Slot> slot;
+    std::vector<int64_t> fill;
+
+    // step scratch (valid until the next step)
+    unsigned char *stage[2] = {nullptr, nullptr};   // pinned gather targets, alternating
+    size_t stage_cap[2] = {0, 0};
+    int cur = 0;
+    std::vector<int32_t> ids, counts, rates;
+    std::vector<float> probs;
+    std::vector<uint8_t> flags, status;
+    std::vector<cvad_event> events;
+    std::vector<cvad_delivery> deliveries;
+    std::vector<float> frame_pool;                   // gated frames handed to voice_continue this step
+    std::vector<std::vector<float>> done_segments;   // segments finished this step
+    int64_t row = 0;
+    int tmax = 0;
+    int threads = 1;
+};
+
+namespace {
+
+constexpr size_t kFeederArenaLimit = (size_t)16 << 30;   // pinned bytes the arena may grow to
+
+int ffail(cvad_feeder *f, int code, const std::string &msg) {
+    if (f) f->err = msg;
+    return code;
+}
+
+inline float feeder_sample(const cvad_feeder *f, const unsigned char *p, size_t k) {
+    if (f->pcm_format == CVAD_PCM_F32) return reinterpret_cast<const float *>(p)[k];
+    const float v = (float)reinterpret_cast<const int16_t *>(p)[k];
+    return f->pcm_format == CVAD_PCM_S16_32767 ? v / 32767.0f : v / 32768.0f;
+}
+
+// numpy's `np.where(np.abs(f) > 0.01, f, 0.0)` on float32 data (audio.py:117-118): the threshold is float32(0.01)
+inline void feeder_gate_append(const cvad_feeder *f, const cvad_feeder::Slot &s, const unsigned char *src, int n,
+                               std::vector<float> &dst) {
+    const size_t o = dst.size();
+    dst.resize(o + (size_t)n);
+    float *d = dst.data() + o;
+    for (int k = 0; k < n; ++k) {
+        const float v = feeder_sample(f, src, (size_t)k);
+        d[k] = (!s.denoise || std::fabs(v) > 0.01f) ? v : 0.0f;
+    }
+}
+
+int feeder_grow_stage(cvad_feeder *f, int which, size_t bytes) {
+    if (bytes <= f->stage_cap[which]) return CVAD_OK;
+    if (f->stage[which]) {
+        if (f->eng) cudaFreeHost(f->stage[which]); else std::free(f->stage[which]);
+        f->stage[which] = nullptr;
+        f->stage_cap[which] = 0;
+    }
+    const size_t cap = bytes + bytes / 4 + 4096;
+    if (f->eng) {
+        void *p = nullptr;
+        if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); return ffail(f, CVAD_E_CUDA, "cudaMallocHost failed"); }
+        f->stage[which] = static_cast<unsigned char *>(p);
+    } else {
+        f->stage[which] = static_cast<unsigned char *>(std::malloc(cap));
+        if (!f->stage[which]) return ffail(f, CVAD_E_CAPACITY, "out of host memory");
+    }
+    f->stage_cap[which] = cap;
+    return CVAD_OK;
+}
+
+// Phase 1 of a step, under the lock: pick the streams that hold at least one whole frame, copy their
+// pending samples into a dense [n][row] block (split_into_frames' input, audio.py:164-190) and drop
+// what the step will consume from the arena (leftovers shorter than a hop stay for the next step).
+int feeder_gather(cvad_feeder *f) {
+    std::lock_guard<std::mutex> lk(f->mu);
+    f->cur ^= 1;
+    f->ids.clear(); f->counts.clear(); f->rates.clear();
+    const bool mixed = f->src_rate == 0;
+    int tmax = 0;
+    int64_t row = 0;
+    for (int s = 0; s < f->max_streams; ++s) {
+        const cvad_feeder::Slot &sl = f->slot[s];
+        if (!sl.open) continue;
+        const int64_t have = f->fill[s];
+        int64_t c;
+        if (mixed) c = have / sl.n_in;
+        else c = have >= f->frame_len ? (have - f->frame_len) / f->hop + 1 : 0;
+        if (c <= 0) continue;
+        if (c > f->max_step_frames) c = f->max_step_frames;
+        f->ids.push_back(s);
+        f->counts.push_back((int32_t)c);
+        if (mixed) {
+            f->rates.push_back(sl.rate);
+            row = std::max<int64_t>(row, c * sl.n_in);
+        }
+        tmax = std::max(tmax, (int)c);
+    }
+    const int n = (int)f->ids.size();
+    f->tmax = tmax;
+    if (n == 0) { f->row = 0; return CVAD_OK; }
+    if (!mixed) row = (int64_t)(tmax - 1) * f->hop + f->frame_len;
+    row += (-row) & 7;                         // rows start 16-byte aligned in either sample format
+    f->row = row;
+    int rc = feeder_grow_stage(f, f->cur, (size_t)n * (size_t)row * f->es);
+    if (rc) return rc;
+    unsigned char *stage = f->stage[f->cur];
+    auto work = [&](int k0, int k1) {
+        for (int k = k0; k < k1; ++k) {
+            const int s = f->ids[k];
+            const cvad_feeder::Slot &sl = f->slot[s];
+            unsigned char *src = f->arena + (size_t)s * f->cap * f->es;
+            const int64_t have = f->fill[s];
+            const int64_t used = (int64_t)f->counts[k] * (mixed ? sl.n_in : f->hop);
+            const int64_t need = mixed ? used : (int64_t)(f->counts[k] - 1) * f->hop + f->frame_len;
+            std::memcpy(stage + (size_t)k * (size_t)row * f->es, src, (size_t)need * f->es);
+            const int64_t rem = have - used;
+            if (rem > 0) std::memmove(src, src + (size_t)used * f->es, (size_t)rem * f->es);
+            f->fill[s] = rem > 0 ? rem : 0;
+            if (rem < 0) f->slot[s].skip = -rem;
+        }
+    };
+    const size_t bytes = (size_t)n * (size_t)row * f->es;
+    const int nt = (f->threads > 1 && bytes > (4u << 20)) ? std::min(f->threads, n) : 1;
+    if (nt <= 1) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, (int)((int64_t)n * t / nt), (int)((int64_t)n * (t + 1) / nt));
+        work(0, n / nt);
+        for (auto &x : th) x.join();
+    }
+    return CVAD_OK;
+}
+
+// Phase 3: the callback side of VADProcessor (silero_model.py:818-949) replayed from the device's per-frame
+// flags -- host mirror of is_voice_active, pre-roll / segment assembly, delivery records.
+void feeder_deliver(cvad_feeder *f) {
+    const int n = (int)f->ids.size(), T = f->tmax;
+    f->deliveries.clear();
+    f->frame_pool.clear();
+    f->done_segments.clear();
+    const unsigned char *stage = f->stage[f->cur];
+    const bool mixed = f->src_rate == 0;
+    // pass 1: how many continue-frames will be pooled (so that frame_pool never reallocates under the records)
+    size_t pool = 0;
+    for (int k = 0; k < n; ++k) {
+        const cvad_feeder::Slot &sl = f->slot[f->ids[k]];
+        if (sl.payload == CVAD_PAYLOAD_FRAMES && sl.rate == 16000) pool += (size_t)f->counts[k] * (size_t)f->frame_len;
+    }
+    f->frame_pool.reserve(pool);
+    for (int k = 0; k < n; ++k) {
+        const int s = f->ids[k];
+        cvad_feeder::Slot &sl = f->slot[s];
+        const int c = f->counts[k];
+        const uint8_t *fl = f->flags.data() + (size_t)k * T;
+        const float *pr = f->probs.data() + (size_t)k * T;
+        if (sl.payload == CVAD_PAYLOAD_NONE) {
+            const uint8_t last = fl[c - 1];
+            sl.active = !(last & CVAD_FLAG_ENDED) && (last & (CVAD_FLAG_STARTED | CVAD_FLAG_CONTINUING));
+            continue;
+        }
+        const unsigned char *rowp = stage + (size_t)k * (size_t)f->row * f->es;
+        const bool raw_mode = sl.payload >= CVAD_PAYLOAD_SEGMENTS && sl.rate != 16000;   // host resamples the payloads
+        const int64_t step_len = mixed ? sl.n_in : f->hop;
+        const int flen = mixed ? sl.n_in : f->frame_len;
+        for (int j = 0; j < c; ++j) {
+            const uint8_t b = fl[j];
+            const unsigned char *fp = rowp + (size_t)j * (size_t)step_len * f->es;
+            cvad_delivery d{};
+            d.slot = s; d.stream = k; d.step_frame = j; d.flags = b;
+            d.prob = pr[j];
+            if (raw_mode) {
+                // every frame is handed over; the host keeps pre-roll / segment for this stream itself
+                d.raw = fp; d.raw_len = flen;
+                const uint8_t last = b;
+                sl.active = !(last & CVAD_FLAG_ENDED) && (last & (CVAD_FLAG_STARTED | CVAD_FLAG_CONTINUING));
+                f->deliveries.push_back(d);
+                continue;
+            }
+            const bool audio = sl.payload >= CVAD_PAYLOAD_SEGMENTS;
+            bool emit = false;
+            if (!sl.active) {
+                if ((double)pr[j] >= sl.start_p) {
+                    if (audio) feeder_gate_append(f, sl, fp, flen, sl.pre_roll);
+                    if (b & CVAD_FLAG_STARTED) {
+                        sl.segment.swap(sl.pre_roll);
+                        sl.pre_roll.clear();
+                        sl.active = true;
+                        emit = true;
+                    }
+                } else {
+                    sl.pre_roll.clear();
+                }
+            } else {
+                size_t frame_at = 0;
+                if (audio) {
+                    frame_at = sl.segment.size();
+                    feeder_gate_append(f, sl, fp, flen, sl.segment);
+                }
+                if (sl.payload == CVAD_PAYLOAD_FRAMES) {
+                    const size_t o = f->frame_pool.size();
+                    f->frame_pool.insert(f->frame_pool.end(), sl.segment.begin() + (ptrdiff_t)frame_at, sl.segment.end());
+                    d.frame = f->frame_pool.data() + o;
+                    d.frame_len = flen;
+                    emit = true;
+                }
+                if (b & CVAD_FLAG_ENDED) {
+                    f->done_segments.emplace_back();
+                    f->done_segments.back().swap(sl.segment);
+                    sl.segment.clear();
+                    d.segment = f->done_segments.back().data();
+                    d.segment_len = (int64_t)f->done_segments.back().size();
+                    sl.active = false;
+                    emit = true;
+                }
+            }
+            if (emit) f->deliveries.push_back(d);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int cvad_feeder_create(cvad_engine *e, int max_streams, int pcm_format, int frame_len, int hop, int src_rate,
+                       int capacity_frames, cvad_feeder **out) {
+    if (!out) return CVAD_E_INVALID;
+    *out = nullptr;
+    if (e) max_streams = e->max_streams;
+    if (max_streams < 1) return fail(e, CVAD_E_INVALID, "feeder: max_streams < 1");
+    if (pcm_format < 0 || pcm_format > 2) return fail(e, CVAD_E_INVALID, "feeder: unknown pcm_format");
+    if (src_rate != 0 && src_rate != 16000) {
+        if (rate_index(src_rate) < 0) return fail(e, CVAD_E_INVALID, "feeder: src_rate must be 0, 8000, 16000, 24000 or 48000");
+        frame_len = hop = rate_n_in(src_rate);
+    }
+    if (src_rate == 0) frame_len = hop = rate_n_in(48000);      // arena sizing; per-slot chunk sizes in Slot::n_in
+    if (frame_len < 1 || frame_len > 2048 || hop < 1) return fail(e, CVAD_E_INVALID, "feeder: frame_len outside [1, 2048] or hop < 1");
+    if (capacity_frames < 2) capacity_frames = 8;
+    cvad_feeder *f = new cvad_feeder();
+    f->eng = e;
+    f->max_streams = max_streams;
+    f->pcm_format = pcm_format;
+    f->frame_len = frame_len;
+    f->hop = hop;
+    f->src_rate = src_rate;
+    f->es = pcm_format == CVAD_PCM_F32 ? 4 : 2;
+    f->max_step_frames = capacity_frames;
+    f->cap = (size_t)frame_len + (size_t)(capacity_frames + 1) * (size_t)std::max(hop, frame_len);
+    f->cap += (-(int64_t)f->cap) & 7;
+    const size_t bytes = (size_t)max_streams * f->cap * f->es;
+    if (e) {
+        cudaSetDevice(e->device);
+        void *p = nullptr;
+        if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            delete f;
+            return fail(e, CVAD_E_CUDA, "feeder: cudaMallocHost of the stream arena failed");
+        }
+        f->arena = static_cast<unsigned char *>(p);
+    } else {
+        f->arena = static_cast<unsigned char *>(std::malloc(bytes));
+        if (!f->arena) { delete f; return CVAD_E_CAPACITY; }
+    }
+    f->slot.resize((size_t)max_streams);
+    f->fill.assign((size_t)max_streams, 0);
+    const unsigned hw = std::thread::hardware_concurrency();
+    f->threads = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    *out = f;
+    return CVAD_OK;
+}
+
+int cvad_feeder_destroy(cvad_feeder *f) {
+    if (!f) return CVAD_OK;
+    for (int w = 0; w < 2; ++w)
+        if (f->stage[w]) { if (f->eng) cudaFreeHost(f->stage[w]); else std::free(f->stage[w]); }
+    if (f->arena) { if (f->eng) cudaFreeHost(f->arena); else std::free(f->arena); }
+    delete f;
+    return CVAD_OK;
+}
+
+const char *cvad_feeder_last_error(const cvad_feeder *f) { return f ? f->err.c_str() : ""; }
+
+int cvad_feeder_open(cvad_feeder *f, int slot, int src_rate, int payload, double vad_start_probability,
+                     int enable_denoising) {
+    if (!f) return CVAD_E_INVALID;
+    if (slot < 0 || slot >= f->max_streams) return ffail(f, CVAD_E_CAPACITY, "slot id out of range");
+    if (payload < CVAD_PAYLOAD_NONE || payload > CVAD_PAYLOAD_FRAMES) return ffail(f, CVAD_E_INVALID, "unknown payload mode");
+    if (src_rate == 0) src_rate = f->src_rate ? f->src_rate : 16000;
+    if (f->src_rate == 0) {
+        if (src_rate != 16000 && rate_index(src_rate) < 0)
+            return ffail(f, CVAD_E_INVALID, "sample_rate must be 8000, 16000, 24000 or 48000");
+    } else if (src_rate != f->src_rate) {
+        return ffail(f, CVAD_E_INVALID, "this feeder takes one source rate for all streams");
+    }
+    std::lock_guard<std::mutex> lk(f->mu);
+    cvad_feeder::Slot &s = f->slot[slot];
+    s.open = true;
+    s.rate = src_rate;
+    s.n_in = rate_n_in(src_rate);
+    s.payload = payload;
+    s.denoise = enable_denoising != 0;
+    s.start_p = vad_start_probability;
+    s.active = false;
+    s.skip = 0;
+    s.pre_roll.clear();
+    s.segment.clear();
+    f->fill[slot] = 0;
+    return CVAD_OK;
+}
+
+int cvad_feeder_close(cvad_feeder *f, int slot) {
+    if (!f) return CVAD_E_INVALID;
+    if (slot < 0 || slot >= f->max_streams) return ffail(f, CVAD_E_CAPACITY, "slot id out of range");
+    std::lock_guard<std::mutex> lk(f->mu);
+    cvad_feeder::Slot &s = f->slot[slot];
+    s.open = false;
+    s.active = false;
+    std::vector<float>().swap(s.pre_roll);
+    std::vector<float>().swap(s.segment);
+    f->fill[slot] = 0;
+    return CVAD_OK;
+}
+
+int cvad_feeder_clear(cvad_feeder *f, int slot) {
+    if (!f) return CVAD_E_INVALID;
+    if (slot < 0 || slot >= f->max_streams) return ffail(f, CVAD_E_CAPACITY, "slot id out of range");
+    std::lock_guard<std::mutex> lk(f->mu);
+    cvad_feeder::Slot &s = f->slot[slot];
+    s.active = false;
+    s.skip = 0;
+    s.pre_roll.clear();
+    s.segment.clear();
+    f->fill[slot] = 0;
+    return CVAD_OK;
+}
+
+int cvad_feeder_is_active(cvad_feeder *f, int slot) {
+    if (!f || slot < 0 || slot >= f->max_streams) return CVAD_E_INVALID;
+    return f->slot[slot].active ? 1 : 0;
+}
+
+int64_t cvad_feeder_pending(cvad_feeder *f, int slot) {
+    if (!f || slot < 0 || slot >= f->max_streams) return CVAD_E_INVALID;
+    std::lock_guard<std::mutex> lk(f->mu);
+    return f->fill[slot];
+}
+
+// Rows grow (all of them: the arena stays one rectangular pinned block) when a producer runs ahead of step().
+static int feeder_grow_arena(cvad_feeder *f, int64_t need) {
+    if (need <= (int64_t)f->cap) return CVAD_OK;
+    size_t cap = std::max<size_t>((size_t)need, 2 * f->cap);
+    cap += (-(int64_t)cap) & 7;
+    const size_t bytes = (size_t)f->max_streams * cap * f->es;
+    if (bytes > kFeederArenaLimit)
+        return ffail(f, CVAD_E_CAPACITY, "stream buffer full: step() the feeder before pushing more audio");
+    unsigned char *p = nullptr;
+    if (f->eng) {
+        void *q = nullptr;
+        if (cudaMallocHost(&q, bytes) != cudaSuccess) { cudaGetLastError(); return ffail(f, CVAD_E_CUDA, "cudaMallocHost failed"); }
+        p = static_cast<unsigned char *>(q);
+    } else {
+        p = static_cast<unsigned char *>(std::malloc(bytes));
+        if (!p) return ffail(f, CVAD_E_CAPACITY, "out of host memory");
+    }
+    for (int s = 0; s < f->max_streams; ++s)
+        if (f->fill[s] > 0)
+            std::memcpy(p + (size_t)s * cap * f->es, f->arena + (size_t)s * f->cap * f->es, (size_t)f->fill[s] * f->es);
+    if (f->eng) cudaFreeHost(f->arena); else std::free(f->arena);
+    f->arena = p;
+    f->cap = cap;
+    return CVAD_OK;
+}
+
+static int feeder_push_locked(cvad_feeder *f, int slot, const void *samples, int64_t n) {
+    cvad_feeder::Slot &s = f->slot[slot];
+    if (!s.open) return ffail(f, CVAD_E_INVALID, "stream is not open");
+    if (s.skip > 0) {
+        const int64_t d = std::min(s.skip, n);
+        samples = static_cast<const unsigned char *>(samples) + (size_t)d * f->es;
+        n -= d;
+        s.skip -= d;
+        if (n == 0) return CVAD_OK;
+    }
+    const int64_t have = f->fill[slot];
+    if (have + n > (int64_t)f->cap) {
+        const int rc = feeder_grow_arena(f, have + n);
+        if (rc) return rc;
+    }
+    std::memcpy(f->arena + ((size_t)slot * f->cap + (size_t)have) * f->es, samples, (size_t)n * f->es);
+    f->fill[slot] = have + n;
+    return CVAD_OK;
+}
+
+static bool feeder_all_finite(const float *x, int64_t n) {
+    // AudioUtils.validate_audio_data (audio.py:227-228): exponent all ones <=> NaN or Inf
+    const uint32_t *u = reinterpret_cast<const uint32_t *>(x);
+    uint32_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) bad |= ((u[i] & 0x7f800000u) == 0x7f800000u);
+    return bad == 0;
+}
+
+int cvad_feeder_push(cvad_feeder *f, int slot, const void *samples, int64_t n_samples) {
+    if (!f) return CVAD_E_INVALID;
+    if (slot < 0 || slot >= f->max_streams) return ffail(f, CVAD_E_CAPACITY, "slot id out of range");
+    if (!samples || n_samples <= 0) return ffail(f, CVAD_E_INVALID, "Audio data is empty");
+    if (f->pcm_format == CVAD_PCM_F32 && !feeder_all_finite(static_cast<const float *>(samples), n_samples))
+        return ffail(f, CVAD_E_INVALID, "Audio data contains infinite or NaN values");
+    std::lock_guard<std::mutex> lk(f->mu);
+    return feeder_push_locked(f, slot, samples, n_samples);
+}
+
+int cvad_feeder_push_many(cvad_feeder *f, int n, const int32_t *slots, const void *block, int64_t row_stride,
+                          int64_t n_samples) {
+    if (!f) return CVAD_E_INVALID;
+    if (n < 0 || !slots) return ffail(f, CVAD_E_INVALID, "push_many: bad slot list");
+    if (!block || n_samples <= 0) return ffail(f, CVAD_E_INVALID, "Audio data is empty");
+    if (row_stride < n_samples) return ffail(f, CVAD_E_INVALID, "push_many: row_stride < n_samples");
+    const unsigned char *b = static_cast<const unsigned char *>(block);
+    for (int i = 0; i < n; ++i) {
+        if (slots[i] < 0 || slots[i] >= f->max_streams) return ffail(f, CVAD_E_CAPACITY, "slot id out of range");
+        if (f->pcm_format == CVAD_PCM_F32 &&
+            !feeder_all_finite(reinterpret_cast<const float *>(b + (size_t)i * (size_t)row_stride * f->es), n_samples))
+            return ffail(f, CVAD_E_INVALID, "Audio data contains infinite or NaN values");
+    }
+    std::lock_guard<std::mutex> lk(f->mu);
+    int64_t need = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!f->slot[slots[i]].open) return ffail(f, CVAD_E_INVALID, "push_many: a stream is not open");
+        need = std::max(need, f->fill[slots[i]] + n_samples);
+    }
+    if (const int rc = feeder_grow_arena(f, need)) return rc;
+    for (int i = 0; i < n; ++i)
+        feeder_push_locked(f, slots[i], b + (size_t)i * (size_t)row_stride * f->es, n_samples);
+    return CVAD_OK;
+}
+
+static void feeder_fill_result(cvad_feeder *f, cvad_feeder_result *r) {
+    std::memset(r, 0, sizeof(*r));
+    const int n = (int)f->ids.size();
+    r->n_streams = n;
+    r->max_frames = f->tmax;
+    int64_t tot = 0;
+    for (int k = 0; k < n; ++k) tot += f->counts[k];
+    r->n_frames_total = tot;
+    r->slots = f->ids.data();
+    r->counts = f->counts.data();
+    r->probs = f->probs.data();
+    r->flags = f->flags.data();
+    r->n_events = (int32_t)f->events.size();
+    r->events = f->events.data();
+    r->n_deliveries = (int32_t)f->deliveries.size();
+    r->deliveries = f->deliveries.data();
+    r->raw = f->stage[f->cur];
+    r->raw_stride = f->row;
+}
+
+int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *r) {
+    if (!f || !r) return CVAD_E_INVALID;
+    if (!f->eng) return ffail(f, CVAD_E_NOGPU, "feeder has no engine: there is no CPU fallback");
+    int rc = feeder_gather(f);
+    if (rc) return rc;
+    const int n = (int)f->ids.size(), T = f->tmax;
+    f->events.clear();
+    f->probs.assign((size_t)n * T, 0.f);
+    f->flags.assign((size_t)n * T, 0);
+    f->status.assign((size_t)n, 0);
+    if (n > 0) {
+        const int max_events = std::max(16, 2 * n * T);
+        f->events.resize((size_t)max_events);
+        int nev = 0;
+        cvad_step_args a{};
+        a.n_streams = n;
+        a.slots = f->ids.data();
+        a.audio = f->stage[f->cur];
+        a.pcm_format = f->pcm_format;
+        a.stream_stride = f->row;
+        a.n_frames = f->counts.data();
+        a.max_frames = T;
+        a.frame_len = f->frame_len;
+        a.hop = f->hop;
+        a.src_rate = f->src_rate ? f->src_rate : 16000;
+        a.src_rates = f->src_rate == 0 ? f->rates.data() : nullptr;
+        a.probs_out = f->probs.data();
+        a.flags_out = f->flags.data();
+        a.status_out = f->status.data();
+        a.events_out = f->events.data();
+        a.max_events = max_events;
+        a.n_events_out = &nev;
+        rc = cvad_step(f->eng, &a);
+        if (rc) { f->events.clear(); return ffail(f, rc, cvad_last_error(f->eng)); }
+        f->events.resize((size_t)std::min(nev, max_events));
+        for (int k = 0; k < n; ++k)
+            if (f->status[k]) {   // cannot happen through cvad_feeder_push (it validates), kept for raw arena writers
+                f->events.clear();
+                return ffail(f, CVAD_E_INVALID, "Audio data contains infinite or NaN values");
+            }
+    }
+    feeder_deliver(f);
+    feeder_fill_result(f, r);
+    return CVAD_OK;
+}
+
+/* Test hooks for hosts without a GPU: the two host phases of cvad_feeder_step on their own. */
+int cvad_feeder_gather_only(cvad_feeder *f, cvad_feeder_result *r) {
+    if (!f || !r) return CVAD_E_INVALID;
+    int rc = feeder_gather(f);
+    if (rc) return rc;
+    const int n = (int)f->ids.size(), T = f->tmax;
+    f->events.clear();
+    f->deliveries.clear();
+    f->probs.assign((size_t)n * T, 0.f);
+    f->flags.assign((size_t)n * T, 0);
+    feeder_fill_result(f, r);
+    return CVAD_OK;
+}
+
+int cvad_feeder_deliver_only(cvad_feeder *f, const float *probs, const uint8_t *flags, cvad_feeder_result *r) {
+    if (!f || !r || !probs || !flags) return CVAD_E_INVALID;
+    const int n = (int)f->ids.size(), T = f->tmax;
+    f->probs.assign(probs, probs + (size_t)n * T);
+    f->flags.assign(flags, flags + (size_t)n * T);
+    feeder_deliver(f);
+    feeder_fill_result(f, r);
+    return CVAD_OK;
+}
+
+}  // extern "C"

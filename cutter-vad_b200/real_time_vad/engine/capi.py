@@ -19,6 +19,7 @@ PCM_F32, PCM_S16_32767, PCM_S16_32768 = 0, 1, 2
 FLAG_STARTED, FLAG_ENDED, FLAG_CONTINUING = 1, 2, 4
 STATUS_NONFINITE = 1
 MATH_FP32, MATH_TC = 0, 1
+PAYLOAD_NONE, PAYLOAD_EVENTS, PAYLOAD_SEGMENTS, PAYLOAD_FRAMES = 0, 1, 2, 3
 
 EXPORTS = (
     "cvad_abi_version", "cvad_device_count", "cvad_last_error", "cvad_create", "cvad_destroy",
@@ -26,6 +27,9 @@ EXPORTS = (
     "cvad_step", "cvad_step_submit", "cvad_step_collect", "cvad_step_device", "cvad_sync", "cvad_launch_count", "cvad_debug_dump",
     "cvad_alloc_pinned", "cvad_free_pinned", "cvad_set_timing", "cvad_read_timing", "cvad_resample_matrix", "cvad_tc_probe", "cvad_tc_rate", "cvad_bulk_rate",
     "cvad_set_math", "cvad_get_math", "cvad_set_profile", "cvad_read_profile",
+    "cvad_feeder_create", "cvad_feeder_destroy", "cvad_feeder_last_error", "cvad_feeder_open", "cvad_feeder_close",
+    "cvad_feeder_clear", "cvad_feeder_is_active", "cvad_feeder_pending", "cvad_feeder_push", "cvad_feeder_push_many",
+    "cvad_feeder_step", "cvad_feeder_gather_only", "cvad_feeder_deliver_only",
 )
 
 
@@ -54,6 +58,19 @@ class StepArgs(C.Structure):
         ("n_events_out", C.c_void_p),
         ("src_rates", C.c_void_p),
     ]
+
+
+class Delivery(C.Structure):
+    _fields_ = [("slot", C.c_int32), ("stream", C.c_int32), ("step_frame", C.c_int32), ("flags", C.c_int32),
+                ("frame", C.c_void_p), ("segment", C.c_void_p), ("segment_len", C.c_int64),
+                ("frame_len", C.c_int32), ("prob", C.c_float), ("raw", C.c_void_p), ("raw_len", C.c_int64)]
+
+
+class FeederResult(C.Structure):
+    _fields_ = [("n_streams", C.c_int32), ("max_frames", C.c_int32), ("n_frames_total", C.c_int64),
+                ("slots", C.c_void_p), ("counts", C.c_void_p), ("probs", C.c_void_p), ("flags", C.c_void_p),
+                ("n_events", C.c_int32), ("n_deliveries", C.c_int32), ("events", C.c_void_p),
+                ("deliveries", C.c_void_p), ("raw", C.c_void_p), ("raw_stride", C.c_int64)]
 
 
 _lib = None
@@ -107,5 +124,20 @@ def lib() -> C.CDLL:
     L.cvad_free_pinned.argtypes = [vp]
     L.cvad_set_timing.argtypes = [vp, i32]
     L.cvad_read_timing.argtypes = [vp, vp, vp, vp]
+    L.cvad_feeder_create.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.POINTER(vp)]
+    L.cvad_feeder_destroy.argtypes = [vp]
+    L.cvad_feeder_last_error.restype = C.c_char_p
+    L.cvad_feeder_last_error.argtypes = [vp]
+    L.cvad_feeder_open.argtypes = [vp, i32, i32, i32, dbl, i32]
+    L.cvad_feeder_close.argtypes = [vp, i32]
+    L.cvad_feeder_clear.argtypes = [vp, i32]
+    L.cvad_feeder_is_active.argtypes = [vp, i32]
+    L.cvad_feeder_pending.restype = i64
+    L.cvad_feeder_pending.argtypes = [vp, i32]
+    L.cvad_feeder_push.argtypes = [vp, i32, vp, i64]
+    L.cvad_feeder_push_many.argtypes = [vp, i32, vp, vp, i64, i64]
+    L.cvad_feeder_step.argtypes = [vp, C.POINTER(FeederResult)]
+    L.cvad_feeder_gather_only.argtypes = [vp, C.POINTER(FeederResult)]
+    L.cvad_feeder_deliver_only.argtypes = [vp, vp, vp, C.POINTER(FeederResult)]
     _lib = L
     return L

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define CVAD_ABI_VERSION 2
+#define CVAD_ABI_VERSION 3
 
 /* error codes */
 #define CVAD_OK 0
@@ -229,6 +229,100 @@ int cvad_read_timing(cvad_engine *e, double *frontend_ms, double *recurrent_ms, 
  * to `dbg_out` (host).  Layout in DESIGN.md ("debug dump").  Returns floats written.
  */
 int cvad_debug_dump(cvad_engine *e, const cvad_step_args *a, float *dbg_out, size_t dbg_floats);
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stream feeder (ABI 3): the host half of the service mode, in native code.
+ *
+ * The reference's websocket server keeps one VADWrapper per client and runs one model call per message on the
+ * event loop (websocket_service/server/vad_websocket_server.py:248-290, :326-369).  A feeder keeps every
+ * client's pending samples in ONE pinned arena (a row per slot); cvad_feeder_push appends a message,
+ * cvad_feeder_step frames whatever is complete (AudioUtils.split_into_frames, src/real_time_vad/utils/audio.py:164-190,
+ * leftovers carried), runs ONE cvad_step over all of those streams, and replays the callback side of VADProcessor
+ * from the device's per-frame flags: the pre-roll buffered since the first above-threshold frame, the voice segment
+ * handed to voice_end, the gated frame handed to voice_continue
+ * (src/real_time_vad/core/silero_model.py:839-869, :891-895, :925-949; vad_wrapper.py:498-519).
+ *
+ * Threading: cvad_feeder_push / push_many may be called from any thread, also while a step runs.
+ * open / close / clear / step: one thread at a time.  Pointers in cvad_feeder_result stay valid until the next
+ * cvad_feeder_step on the same feeder.
+ */
+typedef struct cvad_feeder cvad_feeder;
+
+/* what a stream wants back besides probabilities and events */
+#define CVAD_PAYLOAD_NONE 0      /* nothing: only the voice-active mirror is kept */
+#define CVAD_PAYLOAD_EVENTS 1    /* a delivery record on the frames that start / end a voice segment */
+#define CVAD_PAYLOAD_SEGMENTS 2  /* + the gated float32 samples of the finished segment on the end record */
+#define CVAD_PAYLOAD_FRAMES 3    /* + a record with the gated float32 frame for every frame while voice is active */
+
+typedef struct cvad_delivery {
+    int32_t slot;            /* engine slot id */
+    int32_t stream;          /* row of this stream in the step (index into slots / counts / probs / raw) */
+    int32_t step_frame;      /* frame index inside this step */
+    int32_t flags;           /* CVAD_FLAG_* of the frame */
+    const float *frame;      /* CVAD_PAYLOAD_FRAMES: the gated 16 kHz frame handed to voice_continue, else NULL */
+    const float *segment;    /* on CVAD_FLAG_ENDED with CVAD_PAYLOAD_SEGMENTS/FRAMES: the finished segment, else NULL */
+    int64_t segment_len;     /* samples in `segment` */
+    int32_t frame_len;       /* samples in `frame` */
+    float prob;              /* the frame's speech probability */
+    const void *raw;         /* streams whose source rate is not 16 kHz and that want audio: the frame's source-rate
+                                samples in the feeder's PCM format (the host resamples its payloads); a record is
+                                then produced for EVERY frame and frame / segment stay NULL */
+    int64_t raw_len;
+} cvad_delivery;
+
+typedef struct cvad_feeder_result {
+    int32_t n_streams;                 /* streams that ran at least one frame */
+    int32_t max_frames;                /* row length of probs / flags */
+    int64_t n_frames_total;
+    const int32_t *slots;              /* [n_streams] */
+    const int32_t *counts;             /* [n_streams] frames run per stream */
+    const float *probs;                /* [n_streams][max_frames]; columns >= counts[k] are 0 */
+    const uint8_t *flags;              /* [n_streams][max_frames] */
+    int32_t n_events;
+    int32_t n_deliveries;
+    const cvad_event *events;          /* stream-then-frame order */
+    const cvad_delivery *deliveries;   /* stream-then-frame order */
+    const void *raw;                   /* the block that was stepped: [n_streams][raw_stride] samples, PCM format of the feeder */
+    int64_t raw_stride;
+} cvad_feeder_result;
+
+/* e == NULL builds a feeder for the gather / deliver test hooks only (max_streams is then taken from the argument,
+   otherwise from the engine).  src_rate 0 = every stream has its own rate (cvad_feeder_open), frame_len / hop are then
+   ignored; src_rate 8000 / 24000 / 48000 fixes frame_len = hop = 512*src_rate/16000.  capacity_frames = frames a stream
+   runs per step at most (>= 2; a stream further behind catches up over several steps) and the initial row size;
+   rows grow when a producer runs ahead of step(). */
+int cvad_feeder_create(cvad_engine *e, int max_streams, int pcm_format, int frame_len, int hop, int src_rate,
+                       int capacity_frames, cvad_feeder **out);
+int cvad_feeder_destroy(cvad_feeder *f);
+const char *cvad_feeder_last_error(const cvad_feeder *f);
+
+/* Start / restart buffering for a slot (pending samples and any half-built segment are dropped).  The engine side of a
+   stream (cvad_reset, cvad_configure) is the caller's; vad_start_probability and enable_denoising are needed here
+   because the pre-roll starts at the first frame whose probability reaches the start threshold and payloads are gated
+   like the model input (silero_model.py:832-845, :782-783).  src_rate 0 = the feeder's. */
+int cvad_feeder_open(cvad_feeder *f, int slot, int src_rate, int payload, double vad_start_probability,
+                     int enable_denoising);
+int cvad_feeder_close(cvad_feeder *f, int slot);
+int cvad_feeder_clear(cvad_feeder *f, int slot);          /* VADProcessor.reset: drop pending samples and segment */
+int cvad_feeder_is_active(cvad_feeder *f, int slot);      /* host mirror of is_voice_active: 1 / 0 */
+int64_t cvad_feeder_pending(cvad_feeder *f, int slot);    /* samples buffered */
+
+/* Append samples (feeder's PCM format) to a slot.  float32 input containing NaN / Inf is rejected here, before any
+   state changes (AudioUtils.validate_audio_data, audio.py:227-228).  CVAD_E_CAPACITY when the arena cannot grow further. */
+int cvad_feeder_push(cvad_feeder *f, int slot, const void *samples, int64_t n_samples);
+/* block[i*row_stride .. +n_samples) is appended to slots[i]; all or nothing. */
+int cvad_feeder_push_many(cvad_feeder *f, int n, const int32_t *slots, const void *block, int64_t row_stride,
+                          int64_t n_samples);
+
+/* Frame, step and deliver (see above). */
+int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *out);
+
+/* Test hooks for hosts without a GPU: the two host phases of cvad_feeder_step on their own.  gather_only frames
+   and compacts (probs / flags read as 0); deliver_only replays the callback side for the gathered streams from
+   caller-supplied probs / flags [n_streams][max_frames]. */
+int cvad_feeder_gather_only(cvad_feeder *f, cvad_feeder_result *out);
+int cvad_feeder_deliver_only(cvad_feeder *f, const float *probs, const uint8_t *flags, cvad_feeder_result *out);
 
 #ifdef __cplusplus
 }

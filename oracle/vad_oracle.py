@@ -385,3 +385,34 @@ def events_from_flags(flags: Sequence[int]) -> List[Tuple[int, str]]:
         if f & 2:
             ev.append((i, "E"))
     return ev
+
+
+class VoiceBuffer:
+    """The audio side of VADProcessor, restated literally: `voice_buffer` (pre-roll of above-threshold frames,
+    silero_model.py:839, cleared at :874), `current_voice_data` (:867-869 on start, :925-930 while active) and
+    `_finalize_voice_segment` (:932-949).  Fed the gated frame, its probability and the state machine's flags of
+    that frame; returns (segment handed to voice_end or None, frame handed to voice_continue or None)."""
+
+    def __init__(self, start_p: float):
+        self.start_p = start_p
+        self.active = False
+        self.voice_buffer: List[np.ndarray] = []
+        self.current: Optional[np.ndarray] = None
+
+    def step(self, frame: np.ndarray, probability: float, flags: int):
+        if not self.active:
+            if probability >= self.start_p:
+                self.voice_buffer.append(frame.copy())
+                if flags & 1:
+                    self.active = True
+                    if self.voice_buffer:
+                        self.current = np.concatenate(self.voice_buffer)
+                    self.voice_buffer = []
+            else:
+                self.voice_buffer = []
+            return None, None
+        self.current = frame.copy() if self.current is None else np.concatenate([self.current, frame])
+        seg = None
+        if flags & 2:
+            seg, self.current, self.active = self.current, None, False
+        return seg, frame
