@@ -51,6 +51,8 @@ struct cvad_engine {
     bool v4_t2 = false;                // CVAD_MODEL_V4_8K: two LSTM time steps per frame
     bool fuse_single_frame = true;     // CVAD_FUSE=0 keeps the two-kernel form for one-frame steps (measurement)
     unsigned char *w_fe_tc = nullptr, *w_rec_tc = nullptr;
+    unsigned char *w_fe_h = nullptr, *w_rec_h = nullptr;   // CVAD_MATH_TC16: two FP16 parts, per-layer scale
+    float tc16_inv_w[8] = {0};
     float *nyq_w = nullptr, *b_rec_tc = nullptr;
     DevBuf d_feat_tc;
     DevBuf d_v4_mag;                   // v4 tensor-core path: |STFT| tiles between the two front-end kernels
@@ -284,6 +286,87 @@ V5TcPacked pack_v5_tc(const float *blob) {
         for (int t = 0; t < 3; ++t) P.nyq_w[o * 4 + t] = e0w[(o * 129 + 128) * 3 + t];
     P.b_rec.resize(512);
     for (int n = 0; n < 512; ++n) P.b_rec[n] = bih[n] + bhh[n];
+    return P;
+}
+
+// ---- v5 FP16-split repack (CVAD_MATH_TC16): the same tile order with TWO FP16 parts per weight, every layer scaled
+// by the power of two that brings its largest weight to [2^14, 2^15) (inverse returned in inv_w: stft, enc0..3, W_ih, W_hh)
+struct V5HPacked {
+    std::vector<unsigned char> w_fe, w_rec;
+    float inv_w[8] = {0};
+};
+
+template <typename F>
+void emit_tiles_h(std::vector<unsigned char> &out, int rows, int k0, float scale, F W) {
+    const size_t tile = (size_t)rows * 128;
+    const size_t at = out.size();
+    out.resize(at + 2 * tile, 0);
+    for (int r = 0; r < rows; ++r)
+        for (int kk = 0; kk < 64; ++kk) {
+            float x = W(r, k0 + kk) * scale;
+            const size_t off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((((kk >> 3) ^ r) & 7) << 4) + (size_t)(kk & 7) * 2;
+            for (int part = 0; part < 2; ++part) {
+                const __half h = __float2half_rn(x);
+                const unsigned short b = __half_as_ushort(h);
+                std::memcpy(&out[at + part * tile + off], &b, 2);
+                x -= __half2float(h);
+            }
+        }
+}
+
+float pow2_scale_for(float maxabs, float *inv) {
+    if (!(maxabs > 0.f)) { *inv = 1.f; return 1.f; }
+    int ex;
+    std::frexp(maxabs, &ex);                 // maxabs = m * 2^ex, m in [0.5, 1)  ->  maxabs in [2^(ex-1), 2^ex)
+    const float s = std::ldexp(1.0f, 15 - ex);
+    *inv = std::ldexp(1.0f, ex - 15);
+    return s;
+}
+
+V5HPacked pack_v5_tc16(const float *blob) {
+    const float *basis = blob;                       // [258][256]
+    const float *e0w = basis + 258 * 256;            // [128][129][3]
+    const float *e0b = e0w + 128 * 129 * 3;
+    const float *e1w = e0b + 128;                    // [64][128][3]
+    const float *e1b = e1w + 64 * 128 * 3;
+    const float *e2w = e1b + 64;                     // [64][64][3]
+    const float *e2b = e2w + 64 * 64 * 3;
+    const float *e3w = e2b + 64;                     // [128][64][3]
+    const float *e3b = e3w + 128 * 64 * 3;
+    const float *wih = e3b + 128;                    // [512][128]
+    const float *whh = wih + 512 * 128;
+    auto maxabs = [](const float *w, size_t n) { float m = 0.f; for (size_t i = 0; i < n; ++i) m = std::max(m, std::fabs(w[i])); return m; };
+    V5HPacked P;
+    const float s_stft = pow2_scale_for(maxabs(basis, 258 * 256), &P.inv_w[0]);
+    const float s_e0 = pow2_scale_for(maxabs(e0w, 128 * 129 * 3), &P.inv_w[1]);
+    const float s_e1 = pow2_scale_for(maxabs(e1w, 64 * 128 * 3), &P.inv_w[2]);
+    const float s_e2 = pow2_scale_for(maxabs(e2w, 64 * 64 * 3), &P.inv_w[3]);
+    const float s_e3 = pow2_scale_for(maxabs(e3w, 128 * 64 * 3), &P.inv_w[4]);
+    const float s_ih = pow2_scale_for(maxabs(wih, 512 * 128), &P.inv_w[5]);
+    const float s_hh = pow2_scale_for(maxabs(whh, 512 * 128), &P.inv_w[6]);
+    P.w_fe.reserve(cvad::tc5::kFeStreamBytesH);
+    for (int blk = 0; blk < 2; ++blk)
+        for (int kb = 0; kb < 4; ++kb)
+            emit_tiles_h(P.w_fe, 128, kb * 64, s_stft, [&](int m, int k) {
+                const int row = blk == 0 ? m : (m == 0 ? 128 : 129 + m);
+                return basis[row * 256 + k];
+            });
+    static const int taps0[3] = {1, 0, 2}, taps1[3] = {1, 2, 0};
+    for (int kb = 0; kb < 2; ++kb)
+        for (int ti = 0; ti < 3; ++ti)
+            emit_tiles_h(P.w_fe, 128, kb * 64, s_e0, [&](int o, int c) { return e0w[(o * 129 + c) * 3 + taps0[ti]]; });
+    for (int kb = 0; kb < 2; ++kb)
+        for (int ti = 0; ti < 3; ++ti)
+            emit_tiles_h(P.w_fe, 64, kb * 64, s_e1, [&](int o, int c) { return e1w[(o * 128 + c) * 3 + taps1[ti]]; });
+    for (int tap = 1; tap <= 2; ++tap)
+        emit_tiles_h(P.w_fe, 64, 0, s_e2, [&](int o, int c) { return e2w[(o * 64 + c) * 3 + tap]; });
+    emit_tiles_h(P.w_fe, 128, 0, s_e3, [&](int o, int c) { return e3w[(o * 64 + c) * 3 + 1]; });
+    for (int g = 0; g < 4; ++g)
+        for (int kb = 0; kb < 4; ++kb)
+            emit_tiles_h(P.w_rec, 128, kb * 64, kb < 2 ? s_ih : s_hh, [&](int u, int k) {
+                const int row = g * 128 + u;
+                return k < 128 ? wih[row * 128 + k] : whh[row * 128 + (k - 128)];
+            });
     return P;
 }
 
@@ -523,7 +606,7 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         r.n_streams = a->n_streams; r.n_stiles = n_stiles; r.max_frames = a->max_frames; r.n_frames = a->n_frames;
         r.out = static_cast<float *>(e->d_res.p);
         const int grid_rs = std::min(a->max_frames * n_stiles, e->num_sms);
-        const bool rs_tc = e->math == CVAD_MATH_TC;
+        const bool rs_tc = e->math != CVAD_MATH_FP32;
         const int grid_rs_tc = std::min(a->max_frames * ((a->n_streams + cvad::tc5::kRsTcTile - 1) / cvad::tc5::kRsTcTile),
                                         e->num_sms);
         if (!mixed) {
@@ -609,7 +692,7 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
     p.dbg = d_dbg;
     p.v4_t2 = e->v4_t2 ? 1 : 0;
 
-    if (e->version == CVAD_MODEL_V5 && e->math == CVAD_MATH_TC) {
+    if (e->version == CVAD_MODEL_V5 && e->math != CVAD_MATH_FP32) {
         if ((rc = grow(e, e->d_feat_tc, (size_t)a->max_frames * n_stiles * cvad::tc5::kFeatTileBytes))) return rc;
         p.w_fe_tc = e->w_fe_tc; p.w_rec_tc = e->w_rec_tc; p.nyq_w = e->nyq_w; p.b_rec_tc = e->b_rec_tc;
         p.feat_tc = static_cast<unsigned char *>(e->d_feat_tc.p);
@@ -617,7 +700,13 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         const int grid = std::min(a->max_frames * n_stiles, e->num_sms);
         if (a->max_frames == 1 && !d_dbg && e->fuse_single_frame) {
             // one frame per stream: front end + LSTM step + state machine in ONE kernel (no hand-off, no second launch)
-            cvad::tc5::v5tc_frontend_kernel<false, true><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFusedSmemTC, stream>>>(p);
+            if (e->math == CVAD_MATH_TC16) {
+                p.w_fe_h = e->w_fe_h; p.w_rec_h = e->w_rec_h;
+                std::memcpy(p.tc16_inv_w, e->tc16_inv_w, sizeof(p.tc16_inv_w));
+                cvad::tc5::v5tc_frontend_kernel<false, true, true><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFusedSmemTC, stream>>>(p);
+            } else {
+                cvad::tc5::v5tc_frontend_kernel<false, true><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFusedSmemTC, stream>>>(p);
+            }
             CU_TRY(e, cudaGetLastError());
             e->launches++;
             if (timed) {   // the whole step is the "front-end" interval, the "recurrent" interval is empty
@@ -992,6 +1081,8 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
                                 (int)cvad::tc5::kFeSmemTC));
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kFusedSmemTC));
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::tc5::kFusedSmemTC));
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kRecSmemTC));
     if (model_version == CVAD_MODEL_V5) {
@@ -1004,8 +1095,18 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
         if ((rc = upload(e, &e->w_fe_tc, T.w_fe)) || (rc = upload(e, &e->w_rec_tc, T.w_rec)) ||
             (rc = upload(e, &e->nyq_w, T.nyq_w)) || (rc = upload(e, &e->b_rec_tc, T.b_rec)))
             return bail(rc);
+        {
+            V5HPacked H = pack_v5_tc16(weights);
+            if (H.w_fe.size() != cvad::tc5::kFeStreamBytesH || H.w_rec.size() != cvad::tc5::kRecStreamBytesH) {
+                e->err = "internal: FP16 weight stream has the wrong size";
+                return bail(CVAD_E_WEIGHTS);
+            }
+            if ((rc = upload(e, &e->w_fe_h, H.w_fe)) || (rc = upload(e, &e->w_rec_h, H.w_rec))) return bail(rc);
+            std::memcpy(e->tc16_inv_w, H.inv_w, sizeof(e->tc16_inv_w));
+        }
         const char *m = std::getenv("CVAD_MATH");
-        e->math = (m && std::strcmp(m, "fp32") == 0) ? CVAD_MATH_FP32 : CVAD_MATH_TC;
+        e->math = (m && std::strcmp(m, "fp32") == 0) ? CVAD_MATH_FP32
+                  : (m && std::strcmp(m, "tc16") == 0) ? CVAD_MATH_TC16 : CVAD_MATH_TC;
         const char *fz = std::getenv("CVAD_FUSE");
         e->fuse_single_frame = !(fz && std::strcmp(fz, "0") == 0);
     }
@@ -1062,7 +1163,7 @@ int cvad_destroy(cvad_engine *e) {
     void *ptrs[] = {e->w_fe, e->b_fe, e->w_rec, e->b_rec, e->w_dec, e->h_state, e->c_state, e->sm_active,
                     e->sm_scount, e->sm_ecount, e->frames_done, e->start_p, e->end_p, e->n_start, e->n_end,
                     e->denoise, e->d_status_dev.p, e->d_feat.p, e->d_dbg.p, e->d_cfg_slots.p, e->d_res.p,
-                    e->rs_rt[0], e->rs_rt[1], e->rs_rt[2], e->w_fe_tc, e->w_rec_tc, e->nyq_w, e->b_rec_tc,
+                    e->rs_rt[0], e->rs_rt[1], e->rs_rt[2], e->w_fe_tc, e->w_rec_tc, e->w_fe_h, e->w_rec_h, e->nyq_w, e->b_rec_tc,
                     e->d_feat_tc.p, e->d_prof, e->d_rate_lists.p, e->d_v4_mag.p, e->rs_tc[0], e->rs_tc[1], e->rs_tc[2]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1085,7 +1186,10 @@ int cvad_destroy(cvad_engine *e) {
 
 int cvad_set_math(cvad_engine *e, int math) {
     if (!e) return CVAD_E_INVALID;
-    if (math != CVAD_MATH_FP32 && math != CVAD_MATH_TC) return fail(e, CVAD_E_INVALID, "math must be CVAD_MATH_FP32 or CVAD_MATH_TC");
+    if (math != CVAD_MATH_FP32 && math != CVAD_MATH_TC && math != CVAD_MATH_TC16)
+        return fail(e, CVAD_E_INVALID, "math must be CVAD_MATH_FP32, CVAD_MATH_TC or CVAD_MATH_TC16");
+    if (math == CVAD_MATH_TC16 && e->version != CVAD_MODEL_V5)
+        return fail(e, CVAD_E_INVALID, "CVAD_MATH_TC16 exists for the v5 model only");
     e->math = math;
     return CVAD_OK;
 }

@@ -109,6 +109,10 @@ struct V5Step {
     const float *nyq_w;           // [128][4]: encoder.0 weight of input channel 128, taps 0..2
     const float *b_rec_tc;        // [4][128] gate-major (i,f,g,o), b_ih + b_hh
     unsigned char *feat_tc;       // [max_frames * n_stiles][tc5::kFeatTileBytes]
+    // FP16-split build of the fused kernel (CVAD_MATH_TC16): weight tile streams with two FP16 parts, scaled per layer
+    const unsigned char *w_fe_h;
+    const unsigned char *w_rec_h;
+    float tc16_inv_w[8];          // 1 / weight scale of: stft, encoder.0..3, W_ih, W_hh
     long long *prof;              // optional clock64 marks of CTA 0 (cvad_set_profile), or null
     int v4_t2;                    // v4 8 kHz sub-model: two time steps reach the LSTM per frame
     float *v4_mag;                // v4 tensor-core path: |STFT| tiles [tile][129][8][16] written by v4tc_stft_kernel, or null

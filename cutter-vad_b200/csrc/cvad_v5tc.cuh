@@ -26,6 +26,7 @@
 // strictly sequential, so ONE activation region is reused in place from layer to layer.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "cvad_tc.cuh"
 #include "cvad_v5.cuh"
@@ -70,7 +71,7 @@ constexpr uint32_t kMagKb = 12288;
 constexpr uint32_t kE1Part = 8192;           // E1: 64 rows x 64 K
 constexpr uint32_t kE2Part = 4096;           // E2: 32 rows x 64 K
 constexpr size_t kFeSmemTC = 1024 + kActBytes + (size_t)kFeRing * kSlotBytes + 96 * 4 + (2 * kFeRing + 2) * 8 + 16 +
-                             2 * kTile * 4 + 64;
+                             3 * kTile * 4 + 64;
 // fused single-frame kernel (max_frames == 1): the front end plus the LSTM step of the same 32 streams in one CTA.
 // ACT | H operand (24 KB) | ring (6 slots) | nyq | decoder partials | barriers | meta.  Weight stream per tile:
 // 24 W_hh tiles (issued while the loader runs), the 69 front-end tiles, 24 W_ih tiles.
@@ -78,7 +79,7 @@ constexpr int kFusedRing = 6;
 constexpr int kFusedSlotsPerTile = 24 + kFeSlotsPerTile + 24;
 constexpr uint32_t kColGate = 384;           // TMEM columns 384 + 32 g: gate g (i,f,g,o), one accumulator per gate
 constexpr size_t kFusedSmemTC = 1024 + kActBytes + 24576 + (size_t)kFusedRing * kSlotBytes + 96 * 4 + 128 * 4 +
-                                (2 * kFusedRing + 3) * 8 + 16 + 2 * kTile * 4 + kTile * 16 + 64;
+                                (2 * kFusedRing + 3) * 8 + 16 + 2 * kTile * 4 + kTile * 16 + 7 * kTile * 4 + 64;
 // feature hand-off (front end -> recurrent), per (frame, stream tile): the x half of the recurrent B operand,
 // byte for byte: [kb 0..1][row = part*32 + item (96 rows)][128 B], SW128
 constexpr uint32_t kFeatTileBytes = 2 * 12288;
@@ -236,6 +237,97 @@ __device__ __forceinline__ void issue_gate(int wp, uint32_t a_addr, uint32_t b0,
     }
 }
 
+// ---------------------------------------------------------------- FP16 two-way split (CVAD_MATH_TC16, fused kernel only)
+// x = x0 + x1 with x0 = fp16(s x), x1 = fp16(s x - x0): 22 significant bits once the operand is scaled by a power
+// of two s that brings its largest element to [2^14, 2^15) -- per STREAM for activations (so that a stream's
+// result does not depend on its neighbours in the batch), per layer for weights (host, pack_v5_tc16).  Three
+// products per MAC (w0.x0 + w0.x1 + w1.x0; the dropped w1.x1 is 2^-22 relative) instead of the BF16 split's six:
+// same FP32-level accuracy (tools/tc_split_sim.py: fp16x3 1e-6 vs bf16x6 5e-7 vs plain FP32 1.3e-6 on the
+// probability), half the tensor-pipe and shared-memory-port time.  Elements far below the row maximum fall into
+// FP16's subnormal range and keep an ABSOLUTE error of 2^-25 of the scaled unit, i.e. 2^-39 of the maximum.
+struct Scale { float s, inv; };
+// scale for an operand whose largest magnitude has the float bit pattern `max_bits` (non-negative)
+__device__ __forceinline__ Scale scale_from_max(uint32_t max_bits) {
+    const uint32_t E = max_bits >> 23;
+    Scale r;
+    if (E == 0u) { r.s = 1.f; r.inv = 1.f; return r; }       // all zero (or subnormal): nothing to scale
+    uint32_t se = 268u - E;                                    // 2^(14 - (E - 127)), biased
+    se = se > 252u ? 252u : se;
+    r.s = __uint_as_float(se << 23);
+    r.inv = __uint_as_float((254u - se) << 23);
+    return r;
+}
+constexpr float kHScale = 16384.f, kHInv = 1.f / 16384.f;     // |h| < 1: static scale of the recurrent operand
+// two values at once: word j holds part j of a (low half) and of b (high half)
+__device__ __forceinline__ void split2x2_h(float a, float b, uint32_t &w0, uint32_t &w1) {
+    const __half2 h0 = __floats2half2_rn(a, b);
+    const float2 f0 = __half22float2(h0);
+    const __half2 h1 = __floats2half2_rn(a - f0.x, b - f0.y);
+    w0 = *reinterpret_cast<const uint32_t *>(&h0);
+    w1 = *reinterpret_cast<const uint32_t *>(&h1);
+}
+// store the two parts of (already scaled) values a (row) and b (row + 1) at column k of a B operand with R rows
+__device__ __forceinline__ void store_parts2_h(unsigned char *base, uint32_t ps, uint32_t row, uint32_t k, uint32_t R, float a, float b) {
+    uint32_t w0, w1;
+    split2x2_h(a, b, w0, w1);
+    unsigned char *da = base + tc::sw128_offset(row, k, R);
+    unsigned char *db = base + tc::sw128_offset(row + 1, k, R);
+    *reinterpret_cast<unsigned short *>(da) = (unsigned short)w0;
+    *reinterpret_cast<unsigned short *>(da + ps) = (unsigned short)w1;
+    *reinterpret_cast<unsigned short *>(db) = (unsigned short)(w0 >> 16);
+    *reinterpret_cast<unsigned short *>(db + ps) = (unsigned short)(w1 >> 16);
+}
+// per-stream maximum of non-negative values held one per lane: warp maximum -> shared atomic
+__device__ __forceinline__ void amax_push(uint32_t *slot, float v, int lane) {
+    const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(v));
+    if (lane == 0 && m != 0u) atomicMax(slot, m);
+}
+// instruction descriptor, kind::f16: D = F32, A = B = FP16
+__host__ __device__ constexpr uint32_t idesc_f16_f32(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// front-end weight stream of the FP16 build: the BF16 stream's order with two parts per tile group (46 tiles)
+constexpr int kFeSlotsPerTileH = 46;
+constexpr size_t kFeStreamBytesH = 28 * 16384 + 16 * 8192 + 2 * 16384;
+__host__ __device__ __forceinline__ void fe_slot_h(int s, uint32_t &off, uint32_t &bytes) {
+    if (s < 28) { off = (uint32_t)s * 16384u; bytes = 16384u; }
+    else if (s < 44) { off = 28u * 16384u + (uint32_t)(s - 28) * 8192u; bytes = 8192u; }
+    else { off = 28u * 16384u + 16u * 8192u + (uint32_t)(s - 44) * 16384u; bytes = 16384u; }
+}
+constexpr size_t kRecStreamBytesH = (size_t)32 * 16384;       // gate x kb 0..3 x part 0..1
+constexpr int kFusedSlotsPerTileH = 16 + kFeSlotsPerTileH + 16;
+constexpr uint32_t kColIh = 0;                                // TMEM columns of the W_ih . x accumulators (free after encoder.3)
+// MMAs of one weight tile (part wp) for one 64-element K block, FP16 split: w0.x0 -> d_main, w0.x1 and w1.x0 -> d_corr
+__device__ __forceinline__ void issue_split_h(int wp, uint32_t a_addr, uint32_t b0, uint32_t ps, uint32_t d_main,
+                                              uint32_t d_corr, uint32_t idesc, bool first) {
+    const uint64_t ad = tc::smem_desc_sw128(a_addr);
+    const uint64_t bd0 = tc::smem_desc_sw128(b0), bd1 = tc::smem_desc_sw128(b0 + ps);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t fresh = (first && ks == 0) ? 0u : 1u;
+        if (wp == 0) {
+            tc::mma_bf16(d_corr, ad + ks * 2, bd1 + ks * 2, idesc, fresh);
+            tc::mma_bf16(d_main, ad + ks * 2, bd0 + ks * 2, idesc, fresh);
+        } else {
+            tc::mma_bf16(d_corr, ad + ks * 2, bd0 + ks * 2, idesc, 1u);
+        }
+    }
+}
+// LSTM gate products, FP16 split: all three products of a MAC go to one accumulator; parts 4096 B apart
+__device__ __forceinline__ void issue_gate_h(int wp, uint32_t a_addr, uint32_t b0, uint32_t d, uint32_t idesc, bool first) {
+    const uint64_t ad = tc::smem_desc_sw128(a_addr);
+    const uint64_t bd0 = tc::smem_desc_sw128(b0), bd1 = tc::smem_desc_sw128(b0 + 4096u);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        if (wp == 0) {
+            tc::mma_bf16(d, ad + ks * 2, bd1 + ks * 2, idesc, (first && ks == 0) ? 0u : 1u);
+            tc::mma_bf16(d, ad + ks * 2, bd0 + ks * 2, idesc, 1u);
+        } else {
+            tc::mma_bf16(d, ad + ks * 2, bd0 + ks * 2, idesc, 1u);
+        }
+    }
+}
+
 struct Ring {
     uint32_t buf;        // shared address of slot 0
     uint64_t *full;      // [n]
@@ -247,9 +339,12 @@ struct Ring {
 // =====================================================================================
 // FUSED (max_frames == 1): the same CTA also runs the LSTM step, decoder and state machine of its 32 streams
 // (the W_hh.h products are issued while the frame loader runs, the W_ih.x products after encoder.3).
-template <bool DBG, bool FUSED>
+// H16 (CVAD_MATH_TC16, FUSED only): FP16 two-way operand split with per-stream dynamic scaling, three products per MAC.
+template <bool DBG, bool FUSED, bool H16 = false>
 __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5Step p) {
+    static_assert(!H16 || (FUSED && !DBG), "the FP16 split exists for the fused single-frame kernel only");
     constexpr int RING = FUSED ? kFusedRing : kFeRing;
+    constexpr int NP = H16 ? 2 : 3;                   // operand parts
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     unsigned char *act = base;
@@ -264,6 +359,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     int *s_slot = reinterpret_cast<int *>(tmem_slot + 4);
     int *s_valid = s_slot + kTile;
     double *s_thr = reinterpret_cast<double *>(s_valid + kTile);             // FUSED: start_p[32], end_p[32]
+    uint32_t *amax = reinterpret_cast<uint32_t *>(s_thr + 2 * kTile);        // H16: [6][32] per-stream maxima (bit patterns) of AUD, MAG, E0, E1, E2, X
+    int *s_dn = FUSED ? reinterpret_cast<int *>(amax + 6 * kTile) : s_valid + kTile;   // [32] per-stream denoise flag (fetched with the slot ids)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     CVAD_PROF_NS(120);
@@ -295,11 +392,34 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
             if (!tile_live(p, frame, st, lane, nullptr, nullptr)) continue;
             if (lane == 0) {
-                for (int s = 0; s < (FUSED ? kFusedSlotsPerTile : kFeSlotsPerTile); ++s, ++g) {
+                for (int s = 0; s < (H16 ? kFusedSlotsPerTileH : FUSED ? kFusedSlotsPerTile : kFeSlotsPerTile); ++s, ++g) {
                     const uint32_t slot = g % RING;
                     mbar_wait(&empty[slot], ((g / RING) & 1u) ^ 1u);
                     uint32_t off, bytes;
                     const unsigned char *src;
+                    if (H16) {
+                        // same order with two parts: hh gate g = 4 tiles | STFT 16 | enc0 12 | enc1 12 | enc2 + enc3 6 | W_ih 16
+                        int fe_idx = s, gate = -1, kb = 0, part = 0;
+                        if (s < 4) { gate = 0; kb = 2 + s / 2; part = s % 2; }
+                        else if (s < 20) fe_idx = s - 4;
+                        else if (s < 24) { gate = 1; kb = 2 + (s - 20) / 2; part = (s - 20) % 2; }
+                        else if (s < 36) fe_idx = s - 24 + 16;
+                        else if (s < 40) { gate = 2; kb = 2 + (s - 36) / 2; part = (s - 36) % 2; }
+                        else if (s < 52) fe_idx = s - 40 + 28;
+                        else if (s < 56) { gate = 3; kb = 2 + (s - 52) / 2; part = (s - 52) % 2; }
+                        else if (s < 62) fe_idx = s - 56 + 40;
+                        else { const int r = s - 62; gate = r / 4; kb = (r / 2) % 2; part = r % 2; }
+                        if (gate >= 0) {
+                            src = p.w_rec_h + (size_t)((gate * 4 + kb) * 2 + part) * kSlotBytes;
+                            bytes = kSlotBytes;
+                        } else {
+                            fe_slot_h(fe_idx, off, bytes);
+                            src = p.w_fe_h + off;
+                        }
+                        mbar_arrive_expect_tx(&full[slot], bytes);
+                        bulk_g2s(ring_buf + slot * kSlotBytes, src, bytes, &full[slot]);
+                        continue;
+                    }
                     // FUSED order: hh gate 0 | STFT (24) | hh gate 1 | enc0 (18) | hh gate 2 | enc1 (18) | hh gate 3 |
                     //              enc2 + enc3 (9) | W_ih of the four gates (24).  hh gate g = 6 tiles (K blocks 2,3 x part)
                     int fe_idx = s, gate = -1, kb = 0, part = 0;
@@ -330,9 +450,22 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------ MMA issuer
         uint32_t g = 0, act_phase = 0, h_phase = 0;
-        const uint32_t i128_96 = tc::idesc_bf16_f32(128, 96), i128_64 = tc::idesc_bf16_f32(128, 64),
-                       i128_32 = tc::idesc_bf16_f32(128, 32), i64_64 = tc::idesc_bf16_f32(64, 64),
-                       i64_32 = tc::idesc_bf16_f32(64, 32);
+        const uint32_t i128_96 = H16 ? idesc_f16_f32(128, 96) : tc::idesc_bf16_f32(128, 96),
+                       i128_64 = H16 ? idesc_f16_f32(128, 64) : tc::idesc_bf16_f32(128, 64),
+                       i128_32 = H16 ? idesc_f16_f32(128, 32) : tc::idesc_bf16_f32(128, 32),
+                       i64_64 = H16 ? idesc_f16_f32(64, 64) : tc::idesc_bf16_f32(64, 64),
+                       i64_32 = H16 ? idesc_f16_f32(64, 32) : tc::idesc_bf16_f32(64, 32);
+        // one weight tile of part WP against the activation parts that pair with it (BF16: 3 / 2 / 1 products, FP16: 2 / 1)
+#define CVAD_SPLIT(WP, B0, PS, DM, DC, IDESC, FIRST)                                   \
+    do {                                                                               \
+        if (H16) issue_split_h(WP, a_addr, B0, PS, DM, DC, IDESC, FIRST);              \
+        else issue_split(WP, a_addr, B0, PS, DM, DC, IDESC, FIRST);                    \
+    } while (0)
+#define CVAD_GATE(WP, B0, D, IDESC, FIRST)                                             \
+    do {                                                                               \
+        if (H16) issue_gate_h(WP, a_addr, B0, D, IDESC, FIRST);                        \
+        else issue_gate(WP, a_addr, B0, D, IDESC, FIRST);                              \
+    } while (0)
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
             if (!tile_live(p, frame, st, lane, nullptr, nullptr)) continue;
@@ -355,8 +488,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
 #define CVAD_TC_HH(G)                                                                                              \
     if (FUSED) {                                                                                                   \
         for (int kb = 0; kb < 2; ++kb)                                                                             \
-            for (int wp = 0; wp < 3; ++wp)                                                                         \
-                CVAD_TC_SLOT(issue_gate(wp, a_addr, h_s + kb * kXhKb, kColGate + 32 * (G), i128_32, kb == 0 && wp == 0)) \
+            for (int wp = 0; wp < NP; ++wp)                                                                         \
+                CVAD_TC_SLOT(CVAD_GATE(wp, h_s + kb * kXhKb, kColGate + 32 * (G), i128_32, kb == 0 && wp == 0)) \
     }
             if (FUSED) {
                 mbar_wait(h_ready, h_phase); h_phase ^= 1u;
@@ -370,8 +503,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             tc::fence_after_sync();
             for (int blk = 0; blk < 2; ++blk)
                 for (int kb = 0; kb < 4; ++kb)
-                    for (int wp = 0; wp < 3; ++wp)
-                        CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + (kb & 1) * 16384u + (kb >> 1) * 4096u, kAudPart,
+                    for (int wp = 0; wp < NP; ++wp)
+                        CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s + (kb & 1) * 16384u + (kb >> 1) * 4096u, kAudPart,
                                                  kColMain + blk * 96, kColCorr + blk * 96, i128_96, kb == 0 && wp == 0))
             if (tc::elect_one()) tc::mma_commit(acc_ready);
             CVAD_TC_HH(1)
@@ -382,14 +515,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             CVAD_PROF(34);
             tc::fence_after_sync();
             for (int kb = 0; kb < 2; ++kb) {
-                for (int wp = 0; wp < 3; ++wp)
-                    CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + kb * kMagKb, kMagPart, kColMain, kColCorr, i128_96,
+                for (int wp = 0; wp < NP; ++wp)
+                    CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s + kb * kMagKb, kMagPart, kColMain, kColCorr, i128_96,
                                              kb == 0 && wp == 0))
-                for (int wp = 0; wp < 3; ++wp)
-                    CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + kb * kMagKb, kMagPart, kColMain + 32, kColCorr + 32,
+                for (int wp = 0; wp < NP; ++wp)
+                    CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s + kb * kMagKb, kMagPart, kColMain + 32, kColCorr + 32,
                                              i128_64, false))
-                for (int wp = 0; wp < 3; ++wp)
-                    CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + kb * kMagKb + 32 * 128, kMagPart, kColMain, kColCorr,
+                for (int wp = 0; wp < NP; ++wp)
+                    CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s + kb * kMagKb + 32 * 128, kMagPart, kColMain, kColCorr,
                                              i128_64, false))
             }
             if (tc::elect_one()) tc::mma_commit(acc_ready);
@@ -402,14 +535,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             CVAD_PROF(36);
             tc::fence_after_sync();
             for (int kb = 0; kb < 2; ++kb) {
-                for (int wp = 0; wp < 3; ++wp)
-                    CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + kb * kMagKb, kMagPart, kColMain, kColCorr, i64_64,
+                for (int wp = 0; wp < NP; ++wp)
+                    CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s + kb * kMagKb, kMagPart, kColMain, kColCorr, i64_64,
                                              kb == 0 && wp == 0))
-                for (int wp = 0; wp < 3; ++wp)
-                    CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + kb * kMagKb + 64 * 128, kMagPart, kColMain, kColCorr,
+                for (int wp = 0; wp < NP; ++wp)
+                    CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s + kb * kMagKb + 64 * 128, kMagPart, kColMain, kColCorr,
                                              i64_32, false))
-                for (int wp = 0; wp < 3; ++wp)
-                    CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + kb * kMagKb + 64 * 128, kMagPart, kColMain + 32,
+                for (int wp = 0; wp < NP; ++wp)
+                    CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s + kb * kMagKb + 64 * 128, kMagPart, kColMain + 32,
                                              kColCorr + 32, i64_32, false))
             }
             if (tc::elect_one()) tc::mma_commit(acc_ready);
@@ -420,10 +553,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             mbar_wait(act_ready, act_phase); act_phase ^= 1u;
             CVAD_PROF(38);
             tc::fence_after_sync();
-            for (int wp = 0; wp < 3; ++wp)
-                CVAD_TC_SLOT(issue_split(wp, a_addr, act_s, kE1Part, kColMain, kColCorr, i64_32, wp == 0))
-            for (int wp = 0; wp < 3; ++wp)
-                CVAD_TC_SLOT(issue_split(wp, a_addr, act_s + 32 * 128, kE1Part, kColMain, kColCorr, i64_32, false))
+            for (int wp = 0; wp < NP; ++wp)
+                CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s, kE1Part, kColMain, kColCorr, i64_32, wp == 0))
+            for (int wp = 0; wp < NP; ++wp)
+                CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s + 32 * 128, kE1Part, kColMain, kColCorr, i64_32, false))
             if (tc::elect_one()) tc::mma_commit(acc_ready);
             CVAD_PROF(39);
             __syncwarp();
@@ -431,8 +564,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             mbar_wait(act_ready, act_phase); act_phase ^= 1u;
             CVAD_PROF(40);
             tc::fence_after_sync();
-            for (int wp = 0; wp < 3; ++wp)
-                CVAD_TC_SLOT(issue_split(wp, a_addr, act_s, kE2Part, kColMain, kColCorr, i128_32, wp == 0))
+            for (int wp = 0; wp < NP; ++wp)
+                CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s, kE2Part, kColMain, kColCorr, i128_32, wp == 0))
             if (tc::elect_one()) tc::mma_commit(acc_ready);
             CVAD_PROF(41);
             __syncwarp();
@@ -443,14 +576,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 CVAD_PROF(43);
                 for (int gate = 0; gate < 4; ++gate)
                     for (int kb = 0; kb < 2; ++kb)
-                        for (int wp = 0; wp < 3; ++wp)
-                            CVAD_TC_SLOT(issue_gate(wp, a_addr, act_s + kb * kXhKb, kColGate + 32 * gate, i128_32, false))
+                        for (int wp = 0; wp < NP; ++wp)
+                            CVAD_TC_SLOT(CVAD_GATE(wp, act_s + kb * kXhKb, (H16 ? kColIh : kColGate) + 32 * gate, i128_32, H16 && kb == 0 && wp == 0))
                 if (tc::elect_one()) tc::mma_commit(acc_ready);
                 CVAD_PROF(44);
                 __syncwarp();
             }
 #undef CVAD_TC_HH
 #undef CVAD_TC_SLOT
+#undef CVAD_SPLIT
+#undef CVAD_GATE
         }
     } else {
         // ------------------------------------------------------------ loader + epilogue warps
@@ -465,8 +600,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             if (warp == 0) {
                 s_slot[lane] = my_slot;
                 s_valid[lane] = my_valid;
+                s_dn[lane] = my_slot >= 0 ? (int)p.denoise[my_slot] : 0;
                 if (FUSED && my_slot >= 0) { s_thr[lane] = p.start_p[my_slot]; s_thr[kTile + lane] = p.end_p[my_slot]; }
             }
+            if (H16 && warp >= 1 && warp <= 6) amax[(warp - 1) * kTile + lane] = 0u;
             epi_bar();
             const bool dbg = DBG && tile == 0;
             const bool first_tile = tile == (int)blockIdx.x && tid == 0;
@@ -529,8 +666,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
 #pragma unroll
                 for (int e = 0; e < 8; ++e) hreg[e] = sbuf[u_own * 33 + i_own + e];
 #pragma unroll
-                for (int e = 0; e < 8; e += 2)
-                    store_parts2(hbuf, 32 * 128, (uint32_t)(i_own + e), (uint32_t)u_own, 96u, hreg[e], hreg[e + 1]);
+                for (int e = 0; e < 8; e += 2) {
+                    if (H16) store_parts2_h(hbuf, 32 * 128, (uint32_t)(i_own + e), (uint32_t)u_own, 96u, hreg[e] * kHScale, hreg[e + 1] * kHScale);
+                    else store_parts2(hbuf, 32 * 128, (uint32_t)(i_own + e), (uint32_t)u_own, 96u, hreg[e], hreg[e + 1]);
+                }
                 epi_bar();
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -553,7 +692,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     const int unit = u4 * kEpiThreads + tid;
                     const int s = unit >> 6, c8 = unit & 63;
                     if (ok[u4]) {
-                        const bool dn = p.denoise[s_slot[s]] != 0;
+                        const bool dn = s_dn[s] != 0;
                         bool bad = false;
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
@@ -566,6 +705,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                         }
                         if (bad && p.status) atomicOr(&p.status[st * kTile + s], 1u);
                     }
+                    if (H16) continue;
                     uint32_t w[3][4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) split3x2(v[u4][2 * e], v[u4][2 * e + 1], w[0][e], w[1][e], w[2][e]);
@@ -574,6 +714,35 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
 #pragma unroll
                     for (int part = 0; part < 3; ++part)
                         *reinterpret_cast<uint4 *>(act + part * kAudPart + off) = make_uint4(w[part][0], w[part][1], w[part][2], w[part][3]);
+                }
+                if (H16) {
+                    CVAD_PROF(20);
+                    // per-stream maximum of the gated frame (a unit's stream is warp-uniform: s = 8 u4 + tid / 64) ...
+#pragma unroll
+                    for (int u4 = 0; u4 < 4; ++u4) {
+                        float m = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) m = fmaxf(m, fabsf(v[u4][e]));
+                        amax_push(&amax[u4 * 8 + (tid >> 6)], m, lane);
+                    }
+                    CVAD_PROF(15);
+                    epi_bar();
+                    CVAD_PROF(16);
+                    // ... then scale, split into two FP16 parts, store
+#pragma unroll
+                    for (int u4 = 0; u4 < 4; ++u4) {
+                        const int unit = u4 * kEpiThreads + tid;
+                        const int s = unit >> 6, c8 = unit & 63;
+                        const float sc = scale_from_max(amax[s]).s;
+                        uint32_t w[2][4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) split2x2_h(v[u4][2 * e] * sc, v[u4][2 * e + 1] * sc, w[0][e], w[1][e]);
+                        const uint32_t seg = (uint32_t)c8 >> 4, kk = ((uint32_t)c8 & 15u) * 8u;
+                        const uint32_t off = tc::sw128_offset(seg * 32u + (uint32_t)s, kk, 128u);
+#pragma unroll
+                        for (int part = 0; part < 2; ++part)
+                            *reinterpret_cast<uint4 *>(act + part * kAudPart + off) = make_uint4(w[part][0], w[part][1], w[part][2], w[part][3]);
+                    }
                 }
             }
             tc::fence_async_smem();
@@ -585,7 +754,49 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
             CVAD_PROF(2);
             tc::fence_after_sync();
-            {
+            if (H16) {
+                // a thread owns bin b of streams 8 cg .. 8 cg + 7 at all three time columns: one scale per stream
+                const int b = 32 * q + lane, i0 = 8 * cg;
+                const float iw = p.tc16_inv_w[0];
+                float inv[8], mag[3][8], mx[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { inv[e] = scale_from_max(amax[i0 + e]).inv * iw; mx[e] = 0.f; }
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int c0 = t * 32 + i0;
+                    float mr[8], mi[8], cr[8], ci[8];
+                    tmem_ld8(lane_addr + kColMain + c0, mr);
+                    tmem_ld8(lane_addr + kColMain + 96 + c0, mi);
+                    tmem_ld8(lane_addr + kColCorr + c0, cr);
+                    tmem_ld8(lane_addr + kColCorr + 96 + c0, ci);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float re = (mr[e] + cr[e]) * inv[e];
+                        float im = (mi[e] + ci[e]) * inv[e];
+                        if (b == 0) {
+                            nyq[c0 + e] = fabsf(im);           // sqrt(x*x + 0*0)
+                            im = 0.f;
+                        }
+                        mag[t][e] = sfu_sqrt(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+                        mx[e] = fmaxf(mx[e], mag[t][e]);
+                    }
+                }
+#pragma unroll
+                CVAD_PROF(17);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) amax_push(&amax[kTile + i0 + e], mx[e], lane);
+                CVAD_PROF(18);
+                epi_bar();
+                CVAD_PROF(19);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) inv[e] = scale_from_max(amax[kTile + i0 + e]).s;
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2)
+                        store_parts2_h(act, kMagPart, (uint32_t)(t * 32 + i0 + e), (uint32_t)b, 96u, mag[t][e] * inv[e], mag[t][e + 1] * inv[e + 1]);
+            } else {
                 const int b = 32 * q + lane;   // bin; TMEM lane b of block 1 holds im[b] (b >= 1) or re[128] (b == 0)
 #pragma unroll 1
                 for (int ch = 0; ch < 3; ++ch) {
@@ -624,7 +835,44 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
             CVAD_PROF(4);
             tc::fence_after_sync();
-            {
+            if (H16) {
+                const int o = 32 * q + lane, i0 = 8 * cg;
+                const float bias = __ldg(p.b_fe + o), iw = p.tc16_inv_w[1];
+                const float wn0 = __ldg(p.nyq_w + 4 * o), wn1 = __ldg(p.nyq_w + 4 * o + 1), wn2 = __ldg(p.nyq_w + 4 * o + 2);
+                float sc[8], v[3][8], mx[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { sc[e] = scale_from_max(amax[kTile + i0 + e]).inv * iw; mx[e] = 0.f; }
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int c0 = t * 32 + i0;
+                    float m[8], cr[8];
+                    tmem_ld8(lane_addr + kColMain + c0, m);
+                    tmem_ld8(lane_addr + kColCorr + c0, cr);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int i = i0 + e;
+                        float a = (m[e] + cr[e]) * sc[e];
+                        if (t > 0) a = fmaf(wn0, nyq[(t - 1) * 32 + i], a);
+                        a = fmaf(wn1, nyq[t * 32 + i], a);
+                        if (t < 2) a = fmaf(wn2, nyq[(t + 1) * 32 + i], a);
+                        v[t][e] = fmaxf(a + bias, 0.f);
+                        mx[e] = fmaxf(mx[e], v[t][e]);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) amax_push(&amax[2 * kTile + i0 + e], mx[e], lane);
+                epi_bar();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sc[e] = scale_from_max(amax[2 * kTile + i0 + e]).s;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const uint32_t rb = t == 0 ? 0u : (t == 1 ? 64u : 32u);
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2)
+                        store_parts2_h(act, kMagPart, rb + (uint32_t)(i0 + e), (uint32_t)o, 96u, v[t][e] * sc[e], v[t][e + 1] * sc[e + 1]);
+                }
+            } else {
                 const int o = 32 * q + lane;
                 const float bias = __ldg(p.b_fe + o);
                 const float wn0 = __ldg(p.nyq_w + 4 * o), wn1 = __ldg(p.nyq_w + 4 * o + 1), wn2 = __ldg(p.nyq_w + 4 * o + 2);
@@ -661,7 +909,39 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
             CVAD_PROF(6);
             tc::fence_after_sync();
-            {
+            if (H16) {
+                const int o = 16 * q + (lane & 15), i0 = 8 * cg;
+                const float bias = __ldg(p.b_fe + 128 + o), iw = p.tc16_inv_w[2];
+                float sc[8], v[2][8], mx[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { sc[e] = scale_from_max(amax[2 * kTile + i0 + e]).inv * iw; mx[e] = 0.f; }
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int c0 = t * 32 + i0;
+                    float m[8], cr[8];
+                    tmem_ld8(lane_addr + kColMain + c0, m);
+                    tmem_ld8(lane_addr + kColCorr + c0, cr);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float a = fmaxf((m[e] + cr[e]) * sc[e] + bias, 0.f);
+                        v[t][e] = lane < 16 ? a : 0.f;
+                        mx[e] = fmaxf(mx[e], v[t][e]);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) amax_push(&amax[3 * kTile + i0 + e], mx[e], lane);
+                epi_bar();
+                if (lane < 16) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) sc[e] = scale_from_max(amax[3 * kTile + i0 + e]).s;
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2)
+                            store_parts2_h(act, kE1Part, (uint32_t)(t * 32 + i0 + e), (uint32_t)o, 64u, v[t][e] * sc[e], v[t][e + 1] * sc[e + 1]);
+                }
+            } else {
                 const int o = 16 * q + (lane & 15);
                 const float bias = __ldg(p.b_fe + 128 + o);
 #pragma unroll 1
@@ -692,7 +972,28 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
             CVAD_PROF(8);
             tc::fence_after_sync();
-            {
+            if (H16) {
+                const int o = 16 * q + (lane & 15);
+                const float bias = __ldg(p.b_fe + 192 + o), iw = p.tc16_inv_w[3];
+                const int c0 = cg * 8;
+                float m[8], cr[8], v[8];
+                tmem_ld8(lane_addr + kColMain + c0, m);
+                tmem_ld8(lane_addr + kColCorr + c0, cr);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float a = fmaxf((m[e] + cr[e]) * (scale_from_max(amax[3 * kTile + c0 + e]).inv * iw) + bias, 0.f);
+                    v[e] = lane < 16 ? a : 0.f;
+                    amax_push(&amax[4 * kTile + c0 + e], v[e], lane);
+                }
+                epi_bar();
+                if (lane < 16) {
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2)
+                        store_parts2_h(act, kE2Part, (uint32_t)(c0 + e), (uint32_t)o, 32u, v[e] * scale_from_max(amax[4 * kTile + c0 + e]).s,
+                                       v[e + 1] * scale_from_max(amax[4 * kTile + c0 + e + 1]).s);
+                }
+            } else {
                 const int o = 16 * q + (lane & 15);
                 const float bias = __ldg(p.b_fe + 192 + o);
                 const int c0 = cg * 8;
@@ -720,7 +1021,26 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
             CVAD_PROF(10);
             tc::fence_after_sync();
-            {
+            if (H16) {
+                const int o = 32 * q + lane;
+                const float bias = __ldg(p.b_fe + 256 + o), iw = p.tc16_inv_w[4];
+                const int c0 = cg * 8;
+                float m[8], cr[8], v[8];
+                tmem_ld8(lane_addr + kColMain + c0, m);
+                tmem_ld8(lane_addr + kColCorr + c0, cr);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    v[e] = fmaxf((m[e] + cr[e]) * (scale_from_max(amax[4 * kTile + c0 + e]).inv * iw) + bias, 0.f);
+                    amax_push(&amax[5 * kTile + c0 + e], v[e], lane);
+                }
+                tc::fence_before_sync();   // the W_ih accumulators reuse these TMEM columns
+                epi_bar();
+#pragma unroll
+                for (int e = 0; e < 8; e += 2)
+                    store_parts2_h(act, 32 * 128, (uint32_t)(c0 + e), (uint32_t)o, 96u, v[e] * scale_from_max(amax[5 * kTile + c0 + e]).s,
+                                   v[e + 1] * scale_from_max(amax[5 * kTile + c0 + e + 1]).s);
+            } else {
                 const int o = 32 * q + lane;
                 const float bias = __ldg(p.b_fe + 256 + o);
                 const int c0 = cg * 8;
@@ -762,6 +1082,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) tmem_ld8(lane_addr + kColGate + 32 * gi + i0, gate[gi]);
                 tmem_wait_ld();
+                if (H16) {
+                    // gate = W_hh.h (static scale) + W_ih.x (the stream's own scale), each in its own accumulator
+                    float gx[4][8];
+#pragma unroll
+                    for (int gi = 0; gi < 4; ++gi) tmem_ld8(lane_addr + kColIh + 32 * gi + i0, gx[gi]);
+                    tmem_wait_ld();
+                    const float ih_w = p.tc16_inv_w[5], hh = kHInv * p.tc16_inv_w[6];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float ix = scale_from_max(amax[5 * kTile + i0 + e]).inv * ih_w;
+#pragma unroll
+                        for (int gi = 0; gi < 4; ++gi) gate[gi][e] = fmaf(gx[gi][e], ix, gate[gi][e] * hh);
+                    }
+                }
                 float dv[8], hn[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {

@@ -18,7 +18,7 @@ MODEL_V5, MODEL_V4, MODEL_V4_8K = 5, 4, 48
 PCM_F32, PCM_S16_32767, PCM_S16_32768 = 0, 1, 2
 FLAG_STARTED, FLAG_ENDED, FLAG_CONTINUING = 1, 2, 4
 STATUS_NONFINITE = 1
-MATH_FP32, MATH_TC = 0, 1
+MATH_FP32, MATH_TC, MATH_TC16 = 0, 1, 2
 PAYLOAD_NONE, PAYLOAD_EVENTS, PAYLOAD_SEGMENTS, PAYLOAD_FRAMES = 0, 1, 2, 3
 
 EXPORTS = (

@@ -91,15 +91,16 @@ class StreamEngine:
 
     # ------------------------------------------------------------------ plumbing
     def set_math(self, math: str) -> None:
-        """'fp32' = packed FP32 FMA kernels; 'tc' = tcgen05 tensor cores with the 3-way BF16 split (v5 only)."""
-        code = {"fp32": capi.MATH_FP32, "tc": capi.MATH_TC}.get(math)
+        """'fp32' = packed FP32 FMA kernels; 'tc' = tcgen05 tensor cores with the 3-way BF16 split; 'tc16' (v5) = one-frame
+        steps with the 2-way FP16 split and per-stream scaling (3 products per MAC), other steps as 'tc'."""
+        code = {"fp32": capi.MATH_FP32, "tc": capi.MATH_TC, "tc16": capi.MATH_TC16}.get(math)
         if code is None:
             raise EngineError(capi.E_INVALID, f"unknown math mode {math!r}")
         self._check(self._L.cvad_set_math(self._h, code))
 
     @property
     def math(self) -> str:
-        return "tc" if self._L.cvad_get_math(self._h) == capi.MATH_TC else "fp32"
+        return {capi.MATH_TC: "tc", capi.MATH_TC16: "tc16"}.get(self._L.cvad_get_math(self._h), "fp32")
 
     def _check(self, rc: int) -> None:
         if rc < 0:

@@ -62,6 +62,8 @@ extern "C" {
    TC    = tcgen05 tensor cores, BF16 operands split three ways (6 products, FP32 accumulation in TMEM). */
 #define CVAD_MATH_FP32 0
 #define CVAD_MATH_TC 1
+#define CVAD_MATH_TC16 2   /* v5: one-frame steps (the fused kernel) use FP16 operands split two ways with per-stream
+                              power-of-two scaling, 3 products per MAC instead of 6; multi-frame steps run as CVAD_MATH_TC */
 
 /* audio sample formats accepted by cvad_step */
 #define CVAD_PCM_F32 0        /* float32 in [-1, 1] */

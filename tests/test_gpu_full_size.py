@@ -23,7 +23,7 @@ def workload(ref_v5):
     return base, audio, want
 
 
-@pytest.mark.parametrize("math", ["tc", "fp32"])
+@pytest.mark.parametrize("math", ["tc", "fp32", "tc16"])
 def test_4096_streams_one_frame_per_step(engine_factory, ref_lib, workload, math):
     from vad_oracle import sm_run_c
     base, audio, want = workload

@@ -11,10 +11,11 @@ from conftest import GOLDEN, synth_streams
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["tc", "fp32"])
+@pytest.fixture(autouse=True, params=["tc", "fp32", "tc16"])
 def math_mode(request, monkeypatch):
-    """Every test runs on both arithmetic paths of the v5 engine: tcgen05 tensor cores (BF16 3-way split) and
-    packed FP32 FMA.  cvad_create reads CVAD_MATH; engines are created inside the tests."""
+    """Every test runs on every arithmetic path of the v5 engine: tcgen05 tensor cores with the BF16 3-way split,
+    packed FP32 FMA, and the FP16 2-way split with per-stream scaling that one-frame steps take under "tc16" (its
+    multi-frame steps run as "tc").  cvad_create reads CVAD_MATH; engines are created inside the tests."""
     monkeypatch.setenv("CVAD_MATH", request.param)
     return request.param
 

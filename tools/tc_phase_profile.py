@@ -12,7 +12,7 @@ from conftest import synth_streams  # noqa: E402
 from real_time_vad.engine.stream_engine import StreamEngine  # noqa: E402
 
 n, T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096, int(sys.argv[2]) if len(sys.argv) > 2 else 1
-eng = StreamEngine(max_streams=n, math="tc")
+eng = StreamEngine(max_streams=n, math=sys.argv[3] if len(sys.argv) > 3 else "tc")
 x = np.tile(synth_streams(64, 512 * T, seed=1), (n // 64, 1))
 for _ in range(3):
     eng.step(x)
@@ -30,6 +30,9 @@ for i, nm in enumerate(names):
 print("front end, MMA warp: (act_ready seen, layer issued) x 5:", mm.tolist())
 if out[12]:
     print("fused: state loaded", out[12] - out[0], "| hh issued", out[42] - out[0], "| x ready", out[43] - out[0], "ih issued", out[44] - out[0], "| gates ready", out[13] - out[0], "cell done", out[14] - out[0])
+if out[15]:
+    print("tc16 marks: loader gated", out[20] - out[0], "amax pushed", out[15] - out[0], "barrier", out[16] - out[0],
+          "| stft computed", out[17] - out[0], "amax pushed", out[18] - out[0], "barrier", out[19] - out[0])
 r0 = out[64]
 print("recurrent epilogue: start 0, state loaded", out[65] - r0)
 for j in range(min(T, 8)):
