@@ -425,25 +425,28 @@ def run_ours(args):
     fe_tflops = frames_per_step * flop_fe / fe_avg_s / 1e12 if fe_avg_s > 0 else 0.0
     step_tflops = frames_per_step * flop_frame / (dev_ms / args.steps * 1e-3) / 1e12
 
-    fused = math == "tc" and args.model == "v5" and F == 1 and os.environ.get("CVAD_FUSE", "1") != "0"
+    fused = math in ("tc", "tc16") and args.model == "v5" and F == 1 and os.environ.get("CVAD_FUSE", "1") != "0"
+    h16 = fused and math == "tc16"      # FP16 two-way split: 3 tensor-core products per MAC (BF16 split: 6)
     if fused:
         # one kernel does the whole step (front end + LSTM step + state machine): its FLOPs are the frame's
         flop_fe = flop_frame
         fe_tflops = frames_per_step * flop_fe / fe_avg_s / 1e12 if fe_avg_s > 0 else 0.0
     if rank == 0:
-        tc = math == "tc"
+        tc = math in ("tc", "tc16")
         fe_kernel = (("v4tc_stft_kernel+v4_frontend_kernel" if args.model == "v4" else
+                      "v5tc_frontend_kernel<FUSED,H16>" if h16 else
                       "v5tc_frontend_kernel<FUSED>" if fused else "v5tc_frontend_kernel") if tc
                      else f"{args.model}_frontend_kernel") + ("+resample_kernel" if args.src_rate != 16000 else "")
         traffic = (ncu_traffic_bytes("v5tc_frontend_kernel" if tc else "v5_frontend_kernel")
                    if (n == 4096 and F == 1 and args.model == "v5" and args.src_rate == 16000) else None)
         peak_bf16 = float(peaks.get("bf16_tflops", 1645.0))
         rec_tflops = frames_per_step * flop_rec / rec_avg_s / 1e12 if rec_avg_s else 0.0
-        fe_weight_bytes = (933_888 + (786_432 if fused else 0)) if tc else 156032 * 4
+        fe_weight_bytes = ((622_592 + 524_288) if h16 else (933_888 + (786_432 if fused else 0))) if tc else 156032 * 4
         roofline = {
-            # tc: every algorithmic MAC is executed as 6 BF16 tensor-core products (3-way operand split), so the
-            # executed rate is 6x `achieved`; the path is bound by shared-memory operand bandwidth, not by the
-            # tensor pipe
+            # tc: every algorithmic MAC is executed as 6 BF16 tensor-core products (3-way operand split) -- 3 FP16
+            # products (2-way split, per-stream scaling) in the tc16 build of the fused kernel -- so the executed
+            # rate is 6x / 3x `achieved`; the path is bound by shared-memory operand bandwidth and by the serial
+            # loader -> MMA -> epilogue chain of one tile per SM, not by the tensor pipe
             "bound": "tensor" if tc else "fp32_ffma", "kernel": fe_kernel,
             "achieved": fe_tflops, "peak": peak_bf16 if tc else peak_fp32, "unit": "TFLOP/s",
             "frac": fe_tflops / (peak_bf16 if tc else peak_fp32),
@@ -470,14 +473,17 @@ def run_ours(args):
                     "peak_gbs": peaks.get("hbm_gbs")},
         }
         if tc:
-            roofline["executed_bf16_tflops"] = 6 * fe_tflops
-            roofline["executed_frac"] = 6 * fe_tflops / peak_bf16
+            products = 3 if h16 else 6
+            roofline["tensor_products_per_mac"] = products
+            roofline["executed_bf16_tflops"] = products * fe_tflops
+            roofline["executed_frac"] = products * fe_tflops / peak_bf16
         cpu = None if args.skip_cpu else cpu_baseline_sample(n)
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 operands, f32 accumulate (FP32-equivalent)" if math == "tc" else "f32",
+            "dtype": ("f16x2 operands with per-stream scaling, f32 accumulate (FP32-equivalent)" if h16 else
+                      "bf16x3 operands, f32 accumulate (FP32-equivalent)" if tc else "f32"),
             "data": "synthetic", "config": workload_config(args, pool_mb=round(pool_n * step_bytes / 1e6)),
             "p99_step_ms": float(np.percentile(lat, 99)), "p50_step_ms": float(np.percentile(lat, 50)),
             "frames_per_s": value / 0.032,
@@ -541,7 +547,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--mixed-rates", action="store_true",
                     help="BASELINE.json configs[3] per-GPU share: 24 / 48 kHz streams by parity, resampled in one step")
-    ap.add_argument("--math", choices=["tc", "fp32"], default="tc",
+    ap.add_argument("--math", choices=["tc16", "tc", "fp32"], default="tc16",
                     help="v5 GEMM arithmetic: tc = tcgen05 tensor cores with the 3-way BF16 split, fp32 = packed FP32 FMA")
     ap.add_argument("--model", choices=["v5", "v4"], default="v5", help="v5 = headline (configs[1]); v4 = configs[2]")
     ap.add_argument("--src-rate", type=int, default=16000, choices=[8000, 16000, 24000, 48000],

@@ -1106,7 +1106,7 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
         }
         const char *m = std::getenv("CVAD_MATH");
         e->math = (m && std::strcmp(m, "fp32") == 0) ? CVAD_MATH_FP32
-                  : (m && std::strcmp(m, "tc16") == 0) ? CVAD_MATH_TC16 : CVAD_MATH_TC;
+                  : (m && std::strcmp(m, "tc") == 0) ? CVAD_MATH_TC : CVAD_MATH_TC16;
         const char *fz = std::getenv("CVAD_FUSE");
         e->fuse_single_frame = !(fz && std::strcmp(fz, "0") == 0);
     }

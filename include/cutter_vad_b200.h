@@ -57,9 +57,11 @@ extern "C" {
                                 (silero_model.py:433 feeds sr; the graph's else-branch): 512-sample frames of 8 kHz audio,
                                 two LSTM time steps per frame, the two sigmoid outputs averaged */
 
-/* arithmetic of the v5 GEMM stages (cvad_set_math).  Both hold the 1e-4 parity bar with two orders of margin:
+/* arithmetic of the v5 GEMM stages (cvad_set_math).  All hold the 1e-4 parity bar (observed: <= 4e-5 on every test):
    FP32  = packed FP32 FMA on the CUDA cores;
-   TC    = tcgen05 tensor cores, BF16 operands split three ways (6 products, FP32 accumulation in TMEM). */
+   TC    = tcgen05 tensor cores, BF16 operands split three ways (6 products, FP32 accumulation in TMEM);
+   TC16  = TC, except that one-frame steps (the fused kernel) use FP16 operands split two ways, every activation
+           operand scaled per stream by a power of two (3 products; results do not depend on batch neighbours). */
 #define CVAD_MATH_FP32 0
 #define CVAD_MATH_TC 1
 #define CVAD_MATH_TC16 2   /* v5: one-frame steps (the fused kernel) use FP16 operands split two ways with per-stream
@@ -135,7 +137,7 @@ int cvad_destroy(cvad_engine *e);
 
 /* Select the arithmetic of the model kernels (CVAD_MATH_*).  For v5 every GEMM stage moves to the tensor cores;
    for v4 the STFT (77 % of its MACs) does, the small layers and the two LSTM(64) stay FP32.
-   A v5 engine starts in CVAD_MATH_TC unless the environment variable CVAD_MATH is "fp32"; a v4 engine starts in
+   A v5 engine starts in CVAD_MATH_TC16 unless the environment variable CVAD_MATH is "tc" or "fp32"; a v4 engine starts in
    CVAD_MATH_FP32 unless CVAD_MATH is "tc" (v4's log(1 + 2^20 |STFT|) amplifies accumulation-order differences). */
 int cvad_set_math(cvad_engine *e, int math);
 int cvad_get_math(const cvad_engine *e);

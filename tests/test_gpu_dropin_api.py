@@ -13,7 +13,7 @@ from conftest import GOLDEN, synth_streams
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["tc", "fp32"])
+@pytest.fixture(autouse=True, params=["tc", "fp32", "tc16"])
 def math_mode(request, monkeypatch):
     """Every test runs on both arithmetic paths of the v5 engine: tcgen05 tensor cores (BF16 3-way split) and
     packed FP32 FMA.  cvad_create reads CVAD_MATH; engines are created inside the tests."""

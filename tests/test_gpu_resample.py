@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-@pytest.fixture(autouse=True, params=["tc", "fp32"])
+@pytest.fixture(autouse=True, params=["tc", "fp32", "tc16"])
 def math_mode(request, monkeypatch):
     """Both builds: resampler + model GEMMs on the tcgen05 tensor cores (BF16 3-way split), or FP32 FMA."""
     monkeypatch.setenv("CVAD_MATH", request.param)
