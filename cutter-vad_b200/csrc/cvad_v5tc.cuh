@@ -129,6 +129,15 @@ __device__ __forceinline__ float sfu_sqrt(float x) {
     return y;
 }
 
+// 16-byte read-once global load that stays where it is written (volatile: issued before the state fetch that follows
+// it in program order, so that both HBM latencies overlap), not allocated in L1
+__device__ __forceinline__ float4 ldg_stream4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 // x -> three BF16 parts (bit patterns)
 __device__ __forceinline__ void split3(float x, unsigned short &p0, unsigned short &p1, unsigned short &p2) {
     const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
@@ -626,7 +635,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                         const long long b0 = (long long)(st * kTile + s) * p.stride + (long long)frame * p.hop + 8 * c8;
                         if (fast && p.pcm == 0) {
                             const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.audio) + b0);
-                            const float4 t0 = __ldg(src), t1 = __ldg(src + 1);
+                            const float4 t0 = ldg_stream4(src), t1 = ldg_stream4(src + 1);
                             v[u4][0] = t0.x; v[u4][1] = t0.y; v[u4][2] = t0.z; v[u4][3] = t0.w;
                             v[u4][4] = t1.x; v[u4][5] = t1.y; v[u4][6] = t1.z; v[u4][7] = t1.w;
                         } else if (fast) {
