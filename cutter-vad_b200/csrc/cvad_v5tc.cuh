@@ -79,7 +79,7 @@ constexpr int kFusedRing = 6;
 constexpr int kFusedSlotsPerTile = 24 + kFeSlotsPerTile + 24;
 constexpr uint32_t kColGate = 384;           // TMEM columns 384 + 32 g: gate g (i,f,g,o), one accumulator per gate
 constexpr size_t kFusedSmemTC = 1024 + kActBytes + 24576 + (size_t)kFusedRing * kSlotBytes + 96 * 4 + 128 * 4 +
-                                (2 * kFusedRing + 3) * 8 + 16 + 2 * kTile * 4 + kTile * 16 + 7 * kTile * 4 + 64;
+                                (2 * kFusedRing + 3) * 8 + 16 + 2 * kTile * 4 + kTile * 16 + 7 * kTile * 4 + kTile * 8 + 5 * kTile * 4 + 64;
 // feature hand-off (front end -> recurrent), per (frame, stream tile): the x half of the recurrent B operand,
 // byte for byte: [kb 0..1][row = part*32 + item (96 rows)][128 B], SW128
 constexpr uint32_t kFeatTileBytes = 2 * 12288;
@@ -370,6 +370,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     double *s_thr = reinterpret_cast<double *>(s_valid + kTile);             // FUSED: start_p[32], end_p[32]
     uint32_t *amax = reinterpret_cast<uint32_t *>(s_thr + 2 * kTile);        // H16: [6][32] per-stream maxima (bit patterns) of AUD, MAG, E0, E1, E2, X
     int *s_dn = FUSED ? reinterpret_cast<int *>(amax + 6 * kTile) : s_valid + kTile;   // [32] per-stream denoise flag (fetched with the slot ids)
+    long long *s_f0 = reinterpret_cast<long long *>(s_dn + kTile);           // FUSED: [32] frames_done
+    int *s_sm = reinterpret_cast<int *>(s_f0 + kTile);                       // FUSED: [5][32] is_voice_active, start / end counters, N_s, N_e
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     CVAD_PROF_NS(120);
@@ -610,7 +612,18 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 s_slot[lane] = my_slot;
                 s_valid[lane] = my_valid;
                 s_dn[lane] = my_slot >= 0 ? (int)p.denoise[my_slot] : 0;
-                if (FUSED && my_slot >= 0) { s_thr[lane] = p.start_p[my_slot]; s_thr[kTile + lane] = p.end_p[my_slot]; }
+                if (FUSED && my_slot >= 0) {
+                    // thresholds and state-machine words of the tile's streams, fetched in one batch with the slot data
+                    // (their latency would otherwise sit at the very end of the tile)
+                    const double sp = p.start_p[my_slot], ep = p.end_p[my_slot];
+                    const int a0 = p.sm_active[my_slot], a1 = p.sm_scount[my_slot], a2 = p.sm_ecount[my_slot];
+                    const int a3 = p.n_start[my_slot], a4 = p.n_end[my_slot];
+                    const long long f0 = p.frames_done[my_slot];
+                    s_thr[lane] = sp; s_thr[kTile + lane] = ep;
+                    s_sm[lane] = a0; s_sm[kTile + lane] = a1; s_sm[2 * kTile + lane] = a2;
+                    s_sm[3 * kTile + lane] = a3; s_sm[4 * kTile + lane] = a4;
+                    s_f0[lane] = f0;
+                }
             }
             if (H16 && warp >= 1 && warp <= 6) amax[(warp - 1) * kTile + lane] = 0u;
             epi_bar();
@@ -1159,9 +1172,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 // sigmoid(w . relu(h') + b), then the start/end state machine (silero_model.py:790-923)
                 if (warp == 0 && s_valid[lane]) {
                     const int slot = s_slot[lane];
-                    int sm_active = p.sm_active[slot], sm_sc = p.sm_scount[slot], sm_ec = p.sm_ecount[slot];
-                    const int sm_ns = p.n_start[slot], sm_ne = p.n_end[slot];
-                    const long long sm_f0 = p.frames_done[slot];
+                    int sm_active = s_sm[lane], sm_sc = s_sm[kTile + lane], sm_ec = s_sm[2 * kTile + lane];
+                    const int sm_ns = s_sm[3 * kTile + lane], sm_ne = s_sm[4 * kTile + lane];
+                    const long long sm_f0 = s_f0[lane];
                     const float a = (dpart[lane] + dpart[32 + lane]) + (dpart[64 + lane] + dpart[96 + lane]);
                     const float prob = sigmoid_f(a + dec_b);
                     const double pd = (double)prob;
