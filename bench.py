@@ -547,12 +547,15 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--mixed-rates", action="store_true",
                     help="BASELINE.json configs[3] per-GPU share: 24 / 48 kHz streams by parity, resampled in one step")
-    ap.add_argument("--math", choices=["tc16", "tc", "fp32"], default="tc16",
-                    help="v5 GEMM arithmetic: tc = tcgen05 tensor cores with the 3-way BF16 split, fp32 = packed FP32 FMA")
+    ap.add_argument("--math", choices=["tc16", "tc", "fp32"], default=None,
+                    help="GEMM arithmetic: tc16 (v5 default) = tcgen05 tensor cores, FP16 2-way split with per-stream scaling for "
+                         "one-frame steps; tc = BF16 3-way split; fp32 (v4 default) = packed FP32 FMA")
     ap.add_argument("--model", choices=["v5", "v4"], default="v5", help="v5 = headline (configs[1]); v4 = configs[2]")
     ap.add_argument("--src-rate", type=int, default=16000, choices=[8000, 16000, 24000, 48000],
                     help="source rate of the synthetic streams; != 16000 adds the GPU resampler (configs[2..3])")
     args = ap.parse_args()
+    if args.math is None:
+        args.math = "tc16" if args.model == "v5" else "fp32"
     args.warmup = max(args.warmup, 3)
     _protect_stdout()
     if args.impl == "reference":

@@ -69,6 +69,8 @@ struct cvad_engine {
     cudaEvent_t last_done = nullptr;   // recorded after the kernels of the most recent step
     float *rs_rt[3] = {nullptr, nullptr, nullptr};  // R^T for 8 / 24 / 48 kHz, built on first use
     unsigned char *rs_tc[3] = {nullptr, nullptr, nullptr};  // the same operators as BF16x3 tiles for resample_tc_kernel
+    unsigned char *rs_h[3] = {nullptr, nullptr, nullptr};   // ... and as two scaled FP16 parts (CVAD_MATH_TC16)
+    float rs_h_inv[3] = {1.f, 1.f, 1.f};
     DevBuf d_res;                      // resampled 16 kHz audio of the step being launched
     DevBuf d_rate_lists;               // mixed-rate steps: [4][n] stream lists + 4 counters
     // host-buffer steps run on kLanes lanes so that later steps' H2D copies overlap earlier steps' kernels and D2H
@@ -562,6 +564,17 @@ int ensure_rt_tc(cvad_engine *e, int src_rate, cudaStream_t stream) {
             emit_tiles(tiles, 128, kb * 64, [&](int r, int m) { return rt[(size_t)m * 512 + blk * 128 + r]; });
     CU_TRY(e, cudaMalloc(reinterpret_cast<void **>(&e->rs_tc[ri]), tiles.size()));
     CU_TRY(e, cudaMemcpyAsync(e->rs_tc[ri], tiles.data(), tiles.size(), cudaMemcpyHostToDevice, stream));
+    // the FP16 two-part form of the same operator, scaled so that its largest entry lies in [2^14, 2^15)
+    float mx = 0.f;
+    for (float v : rt) mx = std::max(mx, std::fabs(v));
+    const float sw = pow2_scale_for(mx, &e->rs_h_inv[ri]);
+    std::vector<unsigned char> th;
+    th.reserve((size_t)512 * n_in * 4);
+    for (int kb = 0; kb < n_in / 64; ++kb)
+        for (int blk = 0; blk < 4; ++blk)
+            emit_tiles_h(th, 128, kb * 64, sw, [&](int r, int m) { return rt[(size_t)m * 512 + blk * 128 + r]; });
+    CU_TRY(e, cudaMalloc(reinterpret_cast<void **>(&e->rs_h[ri]), th.size()));
+    CU_TRY(e, cudaMemcpyAsync(e->rs_h[ri], th.data(), th.size(), cudaMemcpyHostToDevice, stream));
     CU_TRY(e, cudaStreamSynchronize(stream));
     return CVAD_OK;
 }
@@ -607,14 +620,21 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         r.out = static_cast<float *>(e->d_res.p);
         const int grid_rs = std::min(a->max_frames * n_stiles, e->num_sms);
         const bool rs_tc = e->math != CVAD_MATH_FP32;
-        const int grid_rs_tc = std::min(a->max_frames * ((a->n_streams + cvad::tc5::kRsTcTile - 1) / cvad::tc5::kRsTcTile),
-                                        e->num_sms);
+        // fewer 64-stream tiles than SMs: share a tile's four output blocks among 2 or 4 CTAs
+        const int rs_tiles = a->max_frames * ((a->n_streams + cvad::tc5::kRsTcTile - 1) / cvad::tc5::kRsTcTile);
+        r.osplit = 4 * rs_tiles <= e->num_sms ? 4 : (2 * rs_tiles <= e->num_sms ? 2 : 1);
+        const int grid_rs_tc = std::min(rs_tiles * r.osplit, e->num_sms);
         if (!mixed) {
             r.n_in = rate_n_in(a->src_rate);
             if (rs_tc) {
                 if ((rc = ensure_rt_tc(e, a->src_rate, stream))) return rc;
-                cvad::tc5::resample_tc_kernel<<<grid_rs_tc, cvad::tc5::kThreadsTC, cvad::tc5::kRsTcSmem, stream>>>(
-                    r, e->rs_tc[rate_index(a->src_rate)]);
+                const int ri = rate_index(a->src_rate);
+                if (e->math == CVAD_MATH_TC16)
+                    cvad::tc5::resample_tc_kernel<true><<<grid_rs_tc, cvad::tc5::kThreadsTC, cvad::tc5::kRsTcSmem, stream>>>(
+                        r, e->rs_h[ri], e->rs_h_inv[ri]);
+                else
+                    cvad::tc5::resample_tc_kernel<false><<<grid_rs_tc, cvad::tc5::kThreadsTC, cvad::tc5::kRsTcSmem, stream>>>(
+                        r, e->rs_tc[ri], 1.f);
             } else {
                 if ((rc = ensure_rt(e, a->src_rate, stream))) return rc;
                 r.rt = e->rs_rt[rate_index(a->src_rate)];
@@ -641,8 +661,12 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
                 r.count = counts + ri;
                 if (rs_tc) {
                     if ((rc = ensure_rt_tc(e, kRates[ri], stream))) return rc;
-                    cvad::tc5::resample_tc_kernel<<<grid_rs_tc, cvad::tc5::kThreadsTC, cvad::tc5::kRsTcSmem, stream>>>(
-                        r, e->rs_tc[ri]);
+                    if (e->math == CVAD_MATH_TC16)
+                        cvad::tc5::resample_tc_kernel<true><<<grid_rs_tc, cvad::tc5::kThreadsTC, cvad::tc5::kRsTcSmem, stream>>>(
+                            r, e->rs_h[ri], e->rs_h_inv[ri]);
+                    else
+                        cvad::tc5::resample_tc_kernel<false><<<grid_rs_tc, cvad::tc5::kThreadsTC, cvad::tc5::kRsTcSmem, stream>>>(
+                            r, e->rs_tc[ri], 1.f);
                 } else {
                     if ((rc = ensure_rt(e, kRates[ri], stream))) return rc;
                     r.rt = e->rs_rt[ri];
@@ -1112,7 +1136,9 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
     }
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::v4tc_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kV4tcSmem));
-    CR_TRY(cudaFuncSetAttribute(cvad::tc5::resample_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::resample_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::tc5::kRsTcSmem));
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::resample_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kRsTcSmem));
     if (model_version == CVAD_MODEL_V4) {
         std::vector<unsigned char> T = pack_v4_stft_tc(weights);
@@ -1163,7 +1189,7 @@ int cvad_destroy(cvad_engine *e) {
     void *ptrs[] = {e->w_fe, e->b_fe, e->w_rec, e->b_rec, e->w_dec, e->h_state, e->c_state, e->sm_active,
                     e->sm_scount, e->sm_ecount, e->frames_done, e->start_p, e->end_p, e->n_start, e->n_end,
                     e->denoise, e->d_status_dev.p, e->d_feat.p, e->d_dbg.p, e->d_cfg_slots.p, e->d_res.p,
-                    e->rs_rt[0], e->rs_rt[1], e->rs_rt[2], e->w_fe_tc, e->w_rec_tc, e->w_fe_h, e->w_rec_h, e->nyq_w, e->b_rec_tc,
+                    e->rs_rt[0], e->rs_rt[1], e->rs_rt[2], e->rs_h[0], e->rs_h[1], e->rs_h[2], e->w_fe_tc, e->w_rec_tc, e->w_fe_h, e->w_rec_h, e->nyq_w, e->b_rec_tc,
                     e->d_feat_tc.p, e->d_prof, e->d_rate_lists.p, e->d_v4_mag.p, e->rs_tc[0], e->rs_tc[1], e->rs_tc[2]};
     for (void *p : ptrs)
         if (p) cudaFree(p);

@@ -37,6 +37,7 @@ struct ResampleStep {
     // device word `count`); null = all n_streams in order
     const int *list;
     const int *count;
+    int osplit;          // resample_tc_kernel: a tile's four 128-sample output blocks are shared among 1, 2 or 4 CTAs
 };
 
 constexpr int kRsPiece = 128;  // source samples staged per piece

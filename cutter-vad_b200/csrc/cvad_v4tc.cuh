@@ -207,9 +207,15 @@ constexpr int kRsTcTile = 64;
 constexpr int kRsTcRing = 8;
 constexpr uint32_t kRsTcBPart = kRsTcTile * 128;                 // one part of one B buffer: 64 rows x 128 B
 constexpr size_t kRsTcSmem = 1024 + 2 * 3 * (size_t)kRsTcBPart + (size_t)kRsTcRing * kSlotBytes + (2 * kRsTcRing + 5) * 8 +
-                             16 + 2 * kRsTcTile * 4 + 64;
+                             16 + 3 * kRsTcTile * 4 + 64;
 
-__global__ void __launch_bounds__(kThreadsTC, 1) resample_tc_kernel(const ResampleStep p, const unsigned char *r_tiles) {
+// H16 (CVAD_MATH_TC16): the operator as two FP16 parts (scaled by a power of two on the host, inverse in `inv_w`), the
+// chunk scaled per stream from its own maximum (a first pass over the chunk, which the second then finds in L2):
+// three products per MAC instead of six, same FP32-level accuracy (cvad_v5tc.cuh, "FP16 two-way split").
+template <bool H16>
+__global__ void __launch_bounds__(kThreadsTC, 1) resample_tc_kernel(const ResampleStep p, const unsigned char *r_tiles,
+                                                                    const float inv_w) {
+    constexpr int NP = H16 ? 2 : 3;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *bbuf = base;                                   // [2][3 parts][64 rows][128 B]
@@ -220,6 +226,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) resample_tc_kernel(const Resamp
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 1);
     int *s_gi = reinterpret_cast<int *>(tmem_slot + 4);           // [64] stream index of each tile row, or -1
     int *s_valid = s_gi + kRsTcTile;
+    float *s_inv = reinterpret_cast<float *>(s_valid + kRsTcTile);   // H16: [64] 1 / (stream scale)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -236,8 +243,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) resample_tc_kernel(const Resamp
 
     const int n_items = p.count ? *p.count : p.n_streams;
     const int n_st = (n_items + kRsTcTile - 1) / kRsTcTile;
-    const int n_tiles = p.max_frames * n_st;
     const int n_kb = p.n_in / 64;
+    // small batches: the four output blocks of a tile are shared among `osplit` CTAs (each reads the tile's audio)
+    const int osplit = p.osplit > 0 ? p.osplit : 1, nblk = 4 / osplit;
+    const int n_tiles = p.max_frames * n_st * osplit;
     const uint32_t b_s = smem_u32(bbuf), ring_s = smem_u32(ring_buf);
 
     // warp-uniform: does tile (frame, st) hold a live (stream, frame) item?  (every warp evaluates all 64 rows)
@@ -260,36 +269,43 @@ __global__ void __launch_bounds__(kThreadsTC, 1) resample_tc_kernel(const Resamp
     if (warp == kProducerWarp) {
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int frame = tile / n_st, st = tile - frame * n_st;
+            const int osp = tile % osplit, ft = tile / osplit;
+            const int frame = ft / n_st, st = ft - frame * n_st;
             if (!tile_live64(frame, st, nullptr, nullptr)) continue;
             if (lane == 0) {
-                for (int s = 0; s < 12 * n_kb; ++s, ++g) {
-                    const uint32_t slot = g % kRsTcRing;
-                    mbar_wait(&empty[slot], ((g / kRsTcRing) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&full[slot], kSlotBytes);
-                    bulk_g2s(ring_buf + slot * kSlotBytes, r_tiles + (size_t)s * kSlotBytes, kSlotBytes, &full[slot]);
-                }
+                for (int kb = 0; kb < n_kb; ++kb)
+                    for (int s = osp * nblk * NP; s < (osp + 1) * nblk * NP; ++s, ++g) {
+                        const uint32_t slot = g % kRsTcRing;
+                        mbar_wait(&empty[slot], ((g / kRsTcRing) & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(&full[slot], kSlotBytes);
+                        bulk_g2s(ring_buf + slot * kSlotBytes, r_tiles + (size_t)(kb * 4 * NP + s) * kSlotBytes, kSlotBytes, &full[slot]);
+                    }
             }
             __syncwarp();
         }
     } else if (warp == kMmaWarp) {
         uint32_t g = 0, nb = 0;                                   // weight slots and B buffers consumed so far
-        const uint32_t idesc = tc::idesc_bf16_f32(128, kRsTcTile);
+        const uint32_t idesc = H16 ? idesc_f16_f32(128, kRsTcTile) : tc::idesc_bf16_f32(128, kRsTcTile);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int frame = tile / n_st, st = tile - frame * n_st;
+            const int ft = tile / osplit;
+            const int frame = ft / n_st, st = ft - frame * n_st;
             if (!tile_live64(frame, st, nullptr, nullptr)) continue;
             for (int kb = 0; kb < n_kb; ++kb, ++nb) {
                 const uint32_t bb = nb & 1u;
                 mbar_wait(&b_full[bb], (nb >> 1) & 1u);
                 tc::fence_after_sync();
-                for (int blk = 0; blk < 4; ++blk)
-                    for (int wp = 0; wp < 3; ++wp, ++g) {
+                for (int blk = 0; blk < nblk; ++blk)
+                    for (int wp = 0; wp < NP; ++wp, ++g) {
                         const uint32_t slot = g % kRsTcRing;
                         mbar_wait(&full[slot], (g / kRsTcRing) & 1u);
                         tc::fence_after_sync();
                         if (tc::elect_one()) {
-                            issue_split(wp, ring_s + slot * kSlotBytes, b_s + bb * 3 * kRsTcBPart, kRsTcBPart, blk * 64u,
-                                        256u + blk * 64u, idesc, kb == 0 && wp == 0);
+                            if (H16)
+                                issue_split_h(wp, ring_s + slot * kSlotBytes, b_s + bb * 3 * kRsTcBPart, kRsTcBPart, blk * 64u,
+                                              256u + blk * 64u, idesc, kb == 0 && wp == 0);
+                            else
+                                issue_split(wp, ring_s + slot * kSlotBytes, b_s + bb * 3 * kRsTcBPart, kRsTcBPart, blk * 64u,
+                                            256u + blk * 64u, idesc, kb == 0 && wp == 0);
                             tc::mma_commit(&empty[slot]);
                         }
                         __syncwarp();
@@ -305,7 +321,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) resample_tc_kernel(const Resamp
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
         uint32_t acc_phase = 0, nb = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int frame = tile / n_st, st = tile - frame * n_st;
+            const int osp = tile % osplit, ft = tile / osplit;
+            const int frame = ft / n_st, st = ft - frame * n_st;
             int gi2[2], valid2[2];
             if (!tile_live64(frame, st, gi2, valid2)) continue;
             if (warp == 0) {
@@ -313,37 +330,101 @@ __global__ void __launch_bounds__(kThreadsTC, 1) resample_tc_kernel(const Resamp
                 s_valid[lane] = valid2[0]; s_valid[32 + lane] = valid2[1];
             }
             epi_bar();
-            // one work unit per thread and K block: 8 source samples of one stream
-            const int s = tid >> 3, c8 = tid & 7;
-            const bool valid = s_valid[s] != 0;
-            const long long b0 = valid ? (long long)s_gi[s] * p.stride + (long long)frame * p.n_in + 8 * c8 : 0;
-            const uint32_t off = tc::sw128_offset((uint32_t)s, (uint32_t)c8 * 8u, (uint32_t)kRsTcTile);
-            for (int kb = 0; kb < n_kb; ++kb, ++nb) {
-                float v[8];
+            // two work units per thread and K block: 4 consecutive source samples of streams tid / 16 and tid / 16 + 32
+            // (16 neighbouring lanes read one stream's 256-byte K block: coalesced, one 16-byte load each when aligned)
+            const int c4 = tid & 15;
+            int su[2];
+            bool valid[2];
+            long long b0[2];
+            uint32_t off[2];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                if (valid) {
-                    const long long o = b0 + 64LL * kb;
+            for (int j = 0; j < 2; ++j) {
+                su[j] = (tid >> 4) + 32 * j;
+                valid[j] = s_valid[su[j]] != 0;
+                b0[j] = valid[j] ? (long long)s_gi[su[j]] * p.stride + (long long)frame * p.n_in + 4 * c4 : 0;
+                off[j] = tc::sw128_offset((uint32_t)su[j], (uint32_t)c4 * 4u, (uint32_t)kRsTcTile);
+            }
+            const bool vec = p.pcm == 0 ? ((reinterpret_cast<uintptr_t>(p.audio) & 15u) == 0 && (p.stride & 3) == 0)
+                                        : ((reinterpret_cast<uintptr_t>(p.audio) & 7u) == 0 && (p.stride & 3) == 0);
+            auto fetch = [&](int kb, int j) -> float4 {       // raw sample values (int16 not yet divided)
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid[j] && kb < n_kb) {
+                    const long long o = b0[j] + 64LL * kb;
                     if (p.pcm == 0) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = __ldg(reinterpret_cast<const float *>(p.audio) + o + e);
+                        const float *src = reinterpret_cast<const float *>(p.audio) + o;
+                        if (vec) r = __ldg(reinterpret_cast<const float4 *>(src));
+                        else r = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
                     } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float x = (float)__ldg(reinterpret_cast<const short *>(p.audio) + o + e);
-                            v[e] = p.pcm == 1 ? __fdiv_rn(x, 32767.0f) : x * (1.0f / 32768.0f);
+                        const short *src = reinterpret_cast<const short *>(p.audio) + o;
+                        if (vec) {
+                            const short4 t = __ldg(reinterpret_cast<const short4 *>(src));
+                            r = make_float4((float)t.x, (float)t.y, (float)t.z, (float)t.w);
+                        } else {
+                            r = make_float4((float)__ldg(src), (float)__ldg(src + 1), (float)__ldg(src + 2), (float)__ldg(src + 3));
                         }
                     }
                 }
-                uint32_t w[3][4];
+                return r;
+            };
+            auto to_unit = [&](float4 r) -> float4 {          // PCM scaling exactly as the loaders of the model kernels do it
+                if (p.pcm == 1) r = make_float4(__fdiv_rn(r.x, 32767.0f), __fdiv_rn(r.y, 32767.0f), __fdiv_rn(r.z, 32767.0f), __fdiv_rn(r.w, 32767.0f));
+                else if (p.pcm == 2) r = make_float4(r.x * (1.0f / 32768.0f), r.y * (1.0f / 32768.0f), r.z * (1.0f / 32768.0f), r.w * (1.0f / 32768.0f));
+                return r;
+            };
+            float sc[2] = {1.f, 1.f};
+            if (H16) {
+                // first pass: each stream's maximum over the chunk (its 16 lanes are neighbours) -> that stream's scale
+                float mx[2] = {0.f, 0.f};
+                for (int kb0 = 0; kb0 < n_kb; kb0 += 4) {          // n_in / 64 = 4, 12 or 24: eight loads in flight per thread
+                    float4 r[4][2];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) split3x2(v[2 * e], v[2 * e + 1], w[0][e], w[1][e], w[2][e]);
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) r[i][j] = fetch(kb0 + i, j);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const float4 u = to_unit(r[i][j]);
+                            mx[j] = fmaxf(mx[j], fmaxf(fmaxf(fabsf(u.x), fabsf(u.y)), fmaxf(fabsf(u.z), fabsf(u.w))));
+                        }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    uint32_t mb = __float_as_uint(mx[j]);
+#pragma unroll
+                    for (int w = 1; w < 16; w <<= 1) mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, w));
+                    const Scale S = scale_from_max(mb);
+                    sc[j] = S.s;
+                    if (c4 == 0) s_inv[su[j]] = S.inv * inv_w;   // read by the epilogue (the K-block barriers lie in between)
+                }
+            }
+            // K block kb + 1 is fetched while K block kb is converted and its MMAs run
+            float4 nxt[2] = {fetch(0, 0), fetch(0, 1)};
+            for (int kb = 0; kb < n_kb; ++kb, ++nb) {
+                float4 v[2] = {to_unit(nxt[0]), to_unit(nxt[1])};
+                nxt[0] = fetch(kb + 1, 0);
+                nxt[1] = fetch(kb + 1, 1);
+                uint32_t w[2][3][2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (H16) {
+                        split2x2_h(v[j].x * sc[j], v[j].y * sc[j], w[j][0][0], w[j][1][0]);
+                        split2x2_h(v[j].z * sc[j], v[j].w * sc[j], w[j][0][1], w[j][1][1]);
+                    } else {
+                        split3x2(v[j].x, v[j].y, w[j][0][0], w[j][1][0], w[j][2][0]);
+                        split3x2(v[j].z, v[j].w, w[j][0][1], w[j][1][1], w[j][2][1]);
+                    }
+                }
                 const uint32_t bb = nb & 1u;
                 mbar_wait(&b_empty[bb], ((nb >> 1) & 1u) ^ 1u);   // the MMAs that read this buffer two K blocks ago are done
-                unsigned char *dst = bbuf + bb * 3 * kRsTcBPart + off;
 #pragma unroll
-                for (int part = 0; part < 3; ++part)
-                    *reinterpret_cast<uint4 *>(dst + part * kRsTcBPart) = make_uint4(w[part][0], w[part][1], w[part][2], w[part][3]);
+                for (int j = 0; j < 2; ++j) {
+                    unsigned char *dst = bbuf + bb * 3 * kRsTcBPart + off[j];
+#pragma unroll
+                    for (int part = 0; part < NP; ++part)
+                        *reinterpret_cast<uint2 *>(dst + part * kRsTcBPart) = make_uint2(w[j][part][0], w[j][part][1]);
+                }
                 tc::fence_async_smem();
                 epi_bar();
                 if (tid == 0) mbar_arrive(&b_full[bb]);
@@ -352,8 +433,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) resample_tc_kernel(const Resamp
             mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
             tc::fence_after_sync();
 #pragma unroll 1
-            for (int blk = 0; blk < 4; ++blk) {
-                const int sample = blk * 128 + 32 * q + lane;
+            for (int blk = 0; blk < nblk; ++blk) {
+                const int sample = (osp * nblk + blk) * 128 + 32 * q + lane;
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
                     const int c0 = cg * 16 + ch * 8;
@@ -365,7 +446,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) resample_tc_kernel(const Resamp
                     for (int e = 0; e < 8; ++e) {
                         const int c = c0 + e;
                         if (s_valid[c])
-                            p.out[(size_t)s_gi[c] * p.max_frames * 512 + (size_t)frame * 512 + sample] = m[e] + cr[e];
+                            p.out[(size_t)s_gi[c] * p.max_frames * 512 + (size_t)frame * 512 + sample] =
+                                H16 ? (m[e] + cr[e]) * s_inv[c] : m[e] + cr[e];
                     }
                 }
             }
