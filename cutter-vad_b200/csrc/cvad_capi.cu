@@ -622,7 +622,10 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         const bool rs_tc = e->math != CVAD_MATH_FP32;
         // fewer 64-stream tiles than SMs: share a tile's four output blocks among 2 or 4 CTAs
         const int rs_tiles = a->max_frames * ((a->n_streams + cvad::tc5::kRsTcTile - 1) / cvad::tc5::kRsTcTile);
-        r.osplit = 4 * rs_tiles <= e->num_sms ? 4 : (2 * rs_tiles <= e->num_sms ? 2 : 1);
+        // (mixed-rate steps launch once per rate over that rate's share of the streams: assume an even share)
+        const int n_rates = mixed ? std::max(1, __builtin_popcount(rates_mask & 7u)) : 1;
+        const int rs_share = (rs_tiles + n_rates - 1) / n_rates;
+        r.osplit = 4 * rs_share <= e->num_sms ? 4 : (2 * rs_share <= e->num_sms ? 2 : 1);
         const int grid_rs_tc = std::min(rs_tiles * r.osplit, e->num_sms);
         if (!mixed) {
             r.n_in = rate_n_in(a->src_rate);
