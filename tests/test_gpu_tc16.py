@@ -93,3 +93,23 @@ def test_tc16_int16_short_frames_slots_and_idle_streams(engine_factory, ref_v5):
         done += run
     assert (done == T).all()
     assert np.abs(got - want).max() <= TOL
+
+
+@pytest.mark.parametrize("math", ["tc16", "tc", "fp32"])
+def test_engine_against_the_pytorch_reference(engine_factory, math):
+    """The CUDA path against third-party kernels directly (oracle/torch_reference.py: torch conv1d + LSTMCell fed the
+    .onnx file's tensors), float32, 1e-4: one frame per step and all frames in one call."""
+    import torch
+    from conftest import V5_ONNX
+    from torch_reference import TorchV5
+    from vad_oracle import v5_named_weights
+    n, T = 64, 30
+    audio = synth_streams(n, 512 * T, seed=88)
+    want = TorchV5(v5_named_weights(str(V5_ONNX)), torch.float32).run(audio, T, denoise=True)
+    eng = engine_factory(512, math=math)
+    eng.reset()
+    eng.configure(enable_denoising=True)
+    got = _steps(eng, audio, T)
+    assert np.abs(got - want).max() <= TOL
+    eng.reset()
+    assert np.abs(eng.step(audio).probs - want).max() <= TOL

@@ -139,3 +139,34 @@ def test_v4_is_ill_conditioned_on_band_limited_input(ref_v4, ref_v5):
     d5 = np.abs(ref_v5.run(ya, T, denoise=False)[0] - ref_v5.run(yb, T, denoise=False)[0])
     assert d5.max() < 2e-5
     assert d4.max() > 1e-4 and d4.max() > 20 * d5.max()
+
+
+def test_oracle_agrees_with_pytorch_modules_fed_the_files_raw_tensors(ref_v5):
+    """Second opinion from third-party kernels (oracle/torch_reference.py): torch.nn.functional.conv1d and
+    torch.nn.LSTMCell loaded with the tensors the .onnx carries under their torch names must give what the op-by-op
+    ONNX interpretation (golden p_*) and its C restatement give -- in particular the LSTM gate re-ordering."""
+    import torch
+    from torch_reference import TorchV5
+    from vad_oracle import v5_named_weights
+    from conftest import synth_streams
+    named = v5_named_weights(str(V5_ONNX))
+    g = np.load(GOLDEN / "v5_frames.npz")
+    t32 = TorchV5(named, torch.float32)
+    for name in ("zeros", "sine440", "noise"):                  # the reference-Python goldens, six frames with state
+        h = np.zeros((1, 128), np.float32)
+        c = np.zeros((1, 128), np.float32)
+        ps = []
+        for _ in range(6):
+            p, h, c = t32.frame(g[f"in_{name}"][None], h, c)
+            ps.append(p[0])
+        assert np.abs(np.array(ps) - g[f"p_{name}"]).max() <= 5e-6, name   # FP32 rounding (same bar as the C restatement)
+        st = g[f"state_{name}"]
+        assert np.abs(h[0] - st[0, 0]).max() <= 2e-5 and np.abs(c[0] - st[1, 0]).max() <= 1e-4
+    # streams with state over 40 frames: C restatement (the GPU checker) vs PyTorch float32 and float64
+    audio = synth_streams(12, 512 * 40, seed=77)
+    want, _, _ = ref_v5.run(audio, 40, denoise=True)
+    got32 = t32.run(audio, 40, denoise=True)
+    got64 = TorchV5(named, torch.float64).run(audio, 40, denoise=True)
+    assert np.abs(got32 - want).max() <= 2e-5
+    assert np.abs(got64 - want).max() <= 2e-5
+    assert want.max() > 0.9 and want.min() < 0.05             # the comparison covers the whole probability range
