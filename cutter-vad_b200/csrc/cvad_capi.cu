@@ -50,6 +50,7 @@ struct cvad_engine {
     int math = CVAD_MATH_FP32;
     bool v4_t2 = false;                // CVAD_MODEL_V4_8K: two LSTM time steps per frame
     bool fuse_single_frame = true;     // CVAD_FUSE=0 keeps the two-kernel form for one-frame steps (measurement)
+    bool h16_multi = true;             // CVAD_H16_MULTI=0: multi-frame steps of CVAD_MATH_TC16 run the BF16-split kernels
     unsigned char *w_fe_tc = nullptr, *w_rec_tc = nullptr;
     unsigned char *w_fe_h = nullptr, *w_rec_h = nullptr;   // CVAD_MATH_TC16: two FP16 parts, per-layer scale
     float tc16_inv_w[8] = {0};
@@ -344,8 +345,10 @@ V5HPacked pack_v5_tc16(const float *blob) {
     const float s_e1 = pow2_scale_for(maxabs(e1w, 64 * 128 * 3), &P.inv_w[2]);
     const float s_e2 = pow2_scale_for(maxabs(e2w, 64 * 64 * 3), &P.inv_w[3]);
     const float s_e3 = pow2_scale_for(maxabs(e3w, 128 * 64 * 3), &P.inv_w[4]);
-    const float s_ih = pow2_scale_for(maxabs(wih, 512 * 128), &P.inv_w[5]);
-    const float s_hh = pow2_scale_for(maxabs(whh, 512 * 128), &P.inv_w[6]);
+    // one scale for [W_ih | W_hh]: the recurrent kernel accumulates both halves of K in the same TMEM columns
+    const float s_ih = pow2_scale_for(std::max(maxabs(wih, 512 * 128), maxabs(whh, 512 * 128)), &P.inv_w[5]);
+    const float s_hh = s_ih;
+    P.inv_w[6] = P.inv_w[5];
     P.w_fe.reserve(cvad::tc5::kFeStreamBytesH);
     for (int blk = 0; blk < 2; ++blk)
         for (int kb = 0; kb < 4; ++kb)
@@ -743,7 +746,13 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
             CU_TRY(e, cudaEventRecord(e->last_done, stream));
             return CVAD_OK;
         }
+        const bool h16 = e->math == CVAD_MATH_TC16 && !d_dbg && e->h16_multi;
+        if (h16) {
+            p.w_fe_h = e->w_fe_h; p.w_rec_h = e->w_rec_h;
+            std::memcpy(p.tc16_inv_w, e->tc16_inv_w, sizeof(p.tc16_inv_w));
+        }
         if (d_dbg) cvad::tc5::v5tc_frontend_kernel<true, false><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFeSmemTC, stream>>>(p);
+        else if (h16) cvad::tc5::v5tc_frontend_kernel<false, false, true><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFeSmemTCH, stream>>>(p);
         else cvad::tc5::v5tc_frontend_kernel<false, false><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFeSmemTC, stream>>>(p);
         CU_TRY(e, cudaGetLastError());
         e->launches++;
@@ -761,7 +770,8 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
             at[0].val.programmaticStreamSerializationAllowed = timed ? 0 : 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            CU_TRY(e, cudaLaunchKernelEx(&cfg, cvad::tc5::v5tc_recurrent_kernel, p));
+            if (h16) CU_TRY(e, cudaLaunchKernelEx(&cfg, cvad::tc5::v5tc_recurrent_kernel<true>, p));
+            else CU_TRY(e, cudaLaunchKernelEx(&cfg, cvad::tc5::v5tc_recurrent_kernel<false>, p));
             CU_TRY(e, cudaGetLastError());
             e->launches++;
         }
@@ -1110,7 +1120,11 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
                                 (int)cvad::tc5::kFusedSmemTC));
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kFusedSmemTC));
-    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::tc5::kFeSmemTCH));
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_recurrent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::tc5::kRecSmemTC));
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_recurrent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kRecSmemTC));
     if (model_version == CVAD_MODEL_V5) {
         V5TcPacked T = pack_v5_tc(weights);
@@ -1136,6 +1150,8 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
                   : (m && std::strcmp(m, "tc") == 0) ? CVAD_MATH_TC : CVAD_MATH_TC16;
         const char *fz = std::getenv("CVAD_FUSE");
         e->fuse_single_frame = !(fz && std::strcmp(fz, "0") == 0);
+        const char *hm = std::getenv("CVAD_H16_MULTI");
+        e->h16_multi = !(hm && std::strcmp(hm, "0") == 0);
     }
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::v4tc_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kV4tcSmem));

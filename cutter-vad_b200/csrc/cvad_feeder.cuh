@@ -10,6 +10,7 @@
 #pragma once
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -496,8 +497,11 @@ static void feeder_fill_result(cvad_feeder *f, cvad_feeder_result *r) {
 int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *r) {
     if (!f || !r) return CVAD_E_INVALID;
     if (!f->eng) return ffail(f, CVAD_E_NOGPU, "feeder has no engine: there is no CPU fallback");
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
     int rc = feeder_gather(f);
     if (rc) return rc;
+    const auto t1 = clk::now();
     const int n = (int)f->ids.size(), T = f->tmax;
     f->events.clear();
     f->probs.assign((size_t)n * T, 0.f);
@@ -534,8 +538,13 @@ int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *r) {
                 return ffail(f, CVAD_E_INVALID, "Audio data contains infinite or NaN values");
             }
     }
+    const auto t2 = clk::now();
     feeder_deliver(f);
     feeder_fill_result(f, r);
+    const auto t3 = clk::now();
+    r->gather_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    r->gpu_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    r->deliver_ms = std::chrono::duration<double, std::milli>(t3 - t2).count();
     return CVAD_OK;
 }
 

@@ -72,6 +72,10 @@ constexpr uint32_t kE1Part = 8192;           // E1: 64 rows x 64 K
 constexpr uint32_t kE2Part = 4096;           // E2: 32 rows x 64 K
 constexpr size_t kFeSmemTC = 1024 + kActBytes + (size_t)kFeRing * kSlotBytes + 96 * 4 + (2 * kFeRing + 2) * 8 + 16 +
                              3 * kTile * 4 + 64;
+constexpr size_t kFeSmemTCH = kFeSmemTC + 2048;   // FP16-split build: + the per-stream maxima
+// bytes [kFeatScaleOff, +128) of a feature tile (row 64 of K block 0: the unused third part) carry, in the FP16-split
+// build, the 32 streams' joint maxima max(|x|max, 1) as float bit patterns: the scale of this frame's [x | h] operand
+constexpr uint32_t kFeatScaleOff = 8192;
 // fused single-frame kernel (max_frames == 1): the front end plus the LSTM step of the same 32 streams in one CTA.
 // ACT | H operand (24 KB) | ring (6 slots) | nyq | decoder partials | barriers | meta.  Weight stream per tile:
 // 24 W_hh tiles (issued while the loader runs), the 69 front-end tiles, 24 W_ih tiles.
@@ -288,7 +292,7 @@ __device__ __forceinline__ void store_parts2_h(unsigned char *base, uint32_t ps,
 }
 // per-stream maximum of non-negative values held one per lane: warp maximum -> shared atomic
 __device__ __forceinline__ void amax_push(uint32_t *slot, float v, int lane) {
-    const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(v));
+    const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(v) & 0x7fffffffu);   // (a ReLU may hand over -0.0)
     if (lane == 0 && m != 0u) atomicMax(slot, m);
 }
 // instruction descriptor, kind::f16: D = F32, A = B = FP16
@@ -351,7 +355,7 @@ struct Ring {
 // H16 (CVAD_MATH_TC16, FUSED only): FP16 two-way operand split with per-stream dynamic scaling, three products per MAC.
 template <bool DBG, bool FUSED, bool H16 = false>
 __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5Step p) {
-    static_assert(!H16 || (FUSED && !DBG), "the FP16 split exists for the fused single-frame kernel only");
+    static_assert(!H16 || !DBG, "the debug dump runs the BF16-split build");
     constexpr int RING = FUSED ? kFusedRing : kFeRing;
     constexpr int NP = H16 ? 2 : 3;                   // operand parts
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -403,11 +407,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
             if (!tile_live(p, frame, st, lane, nullptr, nullptr)) continue;
             if (lane == 0) {
-                for (int s = 0; s < (H16 ? kFusedSlotsPerTileH : FUSED ? kFusedSlotsPerTile : kFeSlotsPerTile); ++s, ++g) {
+                for (int s = 0; s < (H16 ? (FUSED ? kFusedSlotsPerTileH : kFeSlotsPerTileH) : FUSED ? kFusedSlotsPerTile : kFeSlotsPerTile); ++s, ++g) {
                     const uint32_t slot = g % RING;
                     mbar_wait(&empty[slot], ((g / RING) & 1u) ^ 1u);
                     uint32_t off, bytes;
                     const unsigned char *src;
+                    if (H16 && !FUSED) {
+                        fe_slot_h(s, off, bytes);
+                        mbar_arrive_expect_tx(&full[slot], bytes);
+                        bulk_g2s(ring_buf + slot * kSlotBytes, p.w_fe_h + off, bytes, &full[slot]);
+                        continue;
+                    }
                     if (H16) {
                         // same order with two parts: hh gate g = 4 tiles | STFT 16 | enc0 12 | enc1 12 | enc2 + enc3 6 | W_ih 16
                         int fe_idx = s, gate = -1, kb = 0, part = 0;
@@ -1058,10 +1068,25 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 }
                 tc::fence_before_sync();   // the W_ih accumulators reuse these TMEM columns
                 epi_bar();
+                if (FUSED) {
 #pragma unroll
-                for (int e = 0; e < 8; e += 2)
-                    store_parts2_h(act, 32 * 128, (uint32_t)(c0 + e), (uint32_t)o, 96u, v[e] * scale_from_max(amax[5 * kTile + c0 + e]).s,
-                                   v[e + 1] * scale_from_max(amax[5 * kTile + c0 + e + 1]).s);
+                    for (int e = 0; e < 8; e += 2)
+                        store_parts2_h(act, 32 * 128, (uint32_t)(c0 + e), (uint32_t)o, 96u, v[e] * scale_from_max(amax[5 * kTile + c0 + e]).s,
+                                       v[e + 1] * scale_from_max(amax[5 * kTile + c0 + e + 1]).s);
+                } else {
+                    // two-kernel form: x goes to HBM as the recurrent kernel's operand, scaled like the h it will sit
+                    // next to in K: by the stream's joint maximum max(|x|max, 1) (|h| < 1), handed over in the tile
+                    unsigned char *fout = p.feat_tc + (size_t)tile * kFeatTileBytes;
+                    uint32_t jm[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) jm[e] = max(amax[5 * kTile + c0 + e], 0x3f800000u);
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2)
+                        store_parts2_h(fout, 32 * 128, (uint32_t)(c0 + e), (uint32_t)o, 96u, v[e] * scale_from_max(jm[e]).s,
+                                       v[e + 1] * scale_from_max(jm[e + 1]).s);
+                    if (q == 0 && lane < 8)
+                        *reinterpret_cast<uint32_t *>(fout + kFeatScaleOff + 4 * (c0 + lane)) = max(amax[5 * kTile + c0 + lane], 0x3f800000u);
+                }
             } else {
                 const int o = 32 * q + lane;
                 const float bias = __ldg(p.b_fe + 256 + o);
@@ -1239,7 +1264,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
 // multiplies the first (3 - wp) activation parts in ONE MMA (N = 96 / 64 / 32) whose output lands at TMEM column
 // 32*wp of the gate block, so that columns [0,32) collect w0.x0, [32,64) w0.x1 + w1.x0 and [64,96) the three
 // smallest products.
+// H16 (CVAD_MATH_TC16): two FP16 parts; the [x | h] operand of a stream carries ONE scale per frame, the power of two
+// that brings max(|x|max, 1) to [2^14, 2^15) (the front end scales x with it and hands its bit pattern over in the feature
+// tile, the cell epilogue scales the h it writes for the next frame with that frame's).  Part wp of a weight tile
+// multiplies the first (2 - wp) activation parts in one MMA (N = 64 / 32): columns [0,32) collect w0.x0, [32,64)
+// w0.x1 + w1.x0.  W_ih and W_hh share one weight scale (pack_v5_tc16).
+template <bool H16>
 __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5Step p) {
+    constexpr int NP = H16 ? 2 : 3;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     unsigned char *xbuf = base;                               // [2][kFeatTileBytes]
@@ -1300,18 +1332,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
         if (warp == kProducerWarp) {
             if (lane == 0) {
                 uint32_t g = 0;
+                const unsigned char *wsrc = H16 ? p.w_rec_h : p.w_rec_tc;
                 for (int j = 0; j < tmax; ++j)
-                    for (int s = 0; s < kRecSlotsPerFrame; ++s, ++g) {
+                    for (int s = 0; s < 16 * NP; ++s, ++g) {
                         const uint32_t slot = g % kRecRing;
                         mbar_wait(&empty[slot], ((g / kRecRing) & 1u) ^ 1u);
                         mbar_arrive_expect_tx(&full[slot], kSlotBytes);
-                        bulk_g2s(ring_buf + slot * kSlotBytes, p.w_rec_tc + (size_t)s * kSlotBytes, kSlotBytes, &full[slot]);
+                        bulk_g2s(ring_buf + slot * kSlotBytes, wsrc + (size_t)s * kSlotBytes, kSlotBytes, &full[slot]);
                     }
             }
             __syncwarp();
         } else if (warp == kMmaWarp) {
             uint32_t g = 0;
-            const uint32_t idesc[3] = {tc::idesc_bf16_f32(128, 96), tc::idesc_bf16_f32(128, 64), tc::idesc_bf16_f32(128, 32)};
+            const uint32_t idesc[3] = {H16 ? idesc_f16_f32(128, 64) : tc::idesc_bf16_f32(128, 96),
+                                       H16 ? idesc_f16_f32(128, 32) : tc::idesc_bf16_f32(128, 64), tc::idesc_bf16_f32(128, 32)};
             for (int j = 0; j < tmax; ++j) {
                 const bool first_tile = lane == 0 && j < 8;
                 mbar_wait(&xfull[j & 1], (uint32_t)(j >> 1) & 1u);
@@ -1322,7 +1356,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
                 for (int blk = 0; blk < 4; ++blk)
                     for (int kb = 0; kb < 4; ++kb) {
                         const uint32_t b_addr = kb < 2 ? x_s + (j & 1) * kFeatTileBytes + kb * kXhKb : h_s + (kb - 2) * kXhKb;
-                        for (int wp = 0; wp < 3; ++wp, ++g) {
+                        for (int wp = 0; wp < NP; ++wp, ++g) {
                             const uint32_t slot = g % kRecRing;
                             mbar_wait(&full[slot], (g / kRecRing) & 1u);
                             tc::fence_after_sync();
@@ -1368,8 +1402,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
             epi_bar();
 #pragma unroll
             for (int e = 0; e < 8; ++e) hreg[e] = sbuf[u * 33 + i0 + e];
+            if (!H16) {
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) store_parts2(hbuf, 32 * 128, (uint32_t)(i0 + e), (uint32_t)u, 96u, hreg[e], hreg[e + 1]);
+                for (int e = 0; e < 8; e += 2) store_parts2(hbuf, 32 * 128, (uint32_t)(i0 + e), (uint32_t)u, 96u, hreg[e], hreg[e + 1]);
+            }
             epi_bar();
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -1379,9 +1415,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
             epi_bar();
 #pragma unroll
             for (int e = 0; e < 8; ++e) creg[e] = sbuf[u * 33 + i0 + e];
-            tc::fence_async_smem();
-            epi_bar();
-            if (tid == 0) mbar_arrive(h_ready);
+            if (!H16) {
+                tc::fence_async_smem();
+                epi_bar();
+                if (tid == 0) mbar_arrive(h_ready);
+            }
             CVAD_PROF(65);
             // ---- everything above only touched state owned by this kernel; the front end's outputs (status, feat)
             //      are read after the grid dependency resolves
@@ -1416,6 +1454,24 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
             int nfr[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) nfr[e] = s_nfr[i0 + e];
+            // H16: scale of frame 0's operand from its feature tile, then h (resident state) into the operand with it
+            float g_inv[8];                                   // 1 / (this frame's operand scale x weight scale)
+            if (H16) {
+                mbar_wait(&xfull[0], 0u);
+                float s_h[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const Scale S = scale_from_max(*reinterpret_cast<const uint32_t *>(xbuf + kFeatScaleOff + 4 * (i0 + e)));
+                    s_h[e] = S.s;
+                    g_inv[e] = S.inv * p.tc16_inv_w[5];
+                }
+#pragma unroll
+                for (int e = 0; e < 8; e += 2)
+                    store_parts2_h(hbuf, 32 * 128, (uint32_t)(i0 + e), (uint32_t)u, 96u, hreg[e] * s_h[e], hreg[e + 1] * s_h[e + 1]);
+                tc::fence_async_smem();
+                epi_bar();
+                if (tid == 0) mbar_arrive(h_ready);
+            }
 
             for (int j = 0; j < tmax; ++j) {
                 first_tile = tid == 0 && j < 8;
@@ -1434,10 +1490,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
                     float g0[8], g1[8], g2[8];
                     tmem_ld8(lane_addr + blk * 96 + i0, g0);
                     tmem_ld8(lane_addr + blk * 96 + 32 + i0, g1);
-                    tmem_ld8(lane_addr + blk * 96 + 64 + i0, g2);
+                    if (!H16) tmem_ld8(lane_addr + blk * 96 + 64 + i0, g2);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) gate[blk][e] = g0[e] + (g1[e] + g2[e]);
+                    for (int e = 0; e < 8; ++e) gate[blk][e] = H16 ? (g0[e] + g1[e]) * g_inv[e] : g0[e] + (g1[e] + g2[e]);
                 }
                 float dv[8], hn[8];
 #pragma unroll
@@ -1454,8 +1510,26 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
                     hn[e] = hreg[e];                  // a finished stream keeps its last h in the operand
                     dv[e] = wd * fmaxf(hv, 0.f);
                 }
+                if (H16) {
+                    if (j + 1 < tmax) {
+                        // the next frame's operand scale (its tile was requested two frames ago) -> h with it
+                        mbar_wait(&xfull[(j + 1) & 1], (uint32_t)((j + 1) >> 1) & 1u);
+                        const unsigned char *xt = xbuf + ((j + 1) & 1) * kFeatTileBytes + kFeatScaleOff;
+                        float s_h[8];
 #pragma unroll
-                for (int e = 0; e < 8; e += 2) store_parts2(hbuf, 32 * 128, (uint32_t)(i0 + e), (uint32_t)u, 96u, hn[e], hn[e + 1]);
+                        for (int e = 0; e < 8; ++e) {
+                            const Scale S = scale_from_max(*reinterpret_cast<const uint32_t *>(xt + 4 * (i0 + e)));
+                            s_h[e] = S.s;
+                            g_inv[e] = S.inv * p.tc16_inv_w[5];
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2)
+                            store_parts2_h(hbuf, 32 * 128, (uint32_t)(i0 + e), (uint32_t)u, 96u, hn[e] * s_h[e], hn[e + 1] * s_h[e + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) store_parts2(hbuf, 32 * 128, (uint32_t)(i0 + e), (uint32_t)u, 96u, hn[e], hn[e + 1]);
+                }
                 // decoder dot over the 128 units: 8 values x 32 lanes -> every lane ends with item (lane & 7)
 #pragma unroll
                 for (int w = 4; w >= 1; w >>= 1) {

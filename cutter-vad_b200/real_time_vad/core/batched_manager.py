@@ -286,7 +286,9 @@ class BatchedVADManager:
             events = [StreamEvent(slot, "start" if kind == capi.FLAG_STARTED else "end", stream_frame, j)
                       for (k, slot, j, kind, stream_frame) in r.events]
             self._deliver(r.deliveries)
-            return StepOutput(events, r.slots.astype(np.int64), r.counts.astype(np.int64), r.probs, r.flags)
+            out = StepOutput(events, r.slots.astype(np.int64), r.counts.astype(np.int64), r.probs, r.flags)
+            out.phase_ms = r.phase_ms          # (framing, GPU step incl. copies, segment assembly) inside the native step
+            return out
 
     def _deliver(self, deliveries) -> None:
         """Fire the callbacks the feeder found due, in stream-then-frame order: start, then end with the WAV

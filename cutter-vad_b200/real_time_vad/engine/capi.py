@@ -70,7 +70,8 @@ class FeederResult(C.Structure):
     _fields_ = [("n_streams", C.c_int32), ("max_frames", C.c_int32), ("n_frames_total", C.c_int64),
                 ("slots", C.c_void_p), ("counts", C.c_void_p), ("probs", C.c_void_p), ("flags", C.c_void_p),
                 ("n_events", C.c_int32), ("n_deliveries", C.c_int32), ("events", C.c_void_p),
-                ("deliveries", C.c_void_p), ("raw", C.c_void_p), ("raw_stride", C.c_int64)]
+                ("deliveries", C.c_void_p), ("raw", C.c_void_p), ("raw_stride", C.c_int64),
+                ("gather_ms", C.c_double), ("gpu_ms", C.c_double), ("deliver_ms", C.c_double)]
 
 
 _lib = None

@@ -37,12 +37,13 @@ class Delivery(NamedTuple):
 class FeederStep:
     """One step's results; arrays are copies, safe to keep."""
 
-    __slots__ = ("slots", "counts", "probs", "flags", "events", "deliveries", "frames", "raw", "raw_stride")
+    __slots__ = ("slots", "counts", "probs", "flags", "events", "deliveries", "frames", "raw", "raw_stride", "phase_ms")
 
-    def __init__(self, slots, counts, probs, flags, events, deliveries, frames, raw=None, raw_stride=0):
+    def __init__(self, slots, counts, probs, flags, events, deliveries, frames, raw=None, raw_stride=0, phase_ms=(0.0, 0.0, 0.0)):
         self.slots, self.counts, self.probs, self.flags = slots, counts, probs, flags
         self.events, self.deliveries, self.frames = events, deliveries, frames
         self.raw, self.raw_stride = raw, raw_stride
+        self.phase_ms = phase_ms            # (gather, cvad_step, deliver) wall milliseconds inside the native step
 
 
 _EVENT_DT = np.dtype([("stream", "<i4"), ("slot", "<i4"), ("frame", "<i4"), ("kind", "<i4"), ("stream_frame", "<i8")])
@@ -153,7 +154,7 @@ class StreamFeeder:
         if want_raw and n:
             raw_block = _view(r.raw, self.dtype, n * int(r.raw_stride)).reshape(n, int(r.raw_stride)).copy()
         return FeederStep(slots, counts, probs, flags, events, deliveries, int(r.n_frames_total), raw_block,
-                          int(r.raw_stride))
+                          int(r.raw_stride), (float(r.gather_ms), float(r.gpu_ms), float(r.deliver_ms)))
 
     def step(self) -> FeederStep:
         self._check(self._L.cvad_feeder_step(self._h, C.byref(self._res)))

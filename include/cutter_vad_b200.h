@@ -60,12 +60,12 @@ extern "C" {
 /* arithmetic of the v5 GEMM stages (cvad_set_math).  All hold the 1e-4 parity bar (observed: <= 4e-5 on every test):
    FP32  = packed FP32 FMA on the CUDA cores;
    TC    = tcgen05 tensor cores, BF16 operands split three ways (6 products, FP32 accumulation in TMEM);
-   TC16  = TC, except that one-frame steps (the fused kernel) use FP16 operands split two ways, every activation
-           operand scaled per stream by a power of two (3 products; results do not depend on batch neighbours). */
+   TC16  = tcgen05 tensor cores, FP16 operands split two ways, every activation operand scaled per stream by a power
+           of two (3 products; results do not depend on batch neighbours).  The debug dump runs as TC. */
 #define CVAD_MATH_FP32 0
 #define CVAD_MATH_TC 1
-#define CVAD_MATH_TC16 2   /* v5: one-frame steps (the fused kernel) use FP16 operands split two ways with per-stream
-                              power-of-two scaling, 3 products per MAC instead of 6; multi-frame steps run as CVAD_MATH_TC */
+#define CVAD_MATH_TC16 2   /* v5: FP16 operands split two ways with per-stream power-of-two scaling, 3 products per MAC
+                              instead of 6 (fused one-frame kernel, two-kernel multi-frame form and the resampler) */
 
 /* audio sample formats accepted by cvad_step */
 #define CVAD_PCM_F32 0        /* float32 in [-1, 1] */
@@ -289,6 +289,7 @@ typedef struct cvad_feeder_result {
     const cvad_delivery *deliveries;   /* stream-then-frame order */
     const void *raw;                   /* the block that was stepped: [n_streams][raw_stride] samples, PCM format of the feeder */
     int64_t raw_stride;
+    double gather_ms, gpu_ms, deliver_ms;   /* wall time of the three phases of this step (framing, cvad_step, callbacks' side) */
 } cvad_feeder_result;
 
 /* e == NULL builds a feeder for the gather / deliver test hooks only (max_streams is then taken from the argument,

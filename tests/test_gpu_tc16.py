@@ -1,5 +1,6 @@
-"""GPU: the FP16-split build of the fused one-frame kernel (CVAD_MATH_TC16) -- two FP16 operand parts, three
-tensor-core products per MAC, every activation operand scaled per STREAM by a power of two.  Besides the oracle bar
+"""GPU: the FP16-split build of the v5 kernels (CVAD_MATH_TC16; fused one-frame kernel and the two-kernel multi-frame
+form) -- two FP16 operand parts, three tensor-core products per MAC, every activation operand scaled per STREAM by a
+power of two.  Besides the oracle bar
 (1e-4, also run over the whole v5 parity suite through its math_mode fixture) this file checks what the scaling must
 guarantee: a stream's result does not depend on its neighbours in the batch, and loud / quiet / out-of-range streams
 in one tile stay on the oracle."""
@@ -31,10 +32,14 @@ def test_tc16_matches_oracle_and_bf16_split(engine_factory, ref_v5):
     ref.configure(enable_denoising=True)
     other = _steps(ref, audio, T)
     assert np.abs(got - other).max() <= 3e-5
-    # a multi-frame call under tc16 IS the BF16-split two-kernel path
+    # a multi-frame call under tc16 runs the FP16-split two-kernel path: on the oracle, next to the BF16 split, and
+    # next to its own one-frame form
     eng.reset()
     ref.reset()
-    assert np.array_equal(eng.step(audio).probs, ref.step(audio).probs)
+    many = eng.step(audio).probs
+    assert np.abs(many - want).max() <= TOL
+    assert np.abs(many - ref.step(audio).probs).max() <= 3e-5
+    assert np.abs(many - got).max() <= 3e-5
 
 
 def test_tc16_result_does_not_depend_on_the_neighbours(engine_factory):
@@ -53,6 +58,13 @@ def test_tc16_result_does_not_depend_on_the_neighbours(engine_factory):
         eng.reset()
         got = _steps(eng, crowd, T)
         assert np.array_equal(got[where:where + 3], alone), (scale, where)
+    # the same property for the multi-frame (two-kernel) form
+    eng.reset()
+    alone_many = eng.step(probe).probs
+    crowd = (1e5 * rng.standard_normal((96, 512 * T))).astype(np.float32)
+    crowd[50:53] = probe
+    eng.reset()
+    assert np.array_equal(eng.step(crowd).probs[50:53], alone_many)
 
 
 def test_tc16_mixed_amplitudes_in_one_tile_stay_on_the_oracle(engine_factory, ref_v5):

@@ -52,7 +52,7 @@ def main():
     sec = 4
     audio = np.clip(np.round(synth_audio(n, 16000 * sec, seed=1) * 32767.0), -32768, 32767).astype(np.int16)
     pos = np.zeros(n, np.int64)
-    lat_tick, lat_step, frames, events = [], [], 0, 0
+    lat_tick, lat_step, frames, events, phases = [], [], 0, 0, []
     for t in range(args.ticks + 10):
         k = rng.choice([0, 1, 1, 1, 1, 1, 1, 2], size=n)               # jitter: late / on time / catching up
         t_push = 0.0
@@ -83,6 +83,7 @@ def main():
         if t >= 10:
             lat_tick.append(t_push + t2 - t1)
             lat_step.append(t2 - t1)
+            phases.append(getattr(out, "phase_ms", (0.0, 0.0, 0.0)))
             frames += out.frames
             events += len(out.events)
     total = sum(lat_tick)
@@ -92,6 +93,7 @@ def main():
         "timed": "manager calls only (push* + step); the synthetic clients' own array work is outside",
         "tick_ms_p50": 1e3 * float(np.percentile(lat_tick, 50)), "tick_ms_p99": 1e3 * float(np.percentile(lat_tick, 99)),
         "step_ms_p50": 1e3 * float(np.percentile(lat_step, 50)), "step_ms_p99": 1e3 * float(np.percentile(lat_step, 99)),
+        "native_step_ms_p50": dict(zip(("gather", "gpu_step", "deliver"), [float(x) for x in np.percentile(np.array(phases), 50, axis=0)])),
         "frames": frames, "events": events, "callbacks_fired": ev_count,
         "audio_s_per_s": frames * 0.030 / total, "realtime_factor_per_stream": frames * 0.030 / total / n,
         "budget_ms": 30.0,
