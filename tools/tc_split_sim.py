@@ -1,4 +1,5 @@
-"""CPU simulation: max |dp| of the v5 model when its GEMMs use split-precision tensor-core arithmetic.
+"""CPU simulation: max |dp| of the v5 model when its GEMMs use split-precision tensor-core arithmetic,
+including the FP16 two-way split with per-stream scaling the TC16 build uses (fp16x3; fp16x3_unscaled shows why it scales).
 Reads the reference ONNX weights through the oracle; float64 run = ground truth."""
 import sys
 from pathlib import Path
@@ -23,9 +24,35 @@ def split(x, f, n):
     for i in range(n):
         p = f(r); parts.append(p); r = (r - p).astype(np.float32)
     return parts
+def f16(x):
+    with np.errstate(over='ignore'):
+        return x.astype(np.float32).astype(np.float16).astype(np.float32)
+def pow2_at_least(x):
+    return 2.0 ** np.ceil(np.log2(np.maximum(x, 1e-30)))
+def mm_fp16x3(scaled):
+    """FP16 two-way split, 3 products (CVAD_MATH_TC16).  scaled=False: operands as they are (FP16 range problems show);
+    scaled=True: every activation row (= stream) and the weight matrix scaled by the power of two that brings its
+    largest element to [2^14, 2^15), as the kernels do."""
+    def mm(A, Wt):
+        A = A.astype(np.float32); Wt = Wt.astype(np.float32)
+        if scaled:
+            sa = (2.0 ** 15 / pow2_at_least(np.abs(A).max(1, keepdims=True))).astype(np.float32)
+            sa = np.where(np.abs(A).max(1, keepdims=True) > 0, sa, 1.0).astype(np.float32)
+            sw = np.float32(2.0 ** 15 / pow2_at_least(np.abs(Wt).max()))
+        else:
+            sa = np.ones((A.shape[0], 1), np.float32); sw = np.float32(1.0)
+        As = A * sa; Ws = Wt * sw
+        a0 = f16(As); a1 = f16(As - a0); w0 = f16(Ws); w1 = f16(Ws - w0)
+        with np.errstate(invalid='ignore', over='ignore'):
+            corr = (a1 @ w0.T).astype(np.float32) + (a0 @ w1.T).astype(np.float32)
+            acc = (a0 @ w0.T).astype(np.float32) + corr
+        return acc / (sa * sw)
+    return mm
 def mm_factory(mode):
     if mode=='f64': return lambda A,Wt: A.astype(np.float64) @ Wt.astype(np.float64).T
     if mode=='f32': return lambda A,Wt: A.astype(np.float32) @ Wt.astype(np.float32).T
+    if mode=='fp16x3_unscaled': return mm_fp16x3(False)
+    if mode=='fp16x3': return mm_fp16x3(True)
     f, na, nw, terms = {
       'bf16x1': (bf16,1,1,[(0,0)]),
       'tf32x1': (tf32_trunc,1,1,[(0,0)]),
@@ -94,9 +121,10 @@ if __name__ == '__main__':
     gate = (np.floor(t/0.7)%2==0)
     streams.append((v*gate).astype(np.float32)); streams.append((a16[:L]*0.05).astype(np.float32))
     streams.append(np.where(np.abs(a16[:L])>0.01, a16[:L], 0).astype(np.float32))
+    streams.append((a16[:L]*32767).astype(np.float32)); streams.append((a16[:L]*1e-4).astype(np.float32))   # out-of-range amplitudes
     A = np.stack(streams)
     ref = run('f64', A)
     print('ref prob range', ref.min(), ref.max())
-    for mode in sys.argv[1:] or ['f32','tf32x1','bf16x1','bf16x3','bf16x4','tf32x3','bf16x6','bf16_a2w3x5']:
+    for mode in sys.argv[1:] or ['f32','tf32x1','bf16x1','bf16x3','bf16x4','tf32x3','bf16x6','bf16_a2w3x5','fp16x3_unscaled','fp16x3']:
         P = run(mode, A); d = np.abs(P-ref)
         print(f'{mode:12s} max|dp|={d.max():.3e} per-stream max={np.array2string(d.max(1), precision=1)} mean={d.mean():.2e}')
