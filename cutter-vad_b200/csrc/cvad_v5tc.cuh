@@ -65,6 +65,7 @@ constexpr size_t kRecStreamBytes = (size_t)kRecSlotsPerFrame * 16384;
 // front end: ACT (96 KB) | ring | nyq[96] f32 | barriers | tmem slot | tile meta
 constexpr int kFeRing = 7;
 constexpr uint32_t kActBytes = 98304;
+constexpr uint32_t kActBytesH = 65536;       // FP16 build: two parts (AUD 2 x 32 KB is the largest tenant)
 constexpr uint32_t kAudPart = 32768;         // AUD: part stride; K block stride 16384; row = seg*32 + item (128 rows)
 constexpr uint32_t kMagPart = 24576;         // MAG/E0: 96 rows x 128 K; K block stride 12288
 constexpr uint32_t kMagKb = 12288;
@@ -83,7 +84,7 @@ constexpr int kFusedRing = 6;
 constexpr int kFusedSlotsPerTile = 24 + kFeSlotsPerTile + 24;
 constexpr uint32_t kColGate = 384;           // TMEM columns 384 + 32 g: gate g (i,f,g,o), one accumulator per gate
 constexpr size_t kFusedSmemTC = 1024 + kActBytes + 24576 + (size_t)kFusedRing * kSlotBytes + 96 * 4 + 128 * 4 +
-                                (2 * kFusedRing + 3) * 8 + 16 + 2 * kTile * 4 + kTile * 16 + 7 * kTile * 4 + kTile * 8 + 5 * kTile * 4 + 64;
+                                (2 * kFusedRing + 3) * 8 + 16 + 2 * kTile * 4 + kTile * 16 + 7 * kTile * 4 + kTile * 8 + 5 * kTile * 4 + 128;
 // feature hand-off (front end -> recurrent), per (frame, stream tile): the x half of the recurrent B operand,
 // byte for byte: [kb 0..1][row = part*32 + item (96 rows)][128 B], SW128
 constexpr uint32_t kFeatTileBytes = 2 * 12288;
@@ -309,7 +310,7 @@ __host__ __device__ __forceinline__ void fe_slot_h(int s, uint32_t &off, uint32_
 }
 constexpr size_t kRecStreamBytesH = (size_t)32 * 16384;       // gate x kb 0..3 x part 0..1
 constexpr int kFusedSlotsPerTileH = 16 + kFeSlotsPerTileH + 16;
-constexpr uint32_t kColIh = 0;                                // TMEM columns of the W_ih . x accumulators (free after encoder.3)
+constexpr uint32_t kColIh = 0;                                // TMEM columns of the W_ih . x accumulators (64 per gate; free after encoder.3)
 // MMAs of one weight tile (part wp) for one 64-element K block, FP16 split: w0.x0 -> d_main, w0.x1 and w1.x0 -> d_corr
 __device__ __forceinline__ void issue_split_h(int wp, uint32_t a_addr, uint32_t b0, uint32_t ps, uint32_t d_main,
                                               uint32_t d_corr, uint32_t idesc, bool first) {
@@ -341,6 +342,19 @@ __device__ __forceinline__ void issue_gate_h(int wp, uint32_t a_addr, uint32_t b
     }
 }
 
+// W_ih . x of the fused FP16 kernel with the two activation parts concatenated along N (rows 0..63 of the operand are
+// [x0 | x1]): part 0 of a weight tile in ONE N = 64 MMA (columns [d, d+32) collect w0.x0, [d+32, d+64) w0.x1), part 1
+// against x0 alone into [d+32, d+64): two MMAs per K step instead of three
+__device__ __forceinline__ void issue_gate_h_cat(int wp, uint32_t a_addr, uint32_t b0, uint32_t d, uint32_t idesc64,
+                                                 uint32_t idesc32, bool first) {
+    const uint64_t ad = tc::smem_desc_sw128(a_addr), bd = tc::smem_desc_sw128(b0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        if (wp == 0) tc::mma_bf16(d, ad + ks * 2, bd + ks * 2, idesc64, (first && ks == 0) ? 0u : 1u);
+        else tc::mma_bf16(d + 32u, ad + ks * 2, bd + ks * 2, idesc32, 1u);
+    }
+}
+
 struct Ring {
     uint32_t buf;        // shared address of slot 0
     uint64_t *full;      // [n]
@@ -356,12 +370,15 @@ struct Ring {
 template <bool DBG, bool FUSED, bool H16 = false>
 __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5Step p) {
     static_assert(!H16 || !DBG, "the debug dump runs the BF16-split build");
-    constexpr int RING = FUSED ? kFusedRing : kFeRing;
+    // the FP16 build's activation region holds two parts instead of three: the 32 KB go to two more ring slots (the weight
+    // supply of a phase is bound by the L2 -> shared latency of the tiles in flight, not by bandwidth)
+    constexpr uint32_t ACT = H16 ? kActBytesH : kActBytes;
+    constexpr int RING = (FUSED ? kFusedRing : kFeRing) + (H16 ? 2 : 0);
     constexpr int NP = H16 ? 2 : 3;                   // operand parts
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     unsigned char *act = base;
-    unsigned char *hbuf = act + kActBytes;                                   // FUSED: [2 K blocks][96 rows][128 B]
+    unsigned char *hbuf = act + ACT;                                         // FUSED: [2 K blocks][96 rows][128 B]
     unsigned char *ring_buf = hbuf + (FUSED ? 24576 : 0);
     float *nyq = reinterpret_cast<float *>(ring_buf + RING * kSlotBytes);    // [96] |X[128]| per (t, item)
     float *dpart = nyq + 96;                                                 // FUSED: [4][32] decoder partial sums
@@ -598,7 +615,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 for (int gate = 0; gate < 4; ++gate)
                     for (int kb = 0; kb < 2; ++kb)
                         for (int wp = 0; wp < NP; ++wp)
-                            CVAD_TC_SLOT(CVAD_GATE(wp, act_s + kb * kXhKb, (H16 ? kColIh : kColGate) + 32 * gate, i128_32, H16 && kb == 0 && wp == 0))
+                        {
+                            if (H16) CVAD_TC_SLOT(issue_gate_h_cat(wp, a_addr, act_s + kb * kXhKb, kColIh + 64 * gate, i128_64, i128_32,
+                                                                   kb == 0 && wp == 0))
+                            else CVAD_TC_SLOT(CVAD_GATE(wp, act_s + kb * kXhKb, kColGate + 32 * gate, i128_32, false))
+                        }
                 if (tc::elect_one()) tc::mma_commit(acc_ready);
                 CVAD_PROF(44);
                 __syncwarp();
@@ -1131,10 +1152,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 tmem_wait_ld();
                 if (H16) {
                     // gate = W_hh.h (static scale) + W_ih.x (the stream's own scale), each in its own accumulator
-                    float gx[4][8];
+                    float gx[4][8], gy[4][8];
 #pragma unroll
-                    for (int gi = 0; gi < 4; ++gi) tmem_ld8(lane_addr + kColIh + 32 * gi + i0, gx[gi]);
+                    for (int gi = 0; gi < 4; ++gi) {
+                        tmem_ld8(lane_addr + kColIh + 64 * gi + i0, gx[gi]);
+                        tmem_ld8(lane_addr + kColIh + 64 * gi + 32 + i0, gy[gi]);
+                    }
                     tmem_wait_ld();
+#pragma unroll
+                    for (int gi = 0; gi < 4; ++gi)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) gx[gi][e] += gy[gi][e];
                     const float ih_w = p.tc16_inv_w[5], hh = kHInv * p.tc16_inv_w[6];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
