@@ -8,10 +8,11 @@ hand-written restatement of the network.  This is the stand-in for the
 an unpinned third-party wheel, `pyproject.toml:32` `onnxruntime>=1.10.0`, absent
 from this image).
 
-PARITY UNPINNED for model arithmetic: the reference's tests mock every
-`session.run` (tests/test_silero_model.py:278-292) and hold no golden
-probability vector; see DESIGN.md.  What IS pinned: the state machine, framing,
-and the SampleVoiceMono.wav -> 4 segments known answer (tests/test_oracle_pinning.py).
+Pinning: the reference's tests mock every `session.run` (tests/test_silero_model.py:278-292) and hold no golden
+probability vector, and onnxruntime itself cannot be run here.  This interpreter is therefore checked against a
+third-party ONNX executor that can: OpenCV's DNN module executing the same graphs (oracle/onnx_flatten.py;
+tests/test_oracle_pinning.py: v5 goldens <= 5e-6, 40 stateful frames <= 5e-5, both v4 branches <= 2e-5), and against
+PyTorch's own conv1d / LSTMCell (oracle/torch_reference.py).  Not pinned: onnxruntime's own rounding.
 
 `dtype=np.float32` reproduces the reference's arithmetic type;
 `dtype=np.float64` is the high-precision run used to bound FP32 rounding.

@@ -7,7 +7,7 @@ Exposes exactly the names the reference binds at
 interpreter in oracle/onnx_interp.py.  Put `oracle/ort_shim` and `oracle` on
 PYTHONPATH and the reference's UNMODIFIED Python (from /root/reference/src) runs
 on top of it; that pair is the CPU oracle for probabilities and event indices.
-It is NOT onnxruntime: parity against the real wheel is unpinned.
+It is NOT onnxruntime: the interpreter behind it is pinned against OpenCV's DNN module and PyTorch instead.
 """
 import os
 import sys

@@ -8,9 +8,11 @@
  * pyproject.toml:32, absent from this image), and the state machine at
  *   silero_model.py:790-923.
  * The restatement is validated against the op-by-op ONNX interpreter
- * (oracle/onnx_interp.py) in tests/test_oracle_pinning.py.  PARITY UNPINNED with
- * respect to real onnxruntime: the reference's tests hold no golden probabilities
- * (tests/test_silero_model.py:278-292 mocks every run).
+ * (oracle/onnx_interp.py) in tests/test_oracle_pinning.py, and that interpreter against
+ * two third-party executors present in this image: OpenCV's DNN module running the
+ * reference's own graphs, and PyTorch's conv1d / LSTMCell.  Not pinned: onnxruntime's
+ * own rounding -- the wheel cannot be installed here and the reference's tests hold no
+ * golden probabilities (tests/test_silero_model.py:278-292 mocks every run).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this library.  The product never links it.

@@ -6,10 +6,12 @@ restatement in oracle/silero_ref.c.  Only tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs may import this module; the
 product (cutter-vad_b200/) never does.
 
-PARITY UNPINNED for model arithmetic with respect to real onnxruntime (absent from
-this image; the reference pins no probability vectors).  Pinned here instead:
-the state machine against the reference's own test expectations, framing against
-tests/test_audio_utils.py, and SampleVoiceMono.wav -> 4 segments.
+Pinning (tests/test_oracle_pinning.py): the reference pins no probability vectors and its own runtime,
+onnxruntime, is absent from this image, so model arithmetic is pinned against the two third-party executors that
+ARE here -- OpenCV's DNN module running the reference's own graphs (oracle/onnx_flatten.py) and PyTorch's conv1d /
+LSTMCell kernels fed the file's tensors (oracle/torch_reference.py); NOT against onnxruntime itself.  The state machine
+is pinned against the reference's own test expectations, framing against tests/test_audio_utils.py, end to end
+against SampleVoiceMono.wav -> 4 segments.
 """
 from __future__ import annotations
 

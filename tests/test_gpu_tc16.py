@@ -125,3 +125,29 @@ def test_engine_against_the_pytorch_reference(engine_factory, math):
     assert np.abs(got - want).max() <= TOL
     eng.reset()
     assert np.abs(eng.step(audio).probs - want).max() <= TOL
+
+
+@pytest.mark.parametrize("math", ["tc16", "fp32"])
+def test_engine_against_opencv_dnn_on_the_reference_graph(engine_factory, math):
+    """The CUDA path against a third-party ONNX runtime executing the reference's own graph (oracle/onnx_flatten.py:
+    silero_vad_v5.onnx's 16 kHz branch inside OpenCV's DNN module, state fed back per frame), 1e-4."""
+    pytest.importorskip("cv2")
+    from conftest import V5_ONNX
+    from onnx_flatten import OpenCVSession
+    n, T = 6, 30
+    audio = synth_streams(n, 512 * T, seed=19)
+    z = {"input": np.zeros((1, 512), np.float32), "state": np.zeros((2, 1, 128), np.float32), "sr": np.array([16000], np.int64)}
+    sess = OpenCVSession(str(V5_ONNX), z, ["input", "state"])
+    want = np.zeros((n, T))
+    for s in range(n):
+        st = np.zeros((2, 1, 128), np.float32)
+        for j in range(T):
+            f = audio[s, j * 512:(j + 1) * 512]
+            out, st = sess.run({"input": np.where(np.abs(f) > 0.01, f, 0.0).astype(np.float32)[None], "state": st})
+            want[s, j] = float(out.reshape(-1)[0])
+    eng = engine_factory(512, math=math)
+    eng.reset()
+    eng.configure(enable_denoising=True)
+    got = _steps(eng, audio, T)
+    assert np.abs(got - want).max() <= TOL
+    assert want.max() > 0.8 and want.min() < 0.1

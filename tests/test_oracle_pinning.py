@@ -6,8 +6,9 @@ They pin (a) the plain-C restatement used as the GPU checker and CPU baseline,
 (b) the state machine, against the expectations of the reference's own tests
 (tests/test_silero_model.py:542-614, :870-954), (c) framing (tests/test_audio_utils.py:138-168)
 and (d) the end-to-end known answer SampleVoiceMono.wav -> 4 segments
-(websocket_service/README.md:290).  Model arithmetic remains UNPINNED against real
-onnxruntime (absent from the image); see DESIGN.md.
+(websocket_service/README.md:290), and (e) the model arithmetic itself against the third-party executors that exist
+in this image -- OpenCV's DNN module running the reference's own graphs (v5, v4 16 kHz, v4 8 kHz) and PyTorch's
+conv1d / LSTMCell fed the file's tensors.  onnxruntime itself is absent from the image; see DESIGN.md.
 """
 import numpy as np
 import pytest
@@ -170,3 +171,62 @@ def test_oracle_agrees_with_pytorch_modules_fed_the_files_raw_tensors(ref_v5):
     assert np.abs(got32 - want).max() <= 2e-5
     assert np.abs(got64 - want).max() <= 2e-5
     assert want.max() > 0.9 and want.min() < 0.05             # the comparison covers the whole probability range
+
+
+cv2 = pytest.importorskip("cv2", reason="OpenCV's DNN module is the third-party ONNX executor of this pin")
+
+
+def test_v5_graph_executed_by_opencv_dnn_matches_the_goldens_and_the_c_restatement(ref_v5):
+    """A third-party ONNX runtime on the reference's OWN graph.  onnxruntime is absent, OpenCV's DNN module is not: the
+    16 kHz branch of silero_vad_v5.onnx, flattened (oracle/onnx_flatten.py: taken If branches inlined, shape arithmetic
+    folded, compute nodes / attributes / weights as the file has them), is executed by cv2.dnn with the state fed
+    back frame after frame, and must give the golden probabilities and states that the reference's Python produced on
+    the numpy interpreter, and what the C restatement (the GPU checker) gives on speech-like streams."""
+    from onnx_flatten import OpenCVSession
+    from conftest import synth_streams
+    g = np.load(GOLDEN / "v5_frames.npz")
+    z = {"input": np.zeros((1, 512), np.float32), "state": np.zeros((2, 1, 128), np.float32), "sr": np.array([16000], np.int64)}
+    sess = OpenCVSession(str(V5_ONNX), z, ["input", "state"])
+    assert {"Conv", "LSTM", "Pad", "Sqrt", "Sigmoid"} <= set(sess.ops)
+    for name in ("zeros", "sine440", "noise"):
+        st = np.zeros((2, 1, 128), np.float32)
+        ps = []
+        for _ in range(6):
+            out, st = sess.run({"input": g[f"in_{name}"][None], "state": st})
+            ps.append(float(out.reshape(-1)[0]))
+        assert np.abs(np.array(ps) - g[f"p_{name}"]).max() <= 5e-6, name
+        assert np.abs(st - g[f"state_{name}"]).max() <= 1e-4
+    audio = synth_streams(4, 512 * 40, seed=77)
+    want, _, _ = ref_v5.run(audio, 40, denoise=True)
+    for s in range(4):
+        st = np.zeros((2, 1, 128), np.float32)
+        for j in range(40):
+            f = audio[s, j * 512:(j + 1) * 512]
+            f = np.where(np.abs(f) > 0.01, f, 0.0).astype(np.float32)
+            out, st = sess.run({"input": f[None], "state": st})
+            # two FP32 implementations with different accumulation orders, 40 stateful frames: 2e-5 observed
+            assert abs(float(out.reshape(-1)[0]) - want[s, j]) <= 5e-5, (s, j)
+    assert want.max() > 0.9 and want.min() < 0.05
+
+
+@pytest.mark.parametrize("sr", [16000, 8000])
+def test_v4_graph_executed_by_opencv_dnn_matches_the_interpreter(sr):
+    """Same pin for silero_vad.onnx: its 16 kHz branch and its 8 kHz sub-model (two LSTM time steps per frame)."""
+    from onnx_flatten import OpenCVSession
+    from onnx_interp import OnnxInterpreter
+    from conftest import V4_ONNX, synth_streams
+    z = {"input": np.zeros((1, 512), np.float32), "h": np.zeros((2, 1, 64), np.float32), "c": np.zeros((2, 1, 64), np.float32),
+         "sr": np.array([sr], np.int64)}
+    sess = OpenCVSession(str(V4_ONNX), z, ["input", "h", "c"])
+    assert sess.ops.count("LSTM") == 2 and "Log" in sess.ops
+    it = OnnxInterpreter(str(V4_ONNX), np.float32)
+    audio = synth_streams(2, 512 * 12, seed=5)[1] + 0.02 * np.random.default_rng(1).standard_normal(512 * 12).astype(np.float32)
+    h = c = np.zeros((2, 1, 64), np.float32)
+    h2, c2 = h.copy(), c.copy()
+    worst = 0.0
+    for j in range(12):
+        f = audio[j * 512:(j + 1) * 512].astype(np.float32)[None]
+        out, h, c = sess.run({"input": f, "h": h, "c": c})
+        ref, h2, c2 = it.run({"input": f, "h": h2, "c": c2, "sr": np.array([sr], np.int64)})
+        worst = max(worst, abs(float(out.reshape(-1)[0]) - float(np.asarray(ref).reshape(-1)[0])))
+    assert worst <= 2e-5, worst
