@@ -437,7 +437,10 @@ def run_ours(args):
                       "v5tc_frontend_kernel<FUSED,H16>" if h16 else
                       "v5tc_frontend_kernel<FUSED>" if fused else "v5tc_frontend_kernel") if tc
                      else f"{args.model}_frontend_kernel") + ("+resample_kernel" if args.src_rate != 16000 else "")
-        traffic = (ncu_traffic_bytes("v5tc_frontend_kernel" if tc else "v5_frontend_kernel")
+        # the ncu capture of exactly this kernel variant (template arguments <DBG, FUSED, H16>)
+        variant = ("v5tc_frontend_kernel<0, 1, 1>" if h16 else "v5tc_frontend_kernel<0, 1>" if fused else
+                   "v5tc_frontend_kernel<0, 0" if tc else "v5_frontend_kernel")
+        traffic = (ncu_traffic_bytes(variant)
                    if (n == 4096 and F == 1 and args.model == "v5" and args.src_rate == 16000) else None)
         peak_bf16 = float(peaks.get("bf16_tflops", 1645.0))
         rec_tflops = frames_per_step * flop_rec / rec_avg_s / 1e12 if rec_avg_s else 0.0
