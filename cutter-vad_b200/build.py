@@ -21,7 +21,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and OUT.exists() and all(OUT.stat().st_mtime >= s.stat().st_mtime for s in sources()):
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(OUT), str(SRC)]
+    extra = os.environ.get("CVAD_NVCC_EXTRA", "").split()          # experiments, e.g. -DCVAD_H16_MERGE=1
+    cmd = [nvcc, *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-o", str(OUT), str(SRC)]
     subprocess.run(cmd, check=True)
     return OUT
 

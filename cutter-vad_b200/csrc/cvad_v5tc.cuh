@@ -311,6 +311,19 @@ __host__ __device__ __forceinline__ void fe_slot_h(int s, uint32_t &off, uint32_
 constexpr size_t kRecStreamBytesH = (size_t)32 * 16384;       // gate x kb 0..3 x part 0..1
 constexpr int kFusedSlotsPerTileH = 16 + kFeSlotsPerTileH + 16;
 constexpr uint32_t kColIh = 0;                                // TMEM columns of the W_ih . x accumulators (64 per gate; free after encoder.3)
+// CVAD_H16_MERGE=1 (experiment): the three products of the FP16 split accumulate in ONE accumulator, corrections first
+#ifndef CVAD_H16_MERGE
+#define CVAD_H16_MERGE 0
+#endif
+constexpr bool kH16Merge = CVAD_H16_MERGE != 0;
+__device__ __forceinline__ void tmem_ld8_corr(uint32_t taddr, float (&v)[8]) {
+    if (kH16Merge) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    } else {
+        tmem_ld8(taddr, v);
+    }
+}
 // MMAs of one weight tile (part wp) for one 64-element K block, FP16 split: w0.x0 -> d_main, w0.x1 and w1.x0 -> d_corr
 __device__ __forceinline__ void issue_split_h(int wp, uint32_t a_addr, uint32_t b0, uint32_t ps, uint32_t d_main,
                                               uint32_t d_corr, uint32_t idesc, bool first) {
@@ -320,10 +333,10 @@ __device__ __forceinline__ void issue_split_h(int wp, uint32_t a_addr, uint32_t 
     for (int ks = 0; ks < 4; ++ks) {
         const uint32_t fresh = (first && ks == 0) ? 0u : 1u;
         if (wp == 0) {
-            tc::mma_bf16(d_corr, ad + ks * 2, bd1 + ks * 2, idesc, fresh);
-            tc::mma_bf16(d_main, ad + ks * 2, bd0 + ks * 2, idesc, fresh);
+            tc::mma_bf16(kH16Merge ? d_main : d_corr, ad + ks * 2, bd1 + ks * 2, idesc, fresh);
+            tc::mma_bf16(d_main, ad + ks * 2, bd0 + ks * 2, idesc, kH16Merge ? 1u : fresh);
         } else {
-            tc::mma_bf16(d_corr, ad + ks * 2, bd0 + ks * 2, idesc, 1u);
+            tc::mma_bf16(kH16Merge ? d_main : d_corr, ad + ks * 2, bd0 + ks * 2, idesc, 1u);
         }
     }
 }
@@ -820,8 +833,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     float mr[8], mi[8], cr[8], ci[8];
                     tmem_ld8(lane_addr + kColMain + c0, mr);
                     tmem_ld8(lane_addr + kColMain + 96 + c0, mi);
-                    tmem_ld8(lane_addr + kColCorr + c0, cr);
-                    tmem_ld8(lane_addr + kColCorr + 96 + c0, ci);
+                    tmem_ld8_corr(lane_addr + kColCorr + c0, cr);
+                    tmem_ld8_corr(lane_addr + kColCorr + 96 + c0, ci);
                     tmem_wait_ld();
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -900,7 +913,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     const int c0 = t * 32 + i0;
                     float m[8], cr[8];
                     tmem_ld8(lane_addr + kColMain + c0, m);
-                    tmem_ld8(lane_addr + kColCorr + c0, cr);
+                    tmem_ld8_corr(lane_addr + kColCorr + c0, cr);
                     tmem_wait_ld();
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -973,7 +986,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     const int c0 = t * 32 + i0;
                     float m[8], cr[8];
                     tmem_ld8(lane_addr + kColMain + c0, m);
-                    tmem_ld8(lane_addr + kColCorr + c0, cr);
+                    tmem_ld8_corr(lane_addr + kColCorr + c0, cr);
                     tmem_wait_ld();
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -1031,7 +1044,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 const int c0 = cg * 8;
                 float m[8], cr[8], v[8];
                 tmem_ld8(lane_addr + kColMain + c0, m);
-                tmem_ld8(lane_addr + kColCorr + c0, cr);
+                tmem_ld8_corr(lane_addr + kColCorr + c0, cr);
                 tmem_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -1080,7 +1093,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 const int c0 = cg * 8;
                 float m[8], cr[8], v[8];
                 tmem_ld8(lane_addr + kColMain + c0, m);
-                tmem_ld8(lane_addr + kColCorr + c0, cr);
+                tmem_ld8_corr(lane_addr + kColCorr + c0, cr);
                 tmem_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
