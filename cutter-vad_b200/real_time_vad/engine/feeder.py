@@ -140,7 +140,7 @@ class StreamFeeder:
         probs = _view(r.probs, np.float32, n * T).reshape(n, T).copy()
         flags = _view(r.flags, np.uint8, n * T).reshape(n, T).copy()
         ev = _view(r.events, _EVENT_DT, int(r.n_events))
-        events = [(int(e["stream"]), int(e["slot"]), int(e["frame"]), int(e["kind"]), int(e["stream_frame"])) for e in ev]
+        events = ev.tolist()                      # [(stream, slot, frame, kind, stream_frame)] as Python ints
         deliveries: List[Delivery] = []
         for d in _view(r.deliveries, _DELIV_DT, int(r.n_deliveries)):
             frame = _view(int(d["frame"]), np.float32, int(d["frame_len"])).copy() if d["frame"] else None

@@ -190,3 +190,28 @@ def test_v4_8k_through_the_reference_facing_session():
     with pytest.raises(ValueError):
         s5.run(None, {"input": audio[:, :512], "state": np.zeros((2, 1, 128), np.float32), "sr": np.array([8000], np.int64)})
     s5.close()
+
+
+@pytest.mark.parametrize("sr,version", [(16000, "v4"), (8000, "v4_8k")])
+def test_v4_engine_against_opencv_dnn_on_the_reference_graph(engine_factory, sr, version):
+    """v4's CUDA path against a third-party ONNX runtime executing the reference's own graph (oracle/onnx_flatten.py:
+    silero_vad.onnx's 16 kHz branch / 8 kHz sub-model inside OpenCV's DNN module, h / c fed back per frame)."""
+    pytest.importorskip("cv2")
+    from conftest import V4_ONNX
+    from onnx_flatten import OpenCVSession
+    n, T = 4, 10
+    audio = synth_streams(n, 512 * T, seed=71) + 0.02 * np.random.default_rng(2).standard_normal((n, 512 * T)).astype(np.float32)
+    z = {"input": np.zeros((1, 512), np.float32), "h": np.zeros((2, 1, 64), np.float32), "c": np.zeros((2, 1, 64), np.float32),
+         "sr": np.array([sr], np.int64)}
+    sess = OpenCVSession(str(V4_ONNX), z, ["input", "h", "c"])
+    want = np.zeros((n, T))
+    for s in range(n):
+        h = c = np.zeros((2, 1, 64), np.float32)
+        for j in range(T):
+            out, h, c = sess.run({"input": audio[s:s + 1, j * 512:(j + 1) * 512].astype(np.float32), "h": h, "c": c})
+            want[s, j] = float(out.reshape(-1)[0])
+    eng = engine_factory(32, model_version=version)
+    eng.reset()
+    eng.configure(enable_denoising=False)
+    got = eng.step(audio.astype(np.float32)).probs
+    assert np.abs(got - want).max() <= TOL
