@@ -902,7 +902,12 @@ int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, 
         ln.busy = false;
         return fail(e, CVAD_E_INVALID, "stream_stride shorter than one stream's samples in this step");
     }
-    const size_t audio_elems = (size_t)(n - 1) * a->stream_stride + last_row;
+    // rows much wider than what this step reads (a caller stepping the first frames of a longer block): only the
+    // samples that are read cross PCIe, as a 2-D copy into a dense device block
+    const size_t row_al = (row + 7) & ~(size_t)7;
+    const bool dense2d = n > 1 && !a->src_rates && (size_t)a->stream_stride > row_al + row_al / 4;
+    const size_t dev_stride = dense2d ? row_al : (size_t)a->stream_stride;
+    const size_t audio_elems = dense2d ? (size_t)n * row_al : (size_t)(n - 1) * a->stream_stride + last_row;
     const size_t audio_bytes = audio_elems * es;
     auto bail = [&](int code) { ln.busy = false; return code; };
 
@@ -928,11 +933,21 @@ int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, 
     const void *src_audio = a->audio;
     if (!direct) {
         unsigned char *stage = hin + ((small_in + 63) / 64) * 64;
-        std::memcpy(stage, a->audio, audio_bytes);
+        if (dense2d) {
+            for (int i = 0; i < n; ++i)
+                std::memcpy(stage + (size_t)i * row_al * es,
+                            static_cast<const unsigned char *>(a->audio) + (size_t)i * a->stream_stride * es, row * es);
+        } else {
+            std::memcpy(stage, a->audio, audio_bytes);
+        }
         src_audio = stage;
     }
     cudaStream_t st = ln.stream;
-    CU_TRY(e, cudaMemcpyAsync(ln.d_audio.p, src_audio, audio_bytes, cudaMemcpyHostToDevice, st));
+    if (direct && dense2d)
+        CU_TRY(e, cudaMemcpy2DAsync(ln.d_audio.p, row_al * es, src_audio, (size_t)a->stream_stride * es, row * es, (size_t)n,
+                                    cudaMemcpyHostToDevice, st));
+    else
+        CU_TRY(e, cudaMemcpyAsync(ln.d_audio.p, src_audio, audio_bytes, cudaMemcpyHostToDevice, st));
     if (a->slots) CU_TRY(e, cudaMemcpyAsync(ln.d_slots.p, h_slots, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     if (a->n_frames) CU_TRY(e, cudaMemcpyAsync(ln.d_nframes.p, h_nfr, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     if (a->src_rates) CU_TRY(e, cudaMemcpyAsync(ln.d_rates.p, h_rates, (size_t)n * 4, cudaMemcpyHostToDevice, st));
@@ -941,6 +956,7 @@ int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, 
 
     cvad_step_args d = *a;
     d.audio = ln.d_audio.p;
+    d.stream_stride = (int64_t)dev_stride;
     d.slots = a->slots ? static_cast<const int32_t *>(ln.d_slots.p) : nullptr;
     d.n_frames = a->n_frames ? static_cast<const int32_t *>(ln.d_nframes.p) : nullptr;
     d.src_rates = a->src_rates ? static_cast<const int32_t *>(ln.d_rates.p) : nullptr;

@@ -9,6 +9,7 @@
 // Included by cvad_capi.cu (one translation unit); plain C++17, no device code.
 #pragma once
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -58,6 +59,11 @@ struct cvad_feeder {
     int64_t row = 0;
     int tmax = 0;
     int threads = 1;
+    // layout of the gathered block: rows ([n][row], frame j of stream k at k*row + j*hop) or, for the frame-by-frame
+    // rounds of cvad_feeder_step, planes ([tmax][n][plane_row]: plane r holds everybody's r-th frame, contiguous, so
+    // that round 0 is ONE dense host-to-device copy)
+    bool planes = false;
+    int64_t plane_row = 0;
 };
 
 namespace {
@@ -110,7 +116,12 @@ int feeder_grow_stage(cvad_feeder *f, int which, size_t bytes) {
 // Phase 1 of a step, under the lock: pick the streams that hold at least one whole frame, copy their
 // pending samples into a dense [n][row] block (split_into_frames' input, audio.py:164-190) and drop
 // what the step will consume from the arena (leftovers shorter than a hop stay for the next step).
-int feeder_gather(cvad_feeder *f) {
+inline const unsigned char *feeder_frame_ptr(const cvad_feeder *f, const unsigned char *stage, int n, int k, int j, int64_t step_len) {
+    if (f->planes) return stage + (((size_t)j * (size_t)n + (size_t)k) * (size_t)f->plane_row) * f->es;
+    return stage + ((size_t)k * (size_t)f->row + (size_t)j * (size_t)step_len) * f->es;
+}
+
+int feeder_gather(cvad_feeder *f, bool allow_planes = false) {
     std::lock_guard<std::mutex> lk(f->mu);
     f->cur ^= 1;
     f->ids.clear(); f->counts.clear(); f->rates.clear();
@@ -140,7 +151,10 @@ int feeder_gather(cvad_feeder *f) {
     if (!mixed) row = (int64_t)(tmax - 1) * f->hop + f->frame_len;
     row += (-row) & 7;                         // rows start 16-byte aligned in either sample format
     f->row = row;
-    int rc = feeder_grow_stage(f, f->cur, (size_t)n * (size_t)row * f->es);
+    f->planes = allow_planes && !mixed && tmax >= 2 && tmax <= 4;
+    f->plane_row = ((int64_t)f->frame_len + 7) & ~(int64_t)7;
+    const size_t stage_bytes = f->planes ? (size_t)tmax * (size_t)n * (size_t)f->plane_row * f->es : (size_t)n * (size_t)row * f->es;
+    int rc = feeder_grow_stage(f, f->cur, stage_bytes);
     if (rc) return rc;
     unsigned char *stage = f->stage[f->cur];
     auto work = [&](int k0, int k1) {
@@ -151,7 +165,13 @@ int feeder_gather(cvad_feeder *f) {
             const int64_t have = f->fill[s];
             const int64_t used = (int64_t)f->counts[k] * (mixed ? sl.n_in : f->hop);
             const int64_t need = mixed ? used : (int64_t)(f->counts[k] - 1) * f->hop + f->frame_len;
-            std::memcpy(stage + (size_t)k * (size_t)row * f->es, src, (size_t)need * f->es);
+            if (f->planes) {
+                for (int j = 0; j < f->counts[k]; ++j)
+                    std::memcpy(stage + (((size_t)j * (size_t)n + (size_t)k) * (size_t)f->plane_row) * f->es,
+                                src + (size_t)j * (size_t)f->hop * f->es, (size_t)f->frame_len * f->es);
+            } else {
+                std::memcpy(stage + (size_t)k * (size_t)row * f->es, src, (size_t)need * f->es);
+            }
             const int64_t rem = have - used;
             if (rem > 0) std::memmove(src, src + (size_t)used * f->es, (size_t)rem * f->es);
             f->fill[s] = rem > 0 ? rem : 0;
@@ -198,13 +218,13 @@ void feeder_deliver(cvad_feeder *f) {
             sl.active = !(last & CVAD_FLAG_ENDED) && (last & (CVAD_FLAG_STARTED | CVAD_FLAG_CONTINUING));
             continue;
         }
-        const unsigned char *rowp = stage + (size_t)k * (size_t)f->row * f->es;
+
         const bool raw_mode = sl.payload >= CVAD_PAYLOAD_SEGMENTS && sl.rate != 16000;   // host resamples the payloads
         const int64_t step_len = mixed ? sl.n_in : f->hop;
         const int flen = mixed ? sl.n_in : f->frame_len;
         for (int j = 0; j < c; ++j) {
             const uint8_t b = fl[j];
-            const unsigned char *fp = rowp + (size_t)j * (size_t)step_len * f->es;
+            const unsigned char *fp = feeder_frame_ptr(f, stage, n, k, j, step_len);
             cvad_delivery d{};
             d.slot = s; d.stream = k; d.step_frame = j; d.flags = b;
             d.prob = pr[j];
@@ -490,8 +510,8 @@ static void feeder_fill_result(cvad_feeder *f, cvad_feeder_result *r) {
     r->events = f->events.data();
     r->n_deliveries = (int32_t)f->deliveries.size();
     r->deliveries = f->deliveries.data();
-    r->raw = f->stage[f->cur];
-    r->raw_stride = f->row;
+    r->raw = f->planes ? nullptr : f->stage[f->cur];     // the row block (hooks, multi-frame steps); NULL after a step in rounds
+    r->raw_stride = f->planes ? 0 : f->row;
 }
 
 int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *r) {
@@ -499,7 +519,7 @@ int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *r) {
     if (!f->eng) return ffail(f, CVAD_E_NOGPU, "feeder has no engine: there is no CPU fallback");
     using clk = std::chrono::steady_clock;
     const auto t0 = clk::now();
-    int rc = feeder_gather(f);
+    int rc = feeder_gather(f, true);
     if (rc) return rc;
     const auto t1 = clk::now();
     const int n = (int)f->ids.size(), T = f->tmax;
@@ -507,7 +527,74 @@ int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *r) {
     f->probs.assign((size_t)n * T, 0.f);
     f->flags.assign((size_t)n * T, 0);
     f->status.assign((size_t)n, 0);
-    if (n > 0) {
+    // A few frames per stream, most streams with fewer than the maximum (arrival jitter): frame by frame, each round
+    // over the streams that still have one -- every round is a one-frame step (the fused kernel), and only round 0
+    // touches every stream.  Many frames for everybody (a producer that batches) stay one multi-frame step.
+    const bool rounds = n > 0 && f->planes;
+    if (rounds) {
+        const size_t flen_al = (size_t)f->plane_row;
+        std::vector<int32_t> sub_slots, sub_k;
+        std::vector<float> sub_probs;
+        std::vector<uint8_t> sub_flags, sub_status;
+        std::vector<cvad_event> sub_events;
+        for (int r = 0; r < T; ++r) {
+            sub_slots.clear(); sub_k.clear();
+            for (int k = 0; k < n; ++k)
+                if (f->counts[k] > r) { sub_k.push_back(k); sub_slots.push_back(f->ids[k]); }
+            const int nr = (int)sub_k.size();
+            if (nr == 0) break;
+            const void *audio = f->stage[f->cur];     // plane 0: everybody's first frame
+            int64_t stride = (int64_t)flen_al;
+            if (r > 0) {
+                // the r-th frames of the streams that have one, packed into the other pinned buffer
+                if ((rc = feeder_grow_stage(f, f->cur ^ 1, (size_t)nr * flen_al * f->es))) { f->events.clear(); return rc; }
+                unsigned char *dst = f->stage[f->cur ^ 1];
+                for (int i = 0; i < nr; ++i)
+                    std::memcpy(dst + (size_t)i * flen_al * f->es,
+                                feeder_frame_ptr(f, f->stage[f->cur], n, sub_k[i], r, f->hop), (size_t)f->frame_len * f->es);
+                audio = dst;
+            }
+            sub_probs.assign((size_t)nr, 0.f);
+            sub_flags.assign((size_t)nr, 0);
+            sub_status.assign((size_t)nr, 0);
+            sub_events.resize((size_t)std::max(16, 2 * nr));
+            int nev = 0;
+            cvad_step_args a{};
+            a.n_streams = nr;
+            a.slots = sub_slots.data();
+            a.audio = audio;
+            a.pcm_format = f->pcm_format;
+            a.stream_stride = stride;
+            a.max_frames = 1;
+            a.frame_len = f->frame_len;
+            a.hop = f->hop;
+            a.src_rate = f->src_rate;
+            a.probs_out = sub_probs.data();
+            a.flags_out = sub_flags.data();
+            a.status_out = sub_status.data();
+            a.events_out = sub_events.data();
+            a.max_events = (int32_t)sub_events.size();
+            a.n_events_out = &nev;
+            rc = cvad_step(f->eng, &a);
+            if (rc) { f->events.clear(); return ffail(f, rc, cvad_last_error(f->eng)); }
+            for (int i = 0; i < nr; ++i) {
+                if (sub_status[i]) { f->events.clear(); return ffail(f, CVAD_E_INVALID, "Audio data contains infinite or NaN values"); }
+                f->probs[(size_t)sub_k[i] * T + r] = sub_probs[i];
+                f->flags[(size_t)sub_k[i] * T + r] = sub_flags[i];
+            }
+            for (int i = 0; i < std::min(nev, (int)sub_events.size()); ++i) {
+                cvad_event ev = sub_events[i];
+                ev.stream = sub_k[ev.stream];
+                ev.frame = r;
+                f->events.push_back(ev);
+            }
+        }
+        std::sort(f->events.begin(), f->events.end(), [](const cvad_event &x, const cvad_event &y) {
+            if (x.stream != y.stream) return x.stream < y.stream;
+            if (x.frame != y.frame) return x.frame < y.frame;
+            return x.kind < y.kind;
+        });
+    } else if (n > 0) {
         const int max_events = std::max(16, 2 * n * T);
         f->events.resize((size_t)max_events);
         int nev = 0;

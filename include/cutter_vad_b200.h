@@ -287,7 +287,9 @@ typedef struct cvad_feeder_result {
     int32_t n_deliveries;
     const cvad_event *events;          /* stream-then-frame order */
     const cvad_delivery *deliveries;   /* stream-then-frame order */
-    const void *raw;                   /* the block that was stepped: [n_streams][raw_stride] samples, PCM format of the feeder */
+    const void *raw;                   /* the block that was stepped: [n_streams][raw_stride] samples, PCM format of the feeder;
+                                          NULL when the step ran frame by frame (2..4 frames per stream: the feeder then gathers
+                                          frame-major planes and runs one one-frame step per round) */
     int64_t raw_stride;
     double gather_ms, gpu_ms, deliver_ms;   /* wall time of the three phases of this step (framing, cvad_step, callbacks' side) */
 } cvad_feeder_result;

@@ -319,3 +319,30 @@ def test_extreme_inputs_stay_finite_and_on_the_oracle(engine_factory, ref_v5, ca
     steps = np.stack([eng.step(x[:, j * 512:(j + 1) * 512]).probs[:, 0] for j in range(T)], axis=1)
     assert np.isfinite(one).all() and np.isfinite(steps).all()
     assert np.abs(one - want).max() <= TOL and np.abs(steps - want).max() <= TOL
+
+
+def test_wide_rows_only_the_samples_read_are_copied(engine_factory):
+    """stream_stride much larger than what the step reads (the feeder stepping the first frame of longer rows): the
+    host path copies a dense block (2-D copy for pinned input, row-wise staging for pageable input); results are
+    those of a tight block, bit for bit, for float32 and int16, one and several frames."""
+    import ctypes as C
+    from real_time_vad.engine import capi
+    n, wide = 70, 4096
+    audio = synth_streams(n, wide, seed=97)
+    eng = engine_factory(128)
+    eng.configure(enable_denoising=True)
+    L = capi.lib()
+    for dtype, fmt in ((np.float32, capi.PCM_F32), (np.int16, capi.PCM_S16_32767)):
+        block = audio if dtype is np.float32 else np.clip(np.round(audio * 32767.0), -32768, 32767).astype(np.int16)
+        ptr = L.cvad_alloc_pinned(block.nbytes)
+        pinned = np.frombuffer((C.c_char * block.nbytes).from_address(ptr), dtype).reshape(block.shape)
+        pinned[:] = block
+        for T in (1, 3):
+            tight = np.ascontiguousarray(block[:, :512 * T])
+            eng.reset()
+            want = eng.step(tight, pcm_format=fmt, max_frames=T).probs
+            for src in (block, pinned):                                  # pageable, pinned
+                eng.reset()
+                got = eng.step(src, pcm_format=fmt, max_frames=T).probs
+                assert np.array_equal(got, want), (dtype, T)
+        L.cvad_free_pinned(ptr)
