@@ -305,7 +305,8 @@ int cvad_feeder_create(cvad_engine *e, int max_streams, int pcm_format, int fram
     f->src_rate = src_rate;
     f->es = pcm_format == CVAD_PCM_F32 ? 4 : 2;
     f->max_step_frames = capacity_frames;
-    f->cap = (size_t)frame_len + (size_t)(capacity_frames + 1) * (size_t)std::max(hop, frame_len);
+    // rows start small (the arena is max_streams rows of pinned memory) and grow when a producer runs ahead of step()
+    f->cap = (size_t)frame_len + (size_t)(std::min(capacity_frames, 3) + 1) * (size_t)std::max(hop, frame_len);
     f->cap += (-(int64_t)f->cap) & 7;
     const size_t bytes = (size_t)max_streams * f->cap * f->es;
     if (e) {
