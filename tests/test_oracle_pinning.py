@@ -173,15 +173,13 @@ def test_oracle_agrees_with_pytorch_modules_fed_the_files_raw_tensors(ref_v5):
     assert want.max() > 0.9 and want.min() < 0.05             # the comparison covers the whole probability range
 
 
-cv2 = pytest.importorskip("cv2", reason="OpenCV's DNN module is the third-party ONNX executor of this pin")
-
-
 def test_v5_graph_executed_by_opencv_dnn_matches_the_goldens_and_the_c_restatement(ref_v5):
     """A third-party ONNX runtime on the reference's OWN graph.  onnxruntime is absent, OpenCV's DNN module is not: the
     16 kHz branch of silero_vad_v5.onnx, flattened (oracle/onnx_flatten.py: taken If branches inlined, shape arithmetic
     folded, compute nodes / attributes / weights as the file has them), is executed by cv2.dnn with the state fed
     back frame after frame, and must give the golden probabilities and states that the reference's Python produced on
     the numpy interpreter, and what the C restatement (the GPU checker) gives on speech-like streams."""
+    pytest.importorskip("cv2", reason="OpenCV's DNN module is the third-party ONNX executor of this pin")
     from onnx_flatten import OpenCVSession
     from conftest import synth_streams
     g = np.load(GOLDEN / "v5_frames.npz")
@@ -212,6 +210,7 @@ def test_v5_graph_executed_by_opencv_dnn_matches_the_goldens_and_the_c_restateme
 @pytest.mark.parametrize("sr", [16000, 8000])
 def test_v4_graph_executed_by_opencv_dnn_matches_the_interpreter(sr):
     """Same pin for silero_vad.onnx: its 16 kHz branch and its 8 kHz sub-model (two LSTM time steps per frame)."""
+    pytest.importorskip("cv2", reason="OpenCV's DNN module is the third-party ONNX executor of this pin")
     from onnx_flatten import OpenCVSession
     from onnx_interp import OnnxInterpreter
     from conftest import V4_ONNX, synth_streams
