@@ -759,27 +759,34 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     const int s = unit >> 6, c8 = unit & 63;
                     if (ok[u4]) {
                         const bool dn = s_dn[s] != 0;
-                        bool bad = false;
+                        // int16 PCM is scaled first (one uniform branch per unit, not per sample); the non-finite test is
+                        // one integer maximum over the unit: exponent all ones <=> NaN or Inf (audio.py:227-228)
+                        if (p.pcm == 1) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[u4][e] = __fdiv_rn(v[u4][e], 32767.0f);
+                        } else if (p.pcm == 2) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[u4][e] = v[u4][e] * (1.0f / 32768.0f);
+                        }
+                        uint32_t amx = 0u;
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            float x = v[u4][e];
-                            if (p.pcm == 1) x = __fdiv_rn(x, 32767.0f);
-                            else if (p.pcm == 2) x = x * (1.0f / 32768.0f);
-                            if (!isfinite(x)) bad = true;
-                            if (dn && !(fabsf(x) > 0.01f)) x = 0.0f;
-                            v[u4][e] = x;
+                            const float x = v[u4][e];
+                            amx = max(amx, __float_as_uint(x) & 0x7fffffffu);
+                            v[u4][e] = (dn && !(fabsf(x) > 0.01f)) ? 0.0f : x;
                         }
-                        if (bad && p.status) atomicOr(&p.status[st * kTile + s], 1u);
+                        if (amx >= 0x7f800000u && p.status) atomicOr(&p.status[st * kTile + s], 1u);
                     }
-                    if (H16) continue;
-                    uint32_t w[3][4];
+                    if constexpr (!H16) {
+                        uint32_t w[3][4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) split3x2(v[u4][2 * e], v[u4][2 * e + 1], w[0][e], w[1][e], w[2][e]);
-                    const uint32_t seg = (uint32_t)c8 >> 4, kk = ((uint32_t)c8 & 15u) * 8u;   // k inside the 128-sample segment
-                    const uint32_t off = tc::sw128_offset(seg * 32u + (uint32_t)s, kk, 128u);
+                        for (int e = 0; e < 4; ++e) split3x2(v[u4][2 * e], v[u4][2 * e + 1], w[0][e], w[1][e], w[2][e]);
+                        const uint32_t seg = (uint32_t)c8 >> 4, kk = ((uint32_t)c8 & 15u) * 8u;   // k inside the 128-sample segment
+                        const uint32_t off = tc::sw128_offset(seg * 32u + (uint32_t)s, kk, 128u);
 #pragma unroll
-                    for (int part = 0; part < 3; ++part)
-                        *reinterpret_cast<uint4 *>(act + part * kAudPart + off) = make_uint4(w[part][0], w[part][1], w[part][2], w[part][3]);
+                        for (int part = 0; part < 3; ++part)
+                            *reinterpret_cast<uint4 *>(act + part * kAudPart + off) = make_uint4(w[part][0], w[part][1], w[part][2], w[part][3]);
+                    }
                 }
                 if (H16) {
                     CVAD_PROF(20);
