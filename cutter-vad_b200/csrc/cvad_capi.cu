@@ -51,6 +51,7 @@ struct cvad_engine {
     bool v4_t2 = false;                // CVAD_MODEL_V4_8K: two LSTM time steps per frame
     bool fuse_single_frame = true;     // CVAD_FUSE=0 keeps the two-kernel form for one-frame steps (measurement)
     bool h16_multi = true;             // CVAD_H16_MULTI=0: multi-frame steps of CVAD_MATH_TC16 run the BF16-split kernels
+    bool chain_steps = true;           // CVAD_CHAIN=0: device-pointer steps are not chained (memsets + event record per step; measurement)
     unsigned char *w_fe_tc = nullptr, *w_rec_tc = nullptr;
     unsigned char *w_fe_h = nullptr, *w_rec_h = nullptr;   // CVAD_MATH_TC16: two FP16 parts, per-layer scale
     float tc16_inv_w[8] = {0};
@@ -68,6 +69,12 @@ struct cvad_engine {
     // scratch shared by every step (kernels of consecutive steps are serialised by `last_done`)
     DevBuf d_status_dev, d_feat, d_dbg, d_cfg_slots;
     cudaEvent_t last_done = nullptr;   // recorded after the kernels of the most recent step
+    // chained device-pointer steps (cvad_step_device, fused one-frame kernel): consecutive steps are launched with
+    // programmatic stream serialization and NOTHING between the kernels -- no memset (the kernel clears its status words
+    // and counts events in `d_evctr`), no event record (`last_done` is recorded lazily, when another stream needs it)
+    int *d_evctr = nullptr;            // {event count of the step in flight, CTA ticket}; zero between steps
+    bool chain_pending = false;        // the tail of `chain_stream` is a chained kernel without a `last_done` record
+    cudaStream_t chain_stream = nullptr;
     float *rs_rt[3] = {nullptr, nullptr, nullptr};  // R^T for 8 / 24 / 48 kHz, built on first use
     unsigned char *rs_tc[3] = {nullptr, nullptr, nullptr};  // the same operators as BF16x3 tiles for resample_tc_kernel
     unsigned char *rs_h[3] = {nullptr, nullptr, nullptr};   // ... and as two scaled FP16 parts (CVAD_MATH_TC16)
@@ -584,11 +591,32 @@ int ensure_rt_tc(cvad_engine *e, int src_rate, cudaStream_t stream) {
 
 // `rates_mask`: which of the rate slots {8000, 24000, 48000, 16000} may occur in a->src_rates (bit r); callers
 // that cannot look at the array (device-pointer steps) pass 0xF
+// Does this step run as ONE fused kernel on 16 kHz input (the form cvad_step_device chains)?
+bool fused_single_frame(const cvad_engine *e, const cvad_step_args *a) {
+    return e->chain_steps && e->version == CVAD_MODEL_V5 && e->math != CVAD_MATH_FP32 && a->max_frames == 1 && e->fuse_single_frame &&
+           a->src_rates == nullptr && (a->src_rate == 0 || a->src_rate == 16000);
+}
+
+// a chained kernel sits at the tail of its stream without a `last_done` record: place the record now
+int flush_chain(cvad_engine *e) {
+    if (e->chain_pending) {
+        e->chain_pending = false;
+        CU_TRY(e, cudaEventRecord(e->last_done, e->chain_stream));
+    }
+    return CVAD_OK;
+}
+
+// `chain` (cvad_step_device on a fused one-frame step): the caller enqueued no memset; see cvad_engine::d_evctr
 int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status, int commit, float *d_dbg,
-                cudaStream_t stream, unsigned rates_mask = 0xFu) {
+                cudaStream_t stream, unsigned rates_mask = 0xFu, bool chain = false) {
     if (a->n_streams == 0 || a->max_frames == 0) return CVAD_OK;
-    // state and `feat` are shared: kernels of consecutive steps never overlap, whatever stream they use
-    CU_TRY(e, cudaStreamWaitEvent(stream, e->last_done, 0));
+    // state and `feat` are shared: kernels of consecutive steps never overlap, whatever stream they use.  A chained
+    // step behind a chained step on the same stream is ordered by the stream itself.
+    if (!(chain && e->chain_pending && e->chain_stream == stream)) {
+        int rcf = flush_chain(e);
+        if (rcf) return rcf;
+        CU_TRY(e, cudaStreamWaitEvent(stream, e->last_done, 0));
+    }
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     const bool timed = e->timing && !d_dbg;
     if (timed) {
@@ -730,12 +758,31 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         const int grid = std::min(a->max_frames * n_stiles, e->num_sms);
         if (a->max_frames == 1 && !d_dbg && e->fuse_single_frame) {
             // one frame per stream: front end + LSTM step + state machine in ONE kernel (no hand-off, no second launch)
+            if (chain) {
+                if (resampled) return fail(e, CVAD_E_INVALID, "internal: chained step on resampled input");
+                p.status_zero = 1;
+                p.ev_ctr = a->n_events_out ? e->d_evctr : nullptr;
+            }
+            // chained steps: the grid may be scheduled while the previous step's kernel is still running (its CTAs set up
+            // barriers and TMEM and prefetch weight tiles, then block in griddepcontrol.wait); not when timing events
+            // sit between the kernels
+            const bool overlap = chain && !timed;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)grid);
+            cfg.blockDim = dim3((unsigned)cvad::tc5::kThreadsTC);
+            cfg.dynamicSmemBytes = cvad::tc5::kFusedSmemTC;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = overlap ? 1 : 0;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
             if (e->math == CVAD_MATH_TC16) {
                 p.w_fe_h = e->w_fe_h; p.w_rec_h = e->w_rec_h;
                 std::memcpy(p.tc16_inv_w, e->tc16_inv_w, sizeof(p.tc16_inv_w));
-                cvad::tc5::v5tc_frontend_kernel<false, true, true><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFusedSmemTC, stream>>>(p);
+                CU_TRY(e, cudaLaunchKernelEx(&cfg, cvad::tc5::v5tc_frontend_kernel<false, true, true>, p));
             } else {
-                cvad::tc5::v5tc_frontend_kernel<false, true><<<grid, cvad::tc5::kThreadsTC, cvad::tc5::kFusedSmemTC, stream>>>(p);
+                CU_TRY(e, cudaLaunchKernelEx(&cfg, cvad::tc5::v5tc_frontend_kernel<false, true, false>, p));
             }
             CU_TRY(e, cudaGetLastError());
             e->launches++;
@@ -743,9 +790,15 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
                 CU_TRY(e, cudaEventRecord(ev[1], stream));
                 CU_TRY(e, cudaEventRecord(ev[2], stream));
             }
-            CU_TRY(e, cudaEventRecord(e->last_done, stream));
+            if (overlap) {
+                e->chain_pending = true;
+                e->chain_stream = stream;
+            } else {
+                CU_TRY(e, cudaEventRecord(e->last_done, stream));
+            }
             return CVAD_OK;
         }
+        if (chain) return fail(e, CVAD_E_INVALID, "internal: chained step outside the fused one-frame path");
         const bool h16 = e->math == CVAD_MATH_TC16 && !d_dbg && e->h16_multi;
         if (h16) {
             p.w_fe_h = e->w_fe_h; p.w_rec_h = e->w_rec_h;
@@ -1168,6 +1221,8 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
         e->fuse_single_frame = !(fz && std::strcmp(fz, "0") == 0);
         const char *hm = std::getenv("CVAD_H16_MULTI");
         e->h16_multi = !(hm && std::strcmp(hm, "0") == 0);
+        const char *ch = std::getenv("CVAD_CHAIN");
+        e->chain_steps = !(ch && std::strcmp(ch, "0") == 0);
     }
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::v4tc_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kV4tcSmem));
@@ -1206,6 +1261,8 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
             return bail(rc);
     }
     CR_TRY(cudaEventCreateWithFlags(&e->last_done, cudaEventDisableTiming));
+    CR_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_evctr), 2 * sizeof(int)));
+    CR_TRY(cudaMemset(e->d_evctr, 0, 2 * sizeof(int)));
     for (auto &ln : e->lanes) {
         CR_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
         CR_TRY(cudaMalloc(reinterpret_cast<void **>(&ln.d_nevents), sizeof(int)));
@@ -1225,7 +1282,7 @@ int cvad_destroy(cvad_engine *e) {
                     e->sm_scount, e->sm_ecount, e->frames_done, e->start_p, e->end_p, e->n_start, e->n_end,
                     e->denoise, e->d_status_dev.p, e->d_feat.p, e->d_dbg.p, e->d_cfg_slots.p, e->d_res.p,
                     e->rs_rt[0], e->rs_rt[1], e->rs_rt[2], e->rs_h[0], e->rs_h[1], e->rs_h[2], e->w_fe_tc, e->w_rec_tc, e->w_fe_h, e->w_rec_h, e->nyq_w, e->b_rec_tc,
-                    e->d_feat_tc.p, e->d_prof, e->d_rate_lists.p, e->d_v4_mag.p, e->rs_tc[0], e->rs_tc[1], e->rs_tc[2]};
+                    e->d_feat_tc.p, e->d_prof, e->d_evctr, e->d_rate_lists.p, e->d_v4_mag.p, e->rs_tc[0], e->rs_tc[1], e->rs_tc[2]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &ln : e->lanes) {
@@ -1281,6 +1338,7 @@ int cvad_set_stream(cvad_engine *e, void *cuda_stream) {
     if (!e) return CVAD_E_INVALID;
     CU_TRY(e, cudaSetDevice(e->device));
     if (e->stream) CU_TRY(e, cudaStreamSynchronize(e->stream));
+    { int rcf = flush_chain(e); if (rcf) return rcf; }
     if (cuda_stream == nullptr) {
         if (!e->own_stream) {
             CU_TRY(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -1429,12 +1487,20 @@ int cvad_step_device(cvad_engine *e, const cvad_step_args *a) {
         // status is one byte per stream at the ABI; the kernels use a 32-bit word per stream
         return fail(e, CVAD_E_INVALID, "cvad_step_device: status_out must be NULL (use cvad_step for status)");
     }
-    rc = grow(e, e->d_status_dev, (size_t)a->n_streams * sizeof(unsigned int));
-    if (rc) return rc;
+    if ((size_t)a->n_streams * sizeof(unsigned int) > e->d_status_dev.cap) {
+        // (re)allocation frees the old buffer: nothing of an earlier step may still be using it
+        if ((rc = quiesce(e))) return rc;
+        if ((rc = grow(e, e->d_status_dev, (size_t)a->n_streams * sizeof(unsigned int)))) return rc;
+    }
     d_status = static_cast<unsigned int *>(e->d_status_dev.p);
-    CU_TRY(e, cudaMemsetAsync(d_status, 0, (size_t)a->n_streams * sizeof(unsigned int), e->stream));
-    if (a->n_events_out) CU_TRY(e, cudaMemsetAsync(a->n_events_out, 0, sizeof(int), e->stream));
-    return launch_step(e, a, d_status, 1, nullptr, e->stream);
+    // fused one-frame steps on 16 kHz input are chained kernel to kernel: the kernel clears its own status words and
+    // counts events in the engine's counter, so nothing has to be enqueued between two steps' kernels
+    const bool chain = fused_single_frame(e, a);
+    if (!chain) {
+        CU_TRY(e, cudaMemsetAsync(d_status, 0, (size_t)a->n_streams * sizeof(unsigned int), e->stream));
+        if (a->n_events_out) CU_TRY(e, cudaMemsetAsync(a->n_events_out, 0, sizeof(int), e->stream));
+    }
+    return launch_step(e, a, d_status, 1, nullptr, e->stream, 0xFu, chain);
 }
 
 // Hardware probe of the tcgen05 path (test hook): D[128][32] = A[128][256] * B[32][256]^T, operands are

@@ -101,6 +101,8 @@ struct V5Step {
     void *events;                 // cvad_event[max_events] or null
     int max_events;
     int *n_events;                // device counter or null
+    int *ev_ctr;                  // chained fused steps: engine-owned {event count, CTA ticket}, both zero between steps; or null
+    int status_zero;              // chained fused steps: the kernel clears `status` itself (no memset ahead of it)
     int commit;                   // 0: do not write state back (debug)
     float *dbg;                   // front-end debug dump for tile 0, or null
     // tensor-core path (cvad_v5tc.cuh): BF16x3 weight tile streams, Nyquist-channel weights, gate biases, hand-off

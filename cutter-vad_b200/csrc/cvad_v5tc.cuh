@@ -99,6 +99,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// programmatic dependent launch, secondary side: blocks until the preceding grid of the stream has completed and its
+// writes are visible (returns at once when the kernel was launched without the attribute)
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
@@ -432,74 +435,90 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
 
     if (warp == kProducerWarp) {
         // ------------------------------------------------------------ weight producer
+        constexpr int S_TILE = H16 ? (FUSED ? kFusedSlotsPerTileH : kFeSlotsPerTileH) : FUSED ? kFusedSlotsPerTile : kFeSlotsPerTile;
+        // weight tile s of a tile's stream -> ring slot g % RING
+        auto feed = [&](const int s, const uint32_t g) {
+            const uint32_t slot = g % RING;
+            mbar_wait(&empty[slot], ((g / RING) & 1u) ^ 1u);
+            uint32_t off, bytes;
+            const unsigned char *src;
+            if (H16 && !FUSED) {
+                fe_slot_h(s, off, bytes);
+                mbar_arrive_expect_tx(&full[slot], bytes);
+                bulk_g2s(ring_buf + slot * kSlotBytes, p.w_fe_h + off, bytes, &full[slot]);
+                return;
+            }
+            if (H16) {
+                // same order with two parts: hh gate g = 4 tiles | STFT 16 | enc0 12 | enc1 12 | enc2 + enc3 6 | W_ih 16
+                int fe_idx = s, gate = -1, kb = 0, part = 0;
+                if (s < 4) { gate = 0; kb = 2 + s / 2; part = s % 2; }
+                else if (s < 20) fe_idx = s - 4;
+                else if (s < 24) { gate = 1; kb = 2 + (s - 20) / 2; part = (s - 20) % 2; }
+                else if (s < 36) fe_idx = s - 24 + 16;
+                else if (s < 40) { gate = 2; kb = 2 + (s - 36) / 2; part = (s - 36) % 2; }
+                else if (s < 52) fe_idx = s - 40 + 28;
+                else if (s < 56) { gate = 3; kb = 2 + (s - 52) / 2; part = (s - 52) % 2; }
+                else if (s < 62) fe_idx = s - 56 + 40;
+                else { const int r = s - 62; gate = r / 4; kb = (r / 2) % 2; part = r % 2; }
+                if (gate >= 0) {
+                    src = p.w_rec_h + (size_t)((gate * 4 + kb) * 2 + part) * kSlotBytes;
+                    bytes = kSlotBytes;
+                } else {
+                    fe_slot_h(fe_idx, off, bytes);
+                    src = p.w_fe_h + off;
+                }
+                mbar_arrive_expect_tx(&full[slot], bytes);
+                bulk_g2s(ring_buf + slot * kSlotBytes, src, bytes, &full[slot]);
+                return;
+            }
+            // FUSED order: hh gate 0 | STFT (24) | hh gate 1 | enc0 (18) | hh gate 2 | enc1 (18) | hh gate 3 |
+            //              enc2 + enc3 (9) | W_ih of the four gates (24).  hh gate g = 6 tiles (K blocks 2,3 x part)
+            int fe_idx = s, gate = -1, kb = 0, part = 0;
+            if (FUSED) {
+                if (s < 6) { gate = 0; kb = 2 + s / 3; part = s % 3; }
+                else if (s < 30) fe_idx = s - 6;
+                else if (s < 36) { gate = 1; kb = 2 + (s - 30) / 3; part = (s - 30) % 3; }
+                else if (s < 54) fe_idx = s - 36 + 24;
+                else if (s < 60) { gate = 2; kb = 2 + (s - 54) / 3; part = (s - 54) % 3; }
+                else if (s < 78) fe_idx = s - 60 + 42;
+                else if (s < 84) { gate = 3; kb = 2 + (s - 78) / 3; part = (s - 78) % 3; }
+                else if (s < 93) fe_idx = s - 84 + 60;
+                else { const int r = s - 93; gate = r / 6; kb = (r / 3) % 2; part = r % 3; }
+            }
+            if (gate >= 0) {
+                src = p.w_rec_tc + (size_t)((gate * 4 + kb) * 3 + part) * kSlotBytes;
+                bytes = kSlotBytes;
+            } else {
+                fe_slot(fe_idx, off, bytes);
+                src = p.w_fe_tc + off;
+            }
+            mbar_arrive_expect_tx(&full[slot], bytes);
+            bulk_g2s(ring_buf + slot * kSlotBytes, src, bytes, &full[slot]);
+        };
         uint32_t g = 0;
+        int pre = 0;                                   // weight tiles of the NEXT live tile that are already in flight
+        if (FUSED) {
+            // chained one-frame steps (programmatic dependent launch): the first RING weight tiles do not depend on
+            // the previous step's grid, so they are fetched while it is still finishing
+            if (lane == 0)
+                for (; pre < RING; ++pre, ++g) feed(pre, g);
+            pre = __shfl_sync(0xffffffffu, pre, 0);
+            griddep_wait();
+        }
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
             if (!tile_live(p, frame, st, lane, nullptr, nullptr)) continue;
-            if (lane == 0) {
-                for (int s = 0; s < (H16 ? (FUSED ? kFusedSlotsPerTileH : kFeSlotsPerTileH) : FUSED ? kFusedSlotsPerTile : kFeSlotsPerTile); ++s, ++g) {
-                    const uint32_t slot = g % RING;
-                    mbar_wait(&empty[slot], ((g / RING) & 1u) ^ 1u);
-                    uint32_t off, bytes;
-                    const unsigned char *src;
-                    if (H16 && !FUSED) {
-                        fe_slot_h(s, off, bytes);
-                        mbar_arrive_expect_tx(&full[slot], bytes);
-                        bulk_g2s(ring_buf + slot * kSlotBytes, p.w_fe_h + off, bytes, &full[slot]);
-                        continue;
-                    }
-                    if (H16) {
-                        // same order with two parts: hh gate g = 4 tiles | STFT 16 | enc0 12 | enc1 12 | enc2 + enc3 6 | W_ih 16
-                        int fe_idx = s, gate = -1, kb = 0, part = 0;
-                        if (s < 4) { gate = 0; kb = 2 + s / 2; part = s % 2; }
-                        else if (s < 20) fe_idx = s - 4;
-                        else if (s < 24) { gate = 1; kb = 2 + (s - 20) / 2; part = (s - 20) % 2; }
-                        else if (s < 36) fe_idx = s - 24 + 16;
-                        else if (s < 40) { gate = 2; kb = 2 + (s - 36) / 2; part = (s - 36) % 2; }
-                        else if (s < 52) fe_idx = s - 40 + 28;
-                        else if (s < 56) { gate = 3; kb = 2 + (s - 52) / 2; part = (s - 52) % 2; }
-                        else if (s < 62) fe_idx = s - 56 + 40;
-                        else { const int r = s - 62; gate = r / 4; kb = (r / 2) % 2; part = r % 2; }
-                        if (gate >= 0) {
-                            src = p.w_rec_h + (size_t)((gate * 4 + kb) * 2 + part) * kSlotBytes;
-                            bytes = kSlotBytes;
-                        } else {
-                            fe_slot_h(fe_idx, off, bytes);
-                            src = p.w_fe_h + off;
-                        }
-                        mbar_arrive_expect_tx(&full[slot], bytes);
-                        bulk_g2s(ring_buf + slot * kSlotBytes, src, bytes, &full[slot]);
-                        continue;
-                    }
-                    // FUSED order: hh gate 0 | STFT (24) | hh gate 1 | enc0 (18) | hh gate 2 | enc1 (18) | hh gate 3 |
-                    //              enc2 + enc3 (9) | W_ih of the four gates (24).  hh gate g = 6 tiles (K blocks 2,3 x part)
-                    int fe_idx = s, gate = -1, kb = 0, part = 0;
-                    if (FUSED) {
-                        if (s < 6) { gate = 0; kb = 2 + s / 3; part = s % 3; }
-                        else if (s < 30) fe_idx = s - 6;
-                        else if (s < 36) { gate = 1; kb = 2 + (s - 30) / 3; part = (s - 30) % 3; }
-                        else if (s < 54) fe_idx = s - 36 + 24;
-                        else if (s < 60) { gate = 2; kb = 2 + (s - 54) / 3; part = (s - 54) % 3; }
-                        else if (s < 78) fe_idx = s - 60 + 42;
-                        else if (s < 84) { gate = 3; kb = 2 + (s - 78) / 3; part = (s - 78) % 3; }
-                        else if (s < 93) fe_idx = s - 84 + 60;
-                        else { const int r = s - 93; gate = r / 6; kb = (r / 3) % 2; part = r % 3; }
-                    }
-                    if (gate >= 0) {
-                        src = p.w_rec_tc + (size_t)((gate * 4 + kb) * 3 + part) * kSlotBytes;
-                        bytes = kSlotBytes;
-                    } else {
-                        fe_slot(fe_idx, off, bytes);
-                        src = p.w_fe_tc + off;
-                    }
-                    mbar_arrive_expect_tx(&full[slot], bytes);
-                    bulk_g2s(ring_buf + slot * kSlotBytes, src, bytes, &full[slot]);
-                }
-            }
+            if (lane == 0)
+                for (int s = pre; s < S_TILE; ++s, ++g) feed(s, g);
+            pre = 0;
             __syncwarp();
         }
+        // no live tile at all: the prefetched copies must land before the CTA may exit
+        if (FUSED && pre && lane == 0)
+            for (int s = 0; s < pre; ++s) mbar_wait(&full[s], 0u);
     } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------ MMA issuer
+        if (FUSED) griddep_wait();
         uint32_t g = 0, act_phase = 0, h_phase = 0;
         const uint32_t i128_96 = H16 ? idesc_f16_f32(128, 96) : tc::idesc_bf16_f32(128, 96),
                        i128_64 = H16 ? idesc_f16_f32(128, 64) : tc::idesc_bf16_f32(128, 64),
@@ -648,10 +667,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
         uint32_t acc_phase = 0;
         const int flen = p.frame_len < 512 ? p.frame_len : 512;
+        if (FUSED) griddep_wait();
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
             int my_slot, my_valid;
-            if (!tile_live(p, frame, st, lane, &my_slot, &my_valid)) continue;
+            const bool live = tile_live(p, frame, st, lane, &my_slot, &my_valid);
+            // chained steps arrive without a memset in front of them: the tile clears its streams' status words itself
+            // (one tile per stream when max_frames == 1), ordered before the loader's atomicOr by the barrier below
+            if (FUSED && p.status_zero && warp == 0 && st * kTile + lane < p.n_streams) p.status[st * kTile + lane] = 0u;
+            if (!live) continue;
             if (warp == 0) {
                 s_slot[lane] = my_slot;
                 s_valid[lane] = my_valid;
@@ -1279,7 +1303,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                         EventRec *ev = reinterpret_cast<EventRec *>(p.events);
                         for (unsigned int kind = 1u; kind <= 2u; kind <<= 1) {
                             if (fl & kind) {
-                                const int at = atomicAdd(p.n_events, 1);
+                                const int at = atomicAdd(p.ev_ctr ? p.ev_ctr : p.n_events, 1);
                                 if (ev && at < p.max_events) {
                                     ev[at].stream = i; ev[at].slot = slot; ev[at].frame = 0;
                                     ev[at].kind = (int)kind; ev[at].stream_frame = sm_f0;
@@ -1302,6 +1326,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     tc::fence_before_sync();
     __syncthreads();
     if (warp == kProducerWarp) tc::tmem_dealloc(0u, 512);
+    if (FUSED && p.ev_ctr && tid == 0) {
+        // chained steps: events were counted in the engine's own counter (ev_ctr[0]); the last CTA to finish publishes
+        // the total and leaves counter and ticket at zero for the next step -- no memset between the kernels
+        __threadfence();
+        if (atomicAdd(p.ev_ctr + 1, 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            const int total = atomicExch(p.ev_ctr, 0);
+            if (p.n_events) *p.n_events = total;
+            atomicExch(p.ev_ctr + 1, 0);
+        }
+    }
     CVAD_PROF_NS(122);
 }
 
