@@ -48,6 +48,8 @@ def ncu_traffic_bytes(kernel: str):
     (profiles/*.json, written by tools/ncu_summary.py from the same bench command); None if absent."""
     best = None
     for f in sorted((ROOT / "profiles").glob("*.json")):
+        if "warm_caches" in f.name:      # --cache-control none captures re-read the replayed inputs from L2: not a DRAM figure
+            continue
         try:
             d = json.loads(f.read_text())
             for k in d.get("full_capture", []):
@@ -427,9 +429,19 @@ def run_ours(args):
 
     fused = math in ("tc", "tc16") and args.model == "v5" and F == 1 and os.environ.get("CVAD_FUSE", "1") != "0"
     h16 = fused and math == "tc16"      # FP16 two-way split: 3 tensor-core products per MAC (BF16 split: 6)
+    # chained one-frame steps (cvad_step_device on 16 kHz input): the timed region holds K launches of ONE kernel and
+    # nothing else -- no memset, no event -- each scheduled by programmatic dependent launch while its predecessor
+    # drains, so the kernel's average launch duration over the timed region is region / launches.  The duration of a
+    # launch bracketed by its own events (no overlap with its neighbours) is reported beside it.
+    chained = (math in ("tc", "tc16") and args.model == "v5" and F == 1 and args.src_rate == 16000 and not mixed
+               and os.environ.get("CVAD_FUSE", "1") != "0" and os.environ.get("CVAD_CHAIN", "1") != "0"
+               and launches == args.steps)
+    isolated_ms = fe_avg_s * 1e3
     if fused:
         # one kernel does the whole step (front end + LSTM step + state machine): its FLOPs are the frame's
         flop_fe = flop_frame
+        if chained:
+            fe_avg_s = dev_ms / launches * 1e-3
         fe_tflops = frames_per_step * flop_fe / fe_avg_s / 1e12 if fe_avg_s > 0 else 0.0
     if rank == 0:
         tc = math in ("tc", "tc16")
@@ -461,7 +473,11 @@ def run_ours(args):
                             "MEASURED_PEAKS.json clock); the path is FP32-FFMA bound, not HBM or tensor bound"),
             "algorithmic_flop_per_frame": flop_fe, "frames_per_launch": frames_per_step,
             "avg_launch_ms": fe_avg_s * 1e3,
-            "kernel_timing": "second pass over the same K steps with a CUDA event between the two kernels",
+            "isolated_launch_ms": isolated_ms,
+            "kernel_timing": ("avg_launch_ms = timed region (CUDA events on the engine's stream) / launches: the region holds "
+                              "nothing but this kernel's K launches, chained by programmatic dependent launch; "
+                              "isolated_launch_ms = second pass with events around every launch (no overlap)" if chained else
+                              "second pass over the same K steps with a CUDA event between the two kernels"),
             "recurrent_kernel": ({"kernel": "(fused into the kernel above for one-frame steps)", "avg_launch_ms": 0.0,
                                   "achieved": 0.0, "algorithmic_flop_per_frame": 0} if fused else
                                  {"kernel": "v5tc_recurrent_kernel" if tc else f"{args.model}_recurrent_kernel",

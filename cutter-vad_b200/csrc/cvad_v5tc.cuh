@@ -1322,21 +1322,21 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 CVAD_PROF(14);
             }
         }
+        if (FUSED && p.ev_ctr && tid == 0) {
+            // chained steps: events were counted in the engine's own counter (ev_ctr[0]); the last CTA to take a ticket
+            // publishes the total and leaves counter and ticket at zero for the next step -- no memset between the
+            // kernels.  No fence: every event atomicAdd of this CTA returned its index to warp 0 before the barrier
+            // above, i.e. it has been performed at L2, where the ticket and the exchange below are performed too.
+            if (atomicAdd(p.ev_ctr + 1, 1) == (int)gridDim.x - 1) {
+                const int total = atomicExch(p.ev_ctr, 0);
+                if (p.n_events) *p.n_events = total;
+                p.ev_ctr[1] = 0;
+            }
+        }
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == kProducerWarp) tc::tmem_dealloc(0u, 512);
-    if (FUSED && p.ev_ctr && tid == 0) {
-        // chained steps: events were counted in the engine's own counter (ev_ctr[0]); the last CTA to finish publishes
-        // the total and leaves counter and ticket at zero for the next step -- no memset between the kernels
-        __threadfence();
-        if (atomicAdd(p.ev_ctr + 1, 1) == (int)gridDim.x - 1) {
-            __threadfence();
-            const int total = atomicExch(p.ev_ctr, 0);
-            if (p.n_events) *p.n_events = total;
-            atomicExch(p.ev_ctr + 1, 0);
-        }
-    }
     CVAD_PROF_NS(122);
 }
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn gpurun_out/*.ncu-rep + launches CSV into a committed summary under profiles/.
 
-    python tools/ncu_summary.py <tag> <launches.csv> <prof.ncu-rep>
+    python tools/ncu_summary.py <tag> <launches.csv> <prof.ncu-rep> [note] [command]
 """
 import collections
 import csv
@@ -67,7 +67,8 @@ def main():
     tag, lcsv, rep = sys.argv[1:4]
     note = sys.argv[4] if len(sys.argv) > 4 else ""
     out = {"tag": tag, "note": note,
-           "command": "python bench.py --steps 20 --warmup 3 --skip-cpu  (4096 streams x 1 frame per step)",
+           "command": sys.argv[5] if len(sys.argv) > 5 else
+           "python bench.py --steps 20 --warmup 3 --skip-cpu  (4096 streams x 1 frame per step)",
            "launch_list": launches(lcsv), "full_capture": raw(rep)}
     dst = ROOT / "profiles" / f"{tag}.json"
     dst.write_text(json.dumps(out, indent=1))
