@@ -676,21 +676,24 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             // (one tile per stream when max_frames == 1), ordered before the loader's atomicOr by the barrier below
             if (FUSED && p.status_zero && warp == 0 && st * kTile + lane < p.n_streams) p.status[st * kTile + lane] = 0u;
             if (!live) continue;
+            // thresholds, denoise flag and state-machine words of the tile's streams are fetched in one batch with the slot
+            // data (their latency would otherwise sit at the very end of the tile).  FUSED: the loads are only ISSUED
+            // ahead of the barrier -- the values reach shared memory once the audio and state loads are in flight as well,
+            // so that no warp waits for this round trip before it starts its own (first readers: the loader's second
+            // half, two barriers further down)
+            double sp = 0.0, ep = 0.0;
+            int a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, dn = 0;
+            long long f0 = 0;
             if (warp == 0) {
                 s_slot[lane] = my_slot;
                 s_valid[lane] = my_valid;
-                s_dn[lane] = my_slot >= 0 ? (int)p.denoise[my_slot] : 0;
+                if (my_slot >= 0) dn = (int)p.denoise[my_slot];
+                if (!FUSED) s_dn[lane] = dn;
                 if (FUSED && my_slot >= 0) {
-                    // thresholds and state-machine words of the tile's streams, fetched in one batch with the slot data
-                    // (their latency would otherwise sit at the very end of the tile)
-                    const double sp = p.start_p[my_slot], ep = p.end_p[my_slot];
-                    const int a0 = p.sm_active[my_slot], a1 = p.sm_scount[my_slot], a2 = p.sm_ecount[my_slot];
-                    const int a3 = p.n_start[my_slot], a4 = p.n_end[my_slot];
-                    const long long f0 = p.frames_done[my_slot];
-                    s_thr[lane] = sp; s_thr[kTile + lane] = ep;
-                    s_sm[lane] = a0; s_sm[kTile + lane] = a1; s_sm[2 * kTile + lane] = a2;
-                    s_sm[3 * kTile + lane] = a3; s_sm[4 * kTile + lane] = a4;
-                    s_f0[lane] = f0;
+                    sp = p.start_p[my_slot]; ep = p.end_p[my_slot];
+                    a0 = p.sm_active[my_slot]; a1 = p.sm_scount[my_slot]; a2 = p.sm_ecount[my_slot];
+                    a3 = p.n_start[my_slot]; a4 = p.n_end[my_slot];
+                    f0 = p.frames_done[my_slot];
                 }
             }
             if (H16 && warp >= 1 && warp <= 6) amax[(warp - 1) * kTile + lane] = 0u;
@@ -698,6 +701,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             const bool dbg = DBG && tile == 0;
             const bool first_tile = tile == (int)blockIdx.x && tid == 0;
             CVAD_PROF(0);
+            CVAD_PROF_NS(126);
             // ---- frame loader (audio.py:164-190 split, :104-121 gate, silero_model.py:449-474 pad/truncate):
             //      8 samples per work unit -> 3 x 16-byte BF16 chunks of the AUD operand, row = segment*32 + item.
             //      All global loads of the thread's 4 units are issued before the first use -- and, in the fused
@@ -747,28 +751,34 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     hreg[e] = slot >= 0 ? __ldg(p.h_state + (size_t)(idx >> 5) * p.max_streams + slot) : 0.f;
                     creg[e] = slot >= 0 ? __ldg(p.c_state + (size_t)(idx >> 5) * p.max_streams + slot) : 0.f;
                 }
+                if (warp == 0) {
+                    // the slot data fetched at tile start (by now every global load of this warp is in flight)
+                    s_dn[lane] = dn;
+                    if (my_slot >= 0) {
+                        s_thr[lane] = sp; s_thr[kTile + lane] = ep;
+                        s_sm[lane] = a0; s_sm[kTile + lane] = a1; s_sm[2 * kTile + lane] = a2;
+                        s_sm[3 * kTile + lane] = a3; s_sm[4 * kTile + lane] = a4;
+                        s_f0[lane] = f0;
+                    }
+                }
+                float *sbuf_c = sbuf + 128 * 33;                // h and c are transposed side by side: one barrier each way
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int idx = e * kEpiThreads + tid;
                     sbuf[(idx >> 5) * 33 + (idx & 31)] = hreg[e];
+                    sbuf_c[(idx >> 5) * 33 + (idx & 31)] = creg[e];
                 }
                 epi_bar();
 #pragma unroll
-                for (int e = 0; e < 8; ++e) hreg[e] = sbuf[u_own * 33 + i_own + e];
+                for (int e = 0; e < 8; ++e) {
+                    hreg[e] = sbuf[u_own * 33 + i_own + e];
+                    creg[e] = sbuf_c[u_own * 33 + i_own + e];
+                }
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
                     if (H16) store_parts2_h(hbuf, 32 * 128, (uint32_t)(i_own + e), (uint32_t)u_own, 96u, hreg[e] * kHScale, hreg[e + 1] * kHScale);
                     else store_parts2(hbuf, 32 * 128, (uint32_t)(i_own + e), (uint32_t)u_own, 96u, hreg[e], hreg[e + 1]);
                 }
-                epi_bar();
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int idx = e * kEpiThreads + tid;
-                    sbuf[(idx >> 5) * 33 + (idx & 31)] = creg[e];
-                }
-                epi_bar();
-#pragma unroll
-                for (int e = 0; e < 8; ++e) creg[e] = sbuf[u_own * 33 + i_own + e];
                 tc::fence_async_smem();
                 epi_bar();                                     // also: sbuf reads done before the loader rewrites ACT
                 if (tid == 0) mbar_arrive(h_ready);
@@ -1241,9 +1251,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 dv[0] += __shfl_xor_sync(0xffffffffu, dv[0], 16);
                 if (lane < 8) dpart[q * 32 + i0 + lane] = dv[0];
                 // new state back to HBM, coalesced over streams through ACT (dead: every MMA of the tile is complete)
-                float *sbuf = reinterpret_cast<float *>(act);
+                float *sbuf = reinterpret_cast<float *>(act), *sbuf_c = sbuf + 128 * 33;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) sbuf[u * 33 + i0 + e] = hn[e];
+                for (int e = 0; e < 8; ++e) {
+                    sbuf[u * 33 + i0 + e] = hn[e];
+                    sbuf_c[u * 33 + i0 + e] = creg[e];
+                }
                 tc::fence_before_sync();
                 epi_bar();
                 if (p.commit) {
@@ -1251,19 +1264,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     for (int e = 0; e < 8; ++e) {
                         const int idx = e * kEpiThreads + tid;
                         const int s = idx & 31;
-                        if (s_valid[s]) p.h_state[(size_t)(idx >> 5) * p.max_streams + s_slot[s]] = sbuf[(idx >> 5) * 33 + s];
-                    }
-                }
-                epi_bar();
-#pragma unroll
-                for (int e = 0; e < 8; ++e) sbuf[u * 33 + i0 + e] = creg[e];
-                epi_bar();
-                if (p.commit) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int idx = e * kEpiThreads + tid;
-                        const int s = idx & 31;
-                        if (s_valid[s]) p.c_state[(size_t)(idx >> 5) * p.max_streams + s_slot[s]] = sbuf[(idx >> 5) * 33 + s];
+                        if (s_valid[s]) {
+                            const size_t at = (size_t)(idx >> 5) * p.max_streams + s_slot[s];
+                            p.h_state[at] = sbuf[(idx >> 5) * 33 + s];
+                            p.c_state[at] = sbuf_c[(idx >> 5) * 33 + s];
+                        }
                     }
                 }
                 // sigmoid(w . relu(h') + b), then the start/end state machine (silero_model.py:790-923)
@@ -1320,6 +1325,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 }
                 epi_bar();   // ACT, dpart and s_valid are rewritten by the next tile
                 CVAD_PROF(14);
+                CVAD_PROF_NS(127);
             }
         }
         if (FUSED && p.ev_ctr && tid == 0) {

@@ -40,3 +40,9 @@ for j in range(min(T, 8)):
           f" | mma: x ready {out[96 + 3 * j] - r0}, h ready {out[97 + 3 * j] - r0}, issued {out[98 + 3 * j] - r0}")
 g = out[120:126] - out[120]
 print("globaltimer ns: FE entry 0, FE prologue done", g[1], "FE exit", g[2], "| REC entry", g[3], "REC prologue done", g[4], "REC exit", g[5])
+if out[126] and out[127] and out[14]:
+    # the same two points of the tile on both clocks: SM clock actually run, and where the tile sits in the CTA's life
+    ns = int(out[127] - out[126])
+    cyc = int(out[14] - out[0])
+    print(f"tile on the global timer: start at {int(out[126] - out[120])} ns after CTA entry, {ns} ns long = {cyc} cycles "
+          f"-> {cyc / max(ns, 1) * 1e3:.0f} MHz; CTA exits {int(out[122] - out[127])} ns after the tile's last mark")
