@@ -591,10 +591,9 @@ int ensure_rt_tc(cvad_engine *e, int src_rate, cudaStream_t stream) {
 
 // `rates_mask`: which of the rate slots {8000, 24000, 48000, 16000} may occur in a->src_rates (bit r); callers
 // that cannot look at the array (device-pointer steps) pass 0xF
-// Does this step run as ONE fused kernel on 16 kHz input (the form cvad_step_device chains)?
+// Does the model part of this step run as ONE fused kernel (the form cvad_step_device chains)?
 bool fused_single_frame(const cvad_engine *e, const cvad_step_args *a) {
-    return e->chain_steps && e->version == CVAD_MODEL_V5 && e->math != CVAD_MATH_FP32 && a->max_frames == 1 && e->fuse_single_frame &&
-           a->src_rates == nullptr && (a->src_rate == 0 || a->src_rate == 16000);
+    return e->chain_steps && e->version == CVAD_MODEL_V5 && e->math != CVAD_MATH_FP32 && a->max_frames == 1 && e->fuse_single_frame;
 }
 
 // a chained kernel sits at the tail of its stream without a `last_done` record: place the record now
@@ -684,7 +683,7 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
             int *counts = lists + 4 * n;
             CU_TRY(e, cudaMemsetAsync(counts, 0, 4 * sizeof(int), stream));
             cvad::rate_lists_kernel<<<(a->n_streams + 255) / 256, 256, 0, stream>>>(a->src_rates, a->n_streams, lists, counts,
-                                                                                  d_status);
+                                                                                  d_status, chain ? 1 : 0);
             CU_TRY(e, cudaGetLastError());
             e->launches++;
             static const int kRates[3] = {8000, 24000, 48000};
@@ -759,8 +758,7 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         if (a->max_frames == 1 && !d_dbg && e->fuse_single_frame) {
             // one frame per stream: front end + LSTM step + state machine in ONE kernel (no hand-off, no second launch)
             if (chain) {
-                if (resampled) return fail(e, CVAD_E_INVALID, "internal: chained step on resampled input");
-                p.status_zero = 1;
+                p.status_zero = mixed ? 0 : 1;      // mixed rates: rate_lists_kernel has written every status word
                 p.ev_ctr = a->n_events_out ? e->d_evctr : nullptr;
             }
             // chained steps: the grid may be scheduled while the previous step's kernel is still running (its CTAs set up
@@ -1493,8 +1491,8 @@ int cvad_step_device(cvad_engine *e, const cvad_step_args *a) {
         if ((rc = grow(e, e->d_status_dev, (size_t)a->n_streams * sizeof(unsigned int)))) return rc;
     }
     d_status = static_cast<unsigned int *>(e->d_status_dev.p);
-    // fused one-frame steps on 16 kHz input are chained kernel to kernel: the kernel clears its own status words and
-    // counts events in the engine's counter, so nothing has to be enqueued between two steps' kernels
+    // fused one-frame steps are chained kernel to kernel: the kernel (or, with per-stream rates, rate_lists_kernel)
+    // clears the status words and events are counted in the engine's counter, so nothing but kernels is enqueued
     const bool chain = fused_single_frame(e, a);
     if (!chain) {
         CU_TRY(e, cudaMemsetAsync(d_status, 0, (size_t)a->n_streams * sizeof(unsigned int), e->stream));

@@ -184,13 +184,16 @@ __device__ __host__ __forceinline__ int rate_slot(int rate) {
 }
 
 // lists[r][0 .. counts[r]) = indices of the streams whose source rate has slot r (order is irrelevant:
-// streams are independent); a stream with an unknown rate gets status bit 2
-__global__ void rate_lists_kernel(const int *src_rates, int n, int *lists, int *counts, unsigned int *status) {
+// streams are independent); a stream with an unknown rate gets status bit 2.  `init_status` (chained steps: no memset
+// ahead of the step): this kernel, the first of the step to touch `status`, writes every stream's word
+__global__ void rate_lists_kernel(const int *src_rates, int n, int *lists, int *counts, unsigned int *status,
+                                  int init_status) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int r = rate_slot(src_rates[i]);
+    if (status && init_status) status[i] = r < 0 ? 2u : 0u;
     if (r < 0) {
-        if (status) atomicOr(&status[i], 2u);
+        if (status && !init_status) atomicOr(&status[i], 2u);
         return;
     }
     lists[(size_t)r * n + atomicAdd(&counts[r], 1)] = i;

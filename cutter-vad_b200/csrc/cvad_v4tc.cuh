@@ -240,6 +240,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) resample_tc_kernel(const Resamp
     __syncthreads();
     tc::fence_after_sync();
     if (*tmem_slot != 0u) __trap();
+    // chained steps launch the model kernel with programmatic stream serialization: its grid may be scheduled now (it sets
+    // up, prefetches weights and blocks in griddepcontrol.wait until this grid has completed)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int n_items = p.count ? *p.count : p.n_streams;
     const int n_st = (n_items + kRsTcTile - 1) / kRsTcTile;
