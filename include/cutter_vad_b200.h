@@ -189,9 +189,9 @@ int cvad_step_collect(cvad_engine *e, int ticket);
  * DEVICE memory; enqueues on the engine's stream and returns without synchronising.
  * events_out/n_events_out (device) are filled by the kernel in arbitrary order; n_events_out
  * holds the step's total once the step has finished (its value in between is unspecified).
- * One-frame steps of the v5 tensor-core builds on 16 kHz input are chained: consecutive
- * calls enqueue nothing but one kernel each, launched with programmatic stream
- * serialization, so a step's grid is scheduled while its predecessor drains (every read of
+ * One-frame steps of the v5 tensor-core builds are chained: consecutive calls enqueue
+ * nothing but kernels (no memset, no event record), the model kernel launched with
+ * programmatic stream serialization, so a step's grid is scheduled while its predecessor drains (every read of
  * `a`'s buffers still happens after whatever precedes the call on the stream has completed).
  */
 int cvad_step_device(cvad_engine *e, const cvad_step_args *a);
