@@ -5,8 +5,9 @@ kernel by programmatic dependent launch: no memset and no event record between t
 words, counts events in an engine-owned counter that the last CTA publishes, and prefetches weight tiles before
 `griddepcontrol.wait`).  Everything below compares that path, bit for bit, with the host-buffer call `cvad_step` on a
 second engine fed the same audio: probabilities, flags, event records and counts, for partial tiles, dead tiles
-(n_frames == 0 for a whole tile), slot indirection, NaN input, with timing events between the kernels, and with host
-steps interleaved on the same engine.
+(n_frames == 0 for a whole tile), slot indirection, NaN input, with timing events between the kernels, with host
+steps interleaved on the same engine, and on source-rate input (one rate, per-stream rates, an unknown rate), where the
+resampler kernel runs ahead of the chained model kernel.
 """
 import numpy as np
 import pytest
