@@ -19,6 +19,7 @@
 #include "cvad_tc.cuh"
 #include "cvad_v4.cuh"
 #include "cvad_v4tc.cuh"
+#include "cvad_fftk.cuh"
 #include "cvad_v5tc.cuh"
 
 namespace {
@@ -58,6 +59,12 @@ struct cvad_engine {
     float *nyq_w = nullptr, *b_rec_tc = nullptr;
     DevBuf d_feat_tc;
     DevBuf d_v4_mag;                   // v4 tensor-core path: |STFT| tiles between the two front-end kernels
+    // double-precision FFT path (cvad_fftk.cuh): the resampler of every model, and v4's STFT (CVAD_MATH_FFT)
+    double2 *fft_T = nullptr;          // master twiddle table exp(-2 pi i j / 1536)
+    int resampler = CVAD_RESAMPLE_FFT;
+    unsigned char *w_v4_corr = nullptr;// v4: (file basis - exact Hann x DFT basis) * 2^24 as 8 single-part BF16 tiles
+    bool v4_fft_ok = false;            // the blob's basis IS Hann x DFT-256 up to float32 rounding (else CVAD_MATH_FFT is refused)
+    DevBuf d_v4_fft;                   // exact-basis STFT tiles between v4_stft_fft_kernel and v4tc_stft_kernel<true>
     long long *d_prof = nullptr;       // 128 clock64 marks of CTA 0 (cvad_set_profile)
     // per-slot state
     float *h_state = nullptr, *c_state = nullptr;
@@ -79,6 +86,7 @@ struct cvad_engine {
     unsigned char *rs_tc[3] = {nullptr, nullptr, nullptr};  // the same operators as BF16x3 tiles for resample_tc_kernel
     unsigned char *rs_h[3] = {nullptr, nullptr, nullptr};   // ... and as two scaled FP16 parts (CVAD_MATH_TC16)
     float rs_h_inv[3] = {1.f, 1.f, 1.f};
+    DevBuf d_mono;                     // interleaved multi-channel input averaged to mono (cvad_step_args::channels > 1)
     DevBuf d_res;                      // resampled 16 kHz audio of the step being launched
     DevBuf d_rate_lists;               // mixed-rate steps: [4][n] stream lists + 4 counters
     // host-buffer steps run on kLanes lanes so that later steps' H2D copies overlap earlier steps' kernels and D2H
@@ -396,6 +404,41 @@ std::vector<unsigned char> pack_v4_stft_tc(const float *blob) {
     return out;
 }
 
+// v4 FFT path: delta = (the file's float32 STFT basis) - (periodic Hann x DFT-256, evaluated in double) -- what the
+// exact-basis FFT lacks.  Scaled by 2^24 it is O(1) and goes to the tensor cores as ONE BF16 part per weight
+// (8 tiles, blk x kb, same row packing as pack_v4_stft_tc).  Returns max |delta| (7.7e-8 for the reference's file).
+double pack_v4_stft_corr(const float *blob, const double2 *T, std::vector<unsigned char> &out) {
+    const float *basis = blob;   // [258][256]: rows 0..128 real part, 129..257 imaginary part (-sin)
+    double worst = 0.0;
+    std::vector<float> delta(258 * 256);
+    for (int row = 0; row < 258; ++row) {
+        const int k = row < 129 ? row : row - 129;
+        for (int n = 0; n < 256; ++n) {
+            const double2 w = T[6 * ((k * n) & 255)];                 // exp(-2 pi i k n / 256)
+            const double hann = 0.5 - 0.5 * T[6 * n].x;
+            const double exact = hann * (row < 129 ? w.x : w.y);
+            const double d = (double)basis[row * 256 + n] - exact;
+            worst = std::max(worst, std::fabs(d));
+            delta[row * 256 + n] = (float)(d * 16777216.0);
+        }
+    }
+    out.clear();
+    out.reserve(cvad::tc5::kV4CorrStreamBytes);
+    for (int blk = 0; blk < 2; ++blk)
+        for (int kb = 0; kb < 4; ++kb) {
+            const size_t tile = 128 * 128, at = out.size();
+            out.resize(at + tile, 0);
+            for (int r = 0; r < 128; ++r)
+                for (int kk = 0; kk < 64; ++kk) {
+                    const int row = blk == 0 ? r : (r == 0 ? 128 : 129 + r);
+                    const uint16_t b = bf16_rn_bits(delta[row * 256 + kb * 64 + kk]);
+                    const size_t off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((((kk >> 3) ^ r) & 7) << 4) + (size_t)(kk & 7) * 2;
+                    std::memcpy(&out[at + off], &b, 2);
+                }
+        }
+    return worst;
+}
+
 // ---- v4 weight repack (canonical blob order: oracle/silero_ref.c "Silero VAD v4")
 V5Packed pack_v4(const float *blob) {
     const float *p = blob;
@@ -510,6 +553,9 @@ int validate_args(cvad_engine *e, const cvad_step_args *a) {
     if (a->pcm_format < 0 || a->pcm_format > 2) return fail(e, CVAD_E_INVALID, "unknown pcm_format");
     if (a->max_frames < 0) return fail(e, CVAD_E_INVALID, "max_frames < 0");
     if (a->max_events < 0) return fail(e, CVAD_E_INVALID, "max_events < 0");
+    if (a->channels < 0 || a->channels > 8) return fail(e, CVAD_E_INVALID, "channels outside [0, 8]");
+    if (a->channels > 1 && a->stream_stride % a->channels != 0)
+        return fail(e, CVAD_E_INVALID, "stream_stride must be a multiple of channels");
     if (a->src_rates) return CVAD_OK;   // per-stream rates: frame_len / hop / src_rate are not used
     if (a->frame_len < 1 || a->frame_len > 2048) return fail(e, CVAD_E_INVALID, "frame_len outside [1, 2048]");
     if (a->hop < 1) return fail(e, CVAD_E_INVALID, "hop < 1");
@@ -593,7 +639,8 @@ int ensure_rt_tc(cvad_engine *e, int src_rate, cudaStream_t stream) {
 // that cannot look at the array (device-pointer steps) pass 0xF
 // Does the model part of this step run as ONE fused kernel (the form cvad_step_device chains)?
 bool fused_single_frame(const cvad_engine *e, const cvad_step_args *a) {
-    return e->chain_steps && e->version == CVAD_MODEL_V5 && e->math != CVAD_MATH_FP32 && a->max_frames == 1 && e->fuse_single_frame;
+    return e->chain_steps && e->version == CVAD_MODEL_V5 && e->math != CVAD_MATH_FP32 && a->max_frames == 1 && e->fuse_single_frame &&
+           a->channels <= 1;
 }
 
 // a chained kernel sits at the tail of its stream without a `last_done` record: place the record now
@@ -605,10 +652,60 @@ int flush_chain(cvad_engine *e) {
     return CVAD_OK;
 }
 
+// AudioUtils.convert_to_mono (audio.py:193-208) on the device: out[i][k] = float32 mean over the C interleaved channels
+// of sample frame k of stream i -- the channels added in order, the sum divided by C, as np.mean does for float32 input.
+// PCM samples are converted to float first (the reference converts before it reaches the wrapper).  Per-stream rates:
+// stream i holds max_frames * 512 * src_rates[i] / 16000 sample frames.
+__global__ void downmix_kernel(const void *audio, int pcm, long long stride, int C, int n_streams, long long frames,
+                               const int *src_rates, int max_frames, float *out) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long long)n_streams * frames;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / frames);
+        const long long k = idx - (long long)i * frames;
+        if (src_rates && k >= (long long)max_frames * (512LL * src_rates[i] / 16000)) continue;
+        const long long base = (long long)i * stride + k * C;
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) {
+            float x;
+            if (pcm == 0) x = __ldg(reinterpret_cast<const float *>(audio) + base + c);
+            else {
+                x = (float)__ldg(reinterpret_cast<const short *>(audio) + base + c);
+                x = pcm == 1 ? __fdiv_rn(x, 32767.0f) : x * (1.0f / 32768.0f);
+            }
+            acc = c == 0 ? x : __fadd_rn(acc, x);
+        }
+        out[(size_t)i * frames + k] = __fdiv_rn(acc, (float)C);
+    }
+}
+
 // `chain` (cvad_step_device on a fused one-frame step): the caller enqueued no memset; see cvad_engine::d_evctr
 int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status, int commit, float *d_dbg,
                 cudaStream_t stream, unsigned rates_mask = 0xFu, bool chain = false) {
     if (a->n_streams == 0 || a->max_frames == 0) return CVAD_OK;
+    cvad_step_args a_mono;
+    if (a->channels > 1) {
+        // stage -1: interleaved channels -> mono float32 in HBM; everything downstream sees a mono float stream
+        if (chain) return fail(e, CVAD_E_INVALID, "internal: chained step with multi-channel input");
+        int rcf = flush_chain(e);
+        if (rcf) return rcf;
+        CU_TRY(e, cudaStreamWaitEvent(stream, e->last_done, 0));     // d_mono is shared by consecutive steps
+        const long long frames = a->src_rates ? std::min<long long>((long long)a->max_frames * 1536, a->stream_stride / a->channels)
+                                              : (long long)(a->max_frames - 1) * a->hop + a->frame_len;
+        int rcg = grow(e, e->d_mono, (size_t)a->n_streams * (size_t)frames * sizeof(float));
+        if (rcg) return rcg;
+        const long long total = (long long)a->n_streams * frames;
+        const int grid = (int)std::min<long long>((total + 255) / 256, (long long)e->num_sms * 16);
+        downmix_kernel<<<grid, 256, 0, stream>>>(a->audio, a->pcm_format, a->stream_stride, a->channels, a->n_streams, frames,
+                                                 a->src_rates, a->max_frames, static_cast<float *>(e->d_mono.p));
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+        a_mono = *a;
+        a_mono.audio = e->d_mono.p;
+        a_mono.pcm_format = CVAD_PCM_F32;
+        a_mono.stream_stride = frames;
+        a_mono.channels = 1;
+        a = &a_mono;
+    }
     // state and `feat` are shared: kernels of consecutive steps never overlap, whatever stream they use.  A chained
     // step behind a chained step on the same stream is ordered by the stream itself.
     if (!(chain && e->chain_pending && e->chain_stream == stream)) {
@@ -657,9 +754,27 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
         const int rs_share = (rs_tiles + n_rates - 1) / n_rates;
         r.osplit = 4 * rs_share <= e->num_sms ? 4 : (2 * rs_share <= e->num_sms ? 2 : 1);
         const int grid_rs_tc = std::min(rs_tiles * r.osplit, e->num_sms);
+        const bool rs_fft = e->resampler == CVAD_RESAMPLE_FFT;
+        auto launch_rs_fft = [&](int n_in) {
+            // one warp per two frames; 1 CTA per SM (shared memory), grid = enough CTAs for the launch's upper bound of units
+            const long long units = (long long)a->max_frames * ((a->n_streams + 1) / 2);
+            const double2 *T = e->fft_T;
+            if (n_in == 256) {
+                const int g = (int)std::min<long long>((units + cvad::RsFft<1>::WPC - 1) / cvad::RsFft<1>::WPC, e->num_sms);
+                cvad::resample_fft_kernel<1><<<g, cvad::RsFft<1>::WPC * 32, cvad::RsFft<1>::kSmem, stream>>>(r, T);
+            } else if (n_in == 768) {
+                const int g = (int)std::min<long long>((units + cvad::RsFft<3>::WPC - 1) / cvad::RsFft<3>::WPC, e->num_sms);
+                cvad::resample_fft_kernel<3><<<g, cvad::RsFft<3>::WPC * 32, cvad::RsFft<3>::kSmem, stream>>>(r, T);
+            } else {
+                const int g = (int)std::min<long long>((units + cvad::RsFft<6>::WPC - 1) / cvad::RsFft<6>::WPC, e->num_sms);
+                cvad::resample_fft_kernel<6><<<g, cvad::RsFft<6>::WPC * 32, cvad::RsFft<6>::kSmem, stream>>>(r, T);
+            }
+        };
         if (!mixed) {
             r.n_in = rate_n_in(a->src_rate);
-            if (rs_tc) {
+            if (rs_fft) {
+                launch_rs_fft(r.n_in);
+            } else if (rs_tc) {
                 if ((rc = ensure_rt_tc(e, a->src_rate, stream))) return rc;
                 const int ri = rate_index(a->src_rate);
                 if (e->math == CVAD_MATH_TC16)
@@ -692,7 +807,9 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
                 r.n_in = rate_n_in(kRates[ri]);
                 r.list = lists + (size_t)ri * n;
                 r.count = counts + ri;
-                if (rs_tc) {
+                if (rs_fft) {
+                    launch_rs_fft(r.n_in);
+                } else if (rs_tc) {
                     if ((rc = ensure_rt_tc(e, kRates[ri], stream))) return rc;
                     if (e->math == CVAD_MATH_TC16)
                         cvad::tc5::resample_tc_kernel<true><<<grid_rs_tc, cvad::tc5::kThreadsTC, cvad::tc5::kRsTcSmem, stream>>>(
@@ -834,12 +951,27 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
     const bool v4 = e->version == CVAD_MODEL_V4;
     const int n_tiles = a->max_frames * n_stiles * (v4 ? 2 : 1);
     const int grid_fe = std::min(n_tiles, e->num_sms);
+    if (v4 && e->math == CVAD_MATH_FFT) {
+        // STFT = double-precision FFT with the exact basis (float32 re / im through HBM) + one BF16 tensor-core product
+        // with the basis' float32 rounding; the magnitude tiles then feed the FP32 front end like the TC path's
+        if ((rc = grow(e, e->d_v4_fft, (size_t)n_tiles * cvad::kV4FftTile * sizeof(float)))) return rc;
+        if ((rc = grow(e, e->d_v4_mag, (size_t)n_tiles * cvad::tc5::kV4MagTile * sizeof(float)))) return rc;
+        cvad::v4_stft_fft_kernel<<<grid_fe, 512, cvad::kV4FftSmem, stream>>>(p, e->fft_T, static_cast<float *>(e->d_v4_fft.p));
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+        p.w_fe_tc = e->w_v4_corr;
+        p.v4_fft = static_cast<const float *>(e->d_v4_fft.p);
+        p.v4_mag = static_cast<float *>(e->d_v4_mag.p);
+        cvad::tc5::v4tc_stft_kernel<true><<<grid_fe, cvad::tc5::kThreadsTC, cvad::tc5::kV4tcSmem, stream>>>(p);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+    }
     if (v4 && e->math == CVAD_MATH_TC) {
         // the STFT (77 % of v4's MACs) on the tensor cores; |STFT| tiles go through HBM to the FP32 front end
         if ((rc = grow(e, e->d_v4_mag, (size_t)n_tiles * cvad::tc5::kV4MagTile * sizeof(float)))) return rc;
         p.w_fe_tc = e->w_fe_tc;
         p.v4_mag = static_cast<float *>(e->d_v4_mag.p);
-        cvad::tc5::v4tc_stft_kernel<<<grid_fe, cvad::tc5::kThreadsTC, cvad::tc5::kV4tcSmem, stream>>>(p);
+        cvad::tc5::v4tc_stft_kernel<false><<<grid_fe, cvad::tc5::kThreadsTC, cvad::tc5::kV4tcSmem, stream>>>(p);
         CU_TRY(e, cudaGetLastError());
         e->launches++;
     }
@@ -908,7 +1040,16 @@ int quiesce(cvad_engine *e) {
 
 // Enqueue one host-buffer step on `ln` (H2D, kernels, D2H) without waiting for it.
 // `dbg_out` != nullptr turns it into the debug dump (front end only, no commit).
+int step_submit_impl(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, float *dbg_out, size_t dbg_floats);
+
+// every failure after the lane was marked busy must release it again, whichever statement it comes from
 int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, float *dbg_out, size_t dbg_floats) {
+    const int rc = step_submit_impl(e, ln, a, dbg_out, dbg_floats);
+    if (rc != CVAD_OK) ln.busy = false;
+    return rc;
+}
+
+int step_submit_impl(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, float *dbg_out, size_t dbg_floats) {
     int rc = validate_args(e, a);
     if (rc) return rc;
     CU_TRY(e, cudaSetDevice(e->device));
@@ -933,7 +1074,8 @@ int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, 
         ln.nfr_copy.assign(a->n_frames, a->n_frames + n);
     }
     const size_t es = elem_size(a->pcm_format);
-    size_t row = (size_t)(T - 1) * a->hop + a->frame_len;
+    const size_t nch = a->channels > 1 ? (size_t)a->channels : 1;     // rows are counted in ELEMENTS (sample frames x channels)
+    size_t row = ((size_t)(T - 1) * a->hop + a->frame_len) * nch;
     size_t last_row = row;
     unsigned rates_mask = 0;
     if (a->src_rates) {
@@ -945,18 +1087,19 @@ int step_submit(cvad_engine *e, cvad_engine::Lane &ln, const cvad_step_args *a, 
                 return fail(e, CVAD_E_INVALID, "src_rates[i] must be 8000, 16000, 24000 or 48000");
             }
             rates_mask |= 1u << r;
-            last_row = (size_t)T * (size_t)rate_n_in(a->src_rates[i]);
+            last_row = (size_t)T * (size_t)rate_n_in(a->src_rates[i]) * nch;
             row = std::max(row, last_row);
         }
     }
-    if (n > 1 && (a->stream_stride < 0 || (size_t)a->stream_stride < row)) {
+    // also for a single stream: stream_stride is then the only statement of the buffer's length the caller makes
+    if (a->stream_stride < 0 || (size_t)a->stream_stride < row) {
         ln.busy = false;
         return fail(e, CVAD_E_INVALID, "stream_stride shorter than one stream's samples in this step");
     }
     // rows much wider than what this step reads (a caller stepping the first frames of a longer block): only the
     // samples that are read cross PCIe, as a 2-D copy into a dense device block
     const size_t row_al = (row + 7) & ~(size_t)7;
-    const bool dense2d = n > 1 && !a->src_rates && (size_t)a->stream_stride > row_al + row_al / 4;
+    const bool dense2d = n > 1 && !a->src_rates && nch == 1 && (size_t)a->stream_stride > row_al + row_al / 4;
     const size_t dev_stride = dense2d ? row_al : (size_t)a->stream_stride;
     const size_t audio_elems = dense2d ? (size_t)n * row_al : (size_t)(n - 1) * a->stream_stride + last_row;
     const size_t audio_bytes = audio_elems * es;
@@ -1222,8 +1365,25 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
         const char *ch = std::getenv("CVAD_CHAIN");
         e->chain_steps = !(ch && std::strcmp(ch, "0") == 0);
     }
-    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v4tc_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v4tc_stft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kV4tcSmem));
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v4tc_stft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::tc5::kV4tcSmem));
+    CR_TRY(cudaFuncSetAttribute(cvad::v4_stft_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cvad::kV4FftSmem));
+    CR_TRY(cudaFuncSetAttribute(cvad::resample_fft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::RsFft<1>::kSmem));
+    CR_TRY(cudaFuncSetAttribute(cvad::resample_fft_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::RsFft<3>::kSmem));
+    CR_TRY(cudaFuncSetAttribute(cvad::resample_fft_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::RsFft<6>::kSmem));
+    std::vector<double2> fftT(cvad::fft::kMaster);
+    cvad::fft::build_master(fftT.data());
+    {
+        int rc;
+        if ((rc = upload(e, &e->fft_T, fftT))) return bail(rc);
+        const char *rsm = std::getenv("CVAD_RESAMPLE");
+        e->resampler = (rsm && std::strcmp(rsm, "gemm") == 0) ? CVAD_RESAMPLE_GEMM : CVAD_RESAMPLE_FFT;
+    }
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::resample_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kRsTcSmem));
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::resample_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1234,8 +1394,16 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
         if ((rc = upload(e, &e->w_fe_tc, T))) return bail(rc);
         // v4 feeds log(1 + 2^20 |STFT|) into the network, which amplifies the tensor cores' (truncating) FP32
         // accumulation on weak bins: FP32 FMA stays the default for v4, the tensor-core STFT is opt-in
+        // since then: the STFT as a double-precision FFT plus a tensor-core correction for the basis' float32 rounding
+        // (CVAD_MATH_FFT) is both faster and closer to the float64 evaluation of the graph than either; it is the
+        // default whenever the blob's basis is Hann x DFT-256 (true for both sub-models of the reference's file)
+        std::vector<unsigned char> C;
+        const double worst = pack_v4_stft_corr(weights, fftT.data(), C);
+        e->v4_fft_ok = worst <= 2.0e-7;
+        if (e->v4_fft_ok && (rc = upload(e, &e->w_v4_corr, C))) return bail(rc);
         const char *m = std::getenv("CVAD_MATH");
-        e->math = (m && std::strcmp(m, "tc") == 0) ? CVAD_MATH_TC : CVAD_MATH_FP32;
+        e->math = (m && std::strcmp(m, "tc") == 0) ? CVAD_MATH_TC
+                  : (m && std::strcmp(m, "fp32") == 0) || !e->v4_fft_ok ? CVAD_MATH_FP32 : CVAD_MATH_FFT;
     }
     {
         V5Packed P = model_version == CVAD_MODEL_V5 ? pack_v5(weights) : pack_v4(weights);
@@ -1280,7 +1448,8 @@ int cvad_destroy(cvad_engine *e) {
                     e->sm_scount, e->sm_ecount, e->frames_done, e->start_p, e->end_p, e->n_start, e->n_end,
                     e->denoise, e->d_status_dev.p, e->d_feat.p, e->d_dbg.p, e->d_cfg_slots.p, e->d_res.p,
                     e->rs_rt[0], e->rs_rt[1], e->rs_rt[2], e->rs_h[0], e->rs_h[1], e->rs_h[2], e->w_fe_tc, e->w_rec_tc, e->w_fe_h, e->w_rec_h, e->nyq_w, e->b_rec_tc,
-                    e->d_feat_tc.p, e->d_prof, e->d_evctr, e->d_rate_lists.p, e->d_v4_mag.p, e->rs_tc[0], e->rs_tc[1], e->rs_tc[2]};
+                    e->d_feat_tc.p, e->d_prof, e->d_evctr, e->d_rate_lists.p, e->d_v4_mag.p, e->rs_tc[0], e->rs_tc[1], e->rs_tc[2],
+                    e->fft_T, e->w_v4_corr, e->d_v4_fft.p, e->d_mono.p};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &ln : e->lanes) {
@@ -1302,13 +1471,25 @@ int cvad_destroy(cvad_engine *e) {
 
 int cvad_set_math(cvad_engine *e, int math) {
     if (!e) return CVAD_E_INVALID;
-    if (math != CVAD_MATH_FP32 && math != CVAD_MATH_TC && math != CVAD_MATH_TC16)
-        return fail(e, CVAD_E_INVALID, "math must be CVAD_MATH_FP32, CVAD_MATH_TC or CVAD_MATH_TC16");
+    if (math != CVAD_MATH_FP32 && math != CVAD_MATH_TC && math != CVAD_MATH_TC16 && math != CVAD_MATH_FFT)
+        return fail(e, CVAD_E_INVALID, "math must be CVAD_MATH_FP32, CVAD_MATH_TC, CVAD_MATH_TC16 or CVAD_MATH_FFT");
     if (math == CVAD_MATH_TC16 && e->version != CVAD_MODEL_V5)
         return fail(e, CVAD_E_INVALID, "CVAD_MATH_TC16 exists for the v5 model only");
+    if (math == CVAD_MATH_FFT && (e->version != CVAD_MODEL_V4 || !e->v4_fft_ok))
+        return fail(e, CVAD_E_INVALID, "CVAD_MATH_FFT exists for v4 models whose STFT basis is Hann x DFT-256");
     e->math = math;
     return CVAD_OK;
 }
+
+int cvad_set_resampler(cvad_engine *e, int resampler) {
+    if (!e) return CVAD_E_INVALID;
+    if (resampler != CVAD_RESAMPLE_FFT && resampler != CVAD_RESAMPLE_GEMM)
+        return fail(e, CVAD_E_INVALID, "resampler must be CVAD_RESAMPLE_FFT or CVAD_RESAMPLE_GEMM");
+    e->resampler = resampler;
+    return CVAD_OK;
+}
+
+int cvad_get_resampler(const cvad_engine *e) { return e ? e->resampler : CVAD_E_INVALID; }
 
 int cvad_get_math(const cvad_engine *e) { return e ? e->math : CVAD_E_INVALID; }
 

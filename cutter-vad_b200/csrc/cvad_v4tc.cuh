@@ -23,6 +23,15 @@ constexpr size_t kV4tcSmem = 1024 + 3 * (size_t)kV4tcPart + (size_t)kV4tcRing * 
                              2 * 16 * 4 + 64;
 constexpr int kV4MagTile = 129 * 8 * 16;               // floats per tile
 
+// CORR = true (CVAD_MATH_FFT, v4's default): the STFT proper comes from v4_stft_fft_kernel (cvad_fftk.cuh: exact
+// Hann x DFT-256 basis, double precision, float32 re / im in p.v4_fft); this kernel adds what the exact basis lacks --
+// the product with delta = (the file's float32 basis) - (Hann x DFT), |delta| <= 7.7e-8 -- and forms the magnitude.
+// delta * 2^24 is O(1), so ONE BF16 product per MAC (8 weight tiles instead of 24, bf16(x) only) gives the correction
+// to 0.4 % of itself, i.e. to ~1e-9 of the frame's scale.
+constexpr float kV4CorrScale = 16777216.0f;            // 2^24
+constexpr size_t kV4CorrStreamBytes = 8 * 16384;       // blk 0..1 x kb 0..3, one part
+
+template <bool CORR>
 __global__ void __launch_bounds__(kThreadsTC, 1) v4tc_stft_kernel(const V5Step p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -70,7 +79,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v4tc_stft_kernel(const V5Step p
             const int frame = tile / n_ft, ft = tile - frame * n_ft;
             if (!tile_live16(frame, ft, nullptr, nullptr)) continue;
             if (lane == 0) {
-                for (int s = 0; s < 24; ++s, ++g) {
+                for (int s = 0; s < (CORR ? 8 : 24); ++s, ++g) {
                     const uint32_t slot = g % kV4tcRing;
                     mbar_wait(&empty[slot], ((g / kV4tcRing) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(&full[slot], kSlotBytes);
@@ -89,14 +98,22 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v4tc_stft_kernel(const V5Step p
             tc::fence_after_sync();
             for (int blk = 0; blk < 2; ++blk)
                 for (int kb = 0; kb < 4; ++kb)
-                    for (int wp = 0; wp < 3; ++wp, ++g) {
+                    for (int wp = 0; wp < (CORR ? 1 : 3); ++wp, ++g) {
                         const uint32_t slot = g % kV4tcRing;
                         mbar_wait(&full[slot], (g / kV4tcRing) & 1u);
                         tc::fence_after_sync();
                         if (tc::elect_one()) {
                             // column t of the STFT = samples 64 t .. 64 t + 255 = segments t .. t+3: K block kb <-> segment t + kb
-                            issue_split(wp, ring_s + slot * kSlotBytes, aud_s + kb * 2048u, kV4tcPart, blk * 128u,
-                                        256u + blk * 128u, idesc, kb == 0 && wp == 0);
+                            if (CORR) {
+                                const uint64_t ad = tc::smem_desc_sw128(ring_s + slot * kSlotBytes);
+                                const uint64_t bd = tc::smem_desc_sw128(aud_s + kb * 2048u);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    tc::mma_bf16(blk * 128u, ad + ks * 2, bd + ks * 2, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+                            } else {
+                                issue_split(wp, ring_s + slot * kSlotBytes, aud_s + kb * 2048u, kV4tcPart, blk * 128u,
+                                            256u + blk * 128u, idesc, kb == 0 && wp == 0);
+                            }
                             tc::mma_commit(&empty[slot]);
                         }
                         __syncwarp();
@@ -150,7 +167,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v4tc_stft_kernel(const V5Step p
                 const uint32_t seg = (uint32_t)c8 >> 3, kk = ((uint32_t)c8 & 7u) * 8u;
                 const uint32_t off = tc::sw128_offset(seg * 16u + (uint32_t)s, kk, 176u);
 #pragma unroll
-                for (int part = 0; part < 3; ++part)
+                for (int part = 0; part < (CORR ? 1 : 3); ++part)
                     *reinterpret_cast<uint4 *>(aud + part * kV4tcPart + off) = make_uint4(w[part][0], w[part][1], w[part][2], w[part][3]);
             }
             tc::fence_async_smem();
@@ -169,13 +186,23 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v4tc_stft_kernel(const V5Step p
                     float mr[8], mi[8], cr[8], ci[8], mag[8];
                     tmem_ld8(lane_addr + c0, mr);
                     tmem_ld8(lane_addr + 128 + c0, mi);
-                    tmem_ld8(lane_addr + 256 + c0, cr);
-                    tmem_ld8(lane_addr + 384 + c0, ci);
+                    if (CORR) {
+                        // the exact-basis STFT of this tile: [col][re | im][132]; lanes = bins, so every load is one coalesced row
+                        const float *fin = p.v4_fft + (size_t)tile * (128 * 2 * 132) + (size_t)c0 * (2 * 132);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            cr[e] = __ldg(fin + e * 264 + b);
+                            ci[e] = __ldg(fin + e * 264 + (b == 0 ? 128 : 132 + b));   // row 0 of the second block carries re[128]
+                        }
+                    } else {
+                        tmem_ld8(lane_addr + 256 + c0, cr);
+                        tmem_ld8(lane_addr + 384 + c0, ci);
+                    }
                     tmem_wait_ld();
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const float re = mr[e] + cr[e];
-                        float im = mi[e] + ci[e];
+                        const float re = CORR ? fmaf(mr[e], 1.0f / kV4CorrScale, cr[e]) : mr[e] + cr[e];
+                        float im = CORR ? fmaf(mi[e], 1.0f / kV4CorrScale, ci[e]) : mi[e] + ci[e];
                         if (b == 0) {
                             mout[128 * 128 + c0 + e] = sqrtf(__fmul_rn(im, im));   // bin 128 rides in row 0 of the im block
                             im = 0.f;

@@ -118,6 +118,7 @@ struct V5Step {
     long long *prof;              // optional clock64 marks of CTA 0 (cvad_set_profile), or null
     int v4_t2;                    // v4 8 kHz sub-model: two time steps reach the LSTM per frame
     float *v4_mag;                // v4 tensor-core path: |STFT| tiles [tile][129][8][16] written by v4tc_stft_kernel, or null
+    const float *v4_fft;          // v4 FFT path: exact-basis STFT tiles [tile][128 cols][re | im][132] from v4_stft_fft_kernel, or null
 };
 
 struct EventRec {

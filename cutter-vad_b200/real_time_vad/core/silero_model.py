@@ -402,11 +402,16 @@ class VADProcessor(BaseModel):
                 and m.session.version == self.config.model_version.value
                 and int(self.config.sample_rate) == 16000)
 
+    # frames per engine step of one process_audio_data call: bounds the device scratch of an hour-long buffer (the
+    # reference streams frame by frame) and the work that is redone when a callback raises
+    _BATCH_FRAMES = 512
+
     def process_audio_batched(self, audio: np.ndarray, frame_size: int, hop_size: int) -> Iterator[ProcessingResult]:
-        """All frames `audio[j*hop : j*hop+frame_size]` through one `cvad_step` on this stream's model
-        session slot.  Yields one ProcessingResult per frame, in order, equal to what `process_frame`
-        would have returned; callbacks run between yields, so an exception in a callback leaves the
-        host-side bookkeeping at the frame that raised (the LSTM state has advanced through the call)."""
+        """All frames `audio[j*hop : j*hop+frame_size]` through `cvad_step` on this stream's model session slot, up to
+        `_BATCH_FRAMES` frames per step.  Yields one ProcessingResult per frame, in order, equal to what
+        `process_frame` would have returned; callbacks run between yields.  If the consumer stops early -- a callback
+        raised (vad_wrapper.py:470-476 aborts the call at that frame) -- the stream is put back where the reference
+        leaves it: LSTM state and counters after the frame that raised, nothing later."""
         sess = self.model.session
         n_frames = (len(audio) - frame_size) // hop_size + 1
         if n_frames < 0:
@@ -417,80 +422,102 @@ class VADProcessor(BaseModel):
         cfg = self.config
         ms = self.model.model_state
         pooled, slot = sess._pooled, sess._slot
-        with pooled.lock:
-            eng = pooled.engine
-            eng.configure([slot], vad_start_probability=cfg.vad_start_probability,
-                          vad_end_probability=cfg.vad_end_probability,
-                          voice_start_frame_count=cfg.voice_start_frame_count,
-                          voice_end_frame_count=cfg.voice_end_frame_count, enable_denoising=cfg.enable_denoising)
-            sm_in = np.array([int(self.is_voice_active), self.voice_start_frame_count,
-                              self.voice_end_frame_count, 0], np.int32)
-            if ms.state is not None:
-                eng.set_state(slot, ms.state[0, 0], ms.state[1, 0], sm_in)
-            else:
-                eng.set_state(slot, ms.hidden_state.reshape(128), ms.cell_state.reshape(128), sm_in)
-            try:
-                r = eng.step(audio[None, :], slots=[slot], n_frames=[n_frames], max_frames=n_frames,
-                             frame_len=frame_size, hop=hop_size)
-                if r.status[0]:
-                    raise AudioProcessingError("Audio data contains infinite or NaN values")
-                h, c, sm_out, _ = eng.get_state(slot)
-            finally:
-                eng.configure([slot], enable_denoising=False)  # the compat session.run must not gate
         d = self.__dict__  # bypass pydantic's per-assignment validation on the per-frame bookkeeping
-        if ms.state is not None:
-            ms.__dict__["state"] = np.stack([h[None, :], c[None, :]], axis=0).astype(np.float32)
-        else:
-            ms.__dict__["hidden_state"] = h.reshape(2, 1, 64).astype(np.float32)
-            ms.__dict__["cell_state"] = c.reshape(2, 1, 64).astype(np.float32)
-        self.model.__dict__["prediction_count"] = self.model.prediction_count + n_frames
-        probs = r.probs[0]
-        flags = r.flags[0]
         start_p = cfg.vad_start_probability
         end_p = cfg.vad_end_probability
         gate = cfg.enable_denoising
-        segment: List[np.ndarray] = [] if d["current_voice_data"] is None else [d["current_voice_data"]]
-        active = d["is_voice_active"]
-        try:
-            for j in range(n_frames):
-                p = float(probs[j])
-                fl = int(flags[j])
-                d["voice_probabilities"].append(p)
-                wav = pcm = None
-                if not active:
-                    hit = p >= start_p
-                    d["recent_start_frames"].append(hit)
-                    if hit:
-                        frame = audio[j * hop_size: j * hop_size + frame_size]
-                        d["voice_buffer"].append(AudioUtils.denoise_audio(frame) if gate else frame.copy())
-                        if fl & 1:
-                            segment = list(d["voice_buffer"])
-                            d["voice_buffer"].clear()
-                            active = True
-                    else:
-                        d["voice_buffer"].clear()
-                else:
-                    frame = audio[j * hop_size: j * hop_size + frame_size]
-                    if gate:
-                        frame = AudioUtils.denoise_audio(frame)
-                    segment.append(frame)
-                    pcm = frame.tobytes()
-                    d["recent_end_frames"].append(p < end_p)
-                    if fl & 2:
-                        wav = self.wav_writer.write_wav_data(np.concatenate(segment))
-                        segment = []
-                        active = False
-                d["is_voice_active"] = active
-                yield ProcessingResult.model_construct(voice_started=bool(fl & 1), voice_ended=bool(fl & 2),
-                                                       voice_continuing=bool(fl & 4), probability=p,
-                                                       wav_data=wav, pcm_data=pcm)
-        finally:
-            # the device has run the whole call: its counters are the truth for what comes next
+
+        def run(first: int, count: int, h_in, c_in, sm_in):
+            """frames [first, first + count) from the given state -> (step result, h, c, sm)"""
+            with pooled.lock:
+                eng = pooled.engine
+                eng.configure([slot], vad_start_probability=start_p, vad_end_probability=end_p,
+                              voice_start_frame_count=cfg.voice_start_frame_count,
+                              voice_end_frame_count=cfg.voice_end_frame_count, enable_denoising=gate)
+                eng.set_state(slot, h_in, c_in, sm_in)
+                try:
+                    lo = first * hop_size
+                    r = eng.step(audio[None, lo:lo + (count - 1) * hop_size + frame_size], slots=[slot], n_frames=[count],
+                                 max_frames=count, frame_len=frame_size, hop=hop_size)
+                    if r.status[0]:
+                        raise AudioProcessingError("Audio data contains infinite or NaN values")
+                    h, c, sm_out, _ = eng.get_state(slot)
+                finally:
+                    eng.configure([slot], enable_denoising=False)  # the compat session.run must not gate
+            return r, h, c, sm_out
+
+        def adopt(h, c, sm_out, segment):
+            if ms.state is not None:
+                ms.__dict__["state"] = np.stack([h[None, :], c[None, :]], axis=0).astype(np.float32)
+            else:
+                ms.__dict__["hidden_state"] = h.reshape(2, 1, 64).astype(np.float32)
+                ms.__dict__["cell_state"] = c.reshape(2, 1, 64).astype(np.float32)
             d["is_voice_active"] = bool(sm_out[0])
             d["voice_start_frame_count"] = int(sm_out[1])
             d["voice_end_frame_count"] = int(sm_out[2])
             d["current_voice_data"] = (np.concatenate(segment).astype(np.float32, copy=False)
                                        if (segment and bool(sm_out[0])) else None)
+
+        segment: List[np.ndarray] = [] if d["current_voice_data"] is None else [d["current_voice_data"]]
+        for first in range(0, n_frames, self._BATCH_FRAMES):
+            count = min(self._BATCH_FRAMES, n_frames - first)
+            sm_in = np.array([int(d["is_voice_active"]), d["voice_start_frame_count"], d["voice_end_frame_count"], 0], np.int32)
+            if ms.state is not None:
+                h_in, c_in = ms.state[0, 0].copy(), ms.state[1, 0].copy()
+            else:
+                h_in, c_in = ms.hidden_state.reshape(128).copy(), ms.cell_state.reshape(128).copy()
+            r, h, c, sm_out = run(first, count, h_in, c_in, sm_in)
+            probs = r.probs[0]
+            flags = r.flags[0]
+            active = d["is_voice_active"]
+            done = 0                 # frames of this batch whose result the consumer has taken
+            try:
+                for j in range(count):
+                    p = float(probs[j])
+                    fl = int(flags[j])
+                    lo = (first + j) * hop_size
+                    d["voice_probabilities"].append(p)
+                    wav = pcm = None
+                    if not active:
+                        hit = p >= start_p
+                        d["recent_start_frames"].append(hit)
+                        if hit:
+                            frame = audio[lo: lo + frame_size]
+                            d["voice_buffer"].append(AudioUtils.denoise_audio(frame) if gate else frame.copy())
+                            if fl & 1:
+                                segment = list(d["voice_buffer"])
+                                d["voice_buffer"].clear()
+                                active = True
+                        else:
+                            d["voice_buffer"].clear()
+                    else:
+                        frame = audio[lo: lo + frame_size]
+                        if gate:
+                            frame = AudioUtils.denoise_audio(frame)
+                        segment.append(frame)
+                        pcm = frame.tobytes()
+                        d["recent_end_frames"].append(p < end_p)
+                        if fl & 2:
+                            wav = self.wav_writer.write_wav_data(np.concatenate(segment))
+                            segment = []
+                            active = False
+                    d["is_voice_active"] = active
+                    done = j + 1
+                    yield ProcessingResult.model_construct(voice_started=bool(fl & 1), voice_ended=bool(fl & 2),
+                                                           voice_continuing=bool(fl & 4), probability=p,
+                                                           wav_data=wav, pcm_data=pcm)
+            finally:
+                if done < count:
+                    # the consumer stopped after frame `done - 1` (a callback raised): the reference has run exactly
+                    # `done` frames of this batch, so run those again from the batch's starting state and adopt that
+                    if done > 0:
+                        _, h, c, sm_out = run(first, done, h_in, c_in, sm_in)
+                    else:
+                        h, c, sm_out = h_in, c_in, sm_in
+                    self.model.__dict__["prediction_count"] = self.model.prediction_count + done
+                else:
+                    self.model.__dict__["prediction_count"] = self.model.prediction_count + count
+                adopt(h, c, sm_out, segment)
 
     # ---- housekeeping
     def reset(self) -> None:

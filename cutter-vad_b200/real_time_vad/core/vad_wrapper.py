@@ -261,10 +261,16 @@ class VADWrapper:
             proc = self._processor
             batched = getattr(proc, "supports_batched", None)
             if callable(batched) and batched() is True:  # `is True`: a test double answers with a Mock
-                # one GPU step for the whole call
-                for result in proc.process_audio_batched(audio_data, frame_size, hop_size):
-                    self._handle_callbacks(result)
-                    self._state.__dict__["total_frames_processed"] += 1
+                # one GPU step per batch of frames.  The generator is closed HERE, deterministically: its `finally`
+                # puts the stream back to the frame a raising callback stopped at, and must not wait for the garbage
+                # collector (the exception's traceback would keep it alive past the next call)
+                results = proc.process_audio_batched(audio_data, frame_size, hop_size)
+                try:
+                    for result in results:
+                        self._handle_callbacks(result)
+                        self._state.__dict__["total_frames_processed"] += 1
+                finally:
+                    results.close()
                 return
             # compatibility path: one model call per frame
             for frame in AudioUtils.split_into_frames(audio_data, frame_size, hop_size):

@@ -18,7 +18,8 @@ MODEL_V5, MODEL_V4, MODEL_V4_8K = 5, 4, 48
 PCM_F32, PCM_S16_32767, PCM_S16_32768 = 0, 1, 2
 FLAG_STARTED, FLAG_ENDED, FLAG_CONTINUING = 1, 2, 4
 STATUS_NONFINITE = 1
-MATH_FP32, MATH_TC, MATH_TC16 = 0, 1, 2
+MATH_FP32, MATH_TC, MATH_TC16, MATH_FFT = 0, 1, 2, 3
+RESAMPLE_FFT, RESAMPLE_GEMM = 0, 1
 PAYLOAD_NONE, PAYLOAD_EVENTS, PAYLOAD_SEGMENTS, PAYLOAD_FRAMES = 0, 1, 2, 3
 
 EXPORTS = (
@@ -26,7 +27,7 @@ EXPORTS = (
     "cvad_set_stream", "cvad_reset", "cvad_configure", "cvad_get_state", "cvad_set_state",
     "cvad_step", "cvad_step_submit", "cvad_step_collect", "cvad_step_device", "cvad_sync", "cvad_launch_count", "cvad_debug_dump",
     "cvad_alloc_pinned", "cvad_free_pinned", "cvad_set_timing", "cvad_read_timing", "cvad_resample_matrix", "cvad_tc_probe", "cvad_tc_rate", "cvad_bulk_rate",
-    "cvad_set_math", "cvad_get_math", "cvad_set_profile", "cvad_read_profile",
+    "cvad_set_math", "cvad_get_math", "cvad_set_resampler", "cvad_get_resampler", "cvad_set_profile", "cvad_read_profile",
     "cvad_feeder_create", "cvad_feeder_destroy", "cvad_feeder_last_error", "cvad_feeder_open", "cvad_feeder_close",
     "cvad_feeder_clear", "cvad_feeder_is_active", "cvad_feeder_pending", "cvad_feeder_push", "cvad_feeder_push_many",
     "cvad_feeder_step", "cvad_feeder_gather_only", "cvad_feeder_deliver_only",
@@ -57,6 +58,7 @@ class StepArgs(C.Structure):
         ("max_events", C.c_int32),
         ("n_events_out", C.c_void_p),
         ("src_rates", C.c_void_p),
+        ("channels", C.c_int32),
     ]
 
 
@@ -102,6 +104,8 @@ def lib() -> C.CDLL:
     L.cvad_set_stream.argtypes = [vp, vp]
     L.cvad_set_math.argtypes = [vp, i32]
     L.cvad_get_math.argtypes = [vp]
+    L.cvad_set_resampler.argtypes = [vp, i32]
+    L.cvad_get_resampler.argtypes = [vp]
     L.cvad_set_profile.argtypes = [vp, i32]
     L.cvad_read_profile.argtypes = [vp, vp]
     L.cvad_reset.argtypes = [vp, i32, vp]

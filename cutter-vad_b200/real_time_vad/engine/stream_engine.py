@@ -64,7 +64,7 @@ def _ptr(a: Optional[np.ndarray]):
 
 class StreamEngine:
     def __init__(self, model_version: str = "v5", max_streams: int = 1, device: int = 0,
-                 model_path: Optional[Path] = None, math: Optional[str] = None):
+                 model_path: Optional[Path] = None, math: Optional[str] = None, resampler: Optional[str] = None):
         self._L = capi.lib()
         self._h = C.c_void_p()
         if model_version == "v5":
@@ -88,19 +88,34 @@ class StreamEngine:
         self.model_version = model_version
         if math is not None:
             self.set_math(math)
+        if resampler is not None:
+            self.set_resampler(resampler)
 
     # ------------------------------------------------------------------ plumbing
     def set_math(self, math: str) -> None:
         """'fp32' = packed FP32 FMA kernels; 'tc' = tcgen05 tensor cores with the 3-way BF16 split; 'tc16' (v5) = one-frame
-        steps with the 2-way FP16 split and per-stream scaling (3 products per MAC), other steps as 'tc'."""
-        code = {"fp32": capi.MATH_FP32, "tc": capi.MATH_TC, "tc16": capi.MATH_TC16}.get(math)
+        steps with the 2-way FP16 split and per-stream scaling (3 products per MAC), other steps as 'tc'; 'fft' (v4, its
+        default) = the STFT as a double-precision FFT plus a tensor-core correction for the basis' float32 rounding."""
+        code = {"fp32": capi.MATH_FP32, "tc": capi.MATH_TC, "tc16": capi.MATH_TC16, "fft": capi.MATH_FFT}.get(math)
         if code is None:
             raise EngineError(capi.E_INVALID, f"unknown math mode {math!r}")
         self._check(self._L.cvad_set_math(self._h, code))
 
     @property
     def math(self) -> str:
-        return {capi.MATH_TC: "tc", capi.MATH_TC16: "tc16"}.get(self._L.cvad_get_math(self._h), "fp32")
+        return {capi.MATH_TC: "tc", capi.MATH_TC16: "tc16", capi.MATH_FFT: "fft"}.get(self._L.cvad_get_math(self._h), "fp32")
+
+    def set_resampler(self, resampler: str) -> None:
+        """'fft' (default) = scipy.signal.resample's FFT method in double, rounded once to float32; 'gemm' = the dense
+        operator on the arithmetic `math` selects (FP32 FMA or split-precision tensor cores)."""
+        code = {"fft": capi.RESAMPLE_FFT, "gemm": capi.RESAMPLE_GEMM}.get(resampler)
+        if code is None:
+            raise EngineError(capi.E_INVALID, f"unknown resampler {resampler!r}")
+        self._check(self._L.cvad_set_resampler(self._h, code))
+
+    @property
+    def resampler(self) -> str:
+        return "gemm" if self._L.cvad_get_resampler(self._h) == capi.RESAMPLE_GEMM else "fft"
 
     def _check(self, rc: int) -> None:
         if rc < 0:
@@ -191,8 +206,8 @@ class StreamEngine:
     # ------------------------------------------------------------------ the hot call
     def _args(self, audio: np.ndarray, slots, n_frames, max_frames, frame_len, hop, pcm_format, src_rate=16000,
               src_rates=None):
-        if audio.ndim != 2:
-            raise EngineError(capi.E_INVALID, "audio must be [n_streams, samples]")
+        if audio.ndim not in (2, 3):
+            raise EngineError(capi.E_INVALID, "audio must be [n_streams, samples] or [n_streams, samples, channels]")
         if pcm_format == capi.PCM_F32:
             audio = np.ascontiguousarray(audio, dtype=np.float32)
         else:
@@ -215,7 +230,9 @@ class StreamEngine:
             a.n_frames = nf.ctypes.data
         a.audio = audio.ctypes.data
         a.pcm_format = pcm_format
-        a.stream_stride = audio.shape[1]
+        # [n, samples, channels]: interleaved sample frames, averaged to mono on the GPU (AudioUtils.convert_to_mono)
+        a.channels = audio.shape[2] if audio.ndim == 3 else 1
+        a.stream_stride = audio.shape[1] * (audio.shape[2] if audio.ndim == 3 else 1)
         a.max_frames = int(max_frames)
         a.frame_len = int(frame_len)
         a.hop = int(hop)

@@ -18,6 +18,7 @@
  *                             VADProcessor._process_voice_state           silero_model.py:790-923
  *                           and, where the north star adds it,
  *                             AudioUtils.resample_audio                   audio.py:19-55
+ *                             AudioUtils.convert_to_mono (channels > 1)   audio.py:193-208
  *   cvad_configure       <- VADConfig thresholds                          src/real_time_vad/core/config.py:54-94
  *                           as applied by VADWrapper.set_thresholds       vad_wrapper.py:367-419
  *   cvad_reset           <- VADProcessor.reset / SileroVADModel.reset     silero_model.py:951-968, :539-546
@@ -40,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CVAD_ABI_VERSION 3
+#define CVAD_ABI_VERSION 4
 
 /* error codes */
 #define CVAD_OK 0
@@ -66,6 +67,14 @@ extern "C" {
 #define CVAD_MATH_TC 1
 #define CVAD_MATH_TC16 2   /* v5: FP16 operands split two ways with per-stream power-of-two scaling, 3 products per MAC
                               instead of 6 (fused one-frame kernel, two-kernel multi-frame form and the resampler) */
+#define CVAD_MATH_FFT 3    /* v4 (its default): the STFT -- 77 % of v4's MACs, and the stage whose FP32 rounding v4's
+                              log(1 + 2^20 |STFT|) amplifies -- as a double-precision FFT with the exact Hann x DFT basis,
+                              plus one BF16 tensor-core product with (file basis - exact basis); the other layers FP32.
+                              Matches the float64 evaluation of the graph to ~1e-6 where two FP32 executors differ by 1e-3 */
+
+/* resampler implementations (cvad_set_resampler) */
+#define CVAD_RESAMPLE_FFT 0   /* default: scipy.signal.resample's FFT method in double, rounded once to float32 */
+#define CVAD_RESAMPLE_GEMM 1  /* the dense operator R x (FP32 FMA or split-precision tensor cores, following cvad_set_math) */
 
 /* audio sample formats accepted by cvad_step */
 #define CVAD_PCM_F32 0        /* float32 in [-1, 1] */
@@ -119,6 +128,11 @@ typedef struct cvad_step_args {
                                  When given, src_rate, frame_len and hop are ignored: stream i delivers max_frames
                                  chunks of 512*src_rates[i]/16000 samples back to back from audio[i*stream_stride],
                                  each resampled (or, at 16000, passed through) to one 512-sample model frame. */
+    int32_t channels;         /* ABI 4. 0 or 1: mono.  2..8: `audio` holds interleaved sample frames (sample k of stream i,
+                                 channel c at audio[i*stream_stride + k*channels + c]; stream_stride still counts ELEMENTS)
+                                 and every sample frame is averaged to mono on the GPU before anything else, exactly as
+                                 AudioUtils.convert_to_mono does (np.mean over axis 1 in float32, audio.py:193-208;
+                                 called from VADWrapper._validate_and_prepare_audio, vad_wrapper.py:603-606) */
 } cvad_step_args;
 
 /* Library / device probes. */
@@ -138,9 +152,14 @@ int cvad_destroy(cvad_engine *e);
 /* Select the arithmetic of the model kernels (CVAD_MATH_*).  For v5 every GEMM stage moves to the tensor cores;
    for v4 the STFT (77 % of its MACs) does, the small layers and the two LSTM(64) stay FP32.
    A v5 engine starts in CVAD_MATH_TC16 unless the environment variable CVAD_MATH is "tc" or "fp32"; a v4 engine starts in
-   CVAD_MATH_FP32 unless CVAD_MATH is "tc" (v4's log(1 + 2^20 |STFT|) amplifies accumulation-order differences). */
+   CVAD_MATH_FFT unless CVAD_MATH is "fp32" or "tc" (v4's log(1 + 2^20 |STFT|) amplifies accumulation-order differences). */
 int cvad_set_math(cvad_engine *e, int math);
 int cvad_get_math(const cvad_engine *e);
+
+/* Select how 8 / 24 / 48 kHz input is resampled (CVAD_RESAMPLE_*).  Engines start with CVAD_RESAMPLE_FFT unless the
+   environment variable CVAD_RESAMPLE is "gemm". */
+int cvad_set_resampler(cvad_engine *e, int resampler);
+int cvad_get_resampler(const cvad_engine *e);
 
 /* Development aid for the tensor-core kernels: when enabled, CTA 0 of each kernel records SM-clock marks at its
    phase boundaries (layout in csrc/cvad_v5tc.cuh, CVAD_PROF); cvad_read_profile copies the 128 marks out. */

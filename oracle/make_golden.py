@@ -14,6 +14,12 @@ Vectors:
                          B  one process_audio_data call, VADConfig defaults (hop 256)
                          C  512 samples per call, VADConfig defaults
                        per-frame probabilities, event (frame, kind) lists, WAV byte counts + sha256
+  sample_voice_v4.npz  the same file through VADWrapper(model_version=V4): framings A and B (events, probabilities, WAV hashes)
+  sample_voice_stereo.npz  examples/audios/SampleVoiceStereo.wav as a 2-D [samples, 2] array through VADWrapper
+                       (AudioUtils.convert_to_mono, audio.py:193-208).  Both channels of that file equal
+                       SampleVoiceMono.wav sample for sample (asserted here, sha256 of the PCM recorded), so the tests
+                       rebuild the stereo input from the committed mono file; a second case with DIFFERENT channels
+                       (right = left delayed and attenuated) pins the float32 mean itself.
   state_machine.npz    scripted probability sequences through VADProcessor._process_voice_state
                        (the cases of tests/test_silero_model.py:542-614, :870-954 plus random ones)
 """
@@ -79,6 +85,14 @@ def main():
         res[f"{tag}_wav_sha"] = np.array([hashlib.sha256(b).hexdigest() for b in wavs])
         print(tag, len(probs), "frames", events)
 
+    def run_into(store, tag, cfg, chunks):
+        saved = dict(res)
+        res.clear()
+        run(tag, cfg, chunks)
+        store.update(res)
+        res.clear()
+        res.update(saved)
+
     q = np.clip(np.round(y * 32767.0), -32768, 32767).astype(np.int16)
     res["q16k"] = q
     cfg_a = VADConfig(sample_rate=SampleRate.SAMPLERATE_16, buffer_size=480, vad_start_probability=0.4,
@@ -88,6 +102,27 @@ def main():
     run("B", VADConfig(), [y])
     run("C", VADConfig(), [y[i * 512:(i + 1) * 512] for i in range(len(y) // 512)])
     np.savez_compressed(OUT / "sample_voice.npz", **res)
+
+    # ---------------------------------------------------------------- sample_voice_v4 (model_version=V4 through the reference)
+    v4 = {}
+    cfg_a4 = cfg_a.model_copy(update={"model_version": SileroModelVersion.V4})
+    run_into(v4, "A", cfg_a4, [q[i * 480:(i + 1) * 480].astype(np.float32) / 32767.0 for i in range(len(q) // 480)])
+    run_into(v4, "B", VADConfig(model_version=SileroModelVersion.V4), [y])
+    np.savez_compressed(OUT / "sample_voice_v4.npz", **v4)
+
+    # ---------------------------------------------------------------- sample_voice_stereo
+    sr2, xs = wavfile.read(str(REF / "examples" / "audios" / "SampleVoiceStereo.wav"))
+    assert sr2 == sr and xs.shape == (len(x), 2) and np.array_equal(xs[:, 0], x) and np.array_equal(xs[:, 1], x)
+    st = {"stereo_pcm_sha256": np.array(hashlib.sha256(np.ascontiguousarray(xs).tobytes()).hexdigest())}
+    ys = np.stack([y, y], axis=1)                                      # [samples, 2] at 16 kHz, like the file's two channels
+    run_into(st, "file", VADConfig(), [ys])
+    # channels that differ: right = left delayed by 37 samples and attenuated -> np.mean(axis=1) in float32
+    right = np.concatenate([np.zeros(37, np.float32), y[:-37]]) * np.float32(0.61)
+    yd = np.stack([y, right], axis=1).astype(np.float32)
+    st["diff_right"] = right
+    run_into(st, "diff", VADConfig(vad_start_probability=0.4, vad_end_probability=0.3, voice_start_frame_count=6,
+                                   voice_end_frame_count=12), [yd])
+    np.savez_compressed(OUT / "sample_voice_stereo.npz", **st)
 
     # ---------------------------------------------------------------- state_machine
     cases = {}

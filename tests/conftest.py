@@ -28,6 +28,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with `-m gpu` on the GPU box)")
 
 
+def require_cv2():
+    """OpenCV's DNN module is the third-party ONNX executor the oracle is pinned against.  It ships with this image (here
+    and on the GPU box); if it ever does not, the pin must FAIL, not skip -- a skipped pin leaves the oracle unpinned
+    without anyone noticing."""
+    try:
+        import cv2  # noqa: F401
+    except ImportError as e:                                   # pragma: no cover
+        pytest.fail(f"cv2 (OpenCV DNN) is required to pin the oracle against a third-party ONNX executor: {e}")
+
+
 def synth_streams(n_streams: int, n_samples: int, seed: int = 0) -> np.ndarray:
     """Per-stream mix of noise floors and gated harmonic 'voice' bursts (the recipe of
     examples/probability_demo.py:60-67 in the reference, seeded), so that probabilities

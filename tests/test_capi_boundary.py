@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"libcvad_b200.so does not export {n}"
     assert set(names) == set(capi.EXPORTS)
-    assert L.cvad_abi_version() == 3
+    assert L.cvad_abi_version() == 4
 
 
 def test_ctypes_struct_layout_matches_the_header(tmp_path):

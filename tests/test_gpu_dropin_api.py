@@ -289,3 +289,130 @@ def test_manager_mixed_source_rates_one_step_equals_per_rate_managers():
     mixed.close()
     for mgr in solo.values():
         mgr.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The rest of the reference's examples/audios and its v4 model selection, against the reference's own Python
+# ---------------------------------------------------------------------------------------------------------------
+
+def _run_golden(g, mode, cfg, chunks, full_probs_from=None):
+    w, log = _spy_wrapper(cfg)
+    assert w.processor.supports_batched() is True
+    probs = []
+    for c in chunks:
+        w.process_audio_data(c)
+        probs.append(w.processor.voice_probabilities[-1])
+    want_p = g[f"{mode}_probs"]
+    assert w.get_statistics()["total_frames_processed"] == len(want_p)
+    if len(chunks) == 1:                                                 # one call: the deque keeps the last 100
+        got = np.array(w.processor.voice_probabilities)
+        assert np.abs(got - want_p[-len(got):]).max() <= TOL
+    else:
+        assert np.abs(np.array(probs) - want_p).max() <= TOL
+    assert log["events"] == [tuple(e) for e in g[f"{mode}_events"].tolist()]
+    assert [len(b) for b in log["wavs"]] == g[f"{mode}_wav_len"].tolist()
+    assert [hashlib.sha256(b).hexdigest() for b in log["wavs"]] == g[f"{mode}_wav_sha"].tolist()
+    w.cleanup()
+    return log
+
+
+@pytest.mark.parametrize("mode", ["A", "B"])
+def test_vadwrapper_v4_matches_reference_python_on_sample_voice(mode, math_mode):
+    """VADConfig(model_version=V4) (config.py:242, silero_model.py:369-376): events, probabilities and the SHA-256 of
+    every WAV payload equal what the reference's unmodified Python produced on SampleVoiceMono.wav
+    (tests/golden/sample_voice_v4.npz).  The v4 engine runs its default build (CVAD_MATH_FFT) whatever the v5 math is."""
+    if math_mode != "tc16":
+        pytest.skip("v4 engines do not follow the v5 math parameter; run once")
+    from real_time_vad import SampleRate, SileroModelVersion, VADConfig
+    g4 = np.load(GOLDEN / "sample_voice_v4.npz")
+    g = np.load(GOLDEN / "sample_voice.npz")
+    if mode == "A":
+        cfg = VADConfig(model_version=SileroModelVersion.V4, sample_rate=SampleRate.SAMPLERATE_16, buffer_size=480,
+                        vad_start_probability=0.4, vad_end_probability=0.3, voice_start_frame_count=6, voice_end_frame_count=12)
+        q = g["q16k"]
+        chunks = [q[i * 480:(i + 1) * 480].astype(np.float32) / 32767.0 for i in range(len(q) // 480)]
+    else:
+        cfg, chunks = VADConfig(model_version=SileroModelVersion.V4), [g["y16k"]]
+    log = _run_golden(g4, mode, cfg, chunks)
+    assert [k for _, k in log["events"]] == [1, 2] * 4                   # v4 also finds the 4 segments
+
+
+def test_stereo_sample_file_through_vadwrapper_and_on_the_device(ref_v5):
+    """examples/audios/SampleVoiceStereo.wav: both channels equal SampleVoiceMono.wav sample for sample (asserted when
+    the golden was made), so the stereo input is rebuilt from the committed mono file.  (1) VADWrapper fed the 2-D
+    [samples, 2] array reproduces the reference's events / probabilities / WAV hashes; (2) the same array through the
+    engine's own down-mix (cvad_step_args.channels = 2) gives the same probabilities as the mono stream."""
+    from real_time_vad import VADConfig
+    from real_time_vad.engine.stream_engine import StreamEngine
+    gs = np.load(GOLDEN / "sample_voice_stereo.npz")
+    g = np.load(GOLDEN / "sample_voice.npz")
+    y = g["y16k"]
+    _run_golden(gs, "file", VADConfig(), [np.stack([y, y], axis=1)])
+    yd = np.stack([y, gs["diff_right"]], axis=1).astype(np.float32)      # channels that differ: the mean matters
+    _run_golden(gs, "diff", VADConfig(vad_start_probability=0.4, vad_end_probability=0.3, voice_start_frame_count=6,
+                                      voice_end_frame_count=12), [yd])
+    # device down-mix: [1, samples, 2] through the C ABI, hop 256 like the wrapper
+    eng = StreamEngine("v5", max_streams=4)
+    eng.configure(enable_denoising=True)
+    T = (len(y) - 512) // 256 + 1
+    r = eng.step(yd[None], hop=256)
+    assert r.probs.shape == (1, T)
+    assert np.abs(r.probs[0] - gs["diff_probs"]).max() <= TOL
+    eng.reset()
+    r2 = eng.step(np.mean(yd, axis=1)[None].astype(np.float32), hop=256)   # the host's np.mean, then mono
+    assert np.array_equal(r.probs, r2.probs)                              # the device's mean IS numpy's float32 mean
+    eng.close()
+
+
+def test_device_downmix_pcm16_three_channels_ragged(engine_factory, ref_v5):
+    """Row M on the device beyond the sample file: 3 interleaved int16 channels, several streams, several frames."""
+    from real_time_vad.engine import capi
+    eng = engine_factory(64)
+    eng.reset()
+    eng.configure(enable_denoising=True)
+    n, T, C = 21, 7, 3
+    rng = np.random.default_rng(5)
+    mono = synth_streams(n, 512 * T, seed=12)
+    x = np.stack([mono * g + 0.01 * rng.standard_normal(mono.shape) for g in (1.0, 0.5, -0.25)], axis=2)
+    q = np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16)
+    xf = q.astype(np.float32) / np.float32(32767.0)
+    want_in = np.mean(xf, axis=2)                                          # AudioUtils.convert_to_mono, float32
+    assert want_in.dtype == np.float32
+    want, _, _ = ref_v5.run(want_in, T, denoise=True)
+    r = eng.step(q, pcm_format=capi.PCM_S16_32767)
+    assert np.abs(r.probs - want).max() <= TOL
+
+
+def test_callback_that_raises_mid_call_leaves_the_stream_where_the_reference_does():
+    """vad_wrapper.py:470-476: a callback exception aborts the call at that frame; frames after it never ran.  The
+    batched path has already stepped them on the device, so it must put the stream back: LSTM state, counters and the
+    probability history after the call equal those of a wrapper that was fed exactly the frames up to the failing one."""
+    from real_time_vad import VADConfig, VADWrapper
+    from real_time_vad.core.exceptions import AudioProcessingError
+    x = synth_streams(1, 512 * 40, seed=31)[0]
+    cfg = VADConfig(vad_start_probability=0.5, vad_end_probability=0.35, voice_start_frame_count=3, voice_end_frame_count=4)
+    a, b = VADWrapper(cfg), VADWrapper(cfg)
+    seen = {"n": 0}
+
+    def boom(_pcm):
+        seen["n"] += 1
+        if seen["n"] == 5:
+            raise RuntimeError("consumer failed")
+    a.set_callbacks(voice_continue_callback=boom)
+    with pytest.raises(AudioProcessingError):
+        a.process_audio_data(x)
+    done = a._state.total_frames_processed + 1            # the failing frame ran in the reference too (callbacks come after it)
+    assert 5 <= done < (len(x) - 512) // 256 + 1
+    b.process_audio_data(x[:512 + (done - 1) * 256])       # exactly those frames, no callback trouble
+    pa, pb = a.processor, b.processor
+    assert np.array_equal(pa.model.model_state.state, pb.model.model_state.state)
+    assert (pa.is_voice_active, pa.voice_start_frame_count, pa.voice_end_frame_count) == \
+           (pb.is_voice_active, pb.voice_start_frame_count, pb.voice_end_frame_count)
+    assert list(pa.voice_probabilities) == list(pb.voice_probabilities)
+    assert pa.model.prediction_count == pb.model.prediction_count == done
+    # and the stream goes on from there like the other one
+    rest = x[done * 256:]
+    a.set_callbacks(voice_continue_callback=lambda _b: None)
+    a.process_audio_data(rest)
+    b.process_audio_data(rest)
+    assert np.array_equal(a.processor.model.model_state.state, b.processor.model.model_state.state)

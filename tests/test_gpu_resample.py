@@ -14,7 +14,7 @@ TOL = 1e-4
 
 @pytest.fixture(autouse=True, params=["tc", "fp32", "tc16"])
 def math_mode(request, monkeypatch):
-    """Both builds: resampler + model GEMMs on the tcgen05 tensor cores (BF16 3-way split), or FP32 FMA."""
+    """The three arithmetic builds of the v5 model kernels (and of the dense-operator resampler, where a test selects it)."""
     monkeypatch.setenv("CVAD_MATH", request.param)
     return request.param
 
@@ -29,80 +29,157 @@ def _source_audio(n, T, rate, seed):
     return up, n_in
 
 
-def _oracle_16k(x, n_in):
-    from vad_oracle import resample
-    n, L = x.shape
-    T = L // n_in
-    y = np.zeros((n, 512 * T), np.float32)
-    rate = n_in * 16000 // 512
-    for s in range(n):
-        for j in range(T):
-            y[s, j * 512:(j + 1) * 512] = resample(x[s, j * n_in:(j + 1) * n_in], rate, 16000)
-    return y
+def _oracle_16k(x, n_in, exact=False):
+    from vad_oracle import resample_chunks
+    return resample_chunks(x, n_in * 16000 // 512, exact=exact)
 
 
+def _events_equal_up_to_ties(flags_got, probs_truth, cfg, tie=2e-6):
+    """Event frames of the engine against the state machine run on the truth's probabilities.  A frame whose truth
+    probability lies within `tie` of a threshold may legitimately fall on either side; streams that contain such a
+    frame are counted and skipped, all others must match exactly.  -> (streams compared, streams skipped)"""
+    from vad_oracle import sm_flags
+    start_p, end_p, n_start, n_end = cfg
+    compared = skipped = 0
+    for s in range(probs_truth.shape[0]):
+        p = probs_truth[s]
+        if (np.abs(p - start_p) <= tie).any() or (np.abs(p - end_p) <= tie).any():
+            skipped += 1
+            continue
+        want = sm_flags(p, start_p, end_p, n_start, n_end)
+        assert np.array_equal(want & 7, flags_got[s] & 7), f"stream {s}: events differ"
+        compared += 1
+    return compared, skipped
+
+
+SM = dict(vad_start_probability=0.5, vad_end_probability=0.35, voice_start_frame_count=2, voice_end_frame_count=3)
+SM_CFG = (0.5, 0.35, 2, 3)
+
+
+@pytest.mark.parametrize("resampler", ["fft", "gemm"])
 @pytest.mark.parametrize("rate", [8000, 24000, 48000])
-def test_resampled_streams_match_scipy_then_model(engine_factory, ref_v5, rate):
+def test_resampled_streams_match_scipy_then_model(engine_factory, ref_v5, rate, resampler):
+    """v5 behind the resampler, against the literal definition: scipy.signal.resample in float32 per chunk
+    (AudioUtils.resample_audio), then the FP32 oracle.  v5 is well conditioned, so the 1e-4 bar holds on every frame for
+    the exact (FFT, float64) resampler and for the dense-operator builds alike; events are compared as well."""
     eng = engine_factory(128)
+    eng.set_resampler(resampler)
     eng.reset()
-    eng.configure(enable_denoising=False)
+    eng.configure(enable_denoising=False, **SM)
     n, T = 37, 12
     x, n_in = _source_audio(n, T, rate, seed=rate // 1000)
-    y = _oracle_16k(x, n_in)
-    want, _, _ = ref_v5.run(y, T, denoise=False)
+    want, _, _ = ref_v5.run(_oracle_16k(x, n_in), T, denoise=False)
     r1 = eng.step(x[:, :n_in * 5], src_rate=rate)            # two calls: state carries across resampled steps
     r2 = eng.step(x[:, n_in * 5:], src_rate=rate)
     got = np.concatenate([r1.probs, r2.probs], axis=1)
     assert got.shape == (n, T)
     assert np.abs(got - want).max() <= TOL
+    compared, skipped = _events_equal_up_to_ties(np.concatenate([r1.flags, r2.flags], axis=1), want.astype(np.float64), SM_CFG, tie=1e-4)
+    assert compared >= n - 4
+    eng.set_resampler("fft")
 
 
-def test_resampled_int16_with_noise_gate(engine_factory, ref_v5):
-    """48 kHz int16 PCM, gate on.  The gate (|x| > 0.01) is discontinuous, so a resampled sample
-    within 1e-6 of the threshold may fall on the other side than scipy's FP32 FFT puts it; such a
-    flip moves one sample by 0.01.  Assert the 1e-4 bar on (nearly) all frames and a loose bound on all."""
+def test_fft_resampler_is_the_correctly_rounded_scipy_operator(engine_factory, ref_v5):
+    """The FFT resampler's float32 output, observed through the gate: with the gate ON, a sample within one float32 ulp of
+    the 0.01 threshold decides whether the model sees it.  Engine vs [float64 scipy -> float32 -> gate -> FP32 oracle]:
+    EVERY frame within 1e-4; frames that hold a sample within 1 ulp of the threshold in the float64 resample are the only
+    ones excluded, and counted (expected: none or a handful)."""
     from real_time_vad.engine import capi
     eng = engine_factory(128)
     eng.reset()
-    eng.configure(enable_denoising=True)
+    eng.configure(enable_denoising=True, **SM)
     n, T = 33, 10
     x, n_in = _source_audio(n, T, 48000, seed=5)
     q = np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16)
     xf = q.astype(np.float32) / np.float32(32767.0)
-    want, _, _ = ref_v5.run(_oracle_16k(xf, n_in), T, denoise=True)
+    from scipy import signal
+    y64 = np.stack([np.concatenate([signal.resample(xf[s, j * n_in:(j + 1) * n_in].astype(np.float64), 512) for j in range(T)])
+                    for s in range(n)])
+    y = y64.astype(np.float32)
+    ulp = np.spacing(np.float32(0.01)).astype(np.float64)
+    near = (np.abs(np.abs(y64) - np.float64(np.float32(0.01))) <= ulp).reshape(n, T, 512).any(axis=2)
+    want, _, _ = ref_v5.run(y, T, denoise=True)
     r = eng.step(q, src_rate=48000, pcm_format=capi.PCM_S16_32767)
     err = np.abs(r.probs - want)
-    assert (err <= TOL).mean() >= 0.99
-    assert err.max() <= 5e-3
+    # a frame that holds a threshold-straddling sample taints the rest of its stream through the LSTM state
+    tainted = np.maximum.accumulate(near, axis=1)
+    assert tainted.sum() <= 0.02 * n * T, f"{tainted.sum()} of {n * T} frames sit on the gate threshold"
+    assert err[~tainted].max() <= TOL
+    _events_equal_up_to_ties(r.flags[~tainted.any(axis=1)], want[~tainted.any(axis=1)].astype(np.float64), SM_CFG, tie=1e-4)
 
 
-def test_resampled_v4_model(engine_factory, ref_v4):
-    """BASELINE config 3: v4 model behind the resampler.
+@pytest.fixture(scope="module")
+def truth_v4():
+    from conftest import V4_ONNX
+    from vad_oracle import Truth64
+    return Truth64(V4_ONNX, "v4")
 
-    24 kHz source (down-sampling keeps the whole 0-8 kHz band): the 1e-4 bar holds.
-    8 kHz source (config 3 proper): up-sampled audio has an EMPTY 4-8 kHz band, and v4 feeds
-    log(1 + 2^20 |STFT|) of those ~1e-7 bins into the network, so rounding-level differences
-    between two correct resamplers (scipy's FP32 FFT vs this GEMM) are amplified by ~1e4.  The same
-    happens between FP32 and FP64 evaluation of the unmodified graph (7e-4 on a pure tone,
-    DESIGN.md section 5), i.e. onnxruntime would not reproduce itself to 1e-4 there either.
-    tests/test_oracle_pinning.py::test_v4_is_ill_conditioned_on_band_limited_input shows two CPU
-    resamplers that agree to 2.4e-7 on the audio disagree by 2.4e-3 on v4's output (v5: 1e-6).
-    Asserted here: median 1e-5, 1e-4 on most frames, 1e-2 worst case."""
+
+def test_resampled_v4_model_against_float64_truth(engine_factory, ref_v4, truth_v4, math_mode):
+    """BASELINE.json configs[2]: the v4 model behind the 8 kHz resampler.
+
+    Up-sampled audio has an EMPTY 4-8 kHz band and v4 feeds log(1 + 2^20 |STFT|) of those ~1e-7 bins into the network,
+    so FP32 rounding anywhere in resampler or STFT moves the probability by up to 3e-3: the FP32 C oracle and the FP32
+    numpy interpretation of the reference's own graph differ from each other by 1.3e-3 on this input
+    (tests/test_oracle_pinning.py).  No FP32 executor can be THE reference here, so the anchor is the float64
+    evaluation: scipy.signal.resample in float64 -> float32 (the `.astype(np.float32)` is part of
+    AudioUtils.resample_audio, audio.py:55) -> the graph interpreted in float64.
+
+    Default build of v4 (CVAD_MATH_FFT + FFT resampler; the autouse fixture's v5 math is irrelevant for a v4 engine):
+      * every frame within 1e-4 of the truth -- no percentile, no exclusions;
+      * per frame, |engine - truth| <= max(1e-4, 2 |FP32 oracle - truth|) (trivially, given the first; kept as written);
+      * events identical to the state machine run on the truth, for every stream (ties within 2e-6 of a threshold counted).
+    Same for a 24 kHz source (full band), where the FP32 oracle itself is within 1e-4."""
+    if math_mode != "tc16":
+        pytest.skip("v4 engines do not follow the v5 math parameter; run once")
     eng = engine_factory(128, model_version="v4")
-    eng.configure(enable_denoising=False)
-    n, T = 40, 9
-    eng.reset()
-    x, n_in = _source_audio(n, T, 24000, seed=8)
-    want, _, _ = ref_v4.run(_oracle_16k(x, n_in), T, denoise=False)
-    r = eng.step(x, src_rate=24000)
-    assert np.abs(r.probs - want).max() <= TOL
-    eng.reset()
-    x, n_in = _source_audio(n, T, 8000, seed=8)
-    assert n_in == 256
-    want, _, _ = ref_v4.run(_oracle_16k(x, n_in), T, denoise=False)
-    r = eng.step(x, src_rate=8000)
-    err = np.abs(r.probs - want)
-    assert np.median(err) <= 1e-5 and (err <= TOL).mean() >= 0.7 and err.max() <= 1e-2
+    assert eng.math == "fft" and eng.resampler == "fft"
+    eng.configure(enable_denoising=False, **SM)
+    n, T = 40, 30
+    for rate, seed in ((8000, 8), (24000, 9)):
+        eng.reset()
+        x, n_in = _source_audio(n, T, rate, seed=seed)
+        y = _oracle_16k(x, n_in, exact=True)
+        truth = truth_v4.run(y, T)
+        oracle32, _, _ = ref_v4.run(_oracle_16k(x, n_in), T, denoise=False)
+        r = eng.step(x, src_rate=rate)
+        err = np.abs(r.probs.astype(np.float64) - truth)
+        err32 = np.abs(oracle32.astype(np.float64) - truth)
+        assert err.max() <= TOL, (rate, err.max())
+        assert np.all(err <= np.maximum(TOL, 2.0 * err32))
+        compared, skipped = _events_equal_up_to_ties(r.flags, truth, SM_CFG)
+        assert compared + skipped == n and skipped <= 2
+        if rate == 8000:
+            assert err32.max() > 3.0 * TOL          # the case is ill conditioned for FP32 (else this test proves nothing)
+        else:
+            assert err32.max() <= TOL
+
+
+@pytest.mark.parametrize("v4_math", ["fp32", "tc"])
+def test_resampled_v4_model_fp32_builds(engine_factory, ref_v4, truth_v4, math_mode, v4_math):
+    """The FP32-arithmetic builds of v4's STFT (FP32 FMA, BF16-split tensor cores) behind the exact resampler.  They are
+    FP32 executors like the oracle, so on the 8 kHz source they sit as far from the float64 truth as the oracle does:
+    bounded here by 3x the oracle's own worst error over the batch (a bar that fails if the build is worse than an FP32
+    executor has to be).  On the 24 kHz source (full band) the 1e-4 bar holds against the FP32 oracle."""
+    if math_mode != "tc16":
+        pytest.skip("v4 engines do not follow the v5 math parameter; run once")
+    eng = engine_factory(128, model_version="v4")
+    eng.set_math(v4_math)
+    try:
+        eng.configure(enable_denoising=False)
+        n, T = 40, 12
+        eng.reset()
+        x, n_in = _source_audio(n, T, 24000, seed=8)
+        want, _, _ = ref_v4.run(_oracle_16k(x, n_in), T, denoise=False)
+        assert np.abs(eng.step(x, src_rate=24000).probs - want).max() <= TOL
+        eng.reset()
+        x, n_in = _source_audio(n, T, 8000, seed=8)
+        truth = truth_v4.run(_oracle_16k(x, n_in, exact=True), T)
+        err32 = np.abs(ref_v4.run(_oracle_16k(x, n_in), T, denoise=False)[0] - truth)
+        err = np.abs(eng.step(x, src_rate=8000).probs - truth)
+        assert err.max() <= max(TOL, 3.0 * err32.max()), (err.max(), err32.max())
+    finally:
+        eng.set_math("fft")
 
 
 def test_resampler_argument_checks(engine_factory):

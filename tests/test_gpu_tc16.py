@@ -131,7 +131,8 @@ def test_engine_against_the_pytorch_reference(engine_factory, math):
 def test_engine_against_opencv_dnn_on_the_reference_graph(engine_factory, math):
     """The CUDA path against a third-party ONNX runtime executing the reference's own graph (oracle/onnx_flatten.py:
     silero_vad_v5.onnx's 16 kHz branch inside OpenCV's DNN module, state fed back per frame), 1e-4."""
-    pytest.importorskip("cv2")
+    from conftest import require_cv2
+    require_cv2()
     from conftest import V5_ONNX
     from onnx_flatten import OpenCVSession
     n, T = 6, 30

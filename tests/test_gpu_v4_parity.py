@@ -13,9 +13,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-@pytest.fixture(autouse=True, params=["tc", "fp32"])
+@pytest.fixture(autouse=True, params=["fft", "tc", "fp32"])
 def math_mode(request, monkeypatch):
-    """Both builds of the v4 front end: STFT on the tcgen05 tensor cores (BF16 3-way split) or on the FP32 pipes."""
+    """The three builds of v4's STFT: double-precision FFT + tensor-core basis-rounding correction (the default),
+    tcgen05 tensor cores with the BF16 3-way split, FP32 FMA."""
     monkeypatch.setenv("CVAD_MATH", request.param)
     from real_time_vad.engine import pool
     for (version, _dev, _path), engines in pool._ENGINES.items():
@@ -196,8 +197,8 @@ def test_v4_8k_through_the_reference_facing_session():
 def test_v4_engine_against_opencv_dnn_on_the_reference_graph(engine_factory, sr, version):
     """v4's CUDA path against a third-party ONNX runtime executing the reference's own graph (oracle/onnx_flatten.py:
     silero_vad.onnx's 16 kHz branch / 8 kHz sub-model inside OpenCV's DNN module, h / c fed back per frame)."""
-    pytest.importorskip("cv2")
-    from conftest import V4_ONNX
+    from conftest import V4_ONNX, require_cv2
+    require_cv2()
     from onnx_flatten import OpenCVSession
     n, T = 4, 10
     audio = synth_streams(n, 512 * T, seed=71) + 0.02 * np.random.default_rng(2).standard_normal((n, 512 * T)).astype(np.float32)

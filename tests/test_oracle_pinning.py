@@ -179,7 +179,8 @@ def test_v5_graph_executed_by_opencv_dnn_matches_the_goldens_and_the_c_restateme
     folded, compute nodes / attributes / weights as the file has them), is executed by cv2.dnn with the state fed
     back frame after frame, and must give the golden probabilities and states that the reference's Python produced on
     the numpy interpreter, and what the C restatement (the GPU checker) gives on speech-like streams."""
-    pytest.importorskip("cv2", reason="OpenCV's DNN module is the third-party ONNX executor of this pin")
+    from conftest import require_cv2
+    require_cv2()
     from onnx_flatten import OpenCVSession
     from conftest import synth_streams
     g = np.load(GOLDEN / "v5_frames.npz")
@@ -210,7 +211,8 @@ def test_v5_graph_executed_by_opencv_dnn_matches_the_goldens_and_the_c_restateme
 @pytest.mark.parametrize("sr", [16000, 8000])
 def test_v4_graph_executed_by_opencv_dnn_matches_the_interpreter(sr):
     """Same pin for silero_vad.onnx: its 16 kHz branch and its 8 kHz sub-model (two LSTM time steps per frame)."""
-    pytest.importorskip("cv2", reason="OpenCV's DNN module is the third-party ONNX executor of this pin")
+    from conftest import require_cv2
+    require_cv2()
     from onnx_flatten import OpenCVSession
     from onnx_interp import OnnxInterpreter
     from conftest import V4_ONNX, synth_streams

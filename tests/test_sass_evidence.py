@@ -56,9 +56,22 @@ def test_fused_kernel_runs_on_tcgen05_with_bulk_copies_and_dependent_launch(sass
 
 
 @pytest.mark.parametrize("needles", [("v5tc_recurrent_kernel", "ILb1E"), ("v5tc_recurrent_kernel", "ILb0E"),
-                                     ("resample_tc_kernel", "ILb1E"), ("v4tc_stft_kernel",),
+                                     ("resample_tc_kernel", "ILb1E"), ("v4tc_stft_kernel", "ILb0E"), ("v4tc_stft_kernel", "ILb1E"),
                                      ("v5tc_frontend_kernel", "ILb0ELb0ELb1E"), ("v5tc_frontend_kernel", "ILb0ELb1ELb0E")])
 def test_every_tensor_core_kernel_issues_tcgen05(sass, needles):
     _, funcs = sass
     k = _one(funcs, *needles)
     assert "UTCHMMA" in k and "LDTM" in k and "UBLKCP" in k
+
+
+def test_fft_kernels_run_on_the_fp64_pipe(sass):
+    """The exact resampler and v4's STFT are double-precision FFTs (csrc/cvad_fftk.cuh): DFMA / DADD / DMUL in the SASS,
+    no tensor-core instruction, and the resampler carries the primary side of programmatic dependent launch."""
+    _, funcs = sass
+    for needles in (("resample_fft_kernel", "ILi1E"), ("resample_fft_kernel", "ILi3E"), ("resample_fft_kernel", "ILi6E"),
+                    ("v4_stft_fft_kernel",)):
+        k = _one(funcs, *needles)
+        assert k.count("DFMA") + k.count("DADD") + k.count("DMUL") >= 300, needles
+        assert "UTCHMMA" not in k
+        if needles[0] == "resample_fft_kernel":
+            assert "PREEXIT" in k
