@@ -1,20 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 Silero-VAD stream engine.
 
-Metric (BASELINE.json): audio-seconds per wall-second over N concurrent 16 kHz streams
-(Silero v5), plus p99 latency of one batched frame step.  Workload = configs[1]:
-4,096 concurrent 16 kHz streams per GPU, every step advances every stream by
-`--frames-per-step` 512-sample frames (hop 512).  Weak scaling: streams per GPU fixed.
+Metric (BASELINE.json): audio-seconds per wall-second over N concurrent 16 kHz streams (Silero v5), plus p99 latency
+of one batched frame step.  Headline workload = configs[1]: 4,096 concurrent 16 kHz streams per GPU, every step advances
+every stream by `--frames-per-step` 512-sample frames (hop 512).  Weak scaling: streams per GPU fixed.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]              our arm
   python bench.py --impl reference [...]                            CPU arm (oracle port, all host threads)
 
-One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+One JSON line on stdout (rank 0).  Besides the contract's keys (DESIGN.md "Measurement"):
+  value / ms_per_step      median over `repeats` timed regions of exactly K steps each (barrier + synchronize on both
+                           sides of every region, max over ranks per region); value_min / value_max beside it
+  e2e                      the public host-buffer call with the wire format (int16 PCM, CVAD_PCM_S16_32767) in pinned host
+                           buffers, H2D + D2H inside the timed region; e2e.f32 = the same with float32 PCM
+  value_fp32               the same workload on the FP32-FMA build of the kernels (same-precision anchor)
+  extra                    the other configurations of BASELINE.json, each with its own roofline:
+                             configs2  v4 behind the 8 kHz resampler, 16,384 streams (N = 1 only)
+                             configs3  v5, 8,192 streams per GPU, 24 / 48 kHz mixed, resampled on the GPU (every N: the
+                                       65,536-stream configuration is 8 of these), device-resident and e2e (int16 wire)
+                             configs4  10,000 live streams through BatchedVADManager, 30 ms int16 messages with jitter,
+                                       p50 / p99 of one tick (N = 1 only)
 """
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import json
 import os
 import statistics
@@ -22,6 +31,7 @@ import subprocess
 import sys
 import threading
 import time
+from collections import deque
 from pathlib import Path
 
 import numpy as np
@@ -29,17 +39,19 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT / "cutter-vad_b200"))
 
-FLOP_FRAME = 1_127_936          # v5/16k nominal FLOP per 512-sample frame
-FLOP_FRONTEND = 865_536         # STFT + encoder.0-3 share (432,768 MAC)
-FLOP_RECURRENT = 262_400        # LSTM + decoder share (131,200 MAC)
+FLOP_V5 = 1_127_936             # v5/16k nominal FLOP per 512-sample frame
+FLOP_V5_FE = 865_536            # STFT + encoder.0-3 share (432,768 MAC)
+FLOP_V5_REC = 262_400           # LSTM + decoder share (131,200 MAC)
+FLOP_V4 = 1_379_280             # v4/16k nominal (dense STFT counted as the graph states it)
 SMS, FP32_LANES = 148, 128
+# FFT resampler, algorithmic FLOP per chunk: 2.5 N log2 N (real forward) + 2.5 * 512 * 9 (real inverse)
+FLOP_RESAMPLE = {8000: 16_640, 24000: 29_900, 48000: 52_160, 16000: 0}
 
 
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
-        d = json.loads(p.read_text())
-        return d, "measured"
+        return json.loads(p.read_text()), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
@@ -84,7 +96,7 @@ def synth_audio(n_streams: int, n_samples: int, seed: int) -> np.ndarray:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the measurement (B200_PROFILING.md recipe)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -109,7 +121,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """index of the next sample: lets a caller cut out the samples taken during one leg"""
+        return len(self.lines)
+
+    def stop(self, lo: int = 0, hi: int = None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -118,22 +134,26 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        return self.summary(lo, hi)
+
+    def summary(self, lo: int = 0, hi: int = None):
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[lo:hi]:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
             try:
                 sm.append(float(parts[0]))
                 mx.append(float(parts[1]))
+                pw.append(float(parts[2]))
             except ValueError:
                 continue
             for nm, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -168,6 +188,20 @@ def cpu_baseline_sample(n_streams: int, target_s: float = 12.0):
                       f"oracle/silero_ref.c -O3 -march=native + OpenMP; CPU restatement, not onnxruntime"}
 
 
+def workload_config(model: str, streams: int, frames_per_step: int, rate: int = 16000, mixed: bool = False):
+    """`config` of the JSON line: the workload only, identical in both arms (arithmetic and cache notes are separate keys)."""
+    what = f"Silero {model}, {streams} concurrent {rate // 1000} kHz streams per GPU batched per frame step"
+    if (model, rate, mixed) == ("v5", 16000, False):
+        what += " (BASELINE.json configs[1])"
+    elif mixed:
+        what = (f"Silero {model}, {streams} concurrent streams per GPU, 24 / 48 kHz by stream parity, resampled to 16 kHz on the "
+                "GPU and stepped one frame per call (BASELINE.json configs[3] per-GPU share)")
+    elif rate != 16000:
+        what += ", resampled to 16 kHz on the GPU"
+    return {"workload": what, "model": model, "src_rate": rate, "streams_per_gpu": streams,
+            "frames_per_step": frames_per_step, "hop": 512, "frame_len": 512, "denoise": True, "state_machine": True}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -192,8 +226,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, pool_mb=None),
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config("v5", n, F),
         "p99_step_ms": 1e3 * float(np.percentile(lat, 99)),
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
                          "sample": f"every step = full workload ({n} streams x {F} frames); oracle/silero_ref.c "
@@ -205,27 +239,313 @@ def run_reference_arm(args):
     emit(line)
 
 
-def workload_config(args, pool_mb):
-    model = getattr(args, "model", "v5")
-    rate = getattr(args, "src_rate", 16000)
-    return {"workload": f"Silero {model}, {args.streams} concurrent {rate // 1000} kHz streams per GPU batched per "
-                        f"frame step" + (" (BASELINE.json configs[1])" if (model, rate) == ("v5", 16000) else
-                                         ", mixed 24/48 kHz by stream parity, resampled to 16 kHz on the GPU in one step "
-                                         "(BASELINE.json configs[3] per-GPU share)" if getattr(args, "mixed_rates", False) else
-                                         ", resampled to 16 kHz on the GPU" if rate != 16000 else ""),
-            "model": model, "src_rate": rate,
-            "streams_per_gpu": args.streams, "frames_per_step": args.frames_per_step, "hop": 512,
-            "frame_len": 512, "denoise": True, "state_machine": True, "math": getattr(args, "math", "fp32"),
-            "l2": (f"inputs cycle through a pool of distinct step buffers totalling {pool_mb} MB (> 126 MB L2)"
-                   if pool_mb else "n/a (CPU arm)")}
-
-
 # ----------------------------------------------------------------------------- GPU arm
+
+def pin_to_gpu_numa_node(local: int):
+    """Bind this rank's host threads to the CPUs of its GPU's NUMA node BEFORE any pinned buffer is allocated, so that the
+    pages the H2D copies read are local to the GPU's PCIe root (every rank on node 0 halves the copy rate at 8 GPUs)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                   # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "the platform reports no NUMA affinity for this GPU"}
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return {"numa_node": node, "note": "no allowed CPU on the GPU's node"}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as exc:                              # measurement aid only: never fail the bench over it
+        return {"numa_node": None, "note": f"not pinned: {exc}"}
+
+
+class Workload:
+    """Synthetic inputs of one configuration: a pool of distinct step buffers (> 126 MB L2 in total) on the device, and,
+    for the e2e legs, the same in pinned host memory as float32 and as int16 PCM."""
+
+    def __init__(self, torch, local, rank, model, n, F, rate, mixed, want_host=True, pool_bytes=300e6):
+        from real_time_vad.engine import capi
+        self.torch, self.capi, self.local = torch, capi, local
+        self.model, self.n, self.F, self.rate, self.mixed = model, n, F, rate, mixed
+        self.n_in = 1536 if mixed else rate * 512 // 16000          # row length per frame (24 kHz rows use the first half)
+        self.step_samples = self.n_in * F
+        self.step_bytes_f32 = n * self.step_samples * 4
+        self.pool_n = int(min(64, max(2, np.ceil(pool_bytes / self.step_bytes_f32))))
+        self.rates_np = np.where(np.arange(n) & 1, 48000, 24000).astype(np.int32) if mixed else None
+        cu = f"cuda:{local}"
+        self.host_f32, self.host_s16, self.dev = [], [], []
+        for i in range(self.pool_n):
+            x = synth_audio(n, self.step_samples, seed=rank * 7919 + i + (17 if mixed else 0) + rate)
+            if want_host:
+                t = torch.empty((n, self.step_samples), dtype=torch.float32).pin_memory()
+                t.numpy()[:] = x
+                self.host_f32.append(t)
+                if i < 8:
+                    q = torch.empty((n, self.step_samples), dtype=torch.int16).pin_memory()
+                    q.numpy()[:] = np.clip(np.rint(x * 32767.0), -32768, 32767).astype(np.int16)
+                    self.host_s16.append(q)
+                self.dev.append(t.to(cu))
+            else:
+                self.dev.append(torch.from_numpy(x).to(cu))
+        self.d_probs = torch.zeros((n, F), dtype=torch.float32, device=cu)
+        self.d_flags = torch.zeros((n, F), dtype=torch.uint8, device=cu)
+        self.max_events = max(16, 2 * n * F)
+        self.d_events = torch.zeros((self.max_events * 24,), dtype=torch.uint8, device=cu)
+        self.d_nev = torch.zeros((1,), dtype=torch.int32, device=cu)
+        self.d_rates = torch.from_numpy(self.rates_np).to(cu) if mixed else None
+        self.dargs = [self._dev_args(b) for b in self.dev]
+        self.rate_kw = {"src_rates": self.rates_np, "max_frames": F} if mixed else {"src_rate": rate}
+
+    def _dev_args(self, buf):
+        a = self.capi.StepArgs()
+        a.n_streams = self.n
+        a.audio = buf.data_ptr()
+        a.pcm_format = self.capi.PCM_F32
+        a.stream_stride = self.step_samples
+        a.max_frames = self.F
+        a.frame_len = a.hop = self.n_in
+        a.src_rate = 48000 if self.mixed else self.rate
+        if self.mixed:
+            a.src_rates = self.d_rates.data_ptr()
+        a.probs_out = self.d_probs.data_ptr()
+        a.flags_out = self.d_flags.data_ptr()
+        a.events_out = self.d_events.data_ptr()
+        a.max_events = self.max_events
+        a.n_events_out = self.d_nev.data_ptr()
+        return a
+
+    @property
+    def audio_s_per_step(self):
+        return self.n * self.F * 0.032
+
+
+def time_device(torch, dist, world, eng, wl, stream, steps, warmup, min_repeats=15, target_s=1.5, max_repeats=2000):
+    """`value` leg: inputs resident in HBM, cvad_step_device, CUDA events on the engine's stream.  The region of exactly
+    `steps` steps is timed `repeats` times (barrier + synchronize on both sides of each); per region the max over ranks.
+    -> dict(region_ms [repeats], launches per region, per-step latency p50 / p99, per-kernel ms from a separate pass)"""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.reset()
+    for i in range(warmup):
+        eng.step_device(wl.dargs[i % wl.pool_n])
+    eng.sync()
+    barrier()
+
+    def region(k0):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for i in range(steps):
+                eng.step_device(wl.dargs[(k0 + i) % wl.pool_n])
+            e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1), eng.launch_count() - l0
+
+    first_ms, launches = region(warmup)
+    repeats = int(min(max_repeats, max(min_repeats, target_s * 1e3 / max(first_ms, 1e-3))))
+    if world > 1:                                            # every rank must run the same number of barriers
+        r = torch.tensor([repeats], dtype=torch.int64, device=f"cuda:{wl.local}")
+        dist.all_reduce(r, op=dist.ReduceOp.MIN)
+        repeats = int(r[0])
+    ms = [first_ms]
+    for r in range(1, repeats):
+        t, _ = region(warmup + r * steps)
+        ms.append(t)
+    ms_t = torch.tensor(ms, dtype=torch.float64, device=f"cuda:{wl.local}")
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    region_ms = ms_t.cpu().numpy()
+    # per-kernel durations for the roofline: the same K steps again with events around the kernels
+    # (kept out of the passes above: events between the kernels would serialise their overlap)
+    eng.set_timing(True)
+    with torch.cuda.stream(stream):
+        for i in range(steps):
+            eng.step_device(wl.dargs[(warmup + i) % wl.pool_n])
+    barrier()
+    fe_ms, rec_ms, n_timed = eng.read_timing()
+    eng.set_timing(False)
+    lat = []
+    for i in range(min(max(steps, 50), 200)):
+        a0 = torch.cuda.Event(enable_timing=True)
+        a1 = torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        eng.step_device(wl.dargs[i % wl.pool_n])
+        a1.record(stream)
+        a1.synchronize()
+        lat.append(a0.elapsed_time(a1))
+    return {"region_ms": region_ms, "launches": int(launches), "repeats": repeats,
+            "fe_ms": fe_ms / max(n_timed, 1), "rec_ms": rec_ms / max(n_timed, 1),
+            "p50_step_ms": float(np.percentile(lat, 50)), "p99_step_ms": float(np.percentile(lat, 99))}
+
+
+def time_e2e(torch, dist, world, eng, wl, steps, warmup, pcm: str, depth=3, min_s=0.5):
+    """`e2e` leg: the public host-buffer call (StreamEngine.submit / collect -> cvad_step_submit / _collect) with `depth`
+    steps in flight; every step's H2D of its inputs and D2H of its results is inside the timed region (wall clock, max
+    over ranks).  The K-step region is repeated until `min_s` seconds have been measured; the median region counts."""
+    capi = wl.capi
+    pool = [t.numpy() for t in (wl.host_s16 if pcm == "s16" else wl.host_f32)]
+    kw = dict(wl.rate_kw)
+    if pcm == "s16":
+        kw["pcm_format"] = capi.PCM_S16_32767
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.reset()
+    for i in range(warmup):
+        eng.step(pool[i % len(pool)], **kw)
+    barrier()
+    regions, events, k0 = [], 0, 0
+    t_all = time.perf_counter()
+    while True:
+        inflight = deque()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            inflight.append(eng.submit(pool[(k0 + i) % len(pool)], **kw))
+            if len(inflight) == depth:
+                r = inflight.popleft().collect()
+        while inflight:
+            r = inflight.popleft().collect()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        events = len(r.events)
+        t = torch.tensor([dt, float(time.perf_counter() - t_all >= min_s and len(regions) + 1 >= 5)],
+                         dtype=torch.float64, device=f"cuda:{wl.local}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        regions.append(float(t[0]))
+        k0 += steps
+        if float(t[1]) > 0 or len(regions) >= 400:
+            break
+    # one call at a time: latency distribution of the blocking form
+    lat = []
+    for i in range(min(max(steps, 50), 200)):
+        t1 = time.perf_counter()
+        eng.step(pool[i % len(pool)], **kw)
+        lat.append(time.perf_counter() - t1)
+    med = float(np.median(regions))
+    es = 2 if pcm == "s16" else 4
+    return {"value": wl.audio_s_per_step * steps * world / med, "unit": "audio-s/s",
+            "h2d_bytes_per_step": wl.n * wl.step_samples * es, "d2h_bytes_per_step": wl.n * wl.F * 5 + wl.n * 4 + 4,
+            "ms_per_step": 1e3 * med / steps, "repeats": len(regions),
+            "value_min": wl.audio_s_per_step * steps * world / max(regions),
+            "value_max": wl.audio_s_per_step * steps * world / min(regions),
+            "p50_call_ms": 1e3 * float(np.percentile(lat, 50)), "p99_call_ms": 1e3 * float(np.percentile(lat, 99)),
+            "pcm": ("int16 (the websocket wire format, vad_websocket_server.py:341), / 32767.0f in the frame loader"
+                    if pcm == "s16" else "float32"),
+            "events_last_step": events}
+
+
+def pinned_copy_rate(torch, wl):
+    h0 = torch.cuda.Event(enable_timing=True)
+    h1 = torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for i in range(10):
+        wl.dev[i % wl.pool_n].copy_(wl.host_f32[i % wl.pool_n], non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    return 10 * wl.step_bytes_f32 / (h0.elapsed_time(h1) * 1e-3) / 1e9
+
+
+def service_tick(n_streams=10000, ticks=120):
+    """BASELINE.json configs[4]: `n_streams` live clients through BatchedVADManager -- 480-sample int16 messages (30 ms) with
+    arrival jitter, the websocket server's thresholds, 10 % of the streams with start / end callbacks.  Timed: the
+    manager's calls of one tick (pushes + step).  tools/bench_service.py is the long form of this."""
+    from real_time_vad import BatchedVADManager, VADConfig
+    from real_time_vad.engine import capi
+    n = n_streams
+    mgr = BatchedVADManager(max_streams=n, frame_len=480, hop=480, pcm_format=capi.PCM_S16_32767)
+    cfg = VADConfig(buffer_size=480, vad_start_probability=0.4, vad_end_probability=0.3,
+                    voice_start_frame_count=6, voice_end_frame_count=12)
+    fired = [0, 0]
+    ids = []
+    for s in range(n):
+        if s < n // 10:
+            ids.append(mgr.open_stream(cfg, on_voice_start=lambda: fired.__setitem__(0, fired[0] + 1),
+                                       on_voice_end=lambda b: fired.__setitem__(1, fired[1] + 1)))
+        else:
+            ids.append(mgr.open_stream(cfg))
+    ids = np.array(ids)
+    rng = np.random.default_rng(0)
+    sec = 3
+    audio = np.clip(np.round(synth_audio(n, 16000 * sec, seed=1) * 32767.0), -32768, 32767).astype(np.int16)
+    pos = np.zeros(n, np.int64)
+    lat_tick, lat_step, lat_push, frames, events = [], [], [], 0, 0
+    for t in range(ticks + 10):
+        k = rng.choice([0, 1, 1, 1, 1, 1, 1, 2], size=n)               # jitter: late / on time / catching up
+        t_push = 0.0
+        for m in (1, 2):
+            sel = np.flatnonzero(k >= m)
+            if sel.size == 0:
+                continue
+            start = pos[sel] % (16000 * sec - 480)
+            block = audio[sel[:, None], start[:, None] + np.arange(480)[None, :]]   # the clients' side: not timed
+            t0 = time.perf_counter()
+            mgr.push_many(ids[sel], block)
+            t_push += time.perf_counter() - t0
+            pos[sel] += 480
+        t1 = time.perf_counter()
+        out = mgr.step()
+        t2 = time.perf_counter()
+        if t >= 10:
+            lat_tick.append(t_push + t2 - t1)
+            lat_step.append(t2 - t1)
+            lat_push.append(t_push)
+            frames += out.frames
+            events += len(out.events)
+    mgr.close()
+    total = sum(lat_tick)
+    return {"workload": f"{n} live streams through BatchedVADManager, 480-sample int16 messages with jitter, websocket thresholds, "
+                        "10 % of the streams with callbacks (BASELINE.json configs[4])",
+            "ticks": ticks, "budget_ms": 30.0,
+            "tick_ms_p50": 1e3 * float(np.percentile(lat_tick, 50)), "tick_ms_p99": 1e3 * float(np.percentile(lat_tick, 99)),
+            "step_ms_p50": 1e3 * float(np.percentile(lat_step, 50)), "step_ms_p99": 1e3 * float(np.percentile(lat_step, 99)),
+            "push_ms_p50": 1e3 * float(np.percentile(lat_push, 50)), "push_ms_p99": 1e3 * float(np.percentile(lat_push, 99)),
+            "value": frames * 0.030 / total, "unit": "audio-s/s", "frames": frames, "events": events, "callbacks_fired": fired,
+            "timed": "the manager's calls only (push_many + step); building the synthetic clients' messages is outside"}
+
+
+def simple_roofline(kernel, bound, flop_per_frame, frames_per_step, step_ms, peak, peak_src):
+    tf = frames_per_step * flop_per_frame / (step_ms * 1e-3) / 1e12
+    return {"bound": bound, "kernel": kernel, "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+            "traffic": None, "algorithmic_flop_per_frame": flop_per_frame, "frames_per_launch": frames_per_step,
+            "step_ms": step_ms, "peak_source": peak_src,
+            "note": "whole step (every kernel of it) against the peak of the pipe its dominant kernel runs on"}
+
+
+def dev_pool_mb(n, F, rate, mixed):
+    n_in = 1536 if mixed else rate * 512 // 16000
+    step_bytes = n * n_in * F * 4
+    return int(min(64, max(2, np.ceil(300e6 / step_bytes)))) * step_bytes / 1e6
+
+
+def transfer_bound(n, F, rate, mixed, world, h2d_gbs):
+    """audio-s/s the measured pinned-copy rate allows for int16 input (context for e2e: the path is PCIe-bound)"""
+    n_in = 1536 if mixed else rate * 512 // 16000
+    return n * F * 0.032 * world / (n * n_in * F * 2 / (h2d_gbs * 1e9))
+
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from real_time_vad.engine import capi
     from real_time_vad.engine.stream_engine import StreamEngine
 
     rank = int(os.environ.get("RANK", "0"))
@@ -233,263 +553,177 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this engine has no CPU fallback)")
+    numa = pin_to_gpu_numa_node(local)            # before the first pinned allocation
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    n, F = args.streams, args.frames_per_step
-    n_in = args.src_rate * 512 // 16000          # source samples per model frame
-    mixed = bool(getattr(args, "mixed_rates", False))
-    if mixed:                                      # BASELINE.json configs[3]: 24 / 48 kHz by stream parity, one step
-        args.src_rate = 48000
-        n_in = 1536                                # row length; 24 kHz streams use the first half of their row
-        rates_np = np.where(np.arange(n) & 1, 48000, 24000).astype(np.int32)
-    step_samples = n_in * F
-    step_bytes = n * step_samples * 4
-    pool_n = max(2, int(np.ceil(300e6 / step_bytes)))  # > 2x L2 worth of distinct inputs
-    pool_n = min(pool_n, 64)
     peaks, peaks_src = load_peaks()
-
-    eng = StreamEngine(args.model, max_streams=n, device=local)
-    math = args.math
-    eng.set_math(math)
-    flop_frame = FLOP_FRAME if args.model == "v5" else 1_379_280
-    flop_fe = FLOP_FRONTEND if args.model == "v5" else 1_379_280 - 2 * 65_600
-    flop_rec = FLOP_RECURRENT if args.model == "v5" else 2 * 65_600
-    if args.src_rate != 16000:
-        rs_flop = 2 * 512 * (n_in if not mixed else (768 + 1536) // 2)
-        flop_fe += rs_flop                         # the resampling GEMM runs ahead of the front end
-        flop_frame += rs_flop
-    eng.configure(enable_denoising=True)
-    stream = torch.cuda.Stream(device=local)
-    eng.set_stream(stream.cuda_stream)
-
-    # ---- synthetic inputs: pinned host pool (e2e) and device pool (kernel-only)
-    host_pool = []
-    for i in range(pool_n):
-        t = torch.empty((n, step_samples), dtype=torch.float32).pin_memory()
-        t.numpy()[:] = synth_audio(n, step_samples, seed=rank * 7919 + i)
-        host_pool.append(t)
-    dev_pool = [t.to(f"cuda:{local}", non_blocking=False) for t in host_pool]
-    d_probs = torch.zeros((n, F), dtype=torch.float32, device=f"cuda:{local}")
-    d_flags = torch.zeros((n, F), dtype=torch.uint8, device=f"cuda:{local}")
-    d_events = torch.zeros((max(16, 2 * n * F) * 24,), dtype=torch.uint8, device=f"cuda:{local}")
-    d_nev = torch.zeros((1,), dtype=torch.int32, device=f"cuda:{local}")
-
-    d_rates = torch.from_numpy(rates_np).to(f"cuda:{local}") if mixed else None
-    rate_kw = {"src_rates": rates_np, "max_frames": F} if mixed else {"src_rate": args.src_rate}
-
-    def dev_args(buf):
-        a = capi.StepArgs()
-        a.n_streams = n
-        a.audio = buf.data_ptr()
-        a.pcm_format = capi.PCM_F32
-        a.stream_stride = step_samples
-        a.max_frames = F
-        a.frame_len = n_in
-        a.hop = n_in
-        a.src_rate = args.src_rate
-        if mixed:
-            a.src_rates = d_rates.data_ptr()
-        a.probs_out = d_probs.data_ptr()
-        a.flags_out = d_flags.data_ptr()
-        a.events_out = d_events.data_ptr()
-        a.max_events = max(16, 2 * n * F)
-        a.n_events_out = d_nev.data_ptr()
-        return a
-
-    dargs = [dev_args(b) for b in dev_pool]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ================= kernel-only (`value`): inputs resident in HBM, CUDA events on the engine's stream
-    eng.reset()
-    for i in range(args.warmup):
-        eng.step_device(dargs[i % pool_n])
-    eng.sync()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = eng.launch_count()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for i in range(args.steps):
-            eng.step_device(dargs[(args.warmup + i) % pool_n])
-        e1.record(stream)
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
-    launches = eng.launch_count() - launches0
-    # per-kernel durations for the roofline: the same K steps again with an event between the two kernels
-    # (kept out of the pass above: the events would sit between the kernels and serialise their overlap)
-    eng.set_timing(True)
-    with torch.cuda.stream(stream):
-        for i in range(args.steps):
-            eng.step_device(dargs[(args.warmup + i) % pool_n])
-    barrier()
-    fe_ms, rec_ms, n_timed = eng.read_timing()
-    eng.set_timing(False)
-
-    # per-step latency distribution (device side), one step at a time
-    lat = []
-    for i in range(min(args.steps, 200)):
-        a0 = torch.cuda.Event(enable_timing=True)
-        a1 = torch.cuda.Event(enable_timing=True)
-        a0.record(stream)
-        eng.step_device(dargs[i % pool_n])
-        a1.record(stream)
-        a1.synchronize()
-        lat.append(a0.elapsed_time(a1))
-
-    # ================= end to end (`e2e`): public host-buffer call, H2D + D2H inside the timed region
-    eng.reset()
-    host_np = [t.numpy() for t in host_pool]
-    for i in range(args.warmup):
-        eng.step(host_np[i % pool_n], **rate_kw)
-    barrier()
-    # (a) blocking calls: one step at a time -> per-call latency distribution
-    e2e_lat = []
-    t0 = time.perf_counter()
-    for i in range(min(args.steps, 300)):
-        t1 = time.perf_counter()
-        r = eng.step(host_np[(args.warmup + i) % pool_n], **rate_kw)
-        e2e_lat.append(time.perf_counter() - t1)
-    torch.cuda.synchronize()
-    e2e_blocking_s = (time.perf_counter() - t0) / min(args.steps, 300)
-    # (b) pipelined calls (submit steps i+1, i+2 before collecting step i): the throughput figure.
-    #     Every step's H2D of its inputs and D2H of its results is inside the timed region.
-    eng.reset()
-    barrier()
-    from collections import deque
-    depth = 3                                      # steps in flight (the engine allows 4)
-    inflight = deque()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        inflight.append(eng.submit(host_np[(args.warmup + i) % pool_n], **rate_kw))
-        if len(inflight) == depth:
-            r = inflight.popleft().collect()
-    while inflight:
-        r = inflight.popleft().collect()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_events = len(r.events)
-    # (c) the same pipelined loop with 16-bit PCM in the host buffers (the websocket service's wire format,
-    #     vad_websocket_server.py:341; converted with /32767.0f in the frame loader): half the PCIe bytes
-    e2e_s16_s = None
-    if args.src_rate == 16000:
-        s16_pool = []
-        for i in range(min(pool_n, 8)):
-            t = torch.empty((n, step_samples), dtype=torch.int16).pin_memory()
-            t.numpy()[:] = np.clip(np.rint(host_np[i] * 32767.0), -32768, 32767).astype(np.int16)
-            s16_pool.append(t.numpy())
-        eng.reset()
-        for i in range(args.warmup):
-            eng.step(s16_pool[i % len(s16_pool)], pcm_format=capi.PCM_S16_32767)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            inflight.append(eng.submit(s16_pool[i % len(s16_pool)], pcm_format=capi.PCM_S16_32767))
-            if len(inflight) == depth:
-                inflight.popleft().collect()
-        while inflight:
-            inflight.popleft().collect()
-        torch.cuda.synchronize()
-        e2e_s16_s = time.perf_counter() - t0
-    # raw pinned host -> device copy rate of one step's input, for context (e2e is transfer-bound)
-    h0 = torch.cuda.Event(enable_timing=True)
-    h1 = torch.cuda.Event(enable_timing=True)
-    h0.record()
-    for i in range(10):
-        dev_pool[i % pool_n].copy_(host_pool[i % pool_n], non_blocking=True)
-    h1.record()
-    torch.cuda.synchronize()
-    h2d_gbs = 10 * step_bytes / (h0.elapsed_time(h1) * 1e-3) / 1e9
-    clocks = sampler.stop()
-
-    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(times[0]), float(times[1])
-
-    audio_s_per_step = n * F * 0.032
-    total_audio = audio_s_per_step * args.steps * world
-    value = total_audio / (dev_ms_max * 1e-3)
-    e2e_value = total_audio / (e2e_ms_max * 1e-3)
-    frames_per_step = n * F
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     peak_fp32 = SMS * FP32_LANES * 2 * sm_max * 1e6 / 1e12
-    fe_avg_s = fe_ms / max(n_timed, 1) * 1e-3
-    rec_avg_s = rec_ms / max(n_timed, 1) * 1e-3
-    fe_tflops = frames_per_step * flop_fe / fe_avg_s / 1e12 if fe_avg_s > 0 else 0.0
-    step_tflops = frames_per_step * flop_frame / (dev_ms / args.steps * 1e-3) / 1e12
+    peak_bf16 = float(peaks.get("bf16_tflops", 1645.0))
+    peak_bf16_src = f"{peaks_src} MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)"
+    peak_fp32_src = f"148 SMs x 128 FP32 lanes x 2 x sm_max_mhz {sm_max:.0f} ({peaks_src} MEASURED_PEAKS.json clock)"
 
-    fused = math in ("tc", "tc16") and args.model == "v5" and F == 1 and os.environ.get("CVAD_FUSE", "1") != "0"
-    h16 = fused and math == "tc16"      # FP16 two-way split: 3 tensor-core products per MAC (BF16 split: 6)
-    # chained one-frame steps (cvad_step_device on 16 kHz input): the timed region holds K launches of ONE kernel and
-    # nothing else -- no memset, no event -- each scheduled by programmatic dependent launch while its predecessor
-    # drains, so the kernel's average launch duration over the timed region is region / launches.  The duration of a
-    # launch bracketed by its own events (no overlap with its neighbours) is reported beside it.
-    chained = (math in ("tc", "tc16") and args.model == "v5" and F == 1 and args.src_rate == 16000 and not mixed
-               and os.environ.get("CVAD_FUSE", "1") != "0" and os.environ.get("CVAD_CHAIN", "1") != "0"
-               and launches == args.steps)
-    isolated_ms = fe_avg_s * 1e3
-    if fused:
-        # one kernel does the whole step (front end + LSTM step + state machine): its FLOPs are the frame's
-        flop_fe = flop_frame
-        if chained:
-            fe_avg_s = dev_ms / launches * 1e-3
-        fe_tflops = frames_per_step * flop_fe / fe_avg_s / 1e12 if fe_avg_s > 0 else 0.0
+    n, F = args.streams, args.frames_per_step
+    mixed = bool(args.mixed_rates)
+    rate = 48000 if mixed else args.src_rate
+    model, math = args.model, args.math
+    stream = torch.cuda.Stream(device=local)
+    sampler = ClockSampler(local)
+
+    # ================= headline configuration
+    wl = Workload(torch, local, rank, model, n, F, rate, mixed)
+    eng = StreamEngine(model, max_streams=n, device=local)
+    eng.set_math(math)
+    eng.configure(enable_denoising=True)
+    eng.set_stream(stream.cuda_stream)
+    sampler.start()
+    time.sleep(0.12)
+    c_lo = sampler.mark()
+    dev = time_device(torch, dist, world, eng, wl, stream, args.steps, args.warmup)
+    c_hi = sampler.mark()
+    e2e = time_e2e(torch, dist, world, eng, wl, args.steps, args.warmup, "s16")
+    e2e_f32 = time_e2e(torch, dist, world, eng, wl, args.steps, args.warmup, "f32")
+    h2d_gbs = pinned_copy_rate(torch, wl)
+    eng.close()
+
+    region = dev["region_ms"]
+    med_ms = float(np.median(region))
+    total_audio = wl.audio_s_per_step * args.steps * world
+    value = total_audio / (med_ms * 1e-3)
+    frames_per_step = n * F
+    step_ms = med_ms / args.steps
+
+    extras = {}
+    value_fp32 = None
+    run_extras = not args.no_extras and (model, rate, mixed, F) == ("v5", 16000, False, 1)
+    # ================= same workload, FP32-FMA build (same-precision anchor) -- N = 1 only
+    if run_extras and world == 1:
+        e32 = StreamEngine(model, max_streams=n, device=local)
+        e32.set_math("fp32")
+        e32.configure(enable_denoising=True)
+        e32.set_stream(stream.cuda_stream)
+        d32 = time_device(torch, dist, world, e32, wl, stream, args.steps, args.warmup, target_s=0.5)
+        e32.close()
+        m32 = float(np.median(d32["region_ms"]))
+        value_fp32 = {"value": total_audio / (m32 * 1e-3), "unit": "audio-s/s", "ms_per_step": m32 / args.steps,
+                      "math": "fp32 (packed FP32 FMA on the CUDA cores, ascending-k accumulation)", "repeats": d32["repeats"],
+                      "roofline": simple_roofline("v5_frontend_kernel + v5_recurrent_kernel", "fp32_ffma", FLOP_V5, frames_per_step,
+                                                  m32 / args.steps, peak_fp32, peak_fp32_src)}
+    del wl
+    torch.cuda.empty_cache()
+
+    # ================= configs[3] per-GPU share: 8,192 streams, 24 / 48 kHz mixed -- every N
+    if run_extras:
+        w3 = Workload(torch, local, rank, "v5", 8192, 1, 48000, True, pool_bytes=200e6)
+        e3 = StreamEngine("v5", max_streams=8192, device=local)
+        e3.configure(enable_denoising=True)
+        e3.set_stream(stream.cuda_stream)
+        d3 = time_device(torch, dist, world, e3, w3, stream, args.steps, args.warmup, target_s=0.5)
+        x3 = time_e2e(torch, dist, world, e3, w3, args.steps, args.warmup, "s16", min_s=0.4)
+        e3.close()
+        m3 = float(np.median(d3["region_ms"]))
+        flop3 = FLOP_V5 + (FLOP_RESAMPLE[24000] + FLOP_RESAMPLE[48000]) // 2
+        extras["configs3"] = {
+            "config": workload_config("v5", 8192, 1, 48000, True), "n_gpus": world,
+            "value": w3.audio_s_per_step * args.steps * world / (m3 * 1e-3), "unit": "audio-s/s", "ms_per_step": m3 / args.steps,
+            "p99_step_ms": d3["p99_step_ms"], "repeats": d3["repeats"], "gpu_launches": d3["launches"],
+            "e2e": x3,
+            "roofline": simple_roofline("rate_lists + 2 x resample_fft_kernel + v5tc_frontend_kernel<FUSED,H16>", "tensor", flop3,
+                                        8192, m3 / args.steps, peak_bf16, peak_bf16_src)}
+        del w3
+        torch.cuda.empty_cache()
+
+    # ================= configs[2]: v4 behind the 8 kHz resampler, 16,384 streams -- N = 1 only
+    if run_extras and world == 1:
+        w2 = Workload(torch, local, rank, "v4", 16384, 1, 8000, False, want_host=False, pool_bytes=200e6)
+        e2 = StreamEngine("v4", max_streams=16384, device=local)
+        e2.configure(enable_denoising=True)
+        e2.set_stream(stream.cuda_stream)
+        k2 = max(args.steps // 4, 5)
+        d2 = time_device(torch, dist, world, e2, w2, stream, k2, args.warmup, target_s=0.5)
+        m2 = float(np.median(d2["region_ms"])) / k2
+        extras["configs2"] = {
+            "config": workload_config("v4", 16384, 1, 8000), "math": e2.math, "n_gpus": 1, "steps": k2,
+            "value": w2.audio_s_per_step / (m2 * 1e-3), "unit": "audio-s/s", "ms_per_step": m2,
+            "p99_step_ms": d2["p99_step_ms"], "repeats": d2["repeats"], "gpu_launches": d2["launches"],
+            "kernel_ms": {"frontend_kernels": d2["fe_ms"], "v4_recurrent_kernel": d2["rec_ms"]},
+            "roofline": simple_roofline("resample_fft<1> + v4_stft_fft + v4tc_stft<CORR> + v4_frontend + v4_recurrent", "fp32_ffma",
+                                        FLOP_V4 + FLOP_RESAMPLE[8000], 16384, m2, peak_fp32, peak_fp32_src)}
+        e2.close()
+        del w2
+        torch.cuda.empty_cache()
+
+    # ================= configs[4]: the manager's tick at 10,000 live streams -- N = 1 only
+    if run_extras and world == 1:
+        try:
+            extras["configs4"] = service_tick()
+        except Exception as exc:                       # the service leg must not take the headline line down with it
+            extras["configs4"] = {"error": f"{type(exc).__name__}: {exc}"}
+    sampler.stop()
+    clocks = sampler.summary(c_lo, max(c_hi, c_lo + 1))
+    clocks["whole_run"] = sampler.summary()
+
     if rank == 0:
         tc = math in ("tc", "tc16")
-        fe_kernel = (("v4tc_stft_kernel+v4_frontend_kernel" if args.model == "v4" else
+        fused = tc and model == "v5" and F == 1 and os.environ.get("CVAD_FUSE", "1") != "0"
+        h16 = fused and math == "tc16"      # FP16 two-way split: 3 tensor-core products per MAC (BF16 split: 6)
+        # chained one-frame steps (cvad_step_device on 16 kHz input): the timed region holds K launches of ONE kernel and
+        # nothing else -- no memset, no event -- each scheduled by programmatic dependent launch while its predecessor
+        # drains, so the kernel's average launch duration over the timed region is region / launches.  The duration of a
+        # launch bracketed by its own events (no overlap with its neighbours) is reported beside it.
+        chained = (fused and rate == 16000 and not mixed and os.environ.get("CVAD_CHAIN", "1") != "0"
+                   and dev["launches"] == args.steps)
+        flop_frame = FLOP_V5 if model == "v5" else FLOP_V4
+        flop_fe = FLOP_V5_FE if model == "v5" else FLOP_V4 - 2 * 65_600
+        flop_rec = FLOP_V5_REC if model == "v5" else 2 * 65_600
+        if rate != 16000:
+            rs = (FLOP_RESAMPLE[24000] + FLOP_RESAMPLE[48000]) // 2 if mixed else FLOP_RESAMPLE[rate]
+            flop_fe += rs
+            flop_frame += rs
+        fe_s, rec_s = dev["fe_ms"] * 1e-3, dev["rec_ms"] * 1e-3
+        isolated_ms = dev["fe_ms"]
+        if fused:
+            flop_fe = flop_frame            # one kernel does the whole step
+            if chained:
+                fe_s = step_ms * 1e-3
+        fe_tflops = frames_per_step * flop_fe / fe_s / 1e12 if fe_s > 0 else 0.0
+        rec_tflops = frames_per_step * flop_rec / rec_s / 1e12 if rec_s > 0 else 0.0
+        step_tflops = frames_per_step * flop_frame / (step_ms * 1e-3) / 1e12
+        fe_kernel = (("v4_stft_fft_kernel+v4tc_stft_kernel<CORR>+v4_frontend_kernel" if math == "fft" else
+                      "v4tc_stft_kernel+v4_frontend_kernel" if model == "v4" else
                       "v5tc_frontend_kernel<FUSED,H16>" if h16 else
-                      "v5tc_frontend_kernel<FUSED>" if fused else "v5tc_frontend_kernel") if tc
-                     else f"{args.model}_frontend_kernel") + ("+resample_kernel" if args.src_rate != 16000 else "")
-        # the ncu capture of exactly this kernel variant (template arguments <DBG, FUSED, H16>)
+                      "v5tc_frontend_kernel<FUSED>" if fused else "v5tc_frontend_kernel") if (tc or math == "fft")
+                     else f"{model}_frontend_kernel") + ("+resample_fft_kernel" if rate != 16000 else "")
         variant = ("v5tc_frontend_kernel<0, 1, 1>" if h16 else "v5tc_frontend_kernel<0, 1>" if fused else
                    "v5tc_frontend_kernel<0, 0" if tc else "v5_frontend_kernel")
-        traffic = (ncu_traffic_bytes(variant)
-                   if (n == 4096 and F == 1 and args.model == "v5" and args.src_rate == 16000) else None)
-        peak_bf16 = float(peaks.get("bf16_tflops", 1645.0))
-        rec_tflops = frames_per_step * flop_rec / rec_avg_s / 1e12 if rec_avg_s else 0.0
+        traffic = ncu_traffic_bytes(variant) if (n == 4096 and F == 1 and model == "v5" and rate == 16000) else None
         fe_weight_bytes = ((622_592 + 524_288) if h16 else (933_888 + (786_432 if fused else 0))) if tc else 156032 * 4
+        peak = peak_bf16 if tc else peak_fp32
         roofline = {
             # tc: every algorithmic MAC is executed as 6 BF16 tensor-core products (3-way operand split) -- 3 FP16
             # products (2-way split, per-stream scaling) in the tc16 build of the fused kernel -- so the executed
-            # rate is 6x / 3x `achieved`; the path is bound by shared-memory operand bandwidth and by the serial
-            # loader -> MMA -> epilogue chain of one tile per SM, not by the tensor pipe
+            # rate is 6x / 3x `achieved`
             "bound": "tensor" if tc else "fp32_ffma", "kernel": fe_kernel,
-            "achieved": fe_tflops, "peak": peak_bf16 if tc else peak_fp32, "unit": "TFLOP/s",
-            "frac": fe_tflops / (peak_bf16 if tc else peak_fp32),
+            "achieved": fe_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fe_tflops / peak,
             "traffic": (traffic or {}).get("bytes"), "traffic_source": (traffic or {}).get("source"),
             "algorithmic_bytes_per_launch": frames_per_step * 2048 + fe_weight_bytes +
             frames_per_step * ((2 * 1024 + 5) if fused else 768 if tc else 512),
-            "peak_source": (f"{peaks_src} MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)" if tc else
-                            f"148 SMs x 128 FP32 lanes x 2 x sm_max_mhz {sm_max:.0f} ({peaks_src} "
-                            "MEASURED_PEAKS.json clock); the path is FP32-FFMA bound, not HBM or tensor bound"),
+            "peak_source": peak_bf16_src if tc else peak_fp32_src,
             "algorithmic_flop_per_frame": flop_fe, "frames_per_launch": frames_per_step,
-            "avg_launch_ms": fe_avg_s * 1e3,
-            "isolated_launch_ms": isolated_ms,
-            "kernel_timing": ("avg_launch_ms = timed region (CUDA events on the engine's stream) / launches: the region holds "
+            "avg_launch_ms": fe_s * 1e3, "isolated_launch_ms": isolated_ms,
+            "kernel_timing": ("avg_launch_ms = median timed region (CUDA events on the engine's stream) / launches: a region holds "
                               "nothing but this kernel's K launches, chained by programmatic dependent launch; "
-                              "isolated_launch_ms = second pass with events around every launch (no overlap)" if chained else
-                              "second pass over the same K steps with a CUDA event between the two kernels"),
+                              "isolated_launch_ms = separate pass with events around every launch (no overlap)" if chained else
+                              "separate pass over the same K steps with a CUDA event between the kernels"),
             "recurrent_kernel": ({"kernel": "(fused into the kernel above for one-frame steps)", "avg_launch_ms": 0.0,
                                   "achieved": 0.0, "algorithmic_flop_per_frame": 0} if fused else
-                                 {"kernel": "v5tc_recurrent_kernel" if tc else f"{args.model}_recurrent_kernel",
-                                  "avg_launch_ms": rec_avg_s * 1e3, "achieved": rec_tflops,
-                                  "algorithmic_flop_per_frame": flop_rec}),
-            "whole_step": {"achieved": step_tflops, "frac": step_tflops / (peak_bf16 if tc else peak_fp32),
-                           "algorithmic_flop_per_frame": flop_frame},
-            "vs_fp32_ffma_peak": {"peak": peak_fp32, "kernel_frac": fe_tflops / peak_fp32,
-                                  "whole_step_frac": step_tflops / peak_fp32},
+                                 {"kernel": "v5tc_recurrent_kernel" if tc else f"{model}_recurrent_kernel",
+                                  "avg_launch_ms": rec_s * 1e3, "achieved": rec_tflops, "algorithmic_flop_per_frame": flop_rec}),
+            "whole_step": {"achieved": step_tflops, "frac": step_tflops / peak, "algorithmic_flop_per_frame": flop_frame},
+            "vs_fp32_ffma_peak": {"peak": peak_fp32, "kernel_frac": fe_tflops / peak_fp32, "whole_step_frac": step_tflops / peak_fp32},
             "hbm": {"algorithmic_bytes_per_frame": 2048 + 2 * 1024 + 4 + 1,
-                    "achieved_gbs": frames_per_step * (2048 + 2048 + 5) / (dev_ms / args.steps * 1e-3) / 1e9,
-                    "peak_gbs": peaks.get("hbm_gbs")},
+                    "achieved_gbs": frames_per_step * (2048 + 2048 + 5) / (step_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs")},
         }
         if tc:
             products = 3 if h16 else 6
@@ -497,34 +731,37 @@ def run_ours(args):
             roofline["executed_bf16_tflops"] = products * fe_tflops
             roofline["executed_frac"] = products * fe_tflops / peak_bf16
         cpu = None if args.skip_cpu else cpu_baseline_sample(n)
+        e2e["f32"] = {k: e2e_f32[k] for k in ("value", "h2d_bytes_per_step", "ms_per_step", "value_min", "value_max", "repeats")}
+        e2e["pinned_h2d_gbs"] = h2d_gbs
+        e2e["transfer_bound_value"] = transfer_bound(n, F, rate, mixed, world, h2d_gbs)
+        e2e["numa"] = numa
+        e2e["api"] = ("StreamEngine.submit/collect -> cvad_step_submit/cvad_step_collect, three steps in flight, pinned host "
+                      "buffers; p50/p99_call_ms = one blocking StreamEngine.step at a time")
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": ("f16x2 operands with per-stream scaling, f32 accumulate (FP32-equivalent)" if h16 else
-                      "bf16x3 operands, f32 accumulate (FP32-equivalent)" if tc else "f32"),
-            "data": "synthetic", "config": workload_config(args, pool_mb=round(pool_n * step_bytes / 1e6)),
-            "p99_step_ms": float(np.percentile(lat, 99)), "p50_step_ms": float(np.percentile(lat, 50)),
+                      "bf16x3 operands, f32 accumulate (FP32-equivalent)" if tc else
+                      "f64 FFT + bf16 basis correction (STFT), f32 elsewhere" if math == "fft" else "f32"),
+            "data": "synthetic", "config": workload_config(model, n, F, rate, mixed),
+            "math": math,
+            "l2": f"inputs cycle through a pool of distinct step buffers totalling {round(dev_pool_mb(n, F, rate, mixed))} MB (> 126 MB L2)",
+            "repeats": dev["repeats"],
+            "value_min": total_audio / (float(region.max()) * 1e-3), "value_max": total_audio / (float(region.min()) * 1e-3),
+            "timing": f"value = K steps / median of {dev['repeats']} timed regions of exactly K = {args.steps} steps each "
+                      "(barrier + synchronize around every region, max over ranks per region)",
+            "p99_step_ms": dev["p99_step_ms"], "p50_step_ms": dev["p50_step_ms"],
             "frames_per_s": value / 0.032,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": step_bytes,
-                    "d2h_bytes_per_step": n * F * 5 + n * 4 + 4, "ms_per_step": e2e_ms_max / args.steps,
-                    "p99_step_ms": 1e3 * float(np.percentile(e2e_lat, 99)),
-                    "blocking_ms_per_step": 1e3 * e2e_blocking_s,
-                    "blocking_value": audio_s_per_step / e2e_blocking_s,
-                    "pinned_h2d_gbs": h2d_gbs, "transfer_bound_value": audio_s_per_step * world / (step_bytes / (h2d_gbs * 1e9)),
-                    "s16": (None if e2e_s16_s is None else
-                            {"value": audio_s_per_step * args.steps * world / e2e_s16_s, "h2d_bytes_per_step": step_bytes // 2,
-                             "pcm": "int16 / 32767.0f in the frame loader (CVAD_PCM_S16_32767)"}),
-                    "api": "StreamEngine.submit/collect -> cvad_step_submit/cvad_step_collect, three steps in flight, "
-                           "float32 PCM in pinned host buffers; p99_step_ms and blocking_* are the one-call-at-a-time "
-                           "StreamEngine.step figures", "events_last_step": e2e_events},
-            "gpu_launches": int(launches),
+            "e2e": e2e,
+            "value_fp32": value_fp32,
+            "extra": extras,
+            "gpu_launches": dev["launches"],
             "clocks": clocks,
         }
         emit(line)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -558,23 +795,24 @@ def host_threads() -> int:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
     ap.add_argument("--frames-per-step", type=int, default=1, help="512-sample frames per stream per step")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="headline configuration only (no value_fp32 / extra records)")
     ap.add_argument("--mixed-rates", action="store_true",
                     help="BASELINE.json configs[3] per-GPU share: 24 / 48 kHz streams by parity, resampled in one step")
-    ap.add_argument("--math", choices=["tc16", "tc", "fp32"], default=None,
-                    help="GEMM arithmetic: tc16 (v5 default) = tcgen05 tensor cores, FP16 2-way split with per-stream scaling for "
-                         "one-frame steps; tc = BF16 3-way split; fp32 (v4 default) = packed FP32 FMA")
+    ap.add_argument("--math", choices=["tc16", "tc", "fp32", "fft"], default=None,
+                    help="arithmetic: tc16 (v5 default) = tcgen05 tensor cores, FP16 2-way split with per-stream scaling; tc = BF16 "
+                         "3-way split; fp32 = packed FP32 FMA; fft (v4 default) = FP64 FFT STFT + tensor-core basis correction")
     ap.add_argument("--model", choices=["v5", "v4"], default="v5", help="v5 = headline (configs[1]); v4 = configs[2]")
     ap.add_argument("--src-rate", type=int, default=16000, choices=[8000, 16000, 24000, 48000],
                     help="source rate of the synthetic streams; != 16000 adds the GPU resampler (configs[2..3])")
     args = ap.parse_args()
     if args.math is None:
-        args.math = "tc16" if args.model == "v5" else "fp32"
+        args.math = "tc16" if args.model == "v5" else "fft"
     args.warmup = max(args.warmup, 3)
     _protect_stdout()
     if args.impl == "reference":

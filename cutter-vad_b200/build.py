@@ -8,6 +8,8 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 SRC = HERE / "csrc" / "cvad_capi.cu"
 OUT = HERE / "libcvad_b200.so"
+DEV_SRC = HERE / "csrc" / "cvad_dev.cu"            # development probes: a separate library, never loaded by the product
+DEV_OUT = HERE / "libcvad_b200_dev.so"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -17,13 +19,18 @@ def sources():
         [HERE.parent / "include" / "cutter_vad_b200.h"]
 
 
+def _fresh(out: Path) -> bool:
+    return out.exists() and all(out.stat().st_mtime >= s.stat().st_mtime for s in sources())
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and OUT.exists() and all(OUT.stat().st_mtime >= s.stat().st_mtime for s in sources()):
-        return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = os.environ.get("CVAD_NVCC_EXTRA", "").split()          # experiments, e.g. -DCVAD_H16_MERGE=1
-    cmd = [nvcc, *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-o", str(OUT), str(SRC)]
-    subprocess.run(cmd, check=True)
+    for src, out in ((SRC, OUT), (DEV_SRC, DEV_OUT)):
+        if not force and _fresh(out):
+            continue
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-o", str(out), str(src)]
+        subprocess.run(cmd, check=True)
     return OUT
 
 

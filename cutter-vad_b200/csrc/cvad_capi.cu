@@ -1682,70 +1682,6 @@ int cvad_step_device(cvad_engine *e, const cvad_step_args *a) {
     return launch_step(e, a, d_status, 1, nullptr, e->stream, 0xFu, chain);
 }
 
-// Hardware probe of the tcgen05 path (test hook): D[128][32] = A[128][256] * B[32][256]^T, operands are
-// raw bf16 bit patterns on the host, D is float32.  Returns 0, or a negative CVAD_E_* code.
-int cvad_tc_probe(int device, const uint16_t *a_bf16, const uint16_t *b_bf16, float *d_out) {
-    using namespace cvad::tc;
-    if (!a_bf16 || !b_bf16 || !d_out) return CVAD_E_INVALID;
-    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, CVAD_E_NOGPU, "cudaSetDevice failed");
-    __nv_bfloat16 *dA = nullptr, *dB = nullptr;
-    float *dD = nullptr;
-    CU_TRY(nullptr, cudaMalloc(reinterpret_cast<void **>(&dA), kProbeM * kProbeK * 2));
-    CU_TRY(nullptr, cudaMalloc(reinterpret_cast<void **>(&dB), kProbeN * kProbeK * 2));
-    CU_TRY(nullptr, cudaMalloc(reinterpret_cast<void **>(&dD), kProbeM * kProbeN * 4));
-    CU_TRY(nullptr, cudaMemcpy(dA, a_bf16, kProbeM * kProbeK * 2, cudaMemcpyHostToDevice));
-    CU_TRY(nullptr, cudaMemcpy(dB, b_bf16, kProbeN * kProbeK * 2, cudaMemcpyHostToDevice));
-    CU_TRY(nullptr, cudaMemset(dD, 0xFF, kProbeM * kProbeN * 4));
-    CU_TRY(nullptr, cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kProbeSmem));
-    tc_probe_kernel<<<1, 128, kProbeSmem>>>(dA, dB, dD);
-    CU_TRY(nullptr, cudaGetLastError());
-    CU_TRY(nullptr, cudaDeviceSynchronize());
-    CU_TRY(nullptr, cudaMemcpy(d_out, dD, kProbeM * kProbeN * 4, cudaMemcpyDeviceToHost));
-    cudaFree(dA); cudaFree(dB); cudaFree(dD);
-    return CVAD_OK;
-}
-
-
-int cvad_tc_rate(int device, int M, int N, int reps, int a_tiles, int n_acc, int grid, long long *out2) {
-    using namespace cvad::tc;
-    if (!out2 || a_tiles < 1 || a_tiles > 10 || (M != 64 && M != 128) || N < 8 || N > 256 || grid < 1 || n_acc < 1 || n_acc * N > 512) return CVAD_E_INVALID;
-    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, CVAD_E_NOGPU, "cudaSetDevice failed");
-    long long *d = nullptr;
-    const size_t smem = (size_t)a_tiles * 16384 + 32768 + 1024 + 64;
-    CU_TRY(nullptr, cudaMalloc(reinterpret_cast<void **>(&d), 16));
-    CU_TRY(nullptr, cudaFuncSetAttribute(tc_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_rate_kernel<<<grid, 128, smem>>>(M, N, reps, a_tiles, n_acc, d);
-    CU_TRY(nullptr, cudaGetLastError());
-    CU_TRY(nullptr, cudaDeviceSynchronize());
-    CU_TRY(nullptr, cudaMemcpy(out2, d, 16, cudaMemcpyDeviceToHost));
-    cudaFree(d);
-    return CVAD_OK;
-}
-
-int cvad_bulk_rate(int device, int tiles, int depth, int tile_bytes, int grid, size_t src_bytes, long long *out2) {
-    using namespace cvad::tc;
-    if (!out2 || tiles < 1 || depth < 1 || depth * (size_t)tile_bytes > 200 * 1024 || tile_bytes % 16 || grid < 1 ||
-        src_bytes < (size_t)tile_bytes)
-        return CVAD_E_INVALID;
-    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, CVAD_E_NOGPU, "cudaSetDevice failed");
-    long long *d = nullptr;
-    unsigned char *src = nullptr;
-    const size_t smem = (size_t)depth * tile_bytes + 1024 + 8 * depth + 64;
-    CU_TRY(nullptr, cudaMalloc(reinterpret_cast<void **>(&d), 16));
-    CU_TRY(nullptr, cudaMalloc(reinterpret_cast<void **>(&src), src_bytes));
-    CU_TRY(nullptr, cudaMemset(src, 1, src_bytes));
-    CU_TRY(nullptr, cudaFuncSetAttribute(bulk_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (int rep = 0; rep < 2; ++rep) {   // second run: source resident in L2
-        bulk_rate_kernel<<<grid, 64, smem>>>(src, src_bytes, tiles, depth, tile_bytes, d);
-        CU_TRY(nullptr, cudaGetLastError());
-        CU_TRY(nullptr, cudaDeviceSynchronize());
-    }
-    CU_TRY(nullptr, cudaMemcpy(out2, d, 16, cudaMemcpyDeviceToHost));
-    cudaFree(d);
-    cudaFree(src);
-    return CVAD_OK;
-}
-
 int cvad_resample_matrix(int src_rate, float *rt_out, size_t n_floats) {
     if (rate_index(src_rate) < 0 || !rt_out) return CVAD_E_INVALID;
     const int n_in = rate_n_in(src_rate);

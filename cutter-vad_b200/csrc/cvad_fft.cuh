@@ -96,18 +96,25 @@ CVAD_HD void fft16(double2 (&v)[16]) {
 CVAD_HD int fft16_index(int j) { return (j >> 2) + 4 * (j & 3); }   // v[j] holds X[fft16_index(j)]
 
 // Pass 1 of the 256-point transform, thread t = n2 (0..15): v[n1] = z[16 n1 + t] on entry.
-// tw[m * tws] = exp(-2 pi i m / 256).
+// tw[m * tws] = exp(-2 pi i m / 256).  The 16 twiddles W^(t k1) are powers of ONE table entry W^t: they are formed by
+// repeated multiplication (two interleaved chains, even and odd powers; 8 products deep = 1e-15 in double) instead of 16
+// dependent table loads per pass -- the loads, not the FP64 pipe, were what the first version of the kernels waited for.
 template <bool INV>
 CVAD_HD void pass1_regs(double2 (&v)[16], double2 *buf, int t, const double2 *tw, int tws) {
     fft16<INV>(v);
+    double2 w1 = tw[t * tws];
+    if (INV) w1.y = -w1.y;
+    const double2 w2 = cmul(w1, w1);
+    double2 we = make_double2(1.0, 0.0), wo = w1;          // W^(t k1) for even / odd k1
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (int j = 0; j < 16; ++j) {
-        const int k1 = fft16_index(j);
-        double2 w = tw[(t * k1) * tws];
-        if (INV) w.y = -w.y;
-        buf[k1 * kRow + t] = cmul(v[j], w);
+    for (int k1 = 0; k1 < 16; k1 += 2) {
+        // v[j] holds Y[fft16_index(j)]; fft16_index is an involution (it swaps the two base-4 digits)
+        buf[k1 * kRow + t] = k1 == 0 ? v[0] : cmul(v[fft16_index(k1)], we);
+        buf[(k1 + 1) * kRow + t] = cmul(v[fft16_index(k1 + 1)], wo);
+        we = cmul(we, w2);
+        wo = cmul(wo, w2);
     }
 }
 template <bool INV>
@@ -143,11 +150,17 @@ CVAD_HD void unpack2(const double2 *buf, int k, double2 &A, double2 &B) {
 
 // ---- resampler, spectral stage.  bufs = the frame's (R + 1) / 2 forward transforms (sub-sequences 2p, 2p + 1 in
 // transform p).  Returns the inverse transform's inputs Z[k] and Z[256 - k] for one k in 0..128.
+//   X[k]       = sum_r W^(r k) F_r[k]                                    (W = exp(-2 pi i / n_x), F_r = DFT_256 of x[R n + r])
+//   X[256 - k] = sum_r W^(r (256 - k)) conj(F_r[k]) = sum_r c_r conj(W^(r k) F_r[k]),   c_r = exp(-2 pi i r / R)
+// so both come from the same R products, and W^(r k) = (W^k)^r needs ONE table entry per bin.
 template <int R>
 CVAD_HD void rs_spectrum(const double2 *bufs, int k, const double2 *T, double2 &Zk, double2 &Zm) {
     constexpr int NX = 256 * R;
-    constexpr int TS = kMaster / NX;                     // T[TS m] = W_nx^m   (R = 1: unused)
+    constexpr int TS = kMaster / NX;                     // T[TS m] = W_nx^m
+    constexpr double H3 = 0.86602540378443864676;        // sqrt(3) / 2
     double2 P = make_double2(0.0, 0.0), Q = make_double2(0.0, 0.0);
+    const double2 wk = R == 1 ? make_double2(1.0, 0.0) : T[k * TS];
+    double2 wr = make_double2(1.0, 0.0);                 // W^(r k)
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -160,12 +173,16 @@ CVAD_HD void rs_spectrum(const double2 *bufs, int k, const double2 *T, double2 &
         for (int c = 0; c < 2; ++c) {
             const int r = 2 * p + c;
             if (r >= R) break;
-            if (R == 1) {
-                P = F[c];
-            } else {
-                P = cadd(P, cmul(F[c], T[(r * k) * TS]));                        // X[k]       += W^(r k) F_r[k]
-                Q = cadd(Q, cmul(cconj(F[c]), T[(r * (256 - k)) * TS]));         // X[256 - k] += W^(r (256 - k)) conj(F_r[k])
+            const double2 g = r == 0 ? F[c] : cmul(F[c], wr);       // W^(r k) F_r[k]
+            P = cadd(P, g);
+            if (R > 1) {
+                // c_r conj(g): c_r = exp(-2 pi i r / R), an R-th root of unity known at compile time
+                const int q = (r * 6) / R;                           // c_r = exp(-2 pi i q / 6), q = 0..5
+                const double cr = (q == 0) ? 1.0 : (q == 3) ? -1.0 : (q == 1 || q == 5) ? 0.5 : -0.5;
+                const double ci = (q == 0 || q == 3) ? 0.0 : (q < 3 ? -H3 : H3);
+                Q = cadd(Q, cmul(make_double2(cr, ci), cconj(g)));
             }
+            wr = cmul(wr, wk);
         }
     }
     const double inv = 1.0 / (double)NX;

@@ -28,12 +28,6 @@ struct RsFft {
     static constexpr size_t kSmem = (size_t)WPC * 2 * NP * fft::kBuf * sizeof(double2);
 };
 
-__device__ __forceinline__ float rs_load_sample(const ResampleStep &p, long long off) {
-    if (p.pcm == 0) return __ldg(reinterpret_cast<const float *>(p.audio) + off);
-    const float x = (float)__ldg(reinterpret_cast<const short *>(p.audio) + off);
-    return p.pcm == 1 ? __fdiv_rn(x, 32767.0f) : x * (1.0f / 32768.0f);
-}
-
 template <int R>
 __global__ void __launch_bounds__(RsFft<R>::WPC * 32, 1) resample_fft_kernel(const ResampleStep p, const double2 *__restrict__ T) {
     using namespace fft;
@@ -47,6 +41,7 @@ __global__ void __launch_bounds__(RsFft<R>::WPC * 32, 1) resample_fft_kernel(con
     const int n_items = p.count ? *p.count : p.n_streams;
     const int n_pairs = (n_items + 1) >> 1;
     const int n_units = p.max_frames * n_pairs;
+    const bool vec = (p.stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.audio) & (p.pcm == 0 ? 15u : 7u)) == 0;
     for (int unit = blockIdx.x * WPC + warp; unit < n_units; unit += gridDim.x * WPC) {
         const int frame = unit / n_pairs, pair = unit - frame * n_pairs;
         int gi[2];
@@ -63,17 +58,52 @@ __global__ void __launch_bounds__(RsFft<R>::WPC * 32, 1) resample_fft_kernel(con
         }
         if (!valid[0] && !valid[1]) continue;     // warp-uniform
 
-        // ---- load: sample m of the chunk is element m / R of sub-sequence m % R; sub-sequences 2p, 2p+1 share transform p
+        // ---- load: sample m of the chunk is element m / R of sub-sequence m % R; sub-sequences 2p, 2p+1 share transform p.
+        //      All of a frame's loads are issued (16 or 8 bytes per lane each) before the first one is used.
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
             if (!valid[f]) continue;
             double2 *fb = wb + f * NP * kBuf;
             const long long base = (long long)gi[f] * p.stride + (long long)frame * NX;
-            for (int m = lane; m < NX; m += 32) {
-                const float x = rs_load_sample(p, base + m);
-                const int r = m % R, n = m / R;
-                reinterpret_cast<double *>(fb + (r >> 1) * kBuf + pos_in(n))[r & 1] = (double)x;
+            constexpr int NV = NX / 128;                      // 4-sample groups per lane
+            float q[NV][4];
+            if (vec) {
+                if (p.pcm == 0) {
+                    const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.audio) + base);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        const float4 v = __ldg(src + lane + 32 * i);
+                        q[i][0] = v.x; q[i][1] = v.y; q[i][2] = v.z; q[i][3] = v.w;
+                    }
+                } else {
+                    const short4 *src = reinterpret_cast<const short4 *>(reinterpret_cast<const short *>(p.audio) + base);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        const short4 v = __ldg(src + lane + 32 * i);
+                        q[i][0] = (float)v.x; q[i][1] = (float)v.y; q[i][2] = (float)v.z; q[i][3] = (float)v.w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const long long off = base + 4 * (lane + 32 * i) + e;
+                        q[i][e] = p.pcm == 0 ? __ldg(reinterpret_cast<const float *>(p.audio) + off)
+                                             : (float)__ldg(reinterpret_cast<const short *>(p.audio) + off);
+                    }
             }
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float x = q[i][e];
+                    if (p.pcm == 1) x = __fdiv_rn(x, 32767.0f);
+                    else if (p.pcm == 2) x = x * (1.0f / 32768.0f);
+                    const int m = 4 * (lane + 32 * i) + e;
+                    const int r = m % R, n = m / R;
+                    reinterpret_cast<double *>(fb + (r >> 1) * kBuf + pos_in(n))[r & 1] = (double)x;
+                }
             if (R & 1)
                 for (int n = lane; n < 256; n += 32) fb[(NP - 1) * kBuf + pos_in(n)].y = 0.0;
         }
@@ -136,7 +166,7 @@ __global__ void __launch_bounds__(RsFft<R>::WPC * 32, 1) resample_fft_kernel(con
 // ---- v4 STFT.  Output per tile (16 items x 8 columns): [col = t * 16 + item][re | im][132] floats (bins 0..128)
 constexpr int kV4FftRow = 132;
 constexpr int kV4FftTile = 128 * 2 * kV4FftRow;
-constexpr size_t kV4FftSmem = (size_t)16 * 704 * sizeof(float) + (size_t)32 * fft::kBuf * sizeof(double2);
+constexpr size_t kV4FftSmem = (size_t)16 * 704 * sizeof(float) + (size_t)32 * fft::kBuf * sizeof(double2) + 256 * sizeof(double);
 
 __global__ void __launch_bounds__(512, 1) v4_stft_fft_kernel(const V5Step p, const double2 *__restrict__ T, float *__restrict__ fft_out) {
     using namespace fft;
@@ -147,41 +177,54 @@ __global__ void __launch_bounds__(512, 1) v4_stft_fft_kernel(const V5Step p, con
     float *x = xp_all + warp * 704;
     double2 *buf = bufs + (warp * 2 + half) * kBuf;
 
-    double hw[16];                                   // this thread's window values: n = 16 i + t
-#pragma unroll
-    for (int i = 0; i < 16; ++i) hw[i] = hann256(T, 16 * i + t);
+    double *hann = reinterpret_cast<double *>(xp_all + 16 * 704);    // the window, once per CTA
+    for (int n = threadIdx.x; n < 256; n += blockDim.x) hann[n] = hann256(T, n);
+    __syncthreads();
 
     const int n_ft = 2 * p.n_stiles;
     const int n_tiles = p.max_frames * n_ft;
     const int flen = p.frame_len < 512 ? p.frame_len : 512;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // this warp's item of a tile: raw samples k = lane + 32 j into registers (the NEXT tile's while the current one is transformed)
+    struct Item { bool valid; bool dn; int i; };
+    auto fetch = [&](int tile, float (&raw)[16]) -> Item {
+        Item it{false, false, 0};
+        if (tile >= n_tiles) return it;
         const int frame = tile / n_ft, ft = tile - frame * n_ft;
-        const int i = ft * 16 + warp;
-        bool valid = false;
-        int slot = -1;
-        if (i < p.n_streams) {
-            slot = p.slots ? p.slots[i] : i;
-            valid = frame < (p.n_frames ? p.n_frames[i] : p.max_frames);
+        it.i = ft * 16 + warp;
+        if (it.i < p.n_streams) {
+            const int slot = p.slots ? p.slots[it.i] : it.i;
+            it.valid = frame < (p.n_frames ? p.n_frames[it.i] : p.max_frames);
+            if (it.valid) it.dn = p.denoise[slot] != 0;
         }
-        // ---- frame loader (zero-padded / truncated to 512), gate, non-finite flag; an item that is not live reads as silence
+        const long long base = (long long)it.i * p.stride + (long long)frame * p.hop;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int k = lane + 32 * j;
+            float v = 0.f;
+            if (it.valid && k < flen)
+                v = p.pcm == 0 ? __ldg(reinterpret_cast<const float *>(p.audio) + base + k)
+                               : (float)__ldg(reinterpret_cast<const short *>(p.audio) + base + k);
+            raw[j] = v;
+        }
+        return it;
+    };
+    float cur[16], nxt[16];
+    Item it = fetch(blockIdx.x, cur);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const Item it_next = fetch(tile + gridDim.x, nxt);
+        // ---- frame (zero-padded / truncated to 512): PCM scaling, non-finite flag, gate; an item that is not live reads as silence
         {
-            const bool dn = valid ? (p.denoise[slot] != 0) : false;
-            const long long base = (long long)i * p.stride + (long long)frame * p.hop;
             bool bad = false;
-            for (int k = lane; k < 512; k += 32) {
-                float v = 0.f;
-                if (valid && k < flen) {
-                    if (p.pcm == 0) v = __ldg(reinterpret_cast<const float *>(p.audio) + base + k);
-                    else {
-                        v = (float)__ldg(reinterpret_cast<const short *>(p.audio) + base + k);
-                        v = p.pcm == 1 ? __fdiv_rn(v, 32767.0f) : v * (1.0f / 32768.0f);
-                    }
-                    if (!isfinite(v)) bad = true;
-                    if (dn && !(fabsf(v) > 0.01f)) v = 0.0f;
-                }
-                x[96 + k] = v;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float v = cur[j];
+                if (p.pcm == 1) v = __fdiv_rn(v, 32767.0f);
+                else if (p.pcm == 2) v = v * (1.0f / 32768.0f);
+                if (!isfinite(v)) bad = true;
+                if (it.dn && !(fabsf(v) > 0.01f)) v = 0.0f;
+                x[96 + lane + 32 * j] = v;
             }
-            if (__any_sync(0xffffffffu, bad) && lane == 0 && p.status) atomicOr(&p.status[i], 1u);
+            if (__any_sync(0xffffffffu, bad) && lane == 0 && p.status) atomicOr(&p.status[it.i], 1u);
         }
         __syncwarp();
         // reflect padding without edge repeat: xp[j] = x[96 - j], xp[608 + j] = x[510 - j]
@@ -198,7 +241,8 @@ __global__ void __launch_bounds__(512, 1) v4_stft_fft_kernel(const V5Step p, con
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const int n = 16 * q + t;
-                v[q] = make_double2(hw[q] * (double)x[128 * j + n], hw[q] * (double)x[128 * j + 64 + n]);
+                const double w = hann[n];
+                v[q] = make_double2(w * (double)x[128 * j + n], w * (double)x[128 * j + 64 + n]);
             }
             pass1_regs<false>(v, buf, t, T, 6);
             __syncwarp();
@@ -218,6 +262,9 @@ __global__ void __launch_bounds__(512, 1) v4_stft_fft_kernel(const V5Step p, con
             }
             __syncwarp();
         }
+        it = it_next;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
     }
 }
 

@@ -239,6 +239,10 @@ class BatchedVADManager:
         except FeederError as exc:
             self._raise(exc)
 
+    def pending(self, stream_id: int) -> int:
+        """Samples buffered for a stream that no step has consumed yet (callers use it for backpressure)."""
+        return self._feeder.pending(stream_id)
+
     def push_bytes(self, stream_id: int, data: bytes) -> None:
         """A wire message as received (the websocket server's int16 / float32 payload,
         vad_websocket_server.py:334-344) appended without a numpy round trip."""

@@ -3,7 +3,8 @@
 Same class names, constructor signatures, `error_code` strings and message texts as
 the reference's `src/real_time_vad/core/exceptions.py:8-68`, because callers and the
 reference's tests match on them (`pytest.raises(..., match=...)`).  The engine's C ABI
-return codes are mapped onto these classes in `engine/errors.py`.
+return codes become `EngineError` in `engine/stream_engine.py` and are mapped onto these classes where the mirror calls the engine
+(`core/silero_model.py`, `core/batched_manager.py`).
 """
 from __future__ import annotations
 

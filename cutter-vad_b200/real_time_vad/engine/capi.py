@@ -12,6 +12,7 @@ from pathlib import Path
 
 PKG_ROOT = Path(__file__).resolve().parents[2]          # .../cutter-vad_b200
 LIB_PATH = PKG_ROOT / "libcvad_b200.so"
+DEV_LIB_PATH = PKG_ROOT / "libcvad_b200_dev.so"     # development probes (csrc/cvad_dev.cu): tests and tools only
 
 OK, E_INVALID, E_CUDA, E_NOGPU, E_WEIGHTS, E_CAPACITY = 0, -1, -2, -3, -4, -5
 MODEL_V5, MODEL_V4, MODEL_V4_8K = 5, 4, 48
@@ -26,7 +27,7 @@ EXPORTS = (
     "cvad_abi_version", "cvad_device_count", "cvad_last_error", "cvad_create", "cvad_destroy",
     "cvad_set_stream", "cvad_reset", "cvad_configure", "cvad_get_state", "cvad_set_state",
     "cvad_step", "cvad_step_submit", "cvad_step_collect", "cvad_step_device", "cvad_sync", "cvad_launch_count", "cvad_debug_dump",
-    "cvad_alloc_pinned", "cvad_free_pinned", "cvad_set_timing", "cvad_read_timing", "cvad_resample_matrix", "cvad_tc_probe", "cvad_tc_rate", "cvad_bulk_rate",
+    "cvad_alloc_pinned", "cvad_free_pinned", "cvad_set_timing", "cvad_read_timing", "cvad_resample_matrix",
     "cvad_set_math", "cvad_get_math", "cvad_set_resampler", "cvad_get_resampler", "cvad_set_profile", "cvad_read_profile",
     "cvad_feeder_create", "cvad_feeder_destroy", "cvad_feeder_last_error", "cvad_feeder_open", "cvad_feeder_close",
     "cvad_feeder_clear", "cvad_feeder_is_active", "cvad_feeder_pending", "cvad_feeder_push", "cvad_feeder_push_many",
@@ -77,6 +78,26 @@ class FeederResult(C.Structure):
 
 
 _lib = None
+_dev_lib = None
+DEV_EXPORTS = ("cvad_dev_last_error", "cvad_tc_probe", "cvad_tc_rate", "cvad_bulk_rate")
+
+
+def dev_lib() -> C.CDLL:
+    """libcvad_b200_dev.so: hardware probes of the tcgen05 building blocks (include/cutter_vad_b200_dev.h).  The product
+    never calls this."""
+    global _dev_lib
+    if _dev_lib is None:
+        if not DEV_LIB_PATH.exists():
+            raise EngineLibraryMissing(f"{DEV_LIB_PATH} not found: build it with `python cutter-vad_b200/build.py`")
+        L = C.CDLL(str(DEV_LIB_PATH))
+        vp, i32 = C.c_void_p, C.c_int
+        L.cvad_dev_last_error.restype = C.c_char_p
+        L.cvad_tc_probe.argtypes = [i32, vp, vp, vp]
+        L.cvad_tc_rate.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp]
+        L.cvad_bulk_rate.argtypes = [i32, i32, i32, i32, i32, C.c_size_t, vp]
+        _dev_lib = L
+    return _dev_lib
+
 
 
 class EngineLibraryMissing(RuntimeError):
@@ -114,9 +135,6 @@ def lib() -> C.CDLL:
     L.cvad_set_state.argtypes = [vp, i32, vp, vp, vp]
     L.cvad_step.argtypes = [vp, C.POINTER(StepArgs)]
     L.cvad_step_device.argtypes = [vp, C.POINTER(StepArgs)]
-    L.cvad_tc_probe.argtypes = [i32, vp, vp, vp]
-    L.cvad_tc_rate.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp]
-    L.cvad_bulk_rate.argtypes = [i32, i32, i32, i32, i32, C.c_size_t, vp]
     L.cvad_resample_matrix.argtypes = [i32, vp, C.c_size_t]
     L.cvad_step_submit.argtypes = [vp, C.POINTER(StepArgs), C.POINTER(C.c_int)]
     L.cvad_step_collect.argtypes = [vp, i32]

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import asyncio
 import json
+import logging
 import threading
 import time
 import uuid
@@ -104,6 +105,8 @@ class ClientSession:
         self.last_frame_time: Optional[float] = None
         self.timeout_sent = False
         self.frame_count = 0
+        self.dropped_frames = 0
+        self._frame_samples = 1
         self.expected_frame_bytes = self._frame_bytes()
         self._manager: Optional[BatchedVADManager] = None
         self._stream: Optional[int] = None
@@ -124,6 +127,7 @@ class ClientSession:
         if a.sample_width not in (2, 4):
             raise ValueError(f"Unsupported sample width: {a.sample_width}")
         frame_samples = int(a.sample_rate * (a.frame_duration_ms / 1000))
+        self._frame_samples = max(1, frame_samples)
         cfg = VADConfig(sample_rate=SampleRate(a.sample_rate), model_version=SileroModelVersion.V5,
                         vad_start_probability=v.start_probability, vad_end_probability=v.end_probability,
                         voice_start_ratio=v.start_ratio, voice_end_ratio=v.end_ratio,
@@ -136,6 +140,7 @@ class ClientSession:
     def _detach(self) -> None:
         if self._manager is not None and self._stream is not None:
             self._manager.close_stream(self._stream)
+            self.service.release_if_idle(self._manager)
         self._manager, self._stream = None, None
 
     def update_config(self, new_config: ClientConfig) -> None:
@@ -154,6 +159,13 @@ class ClientSession:
         try:
             if len(frame_data) != self.expected_frame_bytes:
                 await self._send_error(f"Invalid frame size: expected {self.expected_frame_bytes}, got {len(frame_data)}")
+                return
+            # backpressure: the reference ran the model inside this call, so a client could never be more than one
+            # message ahead; here audio waits for the next tick, and a flooding client must not grow the shared arena
+            if self._manager.pending(self._stream) >= self.service.max_pending_frames * self._frame_samples:
+                self.dropped_frames += 1
+                if self.dropped_frames == 1 or self.dropped_frames % 100 == 0:
+                    await self._send_error(f"Audio arrives faster than real time: {self.dropped_frames} frame(s) dropped")
                 return
             self.frame_count += 1
             self._manager.push_bytes(self._stream, frame_data)
@@ -215,10 +227,18 @@ class ClientSession:
 class BatchedVADService:
     """All clients of one process: managers keyed by wire format, one GPU step per tick for everybody."""
 
-    def __init__(self, max_clients: int = 10_000, device: Optional[int] = None, tick_s: float = 0.010) -> None:
+    def __init__(self, max_clients: int = 10_000, device: Optional[int] = None, tick_s: float = 0.010,
+                 max_formats: int = 4, max_pending_frames: int = 64) -> None:
         self.max_clients = max_clients
         self.device = device
         self.tick_s = tick_s
+        # a manager owns a max_clients-slot engine and a pinned arena: remote clients choose the wire format, so the number
+        # of distinct formats alive at once is capped, idle managers are freed, and a stream may be at most
+        # max_pending_frames messages ahead of the tick
+        self.max_formats = max_formats
+        self.max_pending_frames = max_pending_frames
+        self.last_error: Optional[str] = None
+        self.failed_ticks = 0
         self.sessions: Dict[str, ClientSession] = {}
         self._managers: Dict[Tuple[int, int, int], BatchedVADManager] = {}
         self.step_lock = threading.RLock()         # open / close / reconfigure vs the step thread
@@ -230,6 +250,9 @@ class BatchedVADService:
         with self.step_lock:
             m = self._managers.get(key)
             if m is None:
+                if len(self._managers) >= self.max_formats:
+                    raise ValueError(f"too many distinct audio formats in use ({len(self._managers)}); "
+                                     f"supported at once: {self.max_formats}")
                 pcm = capi.PCM_S16_32767 if sample_width == 2 else capi.PCM_F32          # server.py:341 divides by 32767
                 if sample_rate == 16000:
                     m = BatchedVADManager(max_streams=self.max_clients, device=self.device, frame_len=frame_samples,
@@ -239,6 +262,16 @@ class BatchedVADService:
                                           source_rate=sample_rate)
                 self._managers[key] = m
             return m
+
+    def release_if_idle(self, manager: BatchedVADManager) -> None:
+        """Free a manager (engine, device state, pinned arena) once its last stream has closed."""
+        with self.step_lock:
+            if manager.open_streams:
+                return
+            for key, m in list(self._managers.items()):
+                if m is manager:
+                    del self._managers[key]
+                    m.close()
 
     def connect(self, send_text: Callable[[str], Awaitable[None]], config: ClientConfig,
                 client_id: Optional[str] = None) -> ClientSession:
@@ -268,9 +301,22 @@ class BatchedVADService:
         return n
 
     async def run(self) -> None:
+        """The process's one step loop.  A failing tick (a CUDA error, an allocation failure, a callback error) must not
+        end the loop silently while clients keep sending: it is logged, reported to every session and on /health, and
+        the loop goes on."""
         while True:
             t0 = time.perf_counter()
-            await self.tick()
+            try:
+                await self.tick()
+                self.last_error = None
+            except asyncio.CancelledError:
+                raise
+            except Exception as exc:
+                self.failed_ticks += 1
+                self.last_error = f"{type(exc).__name__}: {exc}"
+                logging.getLogger(__name__).exception("VAD tick failed")
+                for s in list(self.sessions.values()):
+                    await s._send_error(f"VAD step failed: {exc}")
             await asyncio.sleep(max(0.0, self.tick_s - (time.perf_counter() - t0)))
 
     def close(self) -> None:
@@ -292,6 +338,12 @@ def create_app(service: Optional[BatchedVADService] = None):
     @asynccontextmanager
     async def lifespan(app):
         ticker = asyncio.create_task(svc.run())       # the one step loop of the process
+
+        def _ticker_done(task: "asyncio.Task") -> None:
+            if not task.cancelled() and task.exception() is not None:
+                svc.last_error = f"ticker stopped: {task.exception()!r}"
+                logging.getLogger(__name__).error("VAD ticker stopped: %r", task.exception())
+        ticker.add_done_callback(_ticker_done)
         try:
             yield
         finally:
@@ -361,7 +413,8 @@ def create_app(service: Optional[BatchedVADService] = None):
 
     @app.get("/health")
     async def health():
-        return {"status": "healthy", "connected_clients": len(svc.sessions), "timestamp": _now_ms()}
+        return {"status": "healthy" if svc.last_error is None else "degraded", "last_error": svc.last_error,
+                "failed_ticks": svc.failed_ticks, "connected_clients": len(svc.sessions), "timestamp": _now_ms()}
 
     @app.get("/clients")
     async def clients():

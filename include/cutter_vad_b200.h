@@ -222,18 +222,6 @@ int cvad_sync(cvad_engine *e);
    such that y[n] = sum_m R^T[m][n] x[m] equals scipy.signal.resample(x, 512).  Returns n_in. */
 int cvad_resample_matrix(int src_rate, float *rt_out, size_t n_floats);
 
-/* Test hook: one 128x32x256 BF16 tensor-core GEMM (tcgen05, TMEM accumulator) on `device`;
-   a_bf16[128][256], b_bf16[32][256] are raw bf16 bit patterns, d_out[128][32] = A * B^T in float32. */
-int cvad_tc_probe(int device, const uint16_t *a_bf16, const uint16_t *b_bf16, float *d_out);
-
-/* Measurement hook: issue reps x 4 BF16 MMAs of shape M x N x 16 (both operands in shared memory) on
-   `grid` CTAs, cycling over n_acc TMEM accumulators; out2[0] = SM cycles from first issue to completion on CTA 0, out2[1] = MMAs issued. */
-int cvad_tc_rate(int device, int M, int N, int reps, int a_tiles, int n_acc, int grid, long long *out2);
-
-/* Measurement hook: one thread per CTA streams `tiles` cp.async.bulk copies of tile_bytes through a ring of `depth`
-   slots from a src_bytes buffer (L2-resident on the measured run); out2[0] = SM cycles on CTA 0, out2[1] = tiles. */
-int cvad_bulk_rate(int device, int tiles, int depth, int tile_bytes, int grid, size_t src_bytes, long long *out2);
-
 /* Page-locked host memory for callers that want cvad_step to DMA straight from their
    buffer (pageable buffers are staged through the engine's own pinned area). */
 void *cvad_alloc_pinned(size_t bytes);

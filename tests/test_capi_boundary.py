@@ -14,8 +14,11 @@ from conftest import ROOT
 HEADER = ROOT / "include" / "cutter_vad_b200.h"
 
 
-def _declared_functions():
-    text = HEADER.read_text()
+DEV_HEADER = ROOT / "include" / "cutter_vad_b200_dev.h"
+
+
+def _declared_functions(header=None):
+    text = (header or HEADER).read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(cvad_[a-z_]+)\s*\(", text)))
 
@@ -29,6 +32,19 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), f"libcvad_b200.so does not export {n}"
     assert set(names) == set(capi.EXPORTS)
     assert L.cvad_abi_version() == 4
+
+
+def test_development_probes_live_in_their_own_library():
+    """The tcgen05 probes (hardware probe, MMA issue rate, bulk-copy rate) are test infrastructure: declared in
+    include/cutter_vad_b200_dev.h, exported by libcvad_b200_dev.so only -- the product library holds none of them."""
+    from real_time_vad.engine import capi
+    names = _declared_functions(DEV_HEADER)
+    assert set(names) == set(capi.DEV_EXPORTS)
+    D = capi.dev_lib()
+    L = capi.lib()
+    for n in names:
+        assert hasattr(D, n), f"libcvad_b200_dev.so does not export {n}"
+        assert not hasattr(L, n), f"libcvad_b200.so still exports the development hook {n}"
 
 
 def test_ctypes_struct_layout_matches_the_header(tmp_path):

@@ -21,14 +21,14 @@ def _bf16_val(b: np.ndarray) -> np.ndarray:
 
 def test_tcgen05_probe_matches_numpy():
     from real_time_vad.engine import capi
-    L = capi.lib()
+    L = capi.dev_lib()
     rng = np.random.default_rng(0)
     A = rng.standard_normal((128, 256)).astype(np.float32)
     B = rng.standard_normal((32, 256)).astype(np.float32)
     a, b = _bf16_bits(A), _bf16_bits(B)
     D = np.zeros((128, 32), np.float32)
     rc = L.cvad_tc_probe(0, a.ctypes.data, b.ctypes.data, D.ctypes.data)
-    assert rc == 0, L.cvad_last_error(None)
+    assert rc == 0, L.cvad_dev_last_error()
     assert D[0, 0] != -12345.0, "tensor-core MMA never completed (descriptor problem)"
     want = _bf16_val(a).astype(np.float64) @ _bf16_val(b).astype(np.float64).T
     err = np.abs(D - want).max()

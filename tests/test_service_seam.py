@@ -84,3 +84,90 @@ def test_sessions_reproduce_the_four_segment_answer_for_many_clients():
         s.cleanup()
     assert not svc.sessions
     svc.close()
+
+
+class _StubManager:
+    """Stands in for BatchedVADManager on a box without a GPU: counts streams and pending samples."""
+    made = 0
+
+    def __init__(self, **kw):
+        type(self).made += 1
+        self.kw, self.streams, self.buffered, self.closed = kw, {}, {}, False
+
+    def open_stream(self, cfg, **cb):
+        sid = len(self.streams)
+        self.streams[sid] = cfg
+        self.buffered[sid] = 0
+        return sid
+
+    def close_stream(self, sid):
+        self.streams.pop(sid, None)
+
+    @property
+    def open_streams(self):
+        return sorted(self.streams)
+
+    def pending(self, sid):
+        return self.buffered[sid]
+
+    def push_bytes(self, sid, data):
+        self.buffered[sid] += len(data) // 2
+
+    def step(self):
+        raise RuntimeError("CUDA error: simulated")
+
+    def close(self):
+        self.closed = True
+
+
+def test_remote_clients_cannot_grow_the_service_without_bound(monkeypatch):
+    """A wire format costs a max_clients-slot engine and a pinned arena, and clients choose the format: at most
+    `max_formats` managers exist at once, a manager is freed when its last stream closes, and a stream that runs more
+    than `max_pending_frames` messages ahead of the tick has its audio dropped (with an ERROR) instead of buffered."""
+    from real_time_vad.service import batched_server as bs
+    monkeypatch.setattr(bs, "BatchedVADManager", _StubManager)
+    svc = bs.BatchedVADService(max_clients=8, max_formats=2, max_pending_frames=3)
+    sent = []
+
+    async def send(text):
+        sent.append(json.loads(text))
+
+    async def main():
+        a = svc.connect(send, bs.create_client_config({"frame_duration_ms": 30}))
+        b = svc.connect(send, bs.create_client_config({"frame_duration_ms": 20}))
+        with pytest.raises(ValueError, match="too many distinct audio formats"):
+            svc.connect(send, bs.create_client_config({"frame_duration_ms": 40}))
+        assert len(svc._managers) == 2
+        mgr_b = b._manager
+        b.cleanup()                                               # last stream of its format: the manager goes away
+        assert len(svc._managers) == 1 and mgr_b.closed
+        c = svc.connect(send, bs.create_client_config({"frame_duration_ms": 40}))   # now there is room again
+        msg = b"\x00" * a.expected_frame_bytes
+        for _ in range(6):
+            await a.process_audio_frame(msg)
+        assert a.frame_count == 3 and a.dropped_frames == 3       # three messages ahead, the rest dropped
+        assert any(e["event"] == "ERROR" and "faster than real time" in e["message"] for e in sent)
+        a.cleanup()
+        c.cleanup()
+    asyncio.run(main())
+    assert not svc._managers
+
+
+def test_a_failing_tick_is_reported_and_the_loop_goes_on(monkeypatch):
+    from real_time_vad.service import batched_server as bs
+    monkeypatch.setattr(bs, "BatchedVADManager", _StubManager)
+    svc = bs.BatchedVADService(max_clients=4, tick_s=0.001)
+    sent = []
+
+    async def send(text):
+        sent.append(json.loads(text))
+
+    async def main():
+        svc.connect(send, bs.create_client_config({}))
+        task = asyncio.create_task(svc.run())
+        await asyncio.sleep(0.05)
+        assert not task.done()                                    # the ticker survived its failing steps
+        task.cancel()
+    asyncio.run(main())
+    assert svc.failed_ticks >= 2 and "simulated" in svc.last_error
+    assert any(e["event"] == "ERROR" and "VAD step failed" in e["message"] for e in sent)

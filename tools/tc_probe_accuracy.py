@@ -1,7 +1,7 @@
 import sys, numpy as np, ctypes as C
 sys.path.insert(0, '/root/repo/cutter-vad_b200')
 from real_time_vad.engine import capi
-L = capi.lib()
+L = capi.dev_lib()
 def bf16_bits(x):
     u = x.astype(np.float32).view(np.uint32); r = ((u >> 16) & 1) + 0x7FFF
     return ((u + r) >> 16).astype(np.uint16)
