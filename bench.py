@@ -488,7 +488,7 @@ def service_tick(n_streams=10000, ticks=120):
     sec = 3
     audio = np.clip(np.round(synth_audio(n, 16000 * sec, seed=1) * 32767.0), -32768, 32767).astype(np.int16)
     pos = np.zeros(n, np.int64)
-    lat_tick, lat_step, lat_push, frames, events = [], [], [], 0, 0
+    lat_tick, lat_step, lat_push, frames, events, phases, host = [], [], [], 0, 0, [], []
     for t in range(ticks + 10):
         k = rng.choice([0, 1, 1, 1, 1, 1, 1, 2], size=n)               # jitter: late / on time / catching up
         t_push = 0.0
@@ -509,6 +509,8 @@ def service_tick(n_streams=10000, ticks=120):
             lat_tick.append(t_push + t2 - t1)
             lat_step.append(t2 - t1)
             lat_push.append(t_push)
+            phases.append(getattr(out, "phase_ms", (0.0, 0.0, 0.0)))
+            host.append(getattr(out, "host_ms", (0.0,) * 5))
             frames += out.frames
             events += len(out.events)
     mgr.close()
@@ -519,6 +521,9 @@ def service_tick(n_streams=10000, ticks=120):
             "tick_ms_p50": 1e3 * float(np.percentile(lat_tick, 50)), "tick_ms_p99": 1e3 * float(np.percentile(lat_tick, 99)),
             "step_ms_p50": 1e3 * float(np.percentile(lat_step, 50)), "step_ms_p99": 1e3 * float(np.percentile(lat_step, 99)),
             "push_ms_p50": 1e3 * float(np.percentile(lat_push, 50)), "push_ms_p99": 1e3 * float(np.percentile(lat_push, 99)),
+            "native_step_ms_p50": dict(zip(("gather", "cvad_step", "deliver"), [float(x) for x in np.percentile(np.array(phases), 50, axis=0)])),
+            "python_step_ms_p50": dict(zip(("native_call", "unpack", "event_tuples", "callbacks_wav", "result"),
+                                           [float(x) for x in np.percentile(np.array(host), 50, axis=0)])),
             "value": frames * 0.030 / total, "unit": "audio-s/s", "frames": frames, "events": events, "callbacks_fired": fired,
             "timed": "the manager's calls only (push_many + step); building the synthetic clients' messages is outside"}
 

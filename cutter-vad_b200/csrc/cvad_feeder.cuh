@@ -13,10 +13,78 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
+
+// A few persistent helper threads for the row copies of push_many and gather (10,000 streams x 30 ms of int16 are
+// ~10 MB per tick on each side: one thread's memcpy rate is what bounded both).  run(parts, body) executes body(0..parts-1)
+// on the helpers AND the calling thread and returns when all parts are done.
+class FeederPool {
+public:
+    explicit FeederPool(int workers) {
+        for (int i = 0; i < workers; ++i) th_.emplace_back([this] { loop(); });
+    }
+    ~FeederPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void run(int parts, const std::function<void(int)> &body) {
+        if (parts <= 1 || th_.empty()) {
+            for (int t = 0; t < parts; ++t) body(t);
+            return;
+        }
+        { std::lock_guard<std::mutex> lk(m_); job_ = &body; total_ = parts; next_ = 0; done_ = 0; ++gen_; }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return done_ == total_; });
+        job_ = nullptr;
+    }
+
+private:
+    void work() {
+        for (;;) {
+            int t;
+            const std::function<void(int)> *job;
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (!job_ || next_ >= total_) return;
+                t = next_++;
+                job = job_;
+            }
+            (*job)(t);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (++done_ == total_) cv_done_.notify_all();
+            }
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || (gen_ != seen && job_ != nullptr); });
+                if (stop_) return;
+                seen = gen_;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, cv_done_;
+    const std::function<void(int)> *job_ = nullptr;
+    int total_ = 0, next_ = 0, done_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
 
 struct cvad_feeder {
     cvad_engine *eng = nullptr;        // may be NULL: gather / deliver test hooks only
@@ -59,6 +127,9 @@ struct cvad_feeder {
     int64_t row = 0;
     int tmax = 0;
     int threads = 1;
+    std::unique_ptr<FeederPool> pool;                // threads - 1 helpers, created with the feeder
+    std::vector<uint32_t> mark;                      // push_many: per-slot stamp (parallel row copies need distinct slots)
+    uint32_t mark_gen = 0;
     // layout of the gathered block: rows ([n][row], frame j of stream k at k*row + j*hop) or, for the frame-by-frame
     // rounds of cvad_feeder_step, planes ([tmax][n][plane_row]: plane r holds everybody's r-th frame, contiguous, so
     // that round 0 is ONE dense host-to-device copy)
@@ -179,14 +250,11 @@ int feeder_gather(cvad_feeder *f, bool allow_planes = false) {
         }
     };
     const size_t bytes = (size_t)n * (size_t)row * f->es;
-    const int nt = (f->threads > 1 && bytes > (4u << 20)) ? std::min(f->threads, n) : 1;
-    if (nt <= 1) {
+    const int nt = (f->threads > 1 && bytes > (1u << 20)) ? std::min(f->threads, n) : 1;
+    if (nt <= 1 || !f->pool) {
         work(0, n);
     } else {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; ++t) th.emplace_back(work, (int)((int64_t)n * t / nt), (int)((int64_t)n * (t + 1) / nt));
-        work(0, n / nt);
-        for (auto &x : th) x.join();
+        f->pool->run(nt, [&](int t) { work((int)((int64_t)n * t / nt), (int)((int64_t)n * (t + 1) / nt)); });
     }
     return CVAD_OK;
 }
@@ -326,6 +394,8 @@ int cvad_feeder_create(cvad_engine *e, int max_streams, int pcm_format, int fram
     f->fill.assign((size_t)max_streams, 0);
     const unsigned hw = std::thread::hardware_concurrency();
     f->threads = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    if (f->threads > 1) f->pool.reset(new FeederPool(f->threads - 1));
+    f->mark.assign((size_t)max_streams, 0u);
     *out = f;
     return CVAD_OK;
 }
@@ -490,8 +560,21 @@ int cvad_feeder_push_many(cvad_feeder *f, int n, const int32_t *slots, const voi
         need = std::max(need, f->fill[slots[i]] + n_samples);
     }
     if (const int rc = feeder_grow_arena(f, need)) return rc;
-    for (int i = 0; i < n; ++i)
-        feeder_push_locked(f, slots[i], b + (size_t)i * (size_t)row_stride * f->es, n_samples);
+    // rows of distinct slots are independent (the arena has room for all of them now): copy them on the pool
+    bool distinct = true;
+    if (++f->mark_gen == 0u) { std::fill(f->mark.begin(), f->mark.end(), 0u); f->mark_gen = 1u; }
+    for (int i = 0; i < n && distinct; ++i) {
+        distinct = f->mark[slots[i]] != f->mark_gen;
+        f->mark[slots[i]] = f->mark_gen;
+    }
+    const size_t bytes = (size_t)n * (size_t)n_samples * f->es;
+    const int nt = (distinct && f->pool && bytes > (1u << 20)) ? std::min(f->threads, n) : 1;
+    auto rows = [&](int i0, int i1) {
+        for (int i = i0; i < i1; ++i)
+            feeder_push_locked(f, slots[i], b + (size_t)i * (size_t)row_stride * f->es, n_samples);
+    };
+    if (nt <= 1) rows(0, n);
+    else f->pool->run(nt, [&](int t) { rows((int)((int64_t)n * t / nt), (int)((int64_t)n * (t + 1) / nt)); });
     return CVAD_OK;
 }
 
@@ -538,7 +621,9 @@ int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *r) {
         std::vector<float> sub_probs;
         std::vector<uint8_t> sub_flags, sub_status;
         std::vector<cvad_event> sub_events;
+        static const bool trace = std::getenv("CVAD_FEEDER_TRACE") != nullptr;     // development aid: per-round timings on stderr
         for (int r = 0; r < T; ++r) {
+            const auto tr0 = clk::now();
             sub_slots.clear(); sub_k.clear();
             for (int k = 0; k < n; ++k)
                 if (f->counts[k] > r) { sub_k.push_back(k); sub_slots.push_back(f->ids[k]); }
@@ -576,7 +661,13 @@ int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *r) {
             a.events_out = sub_events.data();
             a.max_events = (int32_t)sub_events.size();
             a.n_events_out = &nev;
+            const auto tr1 = clk::now();
             rc = cvad_step(f->eng, &a);
+            const auto tr2 = clk::now();
+            if (trace)
+                std::fprintf(stderr, "[feeder] round %d: %d streams, prepare %.3f ms, cvad_step %.3f ms\n", r, nr,
+                             std::chrono::duration<double, std::milli>(tr1 - tr0).count(),
+                             std::chrono::duration<double, std::milli>(tr2 - tr1).count());
             if (rc) { f->events.clear(); return ffail(f, rc, cvad_last_error(f->eng)); }
             for (int i = 0; i < nr; ++i) {
                 if (sub_status[i]) { f->events.clear(); return ffail(f, CVAD_E_INVALID, "Audio data contains infinite or NaN values"); }

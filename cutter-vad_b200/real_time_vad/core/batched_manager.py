@@ -287,11 +287,17 @@ class BatchedVADManager:
                 r = self._feeder.step()
             except FeederError as exc:
                 self._raise(exc)
+            import time
+            t0 = time.perf_counter()
             events = [StreamEvent(slot, "start" if kind == capi.FLAG_STARTED else "end", stream_frame, j)
                       for (k, slot, j, kind, stream_frame) in r.events]
+            t1 = time.perf_counter()
             self._deliver(r.deliveries)
+            t2 = time.perf_counter()
             out = StepOutput(events, r.slots.astype(np.int64), r.counts.astype(np.int64), r.probs, r.flags)
             out.phase_ms = r.phase_ms          # (framing, GPU step incl. copies, segment assembly) inside the native step
+            # where the rest of step() goes: (native call, unpack into numpy, event tuples, callbacks incl. WAV encoding, result object)
+            out.host_ms = (r.call_ms[0], r.call_ms[1], 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (time.perf_counter() - t2))
             return out
 
     def _deliver(self, deliveries) -> None:

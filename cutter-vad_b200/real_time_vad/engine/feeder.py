@@ -37,13 +37,14 @@ class Delivery(NamedTuple):
 class FeederStep:
     """One step's results; arrays are copies, safe to keep."""
 
-    __slots__ = ("slots", "counts", "probs", "flags", "events", "deliveries", "frames", "raw", "raw_stride", "phase_ms")
+    __slots__ = ("slots", "counts", "probs", "flags", "events", "deliveries", "frames", "raw", "raw_stride", "phase_ms", "call_ms")
 
     def __init__(self, slots, counts, probs, flags, events, deliveries, frames, raw=None, raw_stride=0, phase_ms=(0.0, 0.0, 0.0)):
         self.slots, self.counts, self.probs, self.flags = slots, counts, probs, flags
         self.events, self.deliveries, self.frames = events, deliveries, frames
         self.raw, self.raw_stride = raw, raw_stride
         self.phase_ms = phase_ms            # (gather, cvad_step, deliver) wall milliseconds inside the native step
+        self.call_ms = (0.0, 0.0)
 
 
 _EVENT_DT = np.dtype([("stream", "<i4"), ("slot", "<i4"), ("frame", "<i4"), ("kind", "<i4"), ("stream_frame", "<i8")])
@@ -157,8 +158,13 @@ class StreamFeeder:
                           int(r.raw_stride), (float(r.gather_ms), float(r.gpu_ms), float(r.deliver_ms)))
 
     def step(self) -> FeederStep:
+        import time
+        t0 = time.perf_counter()
         self._check(self._L.cvad_feeder_step(self._h, C.byref(self._res)))
-        return self._unpack()
+        t1 = time.perf_counter()
+        out = self._unpack()
+        out.call_ms = (1e3 * (t1 - t0), 1e3 * (time.perf_counter() - t1))     # (native call, unpacking into numpy / tuples)
+        return out
 
     # ------------------------------------------------------------------ host-only test hooks
     def gather_only(self) -> FeederStep:
