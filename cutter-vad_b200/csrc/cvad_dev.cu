@@ -44,15 +44,42 @@ int cvad_tc_probe(int device, const uint16_t *a_bf16, const uint16_t *b_bf16, fl
 }
 
 
-int cvad_tc_rate(int device, int M, int N, int reps, int a_tiles, int n_acc, int grid, long long *out2) {
+// MN-major B operand probe: a_bf16[128][64], b_bf16[96][64] -> d_out[128][160] (columns 0..95: A * B^T, 96..159: A * B[32..95]^T)
+int cvad_tc_probe_mn(int device, const uint16_t *a_bf16, const uint16_t *b_bf16, float *d_out) {
     using namespace cvad::tc;
+    if (!a_bf16 || !b_bf16 || !d_out) return CVAD_E_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return dev_fail(CVAD_E_NOGPU, "cudaSetDevice failed");
+    __nv_bfloat16 *dA = nullptr, *dB = nullptr;
+    float *dD = nullptr;
+    DEV_TRY(cudaMalloc(reinterpret_cast<void **>(&dA), 128 * 64 * 2));
+    DEV_TRY(cudaMalloc(reinterpret_cast<void **>(&dB), 96 * 64 * 2));
+    DEV_TRY(cudaMalloc(reinterpret_cast<void **>(&dD), 128 * 160 * 4));
+    DEV_TRY(cudaMemcpy(dA, a_bf16, 128 * 64 * 2, cudaMemcpyHostToDevice));
+    DEV_TRY(cudaMemcpy(dB, b_bf16, 96 * 64 * 2, cudaMemcpyHostToDevice));
+    DEV_TRY(cudaMemset(dD, 0xFF, 128 * 160 * 4));
+    DEV_TRY(cudaFuncSetAttribute(tc_probe_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kProbeMnSmem));
+    tc_probe_mn_kernel<<<1, 128, kProbeMnSmem>>>(dA, dB, dD);
+    DEV_TRY(cudaGetLastError());
+    DEV_TRY(cudaDeviceSynchronize());
+    DEV_TRY(cudaMemcpy(d_out, dD, 128 * 160 * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    return CVAD_OK;
+}
+
+int cvad_tc_rate(int device, int M, int N, int reps, int a_tiles, int n_acc, int grid, long long *out2) {
+    return cvad_tc_rate2(device, M, N, reps, a_tiles, n_acc, grid, 0, out2);
+}
+
+int cvad_tc_rate2(int device, int M, int N, int reps, int a_tiles, int n_acc, int grid, int b_mn, long long *out2) {
+    using namespace cvad::tc;
+    if (b_mn && N % 32) return CVAD_E_INVALID;
     if (!out2 || a_tiles < 1 || a_tiles > 10 || (M != 64 && M != 128) || N < 8 || N > 256 || grid < 1 || n_acc < 1 || n_acc * N > 512) return CVAD_E_INVALID;
     if (cudaSetDevice(device) != cudaSuccess) return dev_fail(CVAD_E_NOGPU, "cudaSetDevice failed");
     long long *d = nullptr;
     const size_t smem = (size_t)a_tiles * 16384 + 32768 + 1024 + 64;
     DEV_TRY(cudaMalloc(reinterpret_cast<void **>(&d), 16));
     DEV_TRY(cudaFuncSetAttribute(tc_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_rate_kernel<<<grid, 128, smem>>>(M, N, reps, a_tiles, n_acc, d);
+    tc_rate_kernel<<<grid, 128, smem>>>(M, N, reps, a_tiles, n_acc, b_mn, d);
     DEV_TRY(cudaGetLastError());
     DEV_TRY(cudaDeviceSynchronize());
     DEV_TRY(cudaMemcpy(out2, d, 16, cudaMemcpyDeviceToHost));

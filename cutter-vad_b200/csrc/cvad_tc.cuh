@@ -34,6 +34,26 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// MN-major B operand, SWIZZLE_64B (2-byte elements): the contiguous dimension is N.  An atom is 8 K rows of 64 bytes
+// (32 N elements); 16-byte chunk c of K row r sits at chunk position c ^ ((r >> 1) & 3) (atoms 512-byte aligned).  Atoms
+// follow each other along N every `lbo` bytes and along K (groups of 8) every `sbo` bytes; one MMA (K = 16) reads two K
+// groups, so the start address advances by 2 * sbo per K step.  Same canonical form as CUTLASS's
+// make_umma_desc<Major::MN> with LayoutType::B64: ((8,4,n),(8,k)) : ((1,8,LBO),(32,SBO)) elements.
+__host__ __device__ __forceinline__ uint32_t mn64_offset(uint32_t n, uint32_t k, uint32_t lbo, uint32_t sbo) {
+    const uint32_t r = k & 7u, c = (n >> 3) & 3u;
+    return (k >> 3) * sbo + (n >> 5) * lbo + r * 64u + ((c ^ ((r >> 1) & 3u)) << 4) + (n & 7u) * 2u;
+}
+__device__ __forceinline__ uint64_t smem_desc_mn64(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1u << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)4u << 61;                    // SWIZZLE_64B
+    return d;
+}
+constexpr uint32_t kIdescBMajorMN = 1u << 16;   // instruction descriptor: B operand is MN-major
+
 // instruction descriptor, kind::f16: D = F32, A = B = BF16, both K-major, M x N
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);

@@ -139,12 +139,19 @@ __device__ __forceinline__ float sfu_sqrt(float x) {
     return y;
 }
 
-// 16-byte read-once global load that stays where it is written (volatile: issued before the state fetch that follows
-// it in program order, so that both HBM latencies overlap), not allocated in L1
+// 16-byte read-once global load that stays where it is written (volatile: issued right behind the state fetch that
+// precedes it in program order, so that both latencies overlap), not allocated in L1
 __device__ __forceinline__ float4 ldg_stream4(const float4 *p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// 4-byte read-only global load as a volatile asm: keeps its program order relative to ldg_stream4 (state before audio)
+__device__ __forceinline__ float ldg_ordered(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 
@@ -245,6 +252,9 @@ __device__ __forceinline__ long long gtime_ns() {
 #else
 #define CVAD_ISSUE_ROLL
 #endif
+#ifndef CVAD_STATE_FIRST
+#define CVAD_STATE_FIRST 0
+#endif
 #define CVAD_PROF_NS(k) do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(k)] = gtime_ns(); } while (0)
 #define CVAD_PROF(k) do { if (p.prof && blockIdx.x == 0 && first_tile) p.prof[(k)] = clock64(); } while (0)
 
@@ -308,10 +318,78 @@ __device__ __forceinline__ void store_parts2_h(unsigned char *base, uint32_t ps,
     *reinterpret_cast<unsigned short *>(db) = (unsigned short)(w0 >> 16);
     *reinterpret_cast<unsigned short *>(db + ps) = (unsigned short)(w1 >> 16);
 }
-// per-stream maximum of non-negative values held one per lane: warp maximum -> shared atomic
-__device__ __forceinline__ void amax_push(uint32_t *slot, float v, int lane) {
-    const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(v) & 0x7fffffffu);   // (a ReLU may hand over -0.0)
-    if (lane == 0 && m != 0u) atomicMax(slot, m);
+// CVAD_H16_MERGE=1 (experiment): the three products of the FP16 split accumulate in ONE accumulator, corrections first
+#ifndef CVAD_H16_MERGE
+#define CVAD_H16_MERGE 0
+#endif
+constexpr bool kH16Merge = CVAD_H16_MERGE != 0;
+// ---- B operands MN-major SWIZZLE_64B (fused FP16 build, every operand an epilogue writes: MAG, E0, E1, E2, X, H)
+// An epilogue thread owns ONE channel (its TMEM lane = the next layer's k) and EIGHT consecutive streams: with N as the
+// contiguous dimension those are one 16-byte chunk per part and time column -- 2 STS.128 where the K-major layout took
+// 16 two-byte stores with their address arithmetic (the store pass of the STFT epilogue: 2.0 k cycles of a 59 k tile).
+// N atom g (32 streams) = time column or part, 512 B apart; K groups `sbo` apart (tc::mn64_offset).  A quarter warp
+// (8 lanes = one K group, same chunk column) touches 8 distinct 16-byte bank groups: conflict-free.
+__device__ __forceinline__ void store_row8_mn(unsigned char *dst, uint32_t ps, const float (&v)[8]) {
+    uint32_t w0[4], w1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split2x2_h(v[2 * j], v[2 * j + 1], w0[j], w1[j]);
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+    *reinterpret_cast<uint4 *>(dst + ps) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+}
+// MMAs of one weight tile (part wp) for one 64-element K block against an MN-major operand: K step = two K groups
+__device__ __forceinline__ void issue_split_mn(int wp, uint32_t a_addr, uint32_t b0, uint32_t ps, uint32_t sbo, uint32_t d_main,
+                                               uint32_t d_corr, uint32_t idesc, bool first) {
+    const uint64_t ad = tc::smem_desc_sw128(a_addr);
+    const uint64_t bd0 = tc::smem_desc_mn64(b0, 512u, sbo), bd1 = tc::smem_desc_mn64(b0 + ps, 512u, sbo);
+    const uint64_t kst = (uint64_t)((2u * sbo) >> 4);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t fresh = (first && ks == 0) ? 0u : 1u;
+        if (wp == 0) {
+            tc::mma_bf16(kH16Merge ? d_main : d_corr, ad + ks * 2, bd1 + ks * kst, idesc, fresh);
+            tc::mma_bf16(d_main, ad + ks * 2, bd0 + ks * kst, idesc, kH16Merge ? 1u : fresh);
+        } else {
+            tc::mma_bf16(kH16Merge ? d_main : d_corr, ad + ks * 2, bd0 + ks * kst, idesc, 1u);
+        }
+    }
+}
+// W_hh . h: the two parts are N atoms 0 and 1 of the H operand (K groups 1,024 B apart), all products to one accumulator
+__device__ __forceinline__ void issue_gate_mn(int wp, uint32_t a_addr, uint32_t b0, uint32_t d, uint32_t idesc, bool first) {
+    const uint64_t ad = tc::smem_desc_sw128(a_addr);
+    const uint64_t bd0 = tc::smem_desc_mn64(b0, 512u, 1024u), bd1 = tc::smem_desc_mn64(b0 + 512u, 512u, 1024u);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        if (wp == 0) {
+            tc::mma_bf16(d, ad + ks * 2, bd1 + ks * 128, idesc, (first && ks == 0) ? 0u : 1u);
+            tc::mma_bf16(d, ad + ks * 2, bd0 + ks * 128, idesc, 1u);
+        } else {
+            tc::mma_bf16(d, ad + ks * 2, bd0 + ks * 128, idesc, 1u);
+        }
+    }
+}
+// W_ih . x with [x0 | x1] = N atoms 0 and 1 (issue_gate_h_cat's products)
+__device__ __forceinline__ void issue_gate_cat_mn(int wp, uint32_t a_addr, uint32_t b0, uint32_t d, uint32_t idesc64,
+                                                  uint32_t idesc32, bool first) {
+    const uint64_t ad = tc::smem_desc_sw128(a_addr), bd = tc::smem_desc_mn64(b0, 512u, 1024u);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        if (wp == 0) tc::mma_bf16(d, ad + ks * 2, bd + ks * 128, idesc64, (first && ks == 0) ? 0u : 1u);
+        else tc::mma_bf16(d + 32u, ad + ks * 2, bd + ks * 128, idesc32, 1u);
+    }
+}
+
+// N (<= 8) per-stream maxima at once, values one per lane, streams slot[0], slot[stride], ...: the N warp reductions are
+// independent and pipeline, then lanes 0..N-1 issue ONE shared atomic each.  (Eight dependent redux -> branch -> atomic
+// round trips cost an epilogue ~730 cycles per layer; tools/tc_phase_profile.py marks 17 / 18.)
+template <int N>
+__device__ __forceinline__ void amax_push_n(uint32_t *slot, int stride, const float (&v)[N], int lane) {
+    uint32_t m[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) m[e] = __reduce_max_sync(0xffffffffu, __float_as_uint(v[e]) & 0x7fffffffu);   // (a ReLU may hand over -0.0)
+    uint32_t mine = m[0];
+#pragma unroll
+    for (int e = 1; e < N; ++e) mine = lane == e ? m[e] : mine;
+    if (lane < N && mine != 0u) atomicMax(slot + lane * stride, mine);
 }
 // instruction descriptor, kind::f16: D = F32, A = B = FP16
 __host__ __device__ constexpr uint32_t idesc_f16_f32(uint32_t M, uint32_t N) {
@@ -328,11 +406,6 @@ __host__ __device__ __forceinline__ void fe_slot_h(int s, uint32_t &off, uint32_
 constexpr size_t kRecStreamBytesH = (size_t)32 * 16384;       // gate x kb 0..3 x part 0..1
 constexpr int kFusedSlotsPerTileH = 16 + kFeSlotsPerTileH + 16;
 constexpr uint32_t kColIh = 0;                                // TMEM columns of the W_ih . x accumulators (64 per gate; free after encoder.3)
-// CVAD_H16_MERGE=1 (experiment): the three products of the FP16 split accumulate in ONE accumulator, corrections first
-#ifndef CVAD_H16_MERGE
-#define CVAD_H16_MERGE 0
-#endif
-constexpr bool kH16Merge = CVAD_H16_MERGE != 0;
 __device__ __forceinline__ void tmem_ld8_corr(uint32_t taddr, float (&v)[8]) {
     if (kH16Merge) {
 #pragma unroll
@@ -405,6 +478,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     constexpr uint32_t ACT = H16 ? kActBytesH : kActBytes;
     constexpr int RING = (FUSED ? kFusedRing : kFeRing) + (H16 ? 2 : 0);
     constexpr int NP = H16 ? 2 : 3;                   // operand parts
+    // fused FP16 build: every B operand an epilogue writes is MN-major SWIZZLE_64B (store_row8_mn); the frame loader's
+    // AUD operand (a thread holds 8 consecutive samples = k) stays K-major
+    constexpr bool BMN = FUSED && H16;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     unsigned char *act = base;
@@ -539,11 +615,19 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                        i128_32 = H16 ? idesc_f16_f32(128, 32) : tc::idesc_bf16_f32(128, 32),
                        i64_64 = H16 ? idesc_f16_f32(64, 64) : tc::idesc_bf16_f32(64, 64),
                        i64_32 = H16 ? idesc_f16_f32(64, 32) : tc::idesc_bf16_f32(64, 32);
+        constexpr uint32_t MN = BMN ? tc::kIdescBMajorMN : 0u;     // operands written by an epilogue
         // one weight tile of part WP against the activation parts that pair with it (BF16: 3 / 2 / 1 products, FP16: 2 / 1)
 #define CVAD_SPLIT(WP, B0, PS, DM, DC, IDESC, FIRST)                                   \
     do {                                                                               \
         if (H16) issue_split_h(WP, a_addr, B0, PS, DM, DC, IDESC, FIRST);              \
         else issue_split(WP, a_addr, B0, PS, DM, DC, IDESC, FIRST);                    \
+    } while (0)
+        // the same against an operand an epilogue wrote: MN-major in the fused FP16 build (K groups SBO apart; row offsets
+        // of the K-major form are N-atom offsets, 512 B per 32 rows), else K-major at B0
+#define CVAD_SPLIT_E(WP, B0, B0MN, PS, SBO, DM, DC, IDESC, FIRST)                      \
+    do {                                                                               \
+        if (BMN) issue_split_mn(WP, a_addr, B0MN, PS, SBO, DM, DC, (IDESC) | MN, FIRST); \
+        else CVAD_SPLIT(WP, B0, PS, DM, DC, IDESC, FIRST);                             \
     } while (0)
 #define CVAD_GATE(WP, B0, D, IDESC, FIRST)                                             \
     do {                                                                               \
@@ -574,7 +658,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
         CVAD_ISSUE_ROLL                                                                                            \
         for (int kb = 0; kb < 2; ++kb)                                                                             \
             for (int wp = 0; wp < NP; ++wp)                                                                         \
-                CVAD_TC_SLOT(CVAD_GATE(wp, h_s + kb * kXhKb, kColGate + 32 * (G), i128_32, kb == 0 && wp == 0)) \
+            {                                                                                                  \
+                if (BMN) CVAD_TC_SLOT(issue_gate_mn(wp, a_addr, h_s + kb * 8192u, kColGate + 32 * (G), i128_32 | MN, kb == 0 && wp == 0)) \
+                else CVAD_TC_SLOT(CVAD_GATE(wp, h_s + kb * kXhKb, kColGate + 32 * (G), i128_32, kb == 0 && wp == 0)) \
+            }                                                                                                  \
     }
             if (FUSED) {
                 mbar_wait(h_ready, h_phase); h_phase ^= 1u;
@@ -606,10 +693,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 CVAD_ISSUE_ROLL
                 for (int tap = 0; tap < 3; ++tap) {       // centre (N 96), tap 0 (D columns 32..), tap 2 (rows 32..)
                     const uint32_t b0 = act_s + kb * kMagKb + (tap == 2 ? 32u * 128u : 0u), dsh = tap == 1 ? 32u : 0u;
+                    const uint32_t b0mn = act_s + kb * kMagKb + (tap == 2 ? 512u : 0u);
                     const uint32_t idesc = tap == 0 ? i128_96 : i128_64;
                     for (int wp = 0; wp < NP; ++wp)
-                        CVAD_TC_SLOT(CVAD_SPLIT(wp, b0, kMagPart, kColMain + dsh, kColCorr + dsh, idesc,
-                                                 kb == 0 && tap == 0 && wp == 0))
+                        CVAD_TC_SLOT(CVAD_SPLIT_E(wp, b0, b0mn, kMagPart, 1536u, kColMain + dsh, kColCorr + dsh, idesc,
+                                                   kb == 0 && tap == 0 && wp == 0))
                 }
             }
             if (tc::elect_one()) tc::mma_commit(acc_ready);
@@ -626,10 +714,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 CVAD_ISSUE_ROLL
                 for (int tap = 0; tap < 3; ++tap) {       // tap 1 (rows 0..63, N 64), tap 2 (rows 64.., out 0), tap 0 (rows 64.., out 1)
                     const uint32_t b0 = act_s + kb * kMagKb + (tap == 0 ? 0u : 64u * 128u), dsh = tap == 2 ? 32u : 0u;
+                    const uint32_t b0mn = act_s + kb * kMagKb + (tap == 0 ? 0u : 1024u);
                     const uint32_t idesc = tap == 0 ? i64_64 : i64_32;
                     for (int wp = 0; wp < NP; ++wp)
-                        CVAD_TC_SLOT(CVAD_SPLIT(wp, b0, kMagPart, kColMain + dsh, kColCorr + dsh, idesc,
-                                                 kb == 0 && tap == 0 && wp == 0))
+                        CVAD_TC_SLOT(CVAD_SPLIT_E(wp, b0, b0mn, kMagPart, 1536u, kColMain + dsh, kColCorr + dsh, idesc,
+                                                   kb == 0 && tap == 0 && wp == 0))
                 }
             }
             if (tc::elect_one()) tc::mma_commit(acc_ready);
@@ -641,9 +730,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             CVAD_PROF(38);
             tc::fence_after_sync();
             for (int wp = 0; wp < NP; ++wp)
-                CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s, kE1Part, kColMain, kColCorr, i64_32, wp == 0))
+                CVAD_TC_SLOT(CVAD_SPLIT_E(wp, act_s, act_s, kE1Part, 1024u, kColMain, kColCorr, i64_32, wp == 0))
             for (int wp = 0; wp < NP; ++wp)
-                CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s + 32 * 128, kE1Part, kColMain, kColCorr, i64_32, false))
+                CVAD_TC_SLOT(CVAD_SPLIT_E(wp, act_s + 32 * 128, act_s + 512u, kE1Part, 1024u, kColMain, kColCorr, i64_32, false))
             if (tc::elect_one()) tc::mma_commit(acc_ready);
             CVAD_PROF(39);
             __syncwarp();
@@ -652,7 +741,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             CVAD_PROF(40);
             tc::fence_after_sync();
             for (int wp = 0; wp < NP; ++wp)
-                CVAD_TC_SLOT(CVAD_SPLIT(wp, act_s, kE2Part, kColMain, kColCorr, i128_32, wp == 0))
+                CVAD_TC_SLOT(CVAD_SPLIT_E(wp, act_s, act_s, kE2Part, 512u, kColMain, kColCorr, i128_32, wp == 0))
             if (tc::elect_one()) tc::mma_commit(acc_ready);
             CVAD_PROF(41);
             __syncwarp();
@@ -667,7 +756,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     for (int kb = 0; kb < 2; ++kb)
                         for (int wp = 0; wp < NP; ++wp)
                         {
-                            if (H16) CVAD_TC_SLOT(issue_gate_h_cat(wp, a_addr, act_s + kb * kXhKb, kColIh + 64 * gate, i128_64, i128_32,
+                            if (BMN) CVAD_TC_SLOT(issue_gate_cat_mn(wp, a_addr, act_s + kb * 8192u, kColIh + 64 * gate, i128_64 | MN, i128_32 | MN,
+                                                                    kb == 0 && wp == 0))
+                            else if (H16) CVAD_TC_SLOT(issue_gate_h_cat(wp, a_addr, act_s + kb * kXhKb, kColIh + 64 * gate, i128_64, i128_32,
                                                                    kb == 0 && wp == 0))
                             else CVAD_TC_SLOT(CVAD_GATE(wp, act_s + kb * kXhKb, kColGate + 32 * gate, i128_32, false))
                         }
@@ -678,6 +769,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
 #undef CVAD_TC_HH
 #undef CVAD_TC_SLOT
 #undef CVAD_SPLIT
+#undef CVAD_SPLIT_E
 #undef CVAD_GATE
         }
     } else {
@@ -724,7 +816,21 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             // ---- frame loader (audio.py:164-190 split, :104-121 gate, silero_model.py:449-474 pad/truncate):
             //      8 samples per work unit -> 3 x 16-byte BF16 chunks of the AUD operand, row = segment*32 + item.
             //      All global loads of the thread's 4 units are issued before the first use -- and, in the fused
-            //      kernel, before the resident state is fetched, so that both HBM latencies overlap.
+            //      kernel, before the resident state is fetched, so that both latencies overlap.
+            float creg[8], hreg[8];
+            const int u_own = 32 * q + lane, i_own = 8 * cg;   // this thread's hidden unit (TMEM lane) and 8 streams
+#if CVAD_STATE_FIRST
+            // experiment: the resident state requested ahead of the audio (measured: the tile gets 1.4 k cycles LONGER)
+            if (FUSED) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int idx = e * kEpiThreads + tid;
+                    const int slot = s_valid[idx & 31] ? s_slot[idx & 31] : -1;
+                    hreg[e] = slot >= 0 ? ldg_ordered(p.h_state + (size_t)(idx >> 5) * p.max_streams + slot) : 0.f;
+                    creg[e] = slot >= 0 ? ldg_ordered(p.c_state + (size_t)(idx >> 5) * p.max_streams + slot) : 0.f;
+                }
+            }
+#endif
                 const bool fast = p.vec_ok && flen == 512;
                 float v[4][8];
                 bool ok[4];
@@ -758,11 +864,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 }
             // FUSED: resident state of the tile's streams: h -> BF16x3 rows of the H operand, c -> registers
             // (global reads coalesced over streams, transposed through the still-unused ACT region)
-            float creg[8];
-            const int u_own = 32 * q + lane, i_own = 8 * cg;   // this thread's hidden unit (TMEM lane) and 8 streams
             if (FUSED) {
                 float *sbuf = reinterpret_cast<float *>(act);   // [128][33]
-                float hreg[8];
+#if !CVAD_STATE_FIRST
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int idx = e * kEpiThreads + tid;
@@ -770,6 +874,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     hreg[e] = slot >= 0 ? __ldg(p.h_state + (size_t)(idx >> 5) * p.max_streams + slot) : 0.f;
                     creg[e] = slot >= 0 ? __ldg(p.c_state + (size_t)(idx >> 5) * p.max_streams + slot) : 0.f;
                 }
+#endif
                 if (warp == 0) {
                     // the slot data fetched at tile start (by now every global load of this warp is in flight)
                     s_dn[lane] = dn;
@@ -793,10 +898,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     hreg[e] = sbuf[u_own * 33 + i_own + e];
                     creg[e] = sbuf_c[u_own * 33 + i_own + e];
                 }
+                if constexpr (BMN) {
 #pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    if (H16) store_parts2_h(hbuf, 32 * 128, (uint32_t)(i_own + e), (uint32_t)u_own, 96u, hreg[e] * kHScale, hreg[e + 1] * kHScale);
-                    else store_parts2(hbuf, 32 * 128, (uint32_t)(i_own + e), (uint32_t)u_own, 96u, hreg[e], hreg[e + 1]);
+                    for (int e = 0; e < 8; ++e) hreg[e] *= kHScale;
+                    store_row8_mn(hbuf + tc::mn64_offset((uint32_t)i_own, (uint32_t)u_own, 512u, 1024u), 512u, hreg);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        if (H16) store_parts2_h(hbuf, 32 * 128, (uint32_t)(i_own + e), (uint32_t)u_own, 96u, hreg[e] * kHScale, hreg[e + 1] * kHScale);
+                        else store_parts2(hbuf, 32 * 128, (uint32_t)(i_own + e), (uint32_t)u_own, 96u, hreg[e], hreg[e + 1]);
+                    }
                 }
                 tc::fence_async_smem();
                 epi_bar();                                     // also: sbuf reads done before the loader rewrites ACT
@@ -844,13 +955,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 if (H16) {
                     CVAD_PROF(20);
                     // per-stream maximum of the gated frame (a unit's stream is warp-uniform: s = 8 u4 + tid / 64) ...
+                    float m4[4];
 #pragma unroll
                     for (int u4 = 0; u4 < 4; ++u4) {
                         float m = 0.f;
 #pragma unroll
                         for (int e = 0; e < 8; ++e) m = fmaxf(m, fabsf(v[u4][e]));
-                        amax_push(&amax[u4 * 8 + (tid >> 6)], m, lane);
+                        m4[u4] = m;
                     }
+                    amax_push_n<4>(&amax[tid >> 6], 8, m4, lane);
                     CVAD_PROF(15);
                     epi_bar();
                     CVAD_PROF(16);
@@ -908,20 +1021,28 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                         mx[e] = fmaxf(mx[e], mag[t][e]);
                     }
                 }
-#pragma unroll
                 CVAD_PROF(17);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) amax_push(&amax[kTile + i0 + e], mx[e], lane);
+                amax_push_n<8>(&amax[kTile + i0], 1, mx, lane);
                 CVAD_PROF(18);
                 epi_bar();
                 CVAD_PROF(19);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) inv[e] = scale_from_max(amax[kTile + i0 + e]).s;
+                if constexpr (BMN) {
+                    unsigned char *dst = act + tc::mn64_offset((uint32_t)i0, (uint32_t)b, 512u, 1536u);
 #pragma unroll
-                for (int t = 0; t < 3; ++t)
+                    for (int t = 0; t < 3; ++t) {
 #pragma unroll
-                    for (int e = 0; e < 8; e += 2)
-                        store_parts2_h(act, kMagPart, (uint32_t)(t * 32 + i0 + e), (uint32_t)b, 96u, mag[t][e] * inv[e], mag[t][e + 1] * inv[e + 1]);
+                        for (int e = 0; e < 8; ++e) mag[t][e] *= inv[e];
+                        store_row8_mn(dst + t * 512, kMagPart, mag[t]);
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 3; ++t)
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2)
+                            store_parts2_h(act, kMagPart, (uint32_t)(t * 32 + i0 + e), (uint32_t)b, 96u, mag[t][e] * inv[e], mag[t][e + 1] * inv[e + 1]);
+                }
             } else {
                 const int b = 32 * q + lane;   // bin; TMEM lane b of block 1 holds im[b] (b >= 1) or re[128] (b == 0)
 #pragma unroll 1
@@ -986,17 +1107,26 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                         mx[e] = fmaxf(mx[e], v[t][e]);
                     }
                 }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) amax_push(&amax[2 * kTile + i0 + e], mx[e], lane);
+                amax_push_n<8>(&amax[2 * kTile + i0], 1, mx, lane);
                 epi_bar();
 #pragma unroll
                 for (int e = 0; e < 8; ++e) sc[e] = scale_from_max(amax[2 * kTile + i0 + e]).s;
+                if constexpr (BMN) {
+                    unsigned char *dst = act + tc::mn64_offset((uint32_t)i0, (uint32_t)o, 512u, 1536u);
 #pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                    const uint32_t rb = t == 0 ? 0u : (t == 1 ? 64u : 32u);
+                    for (int t = 0; t < 3; ++t) {
 #pragma unroll
-                    for (int e = 0; e < 8; e += 2)
-                        store_parts2_h(act, kMagPart, rb + (uint32_t)(i0 + e), (uint32_t)o, 96u, v[t][e] * sc[e], v[t][e + 1] * sc[e + 1]);
+                        for (int e = 0; e < 8; ++e) v[t][e] *= sc[e];
+                        store_row8_mn(dst + (t == 0 ? 0 : (t == 1 ? 1024 : 512)), kMagPart, v[t]);   // N atoms in time order 0, 2, 1
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const uint32_t rb = t == 0 ? 0u : (t == 1 ? 64u : 32u);
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2)
+                            store_parts2_h(act, kMagPart, rb + (uint32_t)(i0 + e), (uint32_t)o, 96u, v[t][e] * sc[e], v[t][e + 1] * sc[e + 1]);
+                    }
                 }
             } else {
                 const int o = 32 * q + lane;
@@ -1055,17 +1185,26 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                         mx[e] = fmaxf(mx[e], v[t][e]);
                     }
                 }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) amax_push(&amax[3 * kTile + i0 + e], mx[e], lane);
+                amax_push_n<8>(&amax[3 * kTile + i0], 1, mx, lane);
                 epi_bar();
                 if (lane < 16) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) sc[e] = scale_from_max(amax[3 * kTile + i0 + e]).s;
+                    if constexpr (BMN) {
+                        unsigned char *dst = act + tc::mn64_offset((uint32_t)i0, (uint32_t)o, 512u, 1024u);
 #pragma unroll
-                    for (int t = 0; t < 2; ++t)
+                        for (int t = 0; t < 2; ++t) {
 #pragma unroll
-                        for (int e = 0; e < 8; e += 2)
-                            store_parts2_h(act, kE1Part, (uint32_t)(t * 32 + i0 + e), (uint32_t)o, 64u, v[t][e] * sc[e], v[t][e + 1] * sc[e + 1]);
+                            for (int e = 0; e < 8; ++e) v[t][e] *= sc[e];
+                            store_row8_mn(dst + t * 512, kE1Part, v[t]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 2; ++t)
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2)
+                                store_parts2_h(act, kE1Part, (uint32_t)(t * 32 + i0 + e), (uint32_t)o, 64u, v[t][e] * sc[e], v[t][e + 1] * sc[e + 1]);
+                    }
                 }
             } else {
                 const int o = 16 * q + (lane & 15);
@@ -1110,14 +1249,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 for (int e = 0; e < 8; ++e) {
                     const float a = fmaxf((m[e] + cr[e]) * (scale_from_max(amax[3 * kTile + c0 + e]).inv * iw) + bias, 0.f);
                     v[e] = lane < 16 ? a : 0.f;
-                    amax_push(&amax[4 * kTile + c0 + e], v[e], lane);
                 }
+                amax_push_n<8>(&amax[4 * kTile + c0], 1, v, lane);
                 epi_bar();
                 if (lane < 16) {
+                    if constexpr (BMN) {
 #pragma unroll
-                    for (int e = 0; e < 8; e += 2)
-                        store_parts2_h(act, kE2Part, (uint32_t)(c0 + e), (uint32_t)o, 32u, v[e] * scale_from_max(amax[4 * kTile + c0 + e]).s,
-                                       v[e + 1] * scale_from_max(amax[4 * kTile + c0 + e + 1]).s);
+                        for (int e = 0; e < 8; ++e) v[e] *= scale_from_max(amax[4 * kTile + c0 + e]).s;
+                        store_row8_mn(act + tc::mn64_offset((uint32_t)c0, (uint32_t)o, 512u, 512u), kE2Part, v);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2)
+                            store_parts2_h(act, kE2Part, (uint32_t)(c0 + e), (uint32_t)o, 32u, v[e] * scale_from_max(amax[4 * kTile + c0 + e]).s,
+                                           v[e + 1] * scale_from_max(amax[4 * kTile + c0 + e + 1]).s);
+                    }
                 }
             } else {
                 const int o = 16 * q + (lane & 15);
@@ -1158,15 +1303,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     v[e] = fmaxf((m[e] + cr[e]) * (scale_from_max(amax[4 * kTile + c0 + e]).inv * iw) + bias, 0.f);
-                    amax_push(&amax[5 * kTile + c0 + e], v[e], lane);
                 }
+                amax_push_n<8>(&amax[5 * kTile + c0], 1, v, lane);
                 tc::fence_before_sync();   // the W_ih accumulators reuse these TMEM columns
                 epi_bar();
-                if (FUSED) {
+                if constexpr (FUSED) {
+                    // [x0 | x1] = N atoms 0 and 1, K groups 1,024 B apart
 #pragma unroll
-                    for (int e = 0; e < 8; e += 2)
-                        store_parts2_h(act, 32 * 128, (uint32_t)(c0 + e), (uint32_t)o, 96u, v[e] * scale_from_max(amax[5 * kTile + c0 + e]).s,
-                                       v[e + 1] * scale_from_max(amax[5 * kTile + c0 + e + 1]).s);
+                    for (int e = 0; e < 8; ++e) v[e] *= scale_from_max(amax[5 * kTile + c0 + e]).s;
+                    store_row8_mn(act + tc::mn64_offset((uint32_t)c0, (uint32_t)o, 512u, 1024u), 512u, v);
                 } else {
                     // two-kernel form: x goes to HBM as the recurrent kernel's operand, scaled like the h it will sit
                     // next to in K: by the stream's joint maximum max(|x|max, 1) (|h| < 1), handed over in the tile
@@ -1244,6 +1389,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                         for (int gi = 0; gi < 4; ++gi) gate[gi][e] = fmaf(gx[gi][e], ix, gate[gi][e] * hh);
                     }
                 }
+                CVAD_PROF(21);
                 float dv[8], hn[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -1256,6 +1402,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     creg[e] = cn;
                     dv[e] = wd * fmaxf(hn[e], 0.f);
                 }
+                CVAD_PROF(22);
 #pragma unroll
                 for (int w = 4; w >= 1; w >>= 1) {
                     const bool upper = (lane & w) != 0;
@@ -1278,6 +1425,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 }
                 tc::fence_before_sync();
                 epi_bar();
+                CVAD_PROF(23);
                 if (p.commit) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -1290,6 +1438,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                         }
                     }
                 }
+                CVAD_PROF(24);
                 // sigmoid(w . relu(h') + b), then the start/end state machine (silero_model.py:790-923)
                 if (warp == 0 && s_valid[lane]) {
                     const int slot = s_slot[lane];

@@ -33,6 +33,9 @@ if out[12]:
 if out[15]:
     print("tc16 marks: loader gated", out[20] - out[0], "amax pushed", out[15] - out[0], "barrier", out[16] - out[0],
           "| stft computed", out[17] - out[0], "amax pushed", out[18] - out[0], "barrier", out[19] - out[0])
+if out[21]:
+    print("fused cell marks: gates in registers", out[21] - out[0], "cell computed", out[22] - out[0], "state transposed + barrier", out[23] - out[0],
+          "state stored", out[24] - out[0], "cell done", out[14] - out[0])
 r0 = out[64]
 print("recurrent epilogue: start 0, state loaded", out[65] - r0)
 for j in range(min(T, 8)):
