@@ -81,6 +81,9 @@ struct cvad_engine {
     // programmatic stream serialization and NOTHING between the kernels -- no memset (the kernel clears its status words
     // and counts events in `d_evctr`), no event record (`last_done` is recorded lazily, when another stream needs it)
     int *d_evctr = nullptr;            // {event count of the step in flight, CTA ticket}; zero between steps
+    // chained steps: [2] = chained steps completed (the last CTA of each counts), [3] = its CTA ticket; chain_seq = chained
+    // steps launched.  A CTA that finds [2] behind its own sequence number was scheduled while the previous step still runs
+    int chain_seq = 0;
     bool chain_pending = false;        // the tail of `chain_stream` is a chained kernel without a `last_done` record
     cudaStream_t chain_stream = nullptr;
     float *rs_rt[3] = {nullptr, nullptr, nullptr};  // R^T for 8 / 24 / 48 kHz, built on first use
@@ -883,6 +886,11 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
             // barriers and TMEM and prefetch weight tiles, then block in griddepcontrol.wait); not when timing events
             // sit between the kernels
             const bool overlap = chain && !timed;
+            if (overlap && p.audio == a->audio) {        // (not when a kernel of this step produced the 16 kHz frames)
+                // the CTAs that are scheduled early prefetch the step's audio into L2 while they wait (v5tc_frontend_kernel)
+                p.step_ctr = e->d_evctr + 2;
+                p.step_seq = e->chain_seq++;
+            }
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)grid);
             cfg.blockDim = dim3((unsigned)cvad::tc5::kThreadsTC);
@@ -1004,6 +1012,22 @@ __global__ void fill_slots_kernel(T *dst, const int *slots, int n, int all_n, T 
     const int r = idx / count, k = idx - r * count;
     const int slot = slots ? slots[k] : k;
     dst[(size_t)r * ld + slot] = value;
+}
+
+// the same for the LSTM state (128 rows per slot, laid out by cvad::state_at)
+__global__ void fill_state_kernel(float *dst, const int *slots, int n, int all_n, float value) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int count = slots ? n : all_n;
+    if (idx >= count * 128) return;
+    const int r = idx / count, k = idx - r * count;
+    dst[cvad::state_at(r, slots ? slots[k] : k)] = value;
+}
+int fill_state(cvad_engine *e, float *dst, const int *d_slots, int n, float value) {
+    const int count = d_slots ? n : e->max_streams;
+    if (count == 0) return CVAD_OK;
+    fill_state_kernel<<<(count * 128 + 255) / 256, 256, 0, e->stream>>>(dst, d_slots, n, e->max_streams, value);
+    CU_TRY(e, cudaGetLastError());
+    return CVAD_OK;
 }
 
 template <typename T>
@@ -1417,8 +1441,9 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
     {
         const size_t ms = (size_t)max_streams;
         int rc;
-        if ((rc = alloc_fill<float>(e, &e->h_state, 128 * ms, 0.f)) ||
-            (rc = alloc_fill<float>(e, &e->c_state, 128 * ms, 0.f)) ||
+        const size_t ms8 = ((size_t)ms + 7) / 8 * 8;       // state rows are grouped by 8 slots (cvad::state_at)
+        if ((rc = alloc_fill<float>(e, &e->h_state, 128 * ms8, 0.f)) ||
+            (rc = alloc_fill<float>(e, &e->c_state, 128 * ms8, 0.f)) ||
             (rc = alloc_fill<int>(e, &e->sm_active, ms, 0)) || (rc = alloc_fill<int>(e, &e->sm_scount, ms, 0)) ||
             (rc = alloc_fill<int>(e, &e->sm_ecount, ms, 0)) ||
             (rc = alloc_fill<long long>(e, &e->frames_done, ms, 0)) ||
@@ -1428,8 +1453,8 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
             return bail(rc);
     }
     CR_TRY(cudaEventCreateWithFlags(&e->last_done, cudaEventDisableTiming));
-    CR_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_evctr), 2 * sizeof(int)));
-    CR_TRY(cudaMemset(e->d_evctr, 0, 2 * sizeof(int)));
+    CR_TRY(cudaMalloc(reinterpret_cast<void **>(&e->d_evctr), 4 * sizeof(int)));
+    CR_TRY(cudaMemset(e->d_evctr, 0, 4 * sizeof(int)));
     for (auto &ln : e->lanes) {
         CR_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
         CR_TRY(cudaMalloc(reinterpret_cast<void **>(&ln.d_nevents), sizeof(int)));
@@ -1540,8 +1565,7 @@ int cvad_reset(cvad_engine *e, int n, const int32_t *slots) {
     int rc = quiesce(e);
     if (rc) return rc;
     if ((rc = stage_slots(e, n, slots, &ds))) return rc;
-    if ((rc = fill_slots<float>(e, e->h_state, ds, n, 0.f, 128)) ||
-        (rc = fill_slots<float>(e, e->c_state, ds, n, 0.f, 128)) ||
+    if ((rc = fill_state(e, e->h_state, ds, n, 0.f)) || (rc = fill_state(e, e->c_state, ds, n, 0.f)) ||
         (rc = fill_slots<int>(e, e->sm_active, ds, n, 0, 1)) || (rc = fill_slots<int>(e, e->sm_scount, ds, n, 0, 1)) ||
         (rc = fill_slots<int>(e, e->sm_ecount, ds, n, 0, 1)) ||
         (rc = fill_slots<long long>(e, e->frames_done, ds, n, 0ll, 1)))
@@ -1580,9 +1604,9 @@ int cvad_get_state(cvad_engine *e, int slot, float *h, float *c, int32_t *sm, in
     if (slot < 0 || slot >= e->max_streams) return fail(e, CVAD_E_CAPACITY, "slot id out of range");
     CU_TRY(e, cudaSetDevice(e->device));
     { int rcq = quiesce(e); if (rcq) return rcq; }
-    const size_t pitch = (size_t)e->max_streams * sizeof(float);
-    if (h) CU_TRY(e, cudaMemcpy2D(h, sizeof(float), e->h_state + slot, pitch, sizeof(float), 128, cudaMemcpyDeviceToHost));
-    if (c) CU_TRY(e, cudaMemcpy2D(c, sizeof(float), e->c_state + slot, pitch, sizeof(float), 128, cudaMemcpyDeviceToHost));
+    const size_t pitch = 8 * sizeof(float), at = cvad::state_at(0, slot);     // rows of one slot are 8 floats apart
+    if (h) CU_TRY(e, cudaMemcpy2D(h, sizeof(float), e->h_state + at, pitch, sizeof(float), 128, cudaMemcpyDeviceToHost));
+    if (c) CU_TRY(e, cudaMemcpy2D(c, sizeof(float), e->c_state + at, pitch, sizeof(float), 128, cudaMemcpyDeviceToHost));
     if (sm) {
         CU_TRY(e, cudaMemcpy(&sm[0], e->sm_active + slot, sizeof(int), cudaMemcpyDeviceToHost));
         CU_TRY(e, cudaMemcpy(&sm[1], e->sm_scount + slot, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1602,9 +1626,9 @@ int cvad_set_state(cvad_engine *e, int slot, const float *h, const float *c, con
     if (slot < 0 || slot >= e->max_streams) return fail(e, CVAD_E_CAPACITY, "slot id out of range");
     CU_TRY(e, cudaSetDevice(e->device));
     { int rcq = quiesce(e); if (rcq) return rcq; }
-    const size_t pitch = (size_t)e->max_streams * sizeof(float);
-    if (h) CU_TRY(e, cudaMemcpy2D(e->h_state + slot, pitch, h, sizeof(float), sizeof(float), 128, cudaMemcpyHostToDevice));
-    if (c) CU_TRY(e, cudaMemcpy2D(e->c_state + slot, pitch, c, sizeof(float), sizeof(float), 128, cudaMemcpyHostToDevice));
+    const size_t pitch = 8 * sizeof(float), at = cvad::state_at(0, slot);
+    if (h) CU_TRY(e, cudaMemcpy2D(e->h_state + at, pitch, h, sizeof(float), sizeof(float), 128, cudaMemcpyHostToDevice));
+    if (c) CU_TRY(e, cudaMemcpy2D(e->c_state + at, pitch, c, sizeof(float), sizeof(float), 128, cudaMemcpyHostToDevice));
     if (sm) {
         CU_TRY(e, cudaMemcpy(e->sm_active + slot, &sm[0], sizeof(int), cudaMemcpyHostToDevice));
         CU_TRY(e, cudaMemcpy(e->sm_scount + slot, &sm[1], sizeof(int), cudaMemcpyHostToDevice));

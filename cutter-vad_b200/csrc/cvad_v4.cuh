@@ -509,7 +509,6 @@ __global__ void __launch_bounds__(kThreads, 1) v4_recurrent_kernel(const V5Step 
     const int tm = tid & 7;   // items 4tm..4tm+3
     const int tn = tid >> 3;  // hidden unit 0..63 (packed columns 4tn..4tn+3 = i,o,f,c)
     const int st = blockIdx.x;
-    const int ms = p.max_streams;
 
     if (tid < kTile) {
         const int i = st * kTile + tid;
@@ -556,14 +555,14 @@ __global__ void __launch_bounds__(kThreads, 1) v4_recurrent_kernel(const V5Step 
     for (int idx = tid; idx < 4096; idx += kThreads) {
         const int s = idx & 31, u = idx >> 5;  // u = layer*64 + unit
         const int slot = s_slot[s];
-        hbuf[idx] = slot >= 0 ? p.h_state[(size_t)u * ms + slot] : 0.f;
+        hbuf[idx] = slot >= 0 ? p.h_state[state_at(u, slot)] : 0.f;
     }
     float creg[2][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int slot = s_slot[4 * tm + i];
 #pragma unroll
-        for (int l = 0; l < 2; ++l) creg[l][i] = slot >= 0 ? p.c_state[(size_t)(l * 64 + tn) * ms + slot] : 0.f;
+        for (int l = 0; l < 2; ++l) creg[l][i] = slot >= 0 ? p.c_state[state_at(l * 64 + tn, slot)] : 0.f;
     }
     int sm_active = 0, sm_sc = 0, sm_ec = 0, sm_ns = 1, sm_ne = 1;
     long long sm_f0 = 0;
@@ -673,14 +672,14 @@ __global__ void __launch_bounds__(kThreads, 1) v4_recurrent_kernel(const V5Step 
         for (int idx = tid; idx < 4096; idx += kThreads) {
             const int s = idx & 31, u = idx >> 5;
             const int slot = s_slot[s];
-            if (slot >= 0 && s_nfr[s] > 0) p.h_state[(size_t)u * ms + slot] = hbuf[idx];
+            if (slot >= 0 && s_nfr[s] > 0) p.h_state[state_at(u, slot)] = hbuf[idx];
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int slot = s_slot[4 * tm + i];
             if (slot >= 0 && s_nfr[4 * tm + i] > 0) {
 #pragma unroll
-                for (int l = 0; l < 2; ++l) p.c_state[(size_t)(l * 64 + tn) * ms + slot] = creg[l][i];
+                for (int l = 0; l < 2; ++l) p.c_state[state_at(l * 64 + tn, slot)] = creg[l][i];
             }
         }
         if (warp == 0 && s_slot[lane] >= 0 && s_nfr[lane] > 0) {

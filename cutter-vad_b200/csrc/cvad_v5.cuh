@@ -61,6 +61,15 @@ __device__ __forceinline__ void rec_ring_issue(const WeightRing &r, uint32_t g) 
 }
 
 // ---------------------------------------------------------------- step parameters
+// Resident LSTM state (h and c, 128 rows each: v5 = 128 hidden units, v4 = 2 layers x 64): [slot / 8][row][slot % 8] floats.
+// A reader that walks 32 consecutive slots of one row touches four 32-byte sectors (as with a [row][slot] matrix), and the
+// 8 streams an epilogue thread of the fused tensor-core kernel owns are ONE 32-byte row when their slots are consecutive
+// and start at a multiple of 8 -- its 32 lanes (rows) then read 1 KB contiguous, straight into the registers that need
+// them (no transposition through shared memory on the way in or out).  Capacity is rounded up to a multiple of 8 slots.
+__host__ __device__ __forceinline__ size_t state_at(int row, int slot) {
+    return ((size_t)(slot >> 3) * 128u + (size_t)row) * 8u + (size_t)(slot & 7);
+}
+
 struct V5Step {
     const void *audio;            // device
     int pcm;                      // CVAD_PCM_*
@@ -84,7 +93,7 @@ struct V5Step {
     const float *w_rec;
     const float *b_rec;           // [512] packed n' order, b_ih + b_hh
     const float *w_dec;           // [128] + bias at [128]
-    // per-slot persistent state (transposed: [unit][max_streams])
+    // per-slot persistent state: [slot / 8][unit (128)][slot % 8] (state_at below)
     float *h_state;
     float *c_state;
     int *sm_active;
@@ -102,6 +111,8 @@ struct V5Step {
     int max_events;
     int *n_events;                // device counter or null
     int *ev_ctr;                  // chained fused steps: engine-owned {event count, CTA ticket}, both zero between steps; or null
+    int *step_ctr;                // chained fused steps: engine-owned {chained steps completed, CTA ticket}; or null
+    int step_seq;                 // chained fused steps: how many chained steps were launched before this one
     int status_zero;              // chained fused steps: the kernel clears `status` itself (no memset ahead of it)
     int commit;                   // 0: do not write state back (debug)
     float *dbg;                   // front-end debug dump for tile 0, or null
@@ -519,7 +530,6 @@ __global__ void __launch_bounds__(kThreads, 1) v5_recurrent_kernel(const V5Step 
     const int tm = tid & 7;   // items 4tm..4tm+3
     const int tn = tid >> 3;  // 0..63: hidden units 2tn, 2tn+1 (packed columns 8tn..8tn+7)
     const int st = blockIdx.x;
-    const int ms = p.max_streams;
 
     if (tid < kTile) {
         const int i = st * kTile + tid;
@@ -564,14 +574,14 @@ __global__ void __launch_bounds__(kThreads, 1) v5_recurrent_kernel(const V5Step 
     for (int idx = tid; idx < 4096; idx += kThreads) {
         const int s = idx & 31, u = idx >> 5;
         const int slot = s_slot[s];
-        hbuf[idx] = slot >= 0 ? p.h_state[(size_t)u * ms + slot] : 0.f;
+        hbuf[idx] = slot >= 0 ? p.h_state[state_at(u, slot)] : 0.f;
     }
     float creg[4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int slot = s_slot[4 * tm + i];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) creg[i][u] = slot >= 0 ? p.c_state[(size_t)(2 * tn + u) * ms + slot] : 0.f;
+        for (int u = 0; u < 2; ++u) creg[i][u] = slot >= 0 ? p.c_state[state_at(2 * tn + u, slot)] : 0.f;
     }
     // state machine words (warp 0, one lane per stream)
     int sm_active = 0, sm_sc = 0, sm_ec = 0, sm_ns = 1, sm_ne = 1;
@@ -697,14 +707,14 @@ __global__ void __launch_bounds__(kThreads, 1) v5_recurrent_kernel(const V5Step 
         for (int idx = tid; idx < 4096; idx += kThreads) {
             const int s = idx & 31, u = idx >> 5;
             const int slot = s_slot[s];
-            if (slot >= 0 && s_nfr[s] > 0) p.h_state[(size_t)u * ms + slot] = hbuf[idx];
+            if (slot >= 0 && s_nfr[s] > 0) p.h_state[state_at(u, slot)] = hbuf[idx];
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int slot = s_slot[4 * tm + i];
             if (slot >= 0 && s_nfr[4 * tm + i] > 0) {
 #pragma unroll
-                for (int u = 0; u < 2; ++u) p.c_state[(size_t)(2 * tn + u) * ms + slot] = creg[i][u];
+                for (int u = 0; u < 2; ++u) p.c_state[state_at(2 * tn + u, slot)] = creg[i][u];
             }
         }
         if (warp == 0 && s_slot[lane] >= 0 && s_nfr[lane] > 0) {

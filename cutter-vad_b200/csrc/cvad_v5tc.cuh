@@ -80,11 +80,12 @@ constexpr uint32_t kFeatScaleOff = 8192;
 // fused single-frame kernel (max_frames == 1): the front end plus the LSTM step of the same 32 streams in one CTA.
 // ACT | H operand (24 KB) | ring (6 slots) | nyq | decoder partials | barriers | meta.  Weight stream per tile:
 // 24 W_hh tiles (issued while the loader runs), the 69 front-end tiles, 24 W_ih tiles.
+constexpr int kPrefetchCtas = 16;            // chained steps: CTAs 0..15, when scheduled early, prefetch the step's audio into L2
 constexpr int kFusedRing = 6;
 constexpr int kFusedSlotsPerTile = 24 + kFeSlotsPerTile + 24;
 constexpr uint32_t kColGate = 384;           // TMEM columns 384 + 32 g: gate g (i,f,g,o), one accumulator per gate
 constexpr size_t kFusedSmemTC = 1024 + kActBytes + 24576 + (size_t)kFusedRing * kSlotBytes + 96 * 4 + 128 * 4 +
-                                (2 * kFusedRing + 3) * 8 + 16 + 2 * kTile * 4 + kTile * 16 + 7 * kTile * 4 + kTile * 8 + 5 * kTile * 4 + 128;
+                                (2 * kFusedRing + 3 + 4) * 8 + 16 + 2 * kTile * 4 + kTile * 16 + 7 * kTile * 4 + kTile * 8 + 5 * kTile * 4 + 16 + 128;
 // feature hand-off (front end -> recurrent), per (frame, stream tile): the x half of the recurrent B operand,
 // byte for byte: [kb 0..1][row = part*32 + item (96 rows)][128 B], SW128
 constexpr uint32_t kFeatTileBytes = 2 * 12288;
@@ -251,9 +252,6 @@ __device__ __forceinline__ long long gtime_ns() {
 #define CVAD_ISSUE_ROLL _Pragma("unroll 1")
 #else
 #define CVAD_ISSUE_ROLL
-#endif
-#ifndef CVAD_STATE_FIRST
-#define CVAD_STATE_FIRST 0
 #endif
 #define CVAD_PROF_NS(k) do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(k)] = gtime_ns(); } while (0)
 #define CVAD_PROF(k) do { if (p.prof && blockIdx.x == 0 && first_tile) p.prof[(k)] = clock64(); } while (0)
@@ -490,8 +488,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     float *dpart = nyq + 96;                                                 // FUSED: [4][32] decoder partial sums
     uint64_t *bars = reinterpret_cast<uint64_t *>(dpart + (FUSED ? 128 : 0));
     uint64_t *full = bars, *empty = bars + RING, *act_ready = bars + 2 * RING, *acc_ready = act_ready + 1,
-             *h_ready = acc_ready + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_ready + 1);
+             *h_ready = acc_ready + 1, *gate_ready = h_ready + 1;          // FUSED: gate_ready[4], one per LSTM gate
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gate_ready + (FUSED ? 4 : 0));
     int *s_slot = reinterpret_cast<int *>(tmem_slot + 4);
     int *s_valid = s_slot + kTile;
     double *s_thr = reinterpret_cast<double *>(s_valid + kTile);             // FUSED: start_p[32], end_p[32]
@@ -499,6 +497,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     int *s_dn = FUSED ? reinterpret_cast<int *>(amax + 6 * kTile) : s_valid + kTile;   // [32] per-stream denoise flag (fetched with the slot ids)
     long long *s_f0 = reinterpret_cast<long long *>(s_dn + kTile);           // FUSED: [32] frames_done
     int *s_sm = reinterpret_cast<int *>(s_f0 + kTile);                       // FUSED: [5][32] is_voice_active, start / end counters, N_s, N_e
+    int *s_grp = s_sm + 5 * kTile;                                           // FUSED: [4] first slot of stream group g when its 8 slots are consecutive from a multiple of 8, else -1
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     CVAD_PROF_NS(120);
@@ -508,6 +507,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
         mbar_init(act_ready, 1);
         mbar_init(acc_ready, 1);
         mbar_init(h_ready, 1);
+        if (FUSED)
+            for (int i = 0; i < 4; ++i) mbar_init(&gate_ready[i], 1);
         mbar_fence_init();
     }
     if (warp == kProducerWarp) tc::tmem_alloc(tmem_slot, 512);
@@ -608,6 +609,28 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             for (int s = 0; s < pre; ++s) mbar_wait(&full[s], 0u);
     } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------ MMA issuer
+        if (FUSED && p.step_ctr && blockIdx.x < kPrefetchCtas) {
+            // Chained steps: ~20 CTAs of a 128-tile step are scheduled on idle SMs while the previous step still runs and
+            // would only wait.  A CTA that finds the completed-steps counter behind its own sequence number is one of
+            // them: it pulls the audio of every 16th tile into L2 (this warp has nothing to do until h_ready), so that
+            // the step's loaders -- all 128 start at once -- read from L2 instead of sharing one HBM burst.  Hints only:
+            // the addresses are the ones the loaders read, no data is consumed ahead of griddepcontrol.wait.
+            const int done = *reinterpret_cast<volatile const int *>(p.step_ctr);
+            if (done - p.step_seq < 0) {
+                const size_t es = p.pcm == 0 ? 4 : 2;
+                const int flen = p.frame_len < 512 ? p.frame_len : 512;
+                const int lines = (int)((flen * es + 127) / 128);
+                for (int t = blockIdx.x; t < p.n_stiles; t += kPrefetchCtas) {
+                    const int rows = min(kTile, p.n_streams - t * kTile);
+                    for (int l = lane; l < rows * lines; l += 32) {
+                        const int s = l / lines, c = l - s * lines;
+                        const unsigned char *a = reinterpret_cast<const unsigned char *>(p.audio) +
+                                                 (size_t)((long long)(t * kTile + s) * p.stride) * es + (size_t)c * 128;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                    }
+                }
+            }
+        }
         if (FUSED) griddep_wait();
         uint32_t g = 0, act_phase = 0, h_phase = 0;
         const uint32_t i128_96 = H16 ? idesc_f16_f32(128, 96) : tc::idesc_bf16_f32(128, 96),
@@ -751,7 +774,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 tc::fence_after_sync();
                 CVAD_PROF(43);
                 CVAD_ISSUE_ROLL
-                for (int gate = 0; gate < 4; ++gate)
+                for (int gate = 0; gate < 4; ++gate) {
                     CVAD_ISSUE_ROLL
                     for (int kb = 0; kb < 2; ++kb)
                         for (int wp = 0; wp < NP; ++wp)
@@ -762,7 +785,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                                                                    kb == 0 && wp == 0))
                             else CVAD_TC_SLOT(CVAD_GATE(wp, act_s + kb * kXhKb, kColGate + 32 * gate, i128_32, false))
                         }
-                if (tc::elect_one()) tc::mma_commit(acc_ready);
+                    // the cell consumes the gates one by one (i, f, g, o), each under the next gate's products: every gate
+                    // has its own barrier (one phase per tile), so a commit can never run two phases ahead of its reader
+                    if (BMN && tc::elect_one()) tc::mma_commit(&gate_ready[gate]);
+                }
+                if (!BMN && tc::elect_one()) tc::mma_commit(acc_ready);
                 CVAD_PROF(44);
                 __syncwarp();
             }
@@ -776,7 +803,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
         // ------------------------------------------------------------ loader + epilogue warps
         const int q = warp & 3, cg = warp >> 2;          // TMEM lane quadrant, column group 0..3
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, gate_phase = 0;
         const int flen = p.frame_len < 512 ? p.frame_len : 512;
         if (FUSED) griddep_wait();
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -798,6 +825,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             if (warp == 0) {
                 s_slot[lane] = my_slot;
                 s_valid[lane] = my_valid;
+                if (FUSED) {
+                    // stream group g = streams 8g .. 8g+7 (one epilogue thread's share): are its slots one aligned row of the state?
+                    const int base = __shfl_sync(0xffffffffu, my_slot, lane & ~7);
+                    const unsigned okm = __ballot_sync(0xffffffffu, my_valid && (base & 7) == 0 && my_slot == base + (lane & 7));
+                    const int gbase = __shfl_sync(0xffffffffu, base, (lane & 3) * 8);
+                    if (lane < 4) s_grp[lane] = ((okm >> (8 * lane)) & 0xffu) == 0xffu ? gbase : -1;
+                }
                 if (my_slot >= 0) dn = (int)p.denoise[my_slot];
                 if (!FUSED) s_dn[lane] = dn;
                 if (FUSED && my_slot >= 0) {
@@ -819,18 +853,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             //      kernel, before the resident state is fetched, so that both latencies overlap.
             float creg[8], hreg[8];
             const int u_own = 32 * q + lane, i_own = 8 * cg;   // this thread's hidden unit (TMEM lane) and 8 streams
-#if CVAD_STATE_FIRST
-            // experiment: the resident state requested ahead of the audio (measured: the tile gets 1.4 k cycles LONGER)
-            if (FUSED) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int idx = e * kEpiThreads + tid;
-                    const int slot = s_valid[idx & 31] ? s_slot[idx & 31] : -1;
-                    hreg[e] = slot >= 0 ? ldg_ordered(p.h_state + (size_t)(idx >> 5) * p.max_streams + slot) : 0.f;
-                    creg[e] = slot >= 0 ? ldg_ordered(p.c_state + (size_t)(idx >> 5) * p.max_streams + slot) : 0.f;
-                }
-            }
-#endif
                 const bool fast = p.vec_ok && flen == 512;
                 float v[4][8];
                 bool ok[4];
@@ -862,19 +884,28 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                         }
                     }
                 }
-            // FUSED: resident state of the tile's streams: h -> BF16x3 rows of the H operand, c -> registers
-            // (global reads coalesced over streams, transposed through the still-unused ACT region)
+            // FUSED: resident state of the tile's streams: h -> rows of the H operand, c -> registers.  The state is laid out
+            // [slot / 8][unit][slot % 8] (state_at): the 8 streams of this thread are one 32-byte row when their slots are
+            // consecutive from a multiple of 8 (s_grp), read with two 16-byte loads straight into the registers that own
+            // them -- a warp's 32 units are 1 KB contiguous; any other slot list is gathered element by element.
             if (FUSED) {
-                float *sbuf = reinterpret_cast<float *>(act);   // [128][33]
-#if !CVAD_STATE_FIRST
+                const int gb = s_grp[cg];
+                if (gb >= 0) {
+                    const float4 *ph = reinterpret_cast<const float4 *>(p.h_state + state_at(u_own, gb));
+                    const float4 *pc = reinterpret_cast<const float4 *>(p.c_state + state_at(u_own, gb));
+                    const float4 h0 = __ldg(ph), h1 = __ldg(ph + 1), c0 = __ldg(pc), c1 = __ldg(pc + 1);
+                    hreg[0] = h0.x; hreg[1] = h0.y; hreg[2] = h0.z; hreg[3] = h0.w;
+                    hreg[4] = h1.x; hreg[5] = h1.y; hreg[6] = h1.z; hreg[7] = h1.w;
+                    creg[0] = c0.x; creg[1] = c0.y; creg[2] = c0.z; creg[3] = c0.w;
+                    creg[4] = c1.x; creg[5] = c1.y; creg[6] = c1.z; creg[7] = c1.w;
+                } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int idx = e * kEpiThreads + tid;
-                    const int slot = s_valid[idx & 31] ? s_slot[idx & 31] : -1;
-                    hreg[e] = slot >= 0 ? __ldg(p.h_state + (size_t)(idx >> 5) * p.max_streams + slot) : 0.f;
-                    creg[e] = slot >= 0 ? __ldg(p.c_state + (size_t)(idx >> 5) * p.max_streams + slot) : 0.f;
+                    for (int e = 0; e < 8; ++e) {
+                        const int slot = s_valid[i_own + e] ? s_slot[i_own + e] : -1;
+                        hreg[e] = slot >= 0 ? __ldg(p.h_state + state_at(u_own, slot)) : 0.f;
+                        creg[e] = slot >= 0 ? __ldg(p.c_state + state_at(u_own, slot)) : 0.f;
+                    }
                 }
-#endif
                 if (warp == 0) {
                     // the slot data fetched at tile start (by now every global load of this warp is in flight)
                     s_dn[lane] = dn;
@@ -884,19 +915,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                         s_sm[3 * kTile + lane] = a3; s_sm[4 * kTile + lane] = a4;
                         s_f0[lane] = f0;
                     }
-                }
-                float *sbuf_c = sbuf + 128 * 33;                // h and c are transposed side by side: one barrier each way
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int idx = e * kEpiThreads + tid;
-                    sbuf[(idx >> 5) * 33 + (idx & 31)] = hreg[e];
-                    sbuf_c[(idx >> 5) * 33 + (idx & 31)] = creg[e];
-                }
-                epi_bar();
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    hreg[e] = sbuf[u_own * 33 + i_own + e];
-                    creg[e] = sbuf_c[u_own * 33 + i_own + e];
                 }
                 if constexpr (BMN) {
 #pragma unroll
@@ -910,7 +928,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     }
                 }
                 tc::fence_async_smem();
-                epi_bar();                                     // also: sbuf reads done before the loader rewrites ACT
+                epi_bar();
                 if (tid == 0) mbar_arrive(h_ready);
                 CVAD_PROF(12);
             }
@@ -1361,6 +1379,44 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     if (s_valid[lane] && p.status && __ldcg(p.status + i) != 0u) s_valid[lane] = 0;
                 }
                 epi_bar();
+                float dv[8], hn[8];
+                if constexpr (BMN) {
+                    // gate by gate as the W_ih products complete: sigmoid(i), sigmoid(f), then g -> c' -> tanh(c') run under the
+                    // products of the following gates; only sigmoid(o) and h' are left when the last product lands.  Same
+                    // operations in the same order per element as the all-at-once form below (bit-identical).
+                    const float ih_w = p.tc16_inv_w[5], hh = kHInv * p.tc16_inv_w[6];
+                    float ix[8], ga[2][8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) ix[e] = scale_from_max(amax[5 * kTile + i0 + e]).inv * ih_w;
+#pragma unroll
+                    for (int gi = 0; gi < 4; ++gi) {
+                        mbar_wait(&gate_ready[gi], gate_phase);
+                        tc::fence_after_sync();
+                        if (gi == 0) CVAD_PROF(13);
+                        float gh[8], gx[8], gy[8];
+                        tmem_ld8(lane_addr + kColGate + 32 * gi + i0, gh);
+                        tmem_ld8(lane_addr + kColIh + 64 * gi + i0, gx);
+                        tmem_ld8(lane_addr + kColIh + 64 * gi + 32 + i0, gy);
+                        tmem_wait_ld();
+                        const float bias = gi == 0 ? b_i : (gi == 1 ? b_f : (gi == 2 ? b_g : b_o));
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float z = fmaf(gx[e] + gy[e], ix[e], gh[e] * hh) + bias;
+                            if (gi < 2) {
+                                ga[gi][e] = sfu_sigmoid(z);
+                            } else if (gi == 2) {
+                                const float cn = __fadd_rn(__fmul_rn(ga[1][e], creg[e]), __fmul_rn(ga[0][e], sfu_tanh(z)));
+                                creg[e] = cn;
+                                ga[0][e] = sfu_tanh(cn);
+                            } else {
+                                hn[e] = sfu_sigmoid(z) * ga[0][e];
+                                dv[e] = wd * fmaxf(hn[e], 0.f);
+                            }
+                        }
+                        if (gi == 2) CVAD_PROF(21);
+                    }
+                    gate_phase ^= 1u;
+                } else {
                 mbar_wait(acc_ready, acc_phase); acc_phase ^= 1u;
                 tc::fence_after_sync();
                 CVAD_PROF(13);
@@ -1390,7 +1446,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     }
                 }
                 CVAD_PROF(21);
-                float dv[8], hn[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float ig = sfu_sigmoid(gate[0][e] + b_i);
@@ -1401,6 +1456,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     hn[e] = og * sfu_tanh(cn);
                     creg[e] = cn;
                     dv[e] = wd * fmaxf(hn[e], 0.f);
+                }
                 }
                 CVAD_PROF(22);
 #pragma unroll
@@ -1416,28 +1472,31 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 dv[0] += __shfl_xor_sync(0xffffffffu, dv[0], 8);
                 dv[0] += __shfl_xor_sync(0xffffffffu, dv[0], 16);
                 if (lane < 8) dpart[q * 32 + i0 + lane] = dv[0];
-                // new state back to HBM, coalesced over streams through ACT (dead: every MMA of the tile is complete)
-                float *sbuf = reinterpret_cast<float *>(act), *sbuf_c = sbuf + 128 * 33;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    sbuf[u * 33 + i0 + e] = hn[e];
-                    sbuf_c[u * 33 + i0 + e] = creg[e];
-                }
-                tc::fence_before_sync();
-                epi_bar();
-                CVAD_PROF(23);
+                // new state back to HBM: one 32-byte row per thread when the group's slots are a row of the state (s_grp) and
+                // none of its streams was flagged non-finite (such a stream keeps its old state), else element by element
                 if (p.commit) {
+                    const int4 va = *reinterpret_cast<const int4 *>(s_valid + i0), vb = *reinterpret_cast<const int4 *>(s_valid + i0 + 4);
+                    const bool all8 = va.x && va.y && va.z && va.w && vb.x && vb.y && vb.z && vb.w;
+                    const int gb = s_grp[cg];
+                    if (gb >= 0 && all8) {
+                        float4 *ph = reinterpret_cast<float4 *>(p.h_state + state_at(u, gb));
+                        float4 *pc = reinterpret_cast<float4 *>(p.c_state + state_at(u, gb));
+                        ph[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                        ph[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                        pc[0] = make_float4(creg[0], creg[1], creg[2], creg[3]);
+                        pc[1] = make_float4(creg[4], creg[5], creg[6], creg[7]);
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int idx = e * kEpiThreads + tid;
-                        const int s = idx & 31;
-                        if (s_valid[s]) {
-                            const size_t at = (size_t)(idx >> 5) * p.max_streams + s_slot[s];
-                            p.h_state[at] = sbuf[(idx >> 5) * 33 + s];
-                            p.c_state[at] = sbuf_c[(idx >> 5) * 33 + s];
-                        }
+                        for (int e = 0; e < 8; ++e)
+                            if (s_valid[i0 + e]) {
+                                const size_t at = state_at(u, s_slot[i0 + e]);
+                                p.h_state[at] = hn[e];
+                                p.c_state[at] = creg[e];
+                            }
                     }
                 }
+                epi_bar();   // dpart
+                CVAD_PROF(23);
                 CVAD_PROF(24);
                 // sigmoid(w . relu(h') + b), then the start/end state machine (silero_model.py:790-923)
                 if (warp == 0 && s_valid[lane]) {
@@ -1496,6 +1555,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 CVAD_PROF_NS(127);
             }
         }
+        if (FUSED && p.step_ctr && tid == 0) {
+            // chained steps: the last CTA counts the step as completed (read by the next step's early CTAs, above)
+            if (atomicAdd(p.step_ctr + 1, 1) == (int)gridDim.x - 1) {
+                p.step_ctr[1] = 0;
+                atomicAdd(p.step_ctr, 1);
+            }
+        }
         if (FUSED && p.ev_ctr && tid == 0) {
             // chained steps: events were counted in the engine's own counter (ev_ctr[0]); the last CTA to take a ticket
             // publishes the total and leaves counter and ticket at zero for the next step -- no memset between the
@@ -1547,7 +1613,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int st = blockIdx.x;
-    const int ms = p.max_streams;
     CVAD_PROF_NS(123);
 
     if (tid < kTile) {
@@ -1648,8 +1713,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
             for (int e = 0; e < 8; ++e) {
                 const int idx = e * kEpiThreads + tid;
                 const int slot = s_slot[idx & 31];
-                hreg[e] = slot >= 0 ? __ldg(p.h_state + (size_t)(idx >> 5) * ms + slot) : 0.f;
-                creg[e] = slot >= 0 ? __ldg(p.c_state + (size_t)(idx >> 5) * ms + slot) : 0.f;
+                hreg[e] = slot >= 0 ? __ldg(p.h_state + state_at(idx >> 5, slot)) : 0.f;
+                creg[e] = slot >= 0 ? __ldg(p.c_state + state_at(idx >> 5, slot)) : 0.f;
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -1860,7 +1925,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
                 for (int idx = tid; idx < 4096; idx += kEpiThreads) {
                     const int s = idx & 31, uu = idx >> 5;
                     const int slot = s_slot[s];
-                    if (slot >= 0 && s_nfr[s] > 0) p.h_state[(size_t)uu * ms + slot] = sbuf[uu * 33 + s];
+                    if (slot >= 0 && s_nfr[s] > 0) p.h_state[state_at(uu, slot)] = sbuf[uu * 33 + s];
                 }
                 epi_bar();
 #pragma unroll
@@ -1869,7 +1934,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5S
                 for (int idx = tid; idx < 4096; idx += kEpiThreads) {
                     const int s = idx & 31, uu = idx >> 5;
                     const int slot = s_slot[s];
-                    if (slot >= 0 && s_nfr[s] > 0) p.c_state[(size_t)uu * ms + slot] = sbuf[uu * 33 + s];
+                    if (slot >= 0 && s_nfr[s] > 0) p.c_state[state_at(uu, slot)] = sbuf[uu * 33 + s];
                 }
                 if (warp == 0 && s_slot[lane] >= 0 && s_nfr[lane] > 0) {
                     const int slot = s_slot[lane];
