@@ -1522,13 +1522,21 @@ int cvad_get_math(const cvad_engine *e) { return e ? e->math : CVAD_E_INVALID; }
 int cvad_set_profile(cvad_engine *e, int enabled) {
     if (!e) return CVAD_E_INVALID;
     if (enabled && !e->d_prof) {
-        CU_TRY(e, cudaMalloc(reinterpret_cast<void **>(&e->d_prof), 128 * sizeof(long long)));
-        CU_TRY(e, cudaMemset(e->d_prof, 0, 128 * sizeof(long long)));
+        CU_TRY(e, cudaMalloc(reinterpret_cast<void **>(&e->d_prof), (128 + 512) * sizeof(long long)));
+        CU_TRY(e, cudaMemset(e->d_prof, 0, (128 + 512) * sizeof(long long)));
     } else if (!enabled && e->d_prof) {
         CU_TRY(e, cudaDeviceSynchronize());
         cudaFree(e->d_prof);
         e->d_prof = nullptr;
     }
+    return CVAD_OK;
+}
+
+int cvad_read_profile_chain(cvad_engine *e, long long *out512) {
+    if (!e || !out512 || !e->d_prof) return CVAD_E_INVALID;
+    CU_TRY(e, cudaSetDevice(e->device));
+    { int rcq = quiesce(e); if (rcq) return rcq; }
+    CU_TRY(e, cudaMemcpy(out512, e->d_prof + 128, 512 * sizeof(long long), cudaMemcpyDeviceToHost));
     return CVAD_OK;
 }
 

@@ -254,6 +254,11 @@ __device__ __forceinline__ long long gtime_ns() {
 #define CVAD_ISSUE_ROLL
 #endif
 #define CVAD_PROF_NS(k) do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(k)] = gtime_ns(); } while (0)
+// chained steps under cvad_set_profile: global-timer marks of CTAs 0, 64 and the last one, kept for the last 8 steps
+// (prof[128 + 64 (step_seq % 8) + 8 b + k], k: 0 entry, 1 prologue done, 2 grid dependency resolved, 3 tile start, 4 tile end, 5 exit)
+#define CVAD_CHAIN_NS(k) do { if (FUSED && p.prof && p.step_ctr && threadIdx.x == 0) {                                       \
+        const int b_ = blockIdx.x == 0 ? 0 : (blockIdx.x == 64 ? 1 : (blockIdx.x == gridDim.x - 1 ? 2 : -1));                \
+        if (b_ >= 0) p.prof[128 + 64 * (p.step_seq & 7) + 8 * b_ + (k)] = gtime_ns(); } } while (0)
 #define CVAD_PROF(k) do { if (p.prof && blockIdx.x == 0 && first_tile) p.prof[(k)] = clock64(); } while (0)
 
 // LSTM gate products of one weight tile (part wp) in the fused kernel: all six products of a MAC go to ONE
@@ -501,6 +506,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     CVAD_PROF_NS(120);
+    CVAD_CHAIN_NS(0);
 
     if (tid == 0) {
         for (int i = 0; i < RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -517,6 +523,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     tc::fence_after_sync();
     if (*tmem_slot != 0u) __trap();   // sole CTA on the SM and all 512 columns: TMEM base is lane 0 / column 0
     CVAD_PROF_NS(121);
+    CVAD_CHAIN_NS(1);
     // programmatic dependent launch: the recurrent kernel may be scheduled now; it runs its own prologue (state
     // load, weight prefetch) and blocks in griddepcontrol.wait until this grid has completed
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -806,6 +813,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
         uint32_t acc_phase = 0, gate_phase = 0;
         const int flen = p.frame_len < 512 ? p.frame_len : 512;
         if (FUSED) griddep_wait();
+        CVAD_CHAIN_NS(2);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
             int my_slot, my_valid;
@@ -847,6 +855,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             const bool first_tile = tile == (int)blockIdx.x && tid == 0;
             CVAD_PROF(0);
             CVAD_PROF_NS(126);
+            CVAD_CHAIN_NS(3);
             // ---- frame loader (audio.py:164-190 split, :104-121 gate, silero_model.py:449-474 pad/truncate):
             //      8 samples per work unit -> 3 x 16-byte BF16 chunks of the AUD operand, row = segment*32 + item.
             //      All global loads of the thread's 4 units are issued before the first use -- and, in the fused
@@ -1475,8 +1484,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 // new state back to HBM: one 32-byte row per thread when the group's slots are a row of the state (s_grp) and
                 // none of its streams was flagged non-finite (such a stream keeps its old state), else element by element
                 if (p.commit) {
-                    const int4 va = *reinterpret_cast<const int4 *>(s_valid + i0), vb = *reinterpret_cast<const int4 *>(s_valid + i0 + 4);
-                    const bool all8 = va.x && va.y && va.z && va.w && vb.x && vb.y && vb.z && vb.w;
+                    bool all8 = true;
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {          // (s_valid is 8-byte aligned)
+                        const int2 v2 = *reinterpret_cast<const int2 *>(s_valid + i0 + e);
+                        all8 = all8 && v2.x && v2.y;
+                    }
                     const int gb = s_grp[cg];
                     if (gb >= 0 && all8) {
                         float4 *ph = reinterpret_cast<float4 *>(p.h_state + state_at(u, gb));
@@ -1553,6 +1566,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 epi_bar();   // ACT, dpart and s_valid are rewritten by the next tile
                 CVAD_PROF(14);
                 CVAD_PROF_NS(127);
+                CVAD_CHAIN_NS(4);
             }
         }
         if (FUSED && p.step_ctr && tid == 0) {
@@ -1578,6 +1592,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     __syncthreads();
     if (warp == kProducerWarp) tc::tmem_dealloc(0u, 512);
     CVAD_PROF_NS(122);
+    CVAD_CHAIN_NS(5);
 }
 
 // =====================================================================================

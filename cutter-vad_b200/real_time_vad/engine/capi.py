@@ -28,7 +28,7 @@ EXPORTS = (
     "cvad_set_stream", "cvad_reset", "cvad_configure", "cvad_get_state", "cvad_set_state",
     "cvad_step", "cvad_step_submit", "cvad_step_collect", "cvad_step_device", "cvad_sync", "cvad_launch_count", "cvad_debug_dump",
     "cvad_alloc_pinned", "cvad_free_pinned", "cvad_set_timing", "cvad_read_timing", "cvad_resample_matrix",
-    "cvad_set_math", "cvad_get_math", "cvad_set_resampler", "cvad_get_resampler", "cvad_set_profile", "cvad_read_profile",
+    "cvad_set_math", "cvad_get_math", "cvad_set_resampler", "cvad_get_resampler", "cvad_set_profile", "cvad_read_profile", "cvad_read_profile_chain",
     "cvad_feeder_create", "cvad_feeder_destroy", "cvad_feeder_last_error", "cvad_feeder_open", "cvad_feeder_close",
     "cvad_feeder_clear", "cvad_feeder_is_active", "cvad_feeder_pending", "cvad_feeder_push", "cvad_feeder_push_many",
     "cvad_feeder_step", "cvad_feeder_gather_only", "cvad_feeder_deliver_only",
@@ -131,6 +131,7 @@ def lib() -> C.CDLL:
     L.cvad_get_resampler.argtypes = [vp]
     L.cvad_set_profile.argtypes = [vp, i32]
     L.cvad_read_profile.argtypes = [vp, vp]
+    L.cvad_read_profile_chain.argtypes = [vp, vp]
     L.cvad_reset.argtypes = [vp, i32, vp]
     L.cvad_configure.argtypes = [vp, i32, vp, dbl, dbl, i32, i32, i32]
     L.cvad_get_state.argtypes = [vp, i32, vp, vp, vp, vp]

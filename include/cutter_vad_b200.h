@@ -165,6 +165,10 @@ int cvad_get_resampler(const cvad_engine *e);
    phase boundaries (layout in csrc/cvad_v5tc.cuh, CVAD_PROF); cvad_read_profile copies the 128 marks out. */
 int cvad_set_profile(cvad_engine *e, int enabled);
 int cvad_read_profile(cvad_engine *e, long long *out128);
+/* Chained device steps (cvad_step_device, one frame per step) under cvad_set_profile: global-timer nanoseconds of CTAs
+   0, 64 and the last one for the last 8 steps, out512[64 (step % 8) + 8 b + k], k = entry, prologue done, grid dependency
+   resolved, tile start, tile end, exit. */
+int cvad_read_profile_chain(cvad_engine *e, long long *out512);
 
 /* Use an existing CUDA stream (cudaStream_t passed as void*); NULL = engine's own. */
 int cvad_set_stream(cvad_engine *e, void *cuda_stream);
