@@ -67,10 +67,10 @@ int cvad_tc_probe_mn(int device, const uint16_t *a_bf16, const uint16_t *b_bf16,
 }
 
 int cvad_tc_rate(int device, int M, int N, int reps, int a_tiles, int n_acc, int grid, long long *out2) {
-    return cvad_tc_rate2(device, M, N, reps, a_tiles, n_acc, grid, 0, out2);
+    return cvad_tc_rate_mn(device, M, N, reps, a_tiles, n_acc, grid, 0, out2);
 }
 
-int cvad_tc_rate2(int device, int M, int N, int reps, int a_tiles, int n_acc, int grid, int b_mn, long long *out2) {
+int cvad_tc_rate_mn(int device, int M, int N, int reps, int a_tiles, int n_acc, int grid, int b_mn, long long *out2) {
     using namespace cvad::tc;
     if (b_mn && N % 32) return CVAD_E_INVALID;
     if (!out2 || a_tiles < 1 || a_tiles > 10 || (M != 64 && M != 128) || N < 8 || N > 256 || grid < 1 || n_acc < 1 || n_acc * N > 512) return CVAD_E_INVALID;

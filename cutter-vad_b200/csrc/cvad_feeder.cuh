@@ -100,18 +100,18 @@ struct cvad_feeder {
     std::string err;
 
     struct Slot {
-        bool open = false;
         int rate = 16000;
         int n_in = 512;                // source samples per model frame (mixed mode)
-        int payload = 0;               // CVAD_PAYLOAD_*
         bool denoise = true;
         double start_p = 0.7;
-        bool active = false;           // host mirror of is_voice_active
-        int64_t skip = 0;              // hop > frame_len: samples between frames that had not arrived when their frame ran
         std::vector<float> pre_roll, segment;
     };
     std::vector<Slot> slot;
     std::vector<int64_t> fill;
+    // what the per-step loops over ALL streams read, side by side (a Slot is two cache lines: at 10,000 streams the walk
+    // over the structs was most of the segment-assembly phase): open flag, CVAD_PAYLOAD_*, host mirror of is_voice_active
+    std::vector<uint8_t> opn, pay, act;
+    std::vector<int64_t> skp;          // hop > frame_len: samples between frames that had not arrived when their frame ran
 
     // step scratch (valid until the next step)
     unsigned char *stage[2] = {nullptr, nullptr};   // pinned gather targets, alternating
@@ -200,8 +200,8 @@ int feeder_gather(cvad_feeder *f, bool allow_planes = false) {
     int tmax = 0;
     int64_t row = 0;
     for (int s = 0; s < f->max_streams; ++s) {
+        if (!f->opn[s]) continue;
         const cvad_feeder::Slot &sl = f->slot[s];
-        if (!sl.open) continue;
         const int64_t have = f->fill[s];
         int64_t c;
         if (mixed) c = have / sl.n_in;
@@ -246,7 +246,7 @@ int feeder_gather(cvad_feeder *f, bool allow_planes = false) {
             const int64_t rem = have - used;
             if (rem > 0) std::memmove(src, src + (size_t)used * f->es, (size_t)rem * f->es);
             f->fill[s] = rem > 0 ? rem : 0;
-            if (rem < 0) f->slot[s].skip = -rem;
+            if (rem < 0) f->skp[s] = -rem;
         }
     };
     const size_t bytes = (size_t)n * (size_t)row * f->es;
@@ -271,23 +271,24 @@ void feeder_deliver(cvad_feeder *f) {
     // pass 1: how many continue-frames will be pooled (so that frame_pool never reallocates under the records)
     size_t pool = 0;
     for (int k = 0; k < n; ++k) {
-        const cvad_feeder::Slot &sl = f->slot[f->ids[k]];
-        if (sl.payload == CVAD_PAYLOAD_FRAMES && sl.rate == 16000) pool += (size_t)f->counts[k] * (size_t)f->frame_len;
+        if (f->pay[f->ids[k]] == CVAD_PAYLOAD_FRAMES && f->slot[f->ids[k]].rate == 16000) pool += (size_t)f->counts[k] * (size_t)f->frame_len;
     }
     f->frame_pool.reserve(pool);
     for (int k = 0; k < n; ++k) {
         const int s = f->ids[k];
-        cvad_feeder::Slot &sl = f->slot[s];
         const int c = f->counts[k];
         const uint8_t *fl = f->flags.data() + (size_t)k * T;
         const float *pr = f->probs.data() + (size_t)k * T;
-        if (sl.payload == CVAD_PAYLOAD_NONE) {
+        const int payload = f->pay[s];
+        if (payload == CVAD_PAYLOAD_NONE) {
             const uint8_t last = fl[c - 1];
-            sl.active = !(last & CVAD_FLAG_ENDED) && (last & (CVAD_FLAG_STARTED | CVAD_FLAG_CONTINUING));
+            f->act[s] = !(last & CVAD_FLAG_ENDED) && (last & (CVAD_FLAG_STARTED | CVAD_FLAG_CONTINUING));
             continue;
         }
+        cvad_feeder::Slot &sl = f->slot[s];
+        bool active = f->act[s] != 0;
 
-        const bool raw_mode = sl.payload >= CVAD_PAYLOAD_SEGMENTS && sl.rate != 16000;   // host resamples the payloads
+        const bool raw_mode = payload >= CVAD_PAYLOAD_SEGMENTS && sl.rate != 16000;   // host resamples the payloads
         const int64_t step_len = mixed ? sl.n_in : f->hop;
         const int flen = mixed ? sl.n_in : f->frame_len;
         for (int j = 0; j < c; ++j) {
@@ -300,19 +301,19 @@ void feeder_deliver(cvad_feeder *f) {
                 // every frame is handed over; the host keeps pre-roll / segment for this stream itself
                 d.raw = fp; d.raw_len = flen;
                 const uint8_t last = b;
-                sl.active = !(last & CVAD_FLAG_ENDED) && (last & (CVAD_FLAG_STARTED | CVAD_FLAG_CONTINUING));
+                active = !(last & CVAD_FLAG_ENDED) && (last & (CVAD_FLAG_STARTED | CVAD_FLAG_CONTINUING));
                 f->deliveries.push_back(d);
                 continue;
             }
-            const bool audio = sl.payload >= CVAD_PAYLOAD_SEGMENTS;
+            const bool audio = payload >= CVAD_PAYLOAD_SEGMENTS;
             bool emit = false;
-            if (!sl.active) {
+            if (!active) {
                 if ((double)pr[j] >= sl.start_p) {
                     if (audio) feeder_gate_append(f, sl, fp, flen, sl.pre_roll);
                     if (b & CVAD_FLAG_STARTED) {
                         sl.segment.swap(sl.pre_roll);
                         sl.pre_roll.clear();
-                        sl.active = true;
+                        active = true;
                         emit = true;
                     }
                 } else {
@@ -324,7 +325,7 @@ void feeder_deliver(cvad_feeder *f) {
                     frame_at = sl.segment.size();
                     feeder_gate_append(f, sl, fp, flen, sl.segment);
                 }
-                if (sl.payload == CVAD_PAYLOAD_FRAMES) {
+                if (payload == CVAD_PAYLOAD_FRAMES) {
                     const size_t o = f->frame_pool.size();
                     f->frame_pool.insert(f->frame_pool.end(), sl.segment.begin() + (ptrdiff_t)frame_at, sl.segment.end());
                     d.frame = f->frame_pool.data() + o;
@@ -337,12 +338,13 @@ void feeder_deliver(cvad_feeder *f) {
                     sl.segment.clear();
                     d.segment = f->done_segments.back().data();
                     d.segment_len = (int64_t)f->done_segments.back().size();
-                    sl.active = false;
+                    active = false;
                     emit = true;
                 }
             }
             if (emit) f->deliveries.push_back(d);
         }
+        f->act[s] = active ? 1 : 0;
     }
 }
 
@@ -392,6 +394,10 @@ int cvad_feeder_create(cvad_engine *e, int max_streams, int pcm_format, int fram
     }
     f->slot.resize((size_t)max_streams);
     f->fill.assign((size_t)max_streams, 0);
+    f->opn.assign((size_t)max_streams, 0);
+    f->pay.assign((size_t)max_streams, 0);
+    f->act.assign((size_t)max_streams, 0);
+    f->skp.assign((size_t)max_streams, 0);
     const unsigned hw = std::thread::hardware_concurrency();
     f->threads = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
     if (f->threads > 1) f->pool.reset(new FeederPool(f->threads - 1));
@@ -425,14 +431,14 @@ int cvad_feeder_open(cvad_feeder *f, int slot, int src_rate, int payload, double
     }
     std::lock_guard<std::mutex> lk(f->mu);
     cvad_feeder::Slot &s = f->slot[slot];
-    s.open = true;
+    f->opn[slot] = 1;
+    f->pay[slot] = (uint8_t)payload;
+    f->act[slot] = 0;
     s.rate = src_rate;
     s.n_in = rate_n_in(src_rate);
-    s.payload = payload;
     s.denoise = enable_denoising != 0;
     s.start_p = vad_start_probability;
-    s.active = false;
-    s.skip = 0;
+    f->skp[slot] = 0;
     s.pre_roll.clear();
     s.segment.clear();
     f->fill[slot] = 0;
@@ -444,8 +450,8 @@ int cvad_feeder_close(cvad_feeder *f, int slot) {
     if (slot < 0 || slot >= f->max_streams) return ffail(f, CVAD_E_CAPACITY, "slot id out of range");
     std::lock_guard<std::mutex> lk(f->mu);
     cvad_feeder::Slot &s = f->slot[slot];
-    s.open = false;
-    s.active = false;
+    f->opn[slot] = 0;
+    f->act[slot] = 0;
     std::vector<float>().swap(s.pre_roll);
     std::vector<float>().swap(s.segment);
     f->fill[slot] = 0;
@@ -457,8 +463,8 @@ int cvad_feeder_clear(cvad_feeder *f, int slot) {
     if (slot < 0 || slot >= f->max_streams) return ffail(f, CVAD_E_CAPACITY, "slot id out of range");
     std::lock_guard<std::mutex> lk(f->mu);
     cvad_feeder::Slot &s = f->slot[slot];
-    s.active = false;
-    s.skip = 0;
+    f->act[slot] = 0;
+    f->skp[slot] = 0;
     s.pre_roll.clear();
     s.segment.clear();
     f->fill[slot] = 0;
@@ -467,7 +473,7 @@ int cvad_feeder_clear(cvad_feeder *f, int slot) {
 
 int cvad_feeder_is_active(cvad_feeder *f, int slot) {
     if (!f || slot < 0 || slot >= f->max_streams) return CVAD_E_INVALID;
-    return f->slot[slot].active ? 1 : 0;
+    return f->act[slot] ? 1 : 0;
 }
 
 int64_t cvad_feeder_pending(cvad_feeder *f, int slot) {
@@ -503,13 +509,13 @@ static int feeder_grow_arena(cvad_feeder *f, int64_t need) {
 }
 
 static int feeder_push_locked(cvad_feeder *f, int slot, const void *samples, int64_t n) {
-    cvad_feeder::Slot &s = f->slot[slot];
-    if (!s.open) return ffail(f, CVAD_E_INVALID, "stream is not open");
-    if (s.skip > 0) {
-        const int64_t d = std::min(s.skip, n);
+    if (!f->opn[slot]) return ffail(f, CVAD_E_INVALID, "stream is not open");
+    int64_t &skip = f->skp[slot];
+    if (skip > 0) {
+        const int64_t d = std::min(skip, n);
         samples = static_cast<const unsigned char *>(samples) + (size_t)d * f->es;
         n -= d;
-        s.skip -= d;
+        skip -= d;
         if (n == 0) return CVAD_OK;
     }
     const int64_t have = f->fill[slot];
@@ -556,7 +562,7 @@ int cvad_feeder_push_many(cvad_feeder *f, int n, const int32_t *slots, const voi
     std::lock_guard<std::mutex> lk(f->mu);
     int64_t need = 0;
     for (int i = 0; i < n; ++i) {
-        if (!f->slot[slots[i]].open) return ffail(f, CVAD_E_INVALID, "push_many: a stream is not open");
+        if (!f->opn[slots[i]]) return ffail(f, CVAD_E_INVALID, "push_many: a stream is not open");
         need = std::max(need, f->fill[slots[i]] + n_samples);
     }
     if (const int rc = feeder_grow_arena(f, need)) return rc;
@@ -616,71 +622,106 @@ int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *r) {
     // touches every stream.  Many frames for everybody (a producer that batches) stay one multi-frame step.
     const bool rounds = n > 0 && f->planes;
     if (rounds) {
+        // Round r runs the streams that hold an r-th frame.  Rounds are SUBMITTED back to back (cvad_step_submit: the engine
+        // orders their kernels, the copies of round r + 1 run under the kernel of round r) and collected afterwards, so the
+        // packing of round r + 1 and the unpacking of round r - 1 happen while the GPU works on round r.
         const size_t flen_al = (size_t)f->plane_row;
-        std::vector<int32_t> sub_slots, sub_k;
-        std::vector<float> sub_probs;
-        std::vector<uint8_t> sub_flags, sub_status;
-        std::vector<cvad_event> sub_events;
-        static const bool trace = std::getenv("CVAD_FEEDER_TRACE") != nullptr;     // development aid: per-round timings on stderr
+        struct Round {
+            std::vector<int32_t> slots, k;
+            std::vector<float> probs;
+            std::vector<uint8_t> flags, status;
+            std::vector<cvad_event> events;
+            int nev = 0, ticket = -1;
+        };
+        std::vector<Round> rd((size_t)T);
+        size_t pack_total = 0;
+        int n_rounds = 0;
         for (int r = 0; r < T; ++r) {
-            const auto tr0 = clk::now();
-            sub_slots.clear(); sub_k.clear();
+            Round &q = rd[(size_t)r];
             for (int k = 0; k < n; ++k)
-                if (f->counts[k] > r) { sub_k.push_back(k); sub_slots.push_back(f->ids[k]); }
-            const int nr = (int)sub_k.size();
-            if (nr == 0) break;
+                if (f->counts[k] > r) { q.k.push_back(k); q.slots.push_back(f->ids[k]); }
+            if (q.k.empty()) break;
+            n_rounds = r + 1;
+            if (r > 0) pack_total += q.k.size() * flen_al * f->es;
+        }
+        if (pack_total && (rc = feeder_grow_stage(f, f->cur ^ 1, pack_total))) { f->events.clear(); return rc; }
+        static const bool trace = std::getenv("CVAD_FEEDER_TRACE") != nullptr;     // development aid: per-round timings on stderr
+        auto collect = [&](int r) -> int {
+            Round &q = rd[(size_t)r];
+            const auto tc0 = clk::now();
+            const int rcc = cvad_step_collect(f->eng, q.ticket);
+            q.ticket = -1;
+            if (trace)
+                std::fprintf(stderr, "[feeder] round %d: %d streams, collect %.3f ms\n", r, (int)q.k.size(),
+                             std::chrono::duration<double, std::milli>(clk::now() - tc0).count());
+            if (rcc) return ffail(f, rcc, cvad_last_error(f->eng));
+            const int nr = (int)q.k.size();
+            for (int i = 0; i < nr; ++i) {
+                if (q.status[i]) return ffail(f, CVAD_E_INVALID, "Audio data contains infinite or NaN values");
+                f->probs[(size_t)q.k[i] * T + r] = q.probs[i];
+                f->flags[(size_t)q.k[i] * T + r] = q.flags[i];
+            }
+            for (int i = 0; i < std::min(q.nev, (int)q.events.size()); ++i) {
+                cvad_event ev = q.events[i];
+                ev.stream = q.k[ev.stream];
+                ev.frame = r;
+                f->events.push_back(ev);
+            }
+            return CVAD_OK;
+        };
+        size_t pack_at = 0;
+        int failed = CVAD_OK;
+        for (int r = 0; r < n_rounds && !failed; ++r) {
+            Round &q = rd[(size_t)r];
+            const auto tr0 = clk::now();
+            const int nr = (int)q.k.size();
             const void *audio = f->stage[f->cur];     // plane 0: everybody's first frame
-            int64_t stride = (int64_t)flen_al;
             if (r > 0) {
-                // the r-th frames of the streams that have one, packed into the other pinned buffer
-                if ((rc = feeder_grow_stage(f, f->cur ^ 1, (size_t)nr * flen_al * f->es))) { f->events.clear(); return rc; }
-                unsigned char *dst = f->stage[f->cur ^ 1];
+                // the r-th frames of the streams that have one, packed into the other pinned buffer (its own stretch of
+                // it: the round's copy may still be in flight when the next round is packed)
+                unsigned char *dst = f->stage[f->cur ^ 1] + pack_at;
+                pack_at += (size_t)nr * flen_al * f->es;
                 for (int i = 0; i < nr; ++i)
                     std::memcpy(dst + (size_t)i * flen_al * f->es,
-                                feeder_frame_ptr(f, f->stage[f->cur], n, sub_k[i], r, f->hop), (size_t)f->frame_len * f->es);
+                                feeder_frame_ptr(f, f->stage[f->cur], n, q.k[i], r, f->hop), (size_t)f->frame_len * f->es);
                 audio = dst;
             }
-            sub_probs.assign((size_t)nr, 0.f);
-            sub_flags.assign((size_t)nr, 0);
-            sub_status.assign((size_t)nr, 0);
-            sub_events.resize((size_t)std::max(16, 2 * nr));
-            int nev = 0;
+            q.probs.assign((size_t)nr, 0.f);
+            q.flags.assign((size_t)nr, 0);
+            q.status.assign((size_t)nr, 0);
+            q.events.resize((size_t)std::max(16, 2 * nr));
             cvad_step_args a{};
             a.n_streams = nr;
-            a.slots = sub_slots.data();
+            a.slots = q.slots.data();
             a.audio = audio;
             a.pcm_format = f->pcm_format;
-            a.stream_stride = stride;
+            a.stream_stride = (int64_t)flen_al;
             a.max_frames = 1;
             a.frame_len = f->frame_len;
             a.hop = f->hop;
             a.src_rate = f->src_rate;
-            a.probs_out = sub_probs.data();
-            a.flags_out = sub_flags.data();
-            a.status_out = sub_status.data();
-            a.events_out = sub_events.data();
-            a.max_events = (int32_t)sub_events.size();
-            a.n_events_out = &nev;
+            a.probs_out = q.probs.data();
+            a.flags_out = q.flags.data();
+            a.status_out = q.status.data();
+            a.events_out = q.events.data();
+            a.max_events = (int32_t)q.events.size();
+            a.n_events_out = &q.nev;
             const auto tr1 = clk::now();
-            rc = cvad_step(f->eng, &a);
-            const auto tr2 = clk::now();
+            rc = cvad_step_submit(f->eng, &a, &q.ticket);
             if (trace)
-                std::fprintf(stderr, "[feeder] round %d: %d streams, prepare %.3f ms, cvad_step %.3f ms\n", r, nr,
+                std::fprintf(stderr, "[feeder] round %d: %d streams, prepare %.3f ms, submit %.3f ms\n", r, nr,
                              std::chrono::duration<double, std::milli>(tr1 - tr0).count(),
-                             std::chrono::duration<double, std::milli>(tr2 - tr1).count());
-            if (rc) { f->events.clear(); return ffail(f, rc, cvad_last_error(f->eng)); }
-            for (int i = 0; i < nr; ++i) {
-                if (sub_status[i]) { f->events.clear(); return ffail(f, CVAD_E_INVALID, "Audio data contains infinite or NaN values"); }
-                f->probs[(size_t)sub_k[i] * T + r] = sub_probs[i];
-                f->flags[(size_t)sub_k[i] * T + r] = sub_flags[i];
-            }
-            for (int i = 0; i < std::min(nev, (int)sub_events.size()); ++i) {
-                cvad_event ev = sub_events[i];
-                ev.stream = sub_k[ev.stream];
-                ev.frame = r;
-                f->events.push_back(ev);
-            }
+                             std::chrono::duration<double, std::milli>(clk::now() - tr1).count());
+            if (rc) { q.ticket = -1; failed = ffail(f, rc, cvad_last_error(f->eng)); break; }
+            if (r > 0) failed = collect(r - 1);
         }
+        // the last round (and, after a failure, whatever is still in flight: its buffers must outlive the copies)
+        for (int r = 0; r < n_rounds; ++r)
+            if (rd[(size_t)r].ticket >= 0) {
+                const int rcc = collect(r);
+                if (!failed) failed = rcc;
+            }
+        if (failed) { f->events.clear(); return failed; }
         std::sort(f->events.begin(), f->events.end(), [](const cvad_event &x, const cvad_event &y) {
             if (x.stream != y.stream) return x.stream < y.stream;
             if (x.frame != y.frame) return x.frame < y.frame;

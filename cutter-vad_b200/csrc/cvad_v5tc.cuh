@@ -812,12 +812,19 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
         uint32_t acc_phase = 0, gate_phase = 0;
         const int flen = p.frame_len < 512 ? p.frame_len : 512;
-        if (FUSED) griddep_wait();
-        CVAD_CHAIN_NS(2);
+        // (Measured and dropped: a rehearsal trip of the tile's first code -- tile_live, the slot data of warp 0 -- ahead of
+        // griddepcontrol.wait, to take its instruction and parameter-bank misses off the 1.1 us between the resolved
+        // dependency and the tile's start: the CTAs that matter are scheduled only 0.9 us before the dependency resolves
+        // and the rehearsal itself took longer than that; tools/dev/chain_timeline.py.)
+        if (FUSED) {
+            griddep_wait();
+            CVAD_CHAIN_NS(2);
+        }
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
             int my_slot, my_valid;
             const bool live = tile_live(p, frame, st, lane, &my_slot, &my_valid);
+            CVAD_CHAIN_NS(6);
             // chained steps arrive without a memset in front of them: the tile clears its streams' status words itself
             // (one tile per stream when max_frames == 1), ordered before the loader's atomicOr by the barrier below
             if (FUSED && p.status_zero && warp == 0 && st * kTile + lane < p.n_streams) p.status[st * kTile + lane] = 0u;
@@ -850,6 +857,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 }
             }
             if (H16 && warp >= 1 && warp <= 6) amax[(warp - 1) * kTile + lane] = 0u;
+            CVAD_CHAIN_NS(7);
             epi_bar();
             const bool dbg = DBG && tile == 0;
             const bool first_tile = tile == (int)blockIdx.x && tid == 0;
@@ -1569,22 +1577,21 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 CVAD_CHAIN_NS(4);
             }
         }
-        if (FUSED && p.step_ctr && tid == 0) {
-            // chained steps: the last CTA counts the step as completed (read by the next step's early CTAs, above)
-            if (atomicAdd(p.step_ctr + 1, 1) == (int)gridDim.x - 1) {
-                p.step_ctr[1] = 0;
-                atomicAdd(p.step_ctr, 1);
-            }
-        }
-        if (FUSED && p.ev_ctr && tid == 0) {
+        if (FUSED && (p.ev_ctr || p.step_ctr) && tid == 0) {
             // chained steps: events were counted in the engine's own counter (ev_ctr[0]); the last CTA to take a ticket
-            // publishes the total and leaves counter and ticket at zero for the next step -- no memset between the
-            // kernels.  No fence: every event atomicAdd of this CTA returned its index to warp 0 before the barrier
-            // above, i.e. it has been performed at L2, where the ticket and the exchange below are performed too.
-            if (atomicAdd(p.ev_ctr + 1, 1) == (int)gridDim.x - 1) {
-                const int total = atomicExch(p.ev_ctr, 0);
-                if (p.n_events) *p.n_events = total;
-                p.ev_ctr[1] = 0;
+            // publishes the total, leaves counter and ticket at zero for the next step -- no memset between the kernels --
+            // and counts the step as completed (read by the next step's early CTAs, above).  ONE ticket for both: the
+            // atomic's round trip (~0.4 us with 128 CTAs on one address) sits between the tile and the CTA's exit.
+            // No fence: every event atomicAdd of this CTA returned its index to warp 0 before the barrier above, i.e.
+            // it has been performed at L2, where the ticket and the exchange below are performed too.
+            int *ticket = p.ev_ctr ? p.ev_ctr + 1 : p.step_ctr + 1;
+            if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+                if (p.ev_ctr) {
+                    const int total = atomicExch(p.ev_ctr, 0);
+                    if (p.n_events) *p.n_events = total;
+                }
+                *ticket = 0;
+                if (p.step_ctr) atomicAdd(p.step_ctr, 1);
             }
         }
     }

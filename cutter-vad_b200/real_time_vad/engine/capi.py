@@ -79,7 +79,7 @@ class FeederResult(C.Structure):
 
 _lib = None
 _dev_lib = None
-DEV_EXPORTS = ("cvad_dev_last_error", "cvad_tc_probe", "cvad_tc_probe_mn", "cvad_tc_rate", "cvad_tc_rate2", "cvad_bulk_rate")
+DEV_EXPORTS = ("cvad_dev_last_error", "cvad_tc_probe", "cvad_tc_probe_mn", "cvad_tc_rate", "cvad_tc_rate_mn", "cvad_bulk_rate")
 
 
 def dev_lib() -> C.CDLL:
@@ -95,7 +95,7 @@ def dev_lib() -> C.CDLL:
         L.cvad_tc_probe.argtypes = [i32, vp, vp, vp]
         L.cvad_tc_probe_mn.argtypes = [i32, vp, vp, vp]
         L.cvad_tc_rate.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp]
-        L.cvad_tc_rate2.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, vp]
+        L.cvad_tc_rate_mn.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, vp]
         L.cvad_bulk_rate.argtypes = [i32, i32, i32, i32, i32, C.c_size_t, vp]
         _dev_lib = L
     return _dev_lib

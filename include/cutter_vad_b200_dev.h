@@ -28,7 +28,7 @@ int cvad_tc_rate(int device, int M, int N, int reps, int a_tiles, int n_acc, int
 int cvad_tc_probe_mn(int device, const uint16_t *a_bf16, const uint16_t *b_bf16, float *d_out);
 
 /* cvad_tc_rate with the B operand MN-major SWIZZLE_64B when b_mn != 0 (N % 32 == 0). */
-int cvad_tc_rate2(int device, int M, int N, int reps, int a_tiles, int n_acc, int grid, int b_mn, long long *out2);
+int cvad_tc_rate_mn(int device, int M, int N, int reps, int a_tiles, int n_acc, int grid, int b_mn, long long *out2);
 
 /* Measurement hook: one thread per CTA streams `tiles` cp.async.bulk copies of tile_bytes through a ring of `depth`
    slots from a src_bytes buffer (L2-resident on the measured run); out2[0] = SM cycles on CTA 0, out2[1] = tiles. */

@@ -33,16 +33,16 @@ for i in range(64):
 eng.sync()
 out = np.zeros(512, np.int64)
 eng._check(L.cvad_read_profile_chain(eng._h, out.ctypes.data))
-m = out.reshape(8, 8, 8)[:, :3, :6]                      # [step % 8][cta 0 / 64 / last][mark]
+m = out.reshape(8, 8, 8)[:, :3, :8]                      # [step % 8][cta 0 / 64 / last][mark]
 order = np.argsort(m[:, 0, 0])                           # steps in time order
 m = m[order]
 t0 = m[0, 0, 0]
-names = ["entry", "prologue", "dep resolved", "tile start", "tile end", "exit"]
+names = ["entry", "prologue", "dep resolved", "tile start", "tile end", "exit", "tile_live done", "at first barrier"]
 print("ns since the first listed step's CTA-0 entry; rows = consecutive steps")
 for b, nm in enumerate(("CTA 0 (scheduled early)", "CTA 64", "last CTA")):
     print(nm)
     for k in range(8):
-        print("   ", "  ".join(f"{names[j]} {int(m[k, b, j] - t0):8d}" for j in range(6)))
+        print("   ", "  ".join(f"{names[j]} {int(m[k, b, j] - t0):8d}" for j in (0, 1, 2, 6, 7, 3, 4, 5)))
 per = np.diff(m[:, 2, 4]).mean()
 print(f"step period (tile end to tile end, last CTA): {per:.0f} ns; tile {np.mean(m[:, 2, 4] - m[:, 2, 3]):.0f} ns; "
       f"previous step's tile end -> this step's tile start (last CTA): {np.mean(m[1:, 2, 3] - m[:-1, 2, 4]):.0f} ns; "

@@ -14,7 +14,7 @@ for M, n_acc in ((128, 2), (64, 2)):
     for N in (32, 64, 96):
         r = []
         for mn in (0, 1):
-            rc = L.cvad_tc_rate2(0, M, N, 512, 8, n_acc, 1, mn, out.ctypes.data)
+            rc = L.cvad_tc_rate_mn(0, M, N, 512, 8, n_acc, 1, mn, out.ctypes.data)
             assert rc == 0, L.cvad_dev_last_error()
             r.append(out[0] / out[1])
         print(f"{M:3d} {N:3d} {n_acc:3d} {r[0]:8.1f} {r[1]:8.1f}")
