@@ -135,6 +135,10 @@ struct cvad_feeder {
     // that round 0 is ONE dense host-to-device copy)
     bool planes = false;
     int64_t plane_row = 0;
+    // planes r >= 1 are DENSE: they hold only the streams that have an r-th frame, in stream order, so that round r's
+    // input is plane r as it stands.  plane_off[r] = first row of plane r, ppos[(r - 1) n + k] = row of stream k inside it
+    int64_t plane_off[5] = {0, 0, 0, 0, 0};
+    std::vector<int32_t> ppos;
 };
 
 namespace {
@@ -153,14 +157,29 @@ inline float feeder_sample(const cvad_feeder *f, const unsigned char *p, size_t 
 }
 
 // numpy's `np.where(np.abs(f) > 0.01, f, 0.0)` on float32 data (audio.py:117-118): the threshold is float32(0.01)
+// One loop per sample format and gate setting, branch-free inside (the compiler vectorises them; the per-sample format
+// test of feeder_sample kept the 480-sample loop scalar: ~0.5 us per frame, most of the segment-assembly phase).
+template <int FMT, bool GATE>
+inline void feeder_gate_loop(const unsigned char *__restrict__ src, int n, float *__restrict__ d) {
+    for (int k = 0; k < n; ++k) {
+        float v;
+        if (FMT == CVAD_PCM_F32) v = reinterpret_cast<const float *>(src)[k];
+        else if (FMT == CVAD_PCM_S16_32767) v = (float)reinterpret_cast<const int16_t *>(src)[k] / 32767.0f;
+        else v = (float)reinterpret_cast<const int16_t *>(src)[k] / 32768.0f;
+        d[k] = (!GATE || std::fabs(v) > 0.01f) ? v : 0.0f;
+    }
+}
 inline void feeder_gate_append(const cvad_feeder *f, const cvad_feeder::Slot &s, const unsigned char *src, int n,
                                std::vector<float> &dst) {
     const size_t o = dst.size();
     dst.resize(o + (size_t)n);
     float *d = dst.data() + o;
-    for (int k = 0; k < n; ++k) {
-        const float v = feeder_sample(f, src, (size_t)k);
-        d[k] = (!s.denoise || std::fabs(v) > 0.01f) ? v : 0.0f;
+    const bool g = s.denoise;
+    switch (f->pcm_format) {
+        case CVAD_PCM_F32: g ? feeder_gate_loop<CVAD_PCM_F32, true>(src, n, d) : feeder_gate_loop<CVAD_PCM_F32, false>(src, n, d); break;
+        case CVAD_PCM_S16_32767:
+            g ? feeder_gate_loop<CVAD_PCM_S16_32767, true>(src, n, d) : feeder_gate_loop<CVAD_PCM_S16_32767, false>(src, n, d); break;
+        default: g ? feeder_gate_loop<CVAD_PCM_S16_32768, true>(src, n, d) : feeder_gate_loop<CVAD_PCM_S16_32768, false>(src, n, d); break;
     }
 }
 
@@ -188,7 +207,10 @@ int feeder_grow_stage(cvad_feeder *f, int which, size_t bytes) {
 // pending samples into a dense [n][row] block (split_into_frames' input, audio.py:164-190) and drop
 // what the step will consume from the arena (leftovers shorter than a hop stay for the next step).
 inline const unsigned char *feeder_frame_ptr(const cvad_feeder *f, const unsigned char *stage, int n, int k, int j, int64_t step_len) {
-    if (f->planes) return stage + (((size_t)j * (size_t)n + (size_t)k) * (size_t)f->plane_row) * f->es;
+    if (f->planes) {
+        const size_t r = j == 0 ? (size_t)k : (size_t)f->plane_off[j] + (size_t)f->ppos[(size_t)(j - 1) * (size_t)n + (size_t)k];
+        return stage + r * (size_t)f->plane_row * f->es;
+    }
     return stage + ((size_t)k * (size_t)f->row + (size_t)j * (size_t)step_len) * f->es;
 }
 
@@ -224,7 +246,19 @@ int feeder_gather(cvad_feeder *f, bool allow_planes = false) {
     f->row = row;
     f->planes = allow_planes && !mixed && tmax >= 2 && tmax <= 4;
     f->plane_row = ((int64_t)f->frame_len + 7) & ~(int64_t)7;
-    const size_t stage_bytes = f->planes ? (size_t)tmax * (size_t)n * (size_t)f->plane_row * f->es : (size_t)n * (size_t)row * f->es;
+    size_t plane_rows = (size_t)n;
+    if (f->planes) {
+        f->ppos.assign((size_t)(tmax - 1) * (size_t)n, 0);
+        f->plane_off[0] = 0;
+        for (int j = 1; j < tmax; ++j) {
+            f->plane_off[j] = (int64_t)plane_rows;
+            int32_t at = 0;
+            for (int k = 0; k < n; ++k)
+                if (f->counts[k] > j) f->ppos[(size_t)(j - 1) * (size_t)n + (size_t)k] = at++;
+            plane_rows += (size_t)at;
+        }
+    }
+    const size_t stage_bytes = f->planes ? plane_rows * (size_t)f->plane_row * f->es : (size_t)n * (size_t)row * f->es;
     int rc = feeder_grow_stage(f, f->cur, stage_bytes);
     if (rc) return rc;
     unsigned char *stage = f->stage[f->cur];
@@ -238,7 +272,7 @@ int feeder_gather(cvad_feeder *f, bool allow_planes = false) {
             const int64_t need = mixed ? used : (int64_t)(f->counts[k] - 1) * f->hop + f->frame_len;
             if (f->planes) {
                 for (int j = 0; j < f->counts[k]; ++j)
-                    std::memcpy(stage + (((size_t)j * (size_t)n + (size_t)k) * (size_t)f->plane_row) * f->es,
+                    std::memcpy(const_cast<unsigned char *>(feeder_frame_ptr(f, stage, n, k, j, f->hop)),
                                 src + (size_t)j * (size_t)f->hop * f->es, (size_t)f->frame_len * f->es);
             } else {
                 std::memcpy(stage + (size_t)k * (size_t)row * f->es, src, (size_t)need * f->es);
@@ -634,7 +668,6 @@ int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *r) {
             int nev = 0, ticket = -1;
         };
         std::vector<Round> rd((size_t)T);
-        size_t pack_total = 0;
         int n_rounds = 0;
         for (int r = 0; r < T; ++r) {
             Round &q = rd[(size_t)r];
@@ -642,9 +675,7 @@ int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *r) {
                 if (f->counts[k] > r) { q.k.push_back(k); q.slots.push_back(f->ids[k]); }
             if (q.k.empty()) break;
             n_rounds = r + 1;
-            if (r > 0) pack_total += q.k.size() * flen_al * f->es;
         }
-        if (pack_total && (rc = feeder_grow_stage(f, f->cur ^ 1, pack_total))) { f->events.clear(); return rc; }
         static const bool trace = std::getenv("CVAD_FEEDER_TRACE") != nullptr;     // development aid: per-round timings on stderr
         auto collect = [&](int r) -> int {
             Round &q = rd[(size_t)r];
@@ -669,23 +700,13 @@ int cvad_feeder_step(cvad_feeder *f, cvad_feeder_result *r) {
             }
             return CVAD_OK;
         };
-        size_t pack_at = 0;
         int failed = CVAD_OK;
         for (int r = 0; r < n_rounds && !failed; ++r) {
             Round &q = rd[(size_t)r];
             const auto tr0 = clk::now();
             const int nr = (int)q.k.size();
-            const void *audio = f->stage[f->cur];     // plane 0: everybody's first frame
-            if (r > 0) {
-                // the r-th frames of the streams that have one, packed into the other pinned buffer (its own stretch of
-                // it: the round's copy may still be in flight when the next round is packed)
-                unsigned char *dst = f->stage[f->cur ^ 1] + pack_at;
-                pack_at += (size_t)nr * flen_al * f->es;
-                for (int i = 0; i < nr; ++i)
-                    std::memcpy(dst + (size_t)i * flen_al * f->es,
-                                feeder_frame_ptr(f, f->stage[f->cur], n, q.k[i], r, f->hop), (size_t)f->frame_len * f->es);
-                audio = dst;
-            }
+            // plane r: the r-th frames of exactly the streams of this round, in their order (feeder_gather)
+            const void *audio = f->stage[f->cur] + (size_t)f->plane_off[r] * flen_al * f->es;
             q.probs.assign((size_t)nr, 0.f);
             q.flags.assign((size_t)nr, 0);
             q.status.assign((size_t)nr, 0);

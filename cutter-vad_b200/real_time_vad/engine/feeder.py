@@ -143,14 +143,17 @@ class StreamFeeder:
         ev = _view(r.events, _EVENT_DT, int(r.n_events))
         events = ev.tolist()                      # [(stream, slot, frame, kind, stream_frame)] as Python ints
         deliveries: List[Delivery] = []
-        for d in _view(r.deliveries, _DELIV_DT, int(r.n_deliveries)):
-            frame = _view(int(d["frame"]), np.float32, int(d["frame_len"])).copy() if d["frame"] else None
-            seg = _view(int(d["segment"]), np.float32, int(d["segment_len"])).copy() if d["segment"] else None
-            raw = _view(int(d["raw"]), self.dtype, int(d["raw_len"])).copy() if d["raw"] else None
-            if d["flags"] & capi.FLAG_ENDED and seg is None and not d["raw"]:
+        # records as plain tuples (one C loop), payloads as one memcpy each: at 10,000 streams field access on numpy void
+        # scalars and view -> copy pairs were most of this function
+        sa, fb, isz = C.string_at, np.frombuffer, self.dtype().itemsize
+        for (slot, stream, step_frame, fl, frame_p, seg_p, seg_len, frame_len, prob, raw_p, raw_len) in \
+                _view(r.deliveries, _DELIV_DT, int(r.n_deliveries)).tolist():
+            frame = fb(sa(frame_p, frame_len * 4), np.float32) if frame_p else None
+            seg = fb(sa(seg_p, seg_len * 4), np.float32) if seg_p and seg_len > 0 else (np.zeros(0, np.float32) if seg_p else None)
+            raw = fb(sa(raw_p, raw_len * isz), self.dtype) if raw_p else None
+            if fl & capi.FLAG_ENDED and seg is None and not raw_p:
                 seg = np.zeros(0, np.float32)
-            deliveries.append(Delivery(int(d["slot"]), int(d["stream"]), int(d["step_frame"]), int(d["flags"]),
-                                       float(d["prob"]), frame, seg, raw))
+            deliveries.append(Delivery(slot, stream, step_frame, fl, prob, frame, seg, raw))
         raw_block = None
         if want_raw and n:
             raw_block = _view(r.raw, self.dtype, n * int(r.raw_stride)).reshape(n, int(r.raw_stride)).copy()
