@@ -904,7 +904,8 @@ int launch_step(cvad_engine *e, const cvad_step_args *a, unsigned int *d_status,
             if (e->math == CVAD_MATH_TC16) {
                 p.w_fe_h = e->w_fe_h; p.w_rec_h = e->w_rec_h;
                 std::memcpy(p.tc16_inv_w, e->tc16_inv_w, sizeof(p.tc16_inv_w));
-                CU_TRY(e, cudaLaunchKernelEx(&cfg, cvad::tc5::v5tc_frontend_kernel<false, true, true>, p));
+                if (p.prof) CU_TRY(e, cudaLaunchKernelEx(&cfg, cvad::tc5::v5tc_frontend_kernel<false, true, true, true>, p));
+                else CU_TRY(e, cudaLaunchKernelEx(&cfg, cvad::tc5::v5tc_frontend_kernel<false, true, true, false>, p));
             } else {
                 CU_TRY(e, cudaLaunchKernelEx(&cfg, cvad::tc5::v5tc_frontend_kernel<false, true, false>, p));
             }
@@ -1352,6 +1353,8 @@ int cvad_create(const float *weights, size_t n_weight_floats, int model_version,
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kFeSmemTC));
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cvad::tc5::kFusedSmemTC));
+    CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<false, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kFusedSmemTC));
     CR_TRY(cudaFuncSetAttribute(cvad::tc5::v5tc_frontend_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cvad::tc5::kFusedSmemTC));

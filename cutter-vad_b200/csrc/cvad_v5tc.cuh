@@ -253,13 +253,15 @@ __device__ __forceinline__ long long gtime_ns() {
 #else
 #define CVAD_ISSUE_ROLL
 #endif
-#define CVAD_PROF_NS(k) do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(k)] = gtime_ns(); } while (0)
+// The marks compile away in the kernel build that runs when no profile was asked for (PROF = false: the ~45 tests of
+// p.prof, each a parameter-bank read and a branch on the epilogue warps' path, were ~3 % of the kernel's stall samples).
+#define CVAD_PROF_NS(k) do { if (PROF && p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(k)] = gtime_ns(); } while (0)
 // chained steps under cvad_set_profile: global-timer marks of CTAs 0, 64 and the last one, kept for the last 8 steps
 // (prof[128 + 64 (step_seq % 8) + 8 b + k], k: 0 entry, 1 prologue done, 2 grid dependency resolved, 3 tile start, 4 tile end, 5 exit)
-#define CVAD_CHAIN_NS(k) do { if (FUSED && p.prof && p.step_ctr && threadIdx.x == 0) {                                       \
+#define CVAD_CHAIN_NS(k) do { if (PROF && FUSED && p.prof && p.step_ctr && threadIdx.x == 0) {                                       \
         const int b_ = blockIdx.x == 0 ? 0 : (blockIdx.x == 64 ? 1 : (blockIdx.x == gridDim.x - 1 ? 2 : -1));                \
         if (b_ >= 0) p.prof[128 + 64 * (p.step_seq & 7) + 8 * b_ + (k)] = gtime_ns(); } } while (0)
-#define CVAD_PROF(k) do { if (p.prof && blockIdx.x == 0 && first_tile) p.prof[(k)] = clock64(); } while (0)
+#define CVAD_PROF(k) do { if (PROF && p.prof && blockIdx.x == 0 && first_tile) p.prof[(k)] = clock64(); } while (0)
 
 // LSTM gate products of one weight tile (part wp) in the fused kernel: all six products of a MAC go to ONE
 // accumulator (TMEM has no room for column groups next to the front end's); b0 = activation part 0, parts 4096 B apart
@@ -290,16 +292,33 @@ __device__ __forceinline__ void issue_gate(int wp, uint32_t a_addr, uint32_t b0,
 // probability), half the tensor-pipe and shared-memory-port time.  Elements far below the row maximum fall into
 // FP16's subnormal range and keep an ABSOLUTE error of 2^-25 of the scaled unit, i.e. 2^-39 of the maximum.
 struct Scale { float s, inv; };
-// scale for an operand whose largest magnitude has the float bit pattern `max_bits` (non-negative)
+// scale for an operand whose largest magnitude has the float bit pattern `max_bits` (non-negative): the power of two that
+// brings it to [2^14, 2^15), capped at 2^125.  An all-zero (or subnormal) operand gets the cap: zeros stay zeros and the
+// products are unscaled by 2^-125 again -- no special case (these few integer operations run ~90 times per thread and
+// tile; with a branch for E == 0 and one load per value they were 9 % of the kernel's stall samples).
 __device__ __forceinline__ Scale scale_from_max(uint32_t max_bits) {
-    const uint32_t E = max_bits >> 23;
+    const uint32_t se = min(268u - (max_bits >> 23), 252u);    // 2^(14 - (E - 127)), biased
     Scale r;
-    if (E == 0u) { r.s = 1.f; r.inv = 1.f; return r; }       // all zero (or subnormal): nothing to scale
-    uint32_t se = 268u - E;                                    // 2^(14 - (E - 127)), biased
-    se = se > 252u ? 252u : se;
     r.s = __uint_as_float(se << 23);
     r.inv = __uint_as_float((254u - se) << 23);
     return r;
+}
+// the same for eight consecutive streams (a 32-byte aligned stretch of the per-stream maxima): two 16-byte loads
+__device__ __forceinline__ void amax_load8(const uint32_t *a, uint32_t (&m)[8]) {
+    const uint4 lo = *reinterpret_cast<const uint4 *>(a), hi = *reinterpret_cast<const uint4 *>(a + 4);
+    m[0] = lo.x; m[1] = lo.y; m[2] = lo.z; m[3] = lo.w; m[4] = hi.x; m[5] = hi.y; m[6] = hi.z; m[7] = hi.w;
+}
+__device__ __forceinline__ void scales8(const uint32_t *a, float (&s8)[8]) {
+    uint32_t m[8];
+    amax_load8(a, m);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s8[e] = scale_from_max(m[e]).s;
+}
+__device__ __forceinline__ void inv_scales8(const uint32_t *a, float mul, float (&i8)[8]) {
+    uint32_t m[8];
+    amax_load8(a, m);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) i8[e] = scale_from_max(m[e]).inv * mul;
 }
 constexpr float kHScale = 16384.f, kHInv = 1.f / 16384.f;     // |h| < 1: static scale of the recurrent operand
 // two values at once: word j holds part j of a (low half) and of b (high half)
@@ -473,7 +492,7 @@ struct Ring {
 // FUSED (max_frames == 1): the same CTA also runs the LSTM step, decoder and state machine of its 32 streams
 // (the W_hh.h products are issued while the frame loader runs, the W_ih.x products after encoder.3).
 // H16 (CVAD_MATH_TC16, FUSED only): FP16 two-way operand split with per-stream dynamic scaling, three products per MAC.
-template <bool DBG, bool FUSED, bool H16 = false>
+template <bool DBG, bool FUSED, bool H16 = false, bool PROF = true>
 __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5Step p) {
     static_assert(!H16 || !DBG, "the debug dump runs the BF16-split build");
     // the FP16 build's activation region holds two parts instead of three: the 32 KB go to two more ring slots (the weight
@@ -494,7 +513,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
     uint64_t *bars = reinterpret_cast<uint64_t *>(dpart + (FUSED ? 128 : 0));
     uint64_t *full = bars, *empty = bars + RING, *act_ready = bars + 2 * RING, *acc_ready = act_ready + 1,
              *h_ready = acc_ready + 1, *gate_ready = h_ready + 1;          // FUSED: gate_ready[4], one per LSTM gate
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gate_ready + (FUSED ? 4 : 0));
+    // (an odd number of barriers is padded by one: the words behind them -- the per-stream maxima above all -- are read
+    // with 16-byte loads)
+    constexpr int kBars = 2 * RING + 3 + (FUSED ? 4 : 0);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kBars + (kBars & 1));
     int *s_slot = reinterpret_cast<int *>(tmem_slot + 4);
     int *s_valid = s_slot + kTile;
     double *s_thr = reinterpret_cast<double *>(s_valid + kTile);             // FUSED: start_p[32], end_p[32]
@@ -1033,8 +1055,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 const int b = 32 * q + lane, i0 = 8 * cg;
                 const float iw = p.tc16_inv_w[0];
                 float inv[8], mag[3][8], mx[8];
+                inv_scales8(amax + i0, iw, inv);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { inv[e] = scale_from_max(amax[i0 + e]).inv * iw; mx[e] = 0.f; }
+                for (int e = 0; e < 8; ++e) mx[e] = 0.f;
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
                     const int c0 = t * 32 + i0;
@@ -1061,8 +1084,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 CVAD_PROF(18);
                 epi_bar();
                 CVAD_PROF(19);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) inv[e] = scale_from_max(amax[kTile + i0 + e]).s;
+                scales8(amax + kTile + i0, inv);
                 if constexpr (BMN) {
                     unsigned char *dst = act + tc::mn64_offset((uint32_t)i0, (uint32_t)b, 512u, 1536u);
 #pragma unroll
@@ -1122,8 +1144,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 const float bias = __ldg(p.b_fe + o), iw = p.tc16_inv_w[1];
                 const float wn0 = __ldg(p.nyq_w + 4 * o), wn1 = __ldg(p.nyq_w + 4 * o + 1), wn2 = __ldg(p.nyq_w + 4 * o + 2);
                 float sc[8], v[3][8], mx[8];
+                inv_scales8(amax + kTile + i0, iw, sc);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { sc[e] = scale_from_max(amax[kTile + i0 + e]).inv * iw; mx[e] = 0.f; }
+                for (int e = 0; e < 8; ++e) mx[e] = 0.f;
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
                     const int c0 = t * 32 + i0;
@@ -1144,8 +1167,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 }
                 amax_push_n<8>(&amax[2 * kTile + i0], 1, mx, lane);
                 epi_bar();
-#pragma unroll
-                for (int e = 0; e < 8; ++e) sc[e] = scale_from_max(amax[2 * kTile + i0 + e]).s;
+                scales8(amax + 2 * kTile + i0, sc);
                 if constexpr (BMN) {
                     unsigned char *dst = act + tc::mn64_offset((uint32_t)i0, (uint32_t)o, 512u, 1536u);
 #pragma unroll
@@ -1204,8 +1226,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 const int o = 16 * q + (lane & 15), i0 = 8 * cg;
                 const float bias = __ldg(p.b_fe + 128 + o), iw = p.tc16_inv_w[2];
                 float sc[8], v[2][8], mx[8];
+                inv_scales8(amax + 2 * kTile + i0, iw, sc);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { sc[e] = scale_from_max(amax[2 * kTile + i0 + e]).inv * iw; mx[e] = 0.f; }
+                for (int e = 0; e < 8; ++e) mx[e] = 0.f;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     const int c0 = t * 32 + i0;
@@ -1223,8 +1246,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 amax_push_n<8>(&amax[3 * kTile + i0], 1, mx, lane);
                 epi_bar();
                 if (lane < 16) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) sc[e] = scale_from_max(amax[3 * kTile + i0 + e]).s;
+                    scales8(amax + 3 * kTile + i0, sc);
                     if constexpr (BMN) {
                         unsigned char *dst = act + tc::mn64_offset((uint32_t)i0, (uint32_t)o, 512u, 1024u);
 #pragma unroll
@@ -1280,17 +1302,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 tmem_ld8(lane_addr + kColMain + c0, m);
                 tmem_ld8_corr(lane_addr + kColCorr + c0, cr);
                 tmem_wait_ld();
+                float si[8];
+                inv_scales8(amax + 3 * kTile + c0, iw, si);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float a = fmaxf((m[e] + cr[e]) * (scale_from_max(amax[3 * kTile + c0 + e]).inv * iw) + bias, 0.f);
+                    const float a = fmaxf((m[e] + cr[e]) * si[e] + bias, 0.f);
                     v[e] = lane < 16 ? a : 0.f;
                 }
                 amax_push_n<8>(&amax[4 * kTile + c0], 1, v, lane);
                 epi_bar();
                 if (lane < 16) {
                     if constexpr (BMN) {
+                        scales8(amax + 4 * kTile + c0, si);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] *= scale_from_max(amax[4 * kTile + c0 + e]).s;
+                        for (int e = 0; e < 8; ++e) v[e] *= si[e];
                         store_row8_mn(act + tc::mn64_offset((uint32_t)c0, (uint32_t)o, 512u, 512u), kE2Part, v);
                     } else {
 #pragma unroll
@@ -1335,17 +1360,18 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                 tmem_ld8(lane_addr + kColMain + c0, m);
                 tmem_ld8_corr(lane_addr + kColCorr + c0, cr);
                 tmem_wait_ld();
+                float si[8];
+                inv_scales8(amax + 4 * kTile + c0, iw, si);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    v[e] = fmaxf((m[e] + cr[e]) * (scale_from_max(amax[4 * kTile + c0 + e]).inv * iw) + bias, 0.f);
-                }
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf((m[e] + cr[e]) * si[e] + bias, 0.f);
                 amax_push_n<8>(&amax[5 * kTile + c0], 1, v, lane);
                 tc::fence_before_sync();   // the W_ih accumulators reuse these TMEM columns
                 epi_bar();
                 if constexpr (FUSED) {
                     // [x0 | x1] = N atoms 0 and 1, K groups 1,024 B apart
+                    scales8(amax + 5 * kTile + c0, si);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] *= scale_from_max(amax[5 * kTile + c0 + e]).s;
+                    for (int e = 0; e < 8; ++e) v[e] *= si[e];
                     store_row8_mn(act + tc::mn64_offset((uint32_t)c0, (uint32_t)o, 512u, 1024u), 512u, v);
                 } else {
                     // two-kernel form: x goes to HBM as the recurrent kernel's operand, scaled like the h it will sit
@@ -1403,8 +1429,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     // operations in the same order per element as the all-at-once form below (bit-identical).
                     const float ih_w = p.tc16_inv_w[5], hh = kHInv * p.tc16_inv_w[6];
                     float ix[8], ga[2][8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) ix[e] = scale_from_max(amax[5 * kTile + i0 + e]).inv * ih_w;
+                    inv_scales8(amax + 5 * kTile + i0, ih_w, ix);
 #pragma unroll
                     for (int gi = 0; gi < 4; ++gi) {
                         mbar_wait(&gate_ready[gi], gate_phase);
@@ -1616,6 +1641,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
 // w0.x1 + w1.x0.  W_ih and W_hh share one weight scale (pack_v5_tc16).
 template <bool H16>
 __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_recurrent_kernel(const V5Step p) {
+    constexpr bool PROF = true;
     constexpr int NP = H16 ? 2 : 3;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space

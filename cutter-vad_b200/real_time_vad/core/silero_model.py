@@ -406,12 +406,32 @@ class VADProcessor(BaseModel):
     # reference streams frame by frame) and the work that is redone when a callback raises
     _BATCH_FRAMES = 512
 
-    def process_audio_batched(self, audio: np.ndarray, frame_size: int, hop_size: int) -> Iterator[ProcessingResult]:
+    def process_audio_batched(self, audio: np.ndarray, frame_size: int, hop_size: int,
+                              src_rate: int = 16000) -> Iterator[ProcessingResult]:
         """All frames `audio[j*hop : j*hop+frame_size]` through `cvad_step` on this stream's model session slot, up to
         `_BATCH_FRAMES` frames per step.  Yields one ProcessingResult per frame, in order, equal to what
         `process_frame` would have returned; callbacks run between yields.  If the consumer stops early -- a callback
         raised (vad_wrapper.py:470-476 aborts the call at that frame) -- the stream is put back where the reference
-        leaves it: LSTM state and counters after the frame that raised, nothing later."""
+        leaves it: LSTM state and counters after the frame that raised, nothing later.
+
+        `src_rate` 8000 / 24000 / 48000 (opt-in, VADWrapper.process_audio_data(..., input_sample_rate=...)): `audio` is
+        at that rate, frame_size == hop_size == 512 * src_rate / 16000 source samples, and every chunk is resampled to
+        one 512-sample model frame ON THE GPU (AudioUtils.resample_audio per chunk, utils/audio.py:19-55 -- the step the
+        reference's wrapper leaves as a placeholder, vad_wrapper.py:619-624).  Callback payloads are 16 kHz audio made
+        from the same chunks with the reference's own resampler, only for frames that reach a payload."""
+        if src_rate != 16000:
+            if src_rate not in (8000, 24000, 48000):
+                raise ValueError("src_rate must be 8000, 16000, 24000 or 48000")
+            if frame_size != hop_size or frame_size != 512 * src_rate // 16000:
+                raise ValueError("resampled input is framed in chunks of 512 * src_rate / 16000 samples")
+        rate_kw = {} if src_rate == 16000 else {"src_rate": src_rate}
+
+        def payload_frame(lo: int) -> np.ndarray:
+            f = audio[lo: lo + frame_size]
+            if src_rate != 16000:
+                f = AudioUtils.resample_audio(f, src_rate, 16000).astype(np.float32)
+            return AudioUtils.denoise_audio(f) if gate else (f.copy() if src_rate == 16000 else f)
+
         sess = self.model.session
         n_frames = (len(audio) - frame_size) // hop_size + 1
         if n_frames < 0:
@@ -438,7 +458,7 @@ class VADProcessor(BaseModel):
                 try:
                     lo = first * hop_size
                     r = eng.step(audio[None, lo:lo + (count - 1) * hop_size + frame_size], slots=[slot], n_frames=[count],
-                                 max_frames=count, frame_len=frame_size, hop=hop_size)
+                                 max_frames=count, frame_len=frame_size, hop=hop_size, **rate_kw)
                     if r.status[0]:
                         raise AudioProcessingError("Audio data contains infinite or NaN values")
                     h, c, sm_out, _ = eng.get_state(slot)
@@ -482,8 +502,7 @@ class VADProcessor(BaseModel):
                         hit = p >= start_p
                         d["recent_start_frames"].append(hit)
                         if hit:
-                            frame = audio[lo: lo + frame_size]
-                            d["voice_buffer"].append(AudioUtils.denoise_audio(frame) if gate else frame.copy())
+                            d["voice_buffer"].append(payload_frame(lo))
                             if fl & 1:
                                 segment = list(d["voice_buffer"])
                                 d["voice_buffer"].clear()
@@ -491,9 +510,7 @@ class VADProcessor(BaseModel):
                         else:
                             d["voice_buffer"].clear()
                     else:
-                        frame = audio[lo: lo + frame_size]
-                        if gate:
-                            frame = AudioUtils.denoise_audio(frame)
+                        frame = payload_frame(lo)
                         segment.append(frame)
                         pcm = frame.tobytes()
                         d["recent_end_frames"].append(p < end_p)

@@ -230,11 +230,15 @@ class VADWrapper:
             if spent > self._MAX_PROCESSING_TIME_WARNING:
                 warnings.warn(f"Audio processing took {spent:.3f}s, which may indicate performance issues")
 
-    def process_audio_data(self, audio_data: Union[np.ndarray, List[float]]) -> None:
+    def process_audio_data(self, audio_data: Union[np.ndarray, List[float]], input_sample_rate: Optional[int] = None) -> None:
+        """The reference's call (vad_wrapper.py:547).  `input_sample_rate` is this package's opt-in to the GPU resampler:
+        8000 / 24000 / 48000 = `audio_data` is at that rate and is resampled to 16 kHz in chunks of one model frame on the
+        device (what the reference leaves as a placeholder under `auto_convert_sample_rate`, :619-624); None or 16000 =
+        the reference's behaviour, overlapped 16 kHz frames."""
         with self._lock:
             with self._processing_context():
                 try:
-                    self._process_audio_frames(self._validate_and_prepare_audio(audio_data))
+                    self._process_audio_frames(self._validate_and_prepare_audio(audio_data), input_sample_rate)
                 except ValidationError as exc:
                     self._state.record_error(exc)
                     raise AudioProcessingError(f"Audio validation failed: {exc}")
@@ -254,12 +258,26 @@ class VADWrapper:
         AudioUtils.validate_audio_data(audio)
         return AudioUtils.convert_to_mono(audio)
 
-    def _process_audio_frames(self, audio_data: np.ndarray) -> None:
+    def _process_audio_frames(self, audio_data: np.ndarray, input_sample_rate: Optional[int] = None) -> None:
         try:
             frame_size = self._config.buffer_size
             hop_size = int(frame_size * self._DEFAULT_FRAME_OVERLAP_RATIO)
             proc = self._processor
             batched = getattr(proc, "supports_batched", None)
+            if input_sample_rate not in (None, 16000):
+                if input_sample_rate not in (8000, 24000, 48000):
+                    raise AudioProcessingError("input_sample_rate must be 8000, 16000, 24000 or 48000")
+                if not (callable(batched) and batched() is True):
+                    raise AudioProcessingError("input_sample_rate needs the engine-backed 16 kHz model")
+                chunk = 512 * input_sample_rate // 16000       # one model frame of source samples, no overlap
+                results = proc.process_audio_batched(audio_data, chunk, chunk, src_rate=input_sample_rate)
+                try:
+                    for result in results:
+                        self._handle_callbacks(result)
+                        self._state.__dict__["total_frames_processed"] += 1
+                finally:
+                    results.close()
+                return
             if callable(batched) and batched() is True:  # `is True`: a test double answers with a Mock
                 # one GPU step per batch of frames.  The generator is closed HERE, deterministically: its `finally`
                 # puts the stream back to the frame a raising callback stopped at, and must not wait for the garbage

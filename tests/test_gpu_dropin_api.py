@@ -416,3 +416,53 @@ def test_callback_that_raises_mid_call_leaves_the_stream_where_the_reference_doe
     a.process_audio_data(rest)
     b.process_audio_data(rest)
     assert np.array_equal(a.processor.model.model_state.state, b.processor.model.model_state.state)
+
+
+@pytest.mark.parametrize("rate", [8000, 48000])
+def test_vadwrapper_input_sample_rate_opt_in_runs_the_gpu_resampler(ref_v5, ref_lib, rate):
+    """VADWrapper.process_audio_data(audio, input_sample_rate=rate): the wrapper's route to the GPU resampler (the reference
+    leaves `auto_convert_sample_rate` a placeholder, vad_wrapper.py:619-624).  Chunks of 512*rate/16000 source samples,
+    each resampled to one model frame on the device = AudioUtils.resample_audio per chunk, then the model: probabilities
+    within 1e-4 of the oracle on the scipy-resampled audio, events at the oracle's frames, WAV payloads = the host-
+    resampled, gated segment; the same stream through BatchedVADManager(source_rate=rate) agrees to 5e-5; calls carry the state across; a rate the engine does not know is an AudioProcessingError."""
+    from scipy import signal
+
+    from real_time_vad import BatchedVADManager, VADConfig
+    from real_time_vad.core.exceptions import AudioProcessingError
+    from vad_oracle import resample_chunks, sm_run_c
+    T, n_in = 60, 512 * rate // 16000
+    cand = synth_streams(12, 512 * T, seed=77)
+    cand_up = signal.resample(cand, n_in * T, axis=1).astype(np.float32)
+    cand_p, _, _ = ref_v5.run(resample_chunks(cand_up, rate), T, denoise=True)
+    n_events = [int(((sm_run_c(ref_lib, cand_p[s], 0.5, 0.35, 0.8, 0.95, 2, 3)[0] & 3) != 0).sum()) for s in range(12)]
+    x = cand_up[int(np.argmax(n_events))]                              # the candidate stream with the most start / end events
+    cfg = VADConfig(vad_start_probability=0.5, vad_end_probability=0.35, voice_start_frame_count=2,
+                    voice_end_frame_count=3, enable_denoising=True, buffer_size=512)
+    w, log = _spy_wrapper(cfg)
+    w.process_audio_data(x[:n_in * 25], input_sample_rate=rate)
+    w.process_audio_data(x[n_in * 25:], input_sample_rate=rate)
+    got = np.array(w.processor.voice_probabilities, np.float32)[-T:]
+    y16 = resample_chunks(x[None, :], rate)
+    want, _, _ = ref_v5.run(y16, T, denoise=True)
+    assert got.shape == (T,) and np.abs(got - want[0]).max() <= TOL
+    fl, _ = sm_run_c(ref_lib, want[0], 0.5, 0.35, 0.8, 0.95, 2, 3)
+    want_ev = sorted([(int(j) + 1, 1) for j in np.flatnonzero(fl & 1)] + [(int(j) + 1, 2) for j in np.flatnonzero(fl & 2)])
+    near = (np.abs(want[0] - 0.5) <= TOL).any() or (np.abs(want[0] - 0.35) <= TOL).any()
+    if not near:
+        assert sorted((f + 1, k) for f, k in log["events"]) == want_ev and len(want_ev) >= 2
+    # the same stream through the manager's source-rate path: same kernels, same bits
+    mgr = BatchedVADManager(max_streams=4, source_rate=rate)
+    sid = mgr.open_stream(VADConfig(vad_start_probability=0.5, vad_end_probability=0.35, voice_start_frame_count=2,
+                                    voice_end_frame_count=3, enable_denoising=True, sample_rate=rate))
+    mgr.push(sid, x)
+    mp = []
+    while len(mp) < T:
+        out = mgr.step()
+        assert sid in out.probabilities
+        mp += list(out.probabilities[sid])
+    # (the manager steps at most 8 frames at a time and runs its last frames through the fused one-frame kernel: same
+    # arithmetic builds, different kernel forms -- agreement well inside the bar, not bit for bit)
+    assert np.abs(np.asarray(mp, np.float32) - got).max() <= 5e-5
+    mgr.close()
+    with pytest.raises(AudioProcessingError):
+        w.process_audio_data(x[:n_in * 4], input_sample_rate=44100)

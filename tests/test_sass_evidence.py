@@ -48,7 +48,7 @@ def test_library_holds_sm_100a_code_only(sass):
 
 def test_fused_kernel_runs_on_tcgen05_with_bulk_copies_and_dependent_launch(sass):
     _, funcs = sass
-    k = _one(funcs, "v5tc_frontend_kernel", "ILb0ELb1ELb1E")     # <DBG = false, FUSED = true, H16 = true>: the default
+    k = _one(funcs, "v5tc_frontend_kernel", "ILb0ELb1ELb1ELb0E")     # <DBG = false, FUSED = true, H16 = true, PROF = false>: the default
     assert k.count("UTCHMMA") >= 32                              # every GEMM stage
     assert "LDTM" in k and "UBLKCP" in k and "UTCBAR" in k       # TMEM read-back, weight stream, tcgen05.commit
     assert "PREEXIT" in k and k.count("ACQBULK") >= 3            # launch_dependents; one wait per warp role

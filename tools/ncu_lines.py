@@ -18,7 +18,7 @@ ROOT = Path(__file__).resolve().parents[1]
 def main():
     rep, kname, mangled = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kname], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name", "regex:" + kname], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
     H = rows[hdr]
