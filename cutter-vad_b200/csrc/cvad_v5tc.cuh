@@ -838,14 +838,39 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
         // griddepcontrol.wait, to take its instruction and parameter-bank misses off the 1.1 us between the resolved
         // dependency and the tile's start: the CTAs that matter are scheduled only 0.9 us before the dependency resolves
         // and the rehearsal itself took longer than that; tools/dev/chain_timeline.py.)
+        // Streams in slot order with no per-stream frame counts (the device-pointer steps of a service that owns its slots):
+        // which of the tile's streams are live, their slots and the per-stream maxima's reset need nothing but kernel
+        // parameters -- the first tile's are set up AHEAD of griddepcontrol.wait (0.7 us of cold code and parameter-bank
+        // reads that sat between the resolved dependency and the tile's first barrier, tools/dev/chain_timeline.py).
+        const bool ident = FUSED && p.slots == nullptr && p.n_frames == nullptr;
+        int pre_slot = -1, pre_valid = 0;
+        bool pre_live = false;
+        auto stream_groups = [&](int slot, int valid) {
+            // stream group g = streams 8g .. 8g+7 (one epilogue thread's share): are its slots one aligned row of the state?
+            const int base = __shfl_sync(0xffffffffu, slot, lane & ~7);
+            const unsigned okm = __ballot_sync(0xffffffffu, valid && (base & 7) == 0 && slot == base + (lane & 7));
+            const int gbase = __shfl_sync(0xffffffffu, base, (lane & 3) * 8);
+            if (lane < 4) s_grp[lane] = ((okm >> (8 * lane)) & 0xffu) == 0xffu ? gbase : -1;
+        };
+        if (ident && (int)blockIdx.x < n_tiles) {
+            const int frame = (int)blockIdx.x / p.n_stiles, st = (int)blockIdx.x - frame * p.n_stiles;
+            pre_live = tile_live(p, frame, st, lane, &pre_slot, &pre_valid);
+            if (warp == 0) {
+                s_slot[lane] = pre_slot;
+                s_valid[lane] = pre_valid;
+                stream_groups(pre_slot, pre_valid);
+            }
+            if (H16 && warp >= 1 && warp <= 6) amax[(warp - 1) * kTile + lane] = 0u;
+        }
         if (FUSED) {
             griddep_wait();
             CVAD_CHAIN_NS(2);
         }
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int frame = tile / p.n_stiles, st = tile - frame * p.n_stiles;
-            int my_slot, my_valid;
-            const bool live = tile_live(p, frame, st, lane, &my_slot, &my_valid);
+            const bool pre = ident && tile == (int)blockIdx.x;          // set up above
+            int my_slot = pre_slot, my_valid = pre_valid;
+            const bool live = pre ? pre_live : tile_live(p, frame, st, lane, &my_slot, &my_valid);
             CVAD_CHAIN_NS(6);
             // chained steps arrive without a memset in front of them: the tile clears its streams' status words itself
             // (one tile per stream when max_frames == 1), ordered before the loader's atomicOr by the barrier below
@@ -860,14 +885,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             int a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, dn = 0;
             long long f0 = 0;
             if (warp == 0) {
-                s_slot[lane] = my_slot;
-                s_valid[lane] = my_valid;
-                if (FUSED) {
-                    // stream group g = streams 8g .. 8g+7 (one epilogue thread's share): are its slots one aligned row of the state?
-                    const int base = __shfl_sync(0xffffffffu, my_slot, lane & ~7);
-                    const unsigned okm = __ballot_sync(0xffffffffu, my_valid && (base & 7) == 0 && my_slot == base + (lane & 7));
-                    const int gbase = __shfl_sync(0xffffffffu, base, (lane & 3) * 8);
-                    if (lane < 4) s_grp[lane] = ((okm >> (8 * lane)) & 0xffu) == 0xffu ? gbase : -1;
+                if (!pre) {
+                    s_slot[lane] = my_slot;
+                    s_valid[lane] = my_valid;
+                    if (FUSED) stream_groups(my_slot, my_valid);
                 }
                 if (my_slot >= 0) dn = (int)p.denoise[my_slot];
                 if (!FUSED) s_dn[lane] = dn;
@@ -878,7 +899,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     f0 = p.frames_done[my_slot];
                 }
             }
-            if (H16 && warp >= 1 && warp <= 6) amax[(warp - 1) * kTile + lane] = 0u;
+            if (H16 && !pre && warp >= 1 && warp <= 6) amax[(warp - 1) * kTile + lane] = 0u;
             CVAD_CHAIN_NS(7);
             epi_bar();
             const bool dbg = DBG && tile == 0;
@@ -1609,6 +1630,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             // atomic's round trip (~0.4 us with 128 CTAs on one address) sits between the tile and the CTA's exit.
             // No fence: every event atomicAdd of this CTA returned its index to warp 0 before the barrier above, i.e.
             // it has been performed at L2, where the ticket and the exchange below are performed too.
+            // (Measured and dropped: taking the ticket inside the last tile, right behind the state machine, with the state
+            // stores moved behind it so that the round trip runs under them -- 4.149 M against 4.156 M audio-s/s: the tail
+            // of the tile grew by what the exit saved.)
             int *ticket = p.ev_ctr ? p.ev_ctr + 1 : p.step_ctr + 1;
             if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
                 if (p.ev_ctr) {

@@ -48,3 +48,17 @@ print(f"step period (tile end to tile end, last CTA): {per:.0f} ns; tile {np.mea
       f"previous step's tile end -> this step's tile start (last CTA): {np.mean(m[1:, 2, 3] - m[:-1, 2, 4]):.0f} ns; "
       f"of which exit -> next entry {np.mean(m[1:, 2, 0] - m[:-1, 2, 5]):.0f}, entry -> prologue {np.mean(m[:, 2, 1] - m[:, 2, 0]):.0f}, "
       f"prologue -> dep resolved {np.mean(m[:, 2, 2] - m[:, 2, 1]):.0f}, dep resolved -> tile start {np.mean(m[:, 2, 3] - m[:, 2, 2]):.0f}")
+
+# the tile's phase marks (clock64, CTA 0) of the LAST chained step: the same table tools/tc_phase_profile.py prints for a
+# host-buffer step, here with the audio prefetched into L2 by the early CTAs and the state left in L2 by the previous step
+prof = np.zeros(128, np.int64)
+eng._check(L.cvad_read_profile(eng._h, prof.ctypes.data))
+fe = prof[0:12] - prof[0]
+names = ["tile start", "loader done", "stft acc", "stft epi", "enc0 acc", "enc0 epi", "enc1 acc", "enc1 epi", "enc2 acc",
+         "enc2 epi", "enc3 acc", "enc3 epi"]
+print("chained step, CTA 0, cycles since tile start (delta):")
+for i, nm in enumerate(names):
+    print(f"  {nm:12s} {fe[i]:8d} {fe[i] - (fe[i - 1] if i else 0):8d}")
+print("  state loaded", prof[12] - prof[0], "| loader gated", prof[20] - prof[0], "amax pushed", prof[15] - prof[0], "| x ready", prof[43] - prof[0],
+      "first gate ready", prof[13] - prof[0], "i,f,g done", prof[21] - prof[0], "cell computed", prof[22] - prof[0],
+      "state stored + barrier", prof[23] - prof[0], "cell done", prof[14] - prof[0])
