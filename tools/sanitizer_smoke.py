@@ -20,6 +20,14 @@ big = np.zeros((70, 1536 * 2), np.float32)
 big[:, :1024] = x[:, :1024]
 eng.step(big, src_rates=rates, max_frames=2)
 eng.close()
+# the default build: FP16-split fused kernel (MN-major operands, direct state rows, gate-pipelined cell), identity slots and
+# a slot list with gaps (the gather path of the state), chained device-pointer steps left to tests/test_gpu_device_steps.py
+e16 = StreamEngine(max_streams=128, math="tc16")
+e16.step(x[:, :512])
+e16.step(x[:, 512:1024])
+e16.step(x[:37, :512], slots=np.arange(0, 74, 2, dtype=np.int32))
+e16.step(x)
+e16.close()
 e4 = StreamEngine("v4", max_streams=64, math="tc")
 e4.step(x[:40])
 e4.close()
