@@ -700,7 +700,8 @@ def run_ours(args):
                       "v5tc_frontend_kernel<FUSED,H16>" if h16 else
                       "v5tc_frontend_kernel<FUSED>" if fused else "v5tc_frontend_kernel") if (tc or math == "fft")
                      else f"{model}_frontend_kernel") + ("+resample_fft_kernel" if rate != 16000 else "")
-        variant = ("v5tc_frontend_kernel<0, 1, 1>" if h16 else "v5tc_frontend_kernel<0, 1>" if fused else
+        # (prefixes: the kernel's trailing template argument PROF is 0 in the build that runs unless a profile was asked for)
+        variant = ("v5tc_frontend_kernel<0, 1, 1" if h16 else "v5tc_frontend_kernel<0, 1, 0" if fused else
                    "v5tc_frontend_kernel<0, 0" if tc else "v5_frontend_kernel")
         traffic = ncu_traffic_bytes(variant) if (n == 4096 and F == 1 and model == "v5" and rate == 16000) else None
         fe_weight_bytes = ((622_592 + 524_288) if h16 else (933_888 + (786_432 if fused else 0))) if tc else 156032 * 4
