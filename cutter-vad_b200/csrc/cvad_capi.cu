@@ -5,7 +5,6 @@
 // pinned staging used by the host-buffer entry point.  There is no CPU fallback: if no
 // sm_100 device is present every compute entry point fails with CVAD_E_NOGPU.
 #include <algorithm>
-#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1747,18 +1746,6 @@ int cvad_step_collect(cvad_engine *e, int ticket) {
 }
 
 int cvad_step(cvad_engine *e, const cvad_step_args *a) {
-    static const bool trace = std::getenv("CVAD_FEEDER_TRACE") != nullptr;
-    if (trace && e) {
-        const auto t0 = std::chrono::steady_clock::now();
-        int ticket = 0;
-        int rc = cvad_step_submit(e, a, &ticket);
-        const auto t1 = std::chrono::steady_clock::now();
-        if (rc == CVAD_OK) rc = cvad_step_collect(e, ticket);
-        const auto t2 = std::chrono::steady_clock::now();
-        std::fprintf(stderr, "[cvad_step] n %d T %d: submit %.3f ms, collect %.3f ms\n", a ? a->n_streams : -1, a ? a->max_frames : -1,
-                     std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
-        return rc;
-    }
     int ticket = 0;
     int rc = cvad_step_submit(e, a, &ticket);
     if (rc) return rc;
