@@ -122,8 +122,15 @@ struct cvad_feeder {
     std::vector<uint8_t> flags, status;
     std::vector<cvad_event> events;
     std::vector<cvad_delivery> deliveries;
-    std::vector<float> frame_pool;                   // gated frames handed to voice_continue this step
-    std::vector<std::vector<float>> done_segments;   // segments finished this step
+    // segment assembly runs on the helper pool over contiguous ranges of the payload-carrying streams; each range keeps
+    // its own records and payload storage (the records point into them; merged in stream order, valid until the next step)
+    struct DeliverPart {
+        std::vector<cvad_delivery> deliv;
+        std::vector<float> pool;                     // gated frames handed to voice_continue this step
+        std::vector<std::vector<float>> segs;        // segments finished this step
+    };
+    std::vector<DeliverPart> dparts;
+    std::vector<int32_t> dwork;                      // indices k of the streams that carry payloads
     int64_t row = 0;
     int tmax = 0;
     int threads = 1;
@@ -298,88 +305,103 @@ int feeder_gather(cvad_feeder *f, bool allow_planes = false) {
 void feeder_deliver(cvad_feeder *f) {
     const int n = (int)f->ids.size(), T = f->tmax;
     f->deliveries.clear();
-    f->frame_pool.clear();
-    f->done_segments.clear();
     const unsigned char *stage = f->stage[f->cur];
     const bool mixed = f->src_rate == 0;
-    // pass 1: how many continue-frames will be pooled (so that frame_pool never reallocates under the records)
-    size_t pool = 0;
-    for (int k = 0; k < n; ++k) {
-        if (f->pay[f->ids[k]] == CVAD_PAYLOAD_FRAMES && f->slot[f->ids[k]].rate == 16000) pool += (size_t)f->counts[k] * (size_t)f->frame_len;
-    }
-    f->frame_pool.reserve(pool);
+    // streams without payloads only update the host mirror of is_voice_active (hot arrays: no Slot is touched)
+    f->dwork.clear();
     for (int k = 0; k < n; ++k) {
         const int s = f->ids[k];
-        const int c = f->counts[k];
-        const uint8_t *fl = f->flags.data() + (size_t)k * T;
-        const float *pr = f->probs.data() + (size_t)k * T;
-        const int payload = f->pay[s];
-        if (payload == CVAD_PAYLOAD_NONE) {
-            const uint8_t last = fl[c - 1];
+        if (f->pay[s] == CVAD_PAYLOAD_NONE) {
+            const uint8_t last = f->flags[(size_t)k * T + (size_t)(f->counts[k] - 1)];
             f->act[s] = !(last & CVAD_FLAG_ENDED) && (last & (CVAD_FLAG_STARTED | CVAD_FLAG_CONTINUING));
-            continue;
+        } else {
+            f->dwork.push_back(k);
         }
-        cvad_feeder::Slot &sl = f->slot[s];
-        bool active = f->act[s] != 0;
-
-        const bool raw_mode = payload >= CVAD_PAYLOAD_SEGMENTS && sl.rate != 16000;   // host resamples the payloads
-        const int64_t step_len = mixed ? sl.n_in : f->hop;
-        const int flen = mixed ? sl.n_in : f->frame_len;
-        for (int j = 0; j < c; ++j) {
-            const uint8_t b = fl[j];
-            const unsigned char *fp = feeder_frame_ptr(f, stage, n, k, j, step_len);
-            cvad_delivery d{};
-            d.slot = s; d.stream = k; d.step_frame = j; d.flags = b;
-            d.prob = pr[j];
-            if (raw_mode) {
-                // every frame is handed over; the host keeps pre-roll / segment for this stream itself
-                d.raw = fp; d.raw_len = flen;
-                const uint8_t last = b;
-                active = !(last & CVAD_FLAG_ENDED) && (last & (CVAD_FLAG_STARTED | CVAD_FLAG_CONTINUING));
-                f->deliveries.push_back(d);
-                continue;
-            }
-            const bool audio = payload >= CVAD_PAYLOAD_SEGMENTS;
-            bool emit = false;
-            if (!active) {
-                if ((double)pr[j] >= sl.start_p) {
-                    if (audio) feeder_gate_append(f, sl, fp, flen, sl.pre_roll);
-                    if (b & CVAD_FLAG_STARTED) {
-                        sl.segment.swap(sl.pre_roll);
+    }
+    const int m = (int)f->dwork.size();
+    const int parts = (f->pool && m >= 128) ? std::min(f->threads, m / 64) : 1;
+    if ((int)f->dparts.size() < parts) f->dparts.resize((size_t)parts);
+    for (auto &P : f->dparts) { P.deliv.clear(); P.pool.clear(); P.segs.clear(); }
+    auto run_part = [&](int part) {
+        cvad_feeder::DeliverPart &P = f->dparts[(size_t)part];
+        const int i0 = (int)((int64_t)m * part / parts), i1 = (int)((int64_t)m * (part + 1) / parts);
+        // how many continue-frames will be pooled (so that the pool never reallocates under the records)
+        size_t need = 0;
+        for (int i = i0; i < i1; ++i) {
+            const int k = f->dwork[(size_t)i], s = f->ids[k];
+            if (f->pay[s] == CVAD_PAYLOAD_FRAMES && f->slot[s].rate == 16000) need += (size_t)f->counts[k] * (size_t)f->frame_len;
+        }
+        P.pool.reserve(need);
+        for (int i = i0; i < i1; ++i) {
+            const int k = f->dwork[(size_t)i], s = f->ids[k];
+            const int c = f->counts[k];
+            const uint8_t *fl = f->flags.data() + (size_t)k * T;
+            const float *pr = f->probs.data() + (size_t)k * T;
+            const int payload = f->pay[s];
+            cvad_feeder::Slot &sl = f->slot[s];
+            bool active = f->act[s] != 0;
+            const bool raw_mode = payload >= CVAD_PAYLOAD_SEGMENTS && sl.rate != 16000;   // host resamples the payloads
+            const int64_t step_len = mixed ? sl.n_in : f->hop;
+            const int flen = mixed ? sl.n_in : f->frame_len;
+            for (int j = 0; j < c; ++j) {
+                const uint8_t b = fl[j];
+                const unsigned char *fp = feeder_frame_ptr(f, stage, n, k, j, step_len);
+                cvad_delivery d{};
+                d.slot = s; d.stream = k; d.step_frame = j; d.flags = b;
+                d.prob = pr[j];
+                if (raw_mode) {
+                    // every frame is handed over; the host keeps pre-roll / segment for this stream itself
+                    d.raw = fp; d.raw_len = flen;
+                    active = !(b & CVAD_FLAG_ENDED) && (b & (CVAD_FLAG_STARTED | CVAD_FLAG_CONTINUING));
+                    P.deliv.push_back(d);
+                    continue;
+                }
+                const bool audio = payload >= CVAD_PAYLOAD_SEGMENTS;
+                bool emit = false;
+                if (!active) {
+                    if ((double)pr[j] >= sl.start_p) {
+                        if (audio) feeder_gate_append(f, sl, fp, flen, sl.pre_roll);
+                        if (b & CVAD_FLAG_STARTED) {
+                            sl.segment.swap(sl.pre_roll);
+                            sl.pre_roll.clear();
+                            active = true;
+                            emit = true;
+                        }
+                    } else {
                         sl.pre_roll.clear();
-                        active = true;
-                        emit = true;
                     }
                 } else {
-                    sl.pre_roll.clear();
+                    size_t frame_at = 0;
+                    if (audio) {
+                        frame_at = sl.segment.size();
+                        feeder_gate_append(f, sl, fp, flen, sl.segment);
+                    }
+                    if (payload == CVAD_PAYLOAD_FRAMES) {
+                        const size_t o = P.pool.size();
+                        P.pool.insert(P.pool.end(), sl.segment.begin() + (ptrdiff_t)frame_at, sl.segment.end());
+                        d.frame = P.pool.data() + o;
+                        d.frame_len = flen;
+                        emit = true;
+                    }
+                    if (b & CVAD_FLAG_ENDED) {
+                        P.segs.emplace_back();
+                        P.segs.back().swap(sl.segment);
+                        sl.segment.clear();
+                        d.segment = P.segs.back().data();
+                        d.segment_len = (int64_t)P.segs.back().size();
+                        active = false;
+                        emit = true;
+                    }
                 }
-            } else {
-                size_t frame_at = 0;
-                if (audio) {
-                    frame_at = sl.segment.size();
-                    feeder_gate_append(f, sl, fp, flen, sl.segment);
-                }
-                if (payload == CVAD_PAYLOAD_FRAMES) {
-                    const size_t o = f->frame_pool.size();
-                    f->frame_pool.insert(f->frame_pool.end(), sl.segment.begin() + (ptrdiff_t)frame_at, sl.segment.end());
-                    d.frame = f->frame_pool.data() + o;
-                    d.frame_len = flen;
-                    emit = true;
-                }
-                if (b & CVAD_FLAG_ENDED) {
-                    f->done_segments.emplace_back();
-                    f->done_segments.back().swap(sl.segment);
-                    sl.segment.clear();
-                    d.segment = f->done_segments.back().data();
-                    d.segment_len = (int64_t)f->done_segments.back().size();
-                    active = false;
-                    emit = true;
-                }
+                if (emit) P.deliv.push_back(d);
             }
-            if (emit) f->deliveries.push_back(d);
+            f->act[s] = active ? 1 : 0;
         }
-        f->act[s] = active ? 1 : 0;
-    }
+    };
+    if (parts <= 1) run_part(0);
+    else f->pool->run(parts, run_part);
+    for (int part = 0; part < parts; ++part)
+        f->deliveries.insert(f->deliveries.end(), f->dparts[(size_t)part].deliv.begin(), f->dparts[(size_t)part].deliv.end());
 }
 
 }  // namespace
@@ -433,7 +455,7 @@ int cvad_feeder_create(cvad_engine *e, int max_streams, int pcm_format, int fram
     f->act.assign((size_t)max_streams, 0);
     f->skp.assign((size_t)max_streams, 0);
     const unsigned hw = std::thread::hardware_concurrency();
-    f->threads = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    f->threads = hw >= 16 ? 6 : (hw >= 8 ? 4 : (hw >= 4 ? 2 : 1));
     if (f->threads > 1) f->pool.reset(new FeederPool(f->threads - 1));
     f->mark.assign((size_t)max_streams, 0u);
     *out = f;

@@ -112,11 +112,10 @@ def test_mixed_rates_frame_by_each_streams_own_chunk():
     f.close()
 
 
-def _run_deliver(pcm_format, payload, denoise, frame_len, hop, seed):
+def _run_deliver(pcm_format, payload, denoise, frame_len, hop, seed, n=6, T=120):
     """Scripted probabilities -> oracle state machine flags -> feeder.deliver_only, against the oracle's VoiceBuffer."""
     from real_time_vad.engine import capi
     from vad_oracle import StateMachine, VoiceBuffer, denoise as gate
-    n, T = 6, 120
     rng = np.random.default_rng(seed)
     start_p, end_p = 0.5, 0.35
     probs = np.clip(0.5 + 0.5 * np.sin(np.arange(T)[None, :] / rng.uniform(3, 9, (n, 1)) + rng.uniform(0, 6, (n, 1)))
@@ -128,7 +127,7 @@ def _run_deliver(pcm_format, payload, denoise, frame_len, hop, seed):
     else:
         wire = np.clip(np.round(audio * 32767.0), -32768, 32767).astype(np.int16)
         as_float = wire.astype(np.float32) / np.float32(32767.0 if pcm_format == capi.PCM_S16_32767 else 32768.0)
-    f = _feeder(max_streams=8, pcm_format=pcm_format, frame_len=frame_len, hop=hop, capacity_frames=5)
+    f = _feeder(max_streams=max(8, n), pcm_format=pcm_format, frame_len=frame_len, hop=hop, capacity_frames=5)
     sms = [StateMachine(start_p, end_p, 0.8, 0.95, 2 + s % 2, 3 + s % 3) for s in range(n)]
     vbs = [VoiceBuffer(start_p) for _ in range(n)]
     for s in range(n):
@@ -189,6 +188,14 @@ def test_deliver_equals_the_reference_voice_buffering(pcm_format, payload, denoi
     n_start, n_seg, n_frames = _run_deliver(pcm_format, payload, denoise, frame_len, hop, seed=17 + payload)
     assert n_start >= 6 and n_seg >= 6
     assert (n_frames > 100) == (payload == 3)
+
+
+def test_deliver_on_the_helper_pool_keeps_stream_order_and_payloads():
+    """Enough payload-carrying streams (>= 128) for the segment assembly to run on the feeder's helper threads, each over its
+    own range of streams with its own record / payload storage: the merged records are still in stream-then-frame order
+    and every payload equals the oracle's."""
+    n_start, n_seg, n_frames = _run_deliver(1, 3, True, 480, 480, seed=5, n=300, T=24)
+    assert n_start >= 100 and n_seg >= 50 and n_frames > 1000
 
 
 def test_streams_without_payloads_only_keep_the_active_mirror():
