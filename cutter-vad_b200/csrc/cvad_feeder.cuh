@@ -10,6 +10,9 @@
 #pragma once
 
 #include <algorithm>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -221,6 +224,37 @@ inline const unsigned char *feeder_frame_ptr(const cvad_feeder *f, const unsigne
     return stage + ((size_t)k * (size_t)f->row + (size_t)j * (size_t)step_len) * f->es;
 }
 
+// Copy into the pinned block the next host-to-device copy reads: streaming (non-temporal) stores.  Measured on the B200
+// box: after the helper threads had gathered 8.4 MB with ordinary stores, the lines sat dirty in six cores' private
+// caches and the DMA engine read them at 12 GB/s (0.7 ms) instead of the 50 GB/s (0.17 ms) it gets from memory.
+inline void feeder_copy_nt(unsigned char *dst, const unsigned char *src, size_t bytes) {
+#if defined(__SSE2__)
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15u) == 0) {
+        size_t i = 0;
+        for (; i + 64 <= bytes; i += 64) {
+            const __m128i a = _mm_load_si128(reinterpret_cast<const __m128i *>(src + i));
+            const __m128i b = _mm_load_si128(reinterpret_cast<const __m128i *>(src + i + 16));
+            const __m128i c = _mm_load_si128(reinterpret_cast<const __m128i *>(src + i + 32));
+            const __m128i d = _mm_load_si128(reinterpret_cast<const __m128i *>(src + i + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), a);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 48), d);
+        }
+        for (; i + 16 <= bytes; i += 16)
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_load_si128(reinterpret_cast<const __m128i *>(src + i)));
+        if (i < bytes) std::memcpy(dst + i, src + i, bytes - i);
+        return;
+    }
+#endif
+    std::memcpy(dst, src, bytes);
+}
+inline void feeder_copy_fence() {
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+}
+
 int feeder_gather(cvad_feeder *f, bool allow_planes = false) {
     std::lock_guard<std::mutex> lk(f->mu);
     f->cur ^= 1;
@@ -279,16 +313,17 @@ int feeder_gather(cvad_feeder *f, bool allow_planes = false) {
             const int64_t need = mixed ? used : (int64_t)(f->counts[k] - 1) * f->hop + f->frame_len;
             if (f->planes) {
                 for (int j = 0; j < f->counts[k]; ++j)
-                    std::memcpy(const_cast<unsigned char *>(feeder_frame_ptr(f, stage, n, k, j, f->hop)),
-                                src + (size_t)j * (size_t)f->hop * f->es, (size_t)f->frame_len * f->es);
+                    feeder_copy_nt(const_cast<unsigned char *>(feeder_frame_ptr(f, stage, n, k, j, f->hop)),
+                                   src + (size_t)j * (size_t)f->hop * f->es, (size_t)f->frame_len * f->es);
             } else {
-                std::memcpy(stage + (size_t)k * (size_t)row * f->es, src, (size_t)need * f->es);
+                feeder_copy_nt(stage + (size_t)k * (size_t)row * f->es, src, (size_t)need * f->es);
             }
             const int64_t rem = have - used;
             if (rem > 0) std::memmove(src, src + (size_t)used * f->es, (size_t)rem * f->es);
             f->fill[s] = rem > 0 ? rem : 0;
             if (rem < 0) f->skp[s] = -rem;
         }
+        feeder_copy_fence();
     };
     const size_t bytes = (size_t)n * (size_t)row * f->es;
     const int nt = (f->threads > 1 && bytes > (1u << 20)) ? std::min(f->threads, n) : 1;
