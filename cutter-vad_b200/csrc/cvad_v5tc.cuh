@@ -913,7 +913,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
             //      kernel, before the resident state is fetched, so that both latencies overlap.
             float creg[8], hreg[8];
             const int u_own = 32 * q + lane, i_own = 8 * cg;   // this thread's hidden unit (TMEM lane) and 8 streams
-                const bool fast = p.vec_ok && flen == 512;
+                // vector loads whenever a frame is a whole number of 8-sample units (512, or the websocket service's 480:
+                // units past the frame's end are the zero padding of _prepare_audio_input, silero_model.py:449-474)
+                const bool fast = p.vec_ok && (flen & 7) == 0;
                 float v[4][8];
                 bool ok[4];
 #pragma unroll
@@ -925,7 +927,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) v5tc_frontend_kernel(const V5St
                     for (int e = 0; e < 8; ++e) v[u4][e] = 0.f;
                     if (ok[u4]) {
                         const long long b0 = (long long)(st * kTile + s) * p.stride + (long long)frame * p.hop + 8 * c8;
-                        if (fast && p.pcm == 0) {
+                        if (fast && 8 * c8 >= flen) {
+                            // zero padding
+                        } else if (fast && p.pcm == 0) {
                             const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.audio) + b0);
                             const float4 t0 = ldg_stream4(src), t1 = ldg_stream4(src + 1);
                             v[u4][0] = t0.x; v[u4][1] = t0.y; v[u4][2] = t0.z; v[u4][3] = t0.w;

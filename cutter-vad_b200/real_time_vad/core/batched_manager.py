@@ -26,6 +26,7 @@ assembles voice segments in C++, and Python only walks the frames a callback is 
 """
 from __future__ import annotations
 
+import ctypes as C
 import threading
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, NamedTuple, Optional, Sequence
@@ -284,7 +285,7 @@ class BatchedVADManager:
         """Run every complete buffered frame of every open stream in one GPU step."""
         with self._lock:
             try:
-                r = self._feeder.step()
+                r = self._feeder.step(borrow=True)
             except FeederError as exc:
                 self._raise(exc)
             import time
@@ -292,7 +293,7 @@ class BatchedVADManager:
             events = [StreamEvent(slot, "start" if kind == capi.FLAG_STARTED else "end", stream_frame, j)
                       for (k, slot, j, kind, stream_frame) in r.events]
             t1 = time.perf_counter()
-            self._deliver(r.deliveries)
+            self._deliver(r.records)
             t2 = time.perf_counter()
             out = StepOutput(events, r.slots.astype(np.int64), r.counts.astype(np.int64), r.probs, r.flags)
             out.phase_ms = r.phase_ms          # (framing, GPU step incl. copies, segment assembly) inside the native step
@@ -300,29 +301,33 @@ class BatchedVADManager:
             out.host_ms = (r.call_ms[0], r.call_ms[1], 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (time.perf_counter() - t2))
             return out
 
-    def _deliver(self, deliveries) -> None:
+    def _deliver(self, records) -> None:
         """Fire the callbacks the feeder found due, in stream-then-frame order: start, then end with the WAV
         bytes, then continue with the float32 frame bytes (vad_wrapper.py:498-519).  16 kHz streams arrive with
         their payloads assembled; for resampled streams (`raw` records, one per frame) the pre-roll / segment
-        bookkeeping of silero_model.py:839-869,:925-949 runs here on host-resampled frames."""
-        for d in deliveries:
-            st = self._streams.get(d.slot)
+        bookkeeping of silero_model.py:839-869,:925-949 runs here on host-resampled frames.  `records` are the native
+        delivery records as tuples (engine/feeder.py: FeederStep.records); payload bytes are copied out only for the
+        callbacks that exist."""
+        sa, streams = C.string_at, self._streams
+        STARTED, ENDED = capi.FLAG_STARTED, capi.FLAG_ENDED
+        for (slot, _row, _j, fl, frame_p, seg_p, seg_len, frame_len, prob, raw_p, raw_len) in records:
+            st = streams.get(slot)
             if st is None:
                 continue
-            if d.raw is None:
-                if d.flags & capi.FLAG_STARTED:
+            if not raw_p:
+                if fl & STARTED:
                     self._call(st.on_start, "voice_start")
-                if d.flags & capi.FLAG_ENDED and st.on_end is not None and d.segment is not None and d.segment.size:
-                    wav = st.writer.write_wav_data(d.segment)
+                if fl & ENDED and st.on_end is not None and seg_p and seg_len > 0:
+                    wav = st.writer.write_wav_data(np.frombuffer(sa(seg_p, seg_len * 4), np.float32))
                     if wav:
                         self._call(st.on_end, "voice_end", wav)
-                if d.frame is not None:
-                    self._call(st.on_continue, "voice_continue", d.frame.tobytes())
+                if frame_p and st.on_continue is not None:
+                    self._call(st.on_continue, "voice_continue", sa(frame_p, frame_len * 4))
                 continue
-            fl = d.flags
-            frame = self._gate(st, d.raw) if (st.active or d.prob >= st.config.vad_start_probability) else None
+            d_raw = np.frombuffer(sa(raw_p, raw_len * self._dtype().itemsize), self._dtype)
+            frame = self._gate(st, d_raw) if (st.active or prob >= st.config.vad_start_probability) else None
             if not st.active:
-                if d.prob >= st.config.vad_start_probability:
+                if prob >= st.config.vad_start_probability:
                     st.pre_roll.append(frame)
                     if fl & capi.FLAG_STARTED:
                         st.segment = st.pre_roll

@@ -37,11 +37,17 @@ class Delivery(NamedTuple):
 class FeederStep:
     """One step's results; arrays are copies, safe to keep."""
 
-    __slots__ = ("slots", "counts", "probs", "flags", "events", "deliveries", "frames", "raw", "raw_stride", "phase_ms", "call_ms")
+    __slots__ = ("slots", "counts", "probs", "flags", "events", "deliveries", "records", "frames", "raw", "raw_stride", "phase_ms",
+                 "call_ms")
 
-    def __init__(self, slots, counts, probs, flags, events, deliveries, frames, raw=None, raw_stride=0, phase_ms=(0.0, 0.0, 0.0)):
+    def __init__(self, slots, counts, probs, flags, events, deliveries, frames, raw=None, raw_stride=0, phase_ms=(0.0, 0.0, 0.0),
+                 records=None):
         self.slots, self.counts, self.probs, self.flags = slots, counts, probs, flags
         self.events, self.deliveries, self.frames = events, deliveries, frames
+        # `step(borrow=True)`: the native delivery records as plain tuples (slot, stream, step_frame, flags, frame_ptr,
+        # segment_ptr, segment_len, frame_len, prob, raw_ptr, raw_len) whose pointers are valid until the feeder's next
+        # step -- for a consumer that walks them at once (BatchedVADManager); `deliveries` is then None
+        self.records = records
         self.raw, self.raw_stride = raw, raw_stride
         self.phase_ms = phase_ms            # (gather, cvad_step, deliver) wall milliseconds inside the native step
         self.call_ms = (0.0, 0.0)
@@ -133,7 +139,7 @@ class StreamFeeder:
         self._check(self._L.cvad_feeder_push_many(self._h, int(ids.size), ids.ctypes.data, block.ctypes.data,
                                                   block.strides[0] // block.itemsize, block.shape[1]))
 
-    def _unpack(self, want_raw: bool = False) -> FeederStep:
+    def _unpack(self, want_raw: bool = False, borrow: bool = False) -> FeederStep:
         r = self._res
         n, T = int(r.n_streams), int(r.max_frames)
         slots = _view(r.slots, np.int32, n).copy()
@@ -142,12 +148,15 @@ class StreamFeeder:
         flags = _view(r.flags, np.uint8, n * T).reshape(n, T).copy()
         ev = _view(r.events, _EVENT_DT, int(r.n_events))
         events = ev.tolist()                      # [(stream, slot, frame, kind, stream_frame)] as Python ints
-        deliveries: List[Delivery] = []
         # records as plain tuples (one C loop), payloads as one memcpy each: at 10,000 streams field access on numpy void
         # scalars and view -> copy pairs were most of this function
+        records = _view(r.deliveries, _DELIV_DT, int(r.n_deliveries)).tolist()
+        if borrow:
+            return FeederStep(slots, counts, probs, flags, events, None, int(r.n_frames_total), None, int(r.raw_stride),
+                              (float(r.gather_ms), float(r.gpu_ms), float(r.deliver_ms)), records)
+        deliveries: List[Delivery] = []
         sa, fb, isz = C.string_at, np.frombuffer, self.dtype().itemsize
-        for (slot, stream, step_frame, fl, frame_p, seg_p, seg_len, frame_len, prob, raw_p, raw_len) in \
-                _view(r.deliveries, _DELIV_DT, int(r.n_deliveries)).tolist():
+        for (slot, stream, step_frame, fl, frame_p, seg_p, seg_len, frame_len, prob, raw_p, raw_len) in records:
             frame = fb(sa(frame_p, frame_len * 4), np.float32) if frame_p else None
             seg = fb(sa(seg_p, seg_len * 4), np.float32) if seg_p and seg_len > 0 else (np.zeros(0, np.float32) if seg_p else None)
             raw = fb(sa(raw_p, raw_len * isz), self.dtype) if raw_p else None
@@ -160,12 +169,12 @@ class StreamFeeder:
         return FeederStep(slots, counts, probs, flags, events, deliveries, int(r.n_frames_total), raw_block,
                           int(r.raw_stride), (float(r.gather_ms), float(r.gpu_ms), float(r.deliver_ms)))
 
-    def step(self) -> FeederStep:
+    def step(self, borrow: bool = False) -> FeederStep:
         import time
         t0 = time.perf_counter()
         self._check(self._L.cvad_feeder_step(self._h, C.byref(self._res)))
         t1 = time.perf_counter()
-        out = self._unpack()
+        out = self._unpack(borrow=borrow)
         out.call_ms = (1e3 * (t1 - t0), 1e3 * (time.perf_counter() - t1))     # (native call, unpacking into numpy / tuples)
         return out
 
