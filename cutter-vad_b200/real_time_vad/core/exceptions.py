@@ -8,50 +8,63 @@ return codes become `EngineError` in `engine/stream_engine.py` and are mapped on
 """
 from __future__ import annotations
 
-from typing import Optional
+from typing import Any, Optional
 
 
 class VADError(Exception):
     """Root of every error raised by this package."""
 
     def __init__(self, message: str, error_code: Optional[str] = None) -> None:
-        super().__init__(message)
-        self.message = message
-        self.error_code = error_code
+        Exception.__init__(self, message)
+        self.message, self.error_code = message, error_code
 
     def __str__(self) -> str:
-        return f"[{self.error_code}] {self.message}" if self.error_code else self.message
+        code = self.error_code
+        return self.message if not code else "[%s] %s" % (code, self.message)
 
 
-class ModelNotFoundError(VADError):
+class _Coded(VADError):
+    """A VADError with a fixed code; `_set` stores the text and the attributes the reference's classes expose."""
+
+    CODE = ""
+
+    def _set(self, text: str, **attributes: Any) -> None:
+        VADError.__init__(self, text, self.CODE)
+        self.__dict__.update(attributes)
+
+
+class ModelNotFoundError(_Coded):
+    CODE = "MODEL_NOT_FOUND"
+
     def __init__(self, model_path: str, message: Optional[str] = None) -> None:
-        super().__init__(message or f"Silero model not found at path: {model_path}", "MODEL_NOT_FOUND")
-        self.model_path = model_path
+        self._set(message or "Silero model not found at path: " + str(model_path), model_path=model_path)
 
 
-class ConfigurationError(VADError):
+class ConfigurationError(_Coded):
+    CODE = "CONFIGURATION_ERROR"
+
     def __init__(self, parameter: str, value: str, message: Optional[str] = None) -> None:
-        super().__init__(message or f"Invalid configuration for parameter '{parameter}': {value}",
-                         "CONFIGURATION_ERROR")
-        self.parameter = parameter
-        self.value = value
+        self._set(message or "Invalid configuration for parameter '%s': %s" % (parameter, value),
+                  parameter=parameter, value=value)
 
 
-class AudioProcessingError(VADError):
+class AudioProcessingError(_Coded):
+    CODE = "AUDIO_PROCESSING_ERROR"
+
     def __init__(self, message: str, audio_data_info: Optional[str] = None) -> None:
-        super().__init__(message, "AUDIO_PROCESSING_ERROR")
-        self.audio_data_info = audio_data_info
+        self._set(message, audio_data_info=audio_data_info)
 
 
-class ModelInitializationError(VADError):
+class ModelInitializationError(_Coded):
+    CODE = "MODEL_INITIALIZATION_ERROR"
+
     def __init__(self, model_version: str, message: Optional[str] = None) -> None:
-        super().__init__(message or f"Failed to initialize Silero model version: {model_version}",
-                         "MODEL_INITIALIZATION_ERROR")
-        self.model_version = model_version
+        self._set(message or "Failed to initialize Silero model version: " + str(model_version), model_version=model_version)
 
 
-class CallbackError(VADError):
+class CallbackError(_Coded):
+    CODE = "CALLBACK_ERROR"
+
     def __init__(self, callback_name: str, original_error: Exception) -> None:
-        super().__init__(f"Error in callback '{callback_name}': {original_error}", "CALLBACK_ERROR")
-        self.callback_name = callback_name
-        self.original_error = original_error
+        self._set("Error in callback '%s': %s" % (callback_name, original_error),
+                  callback_name=callback_name, original_error=original_error)
