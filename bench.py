@@ -20,6 +20,7 @@ One JSON line on stdout (rank 0).  Besides the contract's keys (DESIGN.md "Measu
                                        65,536-stream configuration is 8 of these), device-resident and e2e (int16 wire)
                              configs4  10,000 live streams through BatchedVADManager, 30 ms int16 messages with jitter,
                                        p50 / p99 of one tick (N = 1 only)
+                             configs0  one stream, 60 s of audio in one VADWrapper.process_audio_data call (N = 1 only)
 """
 from __future__ import annotations
 
@@ -467,6 +468,32 @@ def pinned_copy_rate(torch, wl):
     return 10 * wl.step_bytes_f32 / (h0.elapsed_time(h1) * 1e-3) / 1e9
 
 
+def single_stream_call(seconds=60, repeats=5):
+    """BASELINE.json configs[0] on the engine: ONE 16 kHz stream, `seconds` of synthetic audio through
+    VADWrapper.process_audio_data (512-sample frames, hop 256 as the reference frames them, vad_wrapper.py:626-629), callbacks
+    attached.  The recurrent part is strictly sequential (one stream): this is the latency floor of the drop-in call, not a
+    throughput figure."""
+    from real_time_vad import VADConfig, VADWrapper
+    audio = synth_audio(1, 16000 * seconds, seed=3)[0]
+    w = VADWrapper(VADConfig())
+    n_ev = [0]
+    w.set_callbacks(voice_start_callback=lambda: n_ev.__setitem__(0, n_ev[0] + 1),
+                    voice_end_callback=lambda b: n_ev.__setitem__(0, n_ev[0] + 1))
+    w.process_audio_data(audio[:16000])                       # warm-up (engine creation, first launches)
+    ms = []
+    for _ in range(repeats):
+        w.reset()
+        t0 = time.perf_counter()
+        w.process_audio_data(audio)
+        ms.append(1e3 * (time.perf_counter() - t0))
+    frames = (len(audio) - 512) // 256 + 1
+    w.cleanup()
+    med = float(np.median(ms))
+    return {"workload": f"one 16 kHz stream, {seconds} s of audio in one VADWrapper.process_audio_data call (BASELINE.json configs[0])",
+            "frames": frames, "call_ms_p50": med, "call_ms_min": float(min(ms)), "value": seconds / (med * 1e-3), "unit": "audio-s/s",
+            "us_per_frame": 1e3 * med / frames, "events": n_ev[0] // repeats}
+
+
 def service_tick(n_streams=10000, ticks=120):
     """BASELINE.json configs[4]: `n_streams` live clients through BatchedVADManager -- 480-sample int16 messages (30 ms) with
     arrival jitter, the websocket server's thresholds, 10 % of the streams with start / end callbacks.  Timed: the
@@ -661,12 +688,16 @@ def run_ours(args):
         del w2
         torch.cuda.empty_cache()
 
-    # ================= configs[4]: the manager's tick at 10,000 live streams -- N = 1 only
+    # ================= configs[4]: the manager's tick at 10,000 live streams; configs[0]: one stream, one call -- N = 1 only
     if run_extras and world == 1:
         try:
             extras["configs4"] = service_tick()
         except Exception as exc:                       # the service leg must not take the headline line down with it
             extras["configs4"] = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            extras["configs0"] = single_stream_call()
+        except Exception as exc:
+            extras["configs0"] = {"error": f"{type(exc).__name__}: {exc}"}
     sampler.stop()
     clocks = sampler.summary(c_lo, max(c_hi, c_lo + 1))
     clocks["whole_run"] = sampler.summary()
