@@ -20,6 +20,10 @@
 // so time columns are batched into N (N = 96 for the STFT and encoder.0) and the recurrent kernel
 // concatenates the three activation parts along N.
 //
+// The default build (FUSED, H16: one-frame steps, FP16 two-way split with per-stream scaling, three products per MAC) keeps
+// the frame loader's operand K-major and writes every operand an EPILOGUE produces MN-major SWIZZLE_64B, so that a thread's
+// one channel x eight streams is one 16-byte store (store_row8_mn); DESIGN.md section 3a.
+//
 // Warp roles (576 threads): warps 0-15 = loader + epilogue (TMEM -> registers -> activation -> next B operand;
 // warp w reads TMEM lanes 32 (w % 4).. and column group w / 4), warp 16 = weight producer (one lane),
 // warp 17 = MMA issuer (one elected lane).  Layers of one tile are
