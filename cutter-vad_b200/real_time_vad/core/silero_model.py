@@ -447,23 +447,32 @@ class VADProcessor(BaseModel):
         end_p = cfg.vad_end_probability
         gate = cfg.enable_denoising
 
+        want_cfg = (start_p, end_p, cfg.voice_start_frame_count, cfg.voice_end_frame_count, bool(gate))
+
         def run(first: int, count: int, h_in, c_in, sm_in):
-            """frames [first, first + count) from the given state -> (step result, h, c, sm)"""
+            """frames [first, first + count) from the given state -> (step result, h, c, sm).  The session's slot keeps
+            its thresholds and its state between calls: both are uploaded only when they differ from what the device
+            holds (`_dev_cfg`, `_dev_state` on the session; the compat session.run, which uses the same slot without the
+            gate and with its caller's state, invalidates them)."""
             with pooled.lock:
                 eng = pooled.engine
-                eng.configure([slot], vad_start_probability=start_p, vad_end_probability=end_p,
-                              voice_start_frame_count=cfg.voice_start_frame_count,
-                              voice_end_frame_count=cfg.voice_end_frame_count, enable_denoising=gate)
-                eng.set_state(slot, h_in, c_in, sm_in)
-                try:
-                    lo = first * hop_size
-                    r = eng.step(audio[None, lo:lo + (count - 1) * hop_size + frame_size], slots=[slot], n_frames=[count],
-                                 max_frames=count, frame_len=frame_size, hop=hop_size, **rate_kw)
-                    if r.status[0]:
-                        raise AudioProcessingError("Audio data contains infinite or NaN values")
-                    h, c, sm_out, _ = eng.get_state(slot)
-                finally:
-                    eng.configure([slot], enable_denoising=False)  # the compat session.run must not gate
+                if getattr(sess, "_dev_cfg", None) != want_cfg:
+                    eng.configure([slot], vad_start_probability=start_p, vad_end_probability=end_p,
+                                  voice_start_frame_count=cfg.voice_start_frame_count,
+                                  voice_end_frame_count=cfg.voice_end_frame_count, enable_denoising=gate)
+                    sess._dev_cfg = want_cfg
+                held = getattr(sess, "_dev_state", None)
+                if not (held is not None and np.array_equal(held[0], h_in) and np.array_equal(held[1], c_in)
+                        and np.array_equal(held[2][:3], sm_in[:3])):
+                    eng.set_state(slot, h_in, c_in, sm_in)
+                sess._dev_state = None
+                lo = first * hop_size
+                r = eng.step(audio[None, lo:lo + (count - 1) * hop_size + frame_size], slots=[slot], n_frames=[count],
+                             max_frames=count, frame_len=frame_size, hop=hop_size, **rate_kw)
+                if r.status[0]:
+                    raise AudioProcessingError("Audio data contains infinite or NaN values")
+                h, c, sm_out, _ = eng.get_state(slot)
+                sess._dev_state = (h.copy(), c.copy(), np.array(sm_out, np.int32))
             return r, h, c, sm_out
 
         def adopt(h, c, sm_out, segment):

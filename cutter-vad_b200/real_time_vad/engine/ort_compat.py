@@ -152,6 +152,13 @@ class InferenceSession:
             h_in, c_in = h_in.reshape(128), c_in.reshape(128)      # engine rows: layer-major [2][64]
         eng = pooled.engine
         with pooled.lock:
+            if pooled is self._pooled:
+                # the wrapper's fast path (core/silero_model.py: process_audio_batched) leaves its thresholds, gate and state
+                # on this slot; this call runs without the gate and from its caller's state
+                if getattr(self, "_dev_cfg", None) is not None:
+                    eng.configure([slot], enable_denoising=False)
+                    self._dev_cfg = None
+                self._dev_state = None
             eng.set_state(slot, h_in, c_in, np.zeros(4, np.int32))
             frame_len = min(x.shape[1], 512)
             r = eng.step(x, slots=[slot], max_frames=1, frame_len=frame_len, hop=max(frame_len, 1))

@@ -466,3 +466,46 @@ def test_vadwrapper_input_sample_rate_opt_in_runs_the_gpu_resampler(ref_v5, ref_
     mgr.close()
     with pytest.raises(AudioProcessingError):
         w.process_audio_data(x[:n_in * 4], input_sample_rate=44100)
+
+
+def test_wrapper_slot_cache_follows_reset_and_config_changes():
+    """The wrapper's fast path keeps thresholds and LSTM state on its engine slot between calls and uploads them only
+    when the host's copies differ (core/silero_model.py: process_audio_batched.run).  A reset, a state assigned by hand
+    and a new configuration must each reach the device: every run below equals a fresh wrapper given the same history."""
+    from real_time_vad import VADConfig
+    audio = synth_streams(1, 512 * 40, seed=91)[0]
+    cfg_a = VADConfig(vad_start_probability=0.5, vad_end_probability=0.35, voice_start_frame_count=2, voice_end_frame_count=3)
+    cfg_b = VADConfig(vad_start_probability=0.8, vad_end_probability=0.6, voice_start_frame_count=4, voice_end_frame_count=2,
+                      enable_denoising=False)
+
+    def run(w, log, lo, hi):
+        n0 = len(log["events"])
+        for i in range(lo, hi, 2048):                                  # several calls: the cached path
+            w.process_audio_data(audio[i:min(i + 2048, hi)])
+        return list(w.processor.voice_probabilities), log["events"][n0:]
+
+    w, log = _spy_wrapper(cfg_a)
+    first = run(w, log, 0, 512 * 20)
+    w.reset()
+    again = run(w, log, 0, 512 * 20)
+    assert np.array_equal(first[0], again[0])                          # reset reached the slot: same bits from scratch
+    assert [k for _, k in first[1]] == [k for _, k in again[1]]
+    cont = run(w, log, 512 * 20, 512 * 40)                             # carries on from the cached state ...
+    ref, rlog = _spy_wrapper(cfg_a)
+    run(ref, rlog, 0, 512 * 20)
+    want = run(ref, rlog, 512 * 20, 512 * 40)
+    assert np.array_equal(cont[0], want[0])                            # ... like a wrapper that was never reset
+    w.update_config(cfg_b)                                             # new thresholds, gate off: re-configured slot
+    got_b = run(w, log, 0, 512 * 20)
+    fresh, flog = _spy_wrapper(cfg_b)
+    want_b = run(fresh, flog, 0, 512 * 20)
+    assert np.array_equal(got_b[0], want_b[0]) and [k for _, k in got_b[1]] == [k for _, k in want_b[1]]
+    # a state assigned by hand (what a caller of the reference may do) is uploaded before the next call
+    ms = w.processor.model.model_state
+    ms.state = np.zeros_like(ms.state)
+    w.processor.is_voice_active = False
+    w.processor.voice_start_frame_count = 0
+    w.processor.voice_end_frame_count = 0
+    w.processor.voice_probabilities.clear()
+    manual = run(w, log, 0, 512 * 20)
+    assert np.array_equal(manual[0], want_b[0])
