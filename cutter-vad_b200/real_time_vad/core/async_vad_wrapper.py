@@ -96,8 +96,13 @@ class AsyncVADWrapper:
         await self._offload(self.vad_wrapper.set_thresholds, vad_start_probability, vad_end_probability,
                             voice_start_ratio, voice_end_ratio, voice_start_frame_count, voice_end_frame_count)
 
-    async def process_audio_data_async(self, audio_data: Union[np.ndarray, List[float]]) -> None:
-        await self._offload(self.vad_wrapper.process_audio_data, audio_data)
+    async def process_audio_data_async(self, audio_data: Union[np.ndarray, List[float]],
+                                       input_sample_rate: Optional[int] = None) -> None:
+        # `input_sample_rate`: VADWrapper's opt-in to the GPU resampler, forwarded only when given
+        if input_sample_rate is None:
+            await self._offload(self.vad_wrapper.process_audio_data, audio_data)
+        else:
+            await self._offload(self.vad_wrapper.process_audio_data, audio_data, input_sample_rate)
 
     async def process_audio_data_with_buffer_async(self, audio_buffer: np.ndarray, count: int) -> None:
         await self._offload(self.vad_wrapper.process_audio_data_with_buffer, audio_buffer, count)
@@ -127,8 +132,11 @@ class AsyncVADWrapper:
         self.vad_wrapper.set_thresholds(vad_start_probability, vad_end_probability, voice_start_ratio,
                                         voice_end_ratio, voice_start_frame_count, voice_end_frame_count)
 
-    def process_audio_data(self, audio_data: Union[np.ndarray, List[float]]) -> None:
-        self.vad_wrapper.process_audio_data(audio_data)
+    def process_audio_data(self, audio_data: Union[np.ndarray, List[float]], input_sample_rate: Optional[int] = None) -> None:
+        if input_sample_rate is None:
+            self.vad_wrapper.process_audio_data(audio_data)
+        else:
+            self.vad_wrapper.process_audio_data(audio_data, input_sample_rate)
 
     def reset(self) -> None:
         self.vad_wrapper.reset()
